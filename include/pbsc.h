@@ -1,0 +1,183 @@
+/*
+ * pbsc.h — C ABI of the B200-native `stride pbcorrect` hot path (libpbsc.so).
+ *
+ * The reference (ccuchengwei/LongReadSelfCorrect) has no plugin/FFI interface for this
+ * path: its boundary is the template policy pair Processor/PostProcessor of
+ * Concurrency/SequenceProcessFramework.h:359-386 around PacBioSelfCorrectionProcess::process
+ * (PacBio/PacBioSelfCorrectionProcess.cpp:23-54).  Each entry point below names the
+ * reference interface it replaces.  Conventions: plain pointers and sizes only, int return
+ * code (0 = ok, negative = error, text via pbsc_last_error()), no exceptions cross the
+ * boundary, the caller owns every host buffer, the library owns device memory behind
+ * opaque handles.  There is NO CPU fallback: every compute entry point fails with
+ * PBSC_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef PBSC_H
+#define PBSC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBSC_OK 0
+#define PBSC_ERR_ARG (-1)
+#define PBSC_ERR_IO (-2)
+#define PBSC_ERR_FORMAT (-3)
+#define PBSC_ERR_CUDA (-4)
+#define PBSC_ERR_LIMIT (-5)
+#define PBSC_ERR_INTERNAL (-6)
+
+#define PBSC_BWT 0  /* PREFIX.bwt  : BWT of the reads            (BWTIndexSet::pBWT)  */
+#define PBSC_RBWT 1 /* PREFIX.rbwt : BWT of the reversed reads   (BWTIndexSet::pRBWT) */
+
+/* Walk outcome codes of LongReadSelfCorrectByOverlap::extendOverlap
+ * (PacBio/LongReadCorrectByOverlap.cpp:155-211). */
+#define PBSC_WALK_OK 1
+#define PBSC_WALK_HIGH_ERROR (-1)
+#define PBSC_WALK_EXCEED_DEPTH (-2)
+#define PBSC_WALK_EXCEED_LEAVES (-3)
+#define PBSC_WALK_NO_PATH (-4)
+
+typedef struct pbsc_index pbsc_index; /* both rank tables + prefix table, resident on one GPU */
+
+/* Option block of `stride pbcorrect` (StriDe/PacBioSelfCorrection.cpp:71-101) plus the
+ * values PacBioSelfCorrectionMain derives from it (:195-231).  Fill with
+ * pbsc_params_default(), set the option fields, then call pbsc_params_derive(). */
+typedef struct pbsc_params
+{
+    /* command-line options */
+    int32_t pb_coverage;  /* -c, default 90  */
+    double error_rate;    /* -e, default 0.15 */
+    int32_t start_kmer;   /* -k, default 19 (sets `adjust`) */
+    int32_t next_target;  /* -n, default 1   */
+    int32_t max_leaves;   /* -l, default 32  */
+    int32_t idmer_len;    /* -i, default 9   */
+    int32_t min_kmer;     /* -s, default 13  */
+    int32_t genome;       /* -g, 5/10/100, default 10 */
+    int32_t mode;         /* -m, default 1 (sets `manual`) */
+    int32_t manual;       /* -m given */
+    int32_t adjust;       /* -k/-u/-r given */
+    int32_t split;        /* --split */
+    int32_t no_dp;        /* --nodp  */
+    int32_t offset[3];    /* offset[1] = -u, offset[2] = -r */
+    /* derived by pbsc_params_derive() */
+    int32_t pool[8];      /* ascending k-mer sizes, KmerFeature::Log() keys */
+    int32_t n_pool;
+    int32_t scan_kmer;    /* 19 */
+    int32_t kmer_up_bound;/* 50 */
+    int32_t radius;       /* 100 */
+    float hh_ratio;       /* 0.6f */
+    float threshold[3][52]; /* KmerThreshold table[mode][k] (PacBio/KmerThreshold.cpp:43-79) */
+    double freqs_of_kmer[101]; /* pow(1-e,i)*cov, i>=min_kmer (LongReadCorrectByOverlap.cpp:68-70) */
+} pbsc_params;
+
+/* One seed of a read: SeedFeature (PacBio/SeedFeature.h:22-45) after
+ * LongReadProbe::searchSeedsWithHybridKmers (PacBio/LongReadProbe.cpp:34-117). */
+typedef struct pbsc_seed
+{
+    int32_t start;            /* seedStartPos */
+    int32_t len;              /* seedLen */
+    int32_t max_fixed_freq;   /* maxFixedMerFreq */
+    int32_t is_repeat;        /* isRepeat */
+    int32_t start_best_k;     /* startBestKmerSize */
+    int32_t end_best_k;       /* endBestKmerSize */
+    int32_t hitchhiked;       /* isHitchhiked (such seeds are reported only by pbsc_seed_batch with keep_outcast) */
+    int32_t static_k;         /* static k-mer size the seed was grown from */
+} pbsc_seed;
+
+/* Per-read counters of PacBioSelfCorrectionResult (PacBio/PacBioSelfCorrectionProcess.h:59-95). */
+typedef struct pbsc_read_stats
+{
+    int64_t total_reads_len, corrected_len, total_seed_num, total_walk_num, high_error_num,
+        exceed_depth_num, exceed_leave_num, fm_num, dp_num, seed_dis;
+    int32_t merge;      /* result.merge: 1 -> correct.fa, 0 -> discard.fa */
+    int32_t n_pieces;   /* >1 only with --split */
+} pbsc_read_stats;
+
+const char* pbsc_last_error(void);
+int pbsc_device_count(void);
+
+/* ---- parameters: PacBioSelfCorrectionMain, StriDe/PacBioSelfCorrection.cpp:195-231 ---- */
+void pbsc_params_default(pbsc_params* p);
+int pbsc_params_derive(pbsc_params* p);
+/* text of DIR/threshold-table (KmerThreshold::~KmerThreshold/write, PacBio/KmerThreshold.cpp:31-41,65-72);
+ * returns the length written (excluding NUL) or a negative error */
+int pbsc_threshold_table_text(const pbsc_params* p, char* buf, size_t cap);
+
+/* ---- index: replaces RLBWT (SuffixTools/RLBWT.{h,cpp}), BWTReaderBinary::read
+ *      (SuffixTools/BWTReaderBinary.cpp:27-85) and BWTIndexSet for this path ---- */
+/* run bytes as stored on disk after the 30-byte header: high 3 bits symbol rank ($ACGT), low 5 bits run length */
+int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt_n_symbols, uint64_t bwt_n_strings,
+                      const uint8_t* rbwt_runs, uint64_t rbwt_n_runs, uint64_t rbwt_n_symbols, uint64_t rbwt_n_strings,
+                      int device, pbsc_index** out);
+/* reads PREFIX.bwt and PREFIX.rbwt; PREFIX.sai must exist (content unused, as in the reference) unless require_sai==0 */
+int pbsc_index_load(const char* prefix, int device, int require_sai, pbsc_index** out);
+/* synthetic index for the FM microbenchmark: i.i.d. uniform ACGT symbols with n_strings '$' at random
+ * positions, generated on the device from `seed` (both strands get independent streams) */
+int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t seed, int device, pbsc_index** out);
+/* build the short-prefix interval table for all k0-mers (k0 in 1..15); 0 disables it */
+int pbsc_index_build_prefix_table(pbsc_index* idx, int k0);
+void pbsc_index_destroy(pbsc_index* idx);
+uint64_t pbsc_index_num_symbols(const pbsc_index* idx, int which);
+uint64_t pbsc_index_num_strings(const pbsc_index* idx, int which);
+uint64_t pbsc_index_device_bytes(const pbsc_index* idx);
+/* decoded BWT symbol at position i (RLBWT::getChar, SuffixTools/RLBWT.h:42-63); test hook */
+int pbsc_index_get_symbols(const pbsc_index* idx, int which, uint64_t first, uint64_t count, char* out);
+
+/* ---- backward search: BWTAlgorithms::findInterval(const BWT*, w) (SuffixTools/BWTAlgorithms.cpp:14-31) ----
+ * kmers: n strings over ACGT concatenated, offsets[n+1].  lower/upper follow the reference convention
+ * (inclusive; lower > upper when w is absent).  steps[i] (optional) = updateInterval calls executed
+ * before the early break.  Host-buffer entry: copies are part of the call. */
+int pbsc_findinterval_batch(pbsc_index* idx, int which, const char* kmers, const uint64_t* offsets, uint64_t n,
+                            int64_t* lower, int64_t* upper, uint8_t* steps);
+/* fixed-k device-resident variant for timing: kmers2bit is a device pointer to n k-mers packed 2 bits/base
+ * in one uint64 each (base j of the k-mer at bits 2j..2j+1, A=0,C=1,G=2,T=3; k<=32), outputs are device pointers.
+ * Returns kernel milliseconds in *ms (CUDA events on the launch stream). */
+int pbsc_findinterval_device(pbsc_index* idx, int which, const uint64_t* d_kmers2bit, int k, uint64_t n,
+                             int64_t* d_lower, int64_t* d_upper, uint8_t* d_steps, float* ms);
+
+/* ---- seed phase: LongReadProbe::searchSeedsWithHybridKmers (PacBio/LongReadProbe.cpp:34-227) ----
+ * reads: n_reads strings over ACGT concatenated, offsets[n_reads+1].  seeds_out receives the surviving seeds of
+ * read r at seed_offsets[r]..seed_offsets[r+1]; seed_offsets has n_reads+1 entries.  If seeds_cap is too small the
+ * call fails with PBSC_ERR_LIMIT and *seeds_needed says how many are required. */
+int pbsc_seed_batch(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets, uint64_t n_reads,
+                    pbsc_seed* seeds_out, uint64_t seeds_cap, uint64_t* seed_offsets, uint64_t* seeds_needed,
+                    int keep_outcast);
+
+/* ---- FM extension of explicit seed pairs: LongReadSelfCorrectByOverlap ctor + extendOverlap
+ *      (PacBio/LongReadCorrectByOverlap.cpp:17-95,155-211), as called from correctByFMExtension
+ *      (PacBio/PacBioSelfCorrectionProcess.cpp:186-192).  For pair i: src/path/trg strings (already swapped and
+ *      reverse-complemented by the caller when isFromRtoU), dis = disBetweenSrcTarget, k = initkmersize
+ *      (maxOverlap = k+2), min_sa = min_SA_threshold.  status[i] = PBSC_WALK_*; on success the merged
+ *      sequence is out[out_offsets[i]..out_offsets[i+1]). ---- */
+int pbsc_extend_batch(pbsc_index* idx, const pbsc_params* p, uint64_t n_pairs,
+                      const char* src, const uint64_t* src_off, const char* path, const uint64_t* path_off,
+                      const char* trg, const uint64_t* trg_off, const int32_t* dis, const int32_t* k,
+                      const int32_t* min_sa, int32_t* status, char* out, uint64_t out_cap, uint64_t* out_offsets);
+
+/* ---- whole hot path for a batch of reads: PacBioSelfCorrectionProcess::process
+ *      (PacBio/PacBioSelfCorrectionProcess.cpp:23-206) with --nodp semantics for failed walks.
+ *      pieces_out holds the corrected pieces of read r, concatenated, at piece_offsets[...]; piece p of read r
+ *      is pieces_out[piece_offsets[first_piece[r]+p] .. piece_offsets[first_piece[r]+p+1]).  Reads with
+ *      stats[r].merge==0 have no pieces (they go to discard.fa).  first_piece has n_reads+1 entries. ---- */
+int pbsc_correct_batch(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets,
+                       uint64_t n_reads, char* pieces_out, uint64_t pieces_cap, uint64_t* piece_offsets,
+                       uint64_t piece_offsets_cap, uint64_t* first_piece, pbsc_read_stats* stats,
+                       uint64_t* bytes_needed);
+
+/* timing/launch counters of the last pbsc_correct_batch on this thread (ms from CUDA events on the launch stream) */
+typedef struct pbsc_timing
+{
+    float h2d_ms, seed_ms, extend_ms, d2h_ms, total_ms;
+    uint64_t kernel_launches;
+    uint64_t seed_pairs;     /* FM walks attempted */
+    uint64_t rank_queries;   /* occ() lookups issued by the kernels (0 unless built with PBSC_COUNT_OCC) */
+} pbsc_timing;
+int pbsc_last_timing(pbsc_timing* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBSC_H */

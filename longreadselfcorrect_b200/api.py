@@ -1,0 +1,298 @@
+"""ctypes binding of libpbsc.so (include/pbsc.h) — the host-side mirror of the reference interface.
+
+The names follow the reference: ``Params`` is the option block of ``stride pbcorrect``
+(StriDe/PacBioSelfCorrection.cpp:71-101), ``Index`` stands for ``BWTIndexSet`` (pBWT + pRBWT),
+``find_interval`` for ``BWTAlgorithms::findInterval``, ``search_seeds`` for
+``LongReadProbe::searchSeedsWithHybridKmers``, ``extend_overlap`` for
+``LongReadSelfCorrectByOverlap::extendOverlap`` and ``correct_reads`` for
+``PacBioSelfCorrectionProcess::process`` over a batch.  There is no CPU fallback: importing this
+module fails loudly when the CUDA library has not been built, and every compute call fails when no
+GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpbsc.so")
+
+PBSC_BWT, PBSC_RBWT = 0, 1
+
+
+class PbscError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pbsc error {code}: {msg}")
+        self.code = code
+
+
+class CParams(C.Structure):
+    _fields_ = [
+        ("pb_coverage", C.c_int32), ("error_rate", C.c_double), ("start_kmer", C.c_int32), ("next_target", C.c_int32),
+        ("max_leaves", C.c_int32), ("idmer_len", C.c_int32), ("min_kmer", C.c_int32), ("genome", C.c_int32),
+        ("mode", C.c_int32), ("manual", C.c_int32), ("adjust", C.c_int32), ("split", C.c_int32), ("no_dp", C.c_int32),
+        ("offset", C.c_int32 * 3), ("pool", C.c_int32 * 8), ("n_pool", C.c_int32), ("scan_kmer", C.c_int32),
+        ("kmer_up_bound", C.c_int32), ("radius", C.c_int32), ("hh_ratio", C.c_float),
+        ("threshold", (C.c_float * 52) * 3), ("freqs_of_kmer", C.c_double * 101),
+    ]
+
+
+class CSeed(C.Structure):
+    _fields_ = [("start", C.c_int32), ("len", C.c_int32), ("max_fixed_freq", C.c_int32), ("is_repeat", C.c_int32),
+                ("start_best_k", C.c_int32), ("end_best_k", C.c_int32), ("hitchhiked", C.c_int32), ("static_k", C.c_int32)]
+
+
+class CReadStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("total_reads_len", "corrected_len", "total_seed_num", "total_walk_num",
+                                          "high_error_num", "exceed_depth_num", "exceed_leave_num", "fm_num", "dp_num",
+                                          "seed_dis")] + [("merge", C.c_int32), ("n_pieces", C.c_int32)]
+
+
+class CTiming(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("seed_ms", C.c_float), ("extend_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("total_ms", C.c_float), ("kernel_launches", C.c_uint64), ("seed_pairs", C.c_uint64),
+                ("rank_queries", C.c_uint64)]
+
+
+SEED_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("max_fixed_freq", "<i4"), ("is_repeat", "<i4"),
+                       ("start_best_k", "<i4"), ("end_best_k", "<i4"), ("hitchhiked", "<i4"), ("static_k", "<i4")])
+STATS_DTYPE = np.dtype([(n, "<i8") for n in ("total_reads_len", "corrected_len", "total_seed_num", "total_walk_num",
+                                             "high_error_num", "exceed_depth_num", "exceed_leave_num", "fm_num",
+                                             "dp_num", "seed_dis")] + [("merge", "<i4"), ("n_pieces", "<i4")])
+
+# every symbol include/pbsc.h declares
+EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc_params_derive",
+            "pbsc_threshold_table_text", "pbsc_index_create", "pbsc_index_load", "pbsc_index_create_synthetic",
+            "pbsc_index_build_prefix_table", "pbsc_index_destroy", "pbsc_index_num_symbols", "pbsc_index_num_strings",
+            "pbsc_index_device_bytes", "pbsc_index_get_symbols", "pbsc_findinterval_batch", "pbsc_findinterval_device",
+            "pbsc_seed_batch", "pbsc_extend_batch", "pbsc_correct_batch", "pbsc_last_timing"]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpbsc.so; raise if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m longreadselfcorrect_b200.build` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.pbsc_last_error.restype = C.c_char_p
+    for name in ("pbsc_index_num_symbols", "pbsc_index_num_strings", "pbsc_index_device_bytes"):
+        getattr(L, name).restype = C.c_uint64
+    L.pbsc_index_destroy.restype = None
+    L.pbsc_params_default.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc < 0:
+        raise PbscError(rc, lib().pbsc_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(lib().pbsc_device_count())
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _concat(strings):
+    """list[str] -> (bytes array, uint64 offsets[n+1])"""
+    enc = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(enc) + 1, dtype=np.uint64)
+    if enc:
+        off[1:] = np.cumsum([len(e) for e in enc], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, dtype=np.uint8)
+    if buf.size == 0:
+        buf = np.zeros(1, dtype=np.uint8)
+    return buf, off
+
+
+@dataclass
+class Params:
+    """Options of `stride pbcorrect`; `derive()` fills what PacBioSelfCorrectionMain computes (:195-231)."""
+    c: CParams
+
+    @staticmethod
+    def make(coverage: int = 90, error_rate: float = 0.15, genome: int = 10, kmer: int | None = None,
+             unique_offset: int | None = None, repeat_offset: int | None = None, next_target: int = 1,
+             max_leaves: int = 32, idmer_len: int = 9, min_kmer: int = 13, mode: int | None = None,
+             split: bool = False, no_dp: bool = False) -> "Params":
+        p = CParams()
+        lib().pbsc_params_default(C.byref(p))
+        p.pb_coverage, p.error_rate, p.genome = coverage, error_rate, genome
+        p.next_target, p.max_leaves, p.idmer_len, p.min_kmer = next_target, max_leaves, idmer_len, min_kmer
+        p.split, p.no_dp = int(split), int(no_dp)
+        if kmer is not None:
+            p.start_kmer, p.adjust = kmer, 1
+        if unique_offset is not None:
+            p.offset[1], p.adjust = unique_offset, 1
+        if repeat_offset is not None:
+            p.offset[2], p.adjust = repeat_offset, 1
+        if mode is not None:
+            p.mode, p.manual = mode, 1
+        _check(lib().pbsc_params_derive(C.byref(p)))
+        return Params(p)
+
+    def threshold_table_text(self) -> str:
+        buf = C.create_string_buffer(8192)
+        n = lib().pbsc_threshold_table_text(C.byref(self.c), buf, 8192)
+        _check(n)
+        return buf.value.decode()
+
+    @property
+    def pool(self):
+        return [self.c.pool[i] for i in range(self.c.n_pool)]
+
+
+class Index:
+    """Both FM-index strands resident on one GPU (BWTIndexSet::pBWT / pRBWT of the reference)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def load(prefix: str, device: int = 0, require_sai: bool = True) -> "Index":
+        h = C.c_void_p()
+        _check(lib().pbsc_index_load(prefix.encode(), C.c_int(device), C.c_int(int(require_sai)), C.byref(h)))
+        return Index(h)
+
+    @staticmethod
+    def from_runs(bwt_runs: np.ndarray, bwt_nsym: int, bwt_nstr: int, rbwt_runs: np.ndarray, rbwt_nsym: int,
+                  rbwt_nstr: int, device: int = 0) -> "Index":
+        h = C.c_void_p()
+        a = np.ascontiguousarray(bwt_runs, dtype=np.uint8)
+        b = np.ascontiguousarray(rbwt_runs, dtype=np.uint8)
+        _check(lib().pbsc_index_create(_ptr(a, C.c_uint8), C.c_uint64(a.size), C.c_uint64(bwt_nsym), C.c_uint64(bwt_nstr),
+                                       _ptr(b, C.c_uint8), C.c_uint64(b.size), C.c_uint64(rbwt_nsym), C.c_uint64(rbwt_nstr),
+                                       C.c_int(device), C.byref(h)))
+        return Index(h)
+
+    @staticmethod
+    def synthetic(n_symbols: int, n_strings: int, seed: int, device: int = 0) -> "Index":
+        h = C.c_void_p()
+        _check(lib().pbsc_index_create_synthetic(C.c_uint64(n_symbols), C.c_uint64(n_strings), C.c_uint64(seed),
+                                                 C.c_int(device), C.byref(h)))
+        return Index(h)
+
+    def build_prefix_table(self, k0: int) -> None:
+        _check(lib().pbsc_index_build_prefix_table(self._h, C.c_int(k0)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().pbsc_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def num_symbols(self, which: int) -> int:
+        return int(lib().pbsc_index_num_symbols(self._h, C.c_int(which)))
+
+    def num_strings(self, which: int) -> int:
+        return int(lib().pbsc_index_num_strings(self._h, C.c_int(which)))
+
+    def device_bytes(self) -> int:
+        return int(lib().pbsc_index_device_bytes(self._h))
+
+    def symbols(self, which: int, first: int, count: int) -> bytes:
+        buf = np.zeros(max(count, 1), dtype=np.uint8)
+        _check(lib().pbsc_index_get_symbols(self._h, C.c_int(which), C.c_uint64(first), C.c_uint64(count), _ptr(buf, C.c_char)))
+        return buf[:count].tobytes()
+
+    # BWTAlgorithms::findInterval(pBWT, w) for a list of strings; returns (lower, upper, steps)
+    def find_interval(self, which: int, kmers):
+        buf, off = _concat(kmers)
+        n = len(kmers)
+        lo = np.zeros(max(n, 1), dtype=np.int64)
+        hi = np.zeros(max(n, 1), dtype=np.int64)
+        st = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(lib().pbsc_findinterval_batch(self._h, C.c_int(which), _ptr(buf, C.c_char), _ptr(off, C.c_uint64), C.c_uint64(n),
+                                             _ptr(lo, C.c_int64), _ptr(hi, C.c_int64), _ptr(st, C.c_uint8)))
+        return lo[:n], hi[:n], st[:n]
+
+    # LongReadProbe::searchSeedsWithHybridKmers over a batch; returns (seeds structured array, offsets[n+1])
+    def search_seeds(self, params: Params, reads):
+        buf, off = _concat(reads)
+        n = len(reads)
+        cap = int(off[-1] // 10 + 16 * n + 16)
+        seeds = np.zeros(cap, dtype=SEED_DTYPE)
+        soff = np.zeros(n + 1, dtype=np.uint64)
+        need = C.c_uint64(0)
+        _check(lib().pbsc_seed_batch(self._h, C.byref(params.c), _ptr(buf, C.c_char), _ptr(off, C.c_uint64), C.c_uint64(n),
+                                     seeds.ctypes.data_as(C.POINTER(CSeed)), C.c_uint64(cap), _ptr(soff, C.c_uint64),
+                                     C.byref(need), C.c_int(0)))
+        return seeds[: int(soff[-1])], soff
+
+    # LongReadSelfCorrectByOverlap(...).extendOverlap for explicit pairs; returns (status[n], merged strings)
+    def extend_overlap(self, params: Params, src, path, trg, dis, k, min_sa):
+        n = len(src)
+        sb, so = _concat(src)
+        pb, po = _concat(path)
+        tb, to = _concat(trg)
+        d = np.asarray(dis, dtype=np.int32)
+        kk = np.asarray(k, dtype=np.int32)
+        sa = np.asarray(min_sa, dtype=np.int32)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        cap = int(sum(int(1.2 * (len(p) + 10)) + 2 * int(x) + len(t) + 32 for p, x, t in zip(path, k, trg))) + 64
+        out = np.zeros(cap, dtype=np.uint8)
+        ooff = np.zeros(n + 1, dtype=np.uint64)
+        _check(lib().pbsc_extend_batch(self._h, C.byref(params.c), C.c_uint64(n), _ptr(sb, C.c_char), _ptr(so, C.c_uint64),
+                                       _ptr(pb, C.c_char), _ptr(po, C.c_uint64), _ptr(tb, C.c_char), _ptr(to, C.c_uint64),
+                                       _ptr(d, C.c_int32), _ptr(kk, C.c_int32), _ptr(sa, C.c_int32), _ptr(status, C.c_int32),
+                                       _ptr(out, C.c_char), C.c_uint64(cap), _ptr(ooff, C.c_uint64)))
+        raw = out.tobytes()
+        merged = [raw[int(ooff[i]):int(ooff[i + 1])].decode() for i in range(n)]
+        return status[:n], merged
+
+    # PacBioSelfCorrectionProcess::process over a batch; returns (pieces per read, stats structured array)
+    def correct_reads(self, params: Params, reads=None, packed=None):
+        if packed is not None:
+            buf, off = packed
+            n = off.size - 1
+        else:
+            buf, off = _concat(reads)
+            n = len(reads)
+        total = int(off[-1])
+        cap = int(total * 1.3) + 4096 * 4
+        while True:
+            out = np.zeros(cap, dtype=np.uint8)
+            poff_cap = (total // 10 + 4 * n + 16) if params.c.split else (n + 2)
+            poff = np.zeros(poff_cap, dtype=np.uint64)
+            first = np.zeros(n + 1, dtype=np.uint64)
+            stats = np.zeros(max(n, 1), dtype=STATS_DTYPE)
+            need = C.c_uint64(0)
+            rc = lib().pbsc_correct_batch(self._h, C.byref(params.c), _ptr(buf, C.c_char), _ptr(off, C.c_uint64), C.c_uint64(n),
+                                          _ptr(out, C.c_char), C.c_uint64(cap), _ptr(poff, C.c_uint64), C.c_uint64(poff_cap),
+                                          _ptr(first, C.c_uint64), stats.ctypes.data_as(C.POINTER(CReadStats)), C.byref(need))
+            if rc == -5 and need.value > cap:
+                cap = int(need.value) + 64
+                continue
+            _check(rc)
+            break
+        return out, poff, first, stats[:n]
+
+    @staticmethod
+    def pieces_as_strings(out, poff, first):
+        raw = out.tobytes()
+        res = []
+        for r in range(first.size - 1):
+            res.append([raw[int(poff[j]):int(poff[j + 1])].decode() for j in range(int(first[r]), int(first[r + 1]))])
+        return res
+
+
+def last_timing() -> dict:
+    t = CTiming()
+    _check(lib().pbsc_last_timing(C.byref(t)))
+    return {k: getattr(t, k) for k, _ in CTiming._fields_}

@@ -1,0 +1,136 @@
+// fm_table.cuh — GPU-resident flat occurrence table and the backward-search primitives.
+//
+// Replaces RLBWT::getOcc / getPC (SuffixTools/RLBWT.h:118-140; run-length units + two marker
+// levels, ~3 dependent cache lines per query) with one aligned 32-byte sector per occ(c,i):
+//
+//   struct FmBlock { u32 cnt[4]; u32 bases[4]; }      64 BWT symbols per block
+//     cnt[c]   = occurrences of base c (A,C,G,T = 0..3) in bwt[0 .. 64*blk)
+//     bases    = the 64 symbols, 2 bits each, symbol j in word j>>4 at bits 2*(j&15)
+//     '$' is stored as code 0; bit 31 of cnt[0] flags a block that contains a '$', in which
+//     case occ(A,.) is corrected from the sorted '$' position list (rare path: one '$' per read).
+//
+// Intervals are kept half-open [lo, hi) on the device; the reference's inclusive
+// (lower, upper) = (lo, hi-1).  Invalid intervals always have hi == lo (BWTAlgorithms.h:66-72
+// keeps upper == lower-1 once an interval is empty), so size 0 <=> !isValid().
+#ifndef PBSC_FM_TABLE_CUH
+#define PBSC_FM_TABLE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pbsc {
+
+struct __align__(32) FmBlock
+{
+    uint32_t cnt[4];
+    uint32_t bases[4];
+};
+
+// 32-byte prefix-table entry: both strands' intervals of one k0-mer w (key = sum_j w[j]*4^j, w[0] in the low bits):
+//   fwd = interval of reverse(w) in RBWT, rvc = interval of revcomp(w) in BWT.
+struct __align__(32) PrefixEntry
+{
+    uint64_t fwd_lo, rvc_lo;
+    uint32_t fwd_size, rvc_size;
+    uint32_t pad[2];
+};
+
+struct FmTable
+{
+    const FmBlock* blocks;      // n/64 + 1 blocks
+    const uint32_t* dollar_pos; // sorted positions of '$' in the BWT
+    uint64_t n;                 // BWT length (symbols incl. '$')
+    uint64_t C[4];              // C[c] = #symbols lexicographically smaller than base c (RLBWT.cpp:243-247)
+    uint64_t total[4];          // occurrences of each base in the whole BWT
+    uint32_t n_dollar;
+};
+
+struct FmIndexDev
+{
+    FmTable t[2];               // [PBSC_BWT], [PBSC_RBWT]
+    const PrefixEntry* prefix;  // 4^k0 entries or nullptr
+    int k0;
+};
+
+struct Interval   // half-open
+{
+    uint64_t lo, hi;
+    __host__ __device__ __forceinline__ bool valid() const { return hi > lo; }
+    __host__ __device__ __forceinline__ uint64_t size() const { return hi - lo; }
+};
+
+#ifdef PBSC_COUNT_OCC
+__device__ unsigned long long g_occ_counter;
+#define PBSC_OCC_TICK(n) atomicAdd(&g_occ_counter, (unsigned long long)(n))
+#else
+#define PBSC_OCC_TICK(n)
+#endif
+
+__device__ __forceinline__ uint32_t count_dollars(const FmTable& t, uint64_t from, uint64_t to)
+{
+    // number of '$' positions in [from, to): two lower_bounds on the sorted list
+    uint32_t lo = 0, hi = t.n_dollar;
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint64_t)__ldg(t.dollar_pos + m) < from) lo = m + 1; else hi = m; }
+    uint32_t a = lo;
+    hi = t.n_dollar;
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint64_t)__ldg(t.dollar_pos + m) < to) lo = m + 1; else hi = m; }
+    return lo - a;
+}
+
+// occ(c, p): occurrences of base c in bwt[0, p)  ==  RLBWT::getOcc(c, p-1)  (RLBWT.h:121-140)
+__device__ __forceinline__ uint64_t occ(const FmTable& t, int c, uint64_t p)
+{
+    PBSC_OCC_TICK(1);
+    const uint64_t blk = p >> 6;
+    const uint32_t off = (uint32_t)p & 63u;
+    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
+    const uint4 cn = __ldg(bp);
+    const uint4 bs = __ldg(bp + 1);
+    uint32_t base = c == 0 ? cn.x : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
+    const bool has_dollar = (cn.x >> 31) != 0;
+    if (c == 0) base &= 0x7fffffffu;
+    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
+    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
+    const uint64_t pat = 0x5555555555555555ull * (uint64_t)c;
+    uint64_t x0 = w0 ^ pat, x1 = w1 ^ pat;
+    uint64_t m0 = ~(x0 | (x0 >> 1)) & 0x5555555555555555ull;
+    uint64_t m1 = ~(x1 | (x1 >> 1)) & 0x5555555555555555ull;
+    // keep the first `off` symbols
+    if (off < 32) { m0 &= (1ull << (2 * off)) - 1ull; m1 = 0; }
+    else { m1 &= (1ull << (2 * (off - 32))) - 1ull; }
+    uint64_t r = (uint64_t)base + __popcll(m0) + __popcll(m1);
+    if (c == 0 && has_dollar && off) r -= count_dollars(t, blk << 6, p);
+    return r;
+}
+
+// BWTAlgorithms::updateInterval (SuffixTools/BWTAlgorithms.h:66-72) on a half-open interval
+__device__ __forceinline__ Interval update_interval(const FmTable& t, Interval iv, int c)
+{
+    Interval r;
+    const uint64_t a = occ(t, c, iv.lo);
+    const uint64_t b = (iv.hi == iv.lo) ? a : occ(t, c, iv.hi);
+    r.lo = t.C[c] + a;
+    r.hi = t.C[c] + b;
+    return r;
+}
+
+// BWTAlgorithms::initInterval (BWTAlgorithms.h:136-140)
+__device__ __forceinline__ Interval init_interval(const FmTable& t, int c)
+{
+    Interval r;
+    r.lo = t.C[c];
+    r.hi = t.C[c] + t.total[c];
+    return r;
+}
+
+// read one prefix-table entry (one 32-byte sector) and return the strand the caller wants
+__device__ __forceinline__ void prefix_lookup(const FmIndexDev& idx, uint64_t key, Interval& fwd, Interval& rvc)
+{
+    const uint4* ep = reinterpret_cast<const uint4*>(idx.prefix + key);
+    const uint4 a = __ldg(ep), b = __ldg(ep + 1);
+    fwd.lo = (uint64_t)a.x | ((uint64_t)a.y << 32); fwd.hi = fwd.lo + b.x;
+    rvc.lo = (uint64_t)a.z | ((uint64_t)a.w << 32); rvc.hi = rvc.lo + b.y;
+}
+
+}  // namespace pbsc
+#endif

@@ -1,0 +1,54 @@
+// pbsc_batch.cuh — device-side batch layout shared by the seed and extend phases.
+#ifndef PBSC_BATCH_CUH
+#define PBSC_BATCH_CUH
+
+#include "pbsc_internal.h"
+
+namespace pbsc {
+
+// Per-position record of one static k-mer size: what LongReadProbe reads back from
+// KmerFeature::Log()[staticSize][pos] (PacBio/KmerFeature.h:37-136).
+struct __align__(32) StaticFeat
+{
+    uint64_t fwd_lo, rvc_lo;
+    uint32_t fwd_size, rvc_size;
+    int32_t freq;        // KmerFeature::frequency (not yet masked by `fake`)
+    uint32_t count_fake; // count[A..T] in the low 4x7 bits (<=51 each), bit 31 = fake
+};
+
+struct SeedParamsDev
+{
+    int32_t pool[8];
+    int32_t n_pool;
+    int32_t start_kmer, scan_kmer, kmer_up_bound, radius, pb_coverage, manual, mode;
+    int32_t offset[3];
+    int32_t slot_of_mode[3];   // mode -> index into the distinct static sizes
+    int32_t static_size[3];    // distinct static sizes
+    int32_t n_static;
+    float hh_ratio;
+    float threshold[3][52];
+};
+
+// A batch of reads resident on the device.
+struct DeviceBatch
+{
+    DevBuf<uint8_t> codes;      // 2-bit codes, one byte per base, reads concatenated
+    DevBuf<uint64_t> offsets;   // n_reads + 1
+    uint64_t n_reads = 0, n_bases = 0;
+};
+
+// Output of the seed phase, resident on the device.
+struct SeedBuffers
+{
+    DevBuf<pbsc_seed> seeds;       // per-read regions [region[r], region[r+1])
+    DevBuf<uint64_t> region;       // n_reads + 1
+    DevBuf<uint32_t> count;        // surviving seeds of read r (packed at the start of its region)
+    DevBuf<uint32_t> outcast;      // hitchhiked seeds of read r (packed after the surviving ones)
+    uint64_t total_slots = 0;
+};
+
+int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b);
+int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, uint64_t* launches);
+
+}  // namespace pbsc
+#endif

@@ -1,0 +1,66 @@
+// pbsc_internal.h — host-side state shared by the translation units of libpbsc.so.
+#ifndef PBSC_INTERNAL_H
+#define PBSC_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/pbsc.h"
+#include "fm_table.cuh"
+
+struct pbsc_index
+{
+    int device = 0;
+    pbsc::FmIndexDev dev;
+    pbsc::FmBlock* d_blocks[2] = {nullptr, nullptr};
+    uint32_t* d_dollar[2] = {nullptr, nullptr};
+    pbsc::PrefixEntry* d_prefix = nullptr;
+    uint64_t n_symbols[2] = {0, 0}, n_strings[2] = {0, 0}, n_blocks[2] = {0, 0};
+    size_t device_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+namespace pbsc {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define PBSC_CUDA(call)                                                             \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess) return pbsc::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// RAII device buffer (freed on scope exit); keeps the C ABI functions leak-free on error paths
+template <class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t count)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    }
+};
+
+struct Timing
+{
+    float h2d_ms = 0, seed_ms = 0, extend_ms = 0, d2h_ms = 0, total_ms = 0;
+    uint64_t kernel_launches = 0, seed_pairs = 0, rank_queries = 0;
+};
+Timing& last_timing();
+
+// 2-bit code of a base; -1 for anything else
+inline int base_code(char b) { switch (b) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; } }
+
+}  // namespace pbsc
+#endif
