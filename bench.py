@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""Benchmark of the `stride pbcorrect` hot path (seed discovery + FM extension, --nodp) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny]
+
+One "step" = one pass of the hot path over the whole read set of the workload (BASELINE.json configs[1] by
+default: 4.6 Mb synthetic genome, 50x simulated CLR reads, mean 8 kb, `-c 50 -g 5 --nodp`).
+  value  corrected Mbp/s with the reads already resident in HBM (pbsc_batch_run: kernels only, CUDA events)
+  e2e    the same through pbsc_correct_batch on host buffers (H2D of the reads + D2H of the corrected pieces inside)
+N > 1 (torchrun): one process per GPU, the index replicated, every rank corrects the full read set (weak scaling,
+no data-path collective); time = max over ranks, value = N x Mbp / time.
+`--impl reference` times the reference's own multithreaded CPU implementation (oracle/_ref/stride pbcorrect -t <cores>)
+on a bounded sample of the same reads against the same index files.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: genome length, genome seed, coverage, mean read length, read seed, pbcorrect options
+    "cfg2": dict(genome=4_600_000, gseed=2, cov=50, mean=8000, rseed=102, c=50, g=5,
+                 desc="4.6 Mb synthetic genome, 50x simulated CLR reads (mean 8 kb, 13% error), -c 50 -g 5 --nodp"),
+    "cfg1": dict(genome=1_000_000, gseed=1, cov=30, mean=6000, rseed=101, c=30, g=5,
+                 desc="1 Mb synthetic genome, 30x simulated CLR reads (mean 6 kb, 13% error), -c 30 -g 5 --nodp"),
+    "tiny": dict(genome=100_000, gseed=1, cov=30, mean=3000, rseed=101, c=30, g=5,
+                 desc="100 kb synthetic genome, 30x simulated CLR reads (mean 3 kb), -c 30 -g 5 --nodp"),
+}
+REF_STRIDE = os.path.join(ROOT, "oracle", "_ref", "stride")
+ORACLE = os.path.join(ROOT, "oracle", "pbsc_oracle")
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def make_data(wl):
+    from longreadselfcorrect_b200 import synth
+    t = time.time()
+    g = synth.make_genome(wl["genome"], wl["gseed"])
+    codes, off = synth.simulate_reads(g, wl["cov"], wl["mean"], wl["rseed"])
+    log(f"simulated {off.size - 1} reads, {codes.size / 1e6:.1f} Mbp in {time.time() - t:.1f}s")
+    return codes, off
+
+
+def packed_ascii(codes, off):
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    return np.ascontiguousarray(letters), off.astype(np.uint64)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for nm, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=None):
+    """FASTA of the sampled reads + PREFIX.bwt/.rbwt/.sai of the FULL read set, for the reference binary."""
+    from longreadselfcorrect_b200 import bwt_build, synth
+    prefix = os.path.join(d, "idx")
+    if bwt_runs is None:
+        bwt_runs = bwt_build.build_index_files(prefix, codes, off)
+    else:
+        n = off.size - 1
+        for ext in ("bwt", "rbwt"):
+            runs, nsym, nstr = bwt_runs[ext]
+            bwt_build.write_bwt_file(f"{prefix}.{ext}", runs, nstr, nsym)
+        bwt_build.write_sai_file(prefix + ".sai", n)
+    fa = os.path.join(d, "sample.fa")
+    synth.write_fasta(fa, codes[: off[sample_reads]], off[: sample_reads + 1])
+    return prefix, fa, bwt_runs
+
+
+def run_reference(prefix, fa, wl, threads, outdir):
+    """`stride pbcorrect -t T --nodp`; returns (seconds of the processing loop, wall seconds)."""
+    t0 = time.time()
+    r = subprocess.run([REF_STRIDE, "pbcorrect", "-t", str(threads), "-p", prefix, "-o", outdir, "-c", str(wl["c"]), "-g", str(wl["g"]),
+                        "--nodp", fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    wall = time.time() - t0
+    if r.returncode != 0:
+        raise RuntimeError("reference failed: " + r.stderr[-500:])
+    m = re.search(r"Processed \d+ sequences in ([0-9.]+)s", r.stderr)
+    return (float(m.group(1)) if m else wall), wall
+
+
+def oracle_rank_queries(prefix, fa, wl, threads):
+    """Algorithmic rank queries of the reference algorithm on the sample (instrumented oracle)."""
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([ORACLE, "pbcorrect", "--threads", str(threads), "-p", prefix, "-o", os.path.join(d, "o"), "-c", str(wl["c"]),
+                            "-g", str(wl["g"]), "--nodp", fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    m = re.search(r"rank queries (\d+) \(seed (\d+), extend (\d+)\), walks (\d+)", r.stderr)
+    if not m:
+        return None
+    return {"total": int(m.group(1)), "seed": int(m.group(2)), "extend": int(m.group(3)), "walks": int(m.group(4))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--k0", type=int, default=13, help="short-prefix table length (0 = off)")
+    ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="Mbp of reads for the CPU baseline (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        codes, off = make_data(wl)
+        total_mbp = codes.size / 1e6
+        # bounded sample: ~0.06 Mbp/s/core (BASELINE.md probe) x cores x ~25 s per step
+        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.05 * cores * 25))
+        sample_reads = int(np.searchsorted(off, sample_mbp * 1e6))
+        sample_reads = max(1, min(sample_reads, off.size - 1))
+        sample_mbp = float(off[sample_reads]) / 1e6
+        with tempfile.TemporaryDirectory() as d:
+            prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads)
+            times = []
+            for i in range(args.warmup + args.steps):
+                secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, f"out{i}"))
+                log(f"reference step {i}: {secs:.2f}s processing ({wall:.1f}s wall incl. index load)")
+                if i >= args.warmup:
+                    times.append(secs)
+        ms = 1000 * float(np.mean(times))
+        v = sample_mbp / (ms / 1000)
+        sample_desc = f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index"
+        print(json.dumps({
+            "impl": "reference", "metric": "corrected Mbp/s (seed + FM-extend, --nodp)", "value": v, "unit": "Mbp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample": sample_desc, "threads": cores},
+            "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+            "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    from longreadselfcorrect_b200 import api, bwt_build
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    codes, off = make_data(wl)
+    total_mbp = codes.size / 1e6
+    n_reads = off.size - 1
+    t = time.time()
+    runs = {}
+    for ext, rev in (("bwt", False), ("rbwt", True)):
+        b = bwt_build.bwt_symbols(codes, off, reverse=rev, device=f"cuda:{local_rank}")
+        runs[ext] = (bwt_build.run_length_bytes(b), int(b.numel()), n_reads)
+        del b
+    torch.cuda.empty_cache()
+    log(f"rank {rank}: BWT + RBWT of {total_mbp:.1f} Mbp built on the GPU in {time.time() - t:.1f}s")
+    t = time.time()
+    idx = api.Index.from_runs(runs["bwt"][0], runs["bwt"][1], n_reads, runs["rbwt"][0], runs["rbwt"][1], n_reads, device=local_rank)
+    if args.k0:
+        idx.build_prefix_table(args.k0)
+    index_s = time.time() - t
+    log(f"rank {rank}: rank tables + prefix table (k0={args.k0}) on device in {index_s:.1f}s, {idx.device_bytes() / 1e9:.2f} GB")
+    params = api.Params.make(coverage=wl["c"], genome=wl["g"], no_dp=True)
+    packed = packed_ascii(codes, off)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: batch resident on the device, kernels only ----
+    batch = api.Batch(idx, params, packed=packed)
+    for _ in range(args.warmup):
+        batch.run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    step_ms, phase = [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_ms.append(batch.run())
+        tm = api.last_timing()
+        phase.append((tm["seed_ms"], tm["extend_ms"]))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000
+    clocks = sampler.stop()
+    tm = api.last_timing()
+    dev_ms = float(np.sum(step_ms))
+    if dist is not None:
+        tt = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(tt[0]), float(tt[1])
+    ms_per_step = dev_ms / args.steps
+    value = world * total_mbp / (ms_per_step / 1000)
+    out, poff, first, stats = batch.fetch()
+    d2h_bytes = int(poff[-1]) + stats.nbytes + poff.nbytes + first.nbytes
+    merged = stats[stats["merge"] == 1]
+    walks = int(merged["total_walk_num"].sum())
+    fm = int(merged["fm_num"].sum())
+    batch.close()
+
+    # ---- e2e: host buffers in, corrected pieces out, through pbsc_correct_batch ----
+    e2e_ms = []
+    for i in range(args.e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        idx.correct_reads(params, packed=packed)
+        torch.cuda.synchronize()
+        if i > 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1000)
+    e2e = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
+    if dist is not None:
+        tt = torch.tensor([e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = float(tt[0])
+    e2e_value = world * total_mbp / (e2e / 1000)
+    h2d_bytes = int(packed[0].nbytes + packed[1].nbytes)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline (reference binary on a bounded sample) + algorithmic rank-query counts (oracle) ----
+    cpu = None
+    alg = None
+    if not args.no_cpu_baseline and os.path.exists(REF_STRIDE):
+        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.05 * cores * 20))
+        sample_reads = max(1, min(int(np.searchsorted(off, sample_mbp * 1e6)), n_reads))
+        sample_mbp = float(off[sample_reads]) / 1e6
+        with tempfile.TemporaryDirectory() as d:
+            prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=runs)
+            secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"))
+            log(f"reference CPU baseline: {sample_mbp:.1f} Mbp in {secs:.2f}s with {cores} threads")
+            cpu = {"value": sample_mbp / secs, "unit": "Mbp/s", "cores": cores, "kind": "reference",
+                   "sample": f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores} --nodp"}
+            small = max(1, min(int(np.searchsorted(off, min(sample_mbp, 4.0) * 1e6)), n_reads))
+            if os.path.exists(ORACLE):
+                from longreadselfcorrect_b200 import synth
+                fa2 = os.path.join(d, "alg.fa")
+                synth.write_fasta(fa2, codes[: off[small]], off[: small + 1])
+                alg = oracle_rank_queries(prefix, fa2, wl, min(cores, 32))
+                if alg:
+                    alg["sample_bases"] = int(off[small])
+
+    # ---- roofline of the dominant kernel (correct_reads_kernel, the FM-extend chain) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ext_ms = float(np.mean([p[1] for p in phase]))
+    seed_ms = float(np.mean([p[0] for p in phase]))
+    roof = {"bound": "hbm", "kernel": "correct_reads_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "kernel_ms": ext_ms, "seed_phase_ms": seed_ms}
+    if alg and alg.get("walks"):
+        per_walk = alg["extend"] / alg["walks"]
+        alg_bytes = per_walk * walks * 32.0
+        roof["achieved"] = alg_bytes / (ext_ms / 1000) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["algorithmic_rank_queries_per_walk"] = per_walk
+        roof["algorithmic_rank_queries_per_read_base_seed_phase"] = alg["seed"] / alg["sample_bases"]
+        roof["seed_phase_achieved_GBs"] = alg["seed"] / alg["sample_bases"] * codes.size * 32.0 / (seed_ms / 1000) / 1e9
+
+    line = {
+        "metric": "corrected Mbp/s (seed + FM-extend, --nodp)", "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "reads": n_reads, "mbp": total_mbp, "walks": walks, "fm_success": fm,
+                   "index_bytes": idx.device_bytes(), "prefix_k0": args.k0, "index_build_s": index_s,
+                   "l2": "rank tables + prefix table exceed the 126 MB L2; no explicit flush",
+                   "sharding": "index replicated per GPU, every rank corrects the full read set, no collective on the data path",
+                   "wall_ms_per_step": wall_ms / args.steps},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e},
+        "gpu_launches": int(tm["kernel_launches"]) * args.steps,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

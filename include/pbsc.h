@@ -167,7 +167,22 @@ int pbsc_correct_batch(pbsc_index* idx, const pbsc_params* p, const char* reads,
                        uint64_t piece_offsets_cap, uint64_t* first_piece, pbsc_read_stats* stats,
                        uint64_t* bytes_needed);
 
-/* timing/launch counters of the last pbsc_correct_batch on this thread (ms from CUDA events on the launch stream) */
+/* ---- the same path with the batch resident on the device, for callers that pipeline copies themselves
+ *      (Concurrency/SequenceProcessFramework.h:91-230 is replaced by this staged interface):
+ *      upload (pinned async H2D) -> run (seed + extend kernels only, nothing crosses PCIe) -> fetch (D2H). ---- */
+typedef struct pbsc_batch pbsc_batch;
+int pbsc_batch_upload(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets,
+                      uint64_t n_reads, pbsc_batch** out);
+/* runs the kernels; *ms = device time between CUDA events on the launch stream (may be NULL) */
+int pbsc_batch_run(pbsc_batch* b, float* ms);
+/* sizes of the packed result: total piece bytes and number of pieces */
+int pbsc_batch_result_size(pbsc_batch* b, uint64_t* piece_bytes, uint64_t* n_pieces);
+int pbsc_batch_fetch(pbsc_batch* b, char* pieces_out, uint64_t pieces_cap, uint64_t* piece_offsets,
+                     uint64_t piece_offsets_cap, uint64_t* first_piece, pbsc_read_stats* stats);
+void pbsc_batch_destroy(pbsc_batch* b);
+
+/* timing/launch counters of the last pbsc_correct_batch / pbsc_batch_run on this thread (ms from CUDA events
+ * on the launch stream) */
 typedef struct pbsc_timing
 {
     float h2d_ms, seed_ms, extend_ms, d2h_ms, total_ms;

@@ -68,7 +68,8 @@ EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc
             "pbsc_threshold_table_text", "pbsc_index_create", "pbsc_index_load", "pbsc_index_create_synthetic",
             "pbsc_index_build_prefix_table", "pbsc_index_destroy", "pbsc_index_num_symbols", "pbsc_index_num_strings",
             "pbsc_index_device_bytes", "pbsc_index_get_symbols", "pbsc_findinterval_batch", "pbsc_findinterval_device",
-            "pbsc_seed_batch", "pbsc_extend_batch", "pbsc_correct_batch", "pbsc_last_timing"]
+            "pbsc_seed_batch", "pbsc_extend_batch", "pbsc_correct_batch", "pbsc_last_timing",
+            "pbsc_batch_upload", "pbsc_batch_run", "pbsc_batch_result_size", "pbsc_batch_fetch", "pbsc_batch_destroy"]
 
 _lib = None
 
@@ -86,6 +87,7 @@ def lib() -> C.CDLL:
     for name in ("pbsc_index_num_symbols", "pbsc_index_num_strings", "pbsc_index_device_bytes"):
         getattr(L, name).restype = C.c_uint64
     L.pbsc_index_destroy.restype = None
+    L.pbsc_batch_destroy.restype = None
     L.pbsc_params_default.restype = None
     _lib = L
     return L
@@ -290,6 +292,49 @@ class Index:
         for r in range(first.size - 1):
             res.append([raw[int(poff[j]):int(poff[j + 1])].decode() for j in range(int(first[r]), int(first[r + 1]))])
         return res
+
+
+class Batch:
+    """A batch of reads resident on the device: upload -> run (kernels only) -> fetch (pbsc_batch_* in pbsc.h)."""
+
+    def __init__(self, index: Index, params: Params, reads=None, packed=None):
+        if packed is not None:
+            self.buf, self.off = packed
+        else:
+            self.buf, self.off = _concat(reads)
+        self.n = self.off.size - 1
+        self.params = params
+        self.index = index
+        self._h = C.c_void_p()
+        _check(lib().pbsc_batch_upload(index._h, C.byref(params.c), _ptr(self.buf, C.c_char), _ptr(self.off, C.c_uint64),
+                                       C.c_uint64(self.n), C.byref(self._h)))
+
+    def run(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().pbsc_batch_run(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def fetch(self):
+        nb, npieces = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().pbsc_batch_result_size(self._h, C.byref(nb), C.byref(npieces)))
+        out = np.zeros(max(int(nb.value), 1), dtype=np.uint8)
+        poff = np.zeros(int(npieces.value) + 1, dtype=np.uint64)
+        first = np.zeros(self.n + 1, dtype=np.uint64)
+        stats = np.zeros(max(self.n, 1), dtype=STATS_DTYPE)
+        _check(lib().pbsc_batch_fetch(self._h, _ptr(out, C.c_char), C.c_uint64(out.size), _ptr(poff, C.c_uint64), C.c_uint64(poff.size),
+                                      _ptr(first, C.c_uint64), stats.ctypes.data_as(C.POINTER(CReadStats))))
+        return out, poff, first, stats[: self.n]
+
+    def close(self):
+        if self._h:
+            lib().pbsc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def last_timing() -> dict:

@@ -47,8 +47,35 @@ struct SeedBuffers
     uint64_t total_slots = 0;
 };
 
+// Everything one batch needs on the device, allocated once by pbsc_batch_upload so that pbsc_batch_run only
+// launches kernels.
+struct Workspace
+{
+    // seed phase
+    DevBuf<StaticFeat> feats;
+    DevBuf<uint8_t> cls, attr;
+    DevBuf<pbsc_seed> seed_tmp;
+    // extend phase
+    DevBuf<uint8_t> pieces, scratch;
+    DevBuf<uint64_t> piece_region, bounds_region;
+    DevBuf<uint32_t> bounds, order;
+    DevBuf<pbsc_read_stats> stats;
+    DevBuf<int32_t> status;
+    DevBuf<unsigned long long> counters;   // [0] work queue, [1] walks attempted
+    DevBuf<unsigned int> maxima;           // [0] largest seed gap, [1] largest target seed
+    std::vector<uint64_t> h_piece_region, h_bounds_region;
+    uint32_t q_cap = 0, node_cap = 0, merged_cap = 0;
+    int blocks = 0;
+    size_t scratch_stride = 0;
+    float piece_factor = 1.5f;
+};
+
 int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b);
-int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, uint64_t* launches);
+int alloc_seed_workspace(const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w, cudaStream_t st);
+int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches);
+int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w);
+// launches the chain kernel; returns PBSC_ERR_LIMIT when some read overflowed its scratch/piece capacity
+int run_extend_chain(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches);
 
 }  // namespace pbsc
 #endif

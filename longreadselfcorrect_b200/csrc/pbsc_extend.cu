@@ -325,90 +325,74 @@ int launch_geometry(int device, int* blocks)
     return PBSC_OK;
 }
 
-int run_extend_chain(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, const std::vector<uint64_t>& h_offsets,
-                     std::vector<uint8_t>& h_pieces, std::vector<uint64_t>& h_piece_region, std::vector<uint32_t>& h_bounds,
-                     std::vector<uint64_t>& h_bounds_region, std::vector<pbsc_read_stats>& h_stats, uint64_t* launches, uint64_t* walks,
-                     float piece_factor, uint32_t node_cap)
+int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w)
 {
     cudaStream_t st = idx->stream;
     const uint64_t n = b.n_reads;
-    // ---- capacities ----
-    DevBuf<unsigned int> dmax;
-    PBSC_CUDA(dmax.alloc(2));
-    PBSC_CUDA(cudaMemsetAsync(dmax.p, 0, 8, st));
-    if (n) chain_bounds_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, s.seeds.p, s.region.p, s.count.p, p->next_target, dmax.p, dmax.p + 1);
-    unsigned int hmax[2] = {0, 0};
-    PBSC_CUDA(cudaMemcpyAsync(hmax, dmax.p, 8, cudaMemcpyDeviceToHost, st));
-    PBSC_CUDA(cudaStreamSynchronize(st));
-    const uint32_t kmax = 64;
-    const uint32_t q_cap = (uint32_t)align_up((size_t)hmax[0] + hmax[1] + kmax + 16, 16);
-    const uint32_t merged_cap = (uint32_t)align_up((size_t)(1.2 * (hmax[0] + 10)) + 2 * kmax + hmax[1] + 64, 16);
-    ExtParamsDev P;
-    make_ext_params(p, P, q_cap, node_cap, merged_cap);
-    ChainParamsDev C;
-    C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split; C.pb_coverage = p->pb_coverage;
-
-    // ---- per-read output regions ----
-    std::vector<uint32_t> h_count(n);
-    if (n) PBSC_CUDA(cudaMemcpy(h_count.data(), s.count.p, n * 4, cudaMemcpyDeviceToHost));
-    h_piece_region.assign(n + 1, 0);
-    h_bounds_region.assign(n + 1, 0);
+    // per-read output regions sized from the read length alone, so nothing has to come back from the seed phase
+    w.h_piece_region.assign(n + 1, 0);
+    w.h_bounds_region.assign(n + 1, 0);
+    int min_static = p->start_kmer;
+    for (int m = 0; m < 3; m++) min_static = std::min(min_static, p->start_kmer + p->offset[m]);
     for (uint64_t r = 0; r < n; r++)
     {
         const uint64_t L = h_offsets[r + 1] - h_offsets[r];
-        const uint64_t cap = h_count[r] >= 2 ? (uint64_t)(piece_factor * (double)L) + 2048 : 0;
-        h_piece_region[r + 1] = h_piece_region[r] + align_up(cap, 16);
-        h_bounds_region[r + 1] = h_bounds_region[r] + (h_count[r] >= 2 ? (p->split ? h_count[r] + 2 : 2) : 0);
+        const uint64_t cap = (int64_t)L >= p->start_kmer ? (uint64_t)(w.piece_factor * (double)L) + 2048 : 0;
+        w.h_piece_region[r + 1] = w.h_piece_region[r] + align_up(cap, 16);
+        w.h_bounds_region[r + 1] = w.h_bounds_region[r] + (cap ? (p->split ? L / (uint64_t)std::max(min_static, 1) + 4 : 2) : 0);
     }
-    DevBuf<uint8_t> d_pieces; DevBuf<uint64_t> d_piece_region, d_bounds_region; DevBuf<uint32_t> d_bounds, d_order;
-    DevBuf<pbsc_read_stats> d_stats; DevBuf<int32_t> d_status; DevBuf<unsigned long long> d_counter;
-    PBSC_CUDA(d_pieces.alloc(h_piece_region[n])); PBSC_CUDA(d_piece_region.alloc(n + 1)); PBSC_CUDA(d_bounds_region.alloc(n + 1));
-    PBSC_CUDA(d_bounds.alloc(h_bounds_region[n])); PBSC_CUDA(d_order.alloc(n)); PBSC_CUDA(d_stats.alloc(n)); PBSC_CUDA(d_status.alloc(n));
-    PBSC_CUDA(d_counter.alloc(2));
+    PBSC_CUDA(w.pieces.alloc(w.h_piece_region[n])); PBSC_CUDA(w.piece_region.alloc(n + 1)); PBSC_CUDA(w.bounds_region.alloc(n + 1));
+    PBSC_CUDA(w.bounds.alloc(w.h_bounds_region[n])); PBSC_CUDA(w.order.alloc(n)); PBSC_CUDA(w.stats.alloc(n)); PBSC_CUDA(w.status.alloc(n));
+    PBSC_CUDA(w.counters.alloc(2)); PBSC_CUDA(w.maxima.alloc(2));
     // longest reads first: the chain of a read is sequential, so the tail of the batch is the longest chain
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return (h_offsets[a + 1] - h_offsets[a]) > (h_offsets[c + 1] - h_offsets[c]); });
-    PBSC_CUDA(cudaMemcpyAsync(d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, st));
-    PBSC_CUDA(cudaMemcpyAsync(d_piece_region.p, h_piece_region.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    PBSC_CUDA(cudaMemcpyAsync(d_bounds_region.p, h_bounds_region.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    PBSC_CUDA(cudaMemsetAsync(d_counter.p, 0, 16, st));
-
-    int blocks = 0;
-    int rc = launch_geometry(idx->device, &blocks);
+    PBSC_CUDA(cudaMemcpyAsync(w.order.p, order.data(), n * 4, cudaMemcpyHostToDevice, st));
+    PBSC_CUDA(cudaMemcpyAsync(w.piece_region.p, w.h_piece_region.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    PBSC_CUDA(cudaMemcpyAsync(w.bounds_region.p, w.h_bounds_region.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = launch_geometry(idx->device, &w.blocks);
     if (rc != PBSC_OK) return rc;
-    const uint64_t warps_needed = (n + 0);
-    if ((uint64_t)blocks * WARPS_PER_BLOCK > warps_needed) blocks = (int)((warps_needed + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    if (blocks < 1) blocks = 1;
-    const size_t stride = warp_scratch_bytes(q_cap, node_cap, merged_cap);
-    DevBuf<uint8_t> d_scratch;
-    PBSC_CUDA(d_scratch.alloc(stride * (size_t)blocks * WARPS_PER_BLOCK));
-    if (n)
-    {
-        correct_reads_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(idx->dev, P, C, d_scratch.p, stride, d_counter.p, n, d_order.p, b.codes.p, b.offsets.p,
-                                                                      s.seeds.p, s.region.p, s.count.p, d_pieces.p, d_piece_region.p, d_bounds.p,
-                                                                      d_bounds_region.p, d_stats.p, d_status.p, d_counter.p + 1);
-        if (launches) *launches += 2;
-    }
-    PBSC_CUDA(cudaGetLastError());
-    h_pieces.resize(h_piece_region[n]);
-    h_bounds.resize(h_bounds_region[n]);
-    h_stats.resize(n);
-    std::vector<int32_t> h_status(n);
-    if (h_piece_region[n]) PBSC_CUDA(cudaMemcpyAsync(h_pieces.data(), d_pieces.p, h_piece_region[n], cudaMemcpyDeviceToHost, st));
-    if (h_bounds_region[n]) PBSC_CUDA(cudaMemcpyAsync(h_bounds.data(), d_bounds.p, h_bounds_region[n] * 4, cudaMemcpyDeviceToHost, st));
-    if (n) PBSC_CUDA(cudaMemcpyAsync(h_stats.data(), d_stats.p, n * sizeof(pbsc_read_stats), cudaMemcpyDeviceToHost, st));
-    if (n) PBSC_CUDA(cudaMemcpyAsync(h_status.data(), d_status.p, n * 4, cudaMemcpyDeviceToHost, st));
-    unsigned long long hw = 0;
-    PBSC_CUDA(cudaMemcpyAsync(&hw, d_counter.p + 1, 8, cudaMemcpyDeviceToHost, st));
+    if ((uint64_t)w.blocks * WARPS_PER_BLOCK > n) w.blocks = (int)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    if (w.blocks < 1) w.blocks = 1;
+    if (w.q_cap == 0) w.q_cap = 2048;
+    if (w.node_cap == 0) w.node_cap = 1u << 15;
+    w.merged_cap = (uint32_t)align_up((size_t)(1.2 * (w.q_cap + 10)) + 256, 16);
+    w.scratch_stride = warp_scratch_bytes(w.q_cap, w.node_cap, w.merged_cap);
+    PBSC_CUDA(w.scratch.alloc(w.scratch_stride * (size_t)w.blocks * WARPS_PER_BLOCK));
     PBSC_CUDA(cudaStreamSynchronize(st));
-    if (walks) *walks += hw;
-    for (uint64_t r = 0; r < n; r++)
+    return PBSC_OK;
+}
+
+int run_extend_chain(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches)
+{
+    cudaStream_t st = idx->stream;
+    const uint64_t n = b.n_reads;
+    if (n == 0) return PBSC_OK;
+    // ---- does the largest seed gap of this batch fit the per-warp query scratch? (8-byte round trip) ----
+    PBSC_CUDA(cudaMemsetAsync(w.maxima.p, 0, 8, st));
+    chain_bounds_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, s.seeds.p, s.region.p, s.count.p, p->next_target, w.maxima.p, w.maxima.p + 1);
+    unsigned int hmax[2] = {0, 0};
+    PBSC_CUDA(cudaMemcpyAsync(hmax, w.maxima.p, 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    const uint32_t need_q = (uint32_t)align_up((size_t)hmax[0] + hmax[1] + 64 + 16, 16);
+    if (need_q > w.q_cap)
     {
-        if (h_status[r] == PBSC_WALK_OVERFLOW) return PBSC_ERR_LIMIT;   // caller retries with larger capacities
-        if (h_status[r] == PBSC_WALK_UNSUPPORTED) { set_error("read %llu: seed pair outside this build's limits (k-mer > 61, target shorter than -s, ...)", (unsigned long long)r); return PBSC_ERR_INTERNAL; }
-        if (h_status[r] == PBSC_WALK_NO_PATH) { set_error("Does it really happen?"); return PBSC_ERR_INTERNAL; }
+        w.q_cap = need_q;
+        w.merged_cap = (uint32_t)align_up((size_t)(1.2 * (w.q_cap + 10)) + 256, 16);
+        w.scratch_stride = warp_scratch_bytes(w.q_cap, w.node_cap, w.merged_cap);
+        PBSC_CUDA(w.scratch.alloc(w.scratch_stride * (size_t)w.blocks * WARPS_PER_BLOCK));
     }
+    ExtParamsDev P;
+    make_ext_params(p, P, w.q_cap, w.node_cap, w.merged_cap);
+    ChainParamsDev C;
+    C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split; C.pb_coverage = p->pb_coverage;
+    PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 16, st));
+    correct_reads_kernel<<<w.blocks, WARPS_PER_BLOCK * 32, 0, st>>>(idx->dev, P, C, w.scratch.p, w.scratch_stride, w.counters.p, n, w.order.p, b.codes.p, b.offsets.p,
+                                                                    s.seeds.p, s.region.p, s.count.p, w.pieces.p, w.piece_region.p, w.bounds.p,
+                                                                    w.bounds_region.p, w.stats.p, w.status.p, w.counters.p + 1);
+    if (launches) *launches += 2;
+    PBSC_CUDA(cudaGetLastError());
     return PBSC_OK;
 }
 

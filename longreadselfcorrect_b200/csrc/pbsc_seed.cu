@@ -372,44 +372,47 @@ static void make_seed_params(const pbsc_params* p, SeedParamsDev& d)
     memcpy(d.threshold, p->threshold, sizeof d.threshold);
 }
 
-int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, uint64_t* launches)
+int alloc_seed_workspace(const pbsc_params* p, const std::vector<uint64_t>& off, DeviceBatch& b, SeedBuffers& s, Workspace& w, cudaStream_t st)
 {
     SeedParamsDev P;
     make_seed_params(p, P);
-    cudaStream_t st = idx->stream;
     // per-read seed regions: seeds never overlap and are at least min(static size) long
     int min_static = P.static_size[0];
     for (int j = 1; j < P.n_static; j++) min_static = std::min(min_static, P.static_size[j]);
     if (min_static < 1) { set_error("static k-mer size must be positive"); return PBSC_ERR_ARG; }
-    std::vector<uint64_t> off(b.n_reads + 1), region(b.n_reads + 1);
-    PBSC_CUDA(cudaMemcpy(off.data(), b.offsets.p, (b.n_reads + 1) * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> region(b.n_reads + 1);
     region[0] = 0;
     for (uint64_t r = 0; r < b.n_reads; r++) region[r + 1] = region[r] + (off[r + 1] - off[r]) / (uint64_t)min_static + 2;
     s.total_slots = region[b.n_reads];
-    DevBuf<StaticFeat> feats;
-    DevBuf<uint8_t> cls, attr;
-    DevBuf<pbsc_seed> tmp;
-    PBSC_CUDA(feats.alloc((uint64_t)P.n_static * b.n_bases));
-    PBSC_CUDA(cls.alloc(b.n_bases)); PBSC_CUDA(attr.alloc(b.n_bases));
-    PBSC_CUDA(tmp.alloc(s.total_slots)); PBSC_CUDA(s.seeds.alloc(s.total_slots));
+    PBSC_CUDA(w.feats.alloc((uint64_t)P.n_static * b.n_bases));
+    PBSC_CUDA(w.cls.alloc(b.n_bases)); PBSC_CUDA(w.attr.alloc(b.n_bases));
+    PBSC_CUDA(w.seed_tmp.alloc(s.total_slots)); PBSC_CUDA(s.seeds.alloc(s.total_slots));
     PBSC_CUDA(s.region.alloc(b.n_reads + 1)); PBSC_CUDA(s.count.alloc(b.n_reads)); PBSC_CUDA(s.outcast.alloc(b.n_reads));
     PBSC_CUDA(cudaMemcpyAsync(s.region.p, region.data(), (b.n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    return PBSC_OK;
+}
+
+int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches)
+{
+    SeedParamsDev P;
+    make_seed_params(p, P);
+    cudaStream_t st = idx->stream;
     uint64_t nl = 0;
     if (b.n_bases)
     {
-        seed_features_kernel<<<(unsigned)((b.n_bases + 255) / 256), 256, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, feats.p, cls.p);
+        seed_features_kernel<<<(unsigned)((b.n_bases + 255) / 256), 256, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, w.feats.p, w.cls.p);
         nl++;
     }
     if (b.n_reads)
     {
-        seed_scan_kernel<<<(unsigned)((b.n_reads + 127) / 128), 128, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, feats.p, cls.p,
-                                                                              attr.p, tmp.p, s.region.p, s.count.p);
-        seed_bestk_kernel<<<(unsigned)((s.total_slots * 2 + 127) / 128), 128, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, tmp.p, s.region.p, s.count.p, s.total_slots);
-        seed_hitchhike_kernel<<<(unsigned)((b.n_reads + 127) / 128), 128, 0, st>>>(P, b.n_reads, tmp.p, s.seeds.p, s.region.p, s.count.p, s.outcast.p);
+        seed_scan_kernel<<<(unsigned)((b.n_reads + 127) / 128), 128, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, w.feats.p, w.cls.p,
+                                                                              w.attr.p, w.seed_tmp.p, s.region.p, s.count.p);
+        seed_bestk_kernel<<<(unsigned)((s.total_slots * 2 + 127) / 128), 128, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, w.seed_tmp.p, s.region.p, s.count.p, s.total_slots);
+        seed_hitchhike_kernel<<<(unsigned)((b.n_reads + 127) / 128), 128, 0, st>>>(P, b.n_reads, w.seed_tmp.p, s.seeds.p, s.region.p, s.count.p, s.outcast.p);
         nl += 3;
     }
     PBSC_CUDA(cudaGetLastError());
-    PBSC_CUDA(cudaStreamSynchronize(st));
     if (launches) *launches += nl;
     return PBSC_OK;
 }
@@ -426,10 +429,15 @@ extern "C" int pbsc_seed_batch(pbsc_index* idx, const pbsc_params* p, const char
     PBSC_CUDA(cudaSetDevice(idx->device));
     DeviceBatch b;
     SeedBuffers s;
+    Workspace w;
     int rc = upload_reads(idx, reads, offsets, n_reads, b);
     if (rc != PBSC_OK) return rc;
-    rc = run_seed_phase(idx, p, b, s, nullptr);
+    std::vector<uint64_t> h_off(offsets, offsets + n_reads + 1);
+    rc = alloc_seed_workspace(p, h_off, b, s, w, idx->stream);
     if (rc != PBSC_OK) return rc;
+    rc = run_seed_phase(idx, p, b, s, w, nullptr);
+    if (rc != PBSC_OK) return rc;
+    PBSC_CUDA(cudaStreamSynchronize(idx->stream));
     std::vector<uint32_t> cnt(n_reads);
     std::vector<uint64_t> region(n_reads + 1);
     if (n_reads)

@@ -1162,6 +1162,7 @@ struct ReadResult
             exceedDepthNum = 0, exceedLeaveNum = 0, FMNum = 0, DPNum = 0, seedDis = 0;
     SeedVector seeds, outcastSeeds;
     bool outcastWritten = false, seedWritten = false;
+    uint64_t occSeed = 0, occExtend = 0;   // rank queries issued by each phase (roofline numerator)
     std::vector<PairRecord> pairs;
     std::vector<std::pair<std::pair<int,int>,int>> extLog;   // extend/<id>.ext rows
     std::vector<float> ratioLog;
@@ -1286,7 +1287,9 @@ struct Corrector
         std::string readSeq = seq;
         SeedVector seedVec, pieceVec;
         LongReadProbe probe(P);
+        const uint64_t occ0 = OccCounter::n();
         probe.searchSeedsWithHybridKmers(readSeq, seedVec);
+        const uint64_t occ1 = OccCounter::n();
         result.totalSeedNum = seedVec.size();
         result.seeds = seedVec;
         result.outcastSeeds = probe.outcast;
@@ -1294,6 +1297,8 @@ struct Corrector
         result.seedWritten = !((int)readSeq.length() < P.startKmerLen);
         result.ratioLog = probe.ratioLog;
         initCorrect(readSeq, seedVec, pieceVec, result);
+        result.occSeed = occ1 - occ0;
+        result.occExtend = OccCounter::n() - occ1;
         result.merge = !pieceVec.empty();
         result.totalReadsLen = readSeq.length();
         for (const auto& iter : pieceVec) result.correctedStrs.push_back(iter.seedStr);

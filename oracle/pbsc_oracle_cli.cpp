@@ -185,6 +185,9 @@ int main(int argc, char** argv)
                   << "ExceedLeaveNum: " << exceedLeaveNum << ", ratio: " << (float)(exceedLeaveNum * 100) / (DPNum + OutcastNum) << "%\n"
                   << "DisBetweenSeeds: " << seedDis / totalWalkNum << "\n";
     }
-    fprintf(stderr, "[pbsc_oracle] %zu reads, %.3f s, threads %d, rank queries %llu\n", reads.size(), secs, threads, (unsigned long long)occTotal);
+    uint64_t occSeed = 0, occExtend = 0, walkAttempts = 0;
+    for (const auto& r : results) { occSeed += r.occSeed; occExtend += r.occExtend; walkAttempts += r.pairs.size(); }
+    fprintf(stderr, "[pbsc_oracle] %zu reads, %.3f s, threads %d, rank queries %llu (seed %llu, extend %llu), walks %llu\n", reads.size(), secs, threads,
+            (unsigned long long)occTotal, (unsigned long long)occSeed, (unsigned long long)occExtend, (unsigned long long)walkAttempts);
     return 0;
 }
