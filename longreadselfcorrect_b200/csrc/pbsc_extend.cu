@@ -24,8 +24,8 @@ __device__ __forceinline__ unsigned long long warp_next(unsigned long long* coun
     return __shfl_sync(FULL, v, 0);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-extend_pairs_kernel(FmIndexDev idx, ExtParamsDev P, uint8_t* scratch, size_t scratch_stride, unsigned long long* counter,
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+extend_pairs_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t scratch_stride, unsigned long long* counter,
                     uint64_t n_pairs, const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off,
                     const uint8_t* __restrict__ path, const uint64_t* __restrict__ path_off,
                     const uint8_t* __restrict__ trg, const uint64_t* __restrict__ trg_off,
@@ -79,8 +79,8 @@ struct ChainParamsDev
 
 // per-read chain: initCorrect + correctByFMExtension (PacBioSelfCorrectionProcess.cpp:56-206), failed walks take the
 // --nodp branch (:146-153)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-correct_reads_kernel(FmIndexDev idx, ExtParamsDev P, ChainParamsDev C, uint8_t* scratch, size_t scratch_stride,
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+correct_reads_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, ChainParamsDev C, uint8_t* scratch, size_t scratch_stride,
                      unsigned long long* counter, uint64_t n_reads, const uint32_t* __restrict__ order,
                      const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
                      const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region, const uint32_t* __restrict__ seed_count,

@@ -137,11 +137,15 @@ __device__ __forceinline__ void tail_push(uint64_t& rt_hi, uint64_t& rt_lo, int 
     rt_hi = (rt_hi >> 2) | ((uint64_t)c << 62);
 }
 
+// single out-of-line copy of updateInterval for the walk code: the fully inlined kernel was 313 KB of SASS and spent
+// 56% of its stall samples waiting for instructions (profiles/, round 1)
+__device__ __noinline__ Interval update_interval_ool(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
+
 // findInterval of the last K bases of a leaf on one strand (refineSAInterval, LongReadCorrectByOverlap.cpp:355-369):
 //   strand 0: findInterval(RBWT, reverse(w))      processes w[0], w[1], ...
 //   strand 1: findInterval(BWT,  revcomp(w))      processes comp(w[0]), comp(w[1]), ...
 // with w[j] = base at distance K-1-j.  Stops at the first empty interval (BWTAlgorithms.cpp:25-29).
-__device__ __forceinline__ Interval suffix_interval(const FmIndexDev& idx, uint64_t rt_hi, uint64_t rt_lo, int K, int strand)
+__device__ __noinline__ Interval suffix_interval(const FmIndexDev& idx, uint64_t rt_hi, uint64_t rt_lo, int K, int strand)
 {
     const FmTable& t = idx.t[strand == 0 ? PBSC_RBWT : PBSC_BWT];
     Interval iv;
@@ -164,17 +168,18 @@ __device__ __forceinline__ Interval suffix_interval(const FmIndexDev& idx, uint6
         iv = init_interval(t, strand == 0 ? c : 3 - c);
         j = 1;
     }
+    #pragma unroll 1
     for (; j < K; j++)
     {
         const int c = tail_base(rt_hi, rt_lo, K - 1 - j);
-        iv = update_interval(t, iv, strand == 0 ? c : 3 - c);
+        iv = update_interval_ool(t, iv, strand == 0 ? c : 3 - c);
         if (!iv.valid()) break;
     }
     return iv;
 }
 
 // findInterval of a k-mer of the query on one strand, same conventions as suffix_interval
-__device__ __forceinline__ Interval query_interval(const FmIndexDev& idx, const uint8_t* w, int K, int strand)
+__device__ __noinline__ Interval query_interval(const FmIndexDev& idx, const uint8_t* w, int K, int strand)
 {
     const FmTable& t = idx.t[strand == 0 ? PBSC_RBWT : PBSC_BWT];
     Interval iv;
@@ -182,6 +187,7 @@ __device__ __forceinline__ Interval query_interval(const FmIndexDev& idx, const 
     if (idx.prefix != nullptr && K >= idx.k0)
     {
         uint64_t key = 0;
+        #pragma unroll 1
         for (int i = 0; i < idx.k0; i++) key |= (uint64_t)w[i] << (2 * i);
         Interval f, r;
         prefix_lookup(idx, key, f, r);
@@ -194,15 +200,18 @@ __device__ __forceinline__ Interval query_interval(const FmIndexDev& idx, const 
         iv = init_interval(t, strand == 0 ? w[0] : 3 - w[0]);
         j = 1;
     }
+    #pragma unroll 1
     for (; j < K; j++)
     {
-        iv = update_interval(t, iv, strand == 0 ? w[j] : 3 - w[j]);
+        iv = update_interval_ool(t, iv, strand == 0 ? w[j] : 3 - w[j]);
         if (!iv.valid()) break;
     }
     return iv;
 }
 
 struct KeyGreater { __host__ __device__ bool operator()(uint64_t a, uint64_t b) const { return (a >> 32) > (b >> 32); } };
+
+__device__ __noinline__ void sort_desc_ool(uint64_t* a, long n) { stlsort::sort(a, n, KeyGreater()); }
 
 // first index of the run of `key` in an array sorted by key descending; n if absent
 __device__ __forceinline__ uint32_t group_find(const uint64_t* a, uint32_t n, uint32_t key, uint32_t& len)
@@ -241,7 +250,7 @@ __device__ __forceinline__ int ring_alloc_uniform(WarpShared& sh)
 }
 
 // refineSAInterval (LongReadCorrectByOverlap.cpp:355-369) over `cnt` leaves of a bank
-__device__ __forceinline__ void refine_bank(const FmIndexDev& idx, Leaf* bank, uint32_t cnt, int K)
+__device__ __noinline__ void refine_bank(const FmIndexDev& idx, Leaf* bank, uint32_t cnt, int K)
 {
     const int lane = lane_id();
     for (uint32_t it = lane; it < 2 * cnt; it += 32)
@@ -255,12 +264,13 @@ __device__ __forceinline__ void refine_bank(const FmIndexDev& idx, Leaf* bank, u
 }
 
 // SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331)
-__device__ __forceinline__ uint64_t select_freqs(const FmIndexDev& idx, const ExtParamsDev& P, Leaf* bank, uint32_t cnt,
+__device__ __noinline__ uint64_t select_freqs(const FmIndexDev& idx, const ExtParamsDev& P, Leaf* bank, uint32_t cnt,
                                                  uint64_t LB, uint64_t UB)
 {
     const int lane = lane_id();
     const int extra = (int)(UB - LB);     // 0..2 further left extensions
     int mx[3] = {0, 0, 0};
+    #pragma unroll 1
     for (uint32_t base = 0; base < 2 * cnt; base += 32)
     {
         const uint32_t it = base + lane;
@@ -279,6 +289,7 @@ __device__ __forceinline__ uint64_t select_freqs(const FmIndexDev& idx, const Ex
                 // table key x[j] = comp(base at distance j): entry.rvc is the BWT interval after processing
                 // comp(x[j]) = the bases themselves, entry.fwd the RBWT interval after processing x[j] = their complements
                 uint64_t key = 0;
+                #pragma unroll 1
                 for (int j = 0; j < idx.k0; j++) key |= (uint64_t)(3 - tail_base(L.rt_hi, L.rt_lo, j)) << (2 * j);
                 Interval f, r;
                 prefix_lookup(idx, key, f, r);
@@ -291,19 +302,22 @@ __device__ __forceinline__ uint64_t select_freqs(const FmIndexDev& idx, const Ex
                 iv = init_interval(t, strand == 0 ? c : 3 - c);
                 d = 1;
             }
+            #pragma unroll 1
             for (; d < (int)LB && iv.valid(); d++)
             {
                 const int c = tail_base(L.rt_hi, L.rt_lo, d);
-                iv = update_interval(t, iv, strand == 0 ? c : 3 - c);
+                iv = update_interval_ool(t, iv, strand == 0 ? c : 3 - c);
             }
             sz[0] = (int64_t)iv.size();
+            #pragma unroll 1
             for (int e = 1; e <= extra; e++)
             {
                 const int c = tail_base(L.rt_hi, L.rt_lo, (int)LB - 1 + e);
-                if (iv.valid()) iv = update_interval(t, iv, strand == 0 ? c : 3 - c);
+                if (iv.valid()) iv = update_interval_ool(t, iv, strand == 0 ? c : 3 - c);
                 sz[e] = (int64_t)iv.size();
             }
         }
+        #pragma unroll 1
         for (int e = 0; e <= extra; e++)
         {
             int64_t other = __shfl_xor_sync(FULL, sz[e], 1);
@@ -318,7 +332,7 @@ __device__ __forceinline__ uint64_t select_freqs(const FmIndexDev& idx, const Ex
 }
 
 // isInsufficientFreqs (LongReadCorrectByOverlap.cpp:334-352)
-__device__ __forceinline__ bool insufficient_freqs(const ExtParamsDev& P, const Leaf* bank, uint32_t cnt)
+__device__ __noinline__ bool insufficient_freqs(const ExtParamsDev& P, const Leaf* bank, uint32_t cnt)
 {
     const int lane = lane_id();
     uint32_t high = 0;
@@ -335,11 +349,12 @@ __device__ __forceinline__ bool insufficient_freqs(const ExtParamsDev& P, const 
 }
 
 // getFMIndexExtensions' acceptance rule for one leaf (LongReadCorrectByOverlap.cpp:725-781); returns a 4-bit base mask
-__device__ __forceinline__ uint32_t eval_extensions(const WarpShared& sh, uint32_t leaf, uint32_t tailCount, uint64_t cutoffSA)
+__device__ __noinline__ uint32_t eval_extensions(const WarpShared& sh, uint32_t leaf, uint32_t tailCount, uint64_t cutoffSA)
 {
     const int maxfreq = sh.pmax[leaf];
     const uint64_t totalcount = sh.ptotal[leaf];
     uint32_t mask = 0;
+    #pragma unroll 1
     for (int b = 0; b < 4; b++)
     {
         const uint64_t kmerFreq = (uint64_t)(int64_t)sh.pfreq[leaf * 4 + b];
@@ -363,7 +378,7 @@ __device__ __forceinline__ uint32_t eval_extensions(const WarpShared& sh, uint32
 }
 
 // attempToExtend (LongReadCorrectByOverlap.cpp:373-465) + updateLeaves (:468-488).  Returns the number of new leaves.
-__device__ __forceinline__ uint32_t attempt_extend(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
+__device__ __noinline__ uint32_t attempt_extend(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
                                                    WalkState& S, uint64_t thr)
 {
     const int lane = lane_id();
@@ -390,6 +405,7 @@ __device__ __forceinline__ uint32_t attempt_extend(const FmIndexDev& idx, const 
     }
     const uint32_t n = S.n;
     // ---- probes: 8 lanes per leaf = (base, strand) ----
+    #pragma unroll 1
     for (uint32_t base = 0; base < n; base += 4)
     {
         const uint32_t li = base + (lane >> 3);
@@ -401,8 +417,8 @@ __device__ __forceinline__ uint32_t attempt_extend(const FmIndexDev& idx, const 
         {
             const Leaf& L = ws.oldL[li];
             rt_hi = L.rt_hi;
-            if (strand == 0) { iv.lo = L.f_lo; iv.hi = L.f_hi; if (iv.valid()) iv = update_interval(idx.t[PBSC_RBWT], iv, b); }
-            else { iv.lo = L.r_lo; iv.hi = L.r_hi; if (iv.valid()) iv = update_interval(idx.t[PBSC_BWT], iv, 3 - b); }
+            if (strand == 0) { iv.lo = L.f_lo; iv.hi = L.f_hi; if (iv.valid()) iv = update_interval_ool(idx.t[PBSC_RBWT], iv, b); }
+            else { iv.lo = L.r_lo; iv.hi = L.r_hi; if (iv.valid()) iv = update_interval_ool(idx.t[PBSC_BWT], iv, 3 - b); }
             sz = (int64_t)iv.size();
             ProbeIv& pr = ws.probes[li * 4 + b];
             if (strand == 0) { pr.f_lo = iv.lo; pr.f_hi = iv.hi; } else { pr.r_lo = iv.lo; pr.r_hi = iv.hi; }
@@ -454,6 +470,7 @@ __device__ __forceinline__ uint32_t attempt_extend(const FmIndexDev& idx, const 
     {
         if (cnt == 0) ring_free(sh, parent.ring);
         uint32_t j = 0;
+        #pragma unroll 1
         for (int b = 0; b < 4; b++)
         {
             if (!((mask >> b) & 1)) continue;
@@ -493,7 +510,7 @@ __device__ __forceinline__ uint32_t attempt_extend(const FmIndexDev& idx, const 
 }
 
 // PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664)
-__device__ __forceinline__ void prune_by_seed_support(const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh, WalkState& S, uint32_t m)
+__device__ __noinline__ void prune_by_seed_support(const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh, WalkState& S, uint32_t m)
 {
     const int lane = lane_id();
     const uint64_t seedSize = (uint64_t)P.seed_size;
@@ -503,6 +520,7 @@ __device__ __forceinline__ void prune_by_seed_support(const ExtParamsDev& P, War
     const uint64_t smallSeedIdx = currSeedIdx <= indelOffset ? 0 : currSeedIdx - indelOffset;
     const uint64_t largeSeedIdx = (currSeedIdx + indelOffset) >= ((uint64_t)S.qlen - seedSize) ? ((uint64_t)S.qlen - seedSize) : currSeedIdx + indelOffset;
     const uint32_t keyMask = (1u << (2 * P.seed_size)) - 1u;
+    #pragma unroll 1
     for (uint32_t base = 0; base < m; base += 32)
     {
         const uint32_t j = base + lane;
@@ -524,6 +542,7 @@ __device__ __forceinline__ void prune_by_seed_support(const ExtParamsDev& P, War
                 if (rV) gr = group_find(ws.sR, S.n9R, keyMask - keyF, nr);
                 int minIdxDiff = 10000;
                 const uint32_t lim = max(nf, nr);
+                #pragma unroll 1
                 for (uint32_t i = 0; i < lim; i++)
                 {
                     uint64_t v;
@@ -576,9 +595,10 @@ __device__ __forceinline__ void prune_by_seed_support(const ExtParamsDev& P, War
 }
 
 // isTerminated (LongReadCorrectByOverlap.cpp:825-878) over the alive new leaves, in list order
-__device__ __forceinline__ void check_terminated(const ExtParamsDev& P, WarpScratch& ws, WalkState& S, uint32_t m)
+__device__ __noinline__ void check_terminated(const ExtParamsDev& P, WarpScratch& ws, WalkState& S, uint32_t m)
 {
     const int lane = lane_id();
+    #pragma unroll 1
     for (uint32_t base = 0; base < m; base += 32)
     {
         const uint32_t j = base + lane;
@@ -588,6 +608,7 @@ __device__ __forceinline__ void check_terminated(const ExtParamsDev& P, WarpScra
             const Leaf& L = ws.newL[j];
             const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
             first = L.res_first;
+            #pragma unroll 1
             for (int i = max(L.res_second, 0); i < (int)S.nTerm; i++)
             {
                 const Interval tf = ws.termF[i], tr = ws.termR[i];
@@ -628,7 +649,7 @@ __device__ __forceinline__ void check_terminated(const ExtParamsDev& P, WarpScra
 
 // One complete walk.  ws.q[0..qlen) = beginningkmer(k) + strBetweenSrcTarget(dis bases) + targetSeed(trgLen), as 2-bit codes.
 // On success returns 1 and leaves the merged sequence (codes) in ws.merged[0..*mergedLen).
-__device__ inline int walk_pair(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
+__device__ __noinline__ int walk_pair(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
                                 uint32_t qlen, uint32_t k, int32_t dis, uint32_t trgLen, uint64_t minSA, uint32_t* mergedLen)
 {
     const int lane = lane_id();
@@ -684,8 +705,7 @@ __device__ inline int walk_pair(const FmIndexDev& idx, const ExtParamsDev& P, Wa
         ws.c5[p] = (uint16_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6) | (q[p + 4] << 8));
     __syncwarp();
     // the reference sorts each idmer list with std::sort(greater-by-start); start order == key order
-    if (lane == 0) stlsort::sort(ws.sF, (long)S.n9F, KeyGreater());
-    if (lane == 1) stlsort::sort(ws.sR, (long)S.n9R, KeyGreater());
+    if (lane < 2) sort_desc_ool(lane == 0 ? ws.sF : ws.sR, (long)(lane == 0 ? S.n9F : S.n9R));
     // window of curLen = k: positions [max(k - maxIndel, 0), k + maxIndel]
     {
         const int64_t lo = max((int64_t)k - (int64_t)S.maxIndel, (int64_t)0);
