@@ -16,6 +16,9 @@
 namespace pbsc {
 
 constexpr int WARPS_PER_BLOCK = 4;
+#ifndef PBSC_MIN_BLOCKS
+#define PBSC_MIN_BLOCKS 2   // resident blocks per SM the register allocation is capped for
+#endif
 
 __device__ __forceinline__ unsigned long long warp_next(unsigned long long* counter)
 {
@@ -24,7 +27,7 @@ __device__ __forceinline__ unsigned long long warp_next(unsigned long long* coun
     return __shfl_sync(FULL, v, 0);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, PBSC_MIN_BLOCKS)
 extend_pairs_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t scratch_stride, unsigned long long* counter,
                     uint64_t n_pairs, const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off,
                     const uint8_t* __restrict__ path, const uint64_t* __restrict__ path_off,
@@ -79,7 +82,7 @@ struct ChainParamsDev
 
 // per-read chain: initCorrect + correctByFMExtension (PacBioSelfCorrectionProcess.cpp:56-206), failed walks take the
 // --nodp branch (:146-153)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, PBSC_MIN_BLOCKS)
 correct_reads_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, ChainParamsDev C, uint8_t* scratch, size_t scratch_stride,
                      unsigned long long* counter, uint64_t n_reads, const uint32_t* __restrict__ order,
                      const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
