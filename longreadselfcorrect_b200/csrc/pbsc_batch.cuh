@@ -68,6 +68,7 @@ struct Workspace
     int blocks = 0;
     size_t scratch_stride = 0;
     float piece_factor = 1.5f;
+    bool thread_engine = true;
 };
 
 int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b);
@@ -76,6 +77,10 @@ int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBu
 int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w);
 // launches the chain kernel; returns PBSC_ERR_LIMIT when some read overflowed its scratch/piece capacity
 int run_extend_chain(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches);
+// thread-per-walk engine with speculative pair scheduling (pbsc_extend_thread.cu); same outputs in the same buffers
+int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches);
+// PBSC_ENGINE=warp selects the warp-per-read chain kernel, anything else the thread engine
+bool use_thread_engine();
 
 }  // namespace pbsc
 #endif

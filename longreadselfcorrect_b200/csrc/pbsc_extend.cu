@@ -10,6 +10,8 @@
 // Both are persistent: each warp pulls work items from an atomic counter (reads longest first).
 #include <algorithm>
 #include <numeric>
+#include <stdlib.h>
+#include <string.h>
 #include "pbsc_batch.cuh"
 #include "pbsc_walk.cuh"
 
@@ -359,12 +361,19 @@ int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vec
     if ((uint64_t)w.blocks * WARPS_PER_BLOCK > n) w.blocks = (int)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (w.blocks < 1) w.blocks = 1;
     if (w.q_cap == 0) w.q_cap = 2048;
-    if (w.node_cap == 0) w.node_cap = 1u << 15;
     w.merged_cap = (uint32_t)align_up((size_t)(1.2 * (w.q_cap + 10)) + 256, 16);
+    w.thread_engine = use_thread_engine();
+    if (w.node_cap == 0) w.node_cap = w.thread_engine ? (1u << 13) : (1u << 15);
     w.scratch_stride = warp_scratch_bytes(w.q_cap, w.node_cap, w.merged_cap);
-    PBSC_CUDA(w.scratch.alloc(w.scratch_stride * (size_t)w.blocks * WARPS_PER_BLOCK));
+    if (!w.thread_engine) PBSC_CUDA(w.scratch.alloc(w.scratch_stride * (size_t)w.blocks * WARPS_PER_BLOCK));
     PBSC_CUDA(cudaStreamSynchronize(st));
     return PBSC_OK;
+}
+
+bool use_thread_engine()
+{
+    const char* e = getenv("PBSC_ENGINE");
+    return !(e && strcmp(e, "warp") == 0);
 }
 
 int run_extend_chain(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches)

@@ -1,0 +1,495 @@
+// pbsc_extend_thread.cu — FM-extend phase, thread-per-walk engine with speculative pair scheduling.
+//
+// PacBioSelfCorrectionProcess::initCorrect (PacBio/PacBioSelfCorrectionProcess.cpp:56-157) walks the seed pairs of a
+// read in order because the source of walk i+1 is the piece corrected by walk i.  But the only things walk i+1
+// takes from that piece are its last k bases and its length, and they almost always equal what the raw read
+// says (the walk result ends with the target seed itself; SURVEY.md H1 measured 99.9 %).  So:
+//   1. make_spec_tasks_kernel  one task per consecutive seed pair, source taken from the raw seed (speculation)
+//   2. walk_tasks_kernel       every task is an independent walk: one thread each (pbsc_walk_thread.cuh)
+//   3. stitch_kernel           thread per read replays initCorrect in order with the ACTUAL source state; a task whose
+//                              speculated inputs (k, strand swap, source k-mer) match is consumed, otherwise the read
+//                              files one exact request and stalls
+//   4. walk the requests, stitch again, until no read is stalled (also how -n/--next-target > 1 look-aheads run)
+// Results are identical to the sequential chain by construction: a walk is a pure function of its inputs.
+#include <cub/cub.cuh>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include "pbsc_batch.cuh"
+#include "pbsc_walk_thread.cuh"
+
+namespace pbsc {
+
+constexpr int TW_BLOCK = 128;
+#define PBSC_TASK_PENDING (-999)
+
+struct __align__(16) WalkTask
+{
+    uint64_t src_hi, src_lo;   // last k bases of the source piece, newest base in the top two bits of src_hi
+    uint64_t out_off;          // where the merged sequence goes in the output pool
+    uint32_t read;
+    int32_t src_end;           // source.seedEndPos in the raw read
+    int32_t trg_start, trg_len;
+    int32_t k, rtou;
+    int32_t status;
+    uint32_t out_len, out_cap, valid;
+};
+static_assert(sizeof(WalkTask) == 64, "WalkTask must be 64 bytes");
+
+struct ReadState
+{
+    int32_t t, next, started, done, rstatus, firstType;
+    int32_t srcEnd, srcEndBest, srcRepeat;
+    uint32_t nPieces;
+    int64_t srcLen;
+    uint64_t plen;
+    int32_t pending_trg;   // seed index the pending request targets
+    int32_t pad;
+    pbsc_read_stats st;
+};
+
+__device__ __forceinline__ void pack_src(const uint8_t* bases, int k, uint64_t& hi, uint64_t& lo)
+{
+    hi = lo = 0;
+    for (int j = 0; j < k; j++) tail_push(hi, lo, bases[j]);
+}
+
+// extendKmerSize / isFromRtoU of correctByFMExtension (PacBioSelfCorrectionProcess.cpp:163-175)
+__device__ __forceinline__ void pair_inputs(int srcEndBest, int srcRepeat, int64_t srcLen, const pbsc_seed& tg, int start_kmer, int& k, bool& rtou)
+{
+    k = min(srcEndBest, tg.start_best_k) - 2;
+    if (srcRepeat || tg.is_repeat)
+    {
+        k = (int)min(srcLen, (int64_t)tg.len);
+        k = min(k, start_kmer + 2);
+    }
+    rtou = srcRepeat && !tg.is_repeat;
+}
+
+__device__ __forceinline__ uint32_t task_out_cap(int dis, int k, int trgLenWalk)
+{
+    return (uint32_t)((uint64_t)(1.2 * (double)(dis + 10)) + 2 * (uint64_t)k + (uint64_t)trgLenWalk + 24);
+}
+
+// one speculative task per seed t >= 1 of every read: source = raw seed t-1
+__global__ void make_spec_tasks_kernel(uint64_t n_reads, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
+                                       const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
+                                       const uint32_t* __restrict__ seed_count, const uint64_t* __restrict__ task_base,
+                                       WalkTask* __restrict__ tasks, uint64_t* __restrict__ caps, int start_kmer)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const pbsc_seed* sv = seeds + region[r];
+    const uint32_t ns = seed_count[r];
+    const uint8_t* read = codes + offsets[r];
+    for (uint32_t t = 0; t < ns; t++)
+    {
+        WalkTask tk;
+        memset(&tk, 0, sizeof tk);
+        tk.read = (uint32_t)r;
+        if (t >= 1)
+        {
+            const pbsc_seed s = sv[t - 1], tg = sv[t];
+            int k; bool rtou;
+            pair_inputs(s.end_best_k, s.is_repeat, (int64_t)s.len, tg, start_kmer, k, rtou);
+            tk.src_end = s.start + s.len - 1;
+            tk.trg_start = tg.start; tk.trg_len = tg.len;
+            tk.k = k; tk.rtou = rtou ? 1 : 0;
+            tk.status = PBSC_TASK_PENDING;
+            if (k > 0 && k <= s.len && k <= 64)
+            {
+                pack_src(read + s.start + s.len - k, k, tk.src_hi, tk.src_lo);
+                tk.valid = 1;
+                tk.out_cap = task_out_cap(tg.start - tk.src_end - 1, k, rtou ? k : tg.len);
+            }
+        }
+        caps[task_base[r] + t] = tk.out_cap;
+        tasks[task_base[r] + t] = tk;
+    }
+}
+
+__global__ void set_out_offsets_kernel(uint64_t n_tasks, WalkTask* tasks, const uint64_t* off)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n_tasks) tasks[i].out_off = off[i];
+}
+
+// every thread pulls tasks from a queue and walks them
+__global__ void __launch_bounds__(TW_BLOCK)
+walk_tasks_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
+                  unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks,
+                  const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets, uint8_t* outpool, uint64_t minSA,
+                  unsigned long long* walk_counter)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    tw::TScratch ws;
+    tw::carve(scratch + tid * stride, P.q_cap, P.node_cap, ws);
+    unsigned long long done = 0;
+    for (;;)
+    {
+        const unsigned long long it = atomicAdd(counter, 1ull);
+        if (it >= n_items) break;
+        WalkTask& tk = tasks[list ? list[it] : it];
+        if (!tk.valid) continue;
+        const uint8_t* read = codes + offsets[tk.read];
+        const int k = tk.k;
+        const int interval = tk.trg_start - tk.src_end - 1;
+        const uint8_t* pth = read + tk.src_end + 1;
+        const uint8_t* trgS = read + tk.trg_start;
+        int st;
+        uint32_t mlen = 0;
+        uint32_t trgLen, qlen;
+        if (interval < 0 || k <= 0) st = PBSC_WALK_UNSUPPORTED;
+        else
+        {
+            if (!tk.rtou)
+            {
+                trgLen = tk.trg_len; qlen = k + interval + trgLen;
+                if (qlen > P.q_cap) st = PBSC_WALK_OVERFLOW;
+                else
+                {
+                    for (int x = 0; x < k; x++) ws.q[x] = (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - x);
+                    for (int x = 0; x < interval; x++) ws.q[k + x] = pth[x];
+                    for (uint32_t x = 0; x < trgLen; x++) ws.q[k + interval + x] = trgS[x];
+                    st = 0;
+                }
+            }
+            else
+            {
+                // query = revcomp(src_k + path + target[0..k))
+                trgLen = k; qlen = 2 * k + interval;
+                if (qlen > P.q_cap) st = PBSC_WALK_OVERFLOW;
+                else
+                {
+                    for (uint32_t x = 0; x < qlen; x++)
+                    {
+                        const uint32_t y = qlen - 1 - x;
+                        const uint8_t c = y < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - y)
+                                                          : (y < (uint32_t)(k + interval) ? pth[y - k] : trgS[y - k - interval]);
+                        ws.q[x] = 3 - c;
+                    }
+                    st = 0;
+                }
+            }
+            if (st == 0)
+            {
+                st = tw::walk(idx, P, ws, P.node_cap, qlen, (uint32_t)k, interval, trgLen, minSA, outpool + tk.out_off, tk.out_cap, &mlen);
+                done++;
+            }
+        }
+        tk.out_len = st == 1 ? mlen : 0;
+        __threadfence();
+        tk.status = st;
+    }
+    if (done) atomicAdd(walk_counter, done);
+}
+
+struct StitchParams { int32_t start_kmer, next_target, split; };
+
+// thread per read: initCorrect (PacBioSelfCorrectionProcess.cpp:56-157) over finished walk tasks
+__global__ void __launch_bounds__(128)
+stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
+              const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region, const uint32_t* __restrict__ seed_count,
+              const uint64_t* __restrict__ task_base, WalkTask* spec, WalkTask* pending, const uint8_t* __restrict__ outpool,
+              uint64_t pending_pool_off, uint32_t pending_cap, ReadState* states, uint8_t* __restrict__ pieces,
+              const uint64_t* __restrict__ piece_region, uint32_t* __restrict__ piece_bounds, const uint64_t* __restrict__ bounds_region,
+              pbsc_read_stats* __restrict__ stats, int32_t* __restrict__ read_status, uint32_t* stalled_list, unsigned int* n_stalled)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    ReadState S = states[r];
+    if (S.done) return;
+    const uint8_t* read = codes + offsets[r];
+    const int64_t L = (int64_t)(offsets[r + 1] - offsets[r]);
+    const pbsc_seed* sv = seeds + region[r];
+    const uint32_t ns = seed_count[r];
+    uint8_t* piece = pieces + piece_region[r];
+    const uint64_t pieceCap = piece_region[r + 1] - piece_region[r];
+    uint32_t* bounds = piece_bounds + bounds_region[r];
+    const uint64_t boundsCap = bounds_region[r + 1] - bounds_region[r];
+    if (!S.started)
+    {
+        memset(&S, 0, sizeof S);
+        S.started = 1;
+        S.st.total_reads_len = L;
+        S.st.total_seed_num = ns;
+        S.pending_trg = -1;
+        if (ns >= 2)
+        {
+            const pbsc_seed s0 = sv[0];
+            if ((uint64_t)s0.len > pieceCap || boundsCap < 2) S.rstatus = PBSC_WALK_OVERFLOW;
+            else
+            {
+                for (int x = 0; x < s0.len; x++) piece[x] = read[s0.start + x];
+                S.plen = s0.len;
+                bounds[0] = 0;
+            }
+            S.srcLen = s0.len; S.srcEnd = s0.start + s0.len - 1; S.srcEndBest = s0.end_best_k; S.srcRepeat = s0.is_repeat;
+            S.nPieces = 1;
+            S.t = 1; S.next = 0;
+        }
+    }
+    bool stalled = false;
+    if (ns >= 2 && S.rstatus == 0)
+    {
+        while ((uint32_t)S.t < ns)
+        {
+            bool success = false;
+            // S.next > 0 only when resuming inside the look-ahead loop; firstType was saved with it
+            for (; S.next < C.next_target && (uint32_t)(S.t + S.next) < ns; S.next++)
+            {
+                const int ti = S.t + S.next;
+                const pbsc_seed tg = sv[ti];
+                const int interval = tg.start - S.srcEnd - 1;
+                int k; bool rtou;
+                pair_inputs(S.srcEndBest, S.srcRepeat, S.srcLen, tg, C.start_kmer, k, rtou);
+                if (k <= 0 || k > S.srcLen || k > 64 || interval < 0) { S.rstatus = PBSC_WALK_UNSUPPORTED; break; }
+                uint64_t hi, lo;
+                pack_src(piece + S.plen - k, k, hi, lo);
+                // find a finished task with exactly these inputs
+                const WalkTask* use = nullptr;
+                if (S.next == 0)
+                {
+                    const WalkTask* sp = spec + task_base[r] + ti;
+                    if (sp->valid && sp->k == k && sp->rtou == (rtou ? 1 : 0) && sp->src_hi == hi && sp->src_lo == lo && sp->status != PBSC_TASK_PENDING) use = sp;
+                }
+                if (!use)
+                {
+                    WalkTask* pd = pending + r;
+                    if (pd->valid && S.pending_trg == ti && pd->k == k && pd->rtou == (rtou ? 1 : 0) && pd->src_hi == hi && pd->src_lo == lo && pd->src_end == S.srcEnd)
+                    {
+                        if (pd->status != PBSC_TASK_PENDING) use = pd;
+                    }
+                    if (!use)
+                    {
+                        // file the exact request and stall
+                        WalkTask tk;
+                        memset(&tk, 0, sizeof tk);
+                        tk.src_hi = hi; tk.src_lo = lo; tk.read = (uint32_t)r; tk.src_end = S.srcEnd; tk.trg_start = tg.start; tk.trg_len = tg.len;
+                        tk.k = k; tk.rtou = rtou ? 1 : 0; tk.status = PBSC_TASK_PENDING; tk.valid = 1;
+                        tk.out_off = pending_pool_off + r * (uint64_t)pending_cap;
+                        tk.out_cap = pending_cap;
+                        *pd = tk;
+                        S.pending_trg = ti;
+                        stalled = true;
+                        break;
+                    }
+                }
+                const int stw = use->status;
+                if (stw == PBSC_WALK_OVERFLOW || stw == PBSC_WALK_UNSUPPORTED) { S.rstatus = stw; break; }
+                if (S.next == 0) S.firstType = stw;
+                if (stw > 0)
+                {
+                    const uint8_t* merged = outpool + use->out_off;
+                    const uint32_t mlen = use->out_len;
+                    uint64_t outLen;
+                    if (!rtou)
+                    {
+                        outLen = mlen - k;
+                        if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        for (uint64_t x = 0; x < outLen; x++) piece[S.plen + x] = merged[k + x];
+                    }
+                    else
+                    {
+                        const uint64_t tailLen = tg.len - k;
+                        outLen = (mlen - k) + tailLen;
+                        if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        for (uint64_t x = 0; x < mlen - k; x++) piece[S.plen + x] = 3 - merged[mlen - 1 - (k + x)];
+                        for (uint64_t x = 0; x < tailLen; x++) piece[S.plen + (mlen - k) + x] = read[tg.start + k + x];
+                    }
+                    S.plen += outLen;
+                    S.st.corrected_len += outLen;
+                    S.st.seed_dis += interval;
+                    S.st.fm_num++;
+                    S.st.total_walk_num++;
+                    S.srcLen += outLen;
+                    S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat;
+                    S.t += S.next;
+                    success = true;
+                    break;
+                }
+            }
+            if (stalled || S.rstatus) break;
+            if (!success)
+            {
+                const pbsc_seed tg = sv[S.t];
+                if (S.firstType == -1) S.st.high_error_num++;
+                else if (S.firstType == -2) S.st.exceed_depth_num++;
+                else if (S.firstType == -3) S.st.exceed_leave_num++;
+                else { S.rstatus = PBSC_WALK_NO_PATH; break; }
+                S.st.total_walk_num++;
+                if (C.split)
+                {
+                    if (S.plen + tg.len > pieceCap || S.nPieces + 1 >= boundsCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                    bounds[S.nPieces] = (uint32_t)S.plen;
+                    S.nPieces++;
+                    for (int x = 0; x < tg.len; x++) piece[S.plen + x] = read[tg.start + x];
+                    S.plen += tg.len;
+                    S.srcLen = tg.len;
+                }
+                else
+                {
+                    const int tgEnd = tg.start + tg.len - 1;
+                    const uint64_t n = (uint64_t)(tgEnd - S.srcEnd);
+                    if (S.plen + n > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                    for (uint64_t x = 0; x < n; x++) piece[S.plen + x] = read[S.srcEnd + 1 + x];
+                    S.plen += n;
+                    S.srcLen += n;
+                }
+                S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat;
+                S.st.corrected_len += tg.len;
+            }
+            S.t++;
+            S.next = 0;
+            S.firstType = 0;
+        }
+    }
+    if (stalled)
+    {
+        states[r] = S;
+        stalled_list[atomicAdd(n_stalled, 1u)] = (uint32_t)r;
+        return;
+    }
+    S.done = 1;
+    S.st.merge = (ns >= 2) ? 1 : 0;
+    S.st.n_pieces = (int32_t)S.nPieces;
+    if (S.nPieces && S.nPieces < boundsCap) bounds[S.nPieces] = (uint32_t)S.plen;
+    stats[r] = S.st;
+    read_status[r] = S.rstatus;
+    states[r] = S;
+}
+
+void make_ext_params(const pbsc_params* p, ExtParamsDev& d, uint32_t q_cap, uint32_t node_cap, uint32_t merged_cap);
+__global__ void chain_bounds_kernel(uint64_t n_reads, const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
+                                    const uint32_t* __restrict__ seed_count, int next_target, unsigned int* max_gap, unsigned int* max_trg);
+
+static int thread_geometry(int device, int* blocks)
+{
+    cudaDeviceProp prop;
+    PBSC_CUDA(cudaGetDeviceProperties(&prop, device));
+    int per_sm = 0;
+    PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_tasks_kernel, TW_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    const char* e = getenv("PBSC_TW_BLOCKS_PER_SM");
+    if (e && atoi(e) > 0) per_sm = std::min(per_sm, atoi(e));
+    *blocks = prop.multiProcessorCount * per_sm;
+    return PBSC_OK;
+}
+
+// state of the thread engine that lives across the rounds of one batch
+struct ThreadEngine
+{
+    DevBuf<WalkTask> spec, pending;
+    DevBuf<uint64_t> task_base, caps, cap_off;
+    DevBuf<uint8_t> outpool, scratch, cubtmp;
+    DevBuf<ReadState> states;
+    DevBuf<uint32_t> stalled;
+    DevBuf<unsigned int> n_stalled;
+};
+
+static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, Workspace& w, DeviceBatch& b, uint64_t n_items, const uint32_t* list,
+                       WalkTask* tasks, uint64_t minSA, int blocks, size_t stride)
+{
+    cudaStream_t st = idx->stream;
+    PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
+    const uint64_t threads = (uint64_t)blocks * TW_BLOCK;
+    int nb = blocks;
+    if (n_items < threads) nb = (int)((n_items + TW_BLOCK - 1) / TW_BLOCK);
+    if (nb < 1) nb = 1;
+    walk_tasks_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, stride, w.counters.p, n_items, list, tasks, b.codes.p, b.offsets.p,
+                                               E.outpool.p, minSA, w.counters.p + 1);
+    PBSC_CUDA(cudaGetLastError());
+    return PBSC_OK;
+}
+
+int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches)
+{
+    cudaStream_t st = idx->stream;
+    const uint64_t n = b.n_reads;
+    if (n == 0) return PBSC_OK;
+    ThreadEngine E;
+    // ---- task index space: one slot per surviving seed ----
+    PBSC_CUDA(E.task_base.alloc(n + 1));
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, s.count.p, E.task_base.p, (int)n, st);
+        PBSC_CUDA(E.cubtmp.alloc(tb));
+        cub::DeviceScan::ExclusiveSum(E.cubtmp.p, tb, s.count.p, E.task_base.p, (int)n, st);
+    }
+    PBSC_CUDA(cudaMemsetAsync(w.maxima.p, 0, 8, st));
+    chain_bounds_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, s.seeds.p, s.region.p, s.count.p, p->next_target, w.maxima.p, w.maxima.p + 1);
+    uint64_t last_base = 0; uint32_t last_cnt = 0; unsigned int hmax[2] = {0, 0};
+    PBSC_CUDA(cudaMemcpyAsync(&last_base, E.task_base.p + n - 1, 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaMemcpyAsync(&last_cnt, s.count.p + n - 1, 4, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaMemcpyAsync(hmax, w.maxima.p, 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_tasks = last_base + last_cnt;
+    uint64_t nl = 2;
+    // ---- capacities ----
+    const uint32_t need_q = (uint32_t)align_up((size_t)hmax[0] + hmax[1] + 64 + 16, 16);
+    if (need_q > w.q_cap) w.q_cap = need_q;
+    const uint32_t pending_cap = (uint32_t)align_up((size_t)(1.2 * (hmax[0] + 10)) + 2 * 64 + hmax[1] + 64, 16);
+    ExtParamsDev P;
+    make_ext_params(p, P, w.q_cap, w.node_cap, pending_cap);
+    const uint64_t minSA = p->pb_coverage > 60 ? (uint64_t)((p->pb_coverage / 60) * 3) : 3;
+    int blocks = 0;
+    int rc = thread_geometry(idx->device, &blocks);
+    if (rc != PBSC_OK) return rc;
+    const size_t stride = tw::thread_scratch_bytes(w.q_cap, w.node_cap);
+    PBSC_CUDA(E.scratch.alloc(stride * (size_t)blocks * TW_BLOCK));
+    PBSC_CUDA(E.spec.alloc(n_tasks)); PBSC_CUDA(E.pending.alloc(n)); PBSC_CUDA(E.caps.alloc(n_tasks + 1)); PBSC_CUDA(E.cap_off.alloc(n_tasks + 1));
+    PBSC_CUDA(E.states.alloc(n)); PBSC_CUDA(E.stalled.alloc(n)); PBSC_CUDA(E.n_stalled.alloc(1));
+    PBSC_CUDA(cudaMemsetAsync(E.states.p, 0, n * sizeof(ReadState), st));
+    PBSC_CUDA(cudaMemsetAsync(E.pending.p, 0, n * sizeof(WalkTask), st));
+    PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 16, st));
+    uint64_t pool_spec = 0;
+    if (n_tasks)
+    {
+        make_spec_tasks_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, b.codes.p, b.offsets.p, s.seeds.p, s.region.p, s.count.p, E.task_base.p,
+                                                                            E.spec.p, E.caps.p, p->start_kmer);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, E.caps.p, E.cap_off.p, (int)n_tasks, st);
+        if (tb > E.cubtmp.n) PBSC_CUDA(E.cubtmp.alloc(tb));
+        cub::DeviceScan::ExclusiveSum(E.cubtmp.p, tb, E.caps.p, E.cap_off.p, (int)n_tasks, st);
+        set_out_offsets_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, st>>>(n_tasks, E.spec.p, E.cap_off.p);
+        uint64_t lo = 0, lc = 0;
+        PBSC_CUDA(cudaMemcpyAsync(&lo, E.cap_off.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaMemcpyAsync(&lc, E.caps.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaStreamSynchronize(st));
+        pool_spec = lo + lc;
+        nl += 4;
+    }
+    const uint64_t pending_pool_off = align_up(pool_spec, 16);
+    PBSC_CUDA(E.outpool.alloc(pending_pool_off + n * (uint64_t)pending_cap + 16));
+    // ---- round 1: all speculative walks ----
+    if (n_tasks)
+    {
+        rc = launch_walk(idx, P, E, w, b, n_tasks, nullptr, E.spec.p, minSA, blocks, stride);
+        if (rc != PBSC_OK) return rc;
+        nl++;
+    }
+    StitchParams C;
+    C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split;
+    for (int round = 0;; round++)
+    {
+        PBSC_CUDA(cudaMemsetAsync(E.n_stalled.p, 0, 4, st));
+        stitch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(C, n, b.codes.p, b.offsets.p, s.seeds.p, s.region.p, s.count.p, E.task_base.p, E.spec.p,
+                                                                   E.pending.p, E.outpool.p, pending_pool_off, pending_cap, E.states.p, w.pieces.p,
+                                                                   w.piece_region.p, w.bounds.p, w.bounds_region.p, w.stats.p, w.status.p, E.stalled.p,
+                                                                   E.n_stalled.p);
+        nl++;
+        unsigned int ns = 0;
+        PBSC_CUDA(cudaMemcpyAsync(&ns, E.n_stalled.p, 4, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaStreamSynchronize(st));
+        if (ns == 0) break;
+        if (round > 100000) { set_error("stitch did not converge"); return PBSC_ERR_INTERNAL; }
+        // the stalled reads' requests sit in pending[read]
+        rc = launch_walk(idx, P, E, w, b, ns, E.stalled.p, E.pending.p, minSA, blocks, stride);
+        if (rc != PBSC_OK) return rc;
+        nl++;
+    }
+    if (launches) *launches += nl;
+    return PBSC_OK;
+}
+
+}  // namespace pbsc

@@ -66,7 +66,8 @@ int pbsc_batch_run(pbsc_batch* bt, float* ms)
         cudaEventRecord(e[0], st);
         rc = run_seed_phase(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);
         cudaEventRecord(e[1], st);
-        if (rc == PBSC_OK) rc = run_extend_chain(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);
+        if (rc == PBSC_OK) rc = bt->w.thread_engine ? run_extend_threads(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches)
+                                                    : run_extend_chain(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);
         cudaEventRecord(e[2], st);
         if (rc != PBSC_OK) break;
         cudaError_t ce = cudaStreamSynchronize(st);

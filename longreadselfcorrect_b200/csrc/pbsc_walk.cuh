@@ -139,13 +139,13 @@ __device__ __forceinline__ void tail_push(uint64_t& rt_hi, uint64_t& rt_lo, int 
 
 // single out-of-line copy of updateInterval for the walk code: the fully inlined kernel was 313 KB of SASS and spent
 // 56% of its stall samples waiting for instructions (profiles/, round 1)
-__device__ __noinline__ Interval update_interval_ool(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
+static __device__ __noinline__ Interval update_interval_ool(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
 
 // findInterval of the last K bases of a leaf on one strand (refineSAInterval, LongReadCorrectByOverlap.cpp:355-369):
 //   strand 0: findInterval(RBWT, reverse(w))      processes w[0], w[1], ...
 //   strand 1: findInterval(BWT,  revcomp(w))      processes comp(w[0]), comp(w[1]), ...
 // with w[j] = base at distance K-1-j.  Stops at the first empty interval (BWTAlgorithms.cpp:25-29).
-__device__ __noinline__ Interval suffix_interval(const FmIndexDev& idx, uint64_t rt_hi, uint64_t rt_lo, int K, int strand)
+static __device__ __noinline__ Interval suffix_interval(const FmIndexDev& idx, uint64_t rt_hi, uint64_t rt_lo, int K, int strand)
 {
     const FmTable& t = idx.t[strand == 0 ? PBSC_RBWT : PBSC_BWT];
     Interval iv;
@@ -179,7 +179,7 @@ __device__ __noinline__ Interval suffix_interval(const FmIndexDev& idx, uint64_t
 }
 
 // findInterval of a k-mer of the query on one strand, same conventions as suffix_interval
-__device__ __noinline__ Interval query_interval(const FmIndexDev& idx, const uint8_t* w, int K, int strand)
+static __device__ __noinline__ Interval query_interval(const FmIndexDev& idx, const uint8_t* w, int K, int strand)
 {
     const FmTable& t = idx.t[strand == 0 ? PBSC_RBWT : PBSC_BWT];
     Interval iv;
@@ -211,7 +211,7 @@ __device__ __noinline__ Interval query_interval(const FmIndexDev& idx, const uin
 
 struct KeyGreater { __host__ __device__ bool operator()(uint64_t a, uint64_t b) const { return (a >> 32) > (b >> 32); } };
 
-__device__ __noinline__ void sort_desc_ool(uint64_t* a, long n) { stlsort::sort(a, n, KeyGreater()); }
+static __device__ __noinline__ void sort_desc_ool(uint64_t* a, long n) { stlsort::sort(a, n, KeyGreater()); }
 
 // first index of the run of `key` in an array sorted by key descending; n if absent
 __device__ __forceinline__ uint32_t group_find(const uint64_t* a, uint32_t n, uint32_t key, uint32_t& len)
@@ -250,7 +250,7 @@ __device__ __forceinline__ int ring_alloc_uniform(WarpShared& sh)
 }
 
 // refineSAInterval (LongReadCorrectByOverlap.cpp:355-369) over `cnt` leaves of a bank
-__device__ __noinline__ void refine_bank(const FmIndexDev& idx, Leaf* bank, uint32_t cnt, int K)
+static __device__ __noinline__ void refine_bank(const FmIndexDev& idx, Leaf* bank, uint32_t cnt, int K)
 {
     const int lane = lane_id();
     for (uint32_t it = lane; it < 2 * cnt; it += 32)
@@ -264,7 +264,7 @@ __device__ __noinline__ void refine_bank(const FmIndexDev& idx, Leaf* bank, uint
 }
 
 // SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331)
-__device__ __noinline__ uint64_t select_freqs(const FmIndexDev& idx, const ExtParamsDev& P, Leaf* bank, uint32_t cnt,
+static __device__ __noinline__ uint64_t select_freqs(const FmIndexDev& idx, const ExtParamsDev& P, Leaf* bank, uint32_t cnt,
                                                  uint64_t LB, uint64_t UB)
 {
     const int lane = lane_id();
@@ -332,7 +332,7 @@ __device__ __noinline__ uint64_t select_freqs(const FmIndexDev& idx, const ExtPa
 }
 
 // isInsufficientFreqs (LongReadCorrectByOverlap.cpp:334-352)
-__device__ __noinline__ bool insufficient_freqs(const ExtParamsDev& P, const Leaf* bank, uint32_t cnt)
+static __device__ __noinline__ bool insufficient_freqs(const ExtParamsDev& P, const Leaf* bank, uint32_t cnt)
 {
     const int lane = lane_id();
     uint32_t high = 0;
@@ -349,7 +349,7 @@ __device__ __noinline__ bool insufficient_freqs(const ExtParamsDev& P, const Lea
 }
 
 // getFMIndexExtensions' acceptance rule for one leaf (LongReadCorrectByOverlap.cpp:725-781); returns a 4-bit base mask
-__device__ __noinline__ uint32_t eval_extensions(const WarpShared& sh, uint32_t leaf, uint32_t tailCount, uint64_t cutoffSA)
+static __device__ __noinline__ uint32_t eval_extensions(const WarpShared& sh, uint32_t leaf, uint32_t tailCount, uint64_t cutoffSA)
 {
     const int maxfreq = sh.pmax[leaf];
     const uint64_t totalcount = sh.ptotal[leaf];
@@ -378,7 +378,7 @@ __device__ __noinline__ uint32_t eval_extensions(const WarpShared& sh, uint32_t 
 }
 
 // attempToExtend (LongReadCorrectByOverlap.cpp:373-465) + updateLeaves (:468-488).  Returns the number of new leaves.
-__device__ __noinline__ uint32_t attempt_extend(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
+static __device__ __noinline__ uint32_t attempt_extend(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
                                                    WalkState& S, uint64_t thr)
 {
     const int lane = lane_id();
@@ -510,7 +510,7 @@ __device__ __noinline__ uint32_t attempt_extend(const FmIndexDev& idx, const Ext
 }
 
 // PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664)
-__device__ __noinline__ void prune_by_seed_support(const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh, WalkState& S, uint32_t m)
+static __device__ __noinline__ void prune_by_seed_support(const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh, WalkState& S, uint32_t m)
 {
     const int lane = lane_id();
     const uint64_t seedSize = (uint64_t)P.seed_size;
@@ -595,7 +595,7 @@ __device__ __noinline__ void prune_by_seed_support(const ExtParamsDev& P, WarpSc
 }
 
 // isTerminated (LongReadCorrectByOverlap.cpp:825-878) over the alive new leaves, in list order
-__device__ __noinline__ void check_terminated(const ExtParamsDev& P, WarpScratch& ws, WalkState& S, uint32_t m)
+static __device__ __noinline__ void check_terminated(const ExtParamsDev& P, WarpScratch& ws, WalkState& S, uint32_t m)
 {
     const int lane = lane_id();
     #pragma unroll 1
@@ -649,7 +649,7 @@ __device__ __noinline__ void check_terminated(const ExtParamsDev& P, WarpScratch
 
 // One complete walk.  ws.q[0..qlen) = beginningkmer(k) + strBetweenSrcTarget(dis bases) + targetSeed(trgLen), as 2-bit codes.
 // On success returns 1 and leaves the merged sequence (codes) in ws.merged[0..*mergedLen).
-__device__ __noinline__ int walk_pair(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
+static __device__ __noinline__ int walk_pair(const FmIndexDev& idx, const ExtParamsDev& P, WarpScratch& ws, WarpShared& sh,
                                 uint32_t qlen, uint32_t k, int32_t dis, uint32_t trgLen, uint64_t minSA, uint32_t* mergedLen)
 {
     const int lane = lane_id();

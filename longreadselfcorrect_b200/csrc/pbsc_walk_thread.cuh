@@ -1,0 +1,677 @@
+// pbsc_walk_thread.cuh — one FM-index walk per THREAD (scalar restatement of
+// LongReadSelfCorrectByOverlap, PacBio/LongReadCorrectByOverlap.cpp:17-878).
+//
+// Why a second engine: the warp-per-walk engine (pbsc_walk.cuh) spends its time fetching instructions
+// (ncu, profiles/r1: 43-56 % of stall samples are `no_inst`, 246 k warp instructions per walk with 8 of
+// 32 lanes active) because a typical walk has one or two live leaves and ~40 levels: there is no
+// parallelism inside a walk to give to 32 lanes, but there are millions of independent walks.  Here
+// every lane runs its own walk; the loop structure (one level per iteration) is shared by all lanes,
+// and each lane keeps several independent rank sectors in flight.
+//
+// Differences from the warp engine that do not change results:
+//   * the four one-base probes of a leaf read the four counts of ONE sector per interval bound
+//     (occ4): 4 sectors per leaf and level instead of the reference's 16 getOcc calls;
+//   * kmerRatio >= cutoff (LongReadCorrectByOverlap.cpp:740-781) is evaluated as an exact integer
+//     cross-multiplication: for integers 0 <= a <= b < 2^31 and cutoff p/q in {1/8, 1/5, 1/4, 3/10, 3/5, 2}
+//     |a/b - p/q| is either 0 or >= 1/(10 b) >> 2^-53, so fl(a/b) >= fl(p/q) <=> a q >= p b;
+//   * query idmers are looked up in a per-walk hash table; only if the query contains the same idmer
+//     twice (where the reference's std::sort order of equal keys matters) are the validity-filtered
+//     lists built and sorted with the libstdc++ permutation (stl_sort_emul.cuh).
+#ifndef PBSC_WALK_THREAD_CUH
+#define PBSC_WALK_THREAD_CUH
+
+#include "pbsc_walk.cuh"
+
+namespace pbsc {
+namespace tw {
+
+struct TScratch
+{
+    Leaf* oldL; Leaf* newL;
+    double* rings;
+    uint32_t* nodes;
+    WalkResult* res;
+    Interval* termF; Interval* termR;
+    uint8_t* q;
+    uint64_t* hash;
+    uint64_t* sF; uint64_t* sR;
+    uint16_t* c5;
+    uint16_t* win5;
+    uint8_t* ringStack;   // free ring slots
+};
+
+__host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
+
+__host__ __device__ inline size_t thread_scratch_bytes(uint32_t q_cap, uint32_t node_cap)
+{
+    size_t b = 0;
+    b += sizeof(Leaf) * (OLD_CAP + NEW_CAP);
+    b += sizeof(double) * RING_SLOTS * RING_LEN;
+    b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
+    b += sizeof(WalkResult) * RES_CAP;
+    b += sizeof(Interval) * TERM_CAP * 2;
+    b += align_up(q_cap, 16);
+    b += sizeof(uint64_t) * (size_t)pow2_ceil(2 * q_cap);
+    b += sizeof(uint64_t) * (size_t)q_cap * 2;
+    b += align_up(sizeof(uint16_t) * (size_t)q_cap, 16);
+    b += sizeof(uint16_t) * 1024;
+    b += align_up(RING_SLOTS, 16);
+    return align_up(b, 128);
+}
+
+__device__ inline void carve(uint8_t* base, uint32_t q_cap, uint32_t node_cap, TScratch& w)
+{
+    uint8_t* p = base;
+    w.oldL = (Leaf*)p; p += sizeof(Leaf) * OLD_CAP;
+    w.newL = (Leaf*)p; p += sizeof(Leaf) * NEW_CAP;
+    w.rings = (double*)p; p += sizeof(double) * RING_SLOTS * RING_LEN;
+    w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
+    w.res = (WalkResult*)p; p += sizeof(WalkResult) * RES_CAP;
+    w.termF = (Interval*)p; p += sizeof(Interval) * TERM_CAP;
+    w.termR = (Interval*)p; p += sizeof(Interval) * TERM_CAP;
+    w.q = p; p += align_up(q_cap, 16);
+    w.hash = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)pow2_ceil(2 * q_cap);
+    w.sF = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)q_cap;
+    w.sR = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)q_cap;
+    w.c5 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * (size_t)q_cap, 16);
+    w.win5 = (uint16_t*)p; p += sizeof(uint16_t) * 1024;
+    w.ringStack = p;
+}
+
+// occurrences of all four bases in bwt[0, p) from one 32-byte sector
+__device__ __forceinline__ void occ4(const FmTable& t, uint64_t p, uint64_t r[4])
+{
+    PBSC_OCC_TICK(1);
+    const uint64_t blk = p >> 6;
+    const uint32_t off = (uint32_t)p & 63u;
+    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
+    const uint4 cn = __ldg(bp);
+    const uint4 bs = __ldg(bp + 1);
+    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
+    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
+    const uint64_t M = 0x5555555555555555ull;
+    uint64_t k0, k1;   // position masks: one bit per symbol kept
+    if (off < 32) { k0 = ((1ull << (2 * off)) - 1ull) & M; k1 = 0; }
+    else { k0 = M; k1 = ((1ull << (2 * (off - 32))) - 1ull) & M; }
+    const uint64_t l0 = w0 & M, h0 = (w0 >> 1) & M, l1 = w1 & M, h1 = (w1 >> 1) & M;
+    const uint32_t nT = __popcll(h0 & l0 & k0) + __popcll(h1 & l1 & k1);
+    const uint32_t nG = __popcll(h0 & ~l0 & k0) + __popcll(h1 & ~l1 & k1);
+    const uint32_t nC = __popcll(~h0 & l0 & k0) + __popcll(~h1 & l1 & k1);
+    uint32_t nA = off - nT - nG - nC;
+    if ((cn.x >> 31) && off) nA -= count_dollars(t, blk << 6, p);
+    r[0] = (uint64_t)(cn.x & 0x7fffffffu) + nA;
+    r[1] = (uint64_t)cn.y + nC;
+    r[2] = (uint64_t)cn.z + nG;
+    r[3] = (uint64_t)cn.w + nT;
+}
+
+static __device__ __noinline__ Interval update1(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
+
+// both strands of the k-mer w[0..K): fwd = findInterval(RBWT, reverse(w)), rvc = findInterval(BWT, revcomp(w));
+// `get(j)` returns w[j].  The two chains are advanced together so that their sectors are in flight at the same time.
+template <class Get>
+__device__ __forceinline__ void both_strands(const FmIndexDev& idx, Get get, int K, Interval& f, Interval& r)
+{
+    int j;
+    if (idx.prefix != nullptr && K >= idx.k0)
+    {
+        uint64_t key = 0;
+        #pragma unroll 1
+        for (int i = 0; i < idx.k0; i++) key |= (uint64_t)get(i) << (2 * i);
+        prefix_lookup(idx, key, f, r);
+        j = idx.k0;
+    }
+    else
+    {
+        const int c = get(0);
+        f = init_interval(idx.t[PBSC_RBWT], c);
+        r = init_interval(idx.t[PBSC_BWT], 3 - c);
+        j = 1;
+    }
+    #pragma unroll 1
+    for (; j < K && (f.valid() || r.valid()); j++)
+    {
+        const int c = get(j);
+        if (f.valid()) f = update1(idx.t[PBSC_RBWT], f, c);
+        if (r.valid()) r = update1(idx.t[PBSC_BWT], r, 3 - c);
+    }
+}
+
+struct State
+{
+    const FmIndexDev* idx;
+    const ExtParamsDev* P;
+    TScratch s;
+    uint32_t n;
+    uint64_t curLen, curK, maxLength, minLength, maxIndel, minSA;
+    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, node_cap;
+    bool dup;
+    int status;
+};
+
+__device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ringStack[S.nFree++] = (uint8_t)slot; }
+__device__ __forceinline__ int ring_take(State& S) { return S.nFree ? (int)S.s.ringStack[--S.nFree] : -1; }
+
+static __device__ __noinline__ void refine(State& S, Leaf* bank, uint32_t cnt, int K)
+{
+    #pragma unroll 1
+    for (uint32_t i = 0; i < cnt; i++)
+    {
+        const uint64_t hi = bank[i].rt_hi, lo = bank[i].rt_lo;
+        Interval f, r;
+        both_strands(*S.idx, [&](int j) { return tail_base(hi, lo, K - 1 - j); }, K, f, r);
+        bank[i].f_lo = f.lo; bank[i].f_hi = f.hi; bank[i].r_lo = r.lo; bank[i].r_hi = r.hi;
+    }
+}
+
+// SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331)
+static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint32_t cnt, uint64_t LB, uint64_t UB)
+{
+    const FmIndexDev& idx = *S.idx;
+    const int extra = (int)(UB - LB);
+    int mx[3] = {0, 0, 0};
+    #pragma unroll 1
+    for (uint32_t i = 0; i < cnt; i++)
+    {
+        const uint64_t hi = bank[i].rt_hi, lo = bank[i].rt_lo;
+        // Fwdinterval = findInterval(BWT, startkmer): newest base first; Rvcinterval = findInterval(RBWT, complement(startkmer))
+        Interval a, b;   // a on BWT, b on RBWT
+        int d;
+        if (idx.prefix != nullptr && (int)LB >= idx.k0)
+        {
+            uint64_t key = 0;
+            #pragma unroll 1
+            for (int j = 0; j < idx.k0; j++) key |= (uint64_t)(3 - tail_base(hi, lo, j)) << (2 * j);
+            Interval f, r;
+            prefix_lookup(idx, key, f, r);
+            a = r; b = f;
+            d = idx.k0;
+        }
+        else
+        {
+            const int c = tail_base(hi, lo, 0);
+            a = init_interval(idx.t[PBSC_BWT], c);
+            b = init_interval(idx.t[PBSC_RBWT], 3 - c);
+            d = 1;
+        }
+        #pragma unroll 1
+        for (; d < (int)LB && (a.valid() || b.valid()); d++)
+        {
+            const int c = tail_base(hi, lo, d);
+            if (a.valid()) a = update1(idx.t[PBSC_BWT], a, c);
+            if (b.valid()) b = update1(idx.t[PBSC_RBWT], b, 3 - c);
+        }
+        mx[0] = max(mx[0], (int)((int64_t)a.size() + (int64_t)b.size()));
+        #pragma unroll 1
+        for (int e = 1; e <= extra; e++)
+        {
+            const int c = tail_base(hi, lo, (int)LB - 1 + e);
+            if (a.valid()) a = update1(idx.t[PBSC_BWT], a, c);
+            if (b.valid()) b = update1(idx.t[PBSC_RBWT], b, 3 - c);
+            mx[e] = max(mx[e], (int)((int64_t)a.size() + (int64_t)b.size()));
+        }
+    }
+    if (mx[0] - S.P->freq_int[LB] < 5) return LB;
+    for (int e = 1; e <= extra; e++) if (mx[e] - S.P->freq_int[LB + e] < 5) return LB + e;
+    return UB;
+}
+
+// isInsufficientFreqs (LongReadCorrectByOverlap.cpp:334-352)
+__device__ __forceinline__ bool insufficient(const State& S, const Leaf* bank, uint32_t cnt)
+{
+    uint32_t high = 0;
+    for (uint32_t j = 0; j < cnt; j++) high += bank[j].kmerFreq > S.P->high_freq_thr;
+    if (high == 0) return true;
+    if (high <= 2 && cnt >= 5) return true;
+    if (high <= 1 && cnt >= 3) return true;
+    return false;
+}
+
+// acceptance rule of getFMIndexExtensions (LongReadCorrectByOverlap.cpp:725-781) with exact integer ratio tests
+__device__ __forceinline__ uint32_t eval4(const int freq[4], uint64_t totalcount, int maxfreq, uint32_t match5, uint32_t tailCount, uint64_t cutoffSA)
+{
+    uint32_t mask = 0;
+    if (maxfreq <= 0) return 0;   // 0/0 is NaN in the reference: never >= cutoff
+    const bool isHomopolymer = tailCount >= 3;
+    const bool isRepeat = maxfreq > 100, isHighlyRepeat = maxfreq > 150, isLowlyRepeat = maxfreq > 50;
+    const bool isLowCoverage = totalcount >= cutoffSA + 2;
+    #pragma unroll
+    for (int b = 0; b < 4; b++)
+    {
+        const uint64_t kmerFreq = (uint64_t)(int64_t)freq[b];
+        const bool isMatchedBy5mer = (match5 >> b) & 1;
+        const bool isFreqPass = kmerFreq >= cutoffSA;
+        // cutoff as p/q
+        int p, q;
+        if (isMatchedBy5mer && isHighlyRepeat) { p = 1; q = 8; }
+        else if (isMatchedBy5mer && isLowlyRepeat) { p = 1; q = 5; }
+        else if (isFreqPass) { p = 1; q = 4; }
+        else if (isLowCoverage) { p = 3; q = 5; }
+        else { p = 2; q = 1; }
+        // std::max(cutoff, 0.3) / std::max(cutoff, 0.6)
+        if (isHomopolymer && isRepeat) { if (p * 10 < 3 * q) { p = 3; q = 10; } }
+        else if (isHomopolymer) { if (p * 5 < 3 * q) { p = 3; q = 5; } }
+        if ((int64_t)freq[b] * q >= (int64_t)p * maxfreq) mask |= 1u << b;
+    }
+    return mask;
+}
+
+// attempToExtend + getFMIndexExtensions + updateLeaves (LongReadCorrectByOverlap.cpp:373-488, 667-784)
+static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
+{
+    const FmIndexDev& idx = *S.idx;
+    Leaf* oldL = S.s.oldL;
+    Leaf* newL = S.s.newL;
+    double minErr = 1.0;
+    for (uint32_t i = 0; i < S.n; i++) minErr = fmin(minErr, oldL[i].local_err);
+    // drop leaves whose local error rate is far above the best one
+    {
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < S.n; i++)
+        {
+            const double diff = __dsub_rn(oldL[i].local_err, minErr);
+            const bool drop = (diff > 0.05 && S.curLen > (uint64_t)(RING_LEN / 2)) || (diff > 0.1 && S.curLen > 15);
+            if (drop) { ring_release(S, oldL[i].ring); continue; }
+            if (w != i) oldL[w] = oldL[i];
+            w++;
+        }
+        S.n = w;
+    }
+    const uint32_t n = S.n;
+    uint32_t m = 0;
+    #pragma unroll 1
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const Leaf parent = oldL[i];
+        // the eight one-base probes from four sectors
+        uint64_t fl[4], fh[4], rl[4], rh[4];
+        const bool fV = parent.f_hi > parent.f_lo, rV = parent.r_hi > parent.r_lo;
+        if (fV) { occ4(idx.t[PBSC_RBWT], parent.f_lo, fl); occ4(idx.t[PBSC_RBWT], parent.f_hi, fh); }
+        if (rV) { occ4(idx.t[PBSC_BWT], parent.r_lo, rl); occ4(idx.t[PBSC_BWT], parent.r_hi, rh); }
+        int freq[4];
+        Interval pf[4], pr[4];
+        uint64_t total = 0;
+        int mx = 0;
+        uint32_t match5 = 0;
+        #pragma unroll
+        for (int b = 0; b < 4; b++)
+        {
+            if (fV) { pf[b].lo = idx.t[PBSC_RBWT].C[b] + fl[b]; pf[b].hi = idx.t[PBSC_RBWT].C[b] + fh[b]; }
+            else { pf[b].lo = parent.f_lo; pf[b].hi = parent.f_hi; }
+            if (rV) { pr[b].lo = idx.t[PBSC_BWT].C[3 - b] + rl[3 - b]; pr[b].hi = idx.t[PBSC_BWT].C[3 - b] + rh[3 - b]; }
+            else { pr[b].lo = parent.r_lo; pr[b].hi = parent.r_hi; }
+            freq[b] = (int)((int64_t)pf[b].size() + (int64_t)pr[b].size());
+            total += (uint64_t)(int64_t)freq[b];
+            mx = max(mx, freq[b]);
+            const uint32_t code5 = ((uint32_t)b << 8) | (uint32_t)(parent.rt_hi >> 56);
+            if ((pf[b].valid() || pr[b].valid()) && S.s.win5[code5] != 0) match5 |= 1u << b;
+        }
+        uint32_t mask = eval4(freq, total, mx, match5, parent.tailCount, thr);
+        if (!mask && parent.local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, parent.tailCount, thr - 1);
+        if (!mask) continue;
+        const uint32_t cnt = __popc(mask);
+        if (S.nNodes + cnt > S.node_cap) { S.status = PBSC_WALK_OVERFLOW; return 0; }
+        uint32_t j = 0;
+        #pragma unroll 1
+        for (int b = 0; b < 4; b++)
+        {
+            if (!((mask >> b) & 1)) continue;
+            Leaf c = parent;
+            c.f_lo = pf[b].lo; c.f_hi = pf[b].hi; c.r_lo = pr[b].lo; c.r_hi = pr[b].hi;
+            c.kmerFreq = freq[b];
+            tail_push(c.rt_hi, c.rt_lo, b);
+            if (parent.tailLetter == b) c.tailCount = parent.tailCount + 1; else { c.tailLetter = (uint8_t)b; c.tailCount = 1; }
+            c.node = S.nNodes++;
+            S.s.nodes[c.node] = (parent.node << 2) | (uint32_t)b;
+            c.alive = 1;
+            if (j > 0)
+            {
+                // createChild copies both error-rate records (FMIndexWalk/SAINode.cpp:166-189)
+                const int slot = ring_take(S);
+                if (slot < 0) { S.status = PBSC_WALK_OVERFLOW; return 0; }
+                const double* src = S.s.rings + (size_t)parent.ring * RING_LEN;
+                double* dst = S.s.rings + (size_t)slot * RING_LEN;
+                for (int x = 0; x < RING_LEN; x++) dst[x] = src[x];
+                c.ring = (uint16_t)slot;
+            }
+            newL[m++] = c;
+            j++;
+        }
+    }
+    return m;
+}
+
+// first position of the query whose idmer has `key`, from the hash (no duplicate idmers in this query)
+__device__ __forceinline__ int hash_find(const State& S, uint32_t key)
+{
+    uint32_t h = (key * 2654435761u) & S.hashMask;
+    for (;;)
+    {
+        const uint64_t e = S.s.hash[h];
+        if (e == ~0ull) return -1;
+        if ((uint32_t)(e >> 32) == key) return (int)(uint32_t)e;
+        h = (h + 1) & S.hashMask;
+    }
+}
+
+// PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664)
+static __device__ __noinline__ void prune(State& S, uint32_t m)
+{
+    const ExtParamsDev& P = *S.P;
+    const uint64_t seedSize = (uint64_t)P.seed_size;
+    const uint64_t curLen = S.curLen;
+    const uint64_t currSeedIdx = curLen - seedSize;
+    const uint64_t indelOffset = seedSize + S.maxIndel;
+    const uint64_t smallSeedIdx = currSeedIdx <= indelOffset ? 0 : currSeedIdx - indelOffset;
+    const uint64_t largeSeedIdx = (currSeedIdx + indelOffset) >= ((uint64_t)S.qlen - seedSize) ? ((uint64_t)S.qlen - seedSize) : currSeedIdx + indelOffset;
+    const uint32_t keyMask = (1u << (2 * P.seed_size)) - 1u;
+    #pragma unroll 1
+    for (uint32_t j = 0; j < m; j++)
+    {
+        Leaf L = S.s.newL[j];
+        bool found = false;
+        const uint64_t d = curLen - (uint64_t)L.lastOverlapLen;
+        if (d > seedSize || d <= 1)
+        {
+            const uint64_t preSeedIdx = L.lastSeedIdx;
+            const uint64_t seedIdxOffset = (uint64_t)L.lastOverlapLen < curLen - seedSize ? seedSize : curLen - (uint64_t)L.lastOverlapLen;
+            const uint64_t startSeedIdx = max(smallSeedIdx, (uint64_t)L.lastSeedIdx + seedIdxOffset);
+            const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
+            const uint32_t keyF = (uint32_t)(L.rt_hi >> (64 - 2 * P.seed_size));
+            if (!S.dup)
+            {
+                // every idmer of the query is unique: both result lists hold the same single position
+                if (fV || rV)
+                {
+                    const int p = hash_find(S, keyF);
+                    if (p >= 0 && (uint64_t)p >= startSeedIdx && (uint64_t)p <= largeSeedIdx)
+                    {
+                        if (abs(p - (int)currSeedIdx) < 10000) L.lastSeedIdx = (uint32_t)p;   // minIdxDiff starts at 10000 (:580)
+                        L.lastOverlapLen = (uint32_t)curLen;
+                        found = true;
+                    }
+                }
+            }
+            else
+            {
+                uint32_t nf = 0, nr = 0, gf = 0, gr = 0;
+                if (fV) gf = group_find(S.s.sF, S.n9F, keyF, nf);
+                if (rV) gr = group_find(S.s.sR, S.n9R, keyMask - keyF, nr);
+                int minIdxDiff = 10000;
+                const uint32_t lim = max(nf, nr);
+                for (uint32_t i = 0; i < lim; i++)
+                {
+                    uint64_t v = 0;
+                    bool hit = false;
+                    if (i < nf) { v = (uint32_t)S.s.sF[gf + i]; hit = v >= startSeedIdx && v <= largeSeedIdx; }
+                    if (!hit && i < nr) { v = (uint32_t)S.s.sR[gr + i]; hit = v >= startSeedIdx && v <= largeSeedIdx; }
+                    if (hit)
+                    {
+                        const int diff = abs((int)v - (int)currSeedIdx);
+                        if (diff < minIdxDiff) { L.lastSeedIdx = (uint32_t)v; minIdxDiff = diff; }
+                        L.lastOverlapLen = (uint32_t)curLen;
+                        found = true;
+                    }
+                }
+            }
+            if (found)
+            {
+                L.totalSeeds++;
+                if (currSeedIdx + (uint64_t)(int64_t)L.seedOff - preSeedIdx > seedSize) L.redeem = __dadd_rn(L.redeem, P.redeem_a);
+                L.seedOff = (int)L.lastSeedIdx - (int)currSeedIdx;
+            }
+            else
+            {
+                const uint64_t v = currSeedIdx + (uint64_t)(int64_t)L.seedOff - (uint64_t)L.lastSeedIdx;
+                if (v % seedSize == 1) { /* numOfErrors++ : never read */ }
+                else if (v > seedSize - 1) L.redeem = __dadd_rn(L.redeem, P.redeem_b);
+            }
+        }
+        else L.redeem = __dadd_rn(L.redeem, P.redeem_b);
+        // computeErrorRate
+        double matchedLen = __dsub_rn(__dadd_rn((double)L.totalSeeds, (double)seedSize), 1.0);
+        matchedLen = __dadd_rn(matchedLen, L.redeem);
+        const double totalLen = (double)curLen;
+        double err = __ddiv_rn(__dsub_rn(totalLen, matchedLen), totalLen);
+        double* ring = S.s.rings + (size_t)L.ring * RING_LEN;
+        ring[S.level % RING_LEN] = err;
+        L.global_err = err;
+        if (S.level + 1 >= (uint32_t)RING_LEN)
+        {
+            const double old = ring[(S.level + 1) % RING_LEN];
+            err = __ddiv_rn(__dsub_rn(__dmul_rn(err, totalLen), __dmul_rn(old, __dsub_rn(totalLen, (double)RING_LEN))), (double)RING_LEN);
+        }
+        L.local_err = err;
+        if (err > P.walk_error_rate) { L.alive = 0; ring_release(S, L.ring); }
+        S.s.newL[j] = L;
+    }
+}
+
+// isTerminated (LongReadCorrectByOverlap.cpp:825-878)
+static __device__ __noinline__ void terminated(State& S, uint32_t m)
+{
+    #pragma unroll 1
+    for (uint32_t j = 0; j < m; j++)
+    {
+        Leaf& L = S.s.newL[j];
+        if (!L.alive) continue;
+        const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
+        int ilast = -1;
+        #pragma unroll 1
+        for (int i = max(L.res_second, 0); i < (int)S.nTerm; i++)
+        {
+            const Interval tf = S.s.termF[i], tr = S.s.termR[i];
+            const bool ft = fV && tf.valid() && L.f_lo >= tf.lo && L.f_hi <= tf.hi;
+            const bool rt = rV && tr.valid() && L.r_lo >= tr.lo && L.r_hi <= tr.hi;
+            if (ft || rt) ilast = i;
+        }
+        if (ilast < 0) continue;
+        int slot = L.res_first;
+        if (slot == -1)
+        {
+            if (S.nRes >= RES_CAP) { S.status = PBSC_WALK_OVERFLOW; return; }
+            slot = (int)++S.nRes;
+        }
+        WalkResult r; r.err = L.global_err; r.node = L.node; r.i = ilast; r.depth = (uint32_t)S.curLen; r.pad = 0;
+        S.s.res[slot - 1] = r;
+        L.res_first = slot; L.res_second = ilast;
+    }
+}
+
+// One complete walk by one thread.  s.q[0..qlen) holds the query (2-bit codes).  On success returns 1 and writes the merged
+// sequence (codes) to out[0..*outLen).
+static __device__ __noinline__ int walk(const FmIndexDev& idx, const ExtParamsDev& P, const TScratch& scratch, uint32_t node_cap,
+                                 uint32_t qlen, uint32_t k, int32_t dis, uint32_t trgLen, uint64_t minSA,
+                                 uint8_t* out, uint32_t outCap, uint32_t* outLen)
+{
+    State S;
+    S.idx = &idx; S.P = &P; S.s = scratch; S.node_cap = node_cap;
+    S.status = 0;
+    S.qlen = qlen; S.k = k; S.maxOverlap = k + 2; S.trgLen = trgLen; S.minSA = minSA;
+    if (trgLen < (uint32_t)P.min_overlap || k < (uint32_t)P.seed_size || k + 3 > 64 || qlen > P.q_cap || trgLen - P.min_overlap + 1 > TERM_CAP || qlen != k + (uint32_t)dis + trgLen)
+        return PBSC_WALK_UNSUPPORTED;
+    S.maxIndel = dis > 100 ? (uint64_t)__dmul_rn((double)dis, 0.2) : 20;
+    S.maxLength = (uint64_t)__dadd_rn(__dmul_rn(1.2, (double)(dis + 10)), (double)(2 * (uint64_t)k));
+    S.minLength = (uint64_t)__dadd_rn(__dmul_rn(0.8, (double)(dis - 20)), (double)(2 * (uint64_t)k));
+    S.curLen = S.curK = k;
+    S.nTerm = trgLen - P.min_overlap + 1;
+    S.nNodes = 1; S.nRes = 0; S.level = 1;
+    if (S.maxLength + trgLen + 8 > outCap) return PBSC_WALK_OVERFLOW;
+    const uint8_t* q = S.s.q;
+    const uint8_t* trg = q + k + dis;
+    const int s9 = P.seed_size;
+    const uint32_t n9 = qlen - s9 + 1;
+
+    // free ring slots (slot 0 belongs to the root)
+    S.nFree = 0;
+    for (int x = RING_SLOTS - 1; x >= 1; x--) S.s.ringStack[S.nFree++] = (uint8_t)x;
+    // terminal intervals (:82-88)
+    #pragma unroll 1
+    for (uint32_t i = 0; i < S.nTerm; i++)
+    {
+        Interval f, r;
+        const uint8_t* w = trg + i;
+        both_strands(idx, [&](int j) { return (int)w[j]; }, P.min_overlap, f, r);
+        S.s.termF[i] = f; S.s.termR[i] = r;
+    }
+    // query idmers into the hash; a repeated idmer switches to the exact sorted lists
+    S.hashMask = pow2_ceil(2 * n9) - 1;
+    {
+        ulonglong2* hz = reinterpret_cast<ulonglong2*>(S.s.hash);
+        for (uint32_t h = 0; h <= S.hashMask / 2; h++) hz[h] = make_ulonglong2(~0ull, ~0ull);
+    }
+    S.dup = false;
+    {
+        uint32_t key = 0;
+        const uint32_t keyMask = (1u << (2 * s9)) - 1u;
+        for (int j = 0; j < s9 - 1; j++) key |= (uint32_t)q[j] << (2 * (j + 1));   // pre-shifted: completed below
+        #pragma unroll 1
+        for (uint32_t p = 0; p < n9; p++)
+        {
+            key = (key >> 2) | ((uint32_t)q[p + s9 - 1] << (2 * (s9 - 1)));
+            key &= keyMask;
+            uint32_t h = (key * 2654435761u) & S.hashMask;
+            for (;;)
+            {
+                const uint64_t e = S.s.hash[h];
+                if (e == ~0ull) { S.s.hash[h] = ((uint64_t)key << 32) | p; break; }
+                if ((uint32_t)(e >> 32) == key) { S.dup = true; break; }
+                h = (h + 1) & S.hashMask;
+            }
+            if (S.dup) break;
+        }
+    }
+    S.n9F = S.n9R = 0;
+    if (S.dup)
+    {
+        // buildOverlapbyFMindex (:127-152): only idmers with a valid interval on a strand enter that strand's list
+        #pragma unroll 1
+        for (uint32_t p = 0; p < n9; p++)
+        {
+            uint32_t keyF = 0;
+            for (int j = 0; j < s9; j++) keyF |= (uint32_t)q[p + j] << (2 * j);
+            Interval f, r;
+            const uint8_t* w = q + p;
+            both_strands(idx, [&](int j) { return (int)w[j]; }, s9, f, r);
+            if (f.valid()) S.s.sF[S.n9F++] = ((uint64_t)keyF << 32) | p;
+            if (r.valid()) S.s.sR[S.n9R++] = ((uint64_t)(((1u << (2 * s9)) - 1u) - keyF) << 32) | p;
+        }
+        sort_desc_ool(S.s.sF, (long)S.n9F);
+        sort_desc_ool(S.s.sR, (long)S.n9R);
+    }
+    // query 5-mers and the +-maxIndel window around curLen = k
+    S.n5 = qlen >= 5 ? qlen - 4 : 0;
+    for (uint32_t p = 0; p < S.n5; p++) S.s.c5[p] = (uint16_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6) | (q[p + 4] << 8));
+    {
+        uint4* wz = reinterpret_cast<uint4*>(S.s.win5);
+        for (int x = 0; x < 128; x++) wz[x] = make_uint4(0, 0, 0, 0);
+        const int64_t lo = max((int64_t)k - (int64_t)S.maxIndel, (int64_t)0);
+        const int64_t hi = min((int64_t)k + (int64_t)S.maxIndel, (int64_t)S.n5 - 1);
+        for (int64_t p = lo; p <= hi; p++) S.s.win5[S.s.c5[p]]++;
+    }
+    // root leaf (:106-124)
+    {
+        Leaf R;
+        Interval f, r;
+        both_strands(idx, [&](int j) { return (int)q[j]; }, (int)k, f, r);
+        R.f_lo = f.lo; R.f_hi = f.hi; R.r_lo = r.lo; R.r_hi = r.hi;
+        R.redeem = 0; R.local_err = 0; R.global_err = 0;
+        R.rt_hi = R.rt_lo = 0;
+        for (uint32_t j = 0; j < k; j++) tail_push(R.rt_hi, R.rt_lo, q[j]);
+        R.lastOverlapLen = k; R.lastSeedIdx = k - s9; R.totalSeeds = k - s9 + 1; R.seedOff = 0;
+        R.res_first = -1; R.res_second = -1;
+        R.kmerFreq = (int)((int64_t)(R.f_hi - R.f_lo) + (int64_t)(R.r_hi - R.r_lo));
+        R.tailLetter = q[k - 1];
+        uint32_t tc = 0;
+        for (int j = (int)k - 1; j >= 0 && q[j] == R.tailLetter; j--) tc++;
+        R.tailCount = tc;
+        R.node = 0; R.ring = 0; R.alive = 1; R.pad[0] = 0;
+        S.s.oldL[0] = R;
+        S.s.nodes[0] = 0;
+        S.s.rings[0] = 0.0;
+    }
+    S.n = 1;
+
+    // extendOverlap (:155-211)
+    #pragma unroll 1
+    while (S.n > 0 && S.n <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength)
+    {
+        if (S.curK > S.maxOverlap) { refine(S, S.s.oldL, S.n, (int)S.maxOverlap); S.curK = S.maxOverlap; }
+        uint32_t m = attempt(S, S.minSA);
+        if (S.status) return S.status;
+        if (m == 0)
+        {
+            const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
+            const uint64_t R = select_freqs(S, S.s.oldL, S.n, LB, S.curK);
+            refine(S, S.s.oldL, S.n, (int)R);
+            S.curK = R;
+            m = attempt(S, S.minSA);
+            if (S.status) return S.status;
+            if (m == 0) { m = attempt(S, S.minSA - 1); if (S.status) return S.status; }
+        }
+        if (m > 0)
+        {
+            // old leaves are gone: those that were not extended release their ring (children inherited the others)
+            for (uint32_t i = 0; i < S.n; i++)
+            {
+                bool inherited = false;
+                const uint16_t ring = S.s.oldL[i].ring;
+                for (uint32_t j = 0; j < m && !inherited; j++) inherited = S.s.newL[j].ring == ring;
+                if (!inherited) ring_release(S, ring);
+            }
+            S.curLen++;
+            S.curK++;
+            if (insufficient(S, S.s.newL, m))
+            {
+                const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
+                const uint64_t R = select_freqs(S, S.s.newL, m, LB, S.curK);
+                refine(S, S.s.newL, m, (int)R);
+                S.curK = R;
+            }
+            const int64_t add = (int64_t)S.curLen + (int64_t)S.maxIndel;
+            const int64_t rem = (int64_t)S.curLen - 1 - (int64_t)S.maxIndel;
+            if (add < (int64_t)S.n5) S.s.win5[S.s.c5[add]]++;
+            if (rem >= 0 && rem < (int64_t)S.n5) S.s.win5[S.s.c5[rem]]--;
+            prune(S, m);
+            S.level++;
+            if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return S.status; }
+        }
+        uint32_t nn = 0;
+        for (uint32_t j = 0; j < m; j++)
+        {
+            if (!S.s.newL[j].alive) continue;
+            if (nn < OLD_CAP) S.s.oldL[nn] = S.s.newL[j];
+            nn++;
+        }
+        S.n = nn;
+    }
+
+    // findTheBestPath (:214-236)
+    if (S.nRes > 0)
+    {
+        double best = 1.0;
+        int bi = -1;
+        for (uint32_t i = 0; i < S.nRes; i++) { const double e = S.s.res[i].err; if (e < best) { best = e; bi = (int)i; } }
+        if (bi < 0) return PBSC_WALK_NO_PATH;
+        const WalkResult r = S.s.res[bi];
+        const uint32_t chain = r.depth - k;
+        const uint32_t tailFrom = (uint32_t)r.i + P.min_overlap;
+        const uint32_t tailLen = trgLen > (uint32_t)P.min_overlap ? trgLen - tailFrom : 0;
+        const uint32_t len = r.depth + tailLen;
+        if (len > outCap) return PBSC_WALK_OVERFLOW;
+        for (uint32_t x = 0; x < k; x++) out[x] = q[x];
+        for (uint32_t x = 0; x < tailLen; x++) out[r.depth + x] = trg[tailFrom + x];
+        uint32_t node = r.node;
+        for (uint32_t x = 0; x < chain; x++) { const uint32_t v = S.s.nodes[node]; out[r.depth - 1 - x] = (uint8_t)(v & 3); node = v >> 2; }
+        *outLen = len;
+        return 1;
+    }
+    if (S.n == 0) return -1;
+    if (S.curLen > S.maxLength) return -2;
+    if (S.n > (uint32_t)P.max_leaves) return -3;
+    return -4;
+}
+
+}  // namespace tw
+}  // namespace pbsc
+#endif
