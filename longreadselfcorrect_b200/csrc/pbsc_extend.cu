@@ -321,12 +321,12 @@ void make_ext_params(const pbsc_params* p, ExtParamsDev& d, uint32_t q_cap, uint
 
 int launch_geometry(int device, int* blocks)
 {
-    cudaDeviceProp prop;
-    PBSC_CUDA(cudaGetDeviceProperties(&prop, device));
+    int sms = 0;
+    PBSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     int per_sm = 0;
     PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, correct_reads_kernel, WARPS_PER_BLOCK * 32, 0));
     if (per_sm < 1) per_sm = 1;
-    *blocks = prop.multiProcessorCount * per_sm;
+    *blocks = sms * per_sm;
     return PBSC_OK;
 }
 

@@ -75,7 +75,8 @@ __device__ __forceinline__ uint32_t task_out_cap(int dis, int k, int trgLenWalk)
 __global__ void make_spec_tasks_kernel(uint64_t n_reads, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
                                        const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
                                        const uint32_t* __restrict__ seed_count, const uint64_t* __restrict__ task_base,
-                                       WalkTask* __restrict__ tasks, uint64_t* __restrict__ caps, int start_kmer)
+                                       WalkTask* __restrict__ tasks, uint64_t* __restrict__ caps, uint64_t* __restrict__ rec_caps,
+                                       int start_kmer, int min_overlap, int s9)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -104,6 +105,14 @@ __global__ void make_spec_tasks_kernel(uint64_t n_reads, const uint8_t* __restri
             }
         }
         caps[task_base[r] + t] = tk.out_cap;
+        uint64_t rc = 0;
+        if (tk.valid)
+        {
+            const int interval = tk.trg_start - tk.src_end - 1;
+            const uint32_t trgLen = tk.rtou ? (uint32_t)tk.k : (uint32_t)tk.trg_len;
+            rc = tw::setup_record_bytes((uint32_t)(tk.k + interval) + trgLen, trgLen, min_overlap, s9);
+        }
+        rec_caps[task_base[r] + t] = rc;
         tasks[task_base[r] + t] = tk;
     }
 }
@@ -114,72 +123,109 @@ __global__ void set_out_offsets_kernel(uint64_t n_tasks, WalkTask* tasks, const 
     if (i < n_tasks) tasks[i].out_off = off[i];
 }
 
-// every thread pulls tasks from a queue and walks them
+// query of a task: beginningkmer + strBetweenSrcTarget + targetSeed, or its reverse complement when the walk runs from the
+// target towards the source (isFromRtoU, PacBioSelfCorrectionProcess.cpp:176-184)
+__device__ __forceinline__ void task_shape(const WalkTask& tk, int& interval, uint32_t& trgLen, uint32_t& qlen)
+{
+    interval = tk.trg_start - tk.src_end - 1;
+    trgLen = tk.rtou ? (uint32_t)tk.k : (uint32_t)tk.trg_len;
+    qlen = (uint32_t)(tk.k + interval) + trgLen;
+}
+
+__device__ __forceinline__ uint8_t* task_record(const uint32_t* list, uint64_t it, uint8_t* recpool, const uint64_t* rec_off, uint64_t pend_base, uint64_t pend_cap)
+{
+    return list ? recpool + pend_base + (uint64_t)list[it] * pend_cap : recpool + rec_off[it];
+}
+
+// thread per task: everything the constructor of LongReadSelfCorrectByOverlap computes (terminal intervals, query idmer
+// table, query 5-mers, root intervals) goes into the task's setup record
+__global__ void __launch_bounds__(128)
+setup_tasks_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint64_t n_items, const uint32_t* __restrict__ list,
+                   WalkTask* tasks, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets, uint8_t* recpool,
+                   const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap)
+{
+    const uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    WalkTask& tk = tasks[list ? list[it] : it];
+    if (!tk.valid) return;
+    int interval; uint32_t trgLen, qlen;
+    task_shape(tk, interval, trgLen, qlen);
+    if (interval < 0 || tk.k <= 0) { tk.valid = 0; tk.status = PBSC_WALK_UNSUPPORTED; return; }
+    tw::SetupView v;
+    tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
+    const uint8_t* read = codes + offsets[tk.read];
+    const uint8_t* pth = read + tk.src_end + 1;
+    const uint8_t* trgS = read + tk.trg_start;
+    const int k = tk.k;
+    if (!tk.rtou)
+    {
+        for (int x = 0; x < k; x++) v.q[x] = (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - x);
+        for (int x = 0; x < interval; x++) v.q[k + x] = pth[x];
+        for (uint32_t x = 0; x < trgLen; x++) v.q[k + interval + x] = trgS[x];
+    }
+    else
+    {
+        for (uint32_t x = 0; x < qlen; x++)
+        {
+            const uint32_t y = qlen - 1 - x;
+            const uint8_t c = y < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - y)
+                                              : (y < (uint32_t)(k + interval) ? pth[y - k] : trgS[y - k - interval]);
+            v.q[x] = 3 - c;
+        }
+    }
+    tw::setup_task(idx, P, v, qlen, (uint32_t)k, interval, trgLen, tk.out_cap);
+}
+
+// Level loop.  Every lane owns one walk at a time; all lanes of a warp run the same loop (one level of extendOverlap per
+// iteration), and a lane whose walk ended picks the next task at the top of the next iteration, so the warp stays converged
+// at the granularity of a level.
 __global__ void __launch_bounds__(TW_BLOCK)
-walk_tasks_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
-                  unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks,
-                  const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets, uint8_t* outpool, uint64_t minSA,
-                  unsigned long long* walk_counter)
+walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
+                   unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
+                   const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
+                   unsigned long long* walk_counter)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    tw::TScratch ws;
-    tw::carve(scratch + tid * stride, P.q_cap, P.node_cap, ws);
+    tw::TScratch lane;
+    tw::carve(scratch + tid * stride, P.node_cap, lane);
+    tw::State S;
+    S.status = 0; S.n = 0;
+    WalkTask* tk = nullptr;
+    bool active = false, exhausted = false;
     unsigned long long done = 0;
     for (;;)
     {
-        const unsigned long long it = atomicAdd(counter, 1ull);
-        if (it >= n_items) break;
-        WalkTask& tk = tasks[list ? list[it] : it];
-        if (!tk.valid) continue;
-        const uint8_t* read = codes + offsets[tk.read];
-        const int k = tk.k;
-        const int interval = tk.trg_start - tk.src_end - 1;
-        const uint8_t* pth = read + tk.src_end + 1;
-        const uint8_t* trgS = read + tk.trg_start;
-        int st;
-        uint32_t mlen = 0;
-        uint32_t trgLen, qlen;
-        if (interval < 0 || k <= 0) st = PBSC_WALK_UNSUPPORTED;
-        else
+        if (!active && !exhausted)
         {
-            if (!tk.rtou)
+            for (;;)
             {
-                trgLen = tk.trg_len; qlen = k + interval + trgLen;
-                if (qlen > P.q_cap) st = PBSC_WALK_OVERFLOW;
-                else
-                {
-                    for (int x = 0; x < k; x++) ws.q[x] = (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - x);
-                    for (int x = 0; x < interval; x++) ws.q[k + x] = pth[x];
-                    for (uint32_t x = 0; x < trgLen; x++) ws.q[k + interval + x] = trgS[x];
-                    st = 0;
-                }
-            }
-            else
-            {
-                // query = revcomp(src_k + path + target[0..k))
-                trgLen = k; qlen = 2 * k + interval;
-                if (qlen > P.q_cap) st = PBSC_WALK_OVERFLOW;
-                else
-                {
-                    for (uint32_t x = 0; x < qlen; x++)
-                    {
-                        const uint32_t y = qlen - 1 - x;
-                        const uint8_t c = y < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - y)
-                                                          : (y < (uint32_t)(k + interval) ? pth[y - k] : trgS[y - k - interval]);
-                        ws.q[x] = 3 - c;
-                    }
-                    st = 0;
-                }
-            }
-            if (st == 0)
-            {
-                st = tw::walk(idx, P, ws, P.node_cap, qlen, (uint32_t)k, interval, trgLen, minSA, outpool + tk.out_off, tk.out_cap, &mlen);
+                const unsigned long long it = atomicAdd(counter, 1ull);
+                if (it >= n_items) { exhausted = true; break; }
+                tk = &tasks[list ? list[it] : it];
+                if (!tk->valid) continue;
+                int interval; uint32_t trgLen, qlen;
+                task_shape(*tk, interval, trgLen, qlen);
+                tw::SetupView v;
+                tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
+                tw::begin_walk(S, idx, P, lane, v, P.node_cap, minSA);
+                active = true;
                 done++;
+                break;
             }
         }
-        tk.out_len = st == 1 ? mlen : 0;
-        __threadfence();
-        tk.status = st;
+        if (__all_sync(FULL, !active)) break;
+        if (active)
+        {
+            if (tw::walk_continues(S)) tw::one_level(S);
+            if (!tw::walk_continues(S))
+            {
+                uint32_t mlen = 0;
+                const int st = tw::finish_walk(S, outpool + tk->out_off, tk->out_cap, &mlen);
+                tk->out_len = st == 1 ? mlen : 0;
+                tk->status = st;
+                active = false;
+            }
+        }
     }
     if (done) atomicAdd(walk_counter, done);
 }
@@ -363,28 +409,23 @@ void make_ext_params(const pbsc_params* p, ExtParamsDev& d, uint32_t q_cap, uint
 __global__ void chain_bounds_kernel(uint64_t n_reads, const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
                                     const uint32_t* __restrict__ seed_count, int next_target, unsigned int* max_gap, unsigned int* max_trg);
 
-static int thread_geometry(int device, int* blocks)
+// buffers of the thread engine; they live in the index's grow-only arena
+template <class T>
+struct ArenaPtr
 {
-    cudaDeviceProp prop;
-    PBSC_CUDA(cudaGetDeviceProperties(&prop, device));
-    int per_sm = 0;
-    PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_tasks_kernel, TW_BLOCK, 0));
-    if (per_sm < 1) per_sm = 1;
-    const char* e = getenv("PBSC_TW_BLOCKS_PER_SM");
-    if (e && atoi(e) > 0) per_sm = std::min(per_sm, atoi(e));
-    *blocks = prop.multiProcessorCount * per_sm;
-    return PBSC_OK;
-}
-
-// state of the thread engine that lives across the rounds of one batch
+    T* p = nullptr;
+    cudaError_t get(pbsc_index* idx, const char* name, size_t count) { return arena_get(idx, name, (count ? count : 1) * sizeof(T), (void**)&p); }
+};
 struct ThreadEngine
 {
-    DevBuf<WalkTask> spec, pending;
-    DevBuf<uint64_t> task_base, caps, cap_off;
-    DevBuf<uint8_t> outpool, scratch, cubtmp;
-    DevBuf<ReadState> states;
-    DevBuf<uint32_t> stalled;
-    DevBuf<unsigned int> n_stalled;
+    ArenaPtr<WalkTask> spec, pending;
+    ArenaPtr<uint64_t> task_base, caps, cap_off, rec_caps, rec_off;
+    ArenaPtr<uint8_t> outpool, recpool, scratch;
+    DevBuf<uint8_t> cubtmp;
+    ArenaPtr<ReadState> states;
+    ArenaPtr<uint32_t> stalled;
+    ArenaPtr<unsigned int> n_stalled;
+    uint64_t pend_rec_base = 0, pend_rec_cap = 0;
 };
 
 static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, Workspace& w, DeviceBatch& b, uint64_t n_items, const uint32_t* list,
@@ -392,13 +433,37 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
 {
     cudaStream_t st = idx->stream;
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
+    setup_tasks_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, P, n_items, list, tasks, b.codes.p, b.offsets.p, E.recpool.p, E.rec_off.p,
+                                                                         E.pend_rec_base, E.pend_rec_cap);
     const uint64_t threads = (uint64_t)blocks * TW_BLOCK;
     int nb = blocks;
     if (n_items < threads) nb = (int)((n_items + TW_BLOCK - 1) / TW_BLOCK);
     if (nb < 1) nb = 1;
-    walk_tasks_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, stride, w.counters.p, n_items, list, tasks, b.codes.p, b.offsets.p,
-                                               E.outpool.p, minSA, w.counters.p + 1);
+    walk_levels_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
+                                                E.pend_rec_base, E.pend_rec_cap, E.outpool.p, minSA, w.counters.p + 1);
     PBSC_CUDA(cudaGetLastError());
+    return PBSC_OK;
+}
+
+static int thread_geometry(int device, int* blocks)
+{
+    int sms = 0;
+    PBSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int per_sm = 0;
+    PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_levels_kernel, TW_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    const char* e = getenv("PBSC_TW_BLOCKS_PER_SM");
+    if (e && atoi(e) > 0) per_sm = std::min(per_sm, atoi(e));
+    *blocks = sms * per_sm;
+    return PBSC_OK;
+}
+
+static int scan_u64(DevBuf<uint8_t>& tmp, const uint64_t* in, uint64_t* out, uint64_t n, cudaStream_t st)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n, st);
+    if (tb > tmp.n) PBSC_CUDA(tmp.alloc(tb));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, (int)n, st);
     return PBSC_OK;
 }
 
@@ -409,7 +474,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     if (n == 0) return PBSC_OK;
     ThreadEngine E;
     // ---- task index space: one slot per surviving seed ----
-    PBSC_CUDA(E.task_base.alloc(n + 1));
+    PBSC_CUDA(E.task_base.get(idx, "tw.task_base", n + 1));
     {
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, s.count.p, E.task_base.p, (int)n, st);
@@ -429,44 +494,51 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     const uint32_t need_q = (uint32_t)align_up((size_t)hmax[0] + hmax[1] + 64 + 16, 16);
     if (need_q > w.q_cap) w.q_cap = need_q;
     const uint32_t pending_cap = (uint32_t)align_up((size_t)(1.2 * (hmax[0] + 10)) + 2 * 64 + hmax[1] + 64, 16);
+    E.pend_rec_cap = tw::setup_record_bytes(need_q, std::max<uint32_t>(hmax[1], 64), p->min_kmer, p->idmer_len);
     ExtParamsDev P;
     make_ext_params(p, P, w.q_cap, w.node_cap, pending_cap);
     const uint64_t minSA = p->pb_coverage > 60 ? (uint64_t)((p->pb_coverage / 60) * 3) : 3;
     int blocks = 0;
     int rc = thread_geometry(idx->device, &blocks);
     if (rc != PBSC_OK) return rc;
-    const size_t stride = tw::thread_scratch_bytes(w.q_cap, w.node_cap);
-    PBSC_CUDA(E.scratch.alloc(stride * (size_t)blocks * TW_BLOCK));
-    PBSC_CUDA(E.spec.alloc(n_tasks)); PBSC_CUDA(E.pending.alloc(n)); PBSC_CUDA(E.caps.alloc(n_tasks + 1)); PBSC_CUDA(E.cap_off.alloc(n_tasks + 1));
-    PBSC_CUDA(E.states.alloc(n)); PBSC_CUDA(E.stalled.alloc(n)); PBSC_CUDA(E.n_stalled.alloc(1));
+    const size_t stride = tw::thread_scratch_bytes(w.node_cap);
+    PBSC_CUDA(E.scratch.get(idx, "tw.scratch", stride * (size_t)blocks * TW_BLOCK));
+    PBSC_CUDA(E.spec.get(idx, "tw.spec", n_tasks)); PBSC_CUDA(E.pending.get(idx, "tw.pending", n)); PBSC_CUDA(E.caps.get(idx, "tw.caps", n_tasks + 1)); PBSC_CUDA(E.cap_off.get(idx, "tw.cap_off", n_tasks + 1));
+    PBSC_CUDA(E.rec_caps.get(idx, "tw.rec_caps", n_tasks + 1)); PBSC_CUDA(E.rec_off.get(idx, "tw.rec_off", n_tasks + 1));
+    PBSC_CUDA(E.states.get(idx, "tw.states", n)); PBSC_CUDA(E.stalled.get(idx, "tw.stalled", n)); PBSC_CUDA(E.n_stalled.get(idx, "tw.n_stalled", 1));
     PBSC_CUDA(cudaMemsetAsync(E.states.p, 0, n * sizeof(ReadState), st));
     PBSC_CUDA(cudaMemsetAsync(E.pending.p, 0, n * sizeof(WalkTask), st));
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 16, st));
-    uint64_t pool_spec = 0;
+    uint64_t pool_spec = 0, rec_spec = 0;
     if (n_tasks)
     {
         make_spec_tasks_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, b.codes.p, b.offsets.p, s.seeds.p, s.region.p, s.count.p, E.task_base.p,
-                                                                            E.spec.p, E.caps.p, p->start_kmer);
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, E.caps.p, E.cap_off.p, (int)n_tasks, st);
-        if (tb > E.cubtmp.n) PBSC_CUDA(E.cubtmp.alloc(tb));
-        cub::DeviceScan::ExclusiveSum(E.cubtmp.p, tb, E.caps.p, E.cap_off.p, (int)n_tasks, st);
+                                                                            E.spec.p, E.caps.p, E.rec_caps.p, p->start_kmer, p->min_kmer, p->idmer_len);
+        rc = scan_u64(E.cubtmp, E.caps.p, E.cap_off.p, n_tasks, st);
+        if (rc != PBSC_OK) return rc;
+        rc = scan_u64(E.cubtmp, E.rec_caps.p, E.rec_off.p, n_tasks, st);
+        if (rc != PBSC_OK) return rc;
         set_out_offsets_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, st>>>(n_tasks, E.spec.p, E.cap_off.p);
-        uint64_t lo = 0, lc = 0;
-        PBSC_CUDA(cudaMemcpyAsync(&lo, E.cap_off.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
-        PBSC_CUDA(cudaMemcpyAsync(&lc, E.caps.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
+        uint64_t tail[4] = {0, 0, 0, 0};
+        PBSC_CUDA(cudaMemcpyAsync(&tail[0], E.cap_off.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaMemcpyAsync(&tail[1], E.caps.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaMemcpyAsync(&tail[2], E.rec_off.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaMemcpyAsync(&tail[3], E.rec_caps.p + n_tasks - 1, 8, cudaMemcpyDeviceToHost, st));
         PBSC_CUDA(cudaStreamSynchronize(st));
-        pool_spec = lo + lc;
-        nl += 4;
+        pool_spec = tail[0] + tail[1];
+        rec_spec = tail[2] + tail[3];
+        nl += 6;
     }
     const uint64_t pending_pool_off = align_up(pool_spec, 16);
-    PBSC_CUDA(E.outpool.alloc(pending_pool_off + n * (uint64_t)pending_cap + 16));
+    PBSC_CUDA(E.outpool.get(idx, "tw.outpool", pending_pool_off + n * (uint64_t)pending_cap + 16));
+    E.pend_rec_base = align_up(rec_spec, 128);
+    PBSC_CUDA(E.recpool.get(idx, "tw.recpool", E.pend_rec_base + n * E.pend_rec_cap + 128));
     // ---- round 1: all speculative walks ----
     if (n_tasks)
     {
         rc = launch_walk(idx, P, E, w, b, n_tasks, nullptr, E.spec.p, minSA, blocks, stride);
         if (rc != PBSC_OK) return rc;
-        nl++;
+        nl += 2;
     }
     StitchParams C;
     C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split;
@@ -486,7 +558,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         // the stalled reads' requests sit in pending[read]
         rc = launch_walk(idx, P, E, w, b, ns, E.stalled.p, E.pending.p, minSA, blocks, stride);
         if (rc != PBSC_OK) return rc;
-        nl++;
+        nl += 2;
     }
     if (launches) *launches += nl;
     return PBSC_OK;

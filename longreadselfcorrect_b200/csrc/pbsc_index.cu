@@ -335,6 +335,7 @@ int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt
         if (rc == PBSC_OK) rc = upload_strand(idx, w, blocks, dollars, ns[w], nstr[w], total);
     }
     if (rc == PBSC_OK && cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__); }
+    if (rc == PBSC_OK) cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (rc != PBSC_OK) { pbsc_index_destroy(idx); return rc; }
     *out = idx;
     return PBSC_OK;
@@ -439,6 +440,7 @@ int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t
         }
     }
     if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__));
+    cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = idx;
     return PBSC_OK;
 }
@@ -482,6 +484,7 @@ void pbsc_index_destroy(pbsc_index* idx)
     cudaSetDevice(idx->device);
     for (int w = 0; w < 2; w++) { if (idx->d_blocks[w]) cudaFree(idx->d_blocks[w]); if (idx->d_dollar[w]) cudaFree(idx->d_dollar[w]); }
     if (idx->d_prefix) cudaFree(idx->d_prefix);
+    for (auto& kv : idx->arena) if (kv.second.p) cudaFree(kv.second.p);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
 }

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/pbsc.h"
@@ -21,6 +22,11 @@ struct pbsc_index
     uint64_t n_symbols[2] = {0, 0}, n_strings[2] = {0, 0}, n_blocks[2] = {0, 0};
     size_t device_bytes = 0;
     cudaStream_t stream = nullptr;
+    int sm_count = 0;   // cached: cudaGetDeviceProperties costs tens of milliseconds
+    // named scratch buffers that survive across batches (grow-only), so that the hot path does not pay
+    // cudaMalloc/cudaFree of gigabytes per batch; one batch runs at a time per index
+    struct ArenaBuf { void* p = nullptr; size_t cap = 0; };
+    std::map<std::string, ArenaBuf> arena;
 };
 
 namespace pbsc {
@@ -51,6 +57,23 @@ struct DevBuf
         return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
     }
 };
+
+// grow-only named device buffer owned by the index
+inline cudaError_t arena_get(pbsc_index* idx, const char* name, size_t bytes, void** out)
+{
+    pbsc_index::ArenaBuf& a = idx->arena[name];
+    if (a.cap < bytes || a.p == nullptr)
+    {
+        if (a.p) cudaFree(a.p);
+        a.p = nullptr; a.cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&a.p, want);
+        if (e != cudaSuccess) return e;
+        a.cap = want;
+    }
+    *out = a.p;
+    return cudaSuccess;
+}
 
 struct Timing
 {

@@ -42,24 +42,18 @@ struct TScratch
 
 __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
-__host__ __device__ inline size_t thread_scratch_bytes(uint32_t q_cap, uint32_t node_cap)
+__host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap)
 {
     size_t b = 0;
     b += sizeof(Leaf) * (OLD_CAP + NEW_CAP);
     b += sizeof(double) * RING_SLOTS * RING_LEN;
     b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     b += sizeof(WalkResult) * RES_CAP;
-    b += sizeof(Interval) * TERM_CAP * 2;
-    b += align_up(q_cap, 16);
-    b += sizeof(uint64_t) * (size_t)pow2_ceil(2 * q_cap);
-    b += sizeof(uint64_t) * (size_t)q_cap * 2;
-    b += align_up(sizeof(uint16_t) * (size_t)q_cap, 16);
-    b += sizeof(uint16_t) * 1024;
     b += align_up(RING_SLOTS, 16);
     return align_up(b, 128);
 }
 
-__device__ inline void carve(uint8_t* base, uint32_t q_cap, uint32_t node_cap, TScratch& w)
+__device__ inline void carve(uint8_t* base, uint32_t node_cap, TScratch& w)
 {
     uint8_t* p = base;
     w.oldL = (Leaf*)p; p += sizeof(Leaf) * OLD_CAP;
@@ -67,15 +61,8 @@ __device__ inline void carve(uint8_t* base, uint32_t q_cap, uint32_t node_cap, T
     w.rings = (double*)p; p += sizeof(double) * RING_SLOTS * RING_LEN;
     w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     w.res = (WalkResult*)p; p += sizeof(WalkResult) * RES_CAP;
-    w.termF = (Interval*)p; p += sizeof(Interval) * TERM_CAP;
-    w.termR = (Interval*)p; p += sizeof(Interval) * TERM_CAP;
-    w.q = p; p += align_up(q_cap, 16);
-    w.hash = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)pow2_ceil(2 * q_cap);
-    w.sF = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)q_cap;
-    w.sR = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)q_cap;
-    w.c5 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * (size_t)q_cap, 16);
-    w.win5 = (uint16_t*)p; p += sizeof(uint16_t) * 1024;
     w.ringStack = p;
+    w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.c5 = nullptr; w.win5 = nullptr;
 }
 
 // occurrences of all four bases in bwt[0, p) from one 32-byte sector
@@ -144,13 +131,18 @@ struct State
     TScratch s;
     uint32_t n;
     uint64_t curLen, curK, maxLength, minLength, maxIndel, minSA;
-    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, node_cap;
+    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, nFresh, node_cap;
     bool dup;
     int status;
 };
 
 __device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ringStack[S.nFree++] = (uint8_t)slot; }
-__device__ __forceinline__ int ring_take(State& S) { return S.nFree ? (int)S.s.ringStack[--S.nFree] : -1; }
+// released slots first, then slots never used by this walk (slot 0 is the root's)
+__device__ __forceinline__ int ring_take(State& S)
+{
+    if (S.nFree) return (int)S.s.ringStack[--S.nFree];
+    return S.nFresh < (uint32_t)RING_SLOTS ? (int)S.nFresh++ : -1;
+}
 
 static __device__ __noinline__ void refine(State& S, Leaf* bank, uint32_t cnt, int K)
 {
@@ -256,6 +248,8 @@ __device__ __forceinline__ uint32_t eval4(const int freq[4], uint64_t totalcount
     return mask;
 }
 
+__device__ __forceinline__ bool match5_window(const State& S, uint32_t code5);
+
 // attempToExtend + getFMIndexExtensions + updateLeaves (LongReadCorrectByOverlap.cpp:373-488, 667-784)
 static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
 {
@@ -304,7 +298,7 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
             total += (uint64_t)(int64_t)freq[b];
             mx = max(mx, freq[b]);
             const uint32_t code5 = ((uint32_t)b << 8) | (uint32_t)(parent.rt_hi >> 56);
-            if ((pf[b].valid() || pr[b].valid()) && S.s.win5[code5] != 0) match5 |= 1u << b;
+            if ((pf[b].valid() || pr[b].valid()) && match5_window(S, code5)) match5 |= 1u << b;
         }
         uint32_t mask = eval4(freq, total, mx, match5, parent.tailCount, thr);
         if (!mask && parent.local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, parent.tailCount, thr - 1);
@@ -478,71 +472,115 @@ static __device__ __noinline__ void terminated(State& S, uint32_t m)
     }
 }
 
-// One complete walk by one thread.  s.q[0..qlen) holds the query (2-bit codes).  On success returns 1 and writes the merged
-// sequence (codes) to out[0..*outLen).
-static __device__ __noinline__ int walk(const FmIndexDev& idx, const ExtParamsDev& P, const TScratch& scratch, uint32_t node_cap,
-                                 uint32_t qlen, uint32_t k, int32_t dis, uint32_t trgLen, uint64_t minSA,
-                                 uint8_t* out, uint32_t outCap, uint32_t* outLen)
+// ------------------------------------------------------------------------------------------------------------
+// Per-task setup record, produced once by setup_tasks_kernel and read by the level loop.  Everything in
+// LongReadSelfCorrectByOverlap's constructor (LongReadCorrectByOverlap.cpp:17-95,106-152) lands here.
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(16) SetupHdr
 {
-    State S;
-    S.idx = &idx; S.P = &P; S.s = scratch; S.node_cap = node_cap;
-    S.status = 0;
-    S.qlen = qlen; S.k = k; S.maxOverlap = k + 2; S.trgLen = trgLen; S.minSA = minSA;
-    if (trgLen < (uint32_t)P.min_overlap || k < (uint32_t)P.seed_size || k + 3 > 64 || qlen > P.q_cap || trgLen - P.min_overlap + 1 > TERM_CAP || qlen != k + (uint32_t)dis + trgLen)
-        return PBSC_WALK_UNSUPPORTED;
-    S.maxIndel = dis > 100 ? (uint64_t)__dmul_rn((double)dis, 0.2) : 20;
-    S.maxLength = (uint64_t)__dadd_rn(__dmul_rn(1.2, (double)(dis + 10)), (double)(2 * (uint64_t)k));
-    S.minLength = (uint64_t)__dadd_rn(__dmul_rn(0.8, (double)(dis - 20)), (double)(2 * (uint64_t)k));
-    S.curLen = S.curK = k;
-    S.nTerm = trgLen - P.min_overlap + 1;
-    S.nNodes = 1; S.nRes = 0; S.level = 1;
-    if (S.maxLength + trgLen + 8 > outCap) return PBSC_WALK_OVERFLOW;
-    const uint8_t* q = S.s.q;
+    uint64_t rf_lo, rf_hi, rr_lo, rr_hi;   // root fwd / rvc intervals
+    uint64_t maxLength, minLength, maxIndel;
+    uint32_t qlen, k, trgLen, nTerm, n5, hashMask, n9F, n9R;
+    int32_t dis;
+    uint32_t dup;
+    int32_t status0;    // 0, PBSC_WALK_UNSUPPORTED or PBSC_WALK_OVERFLOW decided before any walking
+    uint32_t pad;
+};
+static_assert(sizeof(SetupHdr) % 16 == 0, "SetupHdr must keep 16-byte alignment");
+
+struct SetupView
+{
+    SetupHdr* hdr;
+    uint8_t* q;
+    uint16_t* c5;
+    Interval* termF; Interval* termR;
+    uint64_t* hash;
+    uint64_t* sF; uint64_t* sR;
+};
+
+__host__ __device__ inline size_t setup_record_bytes(uint32_t qlen, uint32_t trgLen, int min_overlap, int s9)
+{
+    const uint32_t nTerm = trgLen >= (uint32_t)min_overlap ? trgLen - min_overlap + 1 : 0;
+    const uint32_t n9 = qlen >= (uint32_t)s9 ? qlen - s9 + 1 : 0;
+    size_t b = sizeof(SetupHdr);
+    b += align_up(qlen, 16);
+    b += align_up(sizeof(uint16_t) * (size_t)qlen, 16);
+    b += sizeof(Interval) * (size_t)nTerm * 2;
+    b += sizeof(uint64_t) * (size_t)pow2_ceil(2 * (n9 ? n9 : 1));
+    b += sizeof(uint64_t) * (size_t)n9 * 2;
+    return align_up(b, 128);
+}
+
+__device__ inline void setup_view(uint8_t* base, uint32_t qlen, uint32_t trgLen, int min_overlap, int s9, SetupView& v)
+{
+    const uint32_t nTerm = trgLen >= (uint32_t)min_overlap ? trgLen - min_overlap + 1 : 0;
+    const uint32_t n9 = qlen >= (uint32_t)s9 ? qlen - s9 + 1 : 0;
+    uint8_t* p = base;
+    v.hdr = (SetupHdr*)p; p += sizeof(SetupHdr);
+    v.q = p; p += align_up(qlen, 16);
+    v.c5 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * (size_t)qlen, 16);
+    v.termF = (Interval*)p; p += sizeof(Interval) * (size_t)nTerm;
+    v.termR = (Interval*)p; p += sizeof(Interval) * (size_t)nTerm;
+    v.hash = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)pow2_ceil(2 * (n9 ? n9 : 1));
+    v.sF = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)n9;
+    v.sR = (uint64_t*)p;
+}
+
+// v.q[0..qlen) already holds the query.  Fills the rest of the record.
+static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtParamsDev& P, SetupView& v, uint32_t qlen, uint32_t k, int32_t dis,
+                                               uint32_t trgLen, uint32_t outCap)
+{
+    SetupHdr H;
+    memset(&H, 0, sizeof H);
+    H.qlen = qlen; H.k = k; H.trgLen = trgLen; H.dis = dis;
+    if (trgLen < (uint32_t)P.min_overlap || k < (uint32_t)P.seed_size || k + 3 > 64 || trgLen - P.min_overlap + 1 > TERM_CAP || qlen != k + (uint32_t)dis + trgLen)
+    { H.status0 = PBSC_WALK_UNSUPPORTED; *v.hdr = H; return; }
+    // LongReadCorrectByOverlap.cpp:54-58,77-79
+    H.maxIndel = dis > 100 ? (uint64_t)__dmul_rn((double)dis, 0.2) : 20;
+    H.maxLength = (uint64_t)__dadd_rn(__dmul_rn(1.2, (double)(dis + 10)), (double)(2 * (uint64_t)k));
+    H.minLength = (uint64_t)__dadd_rn(__dmul_rn(0.8, (double)(dis - 20)), (double)(2 * (uint64_t)k));
+    H.nTerm = trgLen - P.min_overlap + 1;
+    if (H.maxLength + trgLen + 8 > outCap) { H.status0 = PBSC_WALK_OVERFLOW; *v.hdr = H; return; }
+    const uint8_t* q = v.q;
     const uint8_t* trg = q + k + dis;
     const int s9 = P.seed_size;
     const uint32_t n9 = qlen - s9 + 1;
-
-    // free ring slots (slot 0 belongs to the root)
-    S.nFree = 0;
-    for (int x = RING_SLOTS - 1; x >= 1; x--) S.s.ringStack[S.nFree++] = (uint8_t)x;
     // terminal intervals (:82-88)
     #pragma unroll 1
-    for (uint32_t i = 0; i < S.nTerm; i++)
+    for (uint32_t i = 0; i < H.nTerm; i++)
     {
         Interval f, r;
         const uint8_t* w = trg + i;
         both_strands(idx, [&](int j) { return (int)w[j]; }, P.min_overlap, f, r);
-        S.s.termF[i] = f; S.s.termR[i] = r;
+        v.termF[i] = f; v.termR[i] = r;
     }
-    // query idmers into the hash; a repeated idmer switches to the exact sorted lists
-    S.hashMask = pow2_ceil(2 * n9) - 1;
+    // query idmers into the hash; a repeated idmer switches this walk to the exact sorted lists
+    H.hashMask = pow2_ceil(2 * n9) - 1;
     {
-        ulonglong2* hz = reinterpret_cast<ulonglong2*>(S.s.hash);
-        for (uint32_t h = 0; h <= S.hashMask / 2; h++) hz[h] = make_ulonglong2(~0ull, ~0ull);
+        ulonglong2* hz = reinterpret_cast<ulonglong2*>(v.hash);
+        for (uint32_t h = 0; h <= H.hashMask / 2; h++) hz[h] = make_ulonglong2(~0ull, ~0ull);
     }
-    S.dup = false;
+    bool dup = false;
     {
         uint32_t key = 0;
         const uint32_t keyMask = (1u << (2 * s9)) - 1u;
-        for (int j = 0; j < s9 - 1; j++) key |= (uint32_t)q[j] << (2 * (j + 1));   // pre-shifted: completed below
+        for (int j = 0; j < s9 - 1; j++) key |= (uint32_t)q[j] << (2 * (j + 1));
         #pragma unroll 1
-        for (uint32_t p = 0; p < n9; p++)
+        for (uint32_t p = 0; p < n9 && !dup; p++)
         {
-            key = (key >> 2) | ((uint32_t)q[p + s9 - 1] << (2 * (s9 - 1)));
-            key &= keyMask;
-            uint32_t h = (key * 2654435761u) & S.hashMask;
+            key = ((key >> 2) | ((uint32_t)q[p + s9 - 1] << (2 * (s9 - 1)))) & keyMask;
+            uint32_t h = (key * 2654435761u) & H.hashMask;
             for (;;)
             {
-                const uint64_t e = S.s.hash[h];
-                if (e == ~0ull) { S.s.hash[h] = ((uint64_t)key << 32) | p; break; }
-                if ((uint32_t)(e >> 32) == key) { S.dup = true; break; }
-                h = (h + 1) & S.hashMask;
+                const uint64_t e = v.hash[h];
+                if (e == ~0ull) { v.hash[h] = ((uint64_t)key << 32) | p; break; }
+                if ((uint32_t)(e >> 32) == key) { dup = true; break; }
+                h = (h + 1) & H.hashMask;
             }
-            if (S.dup) break;
         }
     }
-    S.n9F = S.n9R = 0;
-    if (S.dup)
+    H.dup = dup ? 1 : 0;
+    if (dup)
     {
         // buildOverlapbyFMindex (:127-152): only idmers with a valid interval on a strand enter that strand's list
         #pragma unroll 1
@@ -553,100 +591,140 @@ static __device__ __noinline__ int walk(const FmIndexDev& idx, const ExtParamsDe
             Interval f, r;
             const uint8_t* w = q + p;
             both_strands(idx, [&](int j) { return (int)w[j]; }, s9, f, r);
-            if (f.valid()) S.s.sF[S.n9F++] = ((uint64_t)keyF << 32) | p;
-            if (r.valid()) S.s.sR[S.n9R++] = ((uint64_t)(((1u << (2 * s9)) - 1u) - keyF) << 32) | p;
+            if (f.valid()) v.sF[H.n9F++] = ((uint64_t)keyF << 32) | p;
+            if (r.valid()) v.sR[H.n9R++] = ((uint64_t)(((1u << (2 * s9)) - 1u) - keyF) << 32) | p;
         }
-        sort_desc_ool(S.s.sF, (long)S.n9F);
-        sort_desc_ool(S.s.sR, (long)S.n9R);
+        sort_desc_ool(v.sF, (long)H.n9F);
+        sort_desc_ool(v.sR, (long)H.n9R);
     }
-    // query 5-mers and the +-maxIndel window around curLen = k
-    S.n5 = qlen >= 5 ? qlen - 4 : 0;
-    for (uint32_t p = 0; p < S.n5; p++) S.s.c5[p] = (uint16_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6) | (q[p + 4] << 8));
+    // query 5-mers, newest base most significant
+    H.n5 = qlen >= 5 ? qlen - 4 : 0;
+    for (uint32_t p = 0; p < H.n5; p++) v.c5[p] = (uint16_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6) | (q[p + 4] << 8));
+    // root intervals (:106-124)
     {
-        uint4* wz = reinterpret_cast<uint4*>(S.s.win5);
-        for (int x = 0; x < 128; x++) wz[x] = make_uint4(0, 0, 0, 0);
-        const int64_t lo = max((int64_t)k - (int64_t)S.maxIndel, (int64_t)0);
-        const int64_t hi = min((int64_t)k + (int64_t)S.maxIndel, (int64_t)S.n5 - 1);
-        for (int64_t p = lo; p <= hi; p++) S.s.win5[S.s.c5[p]]++;
-    }
-    // root leaf (:106-124)
-    {
-        Leaf R;
         Interval f, r;
         both_strands(idx, [&](int j) { return (int)q[j]; }, (int)k, f, r);
-        R.f_lo = f.lo; R.f_hi = f.hi; R.r_lo = r.lo; R.r_hi = r.hi;
-        R.redeem = 0; R.local_err = 0; R.global_err = 0;
-        R.rt_hi = R.rt_lo = 0;
-        for (uint32_t j = 0; j < k; j++) tail_push(R.rt_hi, R.rt_lo, q[j]);
-        R.lastOverlapLen = k; R.lastSeedIdx = k - s9; R.totalSeeds = k - s9 + 1; R.seedOff = 0;
-        R.res_first = -1; R.res_second = -1;
-        R.kmerFreq = (int)((int64_t)(R.f_hi - R.f_lo) + (int64_t)(R.r_hi - R.r_lo));
-        R.tailLetter = q[k - 1];
-        uint32_t tc = 0;
-        for (int j = (int)k - 1; j >= 0 && q[j] == R.tailLetter; j--) tc++;
-        R.tailCount = tc;
-        R.node = 0; R.ring = 0; R.alive = 1; R.pad[0] = 0;
-        S.s.oldL[0] = R;
-        S.s.nodes[0] = 0;
-        S.s.rings[0] = 0.0;
+        H.rf_lo = f.lo; H.rf_hi = f.hi; H.rr_lo = r.lo; H.rr_hi = r.hi;
     }
-    S.n = 1;
+    *v.hdr = H;
+}
 
-    // extendOverlap (:155-211)
-    #pragma unroll 1
-    while (S.n > 0 && S.n <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength)
+// ismatchedbykmer (LongReadCorrectByOverlap.cpp:787-821): any query 5-mer equal to `code5` starting within curLen +- maxIndel
+__device__ __forceinline__ bool match5_window(const State& S, uint32_t code5)
+{
+    const int64_t lo = max((int64_t)S.curLen - (int64_t)S.maxIndel, (int64_t)0);
+    const int64_t hi = min((int64_t)S.curLen + (int64_t)S.maxIndel, (int64_t)S.n5 - 1);
+    if (hi < lo) return false;
+    const uint32_t pat = code5 | (code5 << 16);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(S.s.c5);   // c5 is 16-byte aligned
+    uint32_t hit = 0;
+    int64_t p = lo;
+    if (p & 1) { hit |= (S.s.c5[p] == (uint16_t)code5); p++; }
+    for (; p + 1 <= hi; p += 2) hit |= __vcmpeq2(w[p >> 1], pat);
+    if (p <= hi) hit |= (S.s.c5[p] == (uint16_t)code5);
+    return hit != 0;
+}
+
+// start a walk from its setup record
+__device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, const ExtParamsDev& P, const TScratch& lane_scratch, const SetupView& v,
+                                           uint32_t node_cap, uint64_t minSA)
+{
+    const SetupHdr H = *v.hdr;
+    S.idx = &idx; S.P = &P; S.s = lane_scratch; S.node_cap = node_cap;
+    S.s.q = v.q; S.s.c5 = v.c5; S.s.termF = v.termF; S.s.termR = v.termR; S.s.hash = v.hash; S.s.sF = v.sF; S.s.sR = v.sR;
+    S.status = H.status0;
+    S.qlen = H.qlen; S.k = H.k; S.maxOverlap = H.k + 2; S.trgLen = H.trgLen; S.minSA = minSA;
+    S.maxIndel = H.maxIndel; S.maxLength = H.maxLength; S.minLength = H.minLength;
+    S.curLen = S.curK = H.k;
+    S.nTerm = H.nTerm; S.n5 = H.n5; S.hashMask = H.hashMask; S.n9F = H.n9F; S.n9R = H.n9R; S.dup = H.dup != 0;
+    S.nNodes = 1; S.nRes = 0; S.level = 1;
+    S.n = 0;
+    if (S.status) return;
+    S.nFree = 0;
+    S.nFresh = 1;
+    const uint8_t* q = S.s.q;
+    const uint32_t k = H.k;
+    const int s9 = P.seed_size;
+    Leaf R;
+    R.f_lo = H.rf_lo; R.f_hi = H.rf_hi; R.r_lo = H.rr_lo; R.r_hi = H.rr_hi;
+    R.redeem = 0; R.local_err = 0; R.global_err = 0;
+    R.rt_hi = R.rt_lo = 0;
+    for (uint32_t j = 0; j < k; j++) tail_push(R.rt_hi, R.rt_lo, q[j]);
+    R.lastOverlapLen = k; R.lastSeedIdx = k - s9; R.totalSeeds = k - s9 + 1; R.seedOff = 0;
+    R.res_first = -1; R.res_second = -1;
+    R.kmerFreq = (int)((int64_t)(R.f_hi - R.f_lo) + (int64_t)(R.r_hi - R.r_lo));
+    R.tailLetter = q[k - 1];
+    uint32_t tc = 0;
+    for (int j = (int)k - 1; j >= 0 && q[j] == R.tailLetter; j--) tc++;
+    R.tailCount = tc;
+    R.node = 0; R.ring = 0; R.alive = 1; R.pad[0] = 0;
+    S.s.oldL[0] = R;
+    S.s.nodes[0] = 0;
+    S.s.rings[0] = 0.0;
+    S.n = 1;
+}
+
+// does extendOverlap's loop (LongReadCorrectByOverlap.cpp:161) run another level?
+__device__ __forceinline__ bool walk_continues(const State& S)
+{
+    return S.status == 0 && S.n > 0 && S.n <= (uint32_t)S.P->max_leaves && S.curLen <= S.maxLength;
+}
+
+// one iteration of extendOverlap's loop (:161-197)
+static __device__ __noinline__ void one_level(State& S)
+{
+    const ExtParamsDev& P = *S.P;
+    if (S.curK > S.maxOverlap) { refine(S, S.s.oldL, S.n, (int)S.maxOverlap); S.curK = S.maxOverlap; }
+    uint32_t m = attempt(S, S.minSA);
+    if (S.status) return;
+    if (m == 0)
     {
-        if (S.curK > S.maxOverlap) { refine(S, S.s.oldL, S.n, (int)S.maxOverlap); S.curK = S.maxOverlap; }
-        uint32_t m = attempt(S, S.minSA);
-        if (S.status) return S.status;
-        if (m == 0)
+        const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
+        const uint64_t R = select_freqs(S, S.s.oldL, S.n, LB, S.curK);
+        refine(S, S.s.oldL, S.n, (int)R);
+        S.curK = R;
+        m = attempt(S, S.minSA);
+        if (S.status) return;
+        if (m == 0) { m = attempt(S, S.minSA - 1); if (S.status) return; }
+    }
+    if (m > 0)
+    {
+        // old leaves are gone: those that were not extended release their ring (children inherited the others)
+        for (uint32_t i = 0; i < S.n; i++)
+        {
+            bool inherited = false;
+            const uint16_t ring = S.s.oldL[i].ring;
+            for (uint32_t j = 0; j < m && !inherited; j++) inherited = S.s.newL[j].ring == ring;
+            if (!inherited) ring_release(S, ring);
+        }
+        S.curLen++;
+        S.curK++;
+        if (insufficient(S, S.s.newL, m))
         {
             const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
-            const uint64_t R = select_freqs(S, S.s.oldL, S.n, LB, S.curK);
-            refine(S, S.s.oldL, S.n, (int)R);
+            const uint64_t R = select_freqs(S, S.s.newL, m, LB, S.curK);
+            refine(S, S.s.newL, m, (int)R);
             S.curK = R;
-            m = attempt(S, S.minSA);
-            if (S.status) return S.status;
-            if (m == 0) { m = attempt(S, S.minSA - 1); if (S.status) return S.status; }
         }
-        if (m > 0)
-        {
-            // old leaves are gone: those that were not extended release their ring (children inherited the others)
-            for (uint32_t i = 0; i < S.n; i++)
-            {
-                bool inherited = false;
-                const uint16_t ring = S.s.oldL[i].ring;
-                for (uint32_t j = 0; j < m && !inherited; j++) inherited = S.s.newL[j].ring == ring;
-                if (!inherited) ring_release(S, ring);
-            }
-            S.curLen++;
-            S.curK++;
-            if (insufficient(S, S.s.newL, m))
-            {
-                const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
-                const uint64_t R = select_freqs(S, S.s.newL, m, LB, S.curK);
-                refine(S, S.s.newL, m, (int)R);
-                S.curK = R;
-            }
-            const int64_t add = (int64_t)S.curLen + (int64_t)S.maxIndel;
-            const int64_t rem = (int64_t)S.curLen - 1 - (int64_t)S.maxIndel;
-            if (add < (int64_t)S.n5) S.s.win5[S.s.c5[add]]++;
-            if (rem >= 0 && rem < (int64_t)S.n5) S.s.win5[S.s.c5[rem]]--;
-            prune(S, m);
-            S.level++;
-            if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return S.status; }
-        }
-        uint32_t nn = 0;
-        for (uint32_t j = 0; j < m; j++)
-        {
-            if (!S.s.newL[j].alive) continue;
-            if (nn < OLD_CAP) S.s.oldL[nn] = S.s.newL[j];
-            nn++;
-        }
-        S.n = nn;
+        prune(S, m);
+        S.level++;
+        if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return; }
     }
+    uint32_t nn = 0;
+    for (uint32_t j = 0; j < m; j++)
+    {
+        if (!S.s.newL[j].alive) continue;
+        if (nn < OLD_CAP) S.s.oldL[nn] = S.s.newL[j];
+        nn++;
+    }
+    S.n = nn;
+}
 
-    // findTheBestPath (:214-236)
+// extendOverlap's return value and findTheBestPath (:199-236); writes the merged sequence to out[0..*outLen)
+static __device__ __noinline__ int finish_walk(State& S, uint8_t* out, uint32_t outCap, uint32_t* outLen)
+{
+    if (S.status) return S.status;
+    const ExtParamsDev& P = *S.P;
     if (S.nRes > 0)
     {
         double best = 1.0;
@@ -654,9 +732,12 @@ static __device__ __noinline__ int walk(const FmIndexDev& idx, const ExtParamsDe
         for (uint32_t i = 0; i < S.nRes; i++) { const double e = S.s.res[i].err; if (e < best) { best = e; bi = (int)i; } }
         if (bi < 0) return PBSC_WALK_NO_PATH;
         const WalkResult r = S.s.res[bi];
+        const uint8_t* q = S.s.q;
+        const uint8_t* trg = q + S.qlen - S.trgLen;
+        const uint32_t k = S.k;
         const uint32_t chain = r.depth - k;
         const uint32_t tailFrom = (uint32_t)r.i + P.min_overlap;
-        const uint32_t tailLen = trgLen > (uint32_t)P.min_overlap ? trgLen - tailFrom : 0;
+        const uint32_t tailLen = S.trgLen > (uint32_t)P.min_overlap ? S.trgLen - tailFrom : 0;
         const uint32_t len = r.depth + tailLen;
         if (len > outCap) return PBSC_WALK_OVERFLOW;
         for (uint32_t x = 0; x < k; x++) out[x] = q[x];
