@@ -185,3 +185,83 @@ def test_synthetic_index_matches_oracle(api, oracle_bin, tmp_path):
         lo, hi, _ = idx.find_interval(which, qs)
         assert np.array_equal(lo, ref[:, 0]) and np.array_equal(hi, ref[:, 1])
     idx.close()
+
+
+def _write_records(pieces, stats, reads, split=False):
+    correct, discard = [], []
+    for (rid, seq), pc, st in zip(reads, pieces, stats):
+        if st["merge"]:
+            for j, s in enumerate(pc):
+                correct.append(f">{rid}{'_%d' % j if split else ''}\n{s}\n")
+        else:
+            discard.append(f">{rid}\n{seq}\n")
+    return "".join(correct), "".join(discard)
+
+
+@pytest.mark.parametrize("engine", ["thread", "warp"])
+def test_both_engines_byte_identical(api, tiny_index, tiny_reads, golden, engine, monkeypatch):
+    monkeypatch.setenv("PBSC_ENGINE", engine)
+    p = _params(api, "tiny")
+    tiny_index.build_prefix_table(13)
+    out, poff, first, stats = tiny_index.correct_reads(p, [s for _, s in tiny_reads])
+    c, d = _write_records(api.Index.pieces_as_strings(out, poff, first), stats, tiny_reads)
+    assert c == open(os.path.join(golden, "tiny.correct.fa")).read()
+    assert d == open(os.path.join(golden, "tiny.discard.fa")).read()
+    tiny_index.build_prefix_table(0)
+
+
+def test_cli_drop_in(golden, tmp_path):
+    """The host binary end to end: same files in, byte-identical files out."""
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
+    out = tmp_path / "out"
+    r = subprocess.run([exe, "pbcorrect", "-t", "4", "-p", os.path.join(golden, "tiny"), "-o", str(out), "-c", "30", "-g", "5", "--nodp",
+                        "--batch-mbp", "0.2", os.path.join(golden, "tiny.reads.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    for f in ("correct.fa", "discard.fa", "threshold-table"):
+        assert open(out / f, "rb").read() == open(os.path.join(golden, f"tiny.{f}"), "rb").read(), f
+    want = [l for l in open(os.path.join(golden, "tiny.summary.txt")).read().strip().splitlines() if l]
+    got = [l for l in r.stdout.strip().splitlines() if l and not l.startswith("Time of")]
+    assert got == want
+    # gz input and a FASTA whose last line lacks the trailing newline (the reference drops that read's last line)
+    import gzip
+    raw = open(os.path.join(golden, "tiny.reads.fa"), "rb").read()
+    with gzip.open(tmp_path / "r.fa.gz", "wb") as f:
+        f.write(raw)
+    out2 = tmp_path / "out2"
+    r = subprocess.run([exe, "-p", os.path.join(golden, "tiny"), "-o", str(out2), "-c", "30", "-g", "5", "--nodp", str(tmp_path / "r.fa.gz")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out2 / "correct.fa", "rb").read() == open(os.path.join(golden, "tiny.correct.fa"), "rb").read()
+
+
+@pytest.mark.parametrize("opts,kw", [
+    (["-c", "45", "-g", "5", "--nodp"], dict(coverage=45, genome=5)),
+    (["-c", "70", "-g", "10", "--nodp", "--split"], dict(coverage=70, genome=10, split=True)),
+    (["-c", "45", "-g", "5", "--nodp", "-n", "3", "-m", "2"], dict(coverage=45, genome=5, next_target=3, mode=2)),
+    (["-c", "45", "-g", "100", "--nodp", "-l", "8", "-e", "0.2"], dict(coverage=45, genome=100, max_leaves=8, error_rate=0.2)),
+])
+@pytest.mark.parametrize("engine", ["thread", "warp"])
+def test_repeat_rich_dataset_vs_oracle(api, oracle_bin, tmp_path, opts, kw, engine, monkeypatch):
+    """Fresh data with repeat families and tandem arrays (the cases where equal idmers, strand swaps and look-aheads
+    occur), index built by the torch suffix sorter, oracle as the checker."""
+    from conftest import run_oracle
+    from longreadselfcorrect_b200 import bwt_build, synth
+    monkeypatch.setenv("PBSC_ENGINE", engine)
+    g = synth.make_genome(15000, 21, repeat_families=1, tandem_arrays=3)
+    codes, off = synth.simulate_reads(g, 45, 1200, 211, min_len=300)
+    reads = synth.read_strings(codes, off)
+    fa = str(tmp_path / "reads.fa")
+    synth.write_fasta(fa, codes, off)
+    prefix = str(tmp_path / "idx")
+    bwt_build.build_index_files(prefix, codes, off)
+    run_oracle(oracle_bin, prefix, fa, str(tmp_path / "or"), opts)
+    idx = api.Index.load(prefix)
+    idx.build_prefix_table(13)
+    p = api.Params.make(no_dp=True, **kw)
+    out, poff, first, stats = idx.correct_reads(p, reads)
+    named = [(f"r{i}", s) for i, s in enumerate(reads)]
+    c, d = _write_records(api.Index.pieces_as_strings(out, poff, first), stats, named, split=kw.get("split", False))
+    assert c == open(tmp_path / "or" / "correct.fa").read()
+    assert d == open(tmp_path / "or" / "discard.fa").read()
+    idx.close()
