@@ -7,7 +7,8 @@
 //     cnt[c]   = occurrences of base c (A,C,G,T = 0..3) in bwt[0 .. 64*blk)
 //     bases    = the 64 symbols, 2 bits each, symbol j in word j>>4 at bits 2*(j&15)
 //     '$' is stored as code 0; bit 31 of cnt[0] flags a block that contains a '$', in which
-//     case occ(A,.) is corrected from the sorted '$' position list (rare path: one '$' per read).
+//     case occ(A,.) is corrected from a side bit-vector (one 64-bit word per block, read only for flagged
+//     blocks: one '$' per read, under 1 % of the blocks).
 //
 // Intervals are kept half-open [lo, hi) on the device; the reference's inclusive
 // (lower, upper) = (lo, hi-1).  Invalid intervals always have hi == lo (BWTAlgorithms.h:66-72
@@ -39,6 +40,7 @@ struct FmTable
 {
     const FmBlock* blocks;      // n/64 + 1 blocks
     const uint32_t* dollar_pos; // sorted positions of '$' in the BWT
+    const uint64_t* dollar_mask;// one bit per BWT position, word per block: which symbols of a flagged block are '$'
     uint64_t n;                 // BWT length (symbols incl. '$')
     uint64_t C[4];              // C[c] = #symbols lexicographically smaller than base c (RLBWT.cpp:243-247)
     uint64_t total[4];          // occurrences of each base in the whole BWT
@@ -99,7 +101,7 @@ __device__ __forceinline__ uint64_t occ(const FmTable& t, int c, uint64_t p)
     if (off < 32) { m0 &= (1ull << (2 * off)) - 1ull; m1 = 0; }
     else { m1 &= (1ull << (2 * (off - 32))) - 1ull; }
     uint64_t r = (uint64_t)base + __popcll(m0) + __popcll(m1);
-    if (c == 0 && has_dollar && off) r -= count_dollars(t, blk << 6, p);
+    if (c == 0 && has_dollar && off) r -= __popcll(__ldg(t.dollar_mask + blk) & ((1ull << off) - 1ull));
     return r;
 }
 

@@ -21,6 +21,7 @@
 namespace pbsc {
 
 constexpr int TW_BLOCK = 128;
+constexpr int HEAVY_WARPS = 4;
 #define PBSC_TASK_PENDING (-999)
 
 struct __align__(16) WalkTask
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(TW_BLOCK)
 walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
                    unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
                    const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
-                   unsigned long long* walk_counter)
+                   unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     tw::TScratch lane;
@@ -223,11 +224,71 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
                 const int st = tw::finish_walk(S, outpool + tk->out_off, tk->out_cap, &mlen);
                 tk->out_len = st == 1 ? mlen : 0;
                 tk->status = st;
+                if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
                 active = false;
             }
         }
     }
     if (done) atomicAdd(walk_counter, done);
+}
+
+// Heavy walks (wide frontiers) re-walked by the warp-cooperative engine: warp per task, lanes own leaves / probes.
+__global__ void __launch_bounds__(HEAVY_WARPS * 32, 2)
+walk_heavy_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
+                  unsigned long long* counter, const unsigned int* n_heavy, const uint32_t* __restrict__ heavy_list, WalkTask* tasks,
+                  const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets, uint8_t* outpool, uint64_t minSA)
+{
+    __shared__ WarpShared shared[HEAVY_WARPS];
+    const int warp_in_block = threadIdx.x >> 5;
+    const int lane = lane_id();
+    WarpShared& sh = shared[warp_in_block];
+    WarpScratch ws;
+    carve_scratch(scratch + ((size_t)blockIdx.x * HEAVY_WARPS + warp_in_block) * stride, P, ws);
+    const unsigned long long n_items = *n_heavy;
+    for (;;)
+    {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1ull);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= n_items) break;
+        WalkTask& tk = tasks[heavy_list[it]];
+        int interval; uint32_t trgLen, qlen;
+        task_shape(tk, interval, trgLen, qlen);
+        const uint8_t* read = codes + offsets[tk.read];
+        const uint8_t* pth = read + tk.src_end + 1;
+        const uint8_t* trgS = read + tk.trg_start;
+        const int k = tk.k;
+        int st;
+        uint32_t mlen = 0;
+        if (qlen > P.q_cap) st = PBSC_WALK_OVERFLOW;
+        else
+        {
+            for (uint32_t x = lane; x < qlen; x += 32)
+            {
+                uint8_t c;
+                if (!tk.rtou)
+                    c = x < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - x) : (x < (uint32_t)(k + interval) ? pth[x - k] : trgS[x - k - interval]);
+                else
+                {
+                    const uint32_t y = qlen - 1 - x;
+                    const uint8_t d = y < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - y)
+                                                      : (y < (uint32_t)(k + interval) ? pth[y - k] : trgS[y - k - interval]);
+                    c = 3 - d;
+                }
+                ws.q[x] = c;
+            }
+            __syncwarp();
+            st = walk_pair(idx, P, ws, sh, qlen, (uint32_t)k, interval, trgLen, minSA, &mlen);
+            __syncwarp();
+            if (st == 1)
+            {
+                if (mlen > tk.out_cap) st = PBSC_WALK_OVERFLOW;
+                else for (uint32_t x = lane; x < mlen; x += 32) outpool[tk.out_off + x] = ws.merged[x];
+            }
+        }
+        if (lane == 0) { tk.out_len = st == 1 ? mlen : 0; tk.status = st; }
+        __syncwarp();
+    }
 }
 
 struct StitchParams { int32_t start_kmer, next_target, split; };
@@ -420,7 +481,12 @@ struct ThreadEngine
 {
     ArenaPtr<WalkTask> spec, pending;
     ArenaPtr<uint64_t> task_base, caps, cap_off, rec_caps, rec_off;
-    ArenaPtr<uint8_t> outpool, recpool, scratch;
+    ArenaPtr<uint8_t> outpool, recpool, scratch, wscratch;
+    ArenaPtr<uint32_t> heavy_list;
+    ArenaPtr<unsigned int> n_heavy;
+    ExtParamsDev Pw;
+    size_t wstride = 0;
+    int wblocks = 0;
     DevBuf<uint8_t> cubtmp;
     ArenaPtr<ReadState> states;
     ArenaPtr<uint32_t> stalled;
@@ -439,8 +505,13 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     int nb = blocks;
     if (n_items < threads) nb = (int)((n_items + TW_BLOCK - 1) / TW_BLOCK);
     if (nb < 1) nb = 1;
+    PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 4, st));
     walk_levels_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
-                                                E.pend_rec_base, E.pend_rec_cap, E.outpool.p, minSA, w.counters.p + 1);
+                                                E.pend_rec_base, E.pend_rec_cap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p);
+    // the walks that outgrew the thread engine, on the warp engine (the kernel reads the count from the device)
+    PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
+    walk_heavy_kernel<<<E.wblocks, HEAVY_WARPS * 32, 0, st>>>(idx->dev, E.Pw, E.wscratch.p, E.wstride, w.counters.p, E.n_heavy.p, E.heavy_list.p, tasks,
+                                                             b.codes.p, b.offsets.p, E.outpool.p, minSA);
     PBSC_CUDA(cudaGetLastError());
     return PBSC_OK;
 }
@@ -496,15 +567,21 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     const uint32_t pending_cap = (uint32_t)align_up((size_t)(1.2 * (hmax[0] + 10)) + 2 * 64 + hmax[1] + 64, 16);
     E.pend_rec_cap = tw::setup_record_bytes(need_q, std::max<uint32_t>(hmax[1], 64), p->min_kmer, p->idmer_len);
     ExtParamsDev P;
-    make_ext_params(p, P, w.q_cap, w.node_cap, pending_cap);
+    const uint32_t t_node_cap = 4096;                 // light walks; a walk that needs more is handed to the warp engine
+    make_ext_params(p, P, w.q_cap, t_node_cap, pending_cap);
+    make_ext_params(p, E.Pw, w.q_cap, std::max<uint32_t>(w.node_cap, 1u << 15), pending_cap);
+    E.wstride = warp_scratch_bytes(E.Pw.q_cap, E.Pw.node_cap, E.Pw.merged_cap);
+    E.wblocks = idx->sm_count * 2;
+    PBSC_CUDA(E.wscratch.get(idx, "tw.wscratch", E.wstride * (size_t)E.wblocks * HEAVY_WARPS));
     const uint64_t minSA = p->pb_coverage > 60 ? (uint64_t)((p->pb_coverage / 60) * 3) : 3;
     int blocks = 0;
     int rc = thread_geometry(idx->device, &blocks);
     if (rc != PBSC_OK) return rc;
-    const size_t stride = tw::thread_scratch_bytes(w.node_cap);
+    const size_t stride = tw::thread_scratch_bytes(t_node_cap);
     PBSC_CUDA(E.scratch.get(idx, "tw.scratch", stride * (size_t)blocks * TW_BLOCK));
     PBSC_CUDA(E.spec.get(idx, "tw.spec", n_tasks)); PBSC_CUDA(E.pending.get(idx, "tw.pending", n)); PBSC_CUDA(E.caps.get(idx, "tw.caps", n_tasks + 1)); PBSC_CUDA(E.cap_off.get(idx, "tw.cap_off", n_tasks + 1));
     PBSC_CUDA(E.rec_caps.get(idx, "tw.rec_caps", n_tasks + 1)); PBSC_CUDA(E.rec_off.get(idx, "tw.rec_off", n_tasks + 1));
+    PBSC_CUDA(E.heavy_list.get(idx, "tw.heavy_list", std::max<uint64_t>(n_tasks, n) + 1)); PBSC_CUDA(E.n_heavy.get(idx, "tw.n_heavy", 1));
     PBSC_CUDA(E.states.get(idx, "tw.states", n)); PBSC_CUDA(E.stalled.get(idx, "tw.stalled", n)); PBSC_CUDA(E.n_stalled.get(idx, "tw.n_stalled", 1));
     PBSC_CUDA(cudaMemsetAsync(E.states.p, 0, n * sizeof(ReadState), st));
     PBSC_CUDA(cudaMemsetAsync(E.pending.p, 0, n * sizeof(WalkTask), st));

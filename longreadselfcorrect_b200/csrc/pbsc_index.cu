@@ -67,10 +67,11 @@ static int decode_runs(const uint8_t* runs, uint64_t n_runs, uint64_t n_symbols,
     return PBSC_OK;
 }
 
-static void fill_table(FmTable& t, const FmBlock* d_blocks, const uint32_t* d_dollar, uint64_t n, const uint64_t total[5])
+static void fill_table(FmTable& t, const FmBlock* d_blocks, const uint32_t* d_dollar, const uint64_t* d_dmask, uint64_t n, const uint64_t total[5])
 {
     t.blocks = d_blocks;
     t.dollar_pos = d_dollar;
+    t.dollar_mask = d_dmask;
     t.n = n;
     t.n_dollar = (uint32_t)total[0];
     t.C[0] = total[0];
@@ -148,6 +149,12 @@ __global__ void synth_headers_kernel(FmBlock* blocks, const uint32_t* cntA, cons
     blocks[b].cnt[1] = cntC[b];
     blocks[b].cnt[2] = cntG[b];
     blocks[b].cnt[3] = cntT[b];
+}
+
+__global__ void dollar_mask_kernel(const uint32_t* __restrict__ dollar, uint32_t n, unsigned long long* __restrict__ mask)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) atomicOr(mask + (dollar[i] >> 6), 1ull << (dollar[i] & 63u));
 }
 
 __global__ void unique_count_kernel(const uint32_t* sorted, uint32_t n, uint32_t* out)
@@ -304,8 +311,12 @@ static int upload_strand(pbsc_index* idx, int which, const std::vector<FmBlock>&
     idx->n_symbols[which] = n_symbols;
     idx->n_strings[which] = n_strings;
     idx->n_blocks[which] = blocks.size();
-    idx->device_bytes += blocks.size() * sizeof(FmBlock) + (dollars.size() + 1) * sizeof(uint32_t);
-    fill_table(idx->dev.t[which], idx->d_blocks[which], idx->d_dollar[which], n_symbols, total);
+    PBSC_CUDA(cudaMalloc((void**)&idx->d_dmask[which], blocks.size() * sizeof(uint64_t)));
+    PBSC_CUDA(cudaMemset(idx->d_dmask[which], 0, blocks.size() * sizeof(uint64_t)));
+    if (!dollars.empty()) dollar_mask_kernel<<<(unsigned)((dollars.size() + 255) / 256), 256>>>(idx->d_dollar[which], (uint32_t)dollars.size(), (unsigned long long*)idx->d_dmask[which]);
+    PBSC_CUDA(cudaDeviceSynchronize());
+    idx->device_bytes += blocks.size() * (sizeof(FmBlock) + sizeof(uint64_t)) + (dollars.size() + 1) * sizeof(uint32_t);
+    fill_table(idx->dev.t[which], idx->d_blocks[which], idx->d_dollar[which], idx->d_dmask[which], n_symbols, total);
     return PBSC_OK;
 }
 
@@ -426,8 +437,12 @@ int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t
         idx->n_symbols[w] = n_symbols;
         idx->n_strings[w] = total[0];
         idx->n_blocks[w] = nb;
-        idx->device_bytes += nb * sizeof(FmBlock) + (n_strings + 1) * sizeof(uint32_t);
-        fill_table(idx->dev.t[w], idx->d_blocks[w], idx->d_dollar[w], n_symbols, total);
+        if (cudaMalloc((void**)&idx->d_dmask[w], nb * sizeof(uint64_t)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc dmask", __FILE__, __LINE__));
+        cudaMemset(idx->d_dmask[w], 0, nb * sizeof(uint64_t));
+        if (n_strings) dollar_mask_kernel<<<(unsigned)((n_strings + 255) / 256), 256>>>(idx->d_dollar[w], (uint32_t)n_strings, (unsigned long long*)idx->d_dmask[w]);
+        if (cudaDeviceSynchronize() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "dollar mask", __FILE__, __LINE__));
+        idx->device_bytes += nb * (sizeof(FmBlock) + sizeof(uint64_t)) + (n_strings + 1) * sizeof(uint32_t);
+        fill_table(idx->dev.t[w], idx->d_blocks[w], idx->d_dollar[w], idx->d_dmask[w], n_symbols, total);
         // duplicates in the '$' list are harmless for block generation (skipped) but the count used by
         // count_dollars() must see each position once: compact in place on the host side of the list
         if (n_strings)
@@ -482,7 +497,7 @@ void pbsc_index_destroy(pbsc_index* idx)
 {
     if (!idx) return;
     cudaSetDevice(idx->device);
-    for (int w = 0; w < 2; w++) { if (idx->d_blocks[w]) cudaFree(idx->d_blocks[w]); if (idx->d_dollar[w]) cudaFree(idx->d_dollar[w]); }
+    for (int w = 0; w < 2; w++) { if (idx->d_blocks[w]) cudaFree(idx->d_blocks[w]); if (idx->d_dollar[w]) cudaFree(idx->d_dollar[w]); if (idx->d_dmask[w]) cudaFree(idx->d_dmask[w]); }
     if (idx->d_prefix) cudaFree(idx->d_prefix);
     for (auto& kv : idx->arena) if (kv.second.p) cudaFree(kv.second.p);
     if (idx->stream) cudaStreamDestroy(idx->stream);

@@ -18,6 +18,7 @@ struct pbsc_index
     pbsc::FmIndexDev dev;
     pbsc::FmBlock* d_blocks[2] = {nullptr, nullptr};
     uint32_t* d_dollar[2] = {nullptr, nullptr};
+    uint64_t* d_dmask[2] = {nullptr, nullptr};
     pbsc::PrefixEntry* d_prefix = nullptr;
     uint64_t n_symbols[2] = {0, 0}, n_strings[2] = {0, 0}, n_blocks[2] = {0, 0};
     size_t device_bytes = 0;

@@ -25,6 +25,16 @@
 namespace pbsc {
 namespace tw {
 
+// The thread engine only carries LIGHT walks: at most TW_OLD live leaves and TW_NEW children per level.  A walk that
+// outgrows this (repeats, ExceedLeaves/ExceedDepth cases: a few percent of the walks, but each one costs 10-100x a light
+// walk and would stall the other 31 lanes of its warp) stops with PBSC_WALK_HEAVY and is re-walked from scratch by the
+// warp-cooperative engine (pbsc_walk.cuh), which is the right shape for a wide frontier.
+constexpr int TW_OLD = 4;
+constexpr int TW_NEW = 16;
+constexpr int TW_RINGS = 24;
+constexpr int TW_RES = 32;
+#define PBSC_WALK_HEAVY (-102)
+
 struct TScratch
 {
     Leaf* oldL; Leaf* newL;
@@ -45,22 +55,22 @@ __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; whil
 __host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap)
 {
     size_t b = 0;
-    b += sizeof(Leaf) * (OLD_CAP + NEW_CAP);
-    b += sizeof(double) * RING_SLOTS * RING_LEN;
+    b += sizeof(Leaf) * (TW_OLD + TW_NEW);
+    b += sizeof(double) * TW_RINGS * RING_LEN;
     b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
-    b += sizeof(WalkResult) * RES_CAP;
-    b += align_up(RING_SLOTS, 16);
+    b += sizeof(WalkResult) * TW_RES;
+    b += align_up(TW_RINGS, 16);
     return align_up(b, 128);
 }
 
 __device__ inline void carve(uint8_t* base, uint32_t node_cap, TScratch& w)
 {
     uint8_t* p = base;
-    w.oldL = (Leaf*)p; p += sizeof(Leaf) * OLD_CAP;
-    w.newL = (Leaf*)p; p += sizeof(Leaf) * NEW_CAP;
-    w.rings = (double*)p; p += sizeof(double) * RING_SLOTS * RING_LEN;
+    w.oldL = (Leaf*)p; p += sizeof(Leaf) * TW_OLD;
+    w.newL = (Leaf*)p; p += sizeof(Leaf) * TW_NEW;
+    w.rings = (double*)p; p += sizeof(double) * TW_RINGS * RING_LEN;
     w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
-    w.res = (WalkResult*)p; p += sizeof(WalkResult) * RES_CAP;
+    w.res = (WalkResult*)p; p += sizeof(WalkResult) * TW_RES;
     w.ringStack = p;
     w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.c5 = nullptr; w.win5 = nullptr;
 }
@@ -85,7 +95,7 @@ __device__ __forceinline__ void occ4(const FmTable& t, uint64_t p, uint64_t r[4]
     const uint32_t nG = __popcll(h0 & ~l0 & k0) + __popcll(h1 & ~l1 & k1);
     const uint32_t nC = __popcll(~h0 & l0 & k0) + __popcll(~h1 & l1 & k1);
     uint32_t nA = off - nT - nG - nC;
-    if ((cn.x >> 31) && off) nA -= count_dollars(t, blk << 6, p);
+    if ((cn.x >> 31) && off) nA -= __popcll(__ldg(t.dollar_mask + blk) & ((1ull << off) - 1ull));
     r[0] = (uint64_t)(cn.x & 0x7fffffffu) + nA;
     r[1] = (uint64_t)cn.y + nC;
     r[2] = (uint64_t)cn.z + nG;
@@ -131,7 +141,7 @@ struct State
     TScratch s;
     uint32_t n;
     uint64_t curLen, curK, maxLength, minLength, maxIndel, minSA;
-    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, nFresh, node_cap;
+    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, nFresh, node_cap, phase;
     bool dup;
     int status;
 };
@@ -141,7 +151,7 @@ __device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ring
 __device__ __forceinline__ int ring_take(State& S)
 {
     if (S.nFree) return (int)S.s.ringStack[--S.nFree];
-    return S.nFresh < (uint32_t)RING_SLOTS ? (int)S.nFresh++ : -1;
+    return S.nFresh < (uint32_t)TW_RINGS ? (int)S.nFresh++ : -1;
 }
 
 static __device__ __noinline__ void refine(State& S, Leaf* bank, uint32_t cnt, int K)
@@ -304,7 +314,8 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
         if (!mask && parent.local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, parent.tailCount, thr - 1);
         if (!mask) continue;
         const uint32_t cnt = __popc(mask);
-        if (S.nNodes + cnt > S.node_cap) { S.status = PBSC_WALK_OVERFLOW; return 0; }
+        if (m + cnt > (uint32_t)TW_NEW) { S.status = PBSC_WALK_HEAVY; return 0; }
+        if (S.nNodes + cnt > S.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
         uint32_t j = 0;
         #pragma unroll 1
         for (int b = 0; b < 4; b++)
@@ -322,10 +333,11 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
             {
                 // createChild copies both error-rate records (FMIndexWalk/SAINode.cpp:166-189)
                 const int slot = ring_take(S);
-                if (slot < 0) { S.status = PBSC_WALK_OVERFLOW; return 0; }
+                if (slot < 0) { S.status = PBSC_WALK_HEAVY; return 0; }
                 const double* src = S.s.rings + (size_t)parent.ring * RING_LEN;
                 double* dst = S.s.rings + (size_t)slot * RING_LEN;
-                for (int x = 0; x < RING_LEN; x++) dst[x] = src[x];
+                const int have = min((int)S.level, RING_LEN);   // GlobalErrorRateRecord holds `level` entries so far
+                for (int x = 0; x < have; x++) dst[x] = src[x];
                 c.ring = (uint16_t)slot;
             }
             newL[m++] = c;
@@ -463,7 +475,7 @@ static __device__ __noinline__ void terminated(State& S, uint32_t m)
         int slot = L.res_first;
         if (slot == -1)
         {
-            if (S.nRes >= RES_CAP) { S.status = PBSC_WALK_OVERFLOW; return; }
+            if (S.nRes >= TW_RES) { S.status = PBSC_WALK_HEAVY; return; }
             slot = (int)++S.nRes;
         }
         WalkResult r; r.err = L.global_err; r.node = L.node; r.i = ilast; r.depth = (uint32_t)S.curLen; r.pad = 0;
@@ -637,7 +649,7 @@ __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, cons
     S.maxIndel = H.maxIndel; S.maxLength = H.maxLength; S.minLength = H.minLength;
     S.curLen = S.curK = H.k;
     S.nTerm = H.nTerm; S.n5 = H.n5; S.hashMask = H.hashMask; S.n9F = H.n9F; S.n9R = H.n9R; S.dup = H.dup != 0;
-    S.nNodes = 1; S.nRes = 0; S.level = 1;
+    S.nNodes = 1; S.nRes = 0; S.level = 1; S.phase = 0;
     S.n = 0;
     if (S.status) return;
     S.nFree = 0;
@@ -670,23 +682,21 @@ __device__ __forceinline__ bool walk_continues(const State& S)
     return S.status == 0 && S.n > 0 && S.n <= (uint32_t)S.P->max_leaves && S.curLen <= S.maxLength;
 }
 
-// one iteration of extendOverlap's loop (:161-197)
+// One step of extendOverlap's loop (:161-197).  extendLeaves' fallbacks (reduce the k-mer, then lower the SA threshold,
+// :249-262) are rare per walk but long; run inline they would stall the other 31 lanes of the warp, so a walk that
+// needs them spends extra steps in phases 1 and 2 while its neighbours keep extending, and every lane runs the same
+// attempt / select / refine code in every step.
+//   phase 0: normal level            attempt(thr)
+//   phase 1: after the k-mer was reduced (select + refine on the old leaves happened at the end of the previous step)
+//   phase 2: last resort             attempt(thr - 1)
 static __device__ __noinline__ void one_level(State& S)
 {
     const ExtParamsDev& P = *S.P;
-    if (S.curK > S.maxOverlap) { refine(S, S.s.oldL, S.n, (int)S.maxOverlap); S.curK = S.maxOverlap; }
-    uint32_t m = attempt(S, S.minSA);
+    if (S.phase == 0 && S.curK > S.maxOverlap) { refine(S, S.s.oldL, S.n, (int)S.maxOverlap); S.curK = S.maxOverlap; }
+    const uint32_t m = attempt(S, S.phase == 2 ? S.minSA - 1 : S.minSA);
     if (S.status) return;
-    if (m == 0)
-    {
-        const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
-        const uint64_t R = select_freqs(S, S.s.oldL, S.n, LB, S.curK);
-        refine(S, S.s.oldL, S.n, (int)R);
-        S.curK = R;
-        m = attempt(S, S.minSA);
-        if (S.status) return;
-        if (m == 0) { m = attempt(S, S.minSA - 1); if (S.status) return; }
-    }
+    Leaf* bank = nullptr;
+    uint32_t cnt = 0;
     if (m > 0)
     {
         // old leaves are gone: those that were not extended release their ring (children inherited the others)
@@ -699,25 +709,33 @@ static __device__ __noinline__ void one_level(State& S)
         }
         S.curLen++;
         S.curK++;
-        if (insufficient(S, S.s.newL, m))
-        {
-            const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
-            const uint64_t R = select_freqs(S, S.s.newL, m, LB, S.curK);
-            refine(S, S.s.newL, m, (int)R);
-            S.curK = R;
-        }
-        prune(S, m);
-        S.level++;
-        if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return; }
+        S.phase = 0;
+        if (insufficient(S, S.s.newL, m)) { bank = S.s.newL; cnt = m; }
     }
+    else if (S.phase == 0) { bank = S.s.oldL; cnt = S.n; S.phase = 1; }   // level 1: reduce the k-mer size, then retry
+    else if (S.phase == 1) { S.phase = 2; return; }                        // level 2: retry with the lower threshold
+    else { S.n = 0; return; }                                              // newLeaves stays empty: the walk ends
+    if (cnt)
+    {
+        const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
+        const uint64_t R = select_freqs(S, bank, cnt, LB, S.curK);
+        refine(S, bank, cnt, (int)R);
+        S.curK = R;
+    }
+    if (m == 0) return;
+    prune(S, m);
+    S.level++;
+    if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return; }
     uint32_t nn = 0;
     for (uint32_t j = 0; j < m; j++)
     {
         if (!S.s.newL[j].alive) continue;
-        if (nn < OLD_CAP) S.s.oldL[nn] = S.s.newL[j];
+        if (nn < TW_OLD) S.s.oldL[nn] = S.s.newL[j];
         nn++;
     }
     S.n = nn;
+    // more live leaves than this engine carries, and the reference's loop would go on: hand the walk over
+    if (nn > (uint32_t)TW_OLD && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
 }
 
 // extendOverlap's return value and findTheBestPath (:199-236); writes the merged sequence to out[0..*outLen)
