@@ -45,8 +45,8 @@ struct TScratch
     uint8_t* q;
     uint64_t* hash;
     uint64_t* sF; uint64_t* sR;
-    uint16_t* c5;
-    uint16_t* win5;
+    uint16_t* start4;     // bucket starts of the query 4-mers (257 entries)
+    uint16_t* pos4;       // query positions grouped by 4-mer, ascending inside a bucket
     uint8_t* ringStack;   // free ring slots
 };
 
@@ -72,7 +72,7 @@ __device__ inline void carve(uint8_t* base, uint32_t node_cap, TScratch& w)
     w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     w.res = (WalkResult*)p; p += sizeof(WalkResult) * TW_RES;
     w.ringStack = p;
-    w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.c5 = nullptr; w.win5 = nullptr;
+    w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.start4 = w.pos4 = nullptr;
 }
 
 // occurrences of all four bases in bwt[0, p) from one 32-byte sector
@@ -258,7 +258,7 @@ __device__ __forceinline__ uint32_t eval4(const int freq[4], uint64_t totalcount
     return mask;
 }
 
-__device__ __forceinline__ bool match5_window(const State& S, uint32_t code5);
+__device__ __forceinline__ uint32_t match5_mask(const State& S, uint32_t tail4);
 
 // attempToExtend + getFMIndexExtensions + updateLeaves (LongReadCorrectByOverlap.cpp:373-488, 667-784)
 static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
@@ -297,6 +297,7 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
         uint64_t total = 0;
         int mx = 0;
         uint32_t match5 = 0;
+        const uint32_t near5 = match5_mask(S, (uint32_t)(parent.rt_hi >> 56));
         #pragma unroll
         for (int b = 0; b < 4; b++)
         {
@@ -307,8 +308,7 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
             freq[b] = (int)((int64_t)pf[b].size() + (int64_t)pr[b].size());
             total += (uint64_t)(int64_t)freq[b];
             mx = max(mx, freq[b]);
-            const uint32_t code5 = ((uint32_t)b << 8) | (uint32_t)(parent.rt_hi >> 56);
-            if ((pf[b].valid() || pr[b].valid()) && match5_window(S, code5)) match5 |= 1u << b;
+            if ((pf[b].valid() || pr[b].valid()) && ((near5 >> b) & 1)) match5 |= 1u << b;
         }
         uint32_t mask = eval4(freq, total, mx, match5, parent.tailCount, thr);
         if (!mask && parent.local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, parent.tailCount, thr - 1);
@@ -504,7 +504,7 @@ struct SetupView
 {
     SetupHdr* hdr;
     uint8_t* q;
-    uint16_t* c5;
+    uint16_t* start4; uint16_t* cur4; uint16_t* pos4;
     Interval* termF; Interval* termR;
     uint64_t* hash;
     uint64_t* sF; uint64_t* sR;
@@ -516,7 +516,7 @@ __host__ __device__ inline size_t setup_record_bytes(uint32_t qlen, uint32_t trg
     const uint32_t n9 = qlen >= (uint32_t)s9 ? qlen - s9 + 1 : 0;
     size_t b = sizeof(SetupHdr);
     b += align_up(qlen, 16);
-    b += align_up(sizeof(uint16_t) * (size_t)qlen, 16);
+    b += 2 * align_up(sizeof(uint16_t) * 258, 16) + align_up(sizeof(uint16_t) * (size_t)qlen, 16);
     b += sizeof(Interval) * (size_t)nTerm * 2;
     b += sizeof(uint64_t) * (size_t)pow2_ceil(2 * (n9 ? n9 : 1));
     b += sizeof(uint64_t) * (size_t)n9 * 2;
@@ -530,7 +530,9 @@ __device__ inline void setup_view(uint8_t* base, uint32_t qlen, uint32_t trgLen,
     uint8_t* p = base;
     v.hdr = (SetupHdr*)p; p += sizeof(SetupHdr);
     v.q = p; p += align_up(qlen, 16);
-    v.c5 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * (size_t)qlen, 16);
+    v.start4 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * 258, 16);
+    v.cur4 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * 258, 16);
+    v.pos4 = (uint16_t*)p; p += align_up(sizeof(uint16_t) * (size_t)qlen, 16);
     v.termF = (Interval*)p; p += sizeof(Interval) * (size_t)nTerm;
     v.termR = (Interval*)p; p += sizeof(Interval) * (size_t)nTerm;
     v.hash = (uint64_t*)p; p += sizeof(uint64_t) * (size_t)pow2_ceil(2 * (n9 ? n9 : 1));
@@ -611,7 +613,17 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
     }
     // query 5-mers, newest base most significant
     H.n5 = qlen >= 5 ? qlen - 4 : 0;
-    for (uint32_t p = 0; p < H.n5; p++) v.c5[p] = (uint16_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6) | (q[p + 4] << 8));
+    // positions grouped by their 4-mer (counting sort): ismatchedbykmer asks, for a leaf ending in some 4-mer, which next
+    // bases follow an occurrence of that 4-mer near the current length
+    {
+        uint4* z = reinterpret_cast<uint4*>(v.start4);
+        for (int x = 0; x < 33; x++) z[x] = make_uint4(0, 0, 0, 0);
+        auto c4 = [&](uint32_t p) { return (uint32_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6)); };
+        for (uint32_t p = 0; p < H.n5; p++) v.start4[c4(p) + 1]++;
+        for (int c = 1; c <= 256; c++) v.start4[c] = (uint16_t)(v.start4[c] + v.start4[c - 1]);
+        for (int c = 0; c < 256; c++) v.cur4[c] = v.start4[c];
+        for (uint32_t p = 0; p < H.n5; p++) v.pos4[v.cur4[c4(p)]++] = (uint16_t)p;
+    }
     // root intervals (:106-124)
     {
         Interval f, r;
@@ -621,20 +633,20 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
     *v.hdr = H;
 }
 
-// ismatchedbykmer (LongReadCorrectByOverlap.cpp:787-821): any query 5-mer equal to `code5` starting within curLen +- maxIndel
-__device__ __forceinline__ bool match5_window(const State& S, uint32_t code5)
+// ismatchedbykmer (LongReadCorrectByOverlap.cpp:787-821) for the four probes of one leaf at once: bit b is set when the
+// query holds, starting within curLen +- maxIndel, the leaf's last four bases followed by base b
+__device__ __forceinline__ uint32_t match5_mask(const State& S, uint32_t tail4)
 {
     const int64_t lo = max((int64_t)S.curLen - (int64_t)S.maxIndel, (int64_t)0);
     const int64_t hi = min((int64_t)S.curLen + (int64_t)S.maxIndel, (int64_t)S.n5 - 1);
-    if (hi < lo) return false;
-    const uint32_t pat = code5 | (code5 << 16);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(S.s.c5);   // c5 is 16-byte aligned
-    uint32_t hit = 0;
-    int64_t p = lo;
-    if (p & 1) { hit |= (S.s.c5[p] == (uint16_t)code5); p++; }
-    for (; p + 1 <= hi; p += 2) hit |= __vcmpeq2(w[p >> 1], pat);
-    if (p <= hi) hit |= (S.s.c5[p] == (uint16_t)code5);
-    return hit != 0;
+    uint32_t mask = 0;
+    const uint32_t e1 = S.s.start4[tail4 + 1];
+    for (uint32_t e = S.s.start4[tail4]; e < e1; e++)
+    {
+        const int64_t p = S.s.pos4[e];
+        if (p >= lo && p <= hi) mask |= 1u << S.s.q[p + 4];
+    }
+    return mask;
 }
 
 // start a walk from its setup record
@@ -643,7 +655,7 @@ __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, cons
 {
     const SetupHdr H = *v.hdr;
     S.idx = &idx; S.P = &P; S.s = lane_scratch; S.node_cap = node_cap;
-    S.s.q = v.q; S.s.c5 = v.c5; S.s.termF = v.termF; S.s.termR = v.termR; S.s.hash = v.hash; S.s.sF = v.sF; S.s.sR = v.sR;
+    S.s.q = v.q; S.s.start4 = v.start4; S.s.pos4 = v.pos4; S.s.termF = v.termF; S.s.termR = v.termR; S.s.hash = v.hash; S.s.sF = v.sF; S.s.sR = v.sR;
     S.status = H.status0;
     S.qlen = H.qlen; S.k = H.k; S.maxOverlap = H.k + 2; S.trgLen = H.trgLen; S.minSA = minSA;
     S.maxIndel = H.maxIndel; S.maxLength = H.maxLength; S.minLength = H.minLength;
