@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(TW_BLOCK)
 walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
                    unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
                    const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
-                   unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy)
+                   unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy, uint32_t* nodepool,
+                   unsigned long long* pool_used, uint64_t pool_cap)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     tw::TScratch lane;
@@ -192,6 +193,7 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
     tw::State S;
     S.status = 0; S.n = 0;
     WalkTask* tk = nullptr;
+    tw::SetupHdr* hdr = nullptr;
     bool active = false, exhausted = false;
     unsigned long long done = 0;
     for (;;)
@@ -209,6 +211,7 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
                 tw::SetupView v;
                 tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
                 tw::begin_walk(S, idx, P, lane, v, P.node_cap, minSA);
+                hdr = v.hdr;
                 active = true;
                 done++;
                 break;
@@ -220,9 +223,8 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
             if (tw::walk_continues(S)) tw::one_level(S);
             if (!tw::walk_continues(S))
             {
-                uint32_t mlen = 0;
-                const int st = tw::finish_walk(S, outpool + tk->out_off, tk->out_cap, &mlen);
-                tk->out_len = st == 1 ? mlen : 0;
+                const int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
+                tk->out_len = 0;
                 tk->status = st;
                 if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
                 active = false;
@@ -230,6 +232,25 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
         }
     }
     if (done) atomicAdd(walk_counter, done);
+}
+
+// thread per task: write the merged sequence of every light walk that succeeded
+__global__ void __launch_bounds__(128)
+materialize_kernel(uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool, const uint64_t* __restrict__ rec_off,
+                   uint64_t pend_base, uint64_t pend_cap, const uint32_t* __restrict__ nodepool, uint8_t* outpool, int min_overlap, int s9)
+{
+    const uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    WalkTask& tk = tasks[list ? list[it] : it];
+    if (!tk.valid || tk.status != PBSC_TASK_MATERIALIZE) return;
+    int interval; uint32_t trgLen, qlen;
+    task_shape(tk, interval, trgLen, qlen);
+    tw::SetupView v;
+    tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, min_overlap, s9, v);
+    uint32_t mlen = 0;
+    const int st = tw::materialize(v, min_overlap, nodepool, outpool + tk.out_off, tk.out_cap, &mlen);
+    tk.out_len = st == 1 ? mlen : 0;
+    tk.status = st;
 }
 
 // Heavy walks (wide frontiers) re-walked by the warp-cooperative engine: warp per task, lanes own leaves / probes.
@@ -482,7 +503,9 @@ struct ThreadEngine
     ArenaPtr<WalkTask> spec, pending;
     ArenaPtr<uint64_t> task_base, caps, cap_off, rec_caps, rec_off;
     ArenaPtr<uint8_t> outpool, recpool, scratch, wscratch;
-    ArenaPtr<uint32_t> heavy_list;
+    ArenaPtr<uint32_t> heavy_list, nodepool;
+    ArenaPtr<unsigned long long> pool_used;
+    uint64_t pool_cap = 0;
     ArenaPtr<unsigned int> n_heavy;
     ExtParamsDev Pw;
     size_t wstride = 0;
@@ -506,8 +529,12 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     if (n_items < threads) nb = (int)((n_items + TW_BLOCK - 1) / TW_BLOCK);
     if (nb < 1) nb = 1;
     PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 4, st));
+    PBSC_CUDA(cudaMemsetAsync(E.pool_used.p, 0, 8, st));
     walk_levels_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
-                                                E.pend_rec_base, E.pend_rec_cap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p);
+                                                E.pend_rec_base, E.pend_rec_cap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
+                                                E.nodepool.p, E.pool_used.p, E.pool_cap);
+    materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, E.recpool.p, E.rec_off.p, E.pend_rec_base, E.pend_rec_cap,
+                                                                         E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
     // the walks that outgrew the thread engine, on the warp engine (the kernel reads the count from the device)
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
     walk_heavy_kernel<<<E.wblocks, HEAVY_WARPS * 32, 0, st>>>(idx->dev, E.Pw, E.wscratch.p, E.wstride, w.counters.p, E.n_heavy.p, E.heavy_list.p, tasks,
@@ -582,6 +609,8 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     PBSC_CUDA(E.spec.get(idx, "tw.spec", n_tasks)); PBSC_CUDA(E.pending.get(idx, "tw.pending", n)); PBSC_CUDA(E.caps.get(idx, "tw.caps", n_tasks + 1)); PBSC_CUDA(E.cap_off.get(idx, "tw.cap_off", n_tasks + 1));
     PBSC_CUDA(E.rec_caps.get(idx, "tw.rec_caps", n_tasks + 1)); PBSC_CUDA(E.rec_off.get(idx, "tw.rec_off", n_tasks + 1));
     PBSC_CUDA(E.heavy_list.get(idx, "tw.heavy_list", std::max<uint64_t>(n_tasks, n) + 1)); PBSC_CUDA(E.n_heavy.get(idx, "tw.n_heavy", 1));
+    E.pool_cap = std::max<uint64_t>(n_tasks, n) * (uint64_t)(w.node_cap >= (1u << 16) ? 2048 : 256) + 65536;
+    PBSC_CUDA(E.nodepool.get(idx, "tw.nodepool", E.pool_cap)); PBSC_CUDA(E.pool_used.get(idx, "tw.pool_used", 1));
     PBSC_CUDA(E.states.get(idx, "tw.states", n)); PBSC_CUDA(E.stalled.get(idx, "tw.stalled", n)); PBSC_CUDA(E.n_stalled.get(idx, "tw.n_stalled", 1));
     PBSC_CUDA(cudaMemsetAsync(E.states.p, 0, n * sizeof(ReadState), st));
     PBSC_CUDA(cudaMemsetAsync(E.pending.p, 0, n * sizeof(WalkTask), st));

@@ -496,7 +496,12 @@ struct __align__(16) SetupHdr
     int32_t dis;
     uint32_t dup;
     int32_t status0;    // 0, PBSC_WALK_UNSUPPORTED or PBSC_WALK_OVERFLOW decided before any walking
-    uint32_t pad;
+    // result of a successful light walk, materialised later by materialize_kernel
+    uint32_t res_node, res_depth, n_nodes;
+    int32_t res_i;
+    uint32_t pad2[3];
+    uint64_t node_off;   // where this walk's label tree was copied in the node pool
+    uint64_t pad3;
 };
 static_assert(sizeof(SetupHdr) % 16 == 0, "SetupHdr must keep 16-byte alignment");
 
@@ -750,8 +755,12 @@ static __device__ __noinline__ void one_level(State& S)
     if (nn > (uint32_t)TW_OLD && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
 }
 
-// extendOverlap's return value and findTheBestPath (:199-236); writes the merged sequence to out[0..*outLen)
-static __device__ __noinline__ int finish_walk(State& S, uint8_t* out, uint32_t outCap, uint32_t* outLen)
+#define PBSC_TASK_MATERIALIZE 2   // walk succeeded; the merged sequence is still to be written from the saved label tree
+
+// extendOverlap's return value and findTheBestPath (:199-236).  A successful walk does not chase its label chain here
+// (a serial pointer chase by one lane while 31 wait): it copies its label tree to the node pool and leaves the rest to
+// materialize_kernel.
+static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t* nodepool, unsigned long long* pool_used, uint64_t pool_cap)
 {
     if (S.status) return S.status;
     const ExtParamsDev& P = *S.P;
@@ -762,25 +771,40 @@ static __device__ __noinline__ int finish_walk(State& S, uint8_t* out, uint32_t 
         for (uint32_t i = 0; i < S.nRes; i++) { const double e = S.s.res[i].err; if (e < best) { best = e; bi = (int)i; } }
         if (bi < 0) return PBSC_WALK_NO_PATH;
         const WalkResult r = S.s.res[bi];
-        const uint8_t* q = S.s.q;
-        const uint8_t* trg = q + S.qlen - S.trgLen;
-        const uint32_t k = S.k;
-        const uint32_t chain = r.depth - k;
-        const uint32_t tailFrom = (uint32_t)r.i + P.min_overlap;
-        const uint32_t tailLen = S.trgLen > (uint32_t)P.min_overlap ? S.trgLen - tailFrom : 0;
-        const uint32_t len = r.depth + tailLen;
-        if (len > outCap) return PBSC_WALK_OVERFLOW;
-        for (uint32_t x = 0; x < k; x++) out[x] = q[x];
-        for (uint32_t x = 0; x < tailLen; x++) out[r.depth + x] = trg[tailFrom + x];
-        uint32_t node = r.node;
-        for (uint32_t x = 0; x < chain; x++) { const uint32_t v = S.s.nodes[node]; out[r.depth - 1 - x] = (uint8_t)(v & 3); node = v >> 2; }
-        *outLen = len;
-        return 1;
+        const uint32_t nn = (S.nNodes + 3u) & ~3u;
+        const uint64_t off = atomicAdd(pool_used, (unsigned long long)nn);
+        if (off + nn > pool_cap) return PBSC_WALK_OVERFLOW;
+        const uint4* src = reinterpret_cast<const uint4*>(S.s.nodes);
+        uint4* dst = reinterpret_cast<uint4*>(nodepool + off);
+        for (uint32_t x = 0; x < nn / 4; x++) dst[x] = src[x];
+        hdr->res_node = r.node; hdr->res_depth = r.depth; hdr->res_i = r.i; hdr->n_nodes = S.nNodes; hdr->node_off = off;
+        return PBSC_TASK_MATERIALIZE;
     }
     if (S.n == 0) return -1;
     if (S.curLen > S.maxLength) return -2;
     if (S.n > (uint32_t)P.max_leaves) return -3;
     return -4;
+}
+
+// merged sequence of a successful light walk: beginningkmer + labels along the best leaf's chain + rest of the target
+__device__ __forceinline__ int materialize(const SetupView& v, int min_overlap, const uint32_t* nodepool, uint8_t* out, uint32_t outCap, uint32_t* outLen)
+{
+    const SetupHdr H = *v.hdr;
+    const uint8_t* q = v.q;
+    const uint8_t* trg = q + H.qlen - H.trgLen;
+    const uint32_t k = H.k;
+    const uint32_t chain = H.res_depth - k;
+    const uint32_t tailFrom = (uint32_t)H.res_i + min_overlap;
+    const uint32_t tailLen = H.trgLen > (uint32_t)min_overlap ? H.trgLen - tailFrom : 0;
+    const uint32_t len = H.res_depth + tailLen;
+    if (len > outCap) return PBSC_WALK_OVERFLOW;
+    for (uint32_t x = 0; x < k; x++) out[x] = q[x];
+    for (uint32_t x = 0; x < tailLen; x++) out[H.res_depth + x] = trg[tailFrom + x];
+    const uint32_t* nodes = nodepool + H.node_off;
+    uint32_t node = H.res_node;
+    for (uint32_t x = 0; x < chain; x++) { const uint32_t w = nodes[node]; out[H.res_depth - 1 - x] = (uint8_t)(w & 3); node = w >> 2; }
+    *outLen = len;
+    return 1;
 }
 
 }  // namespace tw
