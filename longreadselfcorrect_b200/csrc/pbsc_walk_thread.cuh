@@ -29,9 +29,9 @@ namespace tw {
 // outgrows this (repeats, ExceedLeaves/ExceedDepth cases: a few percent of the walks, but each one costs 10-100x a light
 // walk and would stall the other 31 lanes of its warp) stops with PBSC_WALK_HEAVY and is re-walked from scratch by the
 // warp-cooperative engine (pbsc_walk.cuh), which is the right shape for a wide frontier.
-constexpr int TW_OLD = 4;
-constexpr int TW_NEW = 16;
-constexpr int TW_RINGS = 24;
+constexpr int TW_OLD = 8;
+constexpr int TW_NEW = 32;
+constexpr int TW_RINGS = 40;
 constexpr int TW_RES = 32;
 #define PBSC_WALK_HEAVY (-102)
 
