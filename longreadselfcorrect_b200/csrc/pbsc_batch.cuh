@@ -53,7 +53,9 @@ struct Workspace
 {
     // seed phase
     DevBuf<StaticFeat> feats;
-    DevBuf<uint8_t> cls, attr;
+    DevBuf<uint8_t> cls, attr, ntriv;
+    DevBuf<ulonglong2> prefix;   // uint4 running counts per base
+    DevBuf<uint64_t> cand;       // SeedCand per base (16 bytes)
     DevBuf<pbsc_seed> seed_tmp;
     // extend phase
     DevBuf<uint8_t> pieces, scratch;

@@ -119,116 +119,200 @@ seed_features_kernel(FmIndexDev idx, SeedParamsDev P, const uint8_t* __restrict_
     cls[g] = cl;
 }
 
-// thread per read: attribute + hybrid k-mer scan
+// ---- getSeqAttribute (LongReadProbe.cpp:120-182) in two data-parallel steps ----
+// (1) warp per read: running counts of the four indicators the sliding box needs
+//     .x = #entering k-mers classified -1 up to and including this position, .y = #entering classified 2,
+//     .z = #leaving k-mers classified -1,                                     .w = #leaving classified 2
 __global__ void __launch_bounds__(128)
-seed_scan_kernel(FmIndexDev idx, SeedParamsDev P, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
-                 uint64_t n_reads, uint64_t n_bases, const StaticFeat* __restrict__ feats, const uint8_t* __restrict__ cls,
-                 uint8_t* __restrict__ attr, pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
-                 uint32_t* __restrict__ seed_count)
+seed_prefix_kernel(const uint64_t* __restrict__ offsets, uint64_t n_reads, const uint8_t* __restrict__ cls, uint4* __restrict__ pre)
 {
-    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= n_reads) return;
     const uint64_t base = offsets[r];
     const int64_t L = (int64_t)(offsets[r + 1] - base);
-    seed_count[r] = 0;
-    if ((int)L < P.start_kmer) return;   // LongReadProbe.cpp:37-38
+    uint32_t run[4] = {0, 0, 0, 0};
+    for (int64_t c = 0; c < L; c += 32)
+    {
+        const int64_t p = c + lane;
+        uint32_t v = 0;
+        if (p < L)
+        {
+            const uint8_t x = cls[base + p];
+            const int in = (int)(x & 15) - 1, out = (int)(x >> 4) - 1;
+            v = (uint32_t)(in == -1) | ((uint32_t)(in == 2) << 8) | ((uint32_t)(out == -1) << 16) | ((uint32_t)(out == 2) << 24);
+        }
+        // inclusive scan of four 8-bit counters packed in one word (a chunk holds at most 32 of each)
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (p < L) pre[base + p] = make_uint4(run[0] + (v & 255), run[1] + ((v >> 8) & 255), run[2] + ((v >> 16) & 255), run[3] + (v >> 24));
+        const uint32_t tot = __shfl_sync(0xffffffffu, v, 31);
+        run[0] += tot & 255; run[1] += (tot >> 8) & 255; run[2] += (tot >> 16) & 255; run[3] += tot >> 24;
+    }
+}
+
+// (2) thread per position: box counts of the +-150 window from the running counts, then the 2 % repeat-ratio rule
+__global__ void __launch_bounds__(256)
+seed_attr_kernel(SeedParamsDev P, const uint64_t* __restrict__ offsets, uint64_t n_reads, uint64_t n_bases, const uint4* __restrict__ pre,
+                 uint8_t* __restrict__ attr)
+{
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= n_bases) return;
+    const uint64_t r = find_read(offsets, n_reads, g);
+    const uint64_t base = __ldg(offsets + r);
+    const int64_t L = (int64_t)(__ldg(offsets + r + 1) - base);
+    const int pos = (int)(g - base);
+    const int range = 300;
+    int left = pos - (range >> 1), right = pos + (range >> 1);
+    left = max(left, 0);
+    right = min(right, (int)(L - 1));
+    // entering k-mers: every position <= right has been added; leaving k-mers: every position < left has been removed
+    const uint4 in = pre[base + right];
+    uint32_t outN = 0, out2 = 0;
+    if (left > 0) { const uint4 o = pre[base + left - 1]; outN = o.z; out2 = o.w; }
+    const int boxN = (int)in.x - (int)outN, box2 = (int)in.y - (int)out2;
+    const int size = (right - left + 1) - boxN;
+    const float ratio = (float)((double)__fdiv_rn((float)box2, (float)size) + 0.0005);
+    uint8_t a = ((double)ratio >= 0.02) ? 2 : 1;
+    if (P.manual) a = (uint8_t)P.mode;
+    attr[g] = a;
+}
+
+// ---- hybrid k-mer scan (LongReadProbe.cpp:46-104) ----
+// One iteration of the reference's outer loop is a pure function of its starting position initPos: it returns the
+// position the loop continues from and possibly one seed.  seed_candidates_kernel evaluates that function for EVERY
+// position in parallel (positions inside a seed region redo part of the extension, a few percent of the feature work);
+// seed_chain_kernel then follows the actual sequence initPos -> f(initPos) + 1 from 0, skipping the trivial positions
+// (f(p) = p, no seed) 32 at a time.
+struct __align__(8) SeedCand
+{
+    int32_t next;          // value of initPos when the outer iteration ends
+    int32_t max_fixed_freq;
+    uint8_t emit, len, is_repeat, static_k;
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(256)
+seed_candidates_kernel(FmIndexDev idx, SeedParamsDev P, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
+                       uint64_t n_reads, uint64_t n_bases, const StaticFeat* __restrict__ feats, const uint8_t* __restrict__ attr,
+                       SeedCand* __restrict__ cand, uint8_t* __restrict__ ntriv)
+{
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= n_bases) return;
+    const uint64_t r = find_read(offsets, n_reads, g);
+    const uint64_t base = __ldg(offsets + r);
+    const int64_t L = (int64_t)(__ldg(offsets + r + 1) - base);
+    const int64_t p0 = (int64_t)(g - base);
+    ntriv[g] = 0;
+    if ((int)L < P.start_kmer) return;
     const uint8_t* s = codes + base;
-    const uint8_t* c8 = cls + base;
-    uint8_t* at = attr + base;
+    const uint8_t* at = attr + base;
     const FmTable& RB = idx.t[PBSC_RBWT];
     const FmTable& FB = idx.t[PBSC_BWT];
-
-    // ---- getSeqAttribute, LongReadProbe.cpp:120-182 ----
+    const float inv_hh = __fdiv_rn(1.0f, P.hh_ratio);
+    int64_t initPos = p0;
+    const int dynamicMode = at[p0];
+    const int staticSize = P.start_kmer + P.offset[dynamicMode];
+    const StaticFeat* F = feats + (uint64_t)P.slot_of_mode[dynamicMode] * n_bases + base;
+    const StaticFeat d0 = F[p0];
+    if (d0.count_fake >> 31) return;                                   // static k-mer runs off the read: breaks at once
+    // first iteration (currPos == p0) uses the static k-mer itself as dynamic k-mer: decide triviality without the full state
     {
-        const int range = 300;
-        int front = 0, fear = -1;
-        int boxN = 0, box2 = 0;   // box[-1], box[2]
-        for (int64_t pos = 0; pos < L; pos++)
-        {
-            int left = (int)pos - (range >> 1);
-            int right = (int)pos + (range >> 1);
-            left = max(left, 0);
-            right = min(right, (int)(L - 1));
-            while (fear < right) { fear++; int m = (int)(c8[fear] & 15) - 1; boxN += (m == -1); box2 += (m == 2); }
-            while (front < left) { int m = (int)(c8[front] >> 4) - 1; front++; boxN -= (m == -1); box2 -= (m == 2); }
-            int size = (right - left + 1) - boxN;
-            float ratio = (float)((double)__fdiv_rn((float)box2, (float)size) + 0.0005);
-            at[pos] = ((double)ratio >= 0.02) ? 2 : 1;
-        }
-        if (P.manual) for (int64_t pos = 0; pos < L; pos++) at[pos] = (uint8_t)P.mode;
+        const float thr = P.threshold[dynamicMode][staticSize];
+        const bool valid = d0.fwd_size > 0 && d0.rvc_size > 0;
+        if ((float)d0.freq < thr || !valid || staticSize > P.kmer_up_bound) return;
     }
+    int dcount[4] = {(int)(d0.count_fake & 127), (int)((d0.count_fake >> 7) & 127), (int)((d0.count_fake >> 14) & 127), (int)((d0.count_fake >> 21) & 127)};
+    int dsize = staticSize;
+    Interval df, dr;
+    df.lo = d0.fwd_lo; df.hi = d0.fwd_lo + d0.fwd_size;
+    dr.lo = d0.rvc_lo; dr.hi = d0.rvc_lo + d0.rvc_size;
+    int dfreq = d0.freq;
+    bool isSeed = false, isRepeat = false;
+    int maxFixedMerFreq = dfreq;
+    const int64_t seedPos = p0;
+    for (int64_t currPos = p0; currPos < L; currPos++)
+    {
+        const int staticMode = at[currPos];
+        const StaticFeat S = F[currPos];
+        if (S.count_fake >> 31) break;
+        if (isSeed)
+        {
+            const int b = s[currPos + staticSize - 1];
+            dsize++;
+            dcount[b]++;
+            if (df.valid()) df = update_interval(RB, df, b);
+            if (dr.valid()) dr = update_interval(FB, dr, 3 - b);
+            dfreq = (int)((df.valid() ? (int64_t)df.size() : 0) + (dr.valid() ? (int64_t)dr.size() : 0));
+        }
+        const float dynamicThreshold = P.threshold[dynamicMode][dsize];
+        const float staticThreshold = P.threshold[staticMode][staticSize];
+        const float repeatThreshold = __fmul_rn((float)(5 - ((staticMode >> 1) << 2)), staticThreshold);
+        if ((float)S.freq < staticThreshold || (float)dfreq < dynamicThreshold || !(df.valid() && dr.valid()) || dsize > P.kmer_up_bound)
+        {
+            if (isSeed) { dsize--; dcount[s[seedPos + dsize]]--; }
+            break;
+        }
+        const float freqDiff = __fdiv_rn((float)S.freq, (float)maxFixedMerFreq);
+        if (freqDiff < P.hh_ratio)
+        {
+            initPos++;
+            dsize--; dcount[s[seedPos + dsize]]--;
+            break;
+        }
+        else if (freqDiff > inv_hh)
+        {
+            initPos = currPos - 1;
+            isSeed = false;
+            break;
+        }
+        initPos = seedPos + dsize - 1;
+        isSeed = true;
+        isRepeat |= ((float)S.freq >= repeatThreshold);
+        maxFixedMerFreq = max(maxFixedMerFreq, S.freq);
+    }
+    SeedCand c;
+    c.next = (int32_t)initPos; c.max_fixed_freq = maxFixedMerFreq; c.emit = (isSeed && !low_complexity(dcount, dsize)) ? 1 : 0;
+    c.len = (uint8_t)dsize; c.is_repeat = isRepeat ? 1 : 0; c.static_k = (uint8_t)staticSize; c.pad = 0;
+    cand[g] = c;
+    ntriv[g] = (c.emit || initPos != p0) ? 1 : 0;
+}
 
-    // ---- hybrid k-mer scan, LongReadProbe.cpp:46-104 ----
+// warp per read: follow initPos -> f(initPos) + 1, 32 trivial positions per step
+__global__ void __launch_bounds__(128)
+seed_chain_kernel(SeedParamsDev P, const uint64_t* __restrict__ offsets, uint64_t n_reads, const SeedCand* __restrict__ cand,
+                  const uint8_t* __restrict__ ntriv, pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
+                  uint32_t* __restrict__ seed_count)
+{
+    const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const uint64_t base = offsets[r];
+    const int64_t L = (int64_t)(offsets[r + 1] - base);
     pbsc_seed* out = seeds + region[r];
     uint32_t ns = 0;
-    const float inv_hh = __fdiv_rn(1.0f, P.hh_ratio);
-    for (int64_t initPos = 0; initPos < L; initPos++)
+    int64_t p = 0;
+    if ((int)L < P.start_kmer) p = L;
+    while (p < L)
     {
-        const int dynamicMode = at[initPos];
-        const int staticSize = P.start_kmer + P.offset[dynamicMode];
-        const StaticFeat* F = feats + (uint64_t)P.slot_of_mode[dynamicMode] * n_bases + base;
-        StaticFeat d0 = F[initPos];
-        // dynamicKmer = Log[staticSize][initPos]
-        int dcount[4] = {(int)(d0.count_fake & 127), (int)((d0.count_fake >> 7) & 127), (int)((d0.count_fake >> 14) & 127), (int)((d0.count_fake >> 21) & 127)};
-        const bool dfake = (d0.count_fake >> 31) != 0;
-        int dsize = dfake ? (int)(L - initPos) : staticSize;
-        Interval df, dr;
-        df.lo = d0.fwd_lo; df.hi = d0.fwd_lo + d0.fwd_size;
-        dr.lo = d0.rvc_lo; dr.hi = d0.rvc_lo + d0.rvc_size;
-        int dfreq = d0.freq;
-        bool isSeed = false, isRepeat = false;
-        int maxFixedMerFreq = dfake ? -1 : dfreq;
-        const int64_t seedPos = initPos;
-        for (int64_t currPos = initPos; currPos < L; currPos++)
+        const int64_t q = p + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, q < L && ntriv[base + q] != 0);
+        if (!m) { p += 32; continue; }
+        const int64_t e = p + (__ffs(m) - 1);
+        const SeedCand c = cand[base + e];
+        if (c.emit)
         {
-            const int staticMode = at[currPos];
-            const StaticFeat S = F[currPos];
-            if (S.count_fake >> 31) break;
-            if (isSeed)
+            if (lane == 0)
             {
-                int b = s[currPos + staticSize - 1];
-                dsize++;
-                dcount[b]++;
-                if (df.valid()) df = update_interval(RB, df, b);
-                if (dr.valid()) dr = update_interval(FB, dr, 3 - b);
-                dfreq = (int)((df.valid() ? (int64_t)df.size() : 0) + (dr.valid() ? (int64_t)dr.size() : 0));
+                pbsc_seed sd;
+                sd.start = (int32_t)e; sd.len = c.len; sd.max_fixed_freq = c.max_fixed_freq; sd.is_repeat = c.is_repeat;
+                sd.start_best_k = c.static_k; sd.end_best_k = c.static_k; sd.hitchhiked = 0; sd.static_k = c.static_k;
+                out[ns] = sd;
             }
-            const float dynamicThreshold = P.threshold[dynamicMode][dsize];
-            const float staticThreshold = P.threshold[staticMode][staticSize];
-            const float repeatThreshold = __fmul_rn((float)(5 - ((staticMode >> 1) << 2)), staticThreshold);
-            const int dgetfreq = dfake ? -1 : dfreq;
-            if ((float)S.freq < staticThreshold || (float)dgetfreq < dynamicThreshold || !(df.valid() && dr.valid()) || dsize > P.kmer_up_bound)
-            {
-                if (isSeed) { dsize--; dcount[s[seedPos + dsize]]--; }
-                break;
-            }
-            const float freqDiff = __fdiv_rn((float)S.freq, (float)maxFixedMerFreq);
-            if (freqDiff < P.hh_ratio)
-            {
-                initPos++;
-                dsize--; dcount[s[seedPos + dsize]]--;
-                break;
-            }
-            else if (freqDiff > inv_hh)
-            {
-                initPos = currPos - 1;
-                isSeed = false;
-                break;
-            }
-            initPos = seedPos + dsize - 1;
-            isSeed = true;
-            isRepeat |= ((float)S.freq >= repeatThreshold);
-            maxFixedMerFreq = max(maxFixedMerFreq, S.freq);
+            ns++;
         }
-        if (isSeed && !low_complexity(dcount, dsize))
-        {
-            pbsc_seed sd;
-            sd.start = (int32_t)seedPos; sd.len = dsize; sd.max_fixed_freq = maxFixedMerFreq; sd.is_repeat = isRepeat ? 1 : 0;
-            sd.start_best_k = staticSize; sd.end_best_k = staticSize; sd.hitchhiked = 0; sd.static_k = staticSize;
-            out[ns++] = sd;
-        }
+        p = (int64_t)c.next + 1;
     }
-    seed_count[r] = ns;
+    if (lane == 0) seed_count[r] = ns;
 }
 
 // countSequenceOccurrences(w, pSelBWT) (BWTAlgorithms.cpp:135-141) for the two poles of a seed.
@@ -386,6 +470,7 @@ int alloc_seed_workspace(const pbsc_params* p, const std::vector<uint64_t>& off,
     s.total_slots = region[b.n_reads];
     PBSC_CUDA(w.feats.alloc((uint64_t)P.n_static * b.n_bases));
     PBSC_CUDA(w.cls.alloc(b.n_bases)); PBSC_CUDA(w.attr.alloc(b.n_bases));
+    PBSC_CUDA(w.prefix.alloc(b.n_bases)); PBSC_CUDA(w.cand.alloc(b.n_bases * 2)); PBSC_CUDA(w.ntriv.alloc(b.n_bases));
     PBSC_CUDA(w.seed_tmp.alloc(s.total_slots)); PBSC_CUDA(s.seeds.alloc(s.total_slots));
     PBSC_CUDA(s.region.alloc(b.n_reads + 1)); PBSC_CUDA(s.count.alloc(b.n_reads)); PBSC_CUDA(s.outcast.alloc(b.n_reads));
     PBSC_CUDA(cudaMemcpyAsync(s.region.p, region.data(), (b.n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -406,8 +491,14 @@ int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBu
     }
     if (b.n_reads)
     {
-        seed_scan_kernel<<<(unsigned)((b.n_reads + 127) / 128), 128, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, w.feats.p, w.cls.p,
-                                                                              w.attr.p, w.seed_tmp.p, s.region.p, s.count.p);
+        const unsigned warp_blocks = (unsigned)((b.n_reads * 32 + 127) / 128);
+        const unsigned base_blocks = (unsigned)((b.n_bases + 255) / 256);
+        seed_prefix_kernel<<<warp_blocks, 128, 0, st>>>(b.offsets.p, b.n_reads, w.cls.p, (uint4*)w.prefix.p);
+        seed_attr_kernel<<<base_blocks, 256, 0, st>>>(P, b.offsets.p, b.n_reads, b.n_bases, (const uint4*)w.prefix.p, w.attr.p);
+        seed_candidates_kernel<<<base_blocks, 256, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, w.feats.p, w.attr.p,
+                                                            (SeedCand*)w.cand.p, w.ntriv.p);
+        seed_chain_kernel<<<warp_blocks, 128, 0, st>>>(P, b.offsets.p, b.n_reads, (const SeedCand*)w.cand.p, w.ntriv.p, w.seed_tmp.p, s.region.p, s.count.p);
+        nl += 3;
         seed_bestk_kernel<<<(unsigned)((s.total_slots * 2 + 127) / 128), 128, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, w.seed_tmp.p, s.region.p, s.count.p, s.total_slots);
         seed_hitchhike_kernel<<<(unsigned)((b.n_reads + 127) / 128), 128, 0, st>>>(P, b.n_reads, w.seed_tmp.p, s.seeds.p, s.region.p, s.count.p, s.outcast.p);
         nl += 3;
