@@ -52,6 +52,9 @@ struct FmIndexDev
     FmTable t[2];               // [PBSC_BWT], [PBSC_RBWT]
     const PrefixEntry* prefix;  // 4^k0 entries or nullptr
     int k0;
+    // per idmer (key = sum_j w[j]*4^j): bit 0 = reverse(w) occurs in RBWT, bit 1 = revcomp(w) occurs in BWT
+    const uint8_t* idmer_valid;
+    int idmer_len;
 };
 
 struct Interval   // half-open

@@ -124,6 +124,17 @@ __global__ void set_out_offsets_kernel(uint64_t n_tasks, WalkTask* tasks, const 
     if (i < n_tasks) tasks[i].out_off = off[i];
 }
 
+// which idmers occur on which strand (replaces the 2 x s findInterval steps per query position that buildOverlapbyFMindex,
+// LongReadCorrectByOverlap.cpp:127-152, spends on deciding whether an idmer enters a strand's list)
+__global__ void idmer_valid_kernel(FmIndexDev idx, int s9, uint64_t n_keys, uint8_t* __restrict__ valid)
+{
+    const uint64_t key = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    Interval f, r;
+    tw::both_strands(idx, [&](int j) { return (int)((key >> (2 * j)) & 3); }, s9, f, r);
+    valid[key] = (uint8_t)((f.valid() ? 1 : 0) | (r.valid() ? 2 : 0));
+}
+
 // query of a task: beginningkmer + strBetweenSrcTarget + targetSeed, or its reverse complement when the walk runs from the
 // target towards the source (isFromRtoU, PacBioSelfCorrectionProcess.cpp:176-184)
 __device__ __forceinline__ void task_shape(const WalkTask& tk, int& interval, uint32_t& trgLen, uint32_t& qlen)
@@ -571,6 +582,18 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     const uint64_t n = b.n_reads;
     if (n == 0) return PBSC_OK;
     ThreadEngine E;
+    if (idx->dev.idmer_len != p->idmer_len)
+    {
+        const uint64_t n_keys = 1ull << (2 * p->idmer_len);
+        if (idx->d_idmer_valid) { cudaFree(idx->d_idmer_valid); idx->d_idmer_valid = nullptr; }
+        PBSC_CUDA(cudaMalloc((void**)&idx->d_idmer_valid, n_keys));
+        idx->dev.idmer_valid = nullptr;
+        idmer_valid_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx->dev, p->idmer_len, n_keys, idx->d_idmer_valid);
+        PBSC_CUDA(cudaGetLastError());
+        idx->dev.idmer_valid = idx->d_idmer_valid;
+        idx->dev.idmer_len = p->idmer_len;
+        idx->device_bytes += n_keys;
+    }
     // ---- task index space: one slot per surviving seed ----
     PBSC_CUDA(E.task_base.get(idx, "tw.task_base", n + 1));
     {

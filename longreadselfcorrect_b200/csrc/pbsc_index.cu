@@ -334,6 +334,8 @@ int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt
     idx->device = device;
     idx->dev.prefix = nullptr;
     idx->dev.k0 = 0;
+    idx->dev.idmer_valid = nullptr;
+    idx->dev.idmer_len = 0;
     int rc = PBSC_OK;
     const uint8_t* runs[2] = {bwt_runs, rbwt_runs};
     const uint64_t nr[2] = {bwt_n_runs, rbwt_n_runs}, ns[2] = {bwt_n_symbols, rbwt_n_symbols}, nstr[2] = {bwt_n_strings, rbwt_n_strings};
@@ -396,7 +398,7 @@ int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t
     PBSC_CUDA(cudaSetDevice(device));
     pbsc_index* idx = new pbsc_index();
     idx->device = device;
-    idx->dev.prefix = nullptr; idx->dev.k0 = 0;
+    idx->dev.prefix = nullptr; idx->dev.k0 = 0; idx->dev.idmer_valid = nullptr; idx->dev.idmer_len = 0;
     auto fail = [&](int rc) { pbsc_index_destroy(idx); return rc; };
     for (int w = 0; w < 2; w++)
     {
@@ -499,6 +501,7 @@ void pbsc_index_destroy(pbsc_index* idx)
     cudaSetDevice(idx->device);
     for (int w = 0; w < 2; w++) { if (idx->d_blocks[w]) cudaFree(idx->d_blocks[w]); if (idx->d_dollar[w]) cudaFree(idx->d_dollar[w]); if (idx->d_dmask[w]) cudaFree(idx->d_dmask[w]); }
     if (idx->d_prefix) cudaFree(idx->d_prefix);
+    if (idx->d_idmer_valid) cudaFree(idx->d_idmer_valid);
     for (auto& kv : idx->arena) if (kv.second.p) cudaFree(kv.second.p);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;

@@ -20,6 +20,7 @@ struct pbsc_index
     uint32_t* d_dollar[2] = {nullptr, nullptr};
     uint64_t* d_dmask[2] = {nullptr, nullptr};
     pbsc::PrefixEntry* d_prefix = nullptr;
+    uint8_t* d_idmer_valid = nullptr;
     uint64_t n_symbols[2] = {0, 0}, n_strings[2] = {0, 0}, n_blocks[2] = {0, 0};
     size_t device_bytes = 0;
     cudaStream_t stream = nullptr;

@@ -607,11 +607,17 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
         {
             uint32_t keyF = 0;
             for (int j = 0; j < s9; j++) keyF |= (uint32_t)q[p + j] << (2 * j);
-            Interval f, r;
-            const uint8_t* w = q + p;
-            both_strands(idx, [&](int j) { return (int)w[j]; }, s9, f, r);
-            if (f.valid()) v.sF[H.n9F++] = ((uint64_t)keyF << 32) | p;
-            if (r.valid()) v.sR[H.n9R++] = ((uint64_t)(((1u << (2 * s9)) - 1u) - keyF) << 32) | p;
+            bool fv, rv;
+            if (idx.idmer_valid != nullptr && idx.idmer_len == s9) { const uint8_t b = __ldg(idx.idmer_valid + keyF); fv = b & 1; rv = (b & 2) != 0; }
+            else
+            {
+                Interval f, r;
+                const uint8_t* w = q + p;
+                both_strands(idx, [&](int j) { return (int)w[j]; }, s9, f, r);
+                fv = f.valid(); rv = r.valid();
+            }
+            if (fv) v.sF[H.n9F++] = ((uint64_t)keyF << 32) | p;
+            if (rv) v.sR[H.n9R++] = ((uint64_t)(((1u << (2 * s9)) - 1u) - keyF) << 32) | p;
         }
         sort_desc_ool(v.sF, (long)H.n9F);
         sort_desc_ool(v.sR, (long)H.n9R);
