@@ -144,9 +144,11 @@ __device__ __forceinline__ void task_shape(const WalkTask& tk, int& interval, ui
     qlen = (uint32_t)(tk.k + interval) + trgLen;
 }
 
-__device__ __forceinline__ uint8_t* task_record(const uint32_t* list, uint64_t it, uint8_t* recpool, const uint64_t* rec_off, uint64_t pend_base, uint64_t pend_cap)
+// setup record of task `ti`: speculative tasks have scanned offsets, a read's pending request has a fixed-size slot
+// (pend_cap != 0 selects the latter)
+__device__ __forceinline__ uint8_t* task_record(uint64_t ti, uint8_t* recpool, const uint64_t* rec_off, uint64_t pend_base, uint64_t pend_cap)
 {
-    return list ? recpool + pend_base + (uint64_t)list[it] * pend_cap : recpool + rec_off[it];
+    return pend_cap ? recpool + pend_base + ti * pend_cap : recpool + rec_off[ti];
 }
 
 // thread per task: everything the constructor of LongReadSelfCorrectByOverlap computes (terminal intervals, query idmer
@@ -158,13 +160,14 @@ setup_tasks_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
 {
     const uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (it >= n_items) return;
-    WalkTask& tk = tasks[list ? list[it] : it];
+    const uint64_t ti = list ? list[it] : it;
+    WalkTask& tk = tasks[ti];
     if (!tk.valid) return;
     int interval; uint32_t trgLen, qlen;
     task_shape(tk, interval, trgLen, qlen);
     if (interval < 0 || tk.k <= 0) { tk.valid = 0; tk.status = PBSC_WALK_UNSUPPORTED; return; }
     tw::SetupView v;
-    tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
+    tw::setup_view(task_record(ti, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
     const uint8_t* read = codes + offsets[tk.read];
     const uint8_t* pth = read + tk.src_end + 1;
     const uint8_t* trgS = read + tk.trg_start;
@@ -196,11 +199,12 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
                    unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
                    const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
                    unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy, uint32_t* nodepool,
-                   unsigned long long* pool_used, uint64_t pool_cap)
+                   unsigned long long* pool_used, uint64_t pool_cap, tw::Caps caps, const unsigned int* n_items_dev, int last_pass)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     tw::TScratch lane;
-    tw::carve(scratch + tid * stride, P.node_cap, lane);
+    tw::carve(scratch + tid * stride, P.node_cap, caps, lane);
+    if (n_items_dev) n_items = *n_items_dev;      // a later pass: its item count was produced on the device
     tw::State S;
     S.status = 0; S.n = 0;
     WalkTask* tk = nullptr;
@@ -215,13 +219,14 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
             {
                 const unsigned long long it = atomicAdd(counter, 1ull);
                 if (it >= n_items) { exhausted = true; break; }
-                tk = &tasks[list ? list[it] : it];
+                const uint64_t ti = list ? list[it] : it;
+                tk = &tasks[ti];
                 if (!tk->valid) continue;
                 int interval; uint32_t trgLen, qlen;
                 task_shape(*tk, interval, trgLen, qlen);
                 tw::SetupView v;
-                tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
-                tw::begin_walk(S, idx, P, lane, v, P.node_cap, minSA);
+                tw::setup_view(task_record(ti, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
+                tw::begin_walk(S, idx, P, lane, v, P.node_cap, caps, minSA);
                 hdr = v.hdr;
                 active = true;
                 done++;
@@ -234,7 +239,10 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
             if (tw::walk_continues(S)) tw::one_level(S);
             if (!tw::walk_continues(S))
             {
-                const int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
+                int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
+                // the last pass carries everything the reference's loop can hold (-l leaves, 4 children each); only the
+                // label tree and the result list are bounded, and running out of those is reported, not hidden
+                if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_WALK_OVERFLOW;
                 tk->out_len = 0;
                 tk->status = st;
                 if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
@@ -252,12 +260,13 @@ materialize_kernel(uint64_t n_items, const uint32_t* __restrict__ list, WalkTask
 {
     const uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (it >= n_items) return;
-    WalkTask& tk = tasks[list ? list[it] : it];
+    const uint64_t ti = list ? list[it] : it;
+    WalkTask& tk = tasks[ti];
     if (!tk.valid || tk.status != PBSC_TASK_MATERIALIZE) return;
     int interval; uint32_t trgLen, qlen;
     task_shape(tk, interval, trgLen, qlen);
     tw::SetupView v;
-    tw::setup_view(task_record(list, it, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, min_overlap, s9, v);
+    tw::setup_view(task_record(ti, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, min_overlap, s9, v);
     uint32_t mlen = 0;
     const int st = tw::materialize(v, min_overlap, nodepool, outpool + tk.out_off, tk.out_cap, &mlen);
     tk.out_len = st == 1 ? mlen : 0;
@@ -513,8 +522,13 @@ struct ThreadEngine
 {
     ArenaPtr<WalkTask> spec, pending;
     ArenaPtr<uint64_t> task_base, caps, cap_off, rec_caps, rec_off;
-    ArenaPtr<uint8_t> outpool, recpool, scratch, wscratch;
+    ArenaPtr<uint8_t> outpool, recpool, scratch, wscratch, hscratch;
     ArenaPtr<uint32_t> heavy_list, nodepool;
+    uint64_t heavy_cap = 0;
+    tw::Caps light, heavy;
+    size_t stride = 0, hstride = 0;
+    int blocks = 0, hblocks = 0;
+    bool heavy_engine_warp = false;
     ArenaPtr<unsigned long long> pool_used;
     uint64_t pool_cap = 0;
     ArenaPtr<unsigned int> n_heavy;
@@ -528,29 +542,42 @@ struct ThreadEngine
     uint64_t pend_rec_base = 0, pend_rec_cap = 0;
 };
 
+// Light pass, then the walks that outgrew it among walks of their own weight, then materialisation.  `is_pending` selects
+// where the setup records live (a read's pending request has a fixed-size slot).
 static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, Workspace& w, DeviceBatch& b, uint64_t n_items, const uint32_t* list,
-                       WalkTask* tasks, uint64_t minSA, int blocks, size_t stride)
+                       WalkTask* tasks, bool is_pending, uint64_t minSA, uint64_t* launches)
 {
     cudaStream_t st = idx->stream;
+    const uint64_t pcap = is_pending ? E.pend_rec_cap : 0;
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
     setup_tasks_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, P, n_items, list, tasks, b.codes.p, b.offsets.p, E.recpool.p, E.rec_off.p,
-                                                                         E.pend_rec_base, E.pend_rec_cap);
-    const uint64_t threads = (uint64_t)blocks * TW_BLOCK;
-    int nb = blocks;
+                                                                         E.pend_rec_base, pcap);
+    const uint64_t threads = (uint64_t)E.blocks * TW_BLOCK;
+    int nb = E.blocks;
     if (n_items < threads) nb = (int)((n_items + TW_BLOCK - 1) / TW_BLOCK);
     if (nb < 1) nb = 1;
-    PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 4, st));
+    PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 8, st));
     PBSC_CUDA(cudaMemsetAsync(E.pool_used.p, 0, 8, st));
-    walk_levels_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
-                                                E.pend_rec_base, E.pend_rec_cap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
-                                                E.nodepool.p, E.pool_used.p, E.pool_cap);
-    materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, E.recpool.p, E.rec_off.p, E.pend_rec_base, E.pend_rec_cap,
-                                                                         E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
-    // the walks that outgrew the thread engine, on the warp engine (the kernel reads the count from the device)
+    walk_levels_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
+                                                E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
+                                                E.nodepool.p, E.pool_used.p, E.pool_cap, E.light, nullptr, 0);
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
-    walk_heavy_kernel<<<E.wblocks, HEAVY_WARPS * 32, 0, st>>>(idx->dev, E.Pw, E.wscratch.p, E.wstride, w.counters.p, E.n_heavy.p, E.heavy_list.p, tasks,
-                                                             b.codes.p, b.offsets.p, E.outpool.p, minSA);
+    if (E.heavy_engine_warp)
+    {
+        // the walks that outgrew the light pass, on the warp engine (the kernel reads the count from the device)
+        walk_heavy_kernel<<<E.wblocks, HEAVY_WARPS * 32, 0, st>>>(idx->dev, E.Pw, E.wscratch.p, E.wstride, w.counters.p, E.n_heavy.p, E.heavy_list.p, tasks,
+                                                                 b.codes.p, b.offsets.p, E.outpool.p, minSA);
+    }
+    else
+    {
+        walk_levels_kernel<<<E.hblocks, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, E.recpool.p, E.rec_off.p,
+                                                           E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p + E.heavy_cap,
+                                                           E.n_heavy.p + 1, E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, E.n_heavy.p, 1);
+    }
+    materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, E.recpool.p, E.rec_off.p, E.pend_rec_base, pcap,
+                                                                         E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
     PBSC_CUDA(cudaGetLastError());
+    if (launches) *launches += 4;
     return PBSC_OK;
 }
 
@@ -617,21 +644,39 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     const uint32_t pending_cap = (uint32_t)align_up((size_t)(1.2 * (hmax[0] + 10)) + 2 * 64 + hmax[1] + 64, 16);
     E.pend_rec_cap = tw::setup_record_bytes(need_q, std::max<uint32_t>(hmax[1], 64), p->min_kmer, p->idmer_len);
     ExtParamsDev P;
-    const uint32_t t_node_cap = 4096;                 // light walks; a walk that needs more is handed to the warp engine
+    const uint32_t t_node_cap = 4096;                 // light walks; a walk that needs more goes to the heavy pass
     make_ext_params(p, P, w.q_cap, t_node_cap, pending_cap);
     make_ext_params(p, E.Pw, w.q_cap, std::max<uint32_t>(w.node_cap, 1u << 15), pending_cap);
-    E.wstride = warp_scratch_bytes(E.Pw.q_cap, E.Pw.node_cap, E.Pw.merged_cap);
-    E.wblocks = idx->sm_count * 2;
-    PBSC_CUDA(E.wscratch.get(idx, "tw.wscratch", E.wstride * (size_t)E.wblocks * HEAVY_WARPS));
+    {
+        const char* e = getenv("PBSC_HEAVY");
+        E.heavy_engine_warp = e && strcmp(e, "warp") == 0;
+    }
     const uint64_t minSA = p->pb_coverage > 60 ? (uint64_t)((p->pb_coverage / 60) * 3) : 3;
-    int blocks = 0;
-    int rc = thread_geometry(idx->device, &blocks);
+    int rc = thread_geometry(idx->device, &E.blocks);
     if (rc != PBSC_OK) return rc;
-    const size_t stride = tw::thread_scratch_bytes(t_node_cap);
-    PBSC_CUDA(E.scratch.get(idx, "tw.scratch", stride * (size_t)blocks * TW_BLOCK));
+    E.light = tw::Caps{8, 32, 40, 32};
+    // everything extendOverlap's loop can hold: -l live leaves, four children each (LongReadCorrectByOverlap.cpp:161)
+    E.heavy = tw::Caps{(uint32_t)OLD_CAP, (uint32_t)NEW_CAP, (uint32_t)RING_SLOTS, (uint32_t)RES_CAP};
+    E.stride = tw::thread_scratch_bytes(t_node_cap, E.light);
+    PBSC_CUDA(E.scratch.get(idx, "tw.scratch", E.stride * (size_t)E.blocks * TW_BLOCK));
+    if (E.heavy_engine_warp)
+    {
+        E.wstride = warp_scratch_bytes(E.Pw.q_cap, E.Pw.node_cap, E.Pw.merged_cap);
+        E.wblocks = idx->sm_count * 2;
+        PBSC_CUDA(E.wscratch.get(idx, "tw.wscratch", E.wstride * (size_t)E.wblocks * HEAVY_WARPS));
+    }
+    else
+    {
+        E.hstride = tw::thread_scratch_bytes(E.Pw.node_cap, E.heavy);
+        E.hblocks = E.blocks;      // same residency as the light pass: the pass is latency-bound, not capacity-bound
+        const char* e = getenv("PBSC_TW_HEAVY_BLOCKS_PER_SM");
+        if (e && atoi(e) > 0) E.hblocks = idx->sm_count * atoi(e);
+        PBSC_CUDA(E.hscratch.get(idx, "tw.hscratch", E.hstride * (size_t)E.hblocks * TW_BLOCK));
+    }
     PBSC_CUDA(E.spec.get(idx, "tw.spec", n_tasks)); PBSC_CUDA(E.pending.get(idx, "tw.pending", n)); PBSC_CUDA(E.caps.get(idx, "tw.caps", n_tasks + 1)); PBSC_CUDA(E.cap_off.get(idx, "tw.cap_off", n_tasks + 1));
     PBSC_CUDA(E.rec_caps.get(idx, "tw.rec_caps", n_tasks + 1)); PBSC_CUDA(E.rec_off.get(idx, "tw.rec_off", n_tasks + 1));
-    PBSC_CUDA(E.heavy_list.get(idx, "tw.heavy_list", std::max<uint64_t>(n_tasks, n) + 1)); PBSC_CUDA(E.n_heavy.get(idx, "tw.n_heavy", 1));
+    E.heavy_cap = std::max<uint64_t>(n_tasks, n) + 1;
+    PBSC_CUDA(E.heavy_list.get(idx, "tw.heavy_list", 2 * E.heavy_cap)); PBSC_CUDA(E.n_heavy.get(idx, "tw.n_heavy", 2));
     E.pool_cap = std::max<uint64_t>(n_tasks, n) * (uint64_t)(w.node_cap >= (1u << 16) ? 2048 : 256) + 65536;
     PBSC_CUDA(E.nodepool.get(idx, "tw.nodepool", E.pool_cap)); PBSC_CUDA(E.pool_used.get(idx, "tw.pool_used", 1));
     PBSC_CUDA(E.states.get(idx, "tw.states", n)); PBSC_CUDA(E.stalled.get(idx, "tw.stalled", n)); PBSC_CUDA(E.n_stalled.get(idx, "tw.n_stalled", 1));
@@ -665,9 +710,8 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     // ---- round 1: all speculative walks ----
     if (n_tasks)
     {
-        rc = launch_walk(idx, P, E, w, b, n_tasks, nullptr, E.spec.p, minSA, blocks, stride);
+        rc = launch_walk(idx, P, E, w, b, n_tasks, nullptr, E.spec.p, false, minSA, &nl);
         if (rc != PBSC_OK) return rc;
-        nl += 2;
     }
     StitchParams C;
     C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split;
@@ -685,9 +729,8 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         if (ns == 0) break;
         if (round > 100000) { set_error("stitch did not converge"); return PBSC_ERR_INTERNAL; }
         // the stalled reads' requests sit in pending[read]
-        rc = launch_walk(idx, P, E, w, b, ns, E.stalled.p, E.pending.p, minSA, blocks, stride);
+        rc = launch_walk(idx, P, E, w, b, ns, E.stalled.p, E.pending.p, true, minSA, &nl);
         if (rc != PBSC_OK) return rc;
-        nl += 2;
     }
     if (launches) *launches += nl;
     return PBSC_OK;

@@ -25,14 +25,11 @@
 namespace pbsc {
 namespace tw {
 
-// The thread engine only carries LIGHT walks: at most TW_OLD live leaves and TW_NEW children per level.  A walk that
-// outgrows this (repeats, ExceedLeaves/ExceedDepth cases: a few percent of the walks, but each one costs 10-100x a light
-// walk and would stall the other 31 lanes of its warp) stops with PBSC_WALK_HEAVY and is re-walked from scratch by the
-// warp-cooperative engine (pbsc_walk.cuh), which is the right shape for a wide frontier.
-constexpr int TW_OLD = 8;
-constexpr int TW_NEW = 32;
-constexpr int TW_RINGS = 40;
-constexpr int TW_RES = 32;
+// A pass of the thread engine carries walks of at most `old_cap` live leaves and `new_cap` children per level.  A walk
+// that outgrows its pass (repeats, ExceedLeaves/ExceedDepth cases: a few percent of the walks, but each one costs 10-100x a
+// light walk and would stall the other 31 lanes of its warp) stops with PBSC_WALK_HEAVY and is re-walked from scratch in the
+// next pass, among walks of its own weight.
+struct Caps { uint32_t old_cap, new_cap, rings, res; };   // per-lane capacities of one pass of the thread engine
 #define PBSC_WALK_HEAVY (-102)
 
 struct TScratch
@@ -52,25 +49,25 @@ struct TScratch
 
 __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
-__host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap)
+__host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap, Caps c)
 {
     size_t b = 0;
-    b += sizeof(Leaf) * (TW_OLD + TW_NEW);
-    b += sizeof(double) * TW_RINGS * RING_LEN;
+    b += sizeof(Leaf) * (size_t)(c.old_cap + c.new_cap);
+    b += sizeof(double) * (size_t)c.rings * RING_LEN;
     b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
-    b += sizeof(WalkResult) * TW_RES;
-    b += align_up(TW_RINGS, 16);
+    b += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
+    b += align_up(c.rings, 16);
     return align_up(b, 128);
 }
 
-__device__ inline void carve(uint8_t* base, uint32_t node_cap, TScratch& w)
+__device__ inline void carve(uint8_t* base, uint32_t node_cap, Caps c, TScratch& w)
 {
     uint8_t* p = base;
-    w.oldL = (Leaf*)p; p += sizeof(Leaf) * TW_OLD;
-    w.newL = (Leaf*)p; p += sizeof(Leaf) * TW_NEW;
-    w.rings = (double*)p; p += sizeof(double) * TW_RINGS * RING_LEN;
+    w.oldL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.old_cap;
+    w.newL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.new_cap;
+    w.rings = (double*)p; p += sizeof(double) * (size_t)c.rings * RING_LEN;
     w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
-    w.res = (WalkResult*)p; p += sizeof(WalkResult) * TW_RES;
+    w.res = (WalkResult*)p; p += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
     w.ringStack = p;
     w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.start4 = w.pos4 = nullptr;
 }
@@ -142,6 +139,7 @@ struct State
     uint32_t n;
     uint64_t curLen, curK, maxLength, minLength, maxIndel, minSA;
     uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, nFresh, node_cap, phase;
+    Caps cap;
     bool dup;
     int status;
 };
@@ -151,7 +149,7 @@ __device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ring
 __device__ __forceinline__ int ring_take(State& S)
 {
     if (S.nFree) return (int)S.s.ringStack[--S.nFree];
-    return S.nFresh < (uint32_t)TW_RINGS ? (int)S.nFresh++ : -1;
+    return S.nFresh < S.cap.rings ? (int)S.nFresh++ : -1;
 }
 
 static __device__ __noinline__ void refine(State& S, Leaf* bank, uint32_t cnt, int K)
@@ -314,7 +312,7 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
         if (!mask && parent.local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, parent.tailCount, thr - 1);
         if (!mask) continue;
         const uint32_t cnt = __popc(mask);
-        if (m + cnt > (uint32_t)TW_NEW) { S.status = PBSC_WALK_HEAVY; return 0; }
+        if (m + cnt > S.cap.new_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
         if (S.nNodes + cnt > S.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
         uint32_t j = 0;
         #pragma unroll 1
@@ -475,7 +473,7 @@ static __device__ __noinline__ void terminated(State& S, uint32_t m)
         int slot = L.res_first;
         if (slot == -1)
         {
-            if (S.nRes >= TW_RES) { S.status = PBSC_WALK_HEAVY; return; }
+            if (S.nRes >= S.cap.res) { S.status = PBSC_WALK_HEAVY; return; }
             slot = (int)++S.nRes;
         }
         WalkResult r; r.err = L.global_err; r.node = L.node; r.i = ilast; r.depth = (uint32_t)S.curLen; r.pad = 0;
@@ -662,10 +660,10 @@ __device__ __forceinline__ uint32_t match5_mask(const State& S, uint32_t tail4)
 
 // start a walk from its setup record
 __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, const ExtParamsDev& P, const TScratch& lane_scratch, const SetupView& v,
-                                           uint32_t node_cap, uint64_t minSA)
+                                           uint32_t node_cap, Caps cap, uint64_t minSA)
 {
     const SetupHdr H = *v.hdr;
-    S.idx = &idx; S.P = &P; S.s = lane_scratch; S.node_cap = node_cap;
+    S.idx = &idx; S.P = &P; S.s = lane_scratch; S.node_cap = node_cap; S.cap = cap;
     S.s.q = v.q; S.s.start4 = v.start4; S.s.pos4 = v.pos4; S.s.termF = v.termF; S.s.termR = v.termR; S.s.hash = v.hash; S.s.sF = v.sF; S.s.sR = v.sR;
     S.status = H.status0;
     S.qlen = H.qlen; S.k = H.k; S.maxOverlap = H.k + 2; S.trgLen = H.trgLen; S.minSA = minSA;
@@ -753,12 +751,12 @@ static __device__ __noinline__ void one_level(State& S)
     for (uint32_t j = 0; j < m; j++)
     {
         if (!S.s.newL[j].alive) continue;
-        if (nn < TW_OLD) S.s.oldL[nn] = S.s.newL[j];
+        if (nn < S.cap.old_cap) S.s.oldL[nn] = S.s.newL[j];
         nn++;
     }
     S.n = nn;
     // more live leaves than this engine carries, and the reference's loop would go on: hand the walk over
-    if (nn > (uint32_t)TW_OLD && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
+    if (nn > S.cap.old_cap && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
 }
 
 #define PBSC_TASK_MATERIALIZE 2   // walk succeeded; the merged sequence is still to be written from the saved label tree
