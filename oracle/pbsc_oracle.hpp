@@ -3,7 +3,8 @@
 //
 // A from-scratch restatement, in plain sequential C++, of the algorithm the reference
 // (ccuchengwei/LongReadSelfCorrect, mounted at /root/reference) runs for
-// `stride pbcorrect --nodp`.  Every function cites the reference file:line it follows.
+// `stride pbcorrect` (the DP/MSA fallback lives in pbsc_oracle_dp.hpp).  Every function cites the
+// reference file:line it follows.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may build or execute anything under oracle/; the product
 // (longreadselfcorrect_b200/) never includes, links or calls it.
@@ -1147,6 +1148,10 @@ struct FMExtend
 // ---------------------------------------------------------------------------------
 // PacBioSelfCorrectionProcess — PacBio/PacBioSelfCorrectionProcess.cpp:23-206
 // ---------------------------------------------------------------------------------
+}  // namespace pbo
+#include "pbsc_oracle_dp.hpp"
+namespace pbo {
+
 struct PairRecord   // one FM-extension attempt, for structured parity checks
 {
     int srcStart, trgStart, extendKmerSize, dis, status;
@@ -1163,6 +1168,8 @@ struct ReadResult
     SeedVector seeds, outcastSeeds;
     bool outcastWritten = false, seedWritten = false;
     uint64_t occSeed = 0, occExtend = 0;   // rank queries issued by each phase (roofline numerator)
+    uint64_t dpCells = 0, dpRows = 0, dpAttempts = 0, occDP = 0;   // banded-DP cells / rows kept / fallbacks tried / LF steps of the DP fallback
+    std::vector<std::pair<int,int>> dpFailLog;                     // extend/<id>.dp rows
     std::vector<PairRecord> pairs;
     std::vector<std::pair<std::pair<int,int>,int>> extLog;   // extend/<id>.ext rows
     std::vector<float> ratioLog;
@@ -1220,12 +1227,35 @@ struct Corrector
         return isFMExtensionSuccess;
     }
 
-    // DP/MSA fallback (PacBioSelfCorrectionProcess.cpp:208-245): only --nodp is restated here.
-    bool correctByMSAlignment(const SeedFeature&, const SeedFeature&, const std::string&, std::string&, ReadResult&)
+    // DP/MSA fallback — PacBioSelfCorrectionProcess.cpp:208-245 (alignment and consensus in pbsc_oracle_dp.hpp)
+    bool correctByMSAlignment(const SeedFeature& source, const SeedFeature& target, const std::string& in, std::string& out, ReadResult& result)
     {
         if (P.NoDp) return false;
-        fprintf(stderr, "pbsc_oracle: the DP/MSA fallback is not restated; run with --nodp\n");
-        exit(EXIT_FAILURE);
+        int interval = target.seedStartPos - source.seedEndPos - 1;
+        int extendKmerSize = std::min(source.endBestKmerSize, target.startBestKmerSize) - 2;
+        if (source.isRepeat || target.isRepeat)
+        {
+            extendKmerSize = std::min(source.seedLen, target.seedLen);
+            extendKmerSize = std::min(extendKmerSize, P.startKmerLen + 2);
+        }
+        std::string path = source.seedStr.substr(source.seedLen - extendKmerSize) + in.substr(source.seedEndPos + 1, interval) + target.seedStr;
+        double identity = 0.65;
+        size_t totalMaxFixedMerFreq = source.maxFixedMerFreq + target.maxFixedMerFreq, min_call_coverage = 15;
+        identity += (totalMaxFixedMerFreq > 50 ? 0.05 : 0);
+        identity += (totalMaxFixedMerFreq > 100 ? 0.05 : 0);
+        min_call_coverage = totalMaxFixedMerFreq > 50 ? totalMaxFixedMerFreq * 0.4 : min_call_coverage;
+        const uint64_t occBefore = OccCounter::n();
+        Msa msa = buildMultipleAlignment(path, extendKmerSize, extendKmerSize, path.length() / 10, identity, P.PBcoverage, P.indices, &result.dpCells);
+        result.occDP += OccCounter::n() - occBefore;
+        result.dpRows += msa.rows.size() - 1;
+        result.dpAttempts++;
+        if (msa.rows.size() <= 3) return false;
+        out = msa.consensus((int)min_call_coverage);
+        out.erase(0, extendKmerSize);
+        result.correctedLen += out.length();
+        result.seedDis += interval;
+        result.DPNum++;
+        return true;
     }
 
     // PacBioSelfCorrectionProcess.cpp:56-157
@@ -1267,6 +1297,7 @@ struct Corrector
                 if (isMSAlignmentSuccess) source.append(mergedSeq, target);
                 else
                 {
+                    result.dpFailLog.push_back(std::make_pair(source.seedStartPos, target.seedStartPos));
                     if (P.Split) pieceVec.push_back(target);
                     else
                     {
@@ -1298,7 +1329,7 @@ struct Corrector
         result.ratioLog = probe.ratioLog;
         initCorrect(readSeq, seedVec, pieceVec, result);
         result.occSeed = occ1 - occ0;
-        result.occExtend = OccCounter::n() - occ1;
+        result.occExtend = OccCounter::n() - occ1 - result.occDP;
         result.merge = !pieceVec.empty();
         result.totalReadsLen = readSeq.length();
         for (const auto& iter : pieceVec) result.correctedStrs.push_back(iter.seedStr);

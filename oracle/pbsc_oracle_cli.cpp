@@ -134,7 +134,8 @@ int main(int argc, char** argv)
             {
                 std::ofstream x((P.directory + "extend/" + r.readid + ".ext").c_str());
                 std::ofstream d((P.directory + "extend/" + r.readid + ".dp").c_str());
-                for (auto& row : r.extLog) { x << row.first.first << "\t" << row.first.second << "\t" << row.second << "\n"; if (P.NoDp) d << row.first.first << "\t" << row.first.second << "\n"; }
+                for (auto& row : r.extLog) x << row.first.first << "\t" << row.first.second << "\t" << row.second << "\n";
+                for (auto& row : r.dpFailLog) d << row.first << "\t" << row.second << "\n";
             }
         }
         if (r.merge)
@@ -185,8 +186,14 @@ int main(int argc, char** argv)
                   << "ExceedLeaveNum: " << exceedLeaveNum << ", ratio: " << (float)(exceedLeaveNum * 100) / (DPNum + OutcastNum) << "%\n"
                   << "DisBetweenSeeds: " << seedDis / totalWalkNum << "\n";
     }
-    uint64_t occSeed = 0, occExtend = 0, walkAttempts = 0;
-    for (const auto& r : results) { occSeed += r.occSeed; occExtend += r.occExtend; walkAttempts += r.pairs.size(); }
+    uint64_t occSeed = 0, occExtend = 0, walkAttempts = 0, dpCells = 0, dpRows = 0, dpAttempts = 0, occDP = 0;
+    for (const auto& r : results)
+    {
+        occSeed += r.occSeed; occExtend += r.occExtend; walkAttempts += r.pairs.size();
+        dpCells += r.dpCells; dpRows += r.dpRows; dpAttempts += r.dpAttempts; occDP += r.occDP;
+    }
+    fprintf(stderr, "[pbsc_oracle] dp fallbacks %llu, rows kept %llu, band cells %llu, LF steps %llu\n", (unsigned long long)dpAttempts,
+            (unsigned long long)dpRows, (unsigned long long)dpCells, (unsigned long long)occDP);
     fprintf(stderr, "[pbsc_oracle] %zu reads, %.3f s, threads %d, rank queries %llu (seed %llu, extend %llu), walks %llu\n", reads.size(), secs, threads,
             (unsigned long long)occTotal, (unsigned long long)occSeed, (unsigned long long)occExtend, (unsigned long long)walkAttempts);
     return 0;

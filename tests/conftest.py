@@ -80,3 +80,21 @@ def oracle_tiny100(oracle_bin, golden, tmp_path_factory):
                    ["-c", "100", "-g", "10", "--nodp", "--debugseed"], dump=dump)
     recs = [json.loads(l) for l in open(dump)]
     return {"dir": out, "dump": recs, "stdout": r.stdout}
+
+
+def _oracle_dp_run(oracle_bin, golden, tmp_path_factory, name, opts):
+    d = tmp_path_factory.mktemp("oracle_dp_" + name)
+    out = str(d / "out")
+    r = run_oracle(oracle_bin, os.path.join(golden, "tiny"), os.path.join(golden, "tiny.reads.fa"), out, opts + ["--debugseed"], threads=8)
+    return {"dir": out, "stdout": r.stdout}
+
+
+@pytest.fixture(scope="session")
+def oracle_tiny_dp(oracle_bin, golden, tmp_path_factory):
+    """Oracle run with DEFAULT options (DP / multiple-alignment fallback on), -c 30 -g 5."""
+    return _oracle_dp_run(oracle_bin, golden, tmp_path_factory, "tiny", ["-c", "30", "-g", "5"])
+
+
+@pytest.fixture(scope="session")
+def oracle_tiny100_dp(oracle_bin, golden, tmp_path_factory):
+    return _oracle_dp_run(oracle_bin, golden, tmp_path_factory, "tiny100", ["-c", "100", "-g", "10"])

@@ -15,6 +15,12 @@ Fixture `tiny`: 20 kb uniform genome (seed 11) with one injected repeat family, 
     tiny.ext.tsv         concatenated extend/<id>.ext dumps (failed walks + failure code)
     tiny.fm_queries.txt / tiny.fm_bwt.txt / tiny.fm_rbwt.txt   findInterval inputs and reference (lower upper)
 Fixture `tiny100`: the same reads corrected with `-c 100 -g 10` (different pool, offsets and thresholds).
+
+    python tests/golden/make_golden.py dp
+
+adds the DEFAULT-option fixtures (DP / multiple-alignment fallback on) from the committed tiny index and reads:
+    tiny.dp.correct.fa, tiny.dp.discard.fa, tiny.dp.summary.txt, tiny.dp.dpfail.tsv (extend/<id>.dp rows: pairs where the
+    DP fallback failed too), and the same for tiny100.
 """
 import os
 import shutil
@@ -95,5 +101,29 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def dp_fixtures():
+    tmp = tempfile.mkdtemp(prefix="pbsc_golden_dp_")
+    reads = os.path.join(HERE, "tiny.reads.fa")
+    n = sum(1 for l in open(reads) if l.startswith(">"))
+    for name, opts in (("tiny", ["-c", "30", "-g", "5"]), ("tiny100", ["-c", "100", "-g", "10"])):
+        out = os.path.join(tmp, name + "_out")
+        r = run([STRIDE, "pbcorrect", "-t", "1", "-p", os.path.join(HERE, "tiny"), "-o", out] + opts + ["--debugseed", reads], cwd=tmp)
+        shutil.copy(os.path.join(out, "correct.fa"), os.path.join(HERE, name + ".dp.correct.fa"))
+        shutil.copy(os.path.join(out, "discard.fa"), os.path.join(HERE, name + ".dp.discard.fa"))
+        summary = "\n".join(l for l in r.stdout.splitlines() if not l.startswith("Time of"))
+        open(os.path.join(HERE, name + ".dp.summary.txt"), "w").write(summary + "\n")
+        with open(os.path.join(HERE, name + ".dp.dpfail.tsv"), "w") as f:
+            for i in range(n):
+                p = os.path.join(out, "extend", f"r{i}.dp")
+                f.write(f"#r{i}\n")
+                if os.path.exists(p):
+                    f.write(open(p).read())
+    shutil.rmtree(tmp)
+    print("DP golden fixtures written to", HERE)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "dp":
+        dp_fixtures()
+    else:
+        main()
