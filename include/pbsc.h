@@ -158,7 +158,9 @@ int pbsc_extend_batch(pbsc_index* idx, const pbsc_params* p, uint64_t n_pairs,
                       const int32_t* min_sa, int32_t* status, char* out, uint64_t out_cap, uint64_t* out_offsets);
 
 /* ---- whole hot path for a batch of reads: PacBioSelfCorrectionProcess::process
- *      (PacBio/PacBioSelfCorrectionProcess.cpp:23-206) with --nodp semantics for failed walks.
+ *      (PacBio/PacBioSelfCorrectionProcess.cpp:23-245): seeds, FM extension and, unless p->no_dp, the DP /
+ *      multiple-alignment fallback for failed walks (correctByMSAlignment, LongReadOverlap::buildMultipleAlignment,
+ *      Overlapper::extendMatch, MultipleAlignment::calculateBaseConsensus).
  *      pieces_out holds the corrected pieces of read r, concatenated, at piece_offsets[...]; piece p of read r
  *      is pieces_out[piece_offsets[first_piece[r]+p] .. piece_offsets[first_piece[r]+p+1]).  Reads with
  *      stats[r].merge==0 have no pieces (they go to discard.fa).  first_piece has n_reads+1 entries. ---- */
@@ -189,6 +191,9 @@ typedef struct pbsc_timing
     uint64_t kernel_launches;
     uint64_t seed_pairs;     /* FM walks attempted */
     uint64_t rank_queries;   /* occ() lookups issued by the kernels (0 unless built with PBSC_COUNT_OCC) */
+    float dp_ms;             /* part of extend_ms spent in the DP / multiple-alignment fallback */
+    uint64_t dp_jobs;        /* failed walks that went through correctByMSAlignment */
+    uint64_t dp_rows;        /* overlapping reads retrieved and aligned for them */
 } pbsc_timing;
 int pbsc_last_timing(pbsc_timing* t);
 

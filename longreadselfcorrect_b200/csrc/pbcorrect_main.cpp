@@ -165,11 +165,6 @@ static void parseOptions(int argc, char** argv)
         std::cerr << SUBPROGRAM ": --debugseed/--onlyseed diagnostics are not part of this build (hot path only)\n";
         exit(EXIT_FAILURE);
     }
-    if (!P.no_dp)
-    {
-        std::cerr << SUBPROGRAM ": the DP/MSA fallback for failed walks is not in this build yet; run with --nodp\n";
-        exit(EXIT_FAILURE);
-    }
     opt::readsFile = argv[optind++];
 }
 

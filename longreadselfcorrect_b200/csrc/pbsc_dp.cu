@@ -1,0 +1,688 @@
+// pbsc_dp.cu — DP / multiple-alignment fallback for seed pairs the FM-index walk could not bridge
+// (PacBioSelfCorrectionProcess::correctByMSAlignment, PacBio/PacBioSelfCorrectionProcess.cpp:208-245).
+//
+// Per failed seed pair (a "job"), with query = beginningkmer + raw read between the seeds + target seed:
+//   dp_collect_kernel   SA intervals of the query's first k-mer and of its last k-mer on both strands; up to `coverage`
+//                       suffix-array rows are taken from each (LongReadOverlap::retrieveStr, PacBio/LongReadOverlap.cpp:667-756)
+//   dp_retrieve_kernel  thread per row: spell the read onwards from the k-mer by LF-mapping, one 32-byte sector per step
+//                       (the same block holds the BWT symbol, RLBWT::getChar, and its rank, RLBWT::getOcc)
+//   dp_align_kernel     warp per row: Overlapper::extendMatch (Thirdparty/overlapper.cpp:421-701): 201-cell band, +1/-1/-8;
+//                       a band column lives in registers (7 cells per lane), the dependency along the column is a max-scan,
+//                       only three "equals predecessor" bits per cell go to memory for the traceback, whose homopolymer-aware
+//                       tie-breaks are replayed exactly; then the overlap-length / identity filters of
+//                       LongReadOverlap::retrieveMatches (PacBio/LongReadOverlap.cpp:593-662)
+//   dp_msa_kernel       thread per job: MultipleAlignment::_addSequence + calculateBaseConsensus
+//                       (Thirdparty/multiple_alignment.cpp:240-393, 517-594) on per-column symbol counts instead of padded
+//                       rows (see "column model" below)
+// Jobs are processed in chunks that fit a fixed scratch budget.
+#include <cub/cub.cuh>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "pbsc_batch.cuh"
+#include "pbsc_task.cuh"
+#include "pbsc_dp.cuh"
+
+namespace pbsc {
+
+constexpr int DP_HALF = 100;              // bandwidth 200 (LongReadOverlap.cpp:629)
+constexpr int DP_BW = 2 * DP_HALF + 1;    // cells per band column
+constexpr int DP_CPL = 7;                 // cells per lane: 32 x 7 = 224 >= 201
+constexpr int DP_NEG = -(1 << 28);
+constexpr int DP_WARPS = 8;               // warps per block of the alignment kernel
+constexpr int DP_TILE = 32;               // traceback tile: columns of flag words staged in shared memory
+constexpr int OP_M = 0, OP_I = 1, OP_D = 2;
+
+struct __align__(16) DpJob
+{
+    uint64_t lo[4];    // first suffix-array row of: source k-mer fwd (RBWT), rvc (BWT), target k-mer fwd (RBWT), rvc (BWT)
+    uint32_t cnt[4];   // rows taken from each: min(interval size, coverage)
+    uint32_t task;     // index into the task array
+    uint32_t qlen, k, maxLen;
+    uint64_t row0;     // first row, numbered over the whole DP stage
+    uint64_t mem;      // byte offset of the job's scratch, over the whole DP stage
+};
+
+struct __align__(16) DpRow
+{
+    uint32_t job, local;       // job index, row index inside the job
+    uint32_t len, seq_start;   // the retrieved read is buf[seq_start, seq_start + len)
+    uint32_t nops;             // alignment columns (ops are stored last column first)
+    int32_t start0, start1;    // match[0].start, match[1].start
+    uint32_t pass;             // 0 dropped, 1 enters the multiple alignment, 2 retrieved and waiting for alignment
+};
+
+struct __align__(8) GapCol { uint16_t cnt[5]; uint16_t pad; uint32_t next; };   // one inserted column: A,C,G,T,'-' counts
+
+__host__ __device__ inline uint32_t dp_max_len(uint32_t qlen)
+{
+    // size_t maxLength = query.length()*1.1+20 (LongReadOverlap.cpp:611); product and sum are exact IEEE operations
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(uint64_t)__dadd_rn(__dmul_rn((double)qlen, 1.1), 20.0);
+#else
+    volatile double m = (double)qlen * 1.1;
+    return (uint32_t)(uint64_t)(m + 20.0);
+#endif
+}
+__host__ __device__ inline uint64_t dp_seq_bytes(uint32_t maxLen) { return align_up((size_t)maxLen, 16); }
+__host__ __device__ inline uint64_t dp_row_bytes(uint32_t qlen, uint32_t maxLen) { return dp_seq_bytes(maxLen) + align_up((size_t)qlen + maxLen, 16); }
+__host__ __device__ inline uint32_t dp_gap_cap(uint32_t qlen) { return 3 * qlen + 128; }
+__host__ __device__ inline uint64_t dp_msa_bytes(uint32_t qlen)
+{
+    const uint64_t np = (uint64_t)qlen + 1;
+    return align_up(np * 5 * 2, 16) + align_up(np * 2, 16) + 2 * align_up(np * 4, 16) + (uint64_t)dp_gap_cap(qlen) * sizeof(GapCol);
+}
+__host__ __device__ inline uint64_t dp_job_bytes(uint32_t qlen, uint32_t maxLen, uint32_t rows)
+{
+    return align_up(align_up((size_t)qlen, 16) + (uint64_t)rows * dp_row_bytes(qlen, maxLen) + dp_msa_bytes(qlen), 128);
+}
+
+// BWT symbol at idx and the LF step from it: returns the symbol (0..3) or -1 for '$'; idx becomes C[b] + occ(b, idx - 1)
+// (RLBWT::getChar + getPC + getOcc, LongReadOverlap.cpp:713-718) from one 32-byte sector
+__device__ __forceinline__ int lf_step(const FmTable& t, uint64_t& idx)
+{
+    const uint64_t blk = idx >> 6;
+    const uint32_t off = (uint32_t)idx & 63u;
+    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
+    const uint4 cn = __ldg(bp);
+    const uint4 bs = __ldg(bp + 1);
+    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
+    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
+    const int c = (int)(((off < 32 ? w0 : w1) >> (2 * (off & 31))) & 3);
+    const bool has_dollar = (cn.x >> 31) != 0;
+    uint64_t dmask = 0;
+    if (has_dollar)
+    {
+        dmask = __ldg(t.dollar_mask + blk);
+        if ((dmask >> off) & 1) return -1;
+    }
+    uint32_t base = c == 0 ? (cn.x & 0x7fffffffu) : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
+    const uint64_t pat = 0x5555555555555555ull * (uint64_t)c;
+    const uint64_t x0 = w0 ^ pat, x1 = w1 ^ pat;
+    uint64_t m0 = ~(x0 | (x0 >> 1)) & 0x5555555555555555ull;
+    uint64_t m1 = ~(x1 | (x1 >> 1)) & 0x5555555555555555ull;
+    if (off < 32) { m0 &= (1ull << (2 * off)) - 1ull; m1 = 0; }
+    else { m1 &= (1ull << (2 * (off - 32))) - 1ull; }
+    uint64_t r = (uint64_t)base + __popcll(m0) + __popcll(m1);
+    if (c == 0 && has_dollar && off) r -= __popcll(dmask & ((1ull << off) - 1ull));
+    idx = t.C[c] + r;
+    return c;
+}
+
+// ---- stage 0: which failed walks get the fallback, and how many rows each one retrieves --------------------------------
+__global__ void __launch_bounds__(128)
+dp_collect_kernel(const __grid_constant__ FmIndexDev idx, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks,
+                  const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets, uint32_t coverage, DpJob* jobs,
+                  uint64_t* job_rows, uint64_t* job_bytes, unsigned int* n_jobs)
+{
+    const uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const uint64_t ti = list ? list[it] : it;
+    WalkTask& tk = tasks[ti];
+    if (!tk.valid) return;
+    tk.dp_status = PBSC_DP_NONE;
+    if (!tk.dp_wanted || !(tk.status == -1 || tk.status == -2 || tk.status == -3)) return;
+    const uint8_t* read = codes + offsets[tk.read];
+    const uint32_t k = (uint32_t)tk.k;
+    const uint32_t qlen = k + (uint32_t)(tk.trg_start - tk.src_end - 1) + (uint32_t)tk.trg_len;
+    DpJob J;
+    Interval f, r;
+    tw::both_strands(idx, [&](int j) { return (int)task_query_base(tk, read, (uint32_t)j); }, (int)k, f, r);
+    J.lo[0] = f.lo; J.cnt[0] = (uint32_t)min(f.size(), (uint64_t)coverage);
+    J.lo[1] = r.lo; J.cnt[1] = (uint32_t)min(r.size(), (uint64_t)coverage);
+    // initKmer = reverseComplement(last k bases of the query) (LongReadOverlap.cpp:680)
+    tw::both_strands(idx, [&](int j) { return 3 - (int)task_query_base(tk, read, qlen - 1 - (uint32_t)j); }, (int)k, f, r);
+    J.lo[2] = f.lo; J.cnt[2] = (uint32_t)min(f.size(), (uint64_t)coverage);
+    J.lo[3] = r.lo; J.cnt[3] = (uint32_t)min(r.size(), (uint64_t)coverage);
+    const uint32_t rows = J.cnt[0] + J.cnt[1] + J.cnt[2] + J.cnt[3];
+    // maquery.getNumRows() <= 3 (PacBioSelfCorrectionProcess.cpp:238): fewer than three rows can never pass
+    if (rows < 3) { tk.dp_status = PBSC_DP_FEW_ROWS; return; }
+    J.task = (uint32_t)ti; J.qlen = qlen; J.k = k; J.maxLen = dp_max_len(qlen);
+    J.row0 = 0; J.mem = 0;
+    const unsigned int j = atomicAdd(n_jobs, 1u);
+    jobs[j] = J;
+    job_rows[j] = rows;
+    job_bytes[j] = dp_job_bytes(qlen, J.maxLen, rows);
+}
+
+__global__ void dp_offsets_kernel(uint64_t n_jobs, DpJob* jobs, const uint64_t* __restrict__ row_off, const uint64_t* __restrict__ mem_off)
+{
+    const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j < n_jobs) { jobs[j].row0 = row_off[j]; jobs[j].mem = mem_off[j]; }
+}
+
+struct JobView
+{
+    uint8_t* q; uint8_t* rows;
+    uint16_t* baseCnt; uint16_t* startAt; uint32_t* head; uint32_t* tail; GapCol* pool;
+    uint64_t rowBytes, seqBytes;
+};
+__device__ __forceinline__ void job_view(uint8_t* mem, const DpJob& J, uint32_t rows, JobView& v)
+{
+    uint8_t* p = mem;
+    v.q = p; p += align_up((size_t)J.qlen, 16);
+    v.rows = p;
+    v.seqBytes = dp_seq_bytes(J.maxLen);
+    v.rowBytes = dp_row_bytes(J.qlen, J.maxLen);
+    p += (uint64_t)rows * v.rowBytes;
+    const uint64_t np = (uint64_t)J.qlen + 1;
+    v.baseCnt = (uint16_t*)p; p += align_up(np * 5 * 2, 16);
+    v.startAt = (uint16_t*)p; p += align_up(np * 2, 16);
+    v.head = (uint32_t*)p; p += align_up(np * 4, 16);
+    v.tail = (uint32_t*)p; p += align_up(np * 4, 16);
+    v.pool = (GapCol*)p;
+}
+__device__ __forceinline__ uint32_t job_rows_of(const DpJob& J) { return J.cnt[0] + J.cnt[1] + J.cnt[2] + J.cnt[3]; }
+
+// ---- stage 1a: thread per job of the chunk: the query, and one descriptor per row -------------------------------------
+__global__ void __launch_bounds__(128)
+dp_rows_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, const uint8_t* __restrict__ codes,
+               const uint64_t* __restrict__ offsets, uint8_t* mem, uint64_t mem0, DpRow* rows, uint64_t row_base)
+{
+    const uint64_t j = j0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= j1) return;
+    const DpJob J = jobs[j];
+    const WalkTask tk = tasks[J.task];
+    const uint8_t* read = codes + offsets[tk.read];
+    const uint32_t nr = job_rows_of(J);
+    JobView v;
+    job_view(mem + (J.mem - mem0), J, nr, v);
+    for (uint32_t x = 0; x < J.qlen; x++) v.q[x] = task_query_base(tk, read, x);
+    for (uint32_t r = 0; r < nr; r++)
+    {
+        DpRow R;
+        R.job = (uint32_t)j; R.local = r; R.len = 0; R.seq_start = 0; R.nops = 0; R.start0 = R.start1 = 0; R.pass = 0;
+        rows[J.row0 - row_base + r] = R;
+    }
+}
+
+// ---- stage 1b: thread per row: LongReadOverlap::retrieveStr ------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+dp_retrieve_kernel(const __grid_constant__ FmIndexDev idx, uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, uint8_t* mem, uint64_t mem0)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    DpRow R = rows[i];
+    const DpJob J = jobs[R.job];
+    JobView v;
+    job_view(mem + (J.mem - mem0), J, job_rows_of(J), v);
+    uint8_t* buf = v.rows + (uint64_t)R.local * v.rowBytes;
+    // which of the four suffix-array ranges this row comes from, in the order the reference pushes them
+    uint32_t l = R.local;
+    int kind = 0;
+    while (l >= J.cnt[kind]) { l -= J.cnt[kind]; kind++; }
+    uint64_t sa = J.lo[kind] + l;
+    const FmTable& t = idx.t[(kind == 0 || kind == 2) ? PBSC_RBWT : PBSC_BWT];
+    const bool compl_ = (kind == 1 || kind == 2);   // the string is the reverse complement of what LF-mapping spells
+    const uint32_t k = J.k, qlen = J.qlen, maxLen = J.maxLen;
+    const uint8_t* q = v.q;
+    uint32_t len, start;
+    if (kind < 2)
+    {
+        // seeded by the query's first k-mer: query[0,k) followed by the read's continuation
+        for (uint32_t x = 0; x < k; x++) buf[x] = q[x];
+        uint32_t pos = k;
+        #pragma unroll 1
+        for (uint32_t n = k; n < maxLen; n++)
+        {
+            const int c = lf_step(t, sa);
+            if (c < 0) break;
+            buf[pos++] = (uint8_t)(compl_ ? 3 - c : c);
+        }
+        len = pos; start = 0;
+    }
+    else
+    {
+        // seeded by the query's last k-mer: the read's preceding bases followed by query[qlen-k, qlen)
+        for (uint32_t x = 0; x < k; x++) buf[maxLen - k + x] = q[qlen - k + x];
+        uint32_t pos = maxLen - k;
+        #pragma unroll 1
+        for (uint32_t n = k; n < maxLen; n++)
+        {
+            const int c = lf_step(t, sa);
+            if (c < 0) break;
+            buf[--pos] = (uint8_t)(compl_ ? 3 - c : c);
+        }
+        start = pos; len = maxLen - pos;
+    }
+    // a read that spells the query itself is ignored (LongReadOverlap.cpp:622-624)
+    bool same = len >= qlen;
+    if (same)
+    {
+        const uint8_t* s = buf + start + (kind < 2 ? 0 : len - qlen);
+        for (uint32_t x = 0; x < qlen && same; x++) same = s[x] == q[x];
+    }
+    R.len = len; R.seq_start = start; R.pass = same ? 0 : 2;
+    rows[i] = R;
+}
+
+// ---- stage 2: warp per row: banded alignment, traceback, filters -------------------------------------------------------
+__global__ void __launch_bounds__(DP_WARPS * 32)
+dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0,
+                uint32_t* flag_slabs, uint64_t slab_words, unsigned long long* counter, unsigned int* n_bad)
+{
+    __shared__ uint32_t tile_s[DP_WARPS][DP_TILE * 32];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    uint32_t* tile = tile_s[wib];
+    uint32_t* flags = flag_slabs + ((size_t)blockIdx.x * DP_WARPS + wib) * slab_words;
+    for (;;)
+    {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1ull);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= n_rows) break;
+        DpRow R = rows[it];
+        if (R.pass != 2) continue;
+        const DpJob J = jobs[R.job];
+        JobView v;
+        job_view(mem + (J.mem - mem0), J, job_rows_of(J), v);
+        uint8_t* buf = v.rows + (uint64_t)R.local * v.rowBytes;
+        const uint8_t* __restrict__ s2 = buf + R.seq_start;
+        uint8_t* ops = buf + v.seqBytes;
+        const uint8_t* __restrict__ q = v.q;
+        const int qlen = (int)J.qlen, mlen = (int)R.len, k = (int)J.k;
+        const bool isRC = R.local >= J.cnt[0] + J.cnt[1];
+        const int start_1 = isRC ? qlen - k : 0, start_2 = isRC ? mlen - k : 0;
+        const int origin = (start_2 - start_1 + 1) - (DP_HALF + 1);
+        const int nRows = mlen + 1;
+
+        int prev[DP_CPL];
+        int sw[DP_CPL];   // s2[j-1] of this lane's rows in the current column; -1 outside the string
+        #pragma unroll
+        for (int t = 0; t < DP_CPL; t++)
+        {
+            prev[t] = 0;
+            const int j = origin + 1 + lane * DP_CPL + t;
+            sw[t] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
+        }
+        int bestRowVal = 0, bestRowI = 0, bestColVal = 0, bestColJ = 0;
+        bool anyRow = false, anyCol = false;
+        #pragma unroll 1
+        for (int i = 1; i <= qlen; i++)
+        {
+            const int jb = origin + i;
+            const int first = max(jb, 1);
+            const int last = min(jb + DP_BW, nRows) - 1;
+            const bool skipCol = (last + 1 <= 0) || first >= nRows || first > last;
+            const int c1 = (int)q[i - 1];
+            const int pn0 = __shfl_down_sync(FULL, prev[0], 1);
+            int a[DP_CPL], cur[DP_CPL];
+            int run = DP_NEG;
+            #pragma unroll
+            for (int t = 0; t < DP_CPL; t++)
+            {
+                const int r = lane * DP_CPL + t, j = jb + r;
+                const bool comp = !skipCol && r < DP_BW && j >= first && j <= last;
+                const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
+                const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
+                // first row of the band: left if it is in the band; last row (when not also the first): no left
+                const bool useLeft = (r + 1 < DP_BW) && !(j == last && j != first);
+                const int v0 = useLeft ? max(diag, pl - 1) : diag;
+                run = max(run, comp ? v0 + r : DP_NEG);
+                a[t] = run;
+            }
+            int incl = run;
+            #pragma unroll
+            for (int off = 1; off < 32; off <<= 1)
+            {
+                const int o = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl = max(incl, o);
+            }
+            int excl = __shfl_up_sync(FULL, incl, 1);
+            if (lane == 0) excl = DP_NEG;
+            #pragma unroll
+            for (int t = 0; t < DP_CPL; t++)
+            {
+                const int r = lane * DP_CPL + t, j = jb + r;
+                const bool comp = !skipCol && r < DP_BW && j >= first && j <= last;
+                cur[t] = comp ? max(a[t], excl) - r : 0;
+            }
+            // traceback bits: does the cell equal each in-band neighbour plus its step (overlapper.cpp:607-610)
+            const int upPrev = __shfl_up_sync(FULL, cur[DP_CPL - 1], 1);
+            uint32_t w = 0;
+            #pragma unroll
+            for (int t = 0; t < DP_CPL; t++)
+            {
+                const int r = lane * DP_CPL + t, j = jb + r;
+                const bool comp = !skipCol && r < DP_BW && j >= first && j <= last;
+                const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
+                const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
+                const int upv = t > 0 ? cur[t - 1] : upPrev;
+                uint32_t f = 0;
+                if (comp)
+                {
+                    f |= (cur[t] == diag) ? 1u : 0u;
+                    f |= (r >= 1 && cur[t] == upv - 1) ? 2u : 0u;
+                    f |= (r + 1 < DP_BW && cur[t] == pl - 1) ? 4u : 0u;
+                }
+                w |= f << (3 * t);
+            }
+            flags[(size_t)i * 32 + lane] = w;
+            // best cell of the last row: first column with the strictly largest score (overlapper.cpp:553-561)
+            if (!skipCol && last == nRows - 1)
+            {
+                const int rs = nRows - 1 - jb;
+                int sel = 0;
+                #pragma unroll
+                for (int t = 0; t < DP_CPL; t++) if (t == rs % DP_CPL) sel = cur[t];
+                const int vv = __shfl_sync(FULL, sel, rs / DP_CPL);
+                if (!anyRow || vv > bestRowVal) { bestRowVal = vv; bestRowI = i; anyRow = true; }
+            }
+            // best cell of the last column: first row with the strictly largest score (:564-570)
+            if (i == qlen && !skipCol)
+            {
+                int lv = DP_NEG, lr = 0x7fffffff;
+                #pragma unroll
+                for (int t = 0; t < DP_CPL; t++)
+                {
+                    const int r = lane * DP_CPL + t, j = jb + r;
+                    const bool comp = r < DP_BW && j >= first && j <= last;
+                    if (comp && cur[t] > lv) { lv = cur[t]; lr = r; }
+                }
+                #pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+                {
+                    const int ov = __shfl_xor_sync(FULL, lv, off), orr = __shfl_xor_sync(FULL, lr, off);
+                    if (ov > lv || (ov == lv && orr < lr)) { lv = ov; lr = orr; }
+                }
+                if (lr != 0x7fffffff) { anyCol = true; bestColVal = lv; bestColJ = jb + lr; }
+            }
+            // next column: the band slides down by one row
+            const int nx = __shfl_down_sync(FULL, sw[0], 1);
+            #pragma unroll
+            for (int t = 0; t < DP_CPL; t++) { prev[t] = cur[t]; if (t < DP_CPL - 1) sw[t] = sw[t + 1]; }
+            if (lane == 31)
+            {
+                const int j = jb + 1 + lane * DP_CPL + (DP_CPL - 1);
+                sw[DP_CPL - 1] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
+            }
+            else sw[DP_CPL - 1] = nx;
+        }
+        __syncwarp();
+        // start of the traceback (:577-586)
+        int i, j;
+        if (anyCol && (!anyRow || bestColVal > bestRowVal)) { i = qlen; j = bestColJ; }
+        else { i = anyRow ? bestRowI : 0; j = nRows - 1; }
+        if (!(anyRow || anyCol) || i <= 0 || j <= 0)
+        {
+            // the reference would abort on its empty-cigar assert; report instead of inventing an alignment
+            if (lane == 0) { atomicAdd(n_bad, 1u); R.pass = 0; rows[it] = R; }
+            continue;
+        }
+        int n = 0, ed = 0;
+        int tlo = -(1 << 30);
+        #pragma unroll 1
+        while (i > 0 && j > 0)
+        {
+            if (i < tlo || i >= tlo + DP_TILE)
+            {
+                tlo = max(i - (DP_TILE - 1), 0);
+                __syncwarp();
+                #pragma unroll 4
+                for (int c = 0; c < DP_TILE; c++)
+                {
+                    const int col = tlo + c;
+                    tile[c * 32 + lane] = (col >= 1 && col <= qlen) ? flags[(size_t)col * 32 + lane] : 0u;
+                }
+                __syncwarp();
+            }
+            const int r = j - (origin + i);
+            const uint32_t f = (tile[(i - tlo) * 32 + r / DP_CPL] >> (3 * (r % DP_CPL))) & 7u;
+            const int s2p = (int)s2[j - 1], s2n = j < mlen ? (int)s2[j] : -1;
+            const int s1p = (int)q[i - 1], s1n = i < qlen ? (int)q[i] : -2;
+            const bool eqD = f & 1u, eqU = (f & 2u) != 0, eqL = (f & 4u) != 0;
+            int op;
+            if (s2p == s2n) op = eqU ? OP_I : (eqL ? OP_D : OP_M);        // s2 homopolymer: prefer consuming s2 (:620-640)
+            else if (s1p == s1n) op = eqL ? OP_D : (eqU ? OP_I : OP_M);   // s1 homopolymer: prefer consuming s1 (:642-661)
+            else op = eqD ? OP_M : (eqL ? OP_D : OP_I);                   // (:663-680)
+            if (op == OP_M) { if (s1p != s2p) ed++; i--; j--; }
+            else if (op == OP_I) { ed++; j--; }
+            else { ed++; i--; }
+            if (lane == 0) ops[n] = (uint8_t)op;
+            n++;
+        }
+        if (lane == 0)
+        {
+            const WalkTask& tk = tasks[J.task];
+            // identity = 0.65 (+0.05 above 50, +0.05 above 100), min_overlap = path.length()/10 (PacBioSelfCorrectionProcess.cpp:225-235)
+            const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
+            double identity = 0.65;
+            identity = __dadd_rn(identity, fsum > 50 ? 0.05 : 0.0);
+            identity = __dadd_rn(identity, fsum > 100 ? 0.05 : 0.0);
+            const double pct = __ddiv_rn(__dmul_rn((double)(n - ed), 100.0), (double)n);   // getPercentIdentity (overlapper.cpp:71-74)
+            const bool passOverlap = (uint64_t)n >= (uint64_t)(qlen / 10);
+            const bool passIdentity = __ddiv_rn(pct, 100.0) >= identity;
+            R.nops = (uint32_t)n; R.start0 = i; R.start1 = j;
+            R.pass = (passOverlap && passIdentity) ? 1u : 0u;
+            rows[it] = R;
+        }
+    }
+}
+
+// ---- stage 3: thread per job: multiple alignment on per-column counts, consensus ---------------------------------------
+// Column model.  MultipleAlignment::_addSequence places every incoming row against row 0 (the query); a new gap column is
+// only ever inserted immediately before a BASE column of row 0, i.e. appended to the run of gap columns in front of that
+// base, so the alignment is: for each query position p a list run(p) of inserted columns, then the base column p.  The
+// consensus only needs, per column, how many rows show A/C/G/T/'-' there.  A new column inserted before base column p gets a
+// '-' from every row that already spans it: rows covering base column p minus rows whose first column IS base column p
+// (MultipleAlignmentElement::insertGapBeforeColumn, multiple_alignment.cpp:112-134).
+__global__ void __launch_bounds__(64)
+dp_msa_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, WalkTask* tasks, const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem,
+              uint64_t mem0, uint8_t* outpool, unsigned int* n_bad)
+{
+    const uint64_t jx = j0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (jx >= j1) return;
+    const DpJob J = jobs[jx];
+    WalkTask& tk = tasks[J.task];
+    const uint32_t nr = job_rows_of(J);
+    const DpRow* R = rows + (J.row0 - row_base);
+    uint32_t passing = 0;
+    for (uint32_t r = 0; r < nr; r++) passing += R[r].pass == 1;
+    if (passing < 3) { tk.dp_status = PBSC_DP_FEW_ROWS; return; }
+    JobView v;
+    job_view(mem + (J.mem - mem0), J, nr, v);
+    const uint32_t qlen = J.qlen;
+    const uint8_t* q = v.q;
+    for (uint32_t p = 0; p <= qlen; p++)
+    {
+        #pragma unroll
+        for (int c = 0; c < 5; c++) v.baseCnt[p * 5 + c] = 0;
+        v.startAt[p] = 0; v.head[p] = 0; v.tail[p] = 0;
+        if (p < qlen) v.baseCnt[p * 5 + q[p]] = 1;
+    }
+    v.startAt[0] = 1;   // row 0 starts at base column 0
+    const uint32_t gapCap = dp_gap_cap(qlen);
+    uint32_t nGap = 0;
+    bool bad = false;
+    for (uint32_t r = 0; r < nr && !bad; r++)
+    {
+        if (R[r].pass != 1) continue;
+        const uint8_t* buf = v.rows + (uint64_t)R[r].local * v.rowBytes;
+        const uint8_t* s2 = buf + R[r].seq_start;
+        const uint8_t* ops = buf + v.seqBytes;
+        uint32_t p = (uint32_t)R[r].start0, inc = (uint32_t)R[r].start1;
+        uint32_t cur = 0;   // 0: at base column p; otherwise gap column cur-1 of run(p)
+        bool firstOp = true;
+        int c = (int)R[r].nops - 1;
+        while (c >= 0)
+        {
+            const int op = ops[c];
+            if (cur)
+            {
+                GapCol& g = v.pool[cur - 1];
+                if (op == OP_I) { g.cnt[s2[inc]]++; inc++; c--; firstOp = false; }
+                else g.cnt[4]++;
+                cur = g.next;
+            }
+            else if (op == OP_I)
+            {
+                if (nGap >= gapCap) { bad = true; break; }
+                uint32_t cover = 0;
+                #pragma unroll
+                for (int s = 0; s < 5; s++) cover += v.baseCnt[p * 5 + s];
+                GapCol g;
+                g.cnt[0] = g.cnt[1] = g.cnt[2] = g.cnt[3] = 0; g.pad = 0; g.next = 0;
+                g.cnt[4] = (uint16_t)(cover - v.startAt[p]);
+                g.cnt[s2[inc]] = 1;
+                v.pool[nGap] = g;
+                nGap++;
+                if (v.tail[p]) v.pool[v.tail[p] - 1].next = nGap; else v.head[p] = nGap;
+                v.tail[p] = nGap;
+                inc++; c--; firstOp = false;
+            }
+            else
+            {
+                if (p >= qlen) { bad = true; break; }
+                v.baseCnt[p * 5 + (op == OP_M ? s2[inc] : 4)]++;
+                if (op == OP_M) inc++;
+                if (firstOp) v.startAt[p]++;
+                firstOp = false;
+                p++; c--;
+                cur = v.head[p];
+            }
+        }
+    }
+    if (bad) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_WALK_OVERFLOW; return; }
+    // calculateBaseConsensus(min_call_coverage, -1) (multiple_alignment.cpp:517-594)
+    const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
+    const int minCall = (int)(fsum > 50 ? (uint64_t)__dmul_rn((double)fsum, 0.4) : 15);
+    uint8_t* out = outpool + tk.out_off;
+    uint32_t n = 0;
+    const uint32_t cap = tk.out_cap;
+    auto call = [&](const uint16_t* cnt, int baseSym) -> int
+    {
+        int maxSym = -1, maxCount = -1;
+        #pragma unroll
+        for (int s = 0; s < 5; s++) if ((int)cnt[s] > maxCount) { maxSym = s; maxCount = cnt[s]; }   // order A,C,G,T,(N),'-'
+        const int baseCount = cnt[baseSym];
+        return (maxCount >= baseCount && baseCount < minCall) ? maxSym : baseSym;
+    };
+    bool over = false;
+    for (uint32_t p = 0; p < qlen && !over; p++)
+    {
+        if (p >= 1)
+            for (uint32_t g = v.head[p]; g; g = v.pool[g - 1].next)
+            {
+                const int s = call(v.pool[g - 1].cnt, 4);
+                if (s != 4) { if (n >= cap) { over = true; break; } out[n++] = (uint8_t)s; }
+            }
+        if (over) break;
+        const int s = call(v.baseCnt + p * 5, (int)q[p]);
+        if (s != 4) { if (n >= cap) { over = true; break; } out[n++] = (uint8_t)s; }
+    }
+    // out.erase(0, extendKmerSize) needs at least k bases
+    if (over || n < J.k) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_WALK_OVERFLOW; return; }
+    tk.out_len = n;
+    tk.dp_status = PBSC_DP_OK;
+}
+
+template <class T>
+static cudaError_t arena(pbsc_index* idx, const char* name, size_t count, T** out) { return arena_get(idx, name, (count ? count : 1) * sizeof(T), (void**)out); }
+
+DpStats& last_dp_stats() { static thread_local DpStats s; return s; }
+
+int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void* tasks_v, uint64_t n_items, const uint32_t* list, uint8_t* outpool,
+                    uint32_t q_cap, uint64_t* launches)
+{
+    WalkTask* tasks = (WalkTask*)tasks_v;
+    cudaStream_t st = idx->stream;
+    if (n_items == 0) return PBSC_OK;
+    DpJob* jobs; uint64_t *job_rows, *job_bytes, *row_off, *mem_off; unsigned int* cnt; unsigned long long* qctr;
+    PBSC_CUDA(arena(idx, "dp.jobs", n_items, &jobs));
+    PBSC_CUDA(arena(idx, "dp.job_rows", n_items + 1, &job_rows));
+    PBSC_CUDA(arena(idx, "dp.job_bytes", n_items + 1, &job_bytes));
+    PBSC_CUDA(arena(idx, "dp.row_off", n_items + 1, &row_off));
+    PBSC_CUDA(arena(idx, "dp.mem_off", n_items + 1, &mem_off));
+    PBSC_CUDA(arena(idx, "dp.cnt", 4, &cnt));
+    PBSC_CUDA(arena(idx, "dp.qctr", 2, &qctr));
+    PBSC_CUDA(cudaMemsetAsync(cnt, 0, 16, st));
+    cudaEvent_t ev[2];
+    PBSC_CUDA(cudaEventCreate(&ev[0])); PBSC_CUDA(cudaEventCreate(&ev[1]));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } guard{ev};
+    PBSC_CUDA(cudaEventRecord(ev[0], st));
+    dp_collect_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, n_items, list, tasks, b.codes.p, b.offsets.p, (uint32_t)p->pb_coverage,
+                                                                        jobs, job_rows, job_bytes, cnt);
+    unsigned int hcnt[2] = {0, 0};
+    PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    if (launches) *launches += 1;
+    const uint64_t nj = hcnt[0];
+    DpStats& S = last_dp_stats();
+    if (nj == 0) return PBSC_OK;
+    // offsets of every job's rows and scratch
+    {
+        size_t tb = 0, tb2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, job_rows, row_off, (int)(nj + 1), st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, job_bytes, mem_off, (int)(nj + 1), st);
+        tb = std::max(tb, tb2);
+        uint8_t* tmp;
+        PBSC_CUDA(arena(idx, "dp.cubtmp", tb, &tmp));
+        PBSC_CUDA(cudaMemsetAsync(job_rows + nj, 0, 8, st));
+        PBSC_CUDA(cudaMemsetAsync(job_bytes + nj, 0, 8, st));
+        cub::DeviceScan::ExclusiveSum(tmp, tb, job_rows, row_off, (int)(nj + 1), st);
+        cub::DeviceScan::ExclusiveSum(tmp, tb, job_bytes, mem_off, (int)(nj + 1), st);
+        dp_offsets_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>(nj, jobs, row_off, mem_off);
+    }
+    std::vector<uint64_t> h_row(nj + 1), h_mem(nj + 1);
+    PBSC_CUDA(cudaMemcpyAsync(h_row.data(), row_off, (nj + 1) * 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaMemcpyAsync(h_mem.data(), mem_off, (nj + 1) * 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    if (launches) *launches += 3;
+    S.jobs += nj; S.rows += h_row[nj];
+    // scratch budget of one chunk
+    uint64_t budget = 6ull << 30;
+    if (const char* e = getenv("PBSC_DP_CHUNK_MB")) { if (atoll(e) > 0) budget = (uint64_t)atoll(e) << 20; }
+    uint64_t max_job = 0;
+    for (uint64_t j = 0; j < nj; j++) max_job = std::max(max_job, h_mem[j + 1] - h_mem[j]);
+    if (max_job > budget) budget = max_job;
+    const uint64_t pool_bytes = std::min(budget, h_mem[nj]);
+    uint8_t* mem;
+    PBSC_CUDA(arena(idx, "dp.mem", pool_bytes, &mem));
+    // alignment kernel geometry: one flag slab per resident warp, sized for the longest query of this stage
+    int per_sm = 0;
+    PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_align_kernel, DP_WARPS * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* e = getenv("PBSC_DP_BLOCKS_PER_SM")) { if (atoi(e) > 0) per_sm = std::min(per_sm, atoi(e)); }
+    const int ablocks = idx->sm_count * per_sm;
+    const uint64_t slab_words = ((uint64_t)q_cap + 2) * 32;
+    uint32_t* slabs;
+    PBSC_CUDA(arena(idx, "dp.flags", slab_words * (uint64_t)ablocks * DP_WARPS, &slabs));
+    uint64_t max_rows = 0;
+    for (uint64_t j0 = 0; j0 < nj;)
+    {
+        uint64_t j1 = j0 + 1;
+        while (j1 < nj && h_mem[j1 + 1] - h_mem[j0] <= pool_bytes) j1++;
+        max_rows = std::max(max_rows, h_row[j1] - h_row[j0]);
+        j0 = j1;
+    }
+    DpRow* rows;
+    PBSC_CUDA(arena(idx, "dp.rows", max_rows, &rows));
+    for (uint64_t j0 = 0; j0 < nj;)
+    {
+        uint64_t j1 = j0 + 1;
+        while (j1 < nj && h_mem[j1 + 1] - h_mem[j0] <= pool_bytes) j1++;
+        const uint64_t nrows = h_row[j1] - h_row[j0], njc = j1 - j0;
+        dp_rows_kernel<<<(unsigned)((njc + 127) / 128), 128, 0, st>>>(j0, j1, jobs, tasks, b.codes.p, b.offsets.p, mem, h_mem[j0], rows, h_row[j0]);
+        dp_retrieve_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(idx->dev, nrows, rows, jobs, mem, h_mem[j0]);
+        PBSC_CUDA(cudaMemsetAsync(qctr, 0, 8, st));
+        const int nb = (int)std::min<uint64_t>((uint64_t)ablocks, (nrows + DP_WARPS - 1) / DP_WARPS);
+        dp_align_kernel<<<nb, DP_WARPS * 32, 0, st>>>(nrows, rows, jobs, tasks, mem, h_mem[j0], slabs, slab_words, qctr, cnt + 1);
+        dp_msa_kernel<<<(unsigned)((njc + 63) / 64), 64, 0, st>>>(j0, j1, jobs, tasks, rows, h_row[j0], mem, h_mem[j0], outpool, cnt + 1);
+        PBSC_CUDA(cudaGetLastError());
+        if (launches) *launches += 4;
+        S.chunks++;
+        j0 = j1;
+    }
+    PBSC_CUDA(cudaEventRecord(ev[1], st));
+    PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    S.bad += hcnt[1];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    S.ms += ms;
+    return PBSC_OK;
+}
+
+}  // namespace pbsc

@@ -16,27 +16,13 @@
 #include <string.h>
 #include <algorithm>
 #include "pbsc_batch.cuh"
-#include "pbsc_walk_thread.cuh"
+#include "pbsc_task.cuh"
+#include "pbsc_dp.cuh"
 
 namespace pbsc {
 
 constexpr int TW_BLOCK = 128;
 constexpr int HEAVY_WARPS = 4;
-#define PBSC_TASK_PENDING (-999)
-
-struct __align__(16) WalkTask
-{
-    uint64_t src_hi, src_lo;   // last k bases of the source piece, newest base in the top two bits of src_hi
-    uint64_t out_off;          // where the merged sequence goes in the output pool
-    uint32_t read;
-    int32_t src_end;           // source.seedEndPos in the raw read
-    int32_t trg_start, trg_len;
-    int32_t k, rtou;
-    int32_t status;
-    uint32_t out_len, out_cap, valid;
-};
-static_assert(sizeof(WalkTask) == 64, "WalkTask must be 64 bytes");
-
 struct ReadState
 {
     int32_t t, next, started, done, rstatus, firstType;
@@ -45,7 +31,11 @@ struct ReadState
     int64_t srcLen;
     uint64_t plen;
     int32_t pending_trg;   // seed index the pending request targets
-    int32_t pad;
+    int32_t srcFreq;       // source.maxFixedMerFreq
+    // DP fallback result of the current target's first (next == 0) walk, kept while the look-ahead walks run
+    int32_t dpStatus0;
+    uint32_t dpLen0;
+    uint64_t dpOff0;
     pbsc_read_stats st;
 };
 
@@ -77,7 +67,7 @@ __global__ void make_spec_tasks_kernel(uint64_t n_reads, const uint8_t* __restri
                                        const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
                                        const uint32_t* __restrict__ seed_count, const uint64_t* __restrict__ task_base,
                                        WalkTask* __restrict__ tasks, uint64_t* __restrict__ caps, uint64_t* __restrict__ rec_caps,
-                                       int start_kmer, int min_overlap, int s9)
+                                       int start_kmer, int min_overlap, int s9, int no_dp)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -98,6 +88,8 @@ __global__ void make_spec_tasks_kernel(uint64_t n_reads, const uint8_t* __restri
             tk.trg_start = tg.start; tk.trg_len = tg.len;
             tk.k = k; tk.rtou = rtou ? 1 : 0;
             tk.status = PBSC_TASK_PENDING;
+            tk.freq_sum = s.max_fixed_freq + tg.max_fixed_freq;
+            tk.dp_wanted = no_dp ? 0 : 1;
             if (k > 0 && k <= s.len && k <= 64)
             {
                 pack_src(read + s.start + s.len - k, k, tk.src_hi, tk.src_lo);
@@ -332,7 +324,7 @@ walk_heavy_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant_
     }
 }
 
-struct StitchParams { int32_t start_kmer, next_target, split; };
+struct StitchParams { int32_t start_kmer, next_target, split, no_dp; };
 
 // thread per read: initCorrect (PacBioSelfCorrectionProcess.cpp:56-157) over finished walk tasks
 __global__ void __launch_bounds__(128)
@@ -373,6 +365,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 bounds[0] = 0;
             }
             S.srcLen = s0.len; S.srcEnd = s0.start + s0.len - 1; S.srcEndBest = s0.end_best_k; S.srcRepeat = s0.is_repeat;
+            S.srcFreq = s0.max_fixed_freq;
             S.nPieces = 1;
             S.t = 1; S.next = 0;
         }
@@ -415,6 +408,8 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                         memset(&tk, 0, sizeof tk);
                         tk.src_hi = hi; tk.src_lo = lo; tk.read = (uint32_t)r; tk.src_end = S.srcEnd; tk.trg_start = tg.start; tk.trg_len = tg.len;
                         tk.k = k; tk.rtou = rtou ? 1 : 0; tk.status = PBSC_TASK_PENDING; tk.valid = 1;
+                        tk.freq_sum = S.srcFreq + tg.max_fixed_freq;
+                        tk.dp_wanted = (S.next == 0 && !C.no_dp) ? 1 : 0;   // correctByMSAlignment only runs on the first target
                         tk.out_off = pending_pool_off + r * (uint64_t)pending_cap;
                         tk.out_cap = pending_cap;
                         *pd = tk;
@@ -425,7 +420,11 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 }
                 const int stw = use->status;
                 if (stw == PBSC_WALK_OVERFLOW || stw == PBSC_WALK_UNSUPPORTED) { S.rstatus = stw; break; }
-                if (S.next == 0) S.firstType = stw;
+                if (S.next == 0)
+                {
+                    S.firstType = stw;
+                    S.dpStatus0 = stw > 0 ? PBSC_DP_NONE : use->dp_status; S.dpLen0 = use->out_len; S.dpOff0 = use->out_off;
+                }
                 if (stw > 0)
                 {
                     const uint8_t* merged = outpool + use->out_off;
@@ -451,7 +450,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                     S.st.fm_num++;
                     S.st.total_walk_num++;
                     S.srcLen += outLen;
-                    S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat;
+                    S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat; S.srcFreq = tg.max_fixed_freq;
                     S.t += S.next;
                     success = true;
                     break;
@@ -466,30 +465,50 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 else if (S.firstType == -3) S.st.exceed_leave_num++;
                 else { S.rstatus = PBSC_WALK_NO_PATH; break; }
                 S.st.total_walk_num++;
-                if (C.split)
+                // correctByMSAlignment (PacBioSelfCorrectionProcess.cpp:134-136, 208-245)
+                if (S.dpStatus0 == PBSC_WALK_OVERFLOW || S.dpStatus0 == PBSC_WALK_UNSUPPORTED) { S.rstatus = S.dpStatus0; break; }
+                if (S.dpStatus0 == PBSC_DP_OK)
                 {
-                    if (S.plen + tg.len > pieceCap || S.nPieces + 1 >= boundsCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
-                    bounds[S.nPieces] = (uint32_t)S.plen;
-                    S.nPieces++;
-                    for (int x = 0; x < tg.len; x++) piece[S.plen + x] = read[tg.start + x];
-                    S.plen += tg.len;
-                    S.srcLen = tg.len;
+                    int k; bool rtou;
+                    pair_inputs(S.srcEndBest, S.srcRepeat, S.srcLen, tg, C.start_kmer, k, rtou);
+                    const uint8_t* cons = outpool + S.dpOff0;
+                    const uint64_t outLen = S.dpLen0 - (uint32_t)k;
+                    if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                    for (uint64_t x = 0; x < outLen; x++) piece[S.plen + x] = cons[k + x];
+                    S.plen += outLen;
+                    S.srcLen += outLen;
+                    S.st.corrected_len += outLen;
+                    S.st.seed_dis += tg.start - S.srcEnd - 1;
+                    S.st.dp_num++;
                 }
                 else
                 {
-                    const int tgEnd = tg.start + tg.len - 1;
-                    const uint64_t n = (uint64_t)(tgEnd - S.srcEnd);
-                    if (S.plen + n > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
-                    for (uint64_t x = 0; x < n; x++) piece[S.plen + x] = read[S.srcEnd + 1 + x];
-                    S.plen += n;
-                    S.srcLen += n;
+                    if (C.split)
+                    {
+                        if (S.plen + tg.len > pieceCap || S.nPieces + 1 >= boundsCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        bounds[S.nPieces] = (uint32_t)S.plen;
+                        S.nPieces++;
+                        for (int x = 0; x < tg.len; x++) piece[S.plen + x] = read[tg.start + x];
+                        S.plen += tg.len;
+                        S.srcLen = tg.len;
+                    }
+                    else
+                    {
+                        const int tgEnd = tg.start + tg.len - 1;
+                        const uint64_t n = (uint64_t)(tgEnd - S.srcEnd);
+                        if (S.plen + n > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        for (uint64_t x = 0; x < n; x++) piece[S.plen + x] = read[S.srcEnd + 1 + x];
+                        S.plen += n;
+                        S.srcLen += n;
+                    }
+                    S.st.corrected_len += tg.len;
                 }
-                S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat;
-                S.st.corrected_len += tg.len;
+                S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat; S.srcFreq = tg.max_fixed_freq;
             }
             S.t++;
             S.next = 0;
             S.firstType = 0;
+            S.dpStatus0 = PBSC_DP_NONE;
         }
     }
     if (stalled)
@@ -529,6 +548,8 @@ struct ThreadEngine
     size_t stride = 0, hstride = 0;
     int blocks = 0, hblocks = 0;
     bool heavy_engine_warp = false;
+    bool no_dp = true;
+    const pbsc_params* params = nullptr;
     ArenaPtr<unsigned long long> pool_used;
     uint64_t pool_cap = 0;
     ArenaPtr<unsigned int> n_heavy;
@@ -578,6 +599,11 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
                                                                          E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
     PBSC_CUDA(cudaGetLastError());
     if (launches) *launches += 4;
+    if (!E.no_dp)
+    {
+        const int rc = run_dp_fallback(idx, E.params, b, tasks, n_items, list, E.outpool.p, w.q_cap, launches);
+        if (rc != PBSC_OK) return rc;
+    }
     return PBSC_OK;
 }
 
@@ -609,6 +635,8 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     const uint64_t n = b.n_reads;
     if (n == 0) return PBSC_OK;
     ThreadEngine E;
+    E.no_dp = p->no_dp != 0;
+    E.params = p;
     if (idx->dev.idmer_len != p->idmer_len)
     {
         const uint64_t n_keys = 1ull << (2 * p->idmer_len);
@@ -687,7 +715,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     if (n_tasks)
     {
         make_spec_tasks_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, b.codes.p, b.offsets.p, s.seeds.p, s.region.p, s.count.p, E.task_base.p,
-                                                                            E.spec.p, E.caps.p, E.rec_caps.p, p->start_kmer, p->min_kmer, p->idmer_len);
+                                                                            E.spec.p, E.caps.p, E.rec_caps.p, p->start_kmer, p->min_kmer, p->idmer_len, p->no_dp);
         rc = scan_u64(E.cubtmp, E.caps.p, E.cap_off.p, n_tasks, st);
         if (rc != PBSC_OK) return rc;
         rc = scan_u64(E.cubtmp, E.rec_caps.p, E.rec_off.p, n_tasks, st);
@@ -714,7 +742,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         if (rc != PBSC_OK) return rc;
     }
     StitchParams C;
-    C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split;
+    C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split; C.no_dp = p->no_dp;
     for (int round = 0;; round++)
     {
         PBSC_CUDA(cudaMemsetAsync(E.n_stalled.p, 0, 4, st));

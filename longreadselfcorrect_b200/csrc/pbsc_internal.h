@@ -81,6 +81,8 @@ struct Timing
 {
     float h2d_ms = 0, seed_ms = 0, extend_ms = 0, d2h_ms = 0, total_ms = 0;
     uint64_t kernel_launches = 0, seed_pairs = 0, rank_queries = 0;
+    float dp_ms = 0;                  // part of extend_ms spent in the DP / multiple-alignment fallback
+    uint64_t dp_jobs = 0, dp_rows = 0;
 };
 Timing& last_timing();
 

@@ -4,6 +4,7 @@
 // pbsc_correct_batch is the three stages back to back on host buffers.
 #include <string.h>
 #include "pbsc_batch.cuh"
+#include "pbsc_dp.cuh"
 
 using namespace pbsc;
 
@@ -30,7 +31,8 @@ int pbsc_batch_upload(pbsc_index* idx, const pbsc_params* p, const char* reads, 
 {
     if (!idx || !p || !reads || !offsets || !out) { set_error("pbsc_batch_upload: null argument"); return PBSC_ERR_ARG; }
     *out = nullptr;
-    if (!p->no_dp) { set_error("the DP/MSA fallback (PacBioSelfCorrectionProcess.cpp:208-245) is not in this build; pass --nodp (no_dp=1)"); return PBSC_ERR_ARG; }
+    if (!p->no_dp && !use_thread_engine())
+    { set_error("the DP/MSA fallback (PacBioSelfCorrectionProcess.cpp:208-245) runs on the thread engine only; unset PBSC_ENGINE=warp or pass --nodp"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
     pbsc_batch* bt = new pbsc_batch();
     bt->idx = idx;
@@ -61,6 +63,7 @@ int pbsc_batch_run(pbsc_batch* bt, float* ms)
     auto done = [&]() { for (auto& x : e) cudaEventDestroy(x); };
     int rc = PBSC_OK;
     bt->launches = 0; bt->walks = 0;
+    last_dp_stats() = DpStats();
     for (int attempt = 0;; attempt++)
     {
         cudaEventRecord(e[0], st);
@@ -105,6 +108,9 @@ int pbsc_batch_run(pbsc_batch* bt, float* ms)
         T.h2d_ms = bt->h2d_ms; T.seed_ms = bt->seed_ms; T.extend_ms = bt->extend_ms; T.d2h_ms = 0;
         T.total_ms = bt->h2d_ms + bt->seed_ms + bt->extend_ms;
         T.kernel_launches = bt->launches; T.seed_pairs = bt->walks;
+        const DpStats& D = last_dp_stats();
+        T.dp_ms = D.ms; T.dp_jobs = D.jobs; T.dp_rows = D.rows;
+        if (D.bad) { set_error("DP fallback: %llu alignments or consensus buffers outside this build's limits", (unsigned long long)D.bad); rc = PBSC_ERR_LIMIT; }
     }
     done();
     return rc;

@@ -265,3 +265,83 @@ def test_repeat_rich_dataset_vs_oracle(api, oracle_bin, tmp_path, opts, kw, engi
     assert c == open(tmp_path / "or" / "correct.fa").read()
     assert d == open(tmp_path / "or" / "discard.fa").read()
     idx.close()
+
+
+# ---- DP / multiple-alignment fallback (default options, correctByMSAlignment) ------------------------------------------
+
+def _summary_counters(stats):
+    m = stats[stats["merge"] == 1]
+    return {k: int(m[k].sum()) for k in ("total_reads_len", "corrected_len", "total_seed_num", "total_walk_num", "fm_num", "dp_num",
+                                         "high_error_num", "exceed_depth_num", "exceed_leave_num", "seed_dis")}
+
+
+@pytest.mark.parametrize("name,kw", [("tiny", dict(coverage=30, genome=5)), ("tiny100", dict(coverage=100, genome=10))])
+@pytest.mark.parametrize("k0", [0, 13])
+def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, golden, name, kw, k0):
+    """Default options: failed walks go through retrieveStr / extendMatch / MultipleAlignment on the GPU; fixtures written by
+    the reference binary (tests/golden/make_golden.py dp)."""
+    p = api.Params.make(no_dp=False, **kw)
+    tiny_index.build_prefix_table(k0)
+    out, poff, first, stats = tiny_index.correct_reads(p, [s for _, s in tiny_reads])
+    c, d = _write_records(api.Index.pieces_as_strings(out, poff, first), stats, tiny_reads)
+    assert c == open(os.path.join(golden, f"{name}.dp.correct.fa")).read()
+    assert d == open(os.path.join(golden, f"{name}.dp.discard.fa")).read()
+    summ = dict(l.split(":")[0:2] for l in open(os.path.join(golden, f"{name}.dp.summary.txt")) if ":" in l)
+    got = _summary_counters(stats)
+    assert got["dp_num"] == int(summ["DPNum"].split(",")[0]) and got["dp_num"] > 0
+    assert got["fm_num"] == int(summ["FMNum"].split(",")[0])
+    assert got["corrected_len"] == int(summ["CorrectedLen"].split(",")[0])
+    assert got["total_walk_num"] == int(summ["TotalWalkNum"])
+    assert got["seed_dis"] // got["total_walk_num"] == int(summ["DisBetweenSeeds"])
+    assert api.last_timing()["dp_jobs"] > 0
+    tiny_index.build_prefix_table(0)
+
+
+@pytest.mark.parametrize("cov,opts,kw", [
+    (45, ["-c", "45", "-g", "5"], dict(coverage=45, genome=5)),
+    (45, ["-c", "70", "-g", "10", "--split", "-n", "2"], dict(coverage=70, genome=10, split=True, next_target=2)),
+    (9, ["-c", "30", "-g", "5"], dict(coverage=30, genome=5)),
+    (9, ["-c", "30", "-g", "5", "--split"], dict(coverage=30, genome=5, split=True)),
+])
+def test_dp_fallback_repeat_rich_vs_oracle(api, oracle_bin, tmp_path, cov, opts, kw, monkeypatch):
+    """Repeat-rich data; the 9x set makes the fallback itself fail (three or fewer rows) so --split matters; a tiny chunk
+    budget forces the chunked path."""
+    from conftest import run_oracle
+    from longreadselfcorrect_b200 import bwt_build, synth
+    monkeypatch.setenv("PBSC_DP_CHUNK_MB", "8")
+    g = synth.make_genome(15000, 23, repeat_families=1, tandem_arrays=3)
+    codes, off = synth.simulate_reads(g, cov, 1200, 213, min_len=300)
+    reads = synth.read_strings(codes, off)
+    fa = str(tmp_path / "reads.fa")
+    synth.write_fasta(fa, codes, off)
+    prefix = str(tmp_path / "idx")
+    bwt_build.build_index_files(prefix, codes, off)
+    o = run_oracle(oracle_bin, prefix, fa, str(tmp_path / "or"), opts, threads=8)
+    idx = api.Index.load(prefix)
+    idx.build_prefix_table(13)
+    p = api.Params.make(no_dp=False, **kw)
+    out, poff, first, stats = idx.correct_reads(p, reads)
+    named = [(f"r{i}", s) for i, s in enumerate(reads)]
+    c, d = _write_records(api.Index.pieces_as_strings(out, poff, first), stats, named, split=kw.get("split", False))
+    assert c == open(tmp_path / "or" / "correct.fa").read()
+    assert d == open(tmp_path / "or" / "discard.fa").read()
+    summ = dict(l.split(":")[0:2] for l in o.stdout.splitlines() if ":" in l)
+    got = _summary_counters(stats)
+    assert got["dp_num"] == int(summ["DPNum"].split(",")[0])
+    assert got["total_walk_num"] - got["fm_num"] - got["dp_num"] == int(summ["OutcastNum"].split(",")[0])
+    idx.close()
+
+
+def test_cli_drop_in_default_options(golden, tmp_path):
+    """`pbcorrect` without --nodp: byte-identical correct.fa / discard.fa and the same stdout summary as the reference."""
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
+    out = tmp_path / "out"
+    r = subprocess.run([exe, "pbcorrect", "-t", "4", "-p", os.path.join(golden, "tiny"), "-o", str(out), "-c", "30", "-g", "5",
+                        "--batch-mbp", "0.2", os.path.join(golden, "tiny.reads.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    for f in ("correct.fa", "discard.fa"):
+        assert open(out / f, "rb").read() == open(os.path.join(golden, f"tiny.dp.{f}"), "rb").read(), f
+    want = [l for l in open(os.path.join(golden, "tiny.dp.summary.txt")).read().strip().splitlines() if l]
+    got = [l for l in r.stdout.strip().splitlines() if l and not l.startswith("Time of")]
+    assert got == want
