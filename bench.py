@@ -1,16 +1,17 @@
 #!/usr/bin/env python3
-"""Benchmark of the `stride pbcorrect` hot path (seed discovery + FM extension, --nodp) on B200.
+"""Benchmark of the `stride pbcorrect` hot path (seed discovery + FM extension + DP/MSA fallback) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny] [--nodp]
 
 One "step" = one pass of the hot path over the whole read set of the workload (BASELINE.json configs[1] by
-default: 4.6 Mb synthetic genome, 50x simulated CLR reads, mean 8 kb, `-c 50 -g 5 --nodp`).
+default: 4.6 Mb synthetic genome, 50x simulated CLR reads, mean 8 kb, `-c 50 -g 5`, the reference's default options;
+`--nodp` measures seeds + FM extension alone).
   value  corrected Mbp/s with the reads already resident in HBM (pbsc_batch_run: kernels only, CUDA events)
   e2e    the same through pbsc_correct_batch on host buffers (H2D of the reads + D2H of the corrected pieces inside)
 N > 1 (torchrun): one process per GPU, the index replicated, every rank corrects the full read set (weak scaling,
 no data-path collective); time = max over ranks, value = N x Mbp / time.
 `--impl reference` times the reference's own multithreaded CPU implementation (oracle/_ref/stride pbcorrect -t <cores>)
-on a bounded sample of the same reads against the same index files.
+on a bounded sample of the same reads against the same index files, with the same options.
 """
 from __future__ import annotations
 
@@ -32,11 +33,11 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: genome length, genome seed, coverage, mean read length, read seed, pbcorrect options
     "cfg2": dict(genome=4_600_000, gseed=2, cov=50, mean=8000, rseed=102, c=50, g=5,
-                 desc="4.6 Mb synthetic genome, 50x simulated CLR reads (mean 8 kb, 13% error), -c 50 -g 5 --nodp"),
+                 desc="4.6 Mb synthetic genome, 50x simulated CLR reads (mean 8 kb, 13% error), -c 50 -g 5"),
     "cfg1": dict(genome=1_000_000, gseed=1, cov=30, mean=6000, rseed=101, c=30, g=5,
-                 desc="1 Mb synthetic genome, 30x simulated CLR reads (mean 6 kb, 13% error), -c 30 -g 5 --nodp"),
+                 desc="1 Mb synthetic genome, 30x simulated CLR reads (mean 6 kb, 13% error), -c 30 -g 5"),
     "tiny": dict(genome=100_000, gseed=1, cov=30, mean=3000, rseed=101, c=30, g=5,
-                 desc="100 kb synthetic genome, 30x simulated CLR reads (mean 3 kb), -c 30 -g 5 --nodp"),
+                 desc="100 kb synthetic genome, 30x simulated CLR reads (mean 3 kb), -c 30 -g 5"),
 }
 REF_STRIDE = os.path.join(ROOT, "oracle", "_ref", "stride")
 ORACLE = os.path.join(ROOT, "oracle", "pbsc_oracle")
@@ -112,11 +113,11 @@ def write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=None):
     return prefix, fa, bwt_runs
 
 
-def run_reference(prefix, fa, wl, threads, outdir):
-    """`stride pbcorrect -t T --nodp`; returns (seconds of the processing loop, wall seconds)."""
+def run_reference(prefix, fa, wl, threads, outdir, nodp):
+    """`stride pbcorrect -t T [--nodp]`; returns (seconds of the processing loop, wall seconds)."""
     t0 = time.time()
-    r = subprocess.run([REF_STRIDE, "pbcorrect", "-t", str(threads), "-p", prefix, "-o", outdir, "-c", str(wl["c"]), "-g", str(wl["g"]),
-                        "--nodp", fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    r = subprocess.run([REF_STRIDE, "pbcorrect", "-t", str(threads), "-p", prefix, "-o", outdir, "-c", str(wl["c"]), "-g", str(wl["g"])]
+                       + (["--nodp"] if nodp else []) + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     wall = time.time() - t0
     if r.returncode != 0:
         raise RuntimeError("reference failed: " + r.stderr[-500:])
@@ -124,15 +125,20 @@ def run_reference(prefix, fa, wl, threads, outdir):
     return (float(m.group(1)) if m else wall), wall
 
 
-def oracle_rank_queries(prefix, fa, wl, threads):
-    """Algorithmic rank queries of the reference algorithm on the sample (instrumented oracle)."""
+def oracle_rank_queries(prefix, fa, wl, threads, nodp):
+    """Algorithmic work of the reference algorithm on the sample (instrumented oracle): rank queries of the seed and
+    FM-extend phases, and for the DP fallback the band cells filled, rows kept and LF steps."""
     with tempfile.TemporaryDirectory() as d:
         r = subprocess.run([ORACLE, "pbcorrect", "--threads", str(threads), "-p", prefix, "-o", os.path.join(d, "o"), "-c", str(wl["c"]),
-                            "-g", str(wl["g"]), "--nodp", fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                            "-g", str(wl["g"])] + (["--nodp"] if nodp else []) + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     m = re.search(r"rank queries (\d+) \(seed (\d+), extend (\d+)\), walks (\d+)", r.stderr)
     if not m:
         return None
-    return {"total": int(m.group(1)), "seed": int(m.group(2)), "extend": int(m.group(3)), "walks": int(m.group(4))}
+    out = {"total": int(m.group(1)), "seed": int(m.group(2)), "extend": int(m.group(3)), "walks": int(m.group(4))}
+    m = re.search(r"dp fallbacks (\d+), rows kept (\d+), band cells (\d+), LF steps (\d+)", r.stderr)
+    if m:
+        out.update({"dp_jobs": int(m.group(1)), "dp_rows_kept": int(m.group(2)), "dp_cells": int(m.group(3)), "dp_lf_steps": int(m.group(4))})
+    return out
 
 
 def main():
@@ -146,8 +152,12 @@ def main():
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="Mbp of reads for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--nodp", action="store_true", help="disable the DP/MSA fallback on both arms (seeds + FM extension only)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.nodp:
+        wl["desc"] += " --nodp"
+    metric = "corrected Mbp/s (seed + FM-extend, --nodp)" if args.nodp else "corrected Mbp/s (seed + FM-extend + DP/MSA fallback, default options)"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,7 +178,7 @@ def main():
             prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads)
             times = []
             for i in range(args.warmup + args.steps):
-                secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, f"out{i}"))
+                secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, f"out{i}"), args.nodp)
                 log(f"reference step {i}: {secs:.2f}s processing ({wall:.1f}s wall incl. index load)")
                 if i >= args.warmup:
                     times.append(secs)
@@ -176,7 +186,7 @@ def main():
         v = sample_mbp / (ms / 1000)
         sample_desc = f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index"
         print(json.dumps({
-            "impl": "reference", "metric": "corrected Mbp/s (seed + FM-extend, --nodp)", "value": v, "unit": "Mbp/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": metric, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "sample": sample_desc, "threads": cores},
@@ -211,7 +221,7 @@ def main():
         idx.build_prefix_table(args.k0)
     index_s = time.time() - t
     log(f"rank {rank}: rank tables + prefix table (k0={args.k0}) on device in {index_s:.1f}s, {idx.device_bytes() / 1e9:.2f} GB")
-    params = api.Params.make(coverage=wl["c"], genome=wl["g"], no_dp=True)
+    params = api.Params.make(coverage=wl["c"], genome=wl["g"], no_dp=args.nodp)
     packed = packed_ascii(codes, off)
 
     def barrier():
@@ -231,7 +241,7 @@ def main():
     for _ in range(args.steps):
         step_ms.append(batch.run())
         tm = api.last_timing()
-        phase.append((tm["seed_ms"], tm["extend_ms"]))
+        phase.append((tm["seed_ms"], tm["extend_ms"], tm["dp_ms"], tm["walk_ms"], tm["walk_launches"], tm["dp_jobs"], tm["dp_rows"]))
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000
     clocks = sampler.stop()
@@ -281,20 +291,22 @@ def main():
         sample_mbp = float(off[sample_reads]) / 1e6
         with tempfile.TemporaryDirectory() as d:
             prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=runs)
-            secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"))
+            secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"), args.nodp)
             log(f"reference CPU baseline: {sample_mbp:.1f} Mbp in {secs:.2f}s with {cores} threads")
             cpu = {"value": sample_mbp / secs, "unit": "Mbp/s", "cores": cores, "kind": "reference",
-                   "sample": f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores} --nodp"}
+                   "sample": f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores}" + (" --nodp" if args.nodp else "")}
             small = max(1, min(int(np.searchsorted(off, min(sample_mbp, 4.0) * 1e6)), n_reads))
             if os.path.exists(ORACLE):
                 from longreadselfcorrect_b200 import synth
                 fa2 = os.path.join(d, "alg.fa")
                 synth.write_fasta(fa2, codes[: off[small]], off[: small + 1])
-                alg = oracle_rank_queries(prefix, fa2, wl, min(cores, 32))
+                alg = oracle_rank_queries(prefix, fa2, wl, min(cores, 32), args.nodp)
                 if alg:
                     alg["sample_bases"] = int(off[small])
 
-    # ---- roofline of the dominant kernel (correct_reads_kernel, the FM-extend chain) ----
+    # ---- roofline of the dominant kernel: walk_levels_kernel (the FM-extend level loop), timed by CUDA events around each of
+    #      its launches inside the library (pbsc_timing.walk_ms).  Algorithmic bytes = rank queries the reference algorithm issues
+    #      for the same walks (instrumented oracle on a sample, scaled by walk count) x 32 B (one sector per occ(c, i)). ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -303,20 +315,38 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ext_ms = float(np.mean([p[1] for p in phase]))
     seed_ms = float(np.mean([p[0] for p in phase]))
-    roof = {"bound": "hbm", "kernel": "correct_reads_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+    dp_ms = float(np.mean([p[2] for p in phase]))
+    walk_ms = float(np.mean([p[3] for p in phase]))
+    walk_launches = int(phase[-1][4])
+    traffic = None
+    try:
+        # per-launch DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/README.md)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(args.workload + ("_nodp" if args.nodp else ""), {}).get("walk_levels_kernel")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "walk_levels_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "kernel_ms": ext_ms, "seed_phase_ms": seed_ms}
+            "kernel_ms": walk_ms, "kernel_launches_per_step": walk_launches, "extend_phase_ms": ext_ms, "seed_phase_ms": seed_ms,
+            "dp_fallback_ms": dp_ms}
     if alg and alg.get("walks"):
         per_walk = alg["extend"] / alg["walks"]
         alg_bytes = per_walk * walks * 32.0
-        roof["achieved"] = alg_bytes / (ext_ms / 1000) / 1e9
+        roof["achieved"] = alg_bytes / (walk_ms / 1000) / 1e9
         roof["frac"] = roof["achieved"] / peak
+        roof["algorithmic_bytes_per_step"] = alg_bytes
         roof["algorithmic_rank_queries_per_walk"] = per_walk
         roof["algorithmic_rank_queries_per_read_base_seed_phase"] = alg["seed"] / alg["sample_bases"]
         roof["seed_phase_achieved_GBs"] = alg["seed"] / alg["sample_bases"] * codes.size * 32.0 / (seed_ms / 1000) / 1e9
+        if alg.get("dp_jobs"):
+            # second kernel family (integer DP, issue-bound rather than HBM-bound): band cells per second
+            dp_jobs = int(phase[-1][5])
+            cells = alg["dp_cells"] / alg["dp_jobs"] * dp_jobs
+            roof["dp_fallback"] = {"jobs_per_step": dp_jobs, "rows_aligned_per_step": int(phase[-1][6]),
+                                   "band_cells_per_step": cells, "Gcells_per_s": cells / (dp_ms / 1000) / 1e9}
 
     line = {
-        "metric": "corrected Mbp/s (seed + FM-extend, --nodp)", "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "reads": n_reads, "mbp": total_mbp, "walks": walks, "fm_success": fm,

@@ -194,6 +194,8 @@ typedef struct pbsc_timing
     float dp_ms;             /* part of extend_ms spent in the DP / multiple-alignment fallback */
     uint64_t dp_jobs;        /* failed walks that went through correctByMSAlignment */
     uint64_t dp_rows;        /* overlapping reads retrieved and aligned for them */
+    float walk_ms;           /* walk_levels_kernel alone: CUDA events around each of its launches, summed */
+    uint64_t walk_launches;
 } pbsc_timing;
 int pbsc_last_timing(pbsc_timing* t);
 

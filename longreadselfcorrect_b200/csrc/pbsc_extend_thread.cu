@@ -186,8 +186,8 @@ setup_tasks_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
 // Level loop.  Every lane owns one walk at a time; all lanes of a warp run the same loop (one level of extendOverlap per
 // iteration), and a lane whose walk ended picks the next task at the top of the next iteration, so the warp stays converged
 // at the granularity of a level.
-__global__ void __launch_bounds__(TW_BLOCK)
-walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
+__device__ __forceinline__ void
+walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch, size_t stride,
                    unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
                    const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
                    unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy, uint32_t* nodepool,
@@ -243,6 +243,33 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
         }
     }
     if (done) atomicAdd(walk_counter, done);
+}
+
+// The level loop is latency-bound (ncu: 59 % of stall samples wait on a rank sector), so the register budget decides how many
+// walks an SM keeps in flight: MINB resident blocks of 128 lanes (3 -> 168 registers, 4 -> 128, 5 -> 96 with spills to L1).
+template <int MINB>
+__global__ void __launch_bounds__(TW_BLOCK, MINB)
+walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
+                   unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
+                   const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
+                   unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy, uint32_t* nodepool,
+                   unsigned long long* pool_used, uint64_t pool_cap, tw::Caps caps, const unsigned int* n_items_dev, int last_pass)
+{
+    walk_levels_body(idx, P, scratch, stride, counter, n_items, list, tasks, recpool, rec_off, pend_base, pend_cap, outpool, minSA, walk_counter,
+                     heavy_list, n_heavy, nodepool, pool_used, pool_cap, caps, n_items_dev, last_pass);
+}
+typedef void (*WalkKernel)(FmIndexDev, ExtParamsDev, uint8_t*, size_t, unsigned long long*, uint64_t, const uint32_t*, WalkTask*, uint8_t*,
+                           const uint64_t*, uint64_t, uint64_t, uint8_t*, uint64_t, unsigned long long*, uint32_t*, unsigned int*, uint32_t*,
+                           unsigned long long*, uint64_t, tw::Caps, const unsigned int*, int);
+static WalkKernel walk_kernel_for(int minb)
+{
+    switch (minb) { case 3: return walk_levels_kernel<3>; case 4: return walk_levels_kernel<4>; case 5: return walk_levels_kernel<5>; default: return walk_levels_kernel<6>; }
+}
+static int walk_min_blocks()
+{
+    const char* e = getenv("PBSC_TW_MINB");
+    const int v = e ? atoi(e) : 6;   // measured on config 2: 1002 ms at 3 blocks/SM, 867 ms at 6
+    return (v >= 3 && v <= 6) ? v : 6;
 }
 
 // thread per task: write the merged sequence of every light walk that succeeded
@@ -550,6 +577,11 @@ struct ThreadEngine
     bool heavy_engine_warp = false;
     bool no_dp = true;
     const pbsc_params* params = nullptr;
+    WalkKernel kernel = nullptr;
+    // CUDA events around every walk_levels_kernel launch (the dominant kernel): its own duration, for the roofline
+    std::vector<cudaEvent_t> ev;
+    ~ThreadEngine() { for (auto e : ev) cudaEventDestroy(e); }
+    void mark(cudaStream_t st) { cudaEvent_t e; if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); ev.push_back(e); } }
     ArenaPtr<unsigned long long> pool_used;
     uint64_t pool_cap = 0;
     ArenaPtr<unsigned int> n_heavy;
@@ -579,9 +611,11 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     if (nb < 1) nb = 1;
     PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 8, st));
     PBSC_CUDA(cudaMemsetAsync(E.pool_used.p, 0, 8, st));
-    walk_levels_kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
+    E.mark(st);
+    E.kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
                                                 E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
                                                 E.nodepool.p, E.pool_used.p, E.pool_cap, E.light, nullptr, 0);
+    E.mark(st);
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
     if (E.heavy_engine_warp)
     {
@@ -591,9 +625,11 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     }
     else
     {
-        walk_levels_kernel<<<E.hblocks, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, E.recpool.p, E.rec_off.p,
+        E.mark(st);
+        E.kernel<<<E.hblocks, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, E.recpool.p, E.rec_off.p,
                                                            E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p + E.heavy_cap,
                                                            E.n_heavy.p + 1, E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, E.n_heavy.p, 1);
+        E.mark(st);
     }
     materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, E.recpool.p, E.rec_off.p, E.pend_rec_base, pcap,
                                                                          E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
@@ -612,7 +648,7 @@ static int thread_geometry(int device, int* blocks)
     int sms = 0;
     PBSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     int per_sm = 0;
-    PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_levels_kernel, TW_BLOCK, 0));
+    PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_kernel_for(walk_min_blocks()), TW_BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
     const char* e = getenv("PBSC_TW_BLOCKS_PER_SM");
     if (e && atoi(e) > 0) per_sm = std::min(per_sm, atoi(e));
@@ -680,6 +716,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         E.heavy_engine_warp = e && strcmp(e, "warp") == 0;
     }
     const uint64_t minSA = p->pb_coverage > 60 ? (uint64_t)((p->pb_coverage / 60) * 3) : 3;
+    E.kernel = walk_kernel_for(walk_min_blocks());
     int rc = thread_geometry(idx->device, &E.blocks);
     if (rc != PBSC_OK) return rc;
     E.light = tw::Caps{8, 32, 40, 32};
@@ -696,7 +733,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     else
     {
         E.hstride = tw::thread_scratch_bytes(E.Pw.node_cap, E.heavy);
-        E.hblocks = E.blocks;      // same residency as the light pass: the pass is latency-bound, not capacity-bound
+        E.hblocks = std::min(E.blocks, idx->sm_count * 3);   // latency-bound like the light pass, but 280 KB of scratch per lane
         const char* e = getenv("PBSC_TW_HEAVY_BLOCKS_PER_SM");
         if (e && atoi(e) > 0) E.hblocks = idx->sm_count * atoi(e);
         PBSC_CUDA(E.hscratch.get(idx, "tw.hscratch", E.hstride * (size_t)E.hblocks * TW_BLOCK));
@@ -761,6 +798,16 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         if (rc != PBSC_OK) return rc;
     }
     if (launches) *launches += nl;
+    {
+        // every launch was followed by a stream synchronisation (the stitch loop reads its counter), so the events are complete
+        Timing& T = last_timing();
+        T.walk_ms = 0; T.walk_launches = 0;
+        for (size_t i = 0; i + 1 < E.ev.size(); i += 2)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, E.ev[i], E.ev[i + 1]) == cudaSuccess) { T.walk_ms += ms; T.walk_launches++; }
+        }
+    }
     return PBSC_OK;
 }
 

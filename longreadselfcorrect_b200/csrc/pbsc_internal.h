@@ -83,6 +83,8 @@ struct Timing
     uint64_t kernel_launches = 0, seed_pairs = 0, rank_queries = 0;
     float dp_ms = 0;                  // part of extend_ms spent in the DP / multiple-alignment fallback
     uint64_t dp_jobs = 0, dp_rows = 0;
+    float walk_ms = 0;                // walk_levels_kernel alone (CUDA events around each of its launches)
+    uint64_t walk_launches = 0;
 };
 Timing& last_timing();
 

@@ -100,6 +100,17 @@ __device__ __forceinline__ void occ4(const FmTable& t, uint64_t p, uint64_t r[4]
 }
 
 static __device__ __noinline__ Interval update1(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
+// one copy of occ4 for the four probes of a leaf: the level loop is bound by instruction fetch (ncu: the GPC instruction cache
+// runs at 86 % of its request peak with 84 KB of SASS), so hot code is kept small rather than inlined
+static __device__ __noinline__ void occ4_ool(const FmTable& t, uint64_t p, uint64_t r[4]) { occ4(t, p, r); }
+// copy of one 128-byte leaf record
+__device__ __forceinline__ void leaf_copy(Leaf* dst, const Leaf* src)
+{
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    #pragma unroll
+    for (int x = 0; x < (int)(sizeof(Leaf) / 16); x++) d4[x] = s4[x];
+}
 
 // both strands of the k-mer w[0..K): fwd = findInterval(RBWT, reverse(w)), rvc = findInterval(BWT, revcomp(w));
 // `get(j)` returns w[j].  The two chains are advanced together so that their sectors are in flight at the same time.
@@ -212,6 +223,7 @@ static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint3
         }
     }
     if (mx[0] - S.P->freq_int[LB] < 5) return LB;
+    #pragma unroll 1
     for (int e = 1; e <= extra; e++) if (mx[e] - S.P->freq_int[LB + e] < 5) return LB + e;
     return UB;
 }
@@ -220,6 +232,7 @@ static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint3
 __device__ __forceinline__ bool insufficient(const State& S, const Leaf* bank, uint32_t cnt)
 {
     uint32_t high = 0;
+    #pragma unroll 1
     for (uint32_t j = 0; j < cnt; j++) high += bank[j].kmerFreq > S.P->high_freq_thr;
     if (high == 0) return true;
     if (high <= 2 && cnt >= 5) return true;
@@ -228,14 +241,14 @@ __device__ __forceinline__ bool insufficient(const State& S, const Leaf* bank, u
 }
 
 // acceptance rule of getFMIndexExtensions (LongReadCorrectByOverlap.cpp:725-781) with exact integer ratio tests
-__device__ __forceinline__ uint32_t eval4(const int freq[4], uint64_t totalcount, int maxfreq, uint32_t match5, uint32_t tailCount, uint64_t cutoffSA)
+static __device__ __noinline__ uint32_t eval4(const int freq[4], uint64_t totalcount, int maxfreq, uint32_t match5, uint32_t tailCount, uint64_t cutoffSA)
 {
     uint32_t mask = 0;
     if (maxfreq <= 0) return 0;   // 0/0 is NaN in the reference: never >= cutoff
     const bool isHomopolymer = tailCount >= 3;
     const bool isRepeat = maxfreq > 100, isHighlyRepeat = maxfreq > 150, isLowlyRepeat = maxfreq > 50;
     const bool isLowCoverage = totalcount >= cutoffSA + 2;
-    #pragma unroll
+    #pragma unroll 1
     for (int b = 0; b < 4; b++)
     {
         const uint64_t kmerFreq = (uint64_t)(int64_t)freq[b];
@@ -265,16 +278,18 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
     Leaf* oldL = S.s.oldL;
     Leaf* newL = S.s.newL;
     double minErr = 1.0;
+    #pragma unroll 1
     for (uint32_t i = 0; i < S.n; i++) minErr = fmin(minErr, oldL[i].local_err);
     // drop leaves whose local error rate is far above the best one
     {
         uint32_t w = 0;
+        #pragma unroll 1
         for (uint32_t i = 0; i < S.n; i++)
         {
             const double diff = __dsub_rn(oldL[i].local_err, minErr);
             const bool drop = (diff > 0.05 && S.curLen > (uint64_t)(RING_LEN / 2)) || (diff > 0.1 && S.curLen > 15);
             if (drop) { ring_release(S, oldL[i].ring); continue; }
-            if (w != i) oldL[w] = oldL[i];
+            if (w != i) leaf_copy(oldL + w, oldL + i);
             w++;
         }
         S.n = w;
@@ -284,61 +299,70 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
     #pragma unroll 1
     for (uint32_t i = 0; i < n; i++)
     {
-        const Leaf parent = oldL[i];
+        const Leaf* parent = oldL + i;
         // the eight one-base probes from four sectors
         uint64_t fl[4], fh[4], rl[4], rh[4];
-        const bool fV = parent.f_hi > parent.f_lo, rV = parent.r_hi > parent.r_lo;
-        if (fV) { occ4(idx.t[PBSC_RBWT], parent.f_lo, fl); occ4(idx.t[PBSC_RBWT], parent.f_hi, fh); }
-        if (rV) { occ4(idx.t[PBSC_BWT], parent.r_lo, rl); occ4(idx.t[PBSC_BWT], parent.r_hi, rh); }
+        const uint64_t pf_lo = parent->f_lo, pf_hi = parent->f_hi, pr_lo = parent->r_lo, pr_hi = parent->r_hi;
+        const bool fV = pf_hi > pf_lo, rV = pr_hi > pr_lo;
+        if (fV) { occ4_ool(idx.t[PBSC_RBWT], pf_lo, fl); occ4_ool(idx.t[PBSC_RBWT], pf_hi, fh); }
+        if (rV) { occ4_ool(idx.t[PBSC_BWT], pr_lo, rl); occ4_ool(idx.t[PBSC_BWT], pr_hi, rh); }
         int freq[4];
         Interval pf[4], pr[4];
         uint64_t total = 0;
         int mx = 0;
         uint32_t match5 = 0;
-        const uint32_t near5 = match5_mask(S, (uint32_t)(parent.rt_hi >> 56));
-        #pragma unroll
+        const uint64_t p_rt_hi = parent->rt_hi;
+        const uint32_t near5 = match5_mask(S, (uint32_t)(p_rt_hi >> 56));
+        #pragma unroll 1
         for (int b = 0; b < 4; b++)
         {
             if (fV) { pf[b].lo = idx.t[PBSC_RBWT].C[b] + fl[b]; pf[b].hi = idx.t[PBSC_RBWT].C[b] + fh[b]; }
-            else { pf[b].lo = parent.f_lo; pf[b].hi = parent.f_hi; }
+            else { pf[b].lo = pf_lo; pf[b].hi = pf_hi; }
             if (rV) { pr[b].lo = idx.t[PBSC_BWT].C[3 - b] + rl[3 - b]; pr[b].hi = idx.t[PBSC_BWT].C[3 - b] + rh[3 - b]; }
-            else { pr[b].lo = parent.r_lo; pr[b].hi = parent.r_hi; }
+            else { pr[b].lo = pr_lo; pr[b].hi = pr_hi; }
             freq[b] = (int)((int64_t)pf[b].size() + (int64_t)pr[b].size());
             total += (uint64_t)(int64_t)freq[b];
             mx = max(mx, freq[b]);
             if ((pf[b].valid() || pr[b].valid()) && ((near5 >> b) & 1)) match5 |= 1u << b;
         }
-        uint32_t mask = eval4(freq, total, mx, match5, parent.tailCount, thr);
-        if (!mask && parent.local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, parent.tailCount, thr - 1);
+        const uint32_t p_tailCount = parent->tailCount;
+        uint32_t mask = eval4(freq, total, mx, match5, p_tailCount, thr);
+        if (!mask && parent->local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, p_tailCount, thr - 1);
         if (!mask) continue;
         const uint32_t cnt = __popc(mask);
         if (m + cnt > S.cap.new_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
         if (S.nNodes + cnt > S.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
+        const uint32_t p_node = parent->node, p_ring = parent->ring, p_tailLetter = parent->tailLetter;
         uint32_t j = 0;
         #pragma unroll 1
         for (int b = 0; b < 4; b++)
         {
             if (!((mask >> b) & 1)) continue;
-            Leaf c = parent;
-            c.f_lo = pf[b].lo; c.f_hi = pf[b].hi; c.r_lo = pr[b].lo; c.r_hi = pr[b].hi;
-            c.kmerFreq = freq[b];
-            tail_push(c.rt_hi, c.rt_lo, b);
-            if (parent.tailLetter == b) c.tailCount = parent.tailCount + 1; else { c.tailLetter = (uint8_t)b; c.tailCount = 1; }
-            c.node = S.nNodes++;
-            S.s.nodes[c.node] = (parent.node << 2) | (uint32_t)b;
-            c.alive = 1;
+            Leaf* c = newL + m;
+            leaf_copy(c, parent);
+            c->f_lo = pf[b].lo; c->f_hi = pf[b].hi; c->r_lo = pr[b].lo; c->r_hi = pr[b].hi;
+            c->kmerFreq = freq[b];
+            uint64_t th = p_rt_hi, tl = parent->rt_lo;
+            tail_push(th, tl, b);
+            c->rt_hi = th; c->rt_lo = tl;
+            if (p_tailLetter == (uint32_t)b) c->tailCount = p_tailCount + 1; else { c->tailLetter = (uint8_t)b; c->tailCount = 1; }
+            const uint32_t node = S.nNodes++;
+            c->node = node;
+            S.s.nodes[node] = (p_node << 2) | (uint32_t)b;
+            c->alive = 1;
             if (j > 0)
             {
                 // createChild copies both error-rate records (FMIndexWalk/SAINode.cpp:166-189)
                 const int slot = ring_take(S);
                 if (slot < 0) { S.status = PBSC_WALK_HEAVY; return 0; }
-                const double* src = S.s.rings + (size_t)parent.ring * RING_LEN;
+                const double* src = S.s.rings + (size_t)p_ring * RING_LEN;
                 double* dst = S.s.rings + (size_t)slot * RING_LEN;
                 const int have = min((int)S.level, RING_LEN);   // GlobalErrorRateRecord holds `level` entries so far
+                #pragma unroll 4
                 for (int x = 0; x < have; x++) dst[x] = src[x];
-                c.ring = (uint16_t)slot;
+                c->ring = (uint16_t)slot;
             }
-            newL[m++] = c;
+            m++;
             j++;
         }
     }
@@ -349,6 +373,7 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
 __device__ __forceinline__ int hash_find(const State& S, uint32_t key)
 {
     uint32_t h = (key * 2654435761u) & S.hashMask;
+    #pragma unroll 1
     for (;;)
     {
         const uint64_t e = S.s.hash[h];
@@ -357,6 +382,10 @@ __device__ __forceinline__ int hash_find(const State& S, uint32_t key)
         h = (h + 1) & S.hashMask;
     }
 }
+
+// out-of-line IEEE division and 64-bit remainder: each expands to a few hundred bytes of SASS
+static __device__ __noinline__ double ddiv_ool(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ __noinline__ uint64_t urem_ool(uint64_t a, uint64_t b) { return a % b; }
 
 // PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664)
 static __device__ __noinline__ void prune(State& S, uint32_t m)
@@ -372,7 +401,7 @@ static __device__ __noinline__ void prune(State& S, uint32_t m)
     #pragma unroll 1
     for (uint32_t j = 0; j < m; j++)
     {
-        Leaf L = S.s.newL[j];
+        Leaf& L = S.s.newL[j];
         bool found = false;
         const uint64_t d = curLen - (uint64_t)L.lastOverlapLen;
         if (d > seedSize || d <= 1)
@@ -403,6 +432,7 @@ static __device__ __noinline__ void prune(State& S, uint32_t m)
                 if (rV) gr = group_find(S.s.sR, S.n9R, keyMask - keyF, nr);
                 int minIdxDiff = 10000;
                 const uint32_t lim = max(nf, nr);
+                #pragma unroll 1
                 for (uint32_t i = 0; i < lim; i++)
                 {
                     uint64_t v = 0;
@@ -427,7 +457,7 @@ static __device__ __noinline__ void prune(State& S, uint32_t m)
             else
             {
                 const uint64_t v = currSeedIdx + (uint64_t)(int64_t)L.seedOff - (uint64_t)L.lastSeedIdx;
-                if (v % seedSize == 1) { /* numOfErrors++ : never read */ }
+                if (urem_ool(v, seedSize) == 1) { /* numOfErrors++ : never read */ }
                 else if (v > seedSize - 1) L.redeem = __dadd_rn(L.redeem, P.redeem_b);
             }
         }
@@ -436,18 +466,17 @@ static __device__ __noinline__ void prune(State& S, uint32_t m)
         double matchedLen = __dsub_rn(__dadd_rn((double)L.totalSeeds, (double)seedSize), 1.0);
         matchedLen = __dadd_rn(matchedLen, L.redeem);
         const double totalLen = (double)curLen;
-        double err = __ddiv_rn(__dsub_rn(totalLen, matchedLen), totalLen);
+        double err = ddiv_ool(__dsub_rn(totalLen, matchedLen), totalLen);
         double* ring = S.s.rings + (size_t)L.ring * RING_LEN;
         ring[S.level % RING_LEN] = err;
         L.global_err = err;
         if (S.level + 1 >= (uint32_t)RING_LEN)
         {
             const double old = ring[(S.level + 1) % RING_LEN];
-            err = __ddiv_rn(__dsub_rn(__dmul_rn(err, totalLen), __dmul_rn(old, __dsub_rn(totalLen, (double)RING_LEN))), (double)RING_LEN);
+            err = ddiv_ool(__dsub_rn(__dmul_rn(err, totalLen), __dmul_rn(old, __dsub_rn(totalLen, (double)RING_LEN))), (double)RING_LEN);
         }
         L.local_err = err;
         if (err > P.walk_error_rate) { L.alive = 0; ring_release(S, L.ring); }
-        S.s.newL[j] = L;
     }
 }
 
@@ -575,18 +604,21 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
     H.hashMask = pow2_ceil(2 * n9) - 1;
     {
         ulonglong2* hz = reinterpret_cast<ulonglong2*>(v.hash);
+        #pragma unroll 1
         for (uint32_t h = 0; h <= H.hashMask / 2; h++) hz[h] = make_ulonglong2(~0ull, ~0ull);
     }
     bool dup = false;
     {
         uint32_t key = 0;
         const uint32_t keyMask = (1u << (2 * s9)) - 1u;
+        #pragma unroll 1
         for (int j = 0; j < s9 - 1; j++) key |= (uint32_t)q[j] << (2 * (j + 1));
         #pragma unroll 1
         for (uint32_t p = 0; p < n9 && !dup; p++)
         {
             key = ((key >> 2) | ((uint32_t)q[p + s9 - 1] << (2 * (s9 - 1)))) & keyMask;
             uint32_t h = (key * 2654435761u) & H.hashMask;
+            #pragma unroll 1
             for (;;)
             {
                 const uint64_t e = v.hash[h];
@@ -604,6 +636,7 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
         for (uint32_t p = 0; p < n9; p++)
         {
             uint32_t keyF = 0;
+            #pragma unroll 1
             for (int j = 0; j < s9; j++) keyF |= (uint32_t)q[p + j] << (2 * j);
             bool fv, rv;
             if (idx.idmer_valid != nullptr && idx.idmer_len == s9) { const uint8_t b = __ldg(idx.idmer_valid + keyF); fv = b & 1; rv = (b & 2) != 0; }
@@ -626,11 +659,16 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
     // bases follow an occurrence of that 4-mer near the current length
     {
         uint4* z = reinterpret_cast<uint4*>(v.start4);
+        #pragma unroll 1
         for (int x = 0; x < 33; x++) z[x] = make_uint4(0, 0, 0, 0);
         auto c4 = [&](uint32_t p) { return (uint32_t)(q[p] | (q[p + 1] << 2) | (q[p + 2] << 4) | (q[p + 3] << 6)); };
+        #pragma unroll 1
         for (uint32_t p = 0; p < H.n5; p++) v.start4[c4(p) + 1]++;
+        #pragma unroll 1
         for (int c = 1; c <= 256; c++) v.start4[c] = (uint16_t)(v.start4[c] + v.start4[c - 1]);
+        #pragma unroll 1
         for (int c = 0; c < 256; c++) v.cur4[c] = v.start4[c];
+        #pragma unroll 1
         for (uint32_t p = 0; p < H.n5; p++) v.pos4[v.cur4[c4(p)]++] = (uint16_t)p;
     }
     // root intervals (:106-124)
@@ -650,6 +688,7 @@ __device__ __forceinline__ uint32_t match5_mask(const State& S, uint32_t tail4)
     const int64_t hi = min((int64_t)S.curLen + (int64_t)S.maxIndel, (int64_t)S.n5 - 1);
     uint32_t mask = 0;
     const uint32_t e1 = S.s.start4[tail4 + 1];
+    #pragma unroll 1
     for (uint32_t e = S.s.start4[tail4]; e < e1; e++)
     {
         const int64_t p = S.s.pos4[e];
@@ -682,12 +721,14 @@ __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, cons
     R.f_lo = H.rf_lo; R.f_hi = H.rf_hi; R.r_lo = H.rr_lo; R.r_hi = H.rr_hi;
     R.redeem = 0; R.local_err = 0; R.global_err = 0;
     R.rt_hi = R.rt_lo = 0;
+    #pragma unroll 1
     for (uint32_t j = 0; j < k; j++) tail_push(R.rt_hi, R.rt_lo, q[j]);
     R.lastOverlapLen = k; R.lastSeedIdx = k - s9; R.totalSeeds = k - s9 + 1; R.seedOff = 0;
     R.res_first = -1; R.res_second = -1;
     R.kmerFreq = (int)((int64_t)(R.f_hi - R.f_lo) + (int64_t)(R.r_hi - R.r_lo));
     R.tailLetter = q[k - 1];
     uint32_t tc = 0;
+    #pragma unroll 1
     for (int j = (int)k - 1; j >= 0 && q[j] == R.tailLetter; j--) tc++;
     R.tailCount = tc;
     R.node = 0; R.ring = 0; R.alive = 1; R.pad[0] = 0;
@@ -721,10 +762,12 @@ static __device__ __noinline__ void one_level(State& S)
     if (m > 0)
     {
         // old leaves are gone: those that were not extended release their ring (children inherited the others)
+        #pragma unroll 1
         for (uint32_t i = 0; i < S.n; i++)
         {
             bool inherited = false;
             const uint16_t ring = S.s.oldL[i].ring;
+            #pragma unroll 1
             for (uint32_t j = 0; j < m && !inherited; j++) inherited = S.s.newL[j].ring == ring;
             if (!inherited) ring_release(S, ring);
         }
@@ -748,10 +791,11 @@ static __device__ __noinline__ void one_level(State& S)
     S.level++;
     if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return; }
     uint32_t nn = 0;
+    #pragma unroll 1
     for (uint32_t j = 0; j < m; j++)
     {
         if (!S.s.newL[j].alive) continue;
-        if (nn < S.cap.old_cap) S.s.oldL[nn] = S.s.newL[j];
+        if (nn < S.cap.old_cap) leaf_copy(S.s.oldL + nn, S.s.newL + j);
         nn++;
     }
     S.n = nn;
@@ -772,6 +816,7 @@ static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t
     {
         double best = 1.0;
         int bi = -1;
+        #pragma unroll 1
         for (uint32_t i = 0; i < S.nRes; i++) { const double e = S.s.res[i].err; if (e < best) { best = e; bi = (int)i; } }
         if (bi < 0) return PBSC_WALK_NO_PATH;
         const WalkResult r = S.s.res[bi];
@@ -780,6 +825,7 @@ static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t
         if (off + nn > pool_cap) return PBSC_WALK_OVERFLOW;
         const uint4* src = reinterpret_cast<const uint4*>(S.s.nodes);
         uint4* dst = reinterpret_cast<uint4*>(nodepool + off);
+        #pragma unroll 4
         for (uint32_t x = 0; x < nn / 4; x++) dst[x] = src[x];
         hdr->res_node = r.node; hdr->res_depth = r.depth; hdr->res_i = r.i; hdr->n_nodes = S.nNodes; hdr->node_off = off;
         return PBSC_TASK_MATERIALIZE;
@@ -802,10 +848,13 @@ __device__ __forceinline__ int materialize(const SetupView& v, int min_overlap, 
     const uint32_t tailLen = H.trgLen > (uint32_t)min_overlap ? H.trgLen - tailFrom : 0;
     const uint32_t len = H.res_depth + tailLen;
     if (len > outCap) return PBSC_WALK_OVERFLOW;
+    #pragma unroll 1
     for (uint32_t x = 0; x < k; x++) out[x] = q[x];
+    #pragma unroll 1
     for (uint32_t x = 0; x < tailLen; x++) out[H.res_depth + x] = trg[tailFrom + x];
     const uint32_t* nodes = nodepool + H.node_off;
     uint32_t node = H.res_node;
+    #pragma unroll 1
     for (uint32_t x = 0; x < chain; x++) { const uint32_t w = nodes[node]; out[H.res_depth - 1 - x] = (uint8_t)(w & 3); node = w >> 2; }
     *outLen = len;
     return 1;
