@@ -226,6 +226,12 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
             }
         }
         if (__all_sync(FULL, !active)) break;
+        {
+            // warp-wide stage: the leaves of all 32 walks that start this level by refining are pooled and dealt out evenly
+            const bool need = active && tw::walk_continues(S) && tw::needs_refine(S);
+            tw::refine_coop(idx, need ? S.n : 0u, S.s.oldL, (int)S.maxOverlap);
+            if (need) S.curK = S.maxOverlap;
+        }
         if (active)
         {
             if (tw::walk_continues(S)) tw::one_level(S);

@@ -175,6 +175,52 @@ static __device__ __noinline__ void refine(State& S, Leaf* bank, uint32_t cnt, i
     }
 }
 
+// refineSAInterval for a whole warp at once.  Every lane passes the leaves of its own walk (cnt may be 0); the warp pools
+// them and deals them out one per lane per round, so a walk with eight live leaves no longer holds the other 31 lanes for
+// eight rounds of dependent rank lookups (ncu, profiles/: the per-lane loop ran with 4.5 of 32 threads active and was 42 %
+// of the kernel's instructions).  Must be called by all 32 lanes converged.
+__device__ __forceinline__ void refine_coop(const FmIndexDev& idx, uint32_t cnt, Leaf* bank, int K)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t incl = cnt;
+    #pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        const uint32_t o = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += o;
+    }
+    const uint32_t excl = incl - cnt;
+    const uint32_t T = __shfl_sync(FULL, incl, 31);
+    const unsigned long long bankBits = (unsigned long long)bank;
+    #pragma unroll 1
+    for (uint32_t base = 0; base < T; base += 32)
+    {
+        const bool has = base + lane < T;
+        const uint32_t x = has ? base + lane : T - 1;
+        // owner = last lane whose first item is <= x
+        int lo = 0, hi = 31;
+        #pragma unroll
+        for (int step = 0; step < 5; step++)
+        {
+            const int mid = (lo + hi + 1) >> 1;
+            const uint32_t e = __shfl_sync(FULL, excl, mid);
+            if (e <= x) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t first = __shfl_sync(FULL, excl, lo);
+        Leaf* ob = (Leaf*)__shfl_sync(FULL, bankBits, lo);
+        const int oK = __shfl_sync(FULL, K, lo);
+        if (has)
+        {
+            Leaf* L = ob + (x - first);
+            const uint64_t rhi = L->rt_hi, rlo = L->rt_lo;
+            Interval f, r;
+            both_strands(idx, [&](int j) { return tail_base(rhi, rlo, oK - 1 - j); }, oK, f, r);
+            L->f_lo = f.lo; L->f_hi = f.hi; L->r_lo = r.lo; L->r_hi = r.hi;
+        }
+    }
+    __syncwarp();
+}
+
 // SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331)
 static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint32_t cnt, uint64_t LB, uint64_t UB)
 {
@@ -738,6 +784,9 @@ __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, cons
     S.n = 1;
 }
 
+// does extendLeaves start by cutting the k-mer back to maxOverlap (LongReadCorrectByOverlap.cpp:242-243)?
+__device__ __forceinline__ bool needs_refine(const State& S) { return S.phase == 0 && S.curK > S.maxOverlap; }
+
 // does extendOverlap's loop (LongReadCorrectByOverlap.cpp:161) run another level?
 __device__ __forceinline__ bool walk_continues(const State& S)
 {
@@ -754,7 +803,7 @@ __device__ __forceinline__ bool walk_continues(const State& S)
 static __device__ __noinline__ void one_level(State& S)
 {
     const ExtParamsDev& P = *S.P;
-    if (S.phase == 0 && S.curK > S.maxOverlap) { refine(S, S.s.oldL, S.n, (int)S.maxOverlap); S.curK = S.maxOverlap; }
+    // (the refineSAInterval(maxOverlap) that opens extendLeaves, :242-243, already ran warp-wide: needs_refine / refine_coop)
     const uint32_t m = attempt(S, S.phase == 2 ? S.minSA - 1 : S.minSA);
     if (S.status) return;
     Leaf* bank = nullptr;
