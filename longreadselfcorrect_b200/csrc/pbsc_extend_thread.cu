@@ -201,31 +201,52 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
     S.status = 0; S.n = 0;
     WalkTask* tk = nullptr;
     tw::SetupHdr* hdr = nullptr;
-    bool active = false, exhausted = false;
+    // lane states: a walk in progress (active), a walk that ended and still has to be filed (ended), nothing (idle).
+    // Filing a result and starting the next walk happen at the top of the iteration for every lane that is waiting.  Batching
+    // them (waiting until 8 lanes are idle) was measured and lost: 783 -> 832 ms on config 2, idle lanes cost more than the
+    // divergent refill path.
+    constexpr int REFILL_BATCH = 1;
+    bool active = false, ended = false, exhausted = false;
     unsigned long long done = 0;
     for (;;)
     {
-        if (!active && !exhausted)
+        const unsigned waiting = __ballot_sync(FULL, !active && !exhausted);
+        const unsigned walking = __ballot_sync(FULL, active);
+        if (waiting && (__popc(waiting) >= REFILL_BATCH || !walking))
         {
-            for (;;)
+            if (ended)
             {
-                const unsigned long long it = atomicAdd(counter, 1ull);
-                if (it >= n_items) { exhausted = true; break; }
-                const uint64_t ti = list ? list[it] : it;
-                tk = &tasks[ti];
-                if (!tk->valid) continue;
-                int interval; uint32_t trgLen, qlen;
-                task_shape(*tk, interval, trgLen, qlen);
-                tw::SetupView v;
-                tw::setup_view(task_record(ti, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
-                tw::begin_walk(S, idx, P, lane, v, P.node_cap, caps, minSA);
-                hdr = v.hdr;
-                active = true;
-                done++;
-                break;
+                int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
+                // the last pass carries everything the reference's loop can hold (-l leaves, 4 children each); only the
+                // label tree and the result list are bounded, and running out of those is reported, not hidden
+                if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_WALK_OVERFLOW;
+                tk->out_len = 0;
+                tk->status = st;
+                if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
+                ended = false;
+            }
+            if (!active && !exhausted)
+            {
+                for (;;)
+                {
+                    const unsigned long long it = atomicAdd(counter, 1ull);
+                    if (it >= n_items) { exhausted = true; break; }
+                    const uint64_t ti = list ? list[it] : it;
+                    tk = &tasks[ti];
+                    if (!tk->valid) continue;
+                    int interval; uint32_t trgLen, qlen;
+                    task_shape(*tk, interval, trgLen, qlen);
+                    tw::SetupView v;
+                    tw::setup_view(task_record(ti, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
+                    tw::begin_walk(S, idx, P, lane, v, P.node_cap, caps, minSA);
+                    hdr = v.hdr;
+                    active = true;
+                    done++;
+                    break;
+                }
             }
         }
-        if (__all_sync(FULL, !active)) break;
+        if (__all_sync(FULL, !active)) break;   // only reached with nobody waiting either: every lane is exhausted
         {
             // warp-wide stage: the leaves of all 32 walks that start this level by refining are pooled and dealt out evenly
             const bool need = active && tw::walk_continues(S) && tw::needs_refine(S);
@@ -235,17 +256,7 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
         if (active)
         {
             if (tw::walk_continues(S)) tw::one_level(S);
-            if (!tw::walk_continues(S))
-            {
-                int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
-                // the last pass carries everything the reference's loop can hold (-l leaves, 4 children each); only the
-                // label tree and the result list are bounded, and running out of those is reported, not hidden
-                if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_WALK_OVERFLOW;
-                tk->out_len = 0;
-                tk->status = st;
-                if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
-                active = false;
-            }
+            if (!tw::walk_continues(S)) { active = false; ended = true; }
         }
     }
     if (done) atomicAdd(walk_counter, done);
