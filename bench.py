@@ -169,8 +169,8 @@ def main():
             return 0
         codes, off = make_data(wl)
         total_mbp = codes.size / 1e6
-        # bounded sample: ~0.06 Mbp/s/core (BASELINE.md probe) x cores x ~25 s per step
-        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.05 * cores * 25))
+        # bounded sample: ~0.03-0.06 Mbp/s/core (BASELINE.md probe; the DP fallback is the slower end) x cores x ~15-25 s per step
+        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.04 * cores * 15))
         sample_reads = int(np.searchsorted(off, sample_mbp * 1e6))
         sample_reads = max(1, min(sample_reads, off.size - 1))
         sample_mbp = float(off[sample_reads]) / 1e6
@@ -260,12 +260,14 @@ def main():
     fm = int(merged["fm_num"].sum())
     batch.close()
 
-    # ---- e2e: host buffers in, corrected pieces out, through pbsc_correct_batch ----
+    # ---- e2e: host buffers in, corrected pieces out, through pbsc_correct_batch: the reads sit in pinned host memory, every
+    #      step copies them to the device, runs the path and copies the corrected pieces back into pinned host memory ----
+    pinned_in = (api.pinned_copy(packed[0]), api.pinned_copy(packed[1]))
     e2e_ms = []
     for i in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
-        idx.correct_reads(params, packed=packed)
+        idx.correct_reads(params, packed=pinned_in, pinned_out=True)
         torch.cuda.synchronize()
         if i > 0:
             e2e_ms.append((time.perf_counter() - t0) * 1000)
@@ -286,7 +288,7 @@ def main():
     cpu = None
     alg = None
     if not args.no_cpu_baseline and os.path.exists(REF_STRIDE):
-        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.05 * cores * 20))
+        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.04 * cores * 15))
         sample_reads = max(1, min(int(np.searchsorted(off, sample_mbp * 1e6)), n_reads))
         sample_mbp = float(off[sample_reads]) / 1e6
         with tempfile.TemporaryDirectory() as d:

@@ -98,6 +98,13 @@ typedef struct pbsc_read_stats
 
 const char* pbsc_last_error(void);
 int pbsc_device_count(void);
+/* Page-locked host memory for the caller's read and result buffers (optional: every entry point also accepts pageable
+ * memory).  From pinned buffers the H2D/D2H copies of pbsc_correct_batch / pbsc_batch_upload / pbsc_batch_fetch run at
+ * PCIe speed.  The reference has no counterpart (its reads live in std::string, SequenceWorkItem.h). */
+int pbsc_host_alloc(void** p, size_t bytes);
+void pbsc_host_free(void* p);
+/* give the library's cache of per-batch device blocks on `device` back to the driver */
+void pbsc_trim(int device);
 
 /* ---- parameters: PacBioSelfCorrectionMain, StriDe/PacBioSelfCorrection.cpp:195-231 ---- */
 void pbsc_params_default(pbsc_params* p);

@@ -70,7 +70,8 @@ EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc
             "pbsc_index_build_prefix_table", "pbsc_index_destroy", "pbsc_index_num_symbols", "pbsc_index_num_strings",
             "pbsc_index_device_bytes", "pbsc_index_get_symbols", "pbsc_findinterval_batch", "pbsc_findinterval_device",
             "pbsc_seed_batch", "pbsc_extend_batch", "pbsc_correct_batch", "pbsc_last_timing",
-            "pbsc_batch_upload", "pbsc_batch_run", "pbsc_batch_result_size", "pbsc_batch_fetch", "pbsc_batch_destroy"]
+            "pbsc_batch_upload", "pbsc_batch_run", "pbsc_batch_result_size", "pbsc_batch_fetch", "pbsc_batch_destroy",
+            "pbsc_host_alloc", "pbsc_host_free", "pbsc_trim"]
 
 _lib = None
 
@@ -105,6 +106,51 @@ def device_count() -> int:
 
 def _ptr(a: np.ndarray, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+class _Pinned:
+    """Owner of one page-locked host block (pbsc_host_alloc); numpy views keep it alive through .base."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        L = lib()
+        L.pbsc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.pbsc_host_free.argtypes = [C.c_void_p]
+        L.pbsc_host_free.restype = None
+        _check(L.pbsc_host_alloc(C.byref(self.ptr), C.c_size_t(max(int(nbytes), 1))))
+        self.nbytes = max(int(nbytes), 1)
+        self.buf = (C.c_uint8 * self.nbytes).from_address(self.ptr.value)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().pbsc_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(count: int, dtype=np.uint8) -> np.ndarray:
+    """numpy array over page-locked host memory (not initialised)."""
+    dt = np.dtype(dtype)
+    own = _Pinned(int(count) * dt.itemsize)
+    a = np.frombuffer(own.buf, dtype=dt, count=int(count))
+    _PINNED_OWNERS[a.ctypes.data] = own
+    return a
+
+
+def pinned_copy(a: np.ndarray) -> np.ndarray:
+    b = pinned_empty(a.size, a.dtype)
+    b[...] = a.reshape(-1)
+    return b
+
+
+_PINNED_OWNERS: dict = {}
+
+
+def pinned_free(a: np.ndarray) -> None:
+    """Release a pinned_empty() block now (otherwise it lives until the process ends)."""
+    _PINNED_OWNERS.pop(a.ctypes.data, None)
 
 
 def _concat(strings):
@@ -260,7 +306,9 @@ class Index:
         return status[:n], merged
 
     # PacBioSelfCorrectionProcess::process over a batch; returns (pieces per read, stats structured array)
-    def correct_reads(self, params: Params, reads=None, packed=None):
+    def correct_reads(self, params: Params, reads=None, packed=None, pinned_out: bool = False):
+        """PacBioSelfCorrectionProcess::process over a batch on host buffers.  With pinned_out the result buffers are
+        page-locked blocks owned by this Index and reused by the next call (their contents are overwritten then)."""
         if packed is not None:
             buf, off = packed
             n = off.size - 1
@@ -270,11 +318,22 @@ class Index:
         total = int(off[-1])
         cap = int(total * 1.3) + 4096 * 4
         while True:
-            out = np.zeros(cap, dtype=np.uint8)
             poff_cap = (total // 10 + 4 * n + 16) if params.c.split else (n + 2)
-            poff = np.zeros(poff_cap, dtype=np.uint64)
-            first = np.zeros(n + 1, dtype=np.uint64)
-            stats = np.zeros(max(n, 1), dtype=STATS_DTYPE)
+            if pinned_out:
+                key = (cap, poff_cap, n)
+                if getattr(self, "_pin_key", None) != key:
+                    for old in getattr(self, "_pin_blocks", ()):
+                        pinned_free(old)
+                    self._pin_blocks = ()
+                    self._pin = (pinned_empty(cap, np.uint8), pinned_empty(poff_cap, np.uint64), pinned_empty(n + 1, np.uint64),
+                                 np.frombuffer(pinned_empty(max(n, 1) * STATS_DTYPE.itemsize, np.uint8), dtype=STATS_DTYPE))
+                    self._pin_key = key
+                out, poff, first, stats = self._pin
+            else:
+                out = np.zeros(cap, dtype=np.uint8)
+                poff = np.zeros(poff_cap, dtype=np.uint64)
+                first = np.zeros(n + 1, dtype=np.uint64)
+                stats = np.zeros(max(n, 1), dtype=STATS_DTYPE)
             need = C.c_uint64(0)
             rc = lib().pbsc_correct_batch(self._h, C.byref(params.c), _ptr(buf, C.c_char), _ptr(off, C.c_uint64), C.c_uint64(n),
                                           _ptr(out, C.c_char), C.c_uint64(cap), _ptr(poff, C.c_uint64), C.c_uint64(poff_cap),

@@ -31,7 +31,6 @@ constexpr int DP_BW = 2 * DP_HALF + 1;    // cells per band column
 constexpr int DP_CPL = 7;                 // cells per lane: 32 x 7 = 224 >= 201
 constexpr int DP_NEG = -(1 << 28);
 constexpr int DP_WARPS = 8;               // warps per block of the alignment kernel
-constexpr int DP_TILE = 32;               // traceback tile: columns of flag words staged in shared memory
 constexpr int OP_M = 0, OP_I = 1, OP_D = 2;
 
 struct __align__(16) DpJob
@@ -257,206 +256,263 @@ dp_retrieve_kernel(const __grid_constant__ FmIndexDev idx, uint64_t n_rows, DpRo
     rows[i] = R;
 }
 
-// ---- stage 2: warp per row: banded alignment, traceback, filters -------------------------------------------------------
-__global__ void __launch_bounds__(DP_WARPS * 32)
-dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0,
-                uint32_t* flag_slabs, uint64_t slab_words, unsigned long long* counter, unsigned int* n_bad)
+// ---- stage 2: banded alignment (warp per row), traceback and filters (lane per row) -------------------------------------
+// A warp takes 32 consecutive rows.  It fills them one after the other, all lanes on one band column at a time, and keeps
+// each row's traceback bits in its own piece of the warp's arena; then every lane walks back through ITS row.  The traceback
+// is a serial chain of ~(query + read) steps: done by the whole warp it was a third of the kernel's instructions
+// (ncu, profiles/r1_dp_align_v0.txt), done lane-parallel it is 1/32 of that.
+struct RowGeom
 {
-    __shared__ uint32_t tile_s[DP_WARPS][DP_TILE * 32];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    uint32_t* tile = tile_s[wib];
-    uint32_t* flags = flag_slabs + ((size_t)blockIdx.x * DP_WARPS + wib) * slab_words;
-    for (;;)
-    {
-        unsigned long long it = 0;
-        if (lane == 0) it = atomicAdd(counter, 1ull);
-        it = __shfl_sync(FULL, it, 0);
-        if (it >= n_rows) break;
-        DpRow R = rows[it];
-        if (R.pass != 2) continue;
-        const DpJob J = jobs[R.job];
-        JobView v;
-        job_view(mem + (J.mem - mem0), J, job_rows_of(J), v);
-        uint8_t* buf = v.rows + (uint64_t)R.local * v.rowBytes;
-        const uint8_t* __restrict__ s2 = buf + R.seq_start;
-        uint8_t* ops = buf + v.seqBytes;
-        const uint8_t* __restrict__ q = v.q;
-        const int qlen = (int)J.qlen, mlen = (int)R.len, k = (int)J.k;
-        const bool isRC = R.local >= J.cnt[0] + J.cnt[1];
-        const int start_1 = isRC ? qlen - k : 0, start_2 = isRC ? mlen - k : 0;
-        const int origin = (start_2 - start_1 + 1) - (DP_HALF + 1);
-        const int nRows = mlen + 1;
+    const uint8_t* s2; const uint8_t* q; uint8_t* ops;
+    int qlen, mlen, origin;
+};
+__device__ __forceinline__ void row_geometry(const DpRow& R, const DpJob& J, uint8_t* mem, uint64_t mem0, RowGeom& g)
+{
+    JobView v;
+    job_view(mem + (J.mem - mem0), J, job_rows_of(J), v);
+    uint8_t* buf = v.rows + (uint64_t)R.local * v.rowBytes;
+    g.s2 = buf + R.seq_start;
+    g.ops = buf + v.seqBytes;
+    g.q = v.q;
+    g.qlen = (int)J.qlen; g.mlen = (int)R.len;
+    const int k = (int)J.k;
+    const bool isRC = R.local >= J.cnt[0] + J.cnt[1];
+    const int start_1 = isRC ? g.qlen - k : 0, start_2 = isRC ? g.mlen - k : 0;
+    g.origin = (start_2 - start_1 + 1) - (DP_HALF + 1);
+}
 
-        int prev[DP_CPL];
-        int sw[DP_CPL];   // s2[j-1] of this lane's rows in the current column; -1 outside the string
+// fill one row's band, column by column, all 32 lanes; returns the traceback start cell (bi, bj), bi == 0 when there is none
+__device__ __forceinline__ void dp_fill_row(const RowGeom& g, uint32_t* __restrict__ flags, int& bi, int& bj)
+{
+    const int lane = threadIdx.x & 31;
+    const uint8_t* __restrict__ s2 = g.s2;
+    const uint8_t* __restrict__ q = g.q;
+    const int qlen = g.qlen, mlen = g.mlen, origin = g.origin;
+    const int nRows = mlen + 1;
+    const int rbase = lane * DP_CPL;
+    int prev[DP_CPL];
+    int sw[DP_CPL];   // s2[j-1] of this lane's rows in the current column; -1 outside the string
+    #pragma unroll
+    for (int t = 0; t < DP_CPL; t++)
+    {
+        prev[t] = 0;
+        const int j = origin + 1 + rbase + t;
+        sw[t] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
+    }
+    int bestRowVal = 0, bestRowI = 0, bestColVal = 0, bestColJ = 0;
+    bool anyRow = false, anyCol = false;
+    #pragma unroll 1
+    for (int i = 1; i <= qlen; i++)
+    {
+        const int jb = origin + i;
+        const int first = max(jb, 1);
+        const int last = min(jb + DP_BW, nRows) - 1;
+        const bool skipCol = (last + 1 <= 0) || first >= nRows || first > last;
+        // band rows [rlo, rhi] of this column are computed; rowNoLeft is the band row that ignores its left neighbour
+        const int rlo = skipCol ? (1 << 20) : first - jb, rhi = skipCol ? (1 << 20) : last - jb;
+        const unsigned span = skipCol ? 0u : (unsigned)(rhi - rlo);   // (unsigned)(r - rlo) <= span  <=>  rlo <= r <= rhi
+        const int rowNoLeft = (rhi != rlo) ? rhi : -1;
+        const int c1 = (int)q[i - 1];
+        const int pn0 = __shfl_down_sync(FULL, prev[0], 1);
+        int a[DP_CPL], cur[DP_CPL];
+        int run = DP_NEG;
         #pragma unroll
         for (int t = 0; t < DP_CPL; t++)
         {
-            prev[t] = 0;
-            const int j = origin + 1 + lane * DP_CPL + t;
-            sw[t] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
+            const int r = rbase + t;
+            const bool comp = (unsigned)(r - rlo) <= span;
+            const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
+            const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
+            // first row of the band: left if it is in the band; last row (when not also the first): no left
+            const bool useLeft = (r < DP_BW - 1) && r != rowNoLeft;
+            const int v0 = useLeft ? max(diag, pl - 1) : diag;
+            run = max(run, comp ? v0 + r : DP_NEG);
+            a[t] = run;
         }
-        int bestRowVal = 0, bestRowI = 0, bestColVal = 0, bestColJ = 0;
-        bool anyRow = false, anyCol = false;
-        #pragma unroll 1
-        for (int i = 1; i <= qlen; i++)
+        int incl = run;
+        #pragma unroll
+        for (int off = 1; off < 32; off <<= 1)
         {
-            const int jb = origin + i;
-            const int first = max(jb, 1);
-            const int last = min(jb + DP_BW, nRows) - 1;
-            const bool skipCol = (last + 1 <= 0) || first >= nRows || first > last;
-            const int c1 = (int)q[i - 1];
-            const int pn0 = __shfl_down_sync(FULL, prev[0], 1);
-            int a[DP_CPL], cur[DP_CPL];
-            int run = DP_NEG;
+            const int o = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl = max(incl, o);
+        }
+        int excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = DP_NEG;
+        #pragma unroll
+        for (int t = 0; t < DP_CPL; t++)
+        {
+            const int r = rbase + t;
+            const bool comp = (unsigned)(r - rlo) <= span;
+            cur[t] = comp ? max(a[t], excl) - r : 0;
+        }
+        // traceback bits: does the cell equal each in-band neighbour plus its step (overlapper.cpp:607-610)
+        const int upPrev = __shfl_up_sync(FULL, cur[DP_CPL - 1], 1);
+        uint32_t w = 0;
+        #pragma unroll
+        for (int t = 0; t < DP_CPL; t++)
+        {
+            const int r = rbase + t;
+            const bool comp = (unsigned)(r - rlo) <= span;
+            const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
+            const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
+            const int upv = t > 0 ? cur[t - 1] : upPrev;
+            uint32_t f = (cur[t] == diag) ? 1u : 0u;
+            f |= (r >= 1 && cur[t] == upv - 1) ? 2u : 0u;
+            f |= (r < DP_BW - 1 && cur[t] == pl - 1) ? 4u : 0u;
+            w |= (comp ? f : 0u) << (3 * t);
+        }
+        flags[(size_t)i * 32 + lane] = w;
+        // best cell of the last row: first column with the strictly largest score (overlapper.cpp:553-561)
+        if (!skipCol && last == nRows - 1)
+        {
+            const int rs = nRows - 1 - jb;
+            int sel = 0;
+            #pragma unroll
+            for (int t = 0; t < DP_CPL; t++) if (t == rs % DP_CPL) sel = cur[t];
+            const int vv = __shfl_sync(FULL, sel, rs / DP_CPL);
+            if (!anyRow || vv > bestRowVal) { bestRowVal = vv; bestRowI = i; anyRow = true; }
+        }
+        // best cell of the last column: first row with the strictly largest score (:564-570)
+        if (i == qlen && !skipCol)
+        {
+            int lv = DP_NEG, lr = 0x7fffffff;
             #pragma unroll
             for (int t = 0; t < DP_CPL; t++)
             {
-                const int r = lane * DP_CPL + t, j = jb + r;
-                const bool comp = !skipCol && r < DP_BW && j >= first && j <= last;
-                const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
-                const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
-                // first row of the band: left if it is in the band; last row (when not also the first): no left
-                const bool useLeft = (r + 1 < DP_BW) && !(j == last && j != first);
-                const int v0 = useLeft ? max(diag, pl - 1) : diag;
-                run = max(run, comp ? v0 + r : DP_NEG);
-                a[t] = run;
+                const int r = rbase + t;
+                const bool comp = (unsigned)(r - rlo) <= span;
+                if (comp && cur[t] > lv) { lv = cur[t]; lr = r; }
             }
-            int incl = run;
             #pragma unroll
-            for (int off = 1; off < 32; off <<= 1)
+            for (int off = 16; off > 0; off >>= 1)
             {
-                const int o = __shfl_up_sync(FULL, incl, off);
-                if (lane >= off) incl = max(incl, o);
+                const int ov = __shfl_xor_sync(FULL, lv, off), orr = __shfl_xor_sync(FULL, lr, off);
+                if (ov > lv || (ov == lv && orr < lr)) { lv = ov; lr = orr; }
             }
-            int excl = __shfl_up_sync(FULL, incl, 1);
-            if (lane == 0) excl = DP_NEG;
-            #pragma unroll
-            for (int t = 0; t < DP_CPL; t++)
-            {
-                const int r = lane * DP_CPL + t, j = jb + r;
-                const bool comp = !skipCol && r < DP_BW && j >= first && j <= last;
-                cur[t] = comp ? max(a[t], excl) - r : 0;
-            }
-            // traceback bits: does the cell equal each in-band neighbour plus its step (overlapper.cpp:607-610)
-            const int upPrev = __shfl_up_sync(FULL, cur[DP_CPL - 1], 1);
-            uint32_t w = 0;
-            #pragma unroll
-            for (int t = 0; t < DP_CPL; t++)
-            {
-                const int r = lane * DP_CPL + t, j = jb + r;
-                const bool comp = !skipCol && r < DP_BW && j >= first && j <= last;
-                const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
-                const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
-                const int upv = t > 0 ? cur[t - 1] : upPrev;
-                uint32_t f = 0;
-                if (comp)
-                {
-                    f |= (cur[t] == diag) ? 1u : 0u;
-                    f |= (r >= 1 && cur[t] == upv - 1) ? 2u : 0u;
-                    f |= (r + 1 < DP_BW && cur[t] == pl - 1) ? 4u : 0u;
-                }
-                w |= f << (3 * t);
-            }
-            flags[(size_t)i * 32 + lane] = w;
-            // best cell of the last row: first column with the strictly largest score (overlapper.cpp:553-561)
-            if (!skipCol && last == nRows - 1)
-            {
-                const int rs = nRows - 1 - jb;
-                int sel = 0;
-                #pragma unroll
-                for (int t = 0; t < DP_CPL; t++) if (t == rs % DP_CPL) sel = cur[t];
-                const int vv = __shfl_sync(FULL, sel, rs / DP_CPL);
-                if (!anyRow || vv > bestRowVal) { bestRowVal = vv; bestRowI = i; anyRow = true; }
-            }
-            // best cell of the last column: first row with the strictly largest score (:564-570)
-            if (i == qlen && !skipCol)
-            {
-                int lv = DP_NEG, lr = 0x7fffffff;
-                #pragma unroll
-                for (int t = 0; t < DP_CPL; t++)
-                {
-                    const int r = lane * DP_CPL + t, j = jb + r;
-                    const bool comp = r < DP_BW && j >= first && j <= last;
-                    if (comp && cur[t] > lv) { lv = cur[t]; lr = r; }
-                }
-                #pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-                {
-                    const int ov = __shfl_xor_sync(FULL, lv, off), orr = __shfl_xor_sync(FULL, lr, off);
-                    if (ov > lv || (ov == lv && orr < lr)) { lv = ov; lr = orr; }
-                }
-                if (lr != 0x7fffffff) { anyCol = true; bestColVal = lv; bestColJ = jb + lr; }
-            }
-            // next column: the band slides down by one row
-            const int nx = __shfl_down_sync(FULL, sw[0], 1);
-            #pragma unroll
-            for (int t = 0; t < DP_CPL; t++) { prev[t] = cur[t]; if (t < DP_CPL - 1) sw[t] = sw[t + 1]; }
-            if (lane == 31)
-            {
-                const int j = jb + 1 + lane * DP_CPL + (DP_CPL - 1);
-                sw[DP_CPL - 1] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
-            }
-            else sw[DP_CPL - 1] = nx;
+            if (lr != 0x7fffffff) { anyCol = true; bestColVal = lv; bestColJ = jb + lr; }
         }
-        __syncwarp();
-        // start of the traceback (:577-586)
-        int i, j;
-        if (anyCol && (!anyRow || bestColVal > bestRowVal)) { i = qlen; j = bestColJ; }
-        else { i = anyRow ? bestRowI : 0; j = nRows - 1; }
-        if (!(anyRow || anyCol) || i <= 0 || j <= 0)
+        // next column: the band slides down by one row
+        const int nx = __shfl_down_sync(FULL, sw[0], 1);
+        #pragma unroll
+        for (int t = 0; t < DP_CPL; t++) { prev[t] = cur[t]; if (t < DP_CPL - 1) sw[t] = sw[t + 1]; }
+        if (lane == 31)
         {
-            // the reference would abort on its empty-cigar assert; report instead of inventing an alignment
-            if (lane == 0) { atomicAdd(n_bad, 1u); R.pass = 0; rows[it] = R; }
-            continue;
+            const int j = jb + 1 + rbase + (DP_CPL - 1);
+            sw[DP_CPL - 1] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
         }
-        int n = 0, ed = 0;
-        int tlo = -(1 << 30);
-        #pragma unroll 1
-        while (i > 0 && j > 0)
+        else sw[DP_CPL - 1] = nx;
+    }
+    // start of the traceback (:577-586)
+    if (anyCol && (!anyRow || bestColVal > bestRowVal)) { bi = qlen; bj = bestColJ; }
+    else { bi = anyRow ? bestRowI : 0; bj = nRows - 1; }
+    if (!(anyRow || anyCol) || bi <= 0 || bj <= 0) bi = 0;
+}
+
+__global__ void __launch_bounds__(DP_WARPS * 32, 3)
+dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0,
+                uint32_t* arenas, uint64_t arena_words, unsigned long long* counter, unsigned int* n_bad)
+{
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    uint32_t* arena = arenas + ((size_t)blockIdx.x * DP_WARPS + wib) * arena_words;
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_rows) break;
+        const int nb = (int)min((unsigned long long)32, n_rows - base);
+        int g0 = 0;
+        uint64_t used = 0;
+        // this lane's row of the current group: where its bits are and where its traceback starts
+        uint64_t my_off = 0; int my_bi = 0, my_bj = 0; bool my_todo = false;
+        for (int kk = 0; kk <= nb; kk++)
         {
-            if (i < tlo || i >= tlo + DP_TILE)
+            // fill row kk (if any), after making room by tracing back the rows filled so far when the arena is full
+            uint64_t need = 0;
+            DpRow R; DpJob J; RowGeom g;
+            bool fill = false;
+            if (kk < nb)
             {
-                tlo = max(i - (DP_TILE - 1), 0);
+                R = rows[base + kk];
+                if (R.pass == 2)
+                {
+                    J = jobs[R.job];
+                    row_geometry(R, J, mem, mem0, g);
+                    need = ((uint64_t)g.qlen + 1) * 32;
+                    fill = true;
+                }
+            }
+            if (kk == nb || (fill && used + need > arena_words))
+            {
+                // lane-parallel traceback of rows [g0, kk)
                 __syncwarp();
-                #pragma unroll 4
-                for (int c = 0; c < DP_TILE; c++)
+                if (lane >= g0 && lane < kk && my_todo)
                 {
-                    const int col = tlo + c;
-                    tile[c * 32 + lane] = (col >= 1 && col <= qlen) ? flags[(size_t)col * 32 + lane] : 0u;
+                    DpRow Rm = rows[base + lane];
+                    const DpJob Jm = jobs[Rm.job];
+                    RowGeom gm;
+                    row_geometry(Rm, Jm, mem, mem0, gm);
+                    const uint32_t* fl = arena + my_off;
+                    const uint8_t* __restrict__ s2 = gm.s2;
+                    const uint8_t* __restrict__ q = gm.q;
+                    const int qlen = gm.qlen, mlen = gm.mlen, origin = gm.origin;
+                    int i = my_bi, j = my_bj, n = 0, ed = 0;
+                    if (i <= 0) { atomicAdd(n_bad, 1u); Rm.pass = 0; }   // the reference would abort on its empty-cigar assert
+                    else
+                    {
+                        // one word ahead: the next step is usually one column to the left in the same word
+                        int r = j - (origin + i);
+                        uint32_t word = fl[(size_t)i * 32 + r / DP_CPL];
+                        int wcol = i, widx = r / DP_CPL;
+                        #pragma unroll 1
+                        while (i > 0 && j > 0)
+                        {
+                            r = j - (origin + i);
+                            const int wi = r / DP_CPL;
+                            if (wcol != i || widx != wi) { word = fl[(size_t)i * 32 + wi]; wcol = i; widx = wi; }
+                            const uint32_t nextWord = i > 1 ? fl[(size_t)(i - 1) * 32 + wi] : 0u;
+                            const uint32_t f = (word >> (3 * (r - wi * DP_CPL))) & 7u;
+                            const int s2p = (int)s2[j - 1], s2n = j < mlen ? (int)s2[j] : -1;
+                            const int s1p = (int)q[i - 1], s1n = i < qlen ? (int)q[i] : -2;
+                            const bool eqD = f & 1u, eqU = (f & 2u) != 0, eqL = (f & 4u) != 0;
+                            int op;
+                            if (s2p == s2n) op = eqU ? OP_I : (eqL ? OP_D : OP_M);        // s2 homopolymer: prefer consuming s2 (:620-640)
+                            else if (s1p == s1n) op = eqL ? OP_D : (eqU ? OP_I : OP_M);   // s1 homopolymer: prefer consuming s1 (:642-661)
+                            else op = eqD ? OP_M : (eqL ? OP_D : OP_I);                   // (:663-680)
+                            if (op == OP_M) { if (s1p != s2p) ed++; i--; j--; }
+                            else if (op == OP_I) { ed++; j--; }
+                            else { ed++; i--; }
+                            if (op != OP_I) { word = nextWord; wcol = i; }
+                            gm.ops[n] = (uint8_t)op;
+                            n++;
+                        }
+                        const WalkTask& tk = tasks[Jm.task];
+                        // identity = 0.65 (+0.05 above 50, +0.05 above 100), min_overlap = path.length()/10
+                        // (PacBioSelfCorrectionProcess.cpp:225-235)
+                        const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
+                        double identity = 0.65;
+                        identity = __dadd_rn(identity, fsum > 50 ? 0.05 : 0.0);
+                        identity = __dadd_rn(identity, fsum > 100 ? 0.05 : 0.0);
+                        const double pct = __ddiv_rn(__dmul_rn((double)(n - ed), 100.0), (double)n);   // getPercentIdentity (overlapper.cpp:71-74)
+                        const bool passOverlap = (uint64_t)n >= (uint64_t)(qlen / 10);
+                        const bool passIdentity = __ddiv_rn(pct, 100.0) >= identity;
+                        Rm.nops = (uint32_t)n; Rm.start0 = i; Rm.start1 = j;
+                        Rm.pass = (passOverlap && passIdentity) ? 1u : 0u;
+                    }
+                    rows[base + lane] = Rm;
+                    my_todo = false;
                 }
                 __syncwarp();
+                g0 = kk; used = 0;
             }
-            const int r = j - (origin + i);
-            const uint32_t f = (tile[(i - tlo) * 32 + r / DP_CPL] >> (3 * (r % DP_CPL))) & 7u;
-            const int s2p = (int)s2[j - 1], s2n = j < mlen ? (int)s2[j] : -1;
-            const int s1p = (int)q[i - 1], s1n = i < qlen ? (int)q[i] : -2;
-            const bool eqD = f & 1u, eqU = (f & 2u) != 0, eqL = (f & 4u) != 0;
-            int op;
-            if (s2p == s2n) op = eqU ? OP_I : (eqL ? OP_D : OP_M);        // s2 homopolymer: prefer consuming s2 (:620-640)
-            else if (s1p == s1n) op = eqL ? OP_D : (eqU ? OP_I : OP_M);   // s1 homopolymer: prefer consuming s1 (:642-661)
-            else op = eqD ? OP_M : (eqL ? OP_D : OP_I);                   // (:663-680)
-            if (op == OP_M) { if (s1p != s2p) ed++; i--; j--; }
-            else if (op == OP_I) { ed++; j--; }
-            else { ed++; i--; }
-            if (lane == 0) ops[n] = (uint8_t)op;
-            n++;
-        }
-        if (lane == 0)
-        {
-            const WalkTask& tk = tasks[J.task];
-            // identity = 0.65 (+0.05 above 50, +0.05 above 100), min_overlap = path.length()/10 (PacBioSelfCorrectionProcess.cpp:225-235)
-            const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
-            double identity = 0.65;
-            identity = __dadd_rn(identity, fsum > 50 ? 0.05 : 0.0);
-            identity = __dadd_rn(identity, fsum > 100 ? 0.05 : 0.0);
-            const double pct = __ddiv_rn(__dmul_rn((double)(n - ed), 100.0), (double)n);   // getPercentIdentity (overlapper.cpp:71-74)
-            const bool passOverlap = (uint64_t)n >= (uint64_t)(qlen / 10);
-            const bool passIdentity = __ddiv_rn(pct, 100.0) >= identity;
-            R.nops = (uint32_t)n; R.start0 = i; R.start1 = j;
-            R.pass = (passOverlap && passIdentity) ? 1u : 0u;
-            rows[it] = R;
+            if (fill)
+            {
+                int bi, bj;
+                dp_fill_row(g, arena + used, bi, bj);
+                if (lane == kk) { my_off = used; my_bi = bi; my_bj = bj; my_todo = true; }
+                used += need;
+            }
         }
     }
 }
@@ -646,9 +702,11 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     if (per_sm < 1) per_sm = 1;
     if (const char* e = getenv("PBSC_DP_BLOCKS_PER_SM")) { if (atoi(e) > 0) per_sm = std::min(per_sm, atoi(e)); }
     const int ablocks = idx->sm_count * per_sm;
-    const uint64_t slab_words = ((uint64_t)q_cap + 2) * 32;
+    // per-warp arena of traceback bits: 32 rows of a typical query, and at least one row of the longest
+    uint64_t arena_words = std::max<uint64_t>(((uint64_t)q_cap + 2) * 32, 1ull << 18);
+    if (const char* e = getenv("PBSC_DP_ARENA_KB")) { if (atoll(e) > 0) arena_words = std::max<uint64_t>(((uint64_t)q_cap + 2) * 32, (uint64_t)atoll(e) * 256); }
     uint32_t* slabs;
-    PBSC_CUDA(arena(idx, "dp.flags", slab_words * (uint64_t)ablocks * DP_WARPS, &slabs));
+    PBSC_CUDA(arena(idx, "dp.flags", arena_words * (uint64_t)ablocks * DP_WARPS, &slabs));
     uint64_t max_rows = 0;
     for (uint64_t j0 = 0; j0 < nj;)
     {
@@ -667,8 +725,8 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         dp_rows_kernel<<<(unsigned)((njc + 127) / 128), 128, 0, st>>>(j0, j1, jobs, tasks, b.codes.p, b.offsets.p, mem, h_mem[j0], rows, h_row[j0]);
         dp_retrieve_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(idx->dev, nrows, rows, jobs, mem, h_mem[j0]);
         PBSC_CUDA(cudaMemsetAsync(qctr, 0, 8, st));
-        const int nb = (int)std::min<uint64_t>((uint64_t)ablocks, (nrows + DP_WARPS - 1) / DP_WARPS);
-        dp_align_kernel<<<nb, DP_WARPS * 32, 0, st>>>(nrows, rows, jobs, tasks, mem, h_mem[j0], slabs, slab_words, qctr, cnt + 1);
+        const int nb = (int)std::min<uint64_t>((uint64_t)ablocks, (nrows + DP_WARPS * 32 - 1) / (DP_WARPS * 32));
+        dp_align_kernel<<<nb, DP_WARPS * 32, 0, st>>>(nrows, rows, jobs, tasks, mem, h_mem[j0], slabs, arena_words, qctr, cnt + 1);
         dp_msa_kernel<<<(unsigned)((njc + 63) / 64), 64, 0, st>>>(j0, j1, jobs, tasks, rows, h_row[j0], mem, h_mem[j0], outpool, cnt + 1);
         PBSC_CUDA(cudaGetLastError());
         if (launches) *launches += 4;

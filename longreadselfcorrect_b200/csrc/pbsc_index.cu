@@ -5,6 +5,8 @@
 #include <sys/stat.h>
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <mutex>
+#include <map>
 #include <fstream>
 #include <sstream>
 #include "pbsc_internal.h"
@@ -26,6 +28,85 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
     set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
     return PBSC_ERR_CUDA;
 }
+// ---- per-device cache of device blocks (see DevBuf) ----
+namespace {
+struct DevCache
+{
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks[16];      // per device: size -> block
+    std::map<void*, std::pair<int, size_t>> live;      // block -> (device, size)
+};
+DevCache& dev_cache() { static DevCache c; return c; }
+size_t cache_round(size_t bytes)
+{
+    // sizes are rounded up to 1/8 of their power of two (at least 1 MB granularity above 8 MB) so that batches of similar
+    // size reuse each other's blocks
+    if (bytes < 4096) return 4096;
+    size_t p2 = 1; while (p2 * 2 <= bytes) p2 *= 2;
+    const size_t step = p2 / 8;
+    return (bytes + step - 1) / step * step;
+}
+}  // namespace
+
+cudaError_t dev_cache_alloc(void** p, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = cache_round(bytes);
+    DevCache& c = dev_cache();
+    {
+        std::lock_guard<std::mutex> g(c.mu);
+        auto& fb = c.free_blocks[dev & 15];
+        auto it = fb.lower_bound(want);
+        if (it != fb.end() && it->first <= want + want / 4)
+        {
+            *p = it->second;
+            c.live[*p] = std::make_pair(dev, it->first);
+            fb.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess)
+    {
+        // give the cache back and retry once
+        cudaGetLastError();
+        dev_cache_trim(dev);
+        e = cudaMalloc(p, want);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> g(c.mu);
+    c.live[*p] = std::make_pair(dev, want);
+    return cudaSuccess;
+}
+
+void dev_cache_free(void* p)
+{
+    if (!p) return;
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) { cudaFree(p); return; }
+    c.free_blocks[it->second.first & 15].insert(std::make_pair(it->second.second, p));
+    c.live.erase(it);
+}
+
+void dev_cache_trim(int device)
+{
+    DevCache& c = dev_cache();
+    std::vector<void*> blocks;
+    {
+        std::lock_guard<std::mutex> g(c.mu);
+        for (auto& kv : c.free_blocks[device & 15]) blocks.push_back(kv.second);
+        c.free_blocks[device & 15].clear();
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    for (void* b : blocks) cudaFree(b);
+    cudaSetDevice(cur);
+}
+
 Timing& last_timing()
 {
     static thread_local Timing t;
@@ -504,8 +585,20 @@ void pbsc_index_destroy(pbsc_index* idx)
     if (idx->d_idmer_valid) cudaFree(idx->d_idmer_valid);
     for (auto& kv : idx->arena) if (kv.second.p) cudaFree(kv.second.p);
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    dev_cache_trim(idx->device);
     delete idx;
 }
+
+/* pinned host memory for the callers' read and result buffers: copies from/to it run at PCIe speed and asynchronously */
+int pbsc_host_alloc(void** p, size_t bytes)
+{
+    if (!p) { set_error("pbsc_host_alloc: null argument"); return PBSC_ERR_ARG; }
+    *p = nullptr;
+    PBSC_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+    return PBSC_OK;
+}
+void pbsc_host_free(void* p) { if (p) cudaFreeHost(p); }
+void pbsc_trim(int device) { dev_cache_trim(device); }
 
 uint64_t pbsc_index_num_symbols(const pbsc_index* idx, int which) { return idx && (which == 0 || which == 1) ? idx->n_symbols[which] : 0; }
 uint64_t pbsc_index_num_strings(const pbsc_index* idx, int which) { return idx && (which == 0 || which == 1) ? idx->n_strings[which] : 0; }

@@ -42,21 +42,28 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_e != cudaSuccess) return pbsc::cuda_fail(_e, #call, __FILE__, __LINE__); \
     } while (0)
 
-// RAII device buffer (freed on scope exit); keeps the C ABI functions leak-free on error paths
+// Device blocks of per-batch buffers are kept in a per-device cache instead of going back to the driver: cudaMalloc/cudaFree
+// of gigabytes per batch cost ~0.2 s per call of the end-to-end entry point (host trace, tools/e2e_trace.py).  pbsc_trim()
+// (and the destruction of the last index on a device) returns the cache to the driver.
+cudaError_t dev_cache_alloc(void** p, size_t bytes);
+void dev_cache_free(void* p);
+void dev_cache_trim(int device);
+
+// RAII device buffer (released on scope exit); keeps the C ABI functions leak-free on error paths
 template <class T>
 struct DevBuf
 {
     T* p = nullptr;
     size_t n = 0;
     DevBuf() {}
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) dev_cache_free(p); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     cudaError_t alloc(size_t count)
     {
-        if (p) { cudaFree(p); p = nullptr; }
+        if (p) { dev_cache_free(p); p = nullptr; }
         n = count;
-        return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+        return dev_cache_alloc((void**)&p, (count ? count : 1) * sizeof(T));
     }
 };
 

@@ -3,6 +3,8 @@
 // stream-ordered pipeline: upload (H2D + workspace) -> run (seed kernels, extend-chain kernel) -> fetch (D2H).
 // pbsc_correct_batch is the three stages back to back on host buffers.
 #include <string.h>
+#include <stdlib.h>
+#include <chrono>
 #include "pbsc_batch.cuh"
 #include "pbsc_dp.cuh"
 
@@ -234,9 +236,15 @@ int pbsc_correct_batch(pbsc_index* idx, const pbsc_params* p, const char* reads,
 {
     if (!idx || !p || !reads || !offsets || !piece_offsets || !first_piece || !stats) { set_error("pbsc_correct_batch: null argument"); return PBSC_ERR_ARG; }
     pbsc_batch* bt = nullptr;
+    const bool trace = getenv("PBSC_TRACE") != nullptr;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     int rc = pbsc_batch_upload(idx, p, reads, offsets, n_reads, &bt);
     if (rc != PBSC_OK) return rc;
+    const auto t1 = now();
     rc = pbsc_batch_run(bt, nullptr);
+    const auto t2 = now();
     if (rc == PBSC_OK)
     {
         uint64_t nb = 0, np = 0;
@@ -244,7 +252,9 @@ int pbsc_correct_batch(pbsc_index* idx, const pbsc_params* p, const char* reads,
         if (bytes_needed) *bytes_needed = nb;
         if (rc == PBSC_OK) rc = pbsc_batch_fetch(bt, pieces_out, pieces_cap, piece_offsets, piece_offsets_cap, first_piece, stats);
     }
+    const auto t3 = now();
     pbsc_batch_destroy(bt);
+    if (trace) fprintf(stderr, "[pbsc] correct_batch host wall: upload %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
     return rc;
 }
 

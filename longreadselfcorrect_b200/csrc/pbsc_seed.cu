@@ -13,12 +13,38 @@
 
 namespace pbsc {
 
-__global__ void ascii_to_codes_kernel(const char* __restrict__ in, uint8_t* __restrict__ out, uint64_t n)
+// 16 bases per thread; *bad is raised when anything but A/C/G/T shows up (SeqReader.cpp:118-125 exits on such reads)
+__global__ void ascii_to_codes_kernel(const char* __restrict__ in, uint8_t* __restrict__ out, uint64_t n, unsigned int* bad)
 {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    char b = in[i];
-    out[i] = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3;
+    const uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    unsigned char c[16];
+    bool wrong = false;
+    if (i0 + 16 <= n && ((uintptr_t)(in + i0) & 15) == 0)
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
+        memcpy(c, &v, 16);
+        #pragma unroll
+        for (int x = 0; x < 16; x++)
+        {
+            const unsigned char b = c[x];
+            wrong |= !(b == 'A' || b == 'C' || b == 'G' || b == 'T');
+            c[x] = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3;
+        }
+        uint4 o;
+        memcpy(&o, c, 16);
+        *reinterpret_cast<uint4*>(out + i0) = o;
+    }
+    else
+    {
+        for (uint64_t i = i0; i < n && i < i0 + 16; i++)
+        {
+            const unsigned char b = (unsigned char)in[i];
+            wrong |= !(b == 'A' || b == 'C' || b == 'G' || b == 'T');
+            out[i] = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3;
+        }
+    }
+    if (wrong) atomicOr(bad, 1u);
 }
 
 __device__ __forceinline__ uint64_t find_read(const uint64_t* __restrict__ offsets, uint64_t n_reads, uint64_t g)
@@ -419,8 +445,6 @@ int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, ui
 {
     const uint64_t n_bases = offsets[n_reads];
     for (uint64_t i = 0; i < n_reads; i++) if (offsets[i + 1] < offsets[i]) { set_error("read offsets must be non-decreasing"); return PBSC_ERR_ARG; }
-    for (uint64_t i = 0; i < n_bases; i++)
-        if (base_code(reads[i]) < 0) { set_error("Error: read contains non-ACGT characters."); return PBSC_ERR_ARG; }   // SeqReader.cpp:118-125
     b.n_reads = n_reads;
     b.n_bases = n_bases;
     DevBuf<char> ascii;
@@ -429,10 +453,16 @@ int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, ui
     PBSC_CUDA(b.offsets.alloc(n_reads + 1));
     PBSC_CUDA(cudaMemcpyAsync(ascii.p, reads, n_bases, cudaMemcpyHostToDevice, idx->stream));
     PBSC_CUDA(cudaMemcpyAsync(b.offsets.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, idx->stream));
-    PBSC_CUDA(cudaMemsetAsync(b.codes.p, 0, n_bases + 64, idx->stream));
-    if (n_bases) ascii_to_codes_kernel<<<(unsigned)((n_bases + 255) / 256), 256, 0, idx->stream>>>(ascii.p, b.codes.p, n_bases);
+    PBSC_CUDA(cudaMemsetAsync(b.codes.p + n_bases, 0, 64, idx->stream));
+    DevBuf<unsigned int> bad;
+    PBSC_CUDA(bad.alloc(1));
+    PBSC_CUDA(cudaMemsetAsync(bad.p, 0, 4, idx->stream));
+    if (n_bases) ascii_to_codes_kernel<<<(unsigned)((n_bases / 16 + 256) / 256), 256, 0, idx->stream>>>(ascii.p, b.codes.p, n_bases, bad.p);
     PBSC_CUDA(cudaGetLastError());
+    unsigned int hbad = 0;
+    PBSC_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, idx->stream));
     PBSC_CUDA(cudaStreamSynchronize(idx->stream));
+    if (hbad) { set_error("Error: read contains non-ACGT characters."); return PBSC_ERR_ARG; }   // SeqReader.cpp:118-125
     return PBSC_OK;
 }
 

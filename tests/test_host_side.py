@@ -89,8 +89,9 @@ def test_cli_option_errors():
     assert "Usage: StriDe PacBioSelfCorrection" in r.stderr
     r = subprocess.run([exe, "-p", "x", "-o", "/tmp/pbsc_cli_test"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "missing arguments" in r.stderr
+    # default options (DP fallback on) are accepted; without a GPU or an index the run fails loudly, never on a CPU path
     r = subprocess.run([exe, "-p", "x", "-o", "/tmp/pbsc_cli_test", "reads.fa"], stderr=subprocess.PIPE, text=True)
-    assert r.returncode == 1 and "--nodp" in r.stderr
+    assert r.returncode == 1 and ("no CUDA device" in r.stderr or "x.bwt" in r.stderr) and "--nodp" not in r.stderr
 
 
 def test_balanced_ranges():
