@@ -127,6 +127,46 @@ __global__ void idmer_valid_kernel(FmIndexDev idx, int s9, uint64_t n_keys, uint
     valid[key] = (uint8_t)((f.valid() ? 1 : 0) | (r.valid() ? 2 : 0));
 }
 
+// Second-guessing the speculation.  A pair whose walk failed and whose DP fallback produced a consensus hands its successor a
+// source that ends with that consensus instead of the raw target seed; waiting for stitch_kernel to discover this costs one
+// round per such pair along a read (14 rounds on config 2).  After every round of walks this kernel looks, for ALL pairs at
+// once, at what each pair's current result would hand to its successor and, where that differs from what the successor was
+// walked with, files an alternative task for the successor.  Alternatives are only ever hints: stitch_kernel still checks the
+// exact inputs before it consumes any task.
+__global__ void make_alt_tasks_kernel(uint64_t n_reads, const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region,
+                                      const uint32_t* __restrict__ seed_count, const uint64_t* __restrict__ task_base, const WalkTask* __restrict__ spec,
+                                      WalkTask* alt, const uint8_t* __restrict__ outpool, uint64_t alt_pool_base, int start_kmer, uint32_t* alt_list,
+                                      unsigned int* n_alt)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const pbsc_seed* sv = seeds + region[r];
+    const uint32_t ns = seed_count[r];
+    const uint64_t b = task_base[r];
+    for (uint32_t t = 1; t + 1 < ns; t++)
+    {
+        const WalkTask* e = (alt[b + t].valid && alt[b + t].status != PBSC_TASK_PENDING) ? &alt[b + t] : &spec[b + t];
+        if (!e->valid || e->status == PBSC_TASK_PENDING) continue;
+        if (!(e->status < 0 && e->dp_status == PBSC_DP_OK)) continue;   // FM success or raw fallback: the piece ends with the raw seed
+        const WalkTask& sp = spec[b + t + 1];
+        if (!sp.valid) continue;
+        int k2; bool rtou2;
+        pair_inputs(sv[t].end_best_k, sv[t].is_repeat, (int64_t)1 << 40, sv[t + 1], start_kmer, k2, rtou2);
+        if (k2 != sp.k || (rtou2 ? 1 : 0) != sp.rtou) continue;
+        if ((int64_t)e->out_len - e->k < k2) continue;
+        uint64_t hi, lo;
+        pack_src(outpool + e->out_off + e->out_len - k2, k2, hi, lo);
+        if (hi == sp.src_hi && lo == sp.src_lo) continue;
+        WalkTask& al = alt[b + t + 1];
+        if (al.valid && al.src_hi == hi && al.src_lo == lo) continue;
+        WalkTask nt = sp;
+        nt.src_hi = hi; nt.src_lo = lo; nt.status = PBSC_TASK_PENDING; nt.dp_status = PBSC_DP_NONE; nt.out_len = 0;
+        nt.out_off = sp.out_off + alt_pool_base;
+        al = nt;
+        alt_list[atomicAdd(n_alt, 1u)] = (uint32_t)(b + t + 1);
+    }
+}
+
 // query of a task: beginningkmer + strBetweenSrcTarget + targetSeed, or its reverse complement when the walk runs from the
 // target towards the source (isFromRtoU, PacBioSelfCorrectionProcess.cpp:176-184)
 __device__ __forceinline__ void task_shape(const WalkTask& tk, int& interval, uint32_t& trgLen, uint32_t& qlen)
@@ -374,7 +414,7 @@ struct StitchParams { int32_t start_kmer, next_target, split, no_dp; };
 __global__ void __launch_bounds__(128)
 stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets,
               const pbsc_seed* __restrict__ seeds, const uint64_t* __restrict__ region, const uint32_t* __restrict__ seed_count,
-              const uint64_t* __restrict__ task_base, WalkTask* spec, WalkTask* pending, const uint8_t* __restrict__ outpool,
+              const uint64_t* __restrict__ task_base, WalkTask* spec, const WalkTask* alt, WalkTask* pending, const uint8_t* __restrict__ outpool,
               uint64_t pending_pool_off, uint32_t pending_cap, ReadState* states, uint8_t* __restrict__ pieces,
               const uint64_t* __restrict__ piece_region, uint32_t* __restrict__ piece_bounds, const uint64_t* __restrict__ bounds_region,
               pbsc_read_stats* __restrict__ stats, int32_t* __restrict__ read_status, uint32_t* stalled_list, unsigned int* n_stalled)
@@ -437,6 +477,11 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 {
                     const WalkTask* sp = spec + task_base[r] + ti;
                     if (sp->valid && sp->k == k && sp->rtou == (rtou ? 1 : 0) && sp->src_hi == hi && sp->src_lo == lo && sp->status != PBSC_TASK_PENDING) use = sp;
+                    if (!use && alt)
+                    {
+                        const WalkTask* al = alt + task_base[r] + ti;
+                        if (al->valid && al->k == k && al->rtou == (rtou ? 1 : 0) && al->src_hi == hi && al->src_lo == lo && al->status != PBSC_TASK_PENDING) use = al;
+                    }
                 }
                 if (!use)
                 {
@@ -583,7 +628,10 @@ struct ArenaPtr
 };
 struct ThreadEngine
 {
-    ArenaPtr<WalkTask> spec, pending;
+    ArenaPtr<WalkTask> spec, pending, alt;
+    ArenaPtr<uint32_t> alt_list;
+    ArenaPtr<unsigned int> n_alt;
+    uint64_t alt_pool_base = 0, alt_rec_base = 0;
     ArenaPtr<uint64_t> task_base, caps, cap_off, rec_caps, rec_off;
     ArenaPtr<uint8_t> outpool, recpool, scratch, wscratch, hscratch;
     ArenaPtr<uint32_t> heavy_list, nodepool;
@@ -615,12 +663,13 @@ struct ThreadEngine
 // Light pass, then the walks that outgrew it among walks of their own weight, then materialisation.  `is_pending` selects
 // where the setup records live (a read's pending request has a fixed-size slot).
 static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, Workspace& w, DeviceBatch& b, uint64_t n_items, const uint32_t* list,
-                       WalkTask* tasks, bool is_pending, uint64_t minSA, uint64_t* launches)
+                       WalkTask* tasks, bool is_pending, uint64_t minSA, uint64_t* launches, uint8_t* recpool = nullptr)
 {
     cudaStream_t st = idx->stream;
+    if (!recpool) recpool = E.recpool.p;
     const uint64_t pcap = is_pending ? E.pend_rec_cap : 0;
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
-    setup_tasks_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, P, n_items, list, tasks, b.codes.p, b.offsets.p, E.recpool.p, E.rec_off.p,
+    setup_tasks_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, P, n_items, list, tasks, b.codes.p, b.offsets.p, recpool, E.rec_off.p,
                                                                          E.pend_rec_base, pcap);
     const uint64_t threads = (uint64_t)E.blocks * TW_BLOCK;
     int nb = E.blocks;
@@ -628,8 +677,22 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     if (nb < 1) nb = 1;
     PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 8, st));
     PBSC_CUDA(cudaMemsetAsync(E.pool_used.p, 0, 8, st));
+    // A small round (re-walks of mispredicted pairs) lasts as long as its longest walk, whatever the pass: one pass at full
+    // capacities instead of a light and a heavy one halves that.
+    const bool single_pass = !E.heavy_engine_warp && n_items * 2 <= (uint64_t)E.hblocks * TW_BLOCK;
+    if (single_pass)
+    {
+        const int hb = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)E.hblocks, (n_items + TW_BLOCK - 1) / TW_BLOCK));
+        E.mark(st);
+        E.kernel<<<hb, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, n_items, list, tasks, recpool, E.rec_off.p,
+                                          E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
+                                          E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, nullptr, 1);
+        E.mark(st);
+    }
+    else
+    {
     E.mark(st);
-    E.kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, E.recpool.p, E.rec_off.p,
+    E.kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, recpool, E.rec_off.p,
                                                 E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
                                                 E.nodepool.p, E.pool_used.p, E.pool_cap, E.light, nullptr, 0);
     E.mark(st);
@@ -643,12 +706,13 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     else
     {
         E.mark(st);
-        E.kernel<<<E.hblocks, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, E.recpool.p, E.rec_off.p,
+        E.kernel<<<E.hblocks, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, recpool, E.rec_off.p,
                                                            E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p + E.heavy_cap,
                                                            E.n_heavy.p + 1, E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, E.n_heavy.p, 1);
         E.mark(st);
     }
-    materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, E.recpool.p, E.rec_off.p, E.pend_rec_base, pcap,
+    }
+    materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, recpool, E.rec_off.p, E.pend_rec_base, pcap,
                                                                          E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
     PBSC_CUDA(cudaGetLastError());
     if (launches) *launches += 4;
@@ -785,14 +849,40 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         rec_spec = tail[2] + tail[3];
         nl += 6;
     }
-    const uint64_t pending_pool_off = align_up(pool_spec, 16);
+    // pools: [speculative tasks | their alternatives (same layout, DP fallback only) | one pending request per read]
+    int alt_rounds = E.no_dp ? 0 : 4;
+    if (const char* e = getenv("PBSC_ALT_ROUNDS")) alt_rounds = E.no_dp ? 0 : std::max(0, atoi(e));
+    const bool use_alt = alt_rounds > 0 && n_tasks > 0;
+    E.alt_pool_base = align_up(pool_spec, 16);
+    const uint64_t pending_pool_off = use_alt ? 2 * E.alt_pool_base : E.alt_pool_base;
     PBSC_CUDA(E.outpool.get(idx, "tw.outpool", pending_pool_off + n * (uint64_t)pending_cap + 16));
-    E.pend_rec_base = align_up(rec_spec, 128);
+    E.alt_rec_base = align_up(rec_spec, 128);
+    E.pend_rec_base = use_alt ? 2 * E.alt_rec_base : E.alt_rec_base;
     PBSC_CUDA(E.recpool.get(idx, "tw.recpool", E.pend_rec_base + n * E.pend_rec_cap + 128));
+    if (use_alt)
+    {
+        PBSC_CUDA(E.alt.get(idx, "tw.alt", n_tasks)); PBSC_CUDA(E.alt_list.get(idx, "tw.alt_list", n_tasks)); PBSC_CUDA(E.n_alt.get(idx, "tw.n_alt", 1));
+        PBSC_CUDA(cudaMemsetAsync(E.alt.p, 0, n_tasks * sizeof(WalkTask), st));
+    }
+    else E.alt.p = nullptr;
     // ---- round 1: all speculative walks ----
     if (n_tasks)
     {
         rc = launch_walk(idx, P, E, w, b, n_tasks, nullptr, E.spec.p, false, minSA, &nl);
+        if (rc != PBSC_OK) return rc;
+    }
+    // ---- alternatives for the successors of pairs the DP fallback corrected (see make_alt_tasks_kernel) ----
+    for (int ar = 0; use_alt && ar < alt_rounds; ar++)
+    {
+        PBSC_CUDA(cudaMemsetAsync(E.n_alt.p, 0, 4, st));
+        make_alt_tasks_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, s.seeds.p, s.region.p, s.count.p, E.task_base.p, E.spec.p, E.alt.p, E.outpool.p,
+                                                                           E.alt_pool_base, p->start_kmer, E.alt_list.p, E.n_alt.p);
+        unsigned int na = 0;
+        PBSC_CUDA(cudaMemcpyAsync(&na, E.n_alt.p, 4, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaStreamSynchronize(st));
+        nl++;
+        if (na == 0) break;
+        rc = launch_walk(idx, P, E, w, b, na, E.alt_list.p, E.alt.p, false, minSA, &nl, E.recpool.p + E.alt_rec_base);
         if (rc != PBSC_OK) return rc;
     }
     StitchParams C;
@@ -801,7 +891,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     {
         PBSC_CUDA(cudaMemsetAsync(E.n_stalled.p, 0, 4, st));
         stitch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(C, n, b.codes.p, b.offsets.p, s.seeds.p, s.region.p, s.count.p, E.task_base.p, E.spec.p,
-                                                                   E.pending.p, E.outpool.p, pending_pool_off, pending_cap, E.states.p, w.pieces.p,
+                                                                   E.alt.p, E.pending.p, E.outpool.p, pending_pool_off, pending_cap, E.states.p, w.pieces.p,
                                                                    w.piece_region.p, w.bounds.p, w.bounds_region.p, w.stats.p, w.status.p, E.stalled.p,
                                                                    E.n_stalled.p);
         nl++;
