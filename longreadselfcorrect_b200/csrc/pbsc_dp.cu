@@ -120,8 +120,10 @@ dp_collect_kernel(const __grid_constant__ FmIndexDev idx, uint64_t n_items, cons
     const uint64_t ti = list ? list[it] : it;
     WalkTask& tk = tasks[ti];
     if (!tk.valid) return;
+    if (tk.dp_wanted != 1) return;   // 0: not asked for, 2: already collected by an earlier DP stage of this round
     tk.dp_status = PBSC_DP_NONE;
-    if (!tk.dp_wanted || !(tk.status == -1 || tk.status == -2 || tk.status == -3)) return;
+    if (!(tk.status == -1 || tk.status == -2 || tk.status == -3)) return;
+    tk.dp_wanted = 2;
     const uint8_t* read = codes + offsets[tk.read];
     const uint32_t k = (uint32_t)tk.k;
     const uint32_t qlen = k + (uint32_t)(tk.trg_start - tk.src_end - 1) + (uint32_t)tk.trg_len;

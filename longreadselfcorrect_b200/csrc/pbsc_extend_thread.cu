@@ -161,6 +161,7 @@ __global__ void make_alt_tasks_kernel(uint64_t n_reads, const pbsc_seed* __restr
         if (al.valid && al.src_hi == hi && al.src_lo == lo) continue;
         WalkTask nt = sp;
         nt.src_hi = hi; nt.src_lo = lo; nt.status = PBSC_TASK_PENDING; nt.dp_status = PBSC_DP_NONE; nt.out_len = 0;
+        nt.dp_wanted = sp.dp_wanted ? 1 : 0;   // (2 marks a task the DP stage has already collected)
         nt.out_off = sp.out_off + alt_pool_base;
         al = nt;
         alt_list[atomicAdd(n_alt, 1u)] = (uint32_t)(b + t + 1);
@@ -679,6 +680,7 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     PBSC_CUDA(cudaMemsetAsync(E.pool_used.p, 0, 8, st));
     // A small round (re-walks of mispredicted pairs) lasts as long as its longest walk, whatever the pass: one pass at full
     // capacities instead of a light and a heavy one halves that.
+    bool dp_done = false;
     const bool single_pass = !E.heavy_engine_warp && n_items * 2 <= (uint64_t)E.hblocks * TW_BLOCK;
     if (single_pass)
     {
@@ -705,18 +707,49 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     }
     else
     {
-        E.mark(st);
-        E.kernel<<<E.hblocks, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, recpool, E.rec_off.p,
+        // The heavy pass is a few long, latency-bound walks; the DP fallback of the light pass's failures is issue-bound and
+        // touches disjoint tasks, so the two can overlap on a side stream (PBSC_OVERLAP=1).  Measured on config 2: no gain
+        // (1920 ms either way: both kernels slow down by what the other takes), so it is off by default.
+        const bool overlap = !E.no_dp && getenv("PBSC_OVERLAP") && atoi(getenv("PBSC_OVERLAP")) > 0;
+        if (overlap)
+        {
+            if (!idx->stream2) PBSC_CUDA(cudaStreamCreateWithFlags(&idx->stream2, cudaStreamNonBlocking));
+            if (!idx->ev_a) PBSC_CUDA(cudaEventCreateWithFlags(&idx->ev_a, cudaEventDisableTiming));
+            if (!idx->ev_b) PBSC_CUDA(cudaEventCreateWithFlags(&idx->ev_b, cudaEventDisableTiming));
+        }
+        cudaStream_t s2 = overlap ? idx->stream2 : st;
+        if (s2 != st) { PBSC_CUDA(cudaEventRecord(idx->ev_a, st)); PBSC_CUDA(cudaStreamWaitEvent(s2, idx->ev_a, 0)); }
+        E.mark(s2);
+        E.kernel<<<E.hblocks, TW_BLOCK, 0, s2>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, recpool, E.rec_off.p,
                                                            E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p + E.heavy_cap,
                                                            E.n_heavy.p + 1, E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, E.n_heavy.p, 1);
-        E.mark(st);
+        E.mark(s2);
+        PBSC_CUDA(cudaGetLastError());
+        if (s2 != st)
+        {
+            PBSC_CUDA(cudaEventRecord(idx->ev_b, s2));
+            // DP fallback of everything the light pass settled (tasks still in the heavy pass are skipped: their status is not final)
+            const int rc = run_dp_fallback(idx, E.params, b, tasks, n_items, list, E.outpool.p, w.q_cap, launches);
+            if (rc != PBSC_OK) { cudaStreamSynchronize(s2); return rc; }
+            PBSC_CUDA(cudaStreamWaitEvent(st, idx->ev_b, 0));
+            // ... and of the heavy pass's own failures
+            unsigned int nh = 0;
+            PBSC_CUDA(cudaMemcpyAsync(&nh, E.n_heavy.p, 4, cudaMemcpyDeviceToHost, st));
+            PBSC_CUDA(cudaStreamSynchronize(st));
+            if (nh)
+            {
+                const int rc2 = run_dp_fallback(idx, E.params, b, tasks, nh, E.heavy_list.p, E.outpool.p, w.q_cap, launches);
+                if (rc2 != PBSC_OK) return rc2;
+            }
+            dp_done = true;
+        }
     }
     }
     materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, recpool, E.rec_off.p, E.pend_rec_base, pcap,
                                                                          E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
     PBSC_CUDA(cudaGetLastError());
     if (launches) *launches += 4;
-    if (!E.no_dp)
+    if (!E.no_dp && !dp_done)
     {
         const int rc = run_dp_fallback(idx, E.params, b, tasks, n_items, list, E.outpool.p, w.q_cap, launches);
         if (rc != PBSC_OK) return rc;

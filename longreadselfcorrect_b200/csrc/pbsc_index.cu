@@ -585,6 +585,9 @@ void pbsc_index_destroy(pbsc_index* idx)
     if (idx->d_idmer_valid) cudaFree(idx->d_idmer_valid);
     for (auto& kv : idx->arena) if (kv.second.p) cudaFree(kv.second.p);
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    if (idx->stream2) cudaStreamDestroy(idx->stream2);
+    if (idx->ev_a) cudaEventDestroy(idx->ev_a);
+    if (idx->ev_b) cudaEventDestroy(idx->ev_b);
     dev_cache_trim(idx->device);
     delete idx;
 }

@@ -24,6 +24,8 @@ struct pbsc_index
     uint64_t n_symbols[2] = {0, 0}, n_strings[2] = {0, 0}, n_blocks[2] = {0, 0};
     size_t device_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // side stream: the heavy walk pass runs here while the DP fallback of the light pass runs on `stream`
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int sm_count = 0;   // cached: cudaGetDeviceProperties costs tens of milliseconds
     // named scratch buffers that survive across batches (grow-only), so that the hot path does not pay
     // cudaMalloc/cudaFree of gigabytes per batch; one batch runs at a time per index
