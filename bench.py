@@ -287,6 +287,7 @@ def main():
     # ---- CPU baseline (reference binary on a bounded sample) + algorithmic rank-query counts (oracle) ----
     cpu = None
     alg = None
+    parity = None
     if not args.no_cpu_baseline and os.path.exists(REF_STRIDE):
         sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.04 * cores * 15))
         sample_reads = max(1, min(int(np.searchsorted(off, sample_mbp * 1e6)), n_reads))
@@ -295,6 +296,30 @@ def main():
             prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=runs)
             secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"), args.nodp)
             log(f"reference CPU baseline: {sample_mbp:.1f} Mbp in {secs:.2f}s with {cores} threads")
+            # parity at full size: what the reference wrote for the sampled reads against what the timed GPU run produced for them
+            try:
+                want = {}
+                for fn in ("correct.fa", "discard.fa"):
+                    name = None
+                    for line in open(os.path.join(d, "out", fn)):
+                        if line.startswith(">"):
+                            name = line[1:].strip()
+                        else:
+                            want[(fn, name)] = line.strip()
+                raw = out.tobytes()
+                bad = 0
+                for r in range(sample_reads):
+                    if stats[r]["merge"]:
+                        j = int(first[r])
+                        got = raw[int(poff[j]):int(poff[j + 1])].decode()
+                        bad += want.get(("correct.fa", f"r{r}")) != got
+                    else:
+                        bad += ("discard.fa", f"r{r}") not in want
+                parity = {"reads_compared": int(sample_reads), "records_in_reference_output": len(want), "mismatches": int(bad),
+                          "identical": bool(bad == 0 and len(want) == sample_reads)}
+                log(f"parity against the reference on the sampled reads: {parity}")
+            except Exception as e:
+                parity = {"error": str(e)}
             cpu = {"value": sample_mbp / secs, "unit": "Mbp/s", "cores": cores, "kind": "reference",
                    "sample": f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores}" + (" --nodp" if args.nodp else "")}
             small = max(1, min(int(np.searchsorted(off, min(sample_mbp, 4.0) * 1e6)), n_reads))
@@ -327,6 +352,12 @@ def main():
         traffic = tr.get(args.workload + ("_nodp" if args.nodp else ""), {}).get("walk_levels_kernel")
     except Exception:
         pass
+    try:
+        # what independent random 32-byte sector reads over a buffer as large as the index reach on this GPU
+        sector_peak = api.random_sector_peak(idx.device_bytes(), local_rank)
+    except Exception as e:   # measurement aid only
+        log("random-sector peak not measured:", e)
+        sector_peak = None
     roof = {"bound": "hbm", "kernel": "walk_levels_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "kernel_ms": walk_ms, "kernel_launches_per_step": walk_launches, "extend_phase_ms": ext_ms, "seed_phase_ms": seed_ms,
@@ -337,6 +368,9 @@ def main():
         roof["achieved"] = alg_bytes / (walk_ms / 1000) / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_step"] = alg_bytes
+        if sector_peak:
+            roof["random_sector_peak"] = sector_peak
+            roof["frac_of_random_sector_peak"] = roof["achieved"] / sector_peak
         roof["algorithmic_rank_queries_per_walk"] = per_walk
         roof["algorithmic_rank_queries_per_read_base_seed_phase"] = alg["seed"] / alg["sample_bases"]
         roof["seed_phase_achieved_GBs"] = alg["seed"] / alg["sample_bases"] * codes.size * 32.0 / (seed_ms / 1000) / 1e9
@@ -361,6 +395,7 @@ def main():
         "gpu_launches": int(tm["kernel_launches"]) * args.steps,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "parity_vs_reference": parity,
     }
     print(json.dumps(line))
     if dist is not None:

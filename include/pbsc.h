@@ -105,6 +105,9 @@ int pbsc_host_alloc(void** p, size_t bytes);
 void pbsc_host_free(void* p);
 /* give the library's cache of per-batch device blocks on `device` back to the driver */
 void pbsc_trim(int device);
+/* measured peak (GB/s) of independent random 32-byte sector reads over `bytes` bytes of HBM: the roofline denominator for
+ * kernels whose every rank query is one aligned sector (no reference counterpart; measurement aid) */
+int pbsc_random_sector_bench(int device, uint64_t bytes, float* gbps);
 
 /* ---- parameters: PacBioSelfCorrectionMain, StriDe/PacBioSelfCorrection.cpp:195-231 ---- */
 void pbsc_params_default(pbsc_params* p);

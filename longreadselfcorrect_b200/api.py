@@ -71,7 +71,7 @@ EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc
             "pbsc_index_device_bytes", "pbsc_index_get_symbols", "pbsc_findinterval_batch", "pbsc_findinterval_device",
             "pbsc_seed_batch", "pbsc_extend_batch", "pbsc_correct_batch", "pbsc_last_timing",
             "pbsc_batch_upload", "pbsc_batch_run", "pbsc_batch_result_size", "pbsc_batch_fetch", "pbsc_batch_destroy",
-            "pbsc_host_alloc", "pbsc_host_free", "pbsc_trim"]
+            "pbsc_host_alloc", "pbsc_host_free", "pbsc_trim", "pbsc_random_sector_bench"]
 
 _lib = None
 
@@ -395,6 +395,13 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+def random_sector_peak(nbytes: int, device: int = 0) -> float:
+    """Measured GB/s of independent random 32-byte sector reads over nbytes of HBM (roofline denominator)."""
+    g = C.c_float(0)
+    _check(lib().pbsc_random_sector_bench(C.c_int(device), C.c_uint64(int(nbytes)), C.byref(g)))
+    return float(g.value)
 
 
 def last_timing() -> dict:

@@ -52,7 +52,7 @@ __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; whil
 __host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap, Caps c)
 {
     size_t b = 0;
-    b += sizeof(Leaf) * (size_t)(c.old_cap + c.new_cap);
+    b += sizeof(Leaf) * (size_t)(2 * c.new_cap);   // two banks of the same size: the level loop swaps them instead of copying
     b += sizeof(double) * (size_t)c.rings * RING_LEN;
     b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     b += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
@@ -63,7 +63,7 @@ __host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap, Caps c
 __device__ inline void carve(uint8_t* base, uint32_t node_cap, Caps c, TScratch& w)
 {
     uint8_t* p = base;
-    w.oldL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.old_cap;
+    w.oldL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.new_cap;
     w.newL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.new_cap;
     w.rings = (double*)p; p += sizeof(double) * (size_t)c.rings * RING_LEN;
     w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
@@ -839,14 +839,17 @@ static __device__ __noinline__ void one_level(State& S)
     prune(S, m);
     S.level++;
     if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return; }
+    // the surviving children become the next level's leaves: the banks swap roles (no copy; the walk kernel's DRAM traffic is
+    // mostly this scratch, profiles/r1_walk_levels_cfg2_light_pass.txt), only the leaves behind a pruned one move forward
     uint32_t nn = 0;
     #pragma unroll 1
     for (uint32_t j = 0; j < m; j++)
     {
         if (!S.s.newL[j].alive) continue;
-        if (nn < S.cap.old_cap) leaf_copy(S.s.oldL + nn, S.s.newL + j);
+        if (nn != j && nn < S.cap.old_cap) leaf_copy(S.s.newL + nn, S.s.newL + j);
         nn++;
     }
+    { Leaf* t = S.s.oldL; S.s.oldL = S.s.newL; S.s.newL = t; }
     S.n = nn;
     // more live leaves than this engine carries, and the reference's loop would go on: hand the walk over
     if (nn > S.cap.old_cap && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
