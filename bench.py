@@ -36,6 +36,12 @@ WORKLOADS = {
                  desc="4.6 Mb synthetic genome, 50x simulated CLR reads (mean 8 kb, 13% error), -c 50 -g 5"),
     "cfg1": dict(genome=1_000_000, gseed=1, cov=30, mean=6000, rseed=101, c=30, g=5,
                  desc="1 Mb synthetic genome, 30x simulated CLR reads (mean 6 kb, 13% error), -c 30 -g 5"),
+    # BASELINE.json configs[2] (12 Mb with injected repeats, 100x): 50 repeat families x 20 copies, 20 tandem arrays
+    "cfg3": dict(genome=12_000_000, gseed=3, cov=100, mean=8000, rseed=103, c=100, g=10, repeat_families=50, tandem_arrays=20,
+                 desc="12 Mb synthetic genome with injected repeats, 100x simulated CLR reads (mean 8 kb, 13% error), -c 100 -g 10"),
+    # the same recipe at 1/6 of the size: a repeat-rich parity and capacity check that fits a short GPU slot
+    "cfg3s": dict(genome=2_000_000, gseed=3, cov=100, mean=8000, rseed=103, c=100, g=10, repeat_families=8, tandem_arrays=4,
+                  desc="2 Mb synthetic genome with injected repeats, 100x simulated CLR reads (mean 8 kb, 13% error), -c 100 -g 10"),
     "tiny": dict(genome=100_000, gseed=1, cov=30, mean=3000, rseed=101, c=30, g=5,
                  desc="100 kb synthetic genome, 30x simulated CLR reads (mean 3 kb), -c 30 -g 5"),
 }
@@ -50,7 +56,7 @@ def log(*a):
 def make_data(wl):
     from longreadselfcorrect_b200 import synth
     t = time.time()
-    g = synth.make_genome(wl["genome"], wl["gseed"])
+    g = synth.make_genome(wl["genome"], wl["gseed"], repeat_families=wl.get("repeat_families", 0), tandem_arrays=wl.get("tandem_arrays", 0))
     codes, off = synth.simulate_reads(g, wl["cov"], wl["mean"], wl["rseed"])
     log(f"simulated {off.size - 1} reads, {codes.size / 1e6:.1f} Mbp in {time.time() - t:.1f}s")
     return codes, off

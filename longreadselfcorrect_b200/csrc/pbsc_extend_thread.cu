@@ -83,14 +83,17 @@ __global__ void make_spec_tasks_kernel(uint64_t n_reads, const uint8_t* __restri
         {
             const pbsc_seed s = sv[t - 1], tg = sv[t];
             int k; bool rtou;
-            pair_inputs(s.end_best_k, s.is_repeat, (int64_t)s.len, tg, start_kmer, k, rtou);
+            // source.seedLen is the length of the whole piece corrected so far (SeedFeature::append): only for the first pair is
+            // it the raw seed's; later it is long, and where the walk k-mer reaches back beyond the seed (repeat seeds shorter
+            // than startKmerLen + 2) the raw read is the best guess of the corrected bases in front of it
+            pair_inputs(s.end_best_k, s.is_repeat, t == 1 ? (int64_t)s.len : ((int64_t)1 << 40), tg, start_kmer, k, rtou);
             tk.src_end = s.start + s.len - 1;
             tk.trg_start = tg.start; tk.trg_len = tg.len;
             tk.k = k; tk.rtou = rtou ? 1 : 0;
             tk.status = PBSC_TASK_PENDING;
             tk.freq_sum = s.max_fixed_freq + tg.max_fixed_freq;
             tk.dp_wanted = no_dp ? 0 : 1;
-            if (k > 0 && k <= s.len && k <= 64)
+            if (k > 0 && k <= s.start + s.len && k <= 64)
             {
                 pack_src(read + s.start + s.len - k, k, tk.src_hi, tk.src_lo);
                 tk.valid = 1;
@@ -147,7 +150,10 @@ __global__ void make_alt_tasks_kernel(uint64_t n_reads, const pbsc_seed* __restr
     {
         const WalkTask* e = (alt[b + t].valid && alt[b + t].status != PBSC_TASK_PENDING) ? &alt[b + t] : &spec[b + t];
         if (!e->valid || e->status == PBSC_TASK_PENDING) continue;
-        if (!(e->status < 0 && e->dp_status == PBSC_DP_OK)) continue;   // FM success or raw fallback: the piece ends with the raw seed
+        // what the piece ends with after this pair: the DP consensus, the walk's merged sequence (plain orientation), or raw read
+        const bool fromDp = e->status < 0 && e->dp_status == PBSC_DP_OK;
+        const bool fromWalk = e->status == 1 && !e->rtou;
+        if (!fromDp && !fromWalk) continue;
         const WalkTask& sp = spec[b + t + 1];
         if (!sp.valid) continue;
         int k2; bool rtou2;
@@ -882,9 +888,9 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         rec_spec = tail[2] + tail[3];
         nl += 6;
     }
-    // pools: [speculative tasks | their alternatives (same layout, DP fallback only) | one pending request per read]
-    int alt_rounds = E.no_dp ? 0 : 4;
-    if (const char* e = getenv("PBSC_ALT_ROUNDS")) alt_rounds = E.no_dp ? 0 : std::max(0, atoi(e));
+    // pools: [speculative tasks | their alternatives (same layout) | one pending request per read]
+    int alt_rounds = 4;
+    if (const char* e = getenv("PBSC_ALT_ROUNDS")) alt_rounds = std::max(0, atoi(e));
     const bool use_alt = alt_rounds > 0 && n_tasks > 0;
     E.alt_pool_base = align_up(pool_spec, 16);
     const uint64_t pending_pool_off = use_alt ? 2 * E.alt_pool_base : E.alt_pool_base;

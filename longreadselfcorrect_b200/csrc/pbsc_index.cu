@@ -594,24 +594,24 @@ void pbsc_index_destroy(pbsc_index* idx)
 
 // ---- random 32-byte-sector gather: the roofline denominator of the rank-query kernels ----
 namespace pbsc {
-__global__ void random_sector_kernel(const uint4* __restrict__ buf, uint64_t n_sectors, uint64_t loads, unsigned long long* sink)
+__global__ void random_sector_kernel(const uint4* __restrict__ buf, uint64_t sector_mask, uint64_t loads, unsigned long long* sink)
 {
-    // every thread issues `loads` independent 32-byte reads at pseudo-random sectors, eight in flight
+    // every thread issues `loads` independent 32-byte reads (one 16-byte load per sector: the sector is the DRAM unit) at
+    // pseudo-random sectors, sixteen in flight
     uint64_t x = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     unsigned long long acc = 0;
-    for (uint64_t i = 0; i < loads; i += 8)
+    for (uint64_t i = 0; i < loads; i += 16)
     {
-        uint4 a[8], b[8];
+        uint4 a[16];
         #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < 16; u++)
         {
             x = x * 6364136223846793005ull + 1442695040888963407ull;
-            const uint64_t sct = (x >> 20) % n_sectors;
+            const uint64_t sct = (x >> 24) & sector_mask;
             a[u] = __ldg(buf + 2 * sct);
-            b[u] = __ldg(buf + 2 * sct + 1);
         }
         #pragma unroll
-        for (int u = 0; u < 8; u++) acc += a[u].x ^ b[u].w;
+        for (int u = 0; u < 16; u++) acc += a[u].x ^ a[u].w;
     }
     if (acc == 0x12345) *sink = acc;
 }
@@ -624,20 +624,21 @@ int pbsc_random_sector_bench(int device, uint64_t bytes, float* gbps)
     if (!gbps || bytes < (1u << 20)) { set_error("pbsc_random_sector_bench: bad argument"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(device));
     DevBuf<uint4> buf; DevBuf<unsigned long long> sink;
-    const uint64_t n_sectors = bytes / 32;
+    uint64_t n_sectors = 1;
+    while (n_sectors * 2 * 32 <= bytes) n_sectors *= 2;   // largest power of two that fits: the sector index is a mask
     PBSC_CUDA(buf.alloc(n_sectors * 2)); PBSC_CUDA(sink.alloc(1));
     PBSC_CUDA(cudaMemset(buf.p, 1, n_sectors * 32));
     int sms = 0;
     PBSC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int blocks = sms * 8, threads = 256;
-    const uint64_t loads = 4096;
+    const uint64_t loads = 8192;
     cudaEvent_t e0, e1;
     PBSC_CUDA(cudaEventCreate(&e0)); PBSC_CUDA(cudaEventCreate(&e1));
     float best = 0;
     for (int rep = 0; rep < 4; rep++)
     {
         cudaEventRecord(e0);
-        pbsc::random_sector_kernel<<<blocks, threads>>>(buf.p, n_sectors, loads, sink.p);
+        pbsc::random_sector_kernel<<<blocks, threads>>>(buf.p, n_sectors - 1, loads, sink.p);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;

@@ -27,6 +27,9 @@ struct pbsc_index
     cudaStream_t stream2 = nullptr;   // side stream: the heavy walk pass runs here while the DP fallback of the light pass runs on `stream`
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int sm_count = 0;   // cached: cudaGetDeviceProperties costs tens of milliseconds
+    // capacities a batch had to grow to (label-tree nodes per walk, piece bytes per read base): later batches start there
+    uint32_t learned_node_cap = 0;
+    float learned_piece_factor = 0;
     // named scratch buffers that survive across batches (grow-only), so that the hot path does not pay
     // cudaMalloc/cudaFree of gigabytes per batch; one batch runs at a time per index
     struct ArenaBuf { void* p = nullptr; size_t cap = 0; };

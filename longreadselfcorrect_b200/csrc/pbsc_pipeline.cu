@@ -40,6 +40,8 @@ int pbsc_batch_upload(pbsc_index* idx, const pbsc_params* p, const char* reads, 
     bt->idx = idx;
     bt->params = *p;
     bt->h_offsets.assign(offsets, offsets + n_reads + 1);
+    if (idx->learned_node_cap) bt->w.node_cap = idx->learned_node_cap;
+    if (idx->learned_piece_factor > 0) bt->w.piece_factor = idx->learned_piece_factor;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, idx->stream);
@@ -93,6 +95,8 @@ int pbsc_batch_run(pbsc_batch* bt, float* ms)
         // grow the capacities and run the batch again
         bt->w.piece_factor *= 2.0f;
         bt->w.node_cap *= 8;
+        idx->learned_node_cap = bt->w.node_cap;
+        idx->learned_piece_factor = bt->w.piece_factor;
         rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w);
         if (rc != PBSC_OK) break;
     }
