@@ -294,10 +294,12 @@ __device__ __forceinline__ void dp_fill_row(const RowGeom& g, uint32_t* __restri
     const int rbase = lane * DP_CPL;
     int prev[DP_CPL];
     int sw[DP_CPL];   // s2[j-1] of this lane's rows in the current column; -1 outside the string
+    int idle[DP_CPL]; // what a cell the fill does not visit reads as: 0 inside the band (the zero-initialised table), never-equal outside
     #pragma unroll
     for (int t = 0; t < DP_CPL; t++)
     {
-        prev[t] = 0;
+        idle[t] = (rbase + t < DP_BW) ? 0 : DP_NEG;
+        prev[t] = idle[t];
         const int j = origin + 1 + rbase + t;
         sw[t] = (j >= 1 && j <= mlen) ? (int)s2[j - 1] : -1;
     }
@@ -326,7 +328,7 @@ __device__ __forceinline__ void dp_fill_row(const RowGeom& g, uint32_t* __restri
             const int diag = prev[t] + (sw[t] == c1 ? 1 : -8);
             const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
             // first row of the band: left if it is in the band; last row (when not also the first): no left
-            const bool useLeft = (r < DP_BW - 1) && r != rowNoLeft;
+            const bool useLeft = r != rowNoLeft;   // (band row 200's left neighbour is outside the band: DP_NEG, never the maximum)
             const int v0 = useLeft ? max(diag, pl - 1) : diag;
             run = max(run, comp ? v0 + r : DP_NEG);
             a[t] = run;
@@ -345,10 +347,11 @@ __device__ __forceinline__ void dp_fill_row(const RowGeom& g, uint32_t* __restri
         {
             const int r = rbase + t;
             const bool comp = (unsigned)(r - rlo) <= span;
-            cur[t] = comp ? max(a[t], excl) - r : 0;
+            cur[t] = comp ? max(a[t], excl) - r : idle[t];
         }
         // traceback bits: does the cell equal each in-band neighbour plus its step (overlapper.cpp:607-610)
-        const int upPrev = __shfl_up_sync(FULL, cur[DP_CPL - 1], 1);
+        int upPrev = __shfl_up_sync(FULL, cur[DP_CPL - 1], 1);
+        if (lane == 0) upPrev = DP_NEG;   // band row 0 has no cell above it in the band: never equal
         uint32_t w = 0;
         #pragma unroll
         for (int t = 0; t < DP_CPL; t++)
@@ -359,19 +362,17 @@ __device__ __forceinline__ void dp_fill_row(const RowGeom& g, uint32_t* __restri
             const int pl = (t < DP_CPL - 1) ? prev[t + 1] : pn0;
             const int upv = t > 0 ? cur[t - 1] : upPrev;
             uint32_t f = (cur[t] == diag) ? 1u : 0u;
-            f |= (r >= 1 && cur[t] == upv - 1) ? 2u : 0u;
-            f |= (r < DP_BW - 1 && cur[t] == pl - 1) ? 4u : 0u;
+            f |= (cur[t] == upv - 1) ? 2u : 0u;
+            f |= (cur[t] == pl - 1) ? 4u : 0u;
             w |= (comp ? f : 0u) << (3 * t);
         }
         flags[(size_t)i * 32 + lane] = w;
         // best cell of the last row: first column with the strictly largest score (overlapper.cpp:553-561)
         if (!skipCol && last == nRows - 1)
         {
-            const int rs = nRows - 1 - jb;
-            int sel = 0;
-            #pragma unroll
-            for (int t = 0; t < DP_CPL; t++) if (t == rs % DP_CPL) sel = cur[t];
-            const int vv = __shfl_sync(FULL, sel, rs / DP_CPL);
+            // the last row is the last computed cell of the column, band row rhi; its score is the end of the column's prefix
+            // maximum: c[rhi] = (max over computed r of a[r] + r) - rhi
+            const int vv = __shfl_sync(FULL, incl, 31) - rhi;
             if (!anyRow || vv > bestRowVal) { bestRowVal = vv; bestRowI = i; anyRow = true; }
         }
         // best cell of the last column: first row with the strictly largest score (:564-570)
