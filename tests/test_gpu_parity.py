@@ -345,3 +345,25 @@ def test_cli_drop_in_default_options(golden, tmp_path):
     want = [l for l in open(os.path.join(golden, "tiny.dp.summary.txt")).read().strip().splitlines() if l]
     got = [l for l in r.stdout.strip().splitlines() if l and not l.startswith("Time of")]
     assert got == want
+
+
+def test_pinned_buffers_and_cached_blocks_give_the_same_bytes(api, tiny_index, tiny_reads, golden):
+    """End-to-end entry from page-locked buffers (pbsc_host_alloc), twice, so the second call runs on cached device blocks
+    and reused pinned outputs: same bytes as the pageable path and as the reference."""
+    p = api.Params.make(coverage=30, genome=5)
+    tiny_index.build_prefix_table(13)
+    buf, off = api._concat([s for _, s in tiny_reads])
+    pin = (api.pinned_copy(buf), api.pinned_copy(off))
+    want = open(os.path.join(golden, "tiny.dp.correct.fa")).read()
+    for _ in range(2):
+        out, poff, first, stats = tiny_index.correct_reads(p, packed=pin, pinned_out=True)
+        c, _d = _write_records(api.Index.pieces_as_strings(out, poff, first), stats, tiny_reads)
+        assert c == want
+    t = api.last_timing()
+    assert t["walk_launches"] > 0 and t["walk_ms"] > 0 and t["dp_rows"] > 0
+    tiny_index.build_prefix_table(0)
+
+
+def test_random_sector_roofline_probe(api):
+    g = api.random_sector_peak(256 << 20)
+    assert 50.0 < g < 8000.0   # GB/s of independent 32-byte reads; a sanity bound, not a performance assertion
