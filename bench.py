@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="Mbp of reads for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--batch-mbp", type=float, default=320.0, help="largest batch of reads resident on the device at once (Mbp)")
     ap.add_argument("--nodp", action="store_true", help="disable the DP/MSA fallback on both arms (seeds + FM extension only)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -235,23 +236,61 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: batch resident on the device, kernels only ----
-    batch = api.Batch(idx, params, packed=packed)
+    # ---- batches: the whole read set is one batch when it fits (config 2 does); larger sets go through in contiguous,
+    #      length-balanced batches of at most --batch-mbp, one after the other, as the pbcorrect binary does ----
+    from longreadselfcorrect_b200 import sharding
+    n_batches = max(1, int(np.ceil(total_mbp / args.batch_mbp)))
+    ranges = sharding.balanced_ranges(np.diff(off), n_batches)
+    chunks = []
+    for b0, b1 in ranges:
+        o = off[b0:b1 + 1]
+        chunks.append((np.ascontiguousarray(packed[0][int(o[0]):int(o[-1])]), (o - o[0]).astype(np.uint64)))
+    log(f"rank {rank}: {len(chunks)} batch(es) per step")
+
+    # ---- value: reads resident on the device, kernels only (a batch is uploaded outside the timed region, run inside it) ----
+    resident = api.Batch(idx, params, packed=chunks[0]) if len(chunks) == 1 else None
+
+    def run_step(keep_first=False):
+        """one pass over all batches; returns (device ms, per-phase tuple, fetched result of the first batch or None)"""
+        if resident is not None:
+            ms = resident.run()
+            tm = api.last_timing()
+            return ms, [tm[k] for k in ("seed_ms", "extend_ms", "dp_ms", "walk_ms", "walk_launches", "dp_jobs", "dp_rows", "kernel_launches")], None
+        tot, acc, first_res = 0.0, [0.0] * 8, None
+        for ci, ch in enumerate(chunks):
+            bt = api.Batch(idx, params, packed=ch)
+            tot += bt.run()
+            tm = api.last_timing()
+            for j, k in enumerate(("seed_ms", "extend_ms", "dp_ms", "walk_ms", "walk_launches", "dp_jobs", "dp_rows", "kernel_launches")):
+                acc[j] += tm[k]
+            if keep_first:
+                res = bt.fetch()
+                if ci == 0:
+                    first_res = res          # pieces of the first batch: compared with the reference below
+                else:
+                    extra_stats.append(res[3].copy())   # the other batches only contribute their counters
+            bt.close()
+        return tot, acc, first_res
+
+    extra_stats = []
     for _ in range(args.warmup):
-        batch.run()
+        run_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     step_ms, phase = [], []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_ms.append(batch.run())
-        tm = api.last_timing()
-        phase.append((tm["seed_ms"], tm["extend_ms"], tm["dp_ms"], tm["walk_ms"], tm["walk_launches"], tm["dp_jobs"], tm["dp_rows"]))
+    last_first = None
+    for si in range(args.steps):
+        extra_stats.clear()
+        ms, ph, fr = run_step(keep_first=(si == args.steps - 1 and resident is None))
+        step_ms.append(ms)
+        phase.append(tuple(ph))
+        last_first = fr
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000
     clocks = sampler.stop()
-    tm = api.last_timing()
+    launches_per_step = int(phase[-1][7])
     dev_ms = float(np.sum(step_ms))
     if dist is not None:
         tt = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
@@ -259,21 +298,30 @@ def main():
         dev_ms, wall_ms = float(tt[0]), float(tt[1])
     ms_per_step = dev_ms / args.steps
     value = world * total_mbp / (ms_per_step / 1000)
-    out, poff, first, stats = batch.fetch()
-    d2h_bytes = int(poff[-1]) + stats.nbytes + poff.nbytes + first.nbytes
-    merged = stats[stats["merge"] == 1]
-    walks = int(merged["total_walk_num"].sum())
-    fm = int(merged["fm_num"].sum())
-    batch.close()
+    if resident is not None:
+        out, poff, first, stats = resident.fetch()
+        all_stats = [stats]
+        resident.close()
+    else:
+        out, poff, first, stats = last_first
+        all_stats = [stats] + extra_stats
+    d2h_bytes = 0
+    walks = fm = 0
+    for st_ in all_stats:
+        m_ = st_[st_["merge"] == 1]
+        walks += int(m_["total_walk_num"].sum())
+        fm += int(m_["fm_num"].sum())
+        d2h_bytes += int(m_["corrected_len"].sum()) + st_.nbytes + 16 * len(st_)
 
     # ---- e2e: host buffers in, corrected pieces out, through pbsc_correct_batch: the reads sit in pinned host memory, every
     #      step copies them to the device, runs the path and copies the corrected pieces back into pinned host memory ----
-    pinned_in = (api.pinned_copy(packed[0]), api.pinned_copy(packed[1]))
+    pinned_in = [(api.pinned_copy(c[0]), api.pinned_copy(c[1])) for c in sorted(chunks, key=lambda c: -c[0].size)]
     e2e_ms = []
     for i in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
-        idx.correct_reads(params, packed=pinned_in, pinned_out=True)
+        for pin in pinned_in:
+            idx.correct_reads(params, packed=pin, pinned_out=True)
         torch.cuda.synchronize()
         if i > 0:
             e2e_ms.append((time.perf_counter() - t0) * 1000)
@@ -283,7 +331,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = float(tt[0])
     e2e_value = world * total_mbp / (e2e / 1000)
-    h2d_bytes = int(packed[0].nbytes + packed[1].nbytes)
+    h2d_bytes = int(sum(c[0].nbytes + c[1].nbytes for c in chunks))
 
     if rank != 0:
         if dist is not None:
@@ -395,10 +443,11 @@ def main():
                    "index_bytes": idx.device_bytes(), "prefix_k0": args.k0, "index_build_s": index_s,
                    "l2": "rank tables + prefix table exceed the 126 MB L2; no explicit flush",
                    "sharding": "index replicated per GPU, every rank corrects the full read set, no collective on the data path",
+                   "batches_per_step": len(chunks),
                    "wall_ms_per_step": wall_ms / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e},
-        "gpu_launches": int(tm["kernel_launches"]) * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "cpu_baseline": cpu,
         "parity_vs_reference": parity,

@@ -320,15 +320,17 @@ class Index:
         while True:
             poff_cap = (total // 10 + 4 * n + 16) if params.c.split else (n + 2)
             if pinned_out:
-                key = (cap, poff_cap, n)
-                if getattr(self, "_pin_key", None) != key:
-                    for old in getattr(self, "_pin_blocks", ()):
+                have = getattr(self, "_pin_caps", None)
+                if have is None or have[0] < cap or have[1] < poff_cap or have[2] < n:
+                    for old in getattr(self, "_pin", ()):
                         pinned_free(old)
-                    self._pin_blocks = ()
-                    self._pin = (pinned_empty(cap, np.uint8), pinned_empty(poff_cap, np.uint64), pinned_empty(n + 1, np.uint64),
-                                 np.frombuffer(pinned_empty(max(n, 1) * STATS_DTYPE.itemsize, np.uint8), dtype=STATS_DTYPE))
-                    self._pin_key = key
-                out, poff, first, stats = self._pin
+                    caps = (max(cap, have[0] if have else 0), max(poff_cap, have[1] if have else 0), max(n, have[2] if have else 0))
+                    self._pin = (pinned_empty(caps[0], np.uint8), pinned_empty(caps[1], np.uint64), pinned_empty(caps[2] + 1, np.uint64),
+                                 pinned_empty(max(caps[2], 1) * STATS_DTYPE.itemsize, np.uint8))
+                    self._pin_caps = caps
+                out, poff, first = self._pin[0], self._pin[1], self._pin[2][: n + 1]
+                stats = np.frombuffer(self._pin[3], dtype=STATS_DTYPE)[: max(n, 1)]
+                cap, poff_cap = out.size, poff.size
             else:
                 out = np.zeros(cap, dtype=np.uint8)
                 poff = np.zeros(poff_cap, dtype=np.uint64)
