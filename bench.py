@@ -342,7 +342,7 @@ def main():
     cpu = None
     alg = None
     parity = None
-    if not args.no_cpu_baseline and os.path.exists(REF_STRIDE):
+    if not args.no_cpu_baseline and world == 1 and os.path.exists(REF_STRIDE):   # rank 0 at N = 1 only
         sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.04 * cores * 15))
         sample_reads = max(1, min(int(np.searchsorted(off, sample_mbp * 1e6)), n_reads))
         sample_mbp = float(off[sample_reads]) / 1e6
@@ -416,6 +416,17 @@ def main():
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "kernel_ms": walk_ms, "kernel_launches_per_step": walk_launches, "extend_phase_ms": ext_ms, "seed_phase_ms": seed_ms,
             "dp_fallback_ms": dp_ms}
+    if not (alg and alg.get("walks")):
+        # CPU legs skipped (N > 1 or --no-cpu-baseline): per-unit algorithmic work from the committed oracle measurement
+        try:
+            c = json.load(open(os.path.join(ROOT, "profiles", "algorithmic.json"))).get(args.workload + ("_nodp" if args.nodp else ""))
+            if c:
+                alg = {"walks": 1.0, "extend": c["rank_queries_per_walk"], "seed": c["seed_rank_queries_per_read_base"], "sample_bases": 1.0,
+                       "source": "profiles/algorithmic.json"}
+                if c.get("dp_band_cells_per_job"):
+                    alg.update({"dp_jobs": 1.0, "dp_cells": c["dp_band_cells_per_job"]})
+        except Exception:
+            pass
     if alg and alg.get("walks"):
         per_walk = alg["extend"] / alg["walks"]
         alg_bytes = per_walk * walks * 32.0
