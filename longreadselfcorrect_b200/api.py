@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpbsc.so")
+LIB_PATH = os.environ.get("PBSC_LIB") or os.path.join(_PKG, "libpbsc.so")   # PBSC_LIB: an alternative build of the same library (experiments)
 
 PBSC_BWT, PBSC_RBWT = 0, 1
 

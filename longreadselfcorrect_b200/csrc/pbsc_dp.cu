@@ -412,7 +412,10 @@ __device__ __forceinline__ void dp_fill_row(const RowGeom& g, uint32_t* __restri
     if (!(anyRow || anyCol) || bi <= 0 || bj <= 0) bi = 0;
 }
 
-__global__ void __launch_bounds__(DP_WARPS * 32, 3)
+#ifndef PBSC_DP_MINB
+#define PBSC_DP_MINB 2   // measured on config 2: DP stage 709 ms at 3 resident blocks (80 registers, spills), 681 ms at 2 (109 registers)
+#endif
+__global__ void __launch_bounds__(DP_WARPS * 32, PBSC_DP_MINB)
 dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0,
                 uint32_t* arenas, uint64_t arena_words, unsigned long long* counter, unsigned int* n_bad)
 {
