@@ -828,7 +828,15 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     const uint32_t pending_cap = (uint32_t)align_up((size_t)(1.2 * (hmax[0] + 10)) + 2 * 64 + hmax[1] + 64, 16);
     E.pend_rec_cap = tw::setup_record_bytes(need_q, std::max<uint32_t>(hmax[1], 64), p->min_kmer, p->idmer_len);
     ExtParamsDev P;
-    const uint32_t t_node_cap = 4096;                 // light walks; a walk that needs more goes to the heavy pass
+    uint32_t t_node_cap = 4096;                       // light walks; a walk that needs more goes to the heavy pass
+    tw::Caps light_caps{8, 32, 40, 32};
+    if (const char* e = getenv("PBSC_TW_LIGHT"))
+    {
+        // "live leaves,children per level,history rings,results,label-tree nodes" of the light pass (experiments)
+        unsigned a = 0, b2 = 0, c = 0, d = 0, n2 = 0;
+        if (sscanf(e, "%u,%u,%u,%u,%u", &a, &b2, &c, &d, &n2) == 5 && a >= 1 && b2 >= 4 * 1 && c >= a + 1 && c <= 255 && d >= 1 && n2 >= 64)
+        { light_caps = tw::Caps{a, b2, c, d}; t_node_cap = n2; }
+    }
     make_ext_params(p, P, w.q_cap, t_node_cap, pending_cap);
     make_ext_params(p, E.Pw, w.q_cap, std::max<uint32_t>(w.node_cap, 1u << 15), pending_cap);
     {
@@ -839,7 +847,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     E.kernel = walk_kernel_for(walk_min_blocks());
     int rc = thread_geometry(idx->device, &E.blocks);
     if (rc != PBSC_OK) return rc;
-    E.light = tw::Caps{8, 32, 40, 32};
+    E.light = light_caps;
     // everything extendOverlap's loop can hold: -l live leaves, four children each (LongReadCorrectByOverlap.cpp:161)
     E.heavy = tw::Caps{(uint32_t)OLD_CAP, (uint32_t)NEW_CAP, (uint32_t)RING_SLOTS, (uint32_t)RES_CAP};
     E.stride = tw::thread_scratch_bytes(t_node_cap, E.light);
