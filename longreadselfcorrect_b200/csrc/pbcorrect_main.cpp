@@ -349,7 +349,7 @@ int main(int argc, char** argv)
 
     int64_t totalReadsLen = 0, correctedLen = 0, totalSeedNum = 0, totalWalkNum = 0, highErrorNum = 0, exceedDepthNum = 0, exceedLeaveNum = 0, FMNum = 0,
             DPNum = 0, seedDis = 0;
-    double seed_s = 0, fm_s = 0;
+    double seed_s = 0, fm_s = 0, dp_s = 0;
     size_t written = 0, nreads = 0;
     uint64_t inBases = 0;
     auto flush = [&](bool all) -> bool {
@@ -387,7 +387,7 @@ int main(int argc, char** argv)
                     discard << "\n";
                 }
             }
-            seed_s += b->timing.seed_ms / 1e3; fm_s += b->timing.extend_ms / 1e3;
+            seed_s += b->timing.seed_ms / 1e3; fm_s += (b->timing.extend_ms - b->timing.dp_ms) / 1e3; dp_s += b->timing.dp_ms / 1e3;
             { std::lock_guard<std::mutex> lk(mu); batches[written].reset(new Batch()); batches[written]->done = true; }
             written++;
         }
@@ -442,7 +442,7 @@ int main(int argc, char** argv)
                   << "DisBetweenSeeds: " << seedDis / totalWalkNum << "\n"
                   << "Time of searching Seeds: " << seed_s << "\n"
                   << "Time of searching FM: " << fm_s << "\n"
-                  << "Time of searching DP: " << 0 << "\n";
+                  << "Time of searching DP: " << dp_s << "\n";
     }
     // KmerThreshold::~KmerThreshold — PacBio/KmerThreshold.cpp:31-41
     {
