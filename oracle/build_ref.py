@@ -16,6 +16,7 @@ Outputs (git-ignored, but shipped to the GPU box by gpurun):
   oracle/_ref/stride          the reference binary
   oracle/_ref/fm_dump         tiny driver linked against the reference objects;
                               prints BWTAlgorithms::findInterval lower/upper
+  oracle/_ref/dp_dump         the same for Overlapper::extendMatch and MultipleAlignment (DP fallback)
   oracle/_ref/obj/*.o         objects
 """
 import os
@@ -67,11 +68,13 @@ def main():
     main_o = [o for o in objs if o.endswith("StriDe_StriDe.o")]
     lib_o = [o for o in objs if o not in main_o]
     drv = os.path.join(HERE, "refbuild", "fm_dump.cpp")
+    drv2 = os.path.join(HERE, "refbuild", "dp_dump.cpp")
     mk = os.path.join(OUT, "Makefile")
     with open(mk, "w") as f:
-        f.write(f"all: {OUT}/stride {OUT}/fm_dump\n")
+        f.write(f"all: {OUT}/stride {OUT}/fm_dump {OUT}/dp_dump\n")
         f.write(f"{OUT}/stride: {' '.join(objs)}\n\tg++ -fopenmp -pthread $^ -lz -o $@\n")
         f.write(f"{OUT}/fm_dump: {drv} {' '.join(lib_o)}\n\t{cxx} $^ -pthread -lz -o $@\n")
+        f.write(f"{OUT}/dp_dump: {drv2} {' '.join(lib_o)}\n\t{cxx} $^ -pthread -lz -o $@\n")
         f.write("\n".join(rules))
     r = subprocess.run(["make", "-f", mk, f"-j{os.cpu_count() or 4}", "-s"], cwd=OUT)
     return r.returncode

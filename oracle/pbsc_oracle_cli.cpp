@@ -8,6 +8,7 @@
 //       seeds / per-pair walk records / pieces for structured parity tests.
 //   pbsc_oracle findinterval FILE.bwt QUERIES     "lower upper" per query (cf. oracle/_ref/fm_dump)
 //   pbsc_oracle occcount ...pbcorrect args...     like pbcorrect, also prints rank queries issued
+//   pbsc_oracle dpcheck FILE                      extendMatch / multiple-alignment records (cf. oracle/_ref/dp_dump)
 #include <getopt.h>
 #include <omp.h>
 #include <sys/stat.h>
@@ -32,11 +33,60 @@ static int findIntervalMain(int argc, char** argv)
     return 0;
 }
 
+// run-length form of an expanded cigar, as Overlapper::compactCigar prints it
+static std::string compactOps(const std::string& ops)
+{
+    std::string out;
+    for (size_t i = 0; i < ops.size();)
+    {
+        size_t j = i;
+        while (j < ops.size() && ops[j] == ops[i]) j++;
+        out += std::to_string(j - i) + ops[i];
+        i = j;
+    }
+    return out;
+}
+
+// same record format as oracle/refbuild/dp_dump.cpp, answered by the restatement in pbsc_oracle_dp.hpp
+static int dpCheckMain(int argc, char** argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: pbsc_oracle dpcheck FILE\n"); return 2; }
+    std::ifstream in(argv[2]);
+    std::string tag;
+    while (in >> tag)
+    {
+        if (tag == "A")
+        {
+            std::string s1, s2; int a, b;
+            in >> s1 >> s2 >> a >> b;
+            PairOverlap o = extendMatch(s1, s2, a, b, 200, 1, -1, -8);
+            std::cout << "A " << o.score << " " << o.start[0] << " " << o.end[0] << " " << o.start[1] << " " << o.end[1] << " " << o.editDistance << " "
+                      << o.totalColumns << " " << compactOps(o.ops) << "\n";
+        }
+        else if (tag == "M")
+        {
+            std::string q; int minCall, n;
+            in >> q >> minCall >> n;
+            Msa msa;
+            msa.addBase(q);
+            for (int i = 0; i < n; i++)
+            {
+                std::string s; int a, b;
+                in >> s >> a >> b;
+                msa.addOverlap(s, extendMatch(q, s, a, b, 200, 1, -1, -8));
+            }
+            std::cout << "M " << msa.rows.size() << " " << msa.consensus(minCall) << "\n";
+        }
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: pbsc_oracle {pbcorrect|findinterval} ...\n"); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: pbsc_oracle {pbcorrect|findinterval|dpcheck} ...\n"); return 2; }
     std::string cmd = argv[1];
     if (cmd == "findinterval") return findIntervalMain(argc, argv);
+    if (cmd == "dpcheck") return dpCheckMain(argc, argv);
     if (cmd != "pbcorrect") { fprintf(stderr, "unknown command %s\n", cmd.c_str()); return 2; }
 
     Params P;

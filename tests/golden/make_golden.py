@@ -101,6 +101,73 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def dp_unit_vectors():
+    """Direct vectors for Overlapper::extendMatch and MultipleAlignment: inputs in dp_units.txt, the reference's answers
+    (oracle/_ref/dp_dump, linked against the reference's own objects) in dp_units.ref.txt."""
+    rng = np.random.Generator(np.random.PCG64(2025))
+    acgt = "ACGT"
+
+    def rand_seq(n):
+        return "".join(acgt[int(x)] for x in rng.integers(0, 4, size=n))
+
+    def mutate(s, rate):
+        out = []
+        for ch in s:
+            u = rng.random()
+            if u < rate * 0.3:
+                continue                                  # deletion
+            if u < rate * 0.45:
+                out.append(acgt[int(rng.integers(0, 4))])  # substitution
+            else:
+                out.append(ch)
+            if rng.random() < rate * 0.55:
+                out.append(out[-1] if rng.random() < 0.5 else acgt[int(rng.integers(0, 4))])   # insertion (often a homopolymer)
+        return "".join(out) or "A"
+
+    lines = []
+    for i in range(360):
+        n = int(rng.integers(20, 420))
+        q = rand_seq(n)
+        if i % 7 == 0:   # low-complexity stretches exercise the homopolymer tie-breaks
+            p0 = int(rng.integers(0, max(1, n - 12)))
+            q = q[:p0] + acgt[int(rng.integers(0, 4))] * 12 + q[p0 + 12:]
+        k = int(rng.integers(9, 20))
+        if n <= k + 2:
+            continue
+        mode = i % 4
+        if mode == 0:     # read starts with the query's first k-mer and runs on (forward seed)
+            m = q[:k] + mutate(q[k:], 0.13) + rand_seq(int(rng.integers(0, 60)))
+            lines.append(f"A {q} {m} 0 0")
+        elif mode == 1:   # read ends with the query's last k-mer (reverse seed)
+            m = rand_seq(int(rng.integers(0, 60))) + mutate(q[:-k], 0.13) + q[-k:]
+            lines.append(f"A {q} {m} {len(q) - k} {len(m) - k}")
+        elif mode == 2:   # short read: the band leaves the matrix
+            m = q[:k] + mutate(q[k:k + int(rng.integers(1, 40))], 0.2)
+            lines.append(f"A {q} {m} 0 0")
+        else:             # unrelated read sharing only the seed
+            m = q[:k] + rand_seq(int(rng.integers(5, 300)))
+            lines.append(f"A {q} {m} 0 0")
+    for i in range(60):
+        n = int(rng.integers(60, 300))
+        q = rand_seq(n)
+        k = 13
+        rows = []
+        for r in range(int(rng.integers(3, 25))):
+            if r % 2 == 0:
+                m = q[:k] + mutate(q[k:], 0.13)
+                rows.append(f"{m} 0 0")
+            else:
+                m = mutate(q[:-k], 0.13) + q[-k:]
+                rows.append(f"{m} {len(q) - k} {len(m) - k}")
+        lines.append(f"M {q} {int(rng.integers(3, 20))} {len(rows)}")
+        lines.extend(rows)
+    path = os.path.join(HERE, "dp_units.txt")
+    open(path, "w").write("\n".join(lines) + "\n")
+    r = run([os.path.join(ROOT, "oracle", "_ref", "dp_dump"), path])
+    open(os.path.join(HERE, "dp_units.ref.txt"), "w").write(r.stdout)
+    print("DP unit vectors:", len(r.stdout.splitlines()), "records")
+
+
 def dp_fixtures():
     tmp = tempfile.mkdtemp(prefix="pbsc_golden_dp_")
     reads = os.path.join(HERE, "tiny.reads.fa")
@@ -125,5 +192,8 @@ def dp_fixtures():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dp":
         dp_fixtures()
+        dp_unit_vectors()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dpunits":
+        dp_unit_vectors()
     else:
         main()
