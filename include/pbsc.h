@@ -206,6 +206,7 @@ typedef struct pbsc_timing
     uint64_t dp_rows;        /* overlapping reads retrieved and aligned for them */
     float walk_ms;           /* walk_levels_kernel alone: CUDA events around each of its launches, summed */
     uint64_t walk_launches;
+    uint64_t dp_thread_rows; /* of dp_rows: aligned by the thread-per-alignment kernel (the rest by the warp-per-row kernel) */
 } pbsc_timing;
 int pbsc_last_timing(pbsc_timing* t);
 

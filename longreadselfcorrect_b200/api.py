@@ -55,7 +55,7 @@ class CTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("seed_ms", C.c_float), ("extend_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("total_ms", C.c_float), ("kernel_launches", C.c_uint64), ("seed_pairs", C.c_uint64),
                 ("rank_queries", C.c_uint64), ("dp_ms", C.c_float), ("dp_jobs", C.c_uint64), ("dp_rows", C.c_uint64),
-                ("walk_ms", C.c_float), ("walk_launches", C.c_uint64)]
+                ("walk_ms", C.c_float), ("walk_launches", C.c_uint64), ("dp_thread_rows", C.c_uint64)]
 
 
 SEED_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("max_fixed_freq", "<i4"), ("is_repeat", "<i4"),

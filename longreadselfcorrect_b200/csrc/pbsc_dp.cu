@@ -23,6 +23,7 @@
 #include "pbsc_batch.cuh"
 #include "pbsc_task.cuh"
 #include "pbsc_dp.cuh"
+#include "pbsc_dp_thread.cuh"
 
 namespace pbsc {
 
@@ -524,6 +525,149 @@ dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, co
     }
 }
 
+// ---- stage 2t: banded alignment, one alignment per thread (pbsc_dp_thread.cuh) -------------------------------------------
+// Rows whose every query column meets the matrix and whose query is at most DPT_QMAX long (nearly all of them) are sorted
+// by query length and aligned here, 32 rows of one length per warp; what is left stays `pass == 2` for dp_align_kernel.
+constexpr int DPT_QMAX = 256;                                                  // longest query of the thread kernel
+constexpr int DPT_NT = 128;                                                    // threads per block
+constexpr int DPT_HWORDS = dpt::HSLOTS / 2;                                    // 16-bit scores, two per word
+constexpr int DPT_SWORDS = (dpt::max_len_bound(DPT_QMAX) + 15) / 16 + 1;       // 2-bit read + one word of slack for bits()
+constexpr int DPT_SMEM = (DPT_HWORDS + DPT_SWORDS) * DPT_NT * 4;               // 75 776 B: three blocks per SM
+constexpr uint64_t DPT_ARENA_WORDS = 32ull * DPT_QMAX * dpt::WMAX;             // flag words of one warp's 32 rows
+constexpr uint32_t DPT_KEY_NONE = 0x7FFu;
+
+__device__ __forceinline__ int dp_row_origin(const DpRow& R, const DpJob& J)
+{
+    const int k = (int)J.k, qlen = (int)J.qlen, mlen = (int)R.len;
+    const bool isRC = R.local >= J.cnt[0] + J.cnt[1];
+    const int start_1 = isRC ? qlen - k : 0, start_2 = isRC ? mlen - k : 0;
+    return (start_2 - start_1 + 1) - (DP_HALF + 1);
+}
+
+// sort key of a row: longest queries first, forward rows before reverse-complement rows; DPT_KEY_NONE = not for this kernel
+__global__ void __launch_bounds__(256)
+dp_keys_kernel(uint64_t n_rows, const DpRow* __restrict__ rows, const DpJob* __restrict__ jobs, uint32_t* keys, uint32_t* order, int qmax,
+               unsigned int* n_thread_rows)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const DpRow R = rows[i];
+    uint32_t key = DPT_KEY_NONE;
+    if (R.pass == 2)
+    {
+        const DpJob J = jobs[R.job];
+        if (dpt::eligible((int)J.qlen, (int)R.len, dp_row_origin(R, J), qmax))
+            key = ((uint32_t)(qmax - (int)J.qlen) << 1) | (R.local >= J.cnt[0] + J.cnt[1] ? 1u : 0u);
+    }
+    keys[i] = key;
+    order[i] = (uint32_t)i;
+    // how many rows take this path (reported in pbsc_timing); one atomic per warp
+    const unsigned m = __ballot_sync(__activemask(), key != DPT_KEY_NONE);
+    if (key != DPT_KEY_NONE && (threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(n_thread_rows, (unsigned)__popc(m));
+}
+
+struct DptH   // previous column: 16-bit scores, slot j & 255, word (slot >> 1) of this thread's column of shared memory
+{
+    uint32_t* p;
+    __device__ __forceinline__ int get(int j) const
+    {
+        const int s = j & (dpt::HSLOTS - 1);
+        return (int)reinterpret_cast<const short*>(p + (s >> 1) * DPT_NT)[s & 1];
+    }
+    __device__ __forceinline__ void set(int j, int v)
+    {
+        const int s = j & (dpt::HSLOTS - 1);
+        reinterpret_cast<short*>(p + (s >> 1) * DPT_NT)[s & 1] = (short)v;
+    }
+    // five aligned pairs from the even row j on: one base address, constant offsets
+    __device__ __forceinline__ bool pairs_ok(int j) const { return ((j >> 1) & (DPT_HWORDS - 1)) <= DPT_HWORDS - 5; }
+    __device__ __forceinline__ uint32_t get2(int j, int u) const { return p[((j >> 1) & (DPT_HWORDS - 1)) * DPT_NT + u * DPT_NT]; }
+    __device__ __forceinline__ void set2(int j, int u, uint32_t w) { p[((j >> 1) & (DPT_HWORDS - 1)) * DPT_NT + u * DPT_NT] = w; }
+};
+struct DptS   // the retrieved read at 2 bits per base, 16 bases per word, in this thread's column of shared memory
+{
+    const uint32_t* p;
+    __device__ __forceinline__ int base(int x) const { return (int)((p[(x >> 4) * DPT_NT] >> (2 * (x & 15))) & 3u); }
+    __device__ __forceinline__ uint32_t bits(int x) const
+    {
+        const uint32_t* w = p + (x >> 4) * DPT_NT;
+        return __funnelshift_r(w[0], w[DPT_NT], 2 * (x & 15));   // shift < 32; bits 20.. are ignored by the caller
+    }
+};
+struct DptF   // flag words of this lane: word n of the lane at arena[n * 32 + lane] (a warp's stores coalesce)
+{
+    uint32_t* p;
+    __device__ __forceinline__ void put(int n, uint32_t w) { p[(size_t)n * 32] = w; }
+    __device__ __forceinline__ uint32_t get(int n) const { return p[(size_t)n * 32]; }
+};
+struct DptQ { const uint8_t* q; __device__ __forceinline__ int operator()(int x) const { return (int)q[x]; } };
+struct DptOps { uint8_t* ops; __device__ __forceinline__ void put(int n, int op) { ops[n] = (uint8_t)op; } };
+
+__global__ void __launch_bounds__(DPT_NT, 3)
+dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, DpRow* rows,
+                       const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0, uint32_t* arenas,
+                       unsigned long long* counter, unsigned int* n_bad)
+{
+    extern __shared__ uint32_t dpt_smem[];
+    const int lane = threadIdx.x & 31;
+    uint32_t* Hs = dpt_smem + threadIdx.x;
+    uint32_t* Ss = dpt_smem + DPT_HWORDS * DPT_NT + threadIdx.x;
+    const uint64_t warp = (uint64_t)blockIdx.x * (DPT_NT / 32) + (threadIdx.x >> 5);
+    DptF F{arenas + warp * DPT_ARENA_WORDS + lane};
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_rows) break;
+        const uint64_t t = base + lane;
+        const uint32_t key = t < n_rows ? keys[t] : DPT_KEY_NONE;
+        if (__shfl_sync(FULL, key, 0) == DPT_KEY_NONE) break;   // sorted: nothing but other rows from here on
+        if (key == DPT_KEY_NONE) continue;
+        const uint64_t ri = order[t];
+        DpRow R = rows[ri];
+        const DpJob J = jobs[R.job];
+        RowGeom g;
+        row_geometry(R, J, mem, mem0, g);
+        // the read at 2 bits per base, the column at zero
+        for (int x = 0; x < g.mlen; x += 16)
+        {
+            uint32_t w = 0;
+            const int m = min(16, g.mlen - x);
+            for (int y = 0; y < m; y++) w |= (uint32_t)g.s2[x + y] << (2 * y);
+            Ss[(x >> 4) * DPT_NT] = w;
+        }
+        Ss[((g.mlen + 15) >> 4) * DPT_NT] = 0u;
+        #pragma unroll 8
+        for (int x = 0; x < DPT_HWORDS; x++) Hs[x * DPT_NT] = 0u;
+        DptH H{Hs};
+        const DptS S{Ss};
+        const DptQ q{g.q};
+        int bi, bj;
+        dpt::fill(g.qlen, g.mlen, g.origin, H, S, F, q, bi, bj);
+        if (bi <= 0) { atomicAdd(n_bad, 1u); R.pass = 0; }   // the reference would abort on its empty-cigar assert
+        else
+        {
+            DptOps ops{g.ops};
+            int n, ed, i0, j0;
+            dpt::traceback(g.qlen, g.mlen, g.origin, S, F, q, bi, bj, ops, n, ed, i0, j0);
+            const WalkTask& tk = tasks[J.task];
+            // identity = 0.65 (+0.05 above 50, +0.05 above 100), min_overlap = path.length()/10
+            // (PacBioSelfCorrectionProcess.cpp:225-235)
+            const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
+            double identity = 0.65;
+            identity = __dadd_rn(identity, fsum > 50 ? 0.05 : 0.0);
+            identity = __dadd_rn(identity, fsum > 100 ? 0.05 : 0.0);
+            const double pct = __ddiv_rn(__dmul_rn((double)(n - ed), 100.0), (double)n);   // getPercentIdentity (overlapper.cpp:71-74)
+            const bool passOverlap = (uint64_t)n >= (uint64_t)(g.qlen / 10);
+            const bool passIdentity = __ddiv_rn(pct, 100.0) >= identity;
+            R.nops = (uint32_t)n; R.start0 = i0; R.start1 = j0;
+            R.pass = (passOverlap && passIdentity) ? 1u : 0u;
+        }
+        rows[ri] = R;
+    }
+}
+
 // ---- stage 3: thread per job: multiple alignment on per-column counts, consensus ---------------------------------------
 // Column model.  MultipleAlignment::_addSequence places every incoming row against row 0 (the query); a new gap column is
 // only ever inserted immediately before a BASE column of row 0, i.e. appended to the run of gap columns in front of that
@@ -667,7 +811,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     PBSC_CUDA(cudaEventRecord(ev[0], st));
     dp_collect_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, n_items, list, tasks, b.codes.p, b.offsets.p, (uint32_t)p->pb_coverage,
                                                                         jobs, job_rows, job_bytes, cnt);
-    unsigned int hcnt[2] = {0, 0};
+    unsigned int hcnt[3] = {0, 0, 0};
     PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 8, cudaMemcpyDeviceToHost, st));
     PBSC_CUDA(cudaStreamSynchronize(st));
     if (launches) *launches += 1;
@@ -736,6 +880,29 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     }
     DpRow* rows;
     PBSC_CUDA(arena(idx, "dp.rows", max_rows, &rows));
+    // thread-per-alignment kernel (stage 2t): sort keys, the sorted order, one flag arena per resident warp
+    bool use_thread = true;
+    if (const char* e = getenv("PBSC_DP_THREAD")) use_thread = atoi(e) != 0;
+    uint32_t *tkeys = nullptr, *tkeys2 = nullptr, *torder = nullptr, *torder2 = nullptr, *tslabs = nullptr;
+    uint8_t* sort_tmp = nullptr;
+    size_t sort_bytes = 0;
+    int tblocks = 0;
+    if (use_thread)
+    {
+        PBSC_CUDA(cudaFuncSetAttribute(dp_align_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPT_SMEM));
+        int tper_sm = 0;
+        PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tper_sm, dp_align_thread_kernel, DPT_NT, DPT_SMEM));
+        if (tper_sm < 1) tper_sm = 1;
+        if (const char* e = getenv("PBSC_DPT_BLOCKS_PER_SM")) { if (atoi(e) > 0) tper_sm = std::min(tper_sm, atoi(e)); }
+        tblocks = idx->sm_count * tper_sm;
+        PBSC_CUDA(arena(idx, "dp.tkeys", max_rows, &tkeys));
+        PBSC_CUDA(arena(idx, "dp.tkeys2", max_rows, &tkeys2));
+        PBSC_CUDA(arena(idx, "dp.torder", max_rows, &torder));
+        PBSC_CUDA(arena(idx, "dp.torder2", max_rows, &torder2));
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, tkeys, tkeys2, torder, torder2, (int)max_rows, 0, 11, st);
+        PBSC_CUDA(arena(idx, "dp.sorttmp", sort_bytes, &sort_tmp));
+        PBSC_CUDA(arena(idx, "dp.tflags", DPT_ARENA_WORDS * (uint64_t)tblocks * (DPT_NT / 32), &tslabs));
+    }
     for (uint64_t j0 = 0; j0 < nj;)
     {
         uint64_t j1 = j0 + 1;
@@ -743,7 +910,16 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         const uint64_t nrows = h_row[j1] - h_row[j0], njc = j1 - j0;
         dp_rows_kernel<<<(unsigned)((njc + 127) / 128), 128, 0, st>>>(j0, j1, jobs, tasks, b.codes.p, b.offsets.p, mem, h_mem[j0], rows, h_row[j0]);
         dp_retrieve_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(idx->dev, nrows, rows, jobs, mem, h_mem[j0]);
-        PBSC_CUDA(cudaMemsetAsync(qctr, 0, 8, st));
+        PBSC_CUDA(cudaMemsetAsync(qctr, 0, 16, st));
+        if (use_thread)
+        {
+            dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, tkeys, torder, DPT_QMAX, cnt + 2);
+            size_t sb = sort_bytes;
+            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, tkeys, tkeys2, torder, torder2, (int)nrows, 0, 11, st);
+            const int tb = (int)std::min<uint64_t>((uint64_t)tblocks, (nrows + DPT_NT - 1) / DPT_NT);
+            dp_align_thread_kernel<<<tb, DPT_NT, DPT_SMEM, st>>>(nrows, tkeys2, torder2, rows, jobs, tasks, mem, h_mem[j0], tslabs, qctr + 1, cnt + 1);
+            if (launches) *launches += 4;   // keys, two radix passes at most (counted as the sort's kernels), alignment
+        }
         const int nb = (int)std::min<uint64_t>((uint64_t)ablocks, (nrows + DP_WARPS * 32 - 1) / (DP_WARPS * 32));
         dp_align_kernel<<<nb, DP_WARPS * 32, 0, st>>>(nrows, rows, jobs, tasks, mem, h_mem[j0], slabs, arena_words, qctr, cnt + 1);
         dp_msa_kernel<<<(unsigned)((njc + 63) / 64), 64, 0, st>>>(j0, j1, jobs, tasks, rows, h_row[j0], mem, h_mem[j0], outpool, cnt + 1);
@@ -753,9 +929,10 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         j0 = j1;
     }
     PBSC_CUDA(cudaEventRecord(ev[1], st));
-    PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 12, cudaMemcpyDeviceToHost, st));
     PBSC_CUDA(cudaStreamSynchronize(st));
     S.bad += hcnt[1];
+    S.thread_rows += hcnt[2];
     float ms = 0;
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
     S.ms += ms;

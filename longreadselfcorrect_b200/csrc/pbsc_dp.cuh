@@ -6,7 +6,7 @@
 
 namespace pbsc {
 
-struct DpStats { uint64_t jobs = 0, rows = 0, chunks = 0, bad = 0; float ms = 0; };
+struct DpStats { uint64_t jobs = 0, rows = 0, chunks = 0, bad = 0, thread_rows = 0; float ms = 0; };
 DpStats& last_dp_stats();
 
 // For every task of the list whose FM walk failed and that asked for it (dp_wanted): retrieve the overlapping reads, align

@@ -830,7 +830,7 @@ int pbsc_last_timing(pbsc_timing* t)
     t->h2d_ms = s.h2d_ms; t->seed_ms = s.seed_ms; t->extend_ms = s.extend_ms; t->d2h_ms = s.d2h_ms; t->total_ms = s.total_ms;
     t->kernel_launches = s.kernel_launches; t->seed_pairs = s.seed_pairs; t->rank_queries = s.rank_queries;
     t->dp_ms = s.dp_ms; t->dp_jobs = s.dp_jobs; t->dp_rows = s.dp_rows;
-    t->walk_ms = s.walk_ms; t->walk_launches = s.walk_launches;
+    t->walk_ms = s.walk_ms; t->walk_launches = s.walk_launches; t->dp_thread_rows = s.dp_thread_rows;
     return PBSC_OK;
 }
 

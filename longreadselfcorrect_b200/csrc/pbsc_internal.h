@@ -97,6 +97,7 @@ struct Timing
     uint64_t dp_jobs = 0, dp_rows = 0;
     float walk_ms = 0;                // walk_levels_kernel alone (CUDA events around each of its launches)
     uint64_t walk_launches = 0;
+    uint64_t dp_thread_rows = 0;      // rows aligned by dp_align_thread_kernel
 };
 Timing& last_timing();
 

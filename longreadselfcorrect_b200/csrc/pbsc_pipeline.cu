@@ -115,7 +115,7 @@ int pbsc_batch_run(pbsc_batch* bt, float* ms)
         T.total_ms = bt->h2d_ms + bt->seed_ms + bt->extend_ms;
         T.kernel_launches = bt->launches; T.seed_pairs = bt->walks;
         const DpStats& D = last_dp_stats();
-        T.dp_ms = D.ms; T.dp_jobs = D.jobs; T.dp_rows = D.rows;
+        T.dp_ms = D.ms; T.dp_jobs = D.jobs; T.dp_rows = D.rows; T.dp_thread_rows = D.thread_rows;
         if (D.bad) { set_error("DP fallback: %llu alignments or consensus buffers outside this build's limits", (unsigned long long)D.bad); rc = PBSC_ERR_LIMIT; }
     }
     done();

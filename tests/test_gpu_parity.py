@@ -277,9 +277,12 @@ def _summary_counters(stats):
 
 @pytest.mark.parametrize("name,kw", [("tiny", dict(coverage=30, genome=5)), ("tiny100", dict(coverage=100, genome=10))])
 @pytest.mark.parametrize("k0", [0, 13])
-def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, golden, name, kw, k0):
+@pytest.mark.parametrize("dp_kernel", ["thread", "warp"])
+def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, golden, name, kw, k0, dp_kernel, monkeypatch):
     """Default options: failed walks go through retrieveStr / extendMatch / MultipleAlignment on the GPU; fixtures written by
-    the reference binary (tests/golden/make_golden.py dp)."""
+    the reference binary (tests/golden/make_golden.py dp).  Both alignment kernels: one alignment per thread (default, with
+    the warp-per-row kernel taking what it leaves) and warp per row alone."""
+    monkeypatch.setenv("PBSC_DP_THREAD", "1" if dp_kernel == "thread" else "0")
     p = api.Params.make(no_dp=False, **kw)
     tiny_index.build_prefix_table(k0)
     out, poff, first, stats = tiny_index.correct_reads(p, [s for _, s in tiny_reads])
@@ -293,7 +296,9 @@ def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, go
     assert got["corrected_len"] == int(summ["CorrectedLen"].split(",")[0])
     assert got["total_walk_num"] == int(summ["TotalWalkNum"])
     assert got["seed_dis"] // got["total_walk_num"] == int(summ["DisBetweenSeeds"])
-    assert api.last_timing()["dp_jobs"] > 0
+    tm = api.last_timing()
+    assert tm["dp_jobs"] > 0
+    assert (tm["dp_thread_rows"] > 0) == (dp_kernel == "thread") and tm["dp_thread_rows"] <= tm["dp_rows"]
     tiny_index.build_prefix_table(0)
 
 
@@ -303,12 +308,14 @@ def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, go
     (9, ["-c", "30", "-g", "5"], dict(coverage=30, genome=5)),
     (9, ["-c", "30", "-g", "5", "--split"], dict(coverage=30, genome=5, split=True)),
 ])
-def test_dp_fallback_repeat_rich_vs_oracle(api, oracle_bin, tmp_path, cov, opts, kw, monkeypatch):
+@pytest.mark.parametrize("dp_kernel", ["thread", "warp"])
+def test_dp_fallback_repeat_rich_vs_oracle(api, oracle_bin, tmp_path, cov, opts, kw, dp_kernel, monkeypatch):
     """Repeat-rich data; the 9x set makes the fallback itself fail (three or fewer rows) so --split matters; a tiny chunk
     budget forces the chunked path."""
     from conftest import run_oracle
     from longreadselfcorrect_b200 import bwt_build, synth
     monkeypatch.setenv("PBSC_DP_CHUNK_MB", "8")
+    monkeypatch.setenv("PBSC_DP_THREAD", "1" if dp_kernel == "thread" else "0")
     g = synth.make_genome(15000, 23, repeat_families=1, tandem_arrays=3)
     codes, off = synth.simulate_reads(g, cov, 1200, 213, min_len=300)
     reads = synth.read_strings(codes, off)

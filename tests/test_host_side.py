@@ -64,6 +64,17 @@ def test_sort_emulation_matches_libstdcxx(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("ok")
 
 
+def test_thread_per_alignment_dp_matches_oracle_extendmatch(tmp_path):
+    """The fill / traceback templates that dp_align_thread_kernel instantiates (csrc/pbsc_dp_thread.cuh), compiled for the host
+    over accessors that mimic the device storage, against the oracle's Overlapper::extendMatch: forward and reverse-complement
+    placements, arbitrary band origins, clipped and unclipped bands, tie-rich two-letter and homopolymer strings."""
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-Wno-sign-compare", os.path.join(ROOT, "tests", "cpp", "test_dp_thread.cpp"),
+                    "-o", exe], check=True)
+    r = subprocess.run([exe, "12000"], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and " failed 0" in r.stdout, r.stdout
+
+
 def test_bwt_builder_equals_reference_index(oracle_bin, tmp_path):
     """The torch suffix sorter used for synthetic inputs yields the intervals of the reference's own (ropebwt2) index."""
     from longreadselfcorrect_b200 import bwt_build
