@@ -16,6 +16,7 @@
 //                       rows (see "column model" below)
 // Jobs are processed in chunks that fit a scratch budget (20 GB, or half of what is free).
 #include <cub/cub.cuh>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -526,15 +527,23 @@ dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, co
 }
 
 // ---- stage 2t: banded alignment, one alignment per thread (pbsc_dp_thread.cuh) -------------------------------------------
-// Rows whose every query column meets the matrix and whose query is at most DPT_QMAX long (nearly all of them) are sorted
-// by query length and aligned here, 32 rows of one length per warp; what is left stays `pass == 2` for dp_align_kernel.
-constexpr int DPT_QMAX = 256;                                                  // longest query of the thread kernel
-constexpr int DPT_NT = 128;                                                    // threads per block
-constexpr int DPT_HWORDS = dpt::HSLOTS / 2;                                    // 16-bit scores, two per word
-constexpr int DPT_SWORDS = (dpt::max_len_bound(DPT_QMAX) + 15) / 16 + 1;       // 2-bit read + one word of slack for bits()
-constexpr int DPT_SMEM = (DPT_HWORDS + DPT_SWORDS) * DPT_NT * 4;               // 75 776 B: three blocks per SM
-constexpr uint64_t DPT_ARENA_WORDS = 32ull * DPT_QMAX * dpt::WMAX;             // flag words of one warp's 32 rows
-constexpr uint32_t DPT_KEY_NONE = 0x7FFu;
+// Rows whose every query column meets the matrix are sorted by query length and aligned here, 32 rows of one length per
+// warp, in two passes of the same kernel: queries of at most 256 bases (80 % of the rows on config 2) with 128 threads per
+// block, three blocks per SM; longer ones up to 1024 bases with 64 threads per block (the 2-bit read in shared memory is
+// longer), four blocks per SM.  What is left (longer queries, reads that end early) stays `pass == 2` for dp_align_kernel.
+template <int QMAX_, int NT_>
+struct DptCfg
+{
+    static constexpr int QMAX = QMAX_;                                          // longest query
+    static constexpr int NT = NT_;                                              // threads per block
+    static constexpr int HWORDS = dpt::HSLOTS / 2;                              // 16-bit scores, two per word
+    static constexpr int SWORDS = (dpt::max_len_bound(QMAX_) + 15) / 16 + 1;    // 2-bit read + one word of slack for bits()
+    static constexpr int SMEM = (HWORDS + SWORDS) * NT_ * 4;
+};
+using DptShort = DptCfg<256, 128>;    // 75 776 B per block: three blocks (12 warps) per SM
+using DptLong = DptCfg<1024, 64>;     // 51 456 B per block: four blocks (8 warps) per SM
+constexpr uint32_t DPT_KEY_NONE = 0xFFFu;
+constexpr int DPT_KEY_BITS = 12;
 
 __device__ __forceinline__ int dp_row_origin(const DpRow& R, const DpJob& J)
 {
@@ -544,7 +553,7 @@ __device__ __forceinline__ int dp_row_origin(const DpRow& R, const DpJob& J)
     return (start_2 - start_1 + 1) - (DP_HALF + 1);
 }
 
-// sort key of a row: longest queries first, forward rows before reverse-complement rows; DPT_KEY_NONE = not for this kernel
+// sort key of a row: longest queries first, forward rows before reverse-complement rows; DPT_KEY_NONE = not for this pass
 __global__ void __launch_bounds__(256)
 dp_keys_kernel(uint64_t n_rows, const DpRow* __restrict__ rows, const DpJob* __restrict__ jobs, uint32_t* keys, uint32_t* order, int qmax,
                unsigned int* n_thread_rows)
@@ -566,32 +575,34 @@ dp_keys_kernel(uint64_t n_rows, const DpRow* __restrict__ rows, const DpJob* __r
     if (key != DPT_KEY_NONE && (threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(n_thread_rows, (unsigned)__popc(m));
 }
 
+template <class C>
 struct DptH   // previous column: 16-bit scores, slot j & 255, word (slot >> 1) of this thread's column of shared memory
 {
     uint32_t* p;
     __device__ __forceinline__ int get(int j) const
     {
         const int s = j & (dpt::HSLOTS - 1);
-        return (int)reinterpret_cast<const short*>(p + (s >> 1) * DPT_NT)[s & 1];
+        return (int)reinterpret_cast<const short*>(p + (s >> 1) * C::NT)[s & 1];
     }
     __device__ __forceinline__ void set(int j, int v)
     {
         const int s = j & (dpt::HSLOTS - 1);
-        reinterpret_cast<short*>(p + (s >> 1) * DPT_NT)[s & 1] = (short)v;
+        reinterpret_cast<short*>(p + (s >> 1) * C::NT)[s & 1] = (short)v;
     }
     // five aligned pairs from the even row j on: one base address, constant offsets
-    __device__ __forceinline__ bool pairs_ok(int j) const { return ((j >> 1) & (DPT_HWORDS - 1)) <= DPT_HWORDS - 5; }
-    __device__ __forceinline__ uint32_t get2(int j, int u) const { return p[((j >> 1) & (DPT_HWORDS - 1)) * DPT_NT + u * DPT_NT]; }
-    __device__ __forceinline__ void set2(int j, int u, uint32_t w) { p[((j >> 1) & (DPT_HWORDS - 1)) * DPT_NT + u * DPT_NT] = w; }
+    __device__ __forceinline__ bool pairs_ok(int j) const { return ((j >> 1) & (C::HWORDS - 1)) <= C::HWORDS - 5; }
+    __device__ __forceinline__ uint32_t get2(int j, int u) const { return p[((j >> 1) & (C::HWORDS - 1)) * C::NT + u * C::NT]; }
+    __device__ __forceinline__ void set2(int j, int u, uint32_t w) { p[((j >> 1) & (C::HWORDS - 1)) * C::NT + u * C::NT] = w; }
 };
+template <class C>
 struct DptS   // the retrieved read at 2 bits per base, 16 bases per word, in this thread's column of shared memory
 {
     const uint32_t* p;
-    __device__ __forceinline__ int base(int x) const { return (int)((p[(x >> 4) * DPT_NT] >> (2 * (x & 15))) & 3u); }
+    __device__ __forceinline__ int base(int x) const { return (int)((p[(x >> 4) * C::NT] >> (2 * (x & 15))) & 3u); }
     __device__ __forceinline__ uint32_t bits(int x) const
     {
-        const uint32_t* w = p + (x >> 4) * DPT_NT;
-        return __funnelshift_r(w[0], w[DPT_NT], 2 * (x & 15));   // shift < 32; bits 20.. are ignored by the caller
+        const uint32_t* w = p + (x >> 4) * C::NT;
+        return __funnelshift_r(w[0], w[C::NT], 2 * (x & 15));   // shift < 32; bits 20.. are ignored by the caller
     }
 };
 struct DptF   // flag words of this lane: word n of the lane at arena[n * 32 + lane] (a warp's stores coalesce)
@@ -603,17 +614,19 @@ struct DptF   // flag words of this lane: word n of the lane at arena[n * 32 + l
 struct DptQ { const uint8_t* q; __device__ __forceinline__ int operator()(int x) const { return (int)q[x]; } };
 struct DptOps { uint8_t* ops; __device__ __forceinline__ void put(int n, int op) { ops[n] = (uint8_t)op; } };
 
-__global__ void __launch_bounds__(DPT_NT, 3)
+// arena_words: flag words of one warp's 32 rows = 32 * (longest query of this pass) * WMAX
+template <class C>
+__global__ void __launch_bounds__(C::NT, 227 * 1024 / (C::SMEM + 1024))
 dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, DpRow* rows,
                        const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0, uint32_t* arenas,
-                       unsigned long long* counter, unsigned int* n_bad)
+                       uint64_t arena_words, unsigned long long* counter, unsigned int* n_bad)
 {
     extern __shared__ uint32_t dpt_smem[];
     const int lane = threadIdx.x & 31;
     uint32_t* Hs = dpt_smem + threadIdx.x;
-    uint32_t* Ss = dpt_smem + DPT_HWORDS * DPT_NT + threadIdx.x;
-    const uint64_t warp = (uint64_t)blockIdx.x * (DPT_NT / 32) + (threadIdx.x >> 5);
-    DptF F{arenas + warp * DPT_ARENA_WORDS + lane};
+    uint32_t* Ss = dpt_smem + C::HWORDS * C::NT + threadIdx.x;
+    const uint64_t warp = (uint64_t)blockIdx.x * (C::NT / 32) + (threadIdx.x >> 5);
+    DptF F{arenas + warp * arena_words + lane};
     for (;;)
     {
         unsigned long long base = 0;
@@ -635,13 +648,13 @@ dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const
             uint32_t w = 0;
             const int m = min(16, g.mlen - x);
             for (int y = 0; y < m; y++) w |= (uint32_t)g.s2[x + y] << (2 * y);
-            Ss[(x >> 4) * DPT_NT] = w;
+            Ss[(x >> 4) * C::NT] = w;
         }
-        Ss[((g.mlen + 15) >> 4) * DPT_NT] = 0u;
+        Ss[((g.mlen + 15) >> 4) * C::NT] = 0u;
         #pragma unroll 8
-        for (int x = 0; x < DPT_HWORDS; x++) Hs[x * DPT_NT] = 0u;
-        DptH H{Hs};
-        const DptS S{Ss};
+        for (int x = 0; x < C::HWORDS; x++) Hs[x * C::NT] = 0u;
+        DptH<C> H{Hs};
+        const DptS<C> S{Ss};
         const DptQ q{g.q};
         int bi, bj;
         dpt::fill(g.qlen, g.mlen, g.origin, H, S, F, q, bi, bj);
@@ -675,12 +688,36 @@ dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const
 // consensus only needs, per column, how many rows show A/C/G/T/'-' there.  A new column inserted before base column p gets a
 // '-' from every row that already spans it: rows covering base column p minus rows whose first column IS base column p
 // (MultipleAlignmentElement::insertGapBeforeColumn, multiple_alignment.cpp:112-134).
-__global__ void __launch_bounds__(64)
-dp_msa_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, WalkTask* tasks, const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem,
-              uint64_t mem0, uint8_t* outpool, unsigned int* n_bad)
+// Jobs of a chunk in order of decreasing work (alignment columns of the rows that passed the filters): a warp of the
+// thread-per-job kernel below lasts as long as its longest job and the launch as long as its last warp, so neighbours
+// should be alike and the long ones should start first.
+__global__ void __launch_bounds__(128)
+dp_job_keys_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, const DpRow* __restrict__ rows, uint64_t row_base, uint32_t* keys,
+                   uint32_t* order)
 {
-    const uint64_t jx = j0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (jx >= j1) return;
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j0 + t >= j1) return;
+    const DpJob J = jobs[j0 + t];
+    const uint32_t nr = job_rows_of(J);
+    const DpRow* R = rows + (J.row0 - row_base);
+    uint32_t passing = 0, cost = 0;
+    for (uint32_t r = 0; r < nr; r++)
+    {
+        const DpRow x = R[r];
+        if (x.pass == 1) { passing++; cost += x.nops; }
+    }
+    if (passing < 3) cost = 0;
+    keys[t] = 0xFFFFu - min(0xFFFFu, cost >> 3);
+    order[t] = (uint32_t)t;
+}
+
+__global__ void __launch_bounds__(64)
+dp_msa_kernel(uint64_t j0, uint64_t j1, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, WalkTask* tasks,
+              const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem, uint64_t mem0, uint8_t* outpool, unsigned int* n_bad)
+{
+    const uint64_t tx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j0 + tx >= j1) return;
+    const uint64_t jx = j0 + (order ? order[tx] : tx);
     const DpJob J = jobs[jx];
     WalkTask& tk = tasks[J.task];
     const uint32_t nr = job_rows_of(J);
@@ -886,23 +923,72 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     uint32_t *tkeys = nullptr, *tkeys2 = nullptr, *torder = nullptr, *torder2 = nullptr, *tslabs = nullptr;
     uint8_t* sort_tmp = nullptr;
     size_t sort_bytes = 0;
-    int tblocks = 0;
+    int tblocks_s = 0, tblocks_l = 0;
+    // queries of this stage are at most q_cap long
+    const uint64_t tq_s = std::min<uint64_t>(DptShort::QMAX, q_cap), tq_l = std::min<uint64_t>(DptLong::QMAX, q_cap);
+    const uint64_t tarena_s = 32ull * tq_s * dpt::WMAX, tarena_l = 32ull * tq_l * dpt::WMAX;
+    const bool use_long = use_thread && q_cap > (uint32_t)DptShort::QMAX && !(getenv("PBSC_DPT_LONG") && atoi(getenv("PBSC_DPT_LONG")) == 0);
     if (use_thread)
     {
-        PBSC_CUDA(cudaFuncSetAttribute(dp_align_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPT_SMEM));
-        int tper_sm = 0;
-        PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tper_sm, dp_align_thread_kernel, DPT_NT, DPT_SMEM));
-        if (tper_sm < 1) tper_sm = 1;
-        if (const char* e = getenv("PBSC_DPT_BLOCKS_PER_SM")) { if (atoi(e) > 0) tper_sm = std::min(tper_sm, atoi(e)); }
-        tblocks = idx->sm_count * tper_sm;
+        PBSC_CUDA(cudaFuncSetAttribute(dp_align_thread_kernel<DptShort>, cudaFuncAttributeMaxDynamicSharedMemorySize, DptShort::SMEM));
+        PBSC_CUDA(cudaFuncSetAttribute(dp_align_thread_kernel<DptLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, DptLong::SMEM));
+        int per = 0;
+        PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dp_align_thread_kernel<DptShort>, DptShort::NT, DptShort::SMEM));
+        if (const char* e = getenv("PBSC_DPT_BLOCKS_PER_SM")) { if (atoi(e) > 0) per = std::min(per, atoi(e)); }
+        tblocks_s = idx->sm_count * std::max(per, 1);
+        PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dp_align_thread_kernel<DptLong>, DptLong::NT, DptLong::SMEM));
+        tblocks_l = idx->sm_count * std::max(per, 1);
         PBSC_CUDA(arena(idx, "dp.tkeys", max_rows, &tkeys));
         PBSC_CUDA(arena(idx, "dp.tkeys2", max_rows, &tkeys2));
         PBSC_CUDA(arena(idx, "dp.torder", max_rows, &torder));
         PBSC_CUDA(arena(idx, "dp.torder2", max_rows, &torder2));
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, tkeys, tkeys2, torder, torder2, (int)max_rows, 0, 11, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, tkeys, tkeys2, torder, torder2, (int)max_rows, 0, DPT_KEY_BITS, st);
         PBSC_CUDA(arena(idx, "dp.sorttmp", sort_bytes, &sort_tmp));
-        PBSC_CUDA(arena(idx, "dp.tflags", DPT_ARENA_WORDS * (uint64_t)tblocks * (DPT_NT / 32), &tslabs));
+        uint64_t words = tarena_s * (uint64_t)tblocks_s * (DptShort::NT / 32);
+        if (use_long) words = std::max(words, tarena_l * (uint64_t)tblocks_l * (DptLong::NT / 32));
+        PBSC_CUDA(arena(idx, "dp.tflags", words, &tslabs));
     }
+    // job order of the multiple-alignment kernel
+    bool sort_jobs = true;
+    if (const char* e = getenv("PBSC_DP_SORT_JOBS")) sort_jobs = atoi(e) != 0;
+    uint32_t *jkeys = nullptr, *jkeys2 = nullptr, *jord = nullptr, *jord2 = nullptr;
+    uint8_t* jsort_tmp = nullptr;
+    size_t jsort_bytes = 0;
+    if (sort_jobs)
+    {
+        PBSC_CUDA(arena(idx, "dp.jkeys", nj, &jkeys));
+        PBSC_CUDA(arena(idx, "dp.jkeys2", nj, &jkeys2));
+        PBSC_CUDA(arena(idx, "dp.jord", nj, &jord));
+        PBSC_CUDA(arena(idx, "dp.jord2", nj, &jord2));
+        cub::DeviceRadixSort::SortPairs(nullptr, jsort_bytes, jkeys, jkeys2, jord, jord2, (int)nj, 0, 16, st);
+        PBSC_CUDA(arena(idx, "dp.jsorttmp", jsort_bytes, &jsort_tmp));
+    }
+    // PBSC_DP_PROFILE=1: per-kernel CUDA-event times of this stage on stderr (diagnostics, off by default)
+    struct Prof
+    {
+        bool on = false; cudaStream_t st; std::vector<std::pair<const char*, cudaEvent_t>> ev;
+        void mark(const char* name) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.emplace_back(name, e); }
+        void report()
+        {
+            if (!on || ev.size() < 2) return;
+            cudaEventSynchronize(ev.back().second);
+            std::vector<std::pair<const char*, float>> acc;
+            for (size_t x = 1; x < ev.size(); x++)
+            {
+                float ms = 0; cudaEventElapsedTime(&ms, ev[x - 1].second, ev[x].second);
+                bool found = false;
+                for (auto& a : acc) if (!strcmp(a.first, ev[x].first)) { a.second += ms; found = true; }
+                if (!found) acc.emplace_back(ev[x].first, ms);
+            }
+            fprintf(stderr, "[pbsc dp profile]");
+            for (auto& a : acc) fprintf(stderr, " %s %.1f ms;", a.first, a.second);
+            fprintf(stderr, "\n");
+            for (auto& e : ev) cudaEventDestroy(e.second);
+        }
+    } prof;
+    prof.st = st;
+    if (const char* e = getenv("PBSC_DP_PROFILE")) prof.on = atoi(e) != 0;
+    prof.mark("start");
     for (uint64_t j0 = 0; j0 < nj;)
     {
         uint64_t j1 = j0 + 1;
@@ -910,25 +996,55 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         const uint64_t nrows = h_row[j1] - h_row[j0], njc = j1 - j0;
         dp_rows_kernel<<<(unsigned)((njc + 127) / 128), 128, 0, st>>>(j0, j1, jobs, tasks, b.codes.p, b.offsets.p, mem, h_mem[j0], rows, h_row[j0]);
         dp_retrieve_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(idx->dev, nrows, rows, jobs, mem, h_mem[j0]);
+        prof.mark("rows+retrieve");
         PBSC_CUDA(cudaMemsetAsync(qctr, 0, 16, st));
         if (use_thread)
         {
-            dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, tkeys, torder, DPT_QMAX, cnt + 2);
+            dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, tkeys, torder, (int)tq_s, cnt + 2);
             size_t sb = sort_bytes;
-            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, tkeys, tkeys2, torder, torder2, (int)nrows, 0, 11, st);
-            const int tb = (int)std::min<uint64_t>((uint64_t)tblocks, (nrows + DPT_NT - 1) / DPT_NT);
-            dp_align_thread_kernel<<<tb, DPT_NT, DPT_SMEM, st>>>(nrows, tkeys2, torder2, rows, jobs, tasks, mem, h_mem[j0], tslabs, qctr + 1, cnt + 1);
-            if (launches) *launches += 4;   // keys, two radix passes at most (counted as the sort's kernels), alignment
+            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, tkeys, tkeys2, torder, torder2, (int)nrows, 0, DPT_KEY_BITS, st);
+            prof.mark("keys+sort");
+            const int tb = (int)std::min<uint64_t>((uint64_t)tblocks_s, (nrows + DptShort::NT - 1) / DptShort::NT);
+            dp_align_thread_kernel<DptShort><<<tb, DptShort::NT, DptShort::SMEM, st>>>(nrows, tkeys2, torder2, rows, jobs, tasks, mem, h_mem[j0], tslabs,
+                                                                                      tarena_s, qctr + 1, cnt + 1);
+            prof.mark("align_thread");
+            if (launches) *launches += 4;   // keys, the sort's kernels counted as two, alignment
+        }
+        if (use_long)
+        {
+            // the rows the first pass left: longer queries
+            PBSC_CUDA(cudaMemsetAsync(qctr + 1, 0, 8, st));
+            dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, tkeys, torder, (int)tq_l, cnt + 2);
+            size_t sb = sort_bytes;
+            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, tkeys, tkeys2, torder, torder2, (int)nrows, 0, DPT_KEY_BITS, st);
+            prof.mark("keys+sort");
+            const int tb = (int)std::min<uint64_t>((uint64_t)tblocks_l, (nrows + DptLong::NT - 1) / DptLong::NT);
+            dp_align_thread_kernel<DptLong><<<tb, DptLong::NT, DptLong::SMEM, st>>>(nrows, tkeys2, torder2, rows, jobs, tasks, mem, h_mem[j0], tslabs,
+                                                                                    tarena_l, qctr + 1, cnt + 1);
+            prof.mark("align_thread_long");
+            if (launches) *launches += 4;
         }
         const int nb = (int)std::min<uint64_t>((uint64_t)ablocks, (nrows + DP_WARPS * 32 - 1) / (DP_WARPS * 32));
         dp_align_kernel<<<nb, DP_WARPS * 32, 0, st>>>(nrows, rows, jobs, tasks, mem, h_mem[j0], slabs, arena_words, qctr, cnt + 1);
-        dp_msa_kernel<<<(unsigned)((njc + 63) / 64), 64, 0, st>>>(j0, j1, jobs, tasks, rows, h_row[j0], mem, h_mem[j0], outpool, cnt + 1);
+        prof.mark("align_warp");
+        const uint32_t* jorder = nullptr;
+        if (sort_jobs)
+        {
+            dp_job_keys_kernel<<<(unsigned)((njc + 127) / 128), 128, 0, st>>>(j0, j1, jobs, rows, h_row[j0], jkeys, jord);
+            size_t sb = jsort_bytes;
+            cub::DeviceRadixSort::SortPairs(jsort_tmp, sb, jkeys, jkeys2, jord, jord2, (int)njc, 0, 16, st);
+            jorder = jord2;
+            if (launches) *launches += 3;
+        }
+        dp_msa_kernel<<<(unsigned)((njc + 63) / 64), 64, 0, st>>>(j0, j1, jorder, jobs, tasks, rows, h_row[j0], mem, h_mem[j0], outpool, cnt + 1);
+        prof.mark("msa");
         PBSC_CUDA(cudaGetLastError());
         if (launches) *launches += 4;
         S.chunks++;
         j0 = j1;
     }
     PBSC_CUDA(cudaEventRecord(ev[1], st));
+    prof.report();
     PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 12, cudaMemcpyDeviceToHost, st));
     PBSC_CUDA(cudaStreamSynchronize(st));
     S.bad += hcnt[1];
