@@ -688,9 +688,10 @@ dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const
 // consensus only needs, per column, how many rows show A/C/G/T/'-' there.  A new column inserted before base column p gets a
 // '-' from every row that already spans it: rows covering base column p minus rows whose first column IS base column p
 // (MultipleAlignmentElement::insertGapBeforeColumn, multiple_alignment.cpp:112-134).
-// Jobs of a chunk in order of decreasing work (alignment columns of the rows that passed the filters): a warp of the
-// thread-per-job kernel below lasts as long as its longest job and the launch as long as its last warp, so neighbours
-// should be alike and the long ones should start first.
+// EXPERIMENT (PBSC_DP_SORT_JOBS, off by default): jobs of a chunk in order of decreasing work (alignment columns of the rows
+// that passed the filters), optionally dealt out across warps (warp w, lane l takes rank l * n_warps + w) so that every warp
+// holds one job of each weight class.  Measured on config 2: natural order 78 ms, dealt out 134 ms, plainly sorted 189 ms —
+// the thread-per-job kernel is bound by the locality of its scattered scratch accesses, not by its longest job.
 __global__ void __launch_bounds__(128)
 dp_job_keys_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, const DpRow* __restrict__ rows, uint64_t row_base, uint32_t* keys,
                    uint32_t* order)
@@ -712,12 +713,20 @@ dp_job_keys_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, con
 }
 
 __global__ void __launch_bounds__(64)
-dp_msa_kernel(uint64_t j0, uint64_t j1, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, WalkTask* tasks,
+dp_msa_kernel(uint64_t j0, uint64_t j1, const uint32_t* __restrict__ order, int deal, const DpJob* __restrict__ jobs, WalkTask* tasks,
               const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem, uint64_t mem0, uint8_t* outpool, unsigned int* n_bad)
 {
     const uint64_t tx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (j0 + tx >= j1) return;
-    const uint64_t jx = j0 + (order ? order[tx] : tx);
+    const uint64_t njc = j1 - j0;
+    uint64_t rank = tx;
+    if (order && deal)
+    {
+        const uint64_t n_warps = (njc + 31) / 32;
+        rank = (tx & 31) * n_warps + (tx >> 5);
+        if (tx >= n_warps * 32) return;
+    }
+    if (rank >= njc) return;
+    const uint64_t jx = j0 + (order ? order[rank] : rank);
     const DpJob J = jobs[jx];
     WalkTask& tk = tasks[J.task];
     const uint32_t nr = job_rows_of(J);
@@ -949,8 +958,10 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         PBSC_CUDA(arena(idx, "dp.tflags", words, &tslabs));
     }
     // job order of the multiple-alignment kernel
-    bool sort_jobs = true;
-    if (const char* e = getenv("PBSC_DP_SORT_JOBS")) sort_jobs = atoi(e) != 0;
+    // 0: natural order (default: neighbouring threads work on neighbouring scratch, which is what this memory-bound kernel
+    // wants: 78 ms on config 2), 1: sorted by work and dealt out across warps (134 ms), 2: sorted (189 ms)
+    int sort_jobs = 0;
+    if (const char* e = getenv("PBSC_DP_SORT_JOBS")) sort_jobs = atoi(e);
     uint32_t *jkeys = nullptr, *jkeys2 = nullptr, *jord = nullptr, *jord2 = nullptr;
     uint8_t* jsort_tmp = nullptr;
     size_t jsort_bytes = 0;
@@ -1036,7 +1047,8 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
             jorder = jord2;
             if (launches) *launches += 3;
         }
-        dp_msa_kernel<<<(unsigned)((njc + 63) / 64), 64, 0, st>>>(j0, j1, jorder, jobs, tasks, rows, h_row[j0], mem, h_mem[j0], outpool, cnt + 1);
+        dp_msa_kernel<<<(unsigned)((((njc + 31) / 32) * 32 + 63) / 64), 64, 0, st>>>(j0, j1, jorder, sort_jobs == 1, jobs, tasks, rows, h_row[j0], mem,
+                                                                                         h_mem[j0], outpool, cnt + 1);
         prof.mark("msa");
         PBSC_CUDA(cudaGetLastError());
         if (launches) *launches += 4;

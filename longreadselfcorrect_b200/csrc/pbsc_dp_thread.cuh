@@ -18,9 +18,9 @@
 //     and the cell exists;
 //   * the traceback compares the cell with ALL in-band neighbours (also the ones the fill ignored), a neighbour outside the
 //     band never compares equal; its three tie-break orders are the reference's (:620-680).
-// Only rows for which every column of the query meets the matrix are eligible (`eligible`): then a computed cell only ever
-// reads computed cells or row 0, and an in-place array indexed by the matrix row reproduces the zero-initialised table.  The
-// rest (queries longer than QMAX, reads that end early) stay with the warp-per-row kernel.
+// A computed cell only ever reads cells computed in the previous column, row 0, or (first computed column) cells nothing has
+// written yet, so an in-place array indexed by the matrix row reproduces the zero-initialised table.  Queries longer than
+// QMAX stay with the warp-per-row kernel.
 #ifndef PBSC_DP_THREAD_CUH
 #define PBSC_DP_THREAD_CUH
 
@@ -58,12 +58,12 @@ PBSC_DPT_HD int imin(int a, int b) { return a < b ? a : b; }
 // longest read retrieved for a query of qmax bases: query.length()*1.1+20 (LongReadOverlap.cpp:611), rounded up
 PBSC_DPT_HD constexpr int max_len_bound(int qmax) { return qmax + qmax / 10 + 21; }
 
-// every column 1..qlen computes at least one cell (the reference's `continue` at overlapper.cpp:470-471 is never taken) and
-// the scores fit 16 bits (|score| <= 8 * qlen)
-PBSC_DPT_HD bool eligible(int qlen, int mlen, int origin, int qmax)
-{
-    return qlen >= 1 && qlen <= qmax && mlen >= 1 && mlen <= max_len_bound(qmax) && origin >= -(BW - 1) && origin + qlen <= mlen;
-}
+// the scores fit 16 bits (|score| <= 8 * qlen) and the read fits its shared-memory slot.  Columns whose band misses the
+// matrix (the reference's `continue`, overlapper.cpp:470-471) can only be the first ones (band above the matrix) or the
+// last ones (band below it); the fill skips them like the reference: the first computed column then reads a column array
+// that is still all zero, like the reference's zero-initialised table, and nothing reads the trailing ones (the traceback
+// starts in a computed cell and leaves the matrix before it could enter a skipped column).
+PBSC_DPT_HD bool eligible(int qlen, int mlen, int /*origin*/, int qmax) { return qlen >= 1 && qlen <= qmax && mlen >= 1 && mlen <= max_len_bound(qmax); }
 // flag words per column: ordinals count from the even row at or below the first computed one, the widest column has
 // min(201, mlen) cells
 PBSC_DPT_HD int words_per_col(int mlen) { return (imin(BW, mlen) + 1 + CPW - 1) / CPW; }
@@ -91,6 +91,7 @@ PBSC_DPT_HD void fill(int qlen, int mlen, int origin, HS& H, const SS& S, FS& F,
         const int jb = origin + i;
         const int first = imax(jb, 1);
         const int last = imin(jb + BW, nRows) - 1;
+        if (last < first) continue;   // the band misses the matrix
         const int c1 = q(i - 1);
         const uint32_t c1rep = (uint32_t)c1 * 0x55555u;
         int j = first;

@@ -105,7 +105,7 @@ int main(int argc, char** argv)
         int start_1 = isRC ? qlen - k : 0, start_2 = isRC ? mlen - k : 0;
         // arbitrary band placements (not only the two the caller uses): first column down to one cell at band row 200, last
         // column down to one cell at band row 0
-        if (it % 13 == 12 && mlen - qlen >= -(BW - 1)) { start_1 = 0; start_2 = rnd(-(BW - 1), mlen - qlen) + HALF; }
+        if (it % 13 == 12) { start_1 = 0; start_2 = rnd(-(BW - 1) - qlen / 2, std::max(mlen - qlen, 0) + qlen / 2) + HALF; }   // also bands that miss the matrix
         const int origin = (start_2 - start_1 + 1) - (HALF + 1);
         if (!eligible(qlen, mlen, origin, qmax)) { skipped++; continue; }
         tested++;
