@@ -144,6 +144,7 @@ dp_collect_kernel(const __grid_constant__ FmIndexDev idx, uint64_t n_items, cons
     J.task = (uint32_t)ti; J.qlen = qlen; J.k = k; J.maxLen = dp_max_len(qlen);
     J.row0 = 0; J.mem = 0;
     const unsigned int j = atomicAdd(n_jobs, 1u);
+    atomicMax(n_jobs + 3, qlen);   // longest query of this stage (sizes the alignment passes)
     jobs[j] = J;
     job_rows[j] = rows;
     job_bytes[j] = dp_job_bytes(qlen, J.maxLen, rows);
@@ -528,9 +529,10 @@ dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, co
 
 // ---- stage 2t: banded alignment, one alignment per thread (pbsc_dp_thread.cuh) -------------------------------------------
 // Rows whose every query column meets the matrix are sorted by query length and aligned here, 32 rows of one length per
-// warp, in two passes of the same kernel: queries of at most 256 bases (80 % of the rows on config 2) with 128 threads per
-// block, three blocks per SM; longer ones up to 1024 bases with 64 threads per block (the 2-bit read in shared memory is
-// longer), four blocks per SM.  What is left (longer queries, reads that end early) stays `pass == 2` for dp_align_kernel.
+// warp, in up to three passes of the same kernel: queries of at most 256 bases (80 % of the rows on config 2) with 128
+// threads per block, three blocks per SM; longer ones up to 1024 bases with 64 threads per block (the 2-bit read in shared
+// memory is longer), four blocks per SM; up to 4000 bases (the 16-bit score limit) with one warp per block.  What is left
+// stays `pass == 2` for dp_align_kernel.
 template <int QMAX_, int NT_>
 struct DptCfg
 {
@@ -542,8 +544,9 @@ struct DptCfg
 };
 using DptShort = DptCfg<256, 128>;    // 75 776 B per block: three blocks (12 warps) per SM
 using DptLong = DptCfg<1024, 64>;     // 51 456 B per block: four blocks (8 warps) per SM
-constexpr uint32_t DPT_KEY_NONE = 0xFFFu;
-constexpr int DPT_KEY_BITS = 12;
+using DptHuge = DptCfg<4000, 32>;     // 51 968 B per block: four blocks (4 warps) per SM; 8 * 4000 still fits 16 bits
+constexpr uint32_t DPT_KEY_NONE = 0x3FFFu;
+constexpr int DPT_KEY_BITS = 14;
 
 __device__ __forceinline__ int dp_row_origin(const DpRow& R, const DpJob& J)
 {
@@ -836,6 +839,38 @@ static cudaError_t arena(pbsc_index* idx, const char* name, size_t count, T** ou
 
 DpStats& last_dp_stats() { static thread_local DpStats s; return s; }
 
+// one pass of dp_align_thread_kernel<C>: queries of at most min(C::QMAX, longest query of the stage) bases
+struct DptPass { bool on = false; uint64_t qmax = 0, arena_words = 0; int blocks = 0; uint64_t flag_words() const { return on ? arena_words * (uint64_t)blocks : 0; } };
+template <class C>
+static cudaError_t dpt_pass_setup(pbsc_index* idx, uint64_t q_longest, uint64_t q_prev_max, int cap_per_sm, DptPass& g)
+{
+    g.on = q_longest > q_prev_max;   // something is left for this pass
+    if (!g.on) return cudaSuccess;
+    g.qmax = std::min<uint64_t>((uint64_t)C::QMAX, q_longest);
+    g.arena_words = 32ull * g.qmax * dpt::WMAX;
+    cudaError_t e = cudaFuncSetAttribute(dp_align_thread_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    int per = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dp_align_thread_kernel<C>, C::NT, C::SMEM);
+    if (e != cudaSuccess) return e;
+    if (cap_per_sm > 0) per = std::min(per, cap_per_sm);
+    g.blocks = idx->sm_count * std::max(per, 1);
+    g.arena_words *= (uint64_t)(C::NT / 32);   // per block
+    return cudaSuccess;
+}
+template <class C>
+static void dpt_pass_launch(const DptPass& g, cudaStream_t st, uint64_t nrows, DpRow* rows, const DpJob* jobs, const WalkTask* tasks, uint8_t* mem,
+                            uint64_t mem0, uint32_t* keys, uint32_t* keys2, uint32_t* order, uint32_t* order2, uint8_t* sort_tmp, size_t sort_bytes,
+                            uint32_t* slabs, unsigned long long* counter, unsigned int* cnt)
+{
+    cudaMemsetAsync(counter, 0, 8, st);
+    dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, keys, order, (int)g.qmax, cnt + 2);
+    cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys2, order, order2, (int)nrows, 0, DPT_KEY_BITS, st);
+    const int tb = (int)std::min<uint64_t>((uint64_t)g.blocks, (nrows + C::NT - 1) / C::NT);
+    dp_align_thread_kernel<C><<<tb, C::NT, C::SMEM, st>>>(nrows, keys2, order2, rows, jobs, tasks, mem, mem0, slabs, g.arena_words / (C::NT / 32), counter,
+                                                          cnt + 1);
+}
+
 int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void* tasks_v, uint64_t n_items, const uint32_t* list, uint8_t* outpool,
                     uint32_t q_cap, uint64_t* launches)
 {
@@ -857,8 +892,8 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     PBSC_CUDA(cudaEventRecord(ev[0], st));
     dp_collect_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, n_items, list, tasks, b.codes.p, b.offsets.p, (uint32_t)p->pb_coverage,
                                                                         jobs, job_rows, job_bytes, cnt);
-    unsigned int hcnt[3] = {0, 0, 0};
-    PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+    unsigned int hcnt[4] = {0, 0, 0, 0};
+    PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 16, cudaMemcpyDeviceToHost, st));
     PBSC_CUDA(cudaStreamSynchronize(st));
     if (launches) *launches += 1;
     const uint64_t nj = hcnt[0];
@@ -932,30 +967,24 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     uint32_t *tkeys = nullptr, *tkeys2 = nullptr, *torder = nullptr, *torder2 = nullptr, *tslabs = nullptr;
     uint8_t* sort_tmp = nullptr;
     size_t sort_bytes = 0;
-    int tblocks_s = 0, tblocks_l = 0;
-    // queries of this stage are at most q_cap long
-    const uint64_t tq_s = std::min<uint64_t>(DptShort::QMAX, q_cap), tq_l = std::min<uint64_t>(DptLong::QMAX, q_cap);
-    const uint64_t tarena_s = 32ull * tq_s * dpt::WMAX, tarena_l = 32ull * tq_l * dpt::WMAX;
-    const bool use_long = use_thread && q_cap > (uint32_t)DptShort::QMAX && !(getenv("PBSC_DPT_LONG") && atoi(getenv("PBSC_DPT_LONG")) == 0);
+    // the longest query of this stage decides which passes run and how large their flag arenas are
+    const uint64_t q_longest = std::min<uint64_t>(q_cap, hcnt[3]);
+    DptPass pass_s, pass_l, pass_h;
     if (use_thread)
     {
-        PBSC_CUDA(cudaFuncSetAttribute(dp_align_thread_kernel<DptShort>, cudaFuncAttributeMaxDynamicSharedMemorySize, DptShort::SMEM));
-        PBSC_CUDA(cudaFuncSetAttribute(dp_align_thread_kernel<DptLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, DptLong::SMEM));
-        int per = 0;
-        PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dp_align_thread_kernel<DptShort>, DptShort::NT, DptShort::SMEM));
-        if (const char* e = getenv("PBSC_DPT_BLOCKS_PER_SM")) { if (atoi(e) > 0) per = std::min(per, atoi(e)); }
-        tblocks_s = idx->sm_count * std::max(per, 1);
-        PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dp_align_thread_kernel<DptLong>, DptLong::NT, DptLong::SMEM));
-        tblocks_l = idx->sm_count * std::max(per, 1);
+        int cap = 0;
+        if (const char* e = getenv("PBSC_DPT_BLOCKS_PER_SM")) cap = atoi(e);
+        const bool longer = !(getenv("PBSC_DPT_LONG") && atoi(getenv("PBSC_DPT_LONG")) == 0);
+        PBSC_CUDA(dpt_pass_setup<DptShort>(idx, q_longest, 0, cap, pass_s));
+        if (longer) PBSC_CUDA(dpt_pass_setup<DptLong>(idx, q_longest, DptShort::QMAX, 0, pass_l));
+        if (longer) PBSC_CUDA(dpt_pass_setup<DptHuge>(idx, q_longest, DptLong::QMAX, 0, pass_h));
         PBSC_CUDA(arena(idx, "dp.tkeys", max_rows, &tkeys));
         PBSC_CUDA(arena(idx, "dp.tkeys2", max_rows, &tkeys2));
         PBSC_CUDA(arena(idx, "dp.torder", max_rows, &torder));
         PBSC_CUDA(arena(idx, "dp.torder2", max_rows, &torder2));
         cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, tkeys, tkeys2, torder, torder2, (int)max_rows, 0, DPT_KEY_BITS, st);
         PBSC_CUDA(arena(idx, "dp.sorttmp", sort_bytes, &sort_tmp));
-        uint64_t words = tarena_s * (uint64_t)tblocks_s * (DptShort::NT / 32);
-        if (use_long) words = std::max(words, tarena_l * (uint64_t)tblocks_l * (DptLong::NT / 32));
-        PBSC_CUDA(arena(idx, "dp.tflags", words, &tslabs));
+        PBSC_CUDA(arena(idx, "dp.tflags", std::max(pass_s.flag_words(), std::max(pass_l.flag_words(), pass_h.flag_words())), &tslabs));
     }
     // job order of the multiple-alignment kernel
     // 0: natural order (default: neighbouring threads work on neighbouring scratch, which is what this memory-bound kernel
@@ -1009,30 +1038,26 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         dp_retrieve_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(idx->dev, nrows, rows, jobs, mem, h_mem[j0]);
         prof.mark("rows+retrieve");
         PBSC_CUDA(cudaMemsetAsync(qctr, 0, 16, st));
-        if (use_thread)
+        if (pass_s.on)
         {
-            dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, tkeys, torder, (int)tq_s, cnt + 2);
-            size_t sb = sort_bytes;
-            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, tkeys, tkeys2, torder, torder2, (int)nrows, 0, DPT_KEY_BITS, st);
-            prof.mark("keys+sort");
-            const int tb = (int)std::min<uint64_t>((uint64_t)tblocks_s, (nrows + DptShort::NT - 1) / DptShort::NT);
-            dp_align_thread_kernel<DptShort><<<tb, DptShort::NT, DptShort::SMEM, st>>>(nrows, tkeys2, torder2, rows, jobs, tasks, mem, h_mem[j0], tslabs,
-                                                                                      tarena_s, qctr + 1, cnt + 1);
-            prof.mark("align_thread");
+            dpt_pass_launch<DptShort>(pass_s, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,
+                                      qctr + 1, cnt);
+            prof.mark("align_thread_256");
             if (launches) *launches += 4;   // keys, the sort's kernels counted as two, alignment
         }
-        if (use_long)
+        if (pass_l.on)
         {
             // the rows the first pass left: longer queries
-            PBSC_CUDA(cudaMemsetAsync(qctr + 1, 0, 8, st));
-            dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, tkeys, torder, (int)tq_l, cnt + 2);
-            size_t sb = sort_bytes;
-            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, tkeys, tkeys2, torder, torder2, (int)nrows, 0, DPT_KEY_BITS, st);
-            prof.mark("keys+sort");
-            const int tb = (int)std::min<uint64_t>((uint64_t)tblocks_l, (nrows + DptLong::NT - 1) / DptLong::NT);
-            dp_align_thread_kernel<DptLong><<<tb, DptLong::NT, DptLong::SMEM, st>>>(nrows, tkeys2, torder2, rows, jobs, tasks, mem, h_mem[j0], tslabs,
-                                                                                    tarena_l, qctr + 1, cnt + 1);
-            prof.mark("align_thread_long");
+            dpt_pass_launch<DptLong>(pass_l, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,
+                                     qctr + 1, cnt);
+            prof.mark("align_thread_1024");
+            if (launches) *launches += 4;
+        }
+        if (pass_h.on)
+        {
+            dpt_pass_launch<DptHuge>(pass_h, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,
+                                     qctr + 1, cnt);
+            prof.mark("align_thread_4000");
             if (launches) *launches += 4;
         }
         const int nb = (int)std::min<uint64_t>((uint64_t)ablocks, (nrows + DP_WARPS * 32 - 1) / (DP_WARPS * 32));

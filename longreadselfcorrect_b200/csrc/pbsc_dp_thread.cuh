@@ -42,14 +42,14 @@ constexpr int NEVER = -(1 << 28);      // a neighbour that is not there: never t
 constexpr int OP_M = 0, OP_I = 1, OP_D = 2;
 constexpr int HSLOTS = 256;            // circular previous-column array: the live rows are [jb - 1, jb + 200]
 
-// append "v == x" to a word of flags, for v >= x: v - x - 1 is negative exactly when they are equal, and its sign bit is
-// shifted in by one funnel shift
-PBSC_DPT_HD uint32_t push_eq(uint32_t w, int v, int x)
+// append "v != x" to a word of flags, for v >= x: x - v is negative exactly when they differ, and its sign bit is shifted in
+// by one funnel shift (the caller inverts the finished word)
+PBSC_DPT_HD uint32_t push_ne(uint32_t w, int v, int x)
 {
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_l((uint32_t)(v - x - 1), w, 1);
+    return __funnelshift_l((uint32_t)(x - v), w, 1);
 #else
-    return (w << 1) | ((uint32_t)(v - x - 1) >> 31);
+    return (w << 1) | ((uint32_t)(x - v) >> 31);
 #endif
 }
 PBSC_DPT_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -145,18 +145,19 @@ PBSC_DPT_HD void fill(int qlen, int mlen, int origin, HS& H, const SS& S, FS& F,
             {
                 const uint32_t old2 = H.get2(j, u);
                 const int leftA = (int)(int16_t)(old2 & 0xFFFFu), leftB = (int)old2 >> 16;
-                const int dA = diagOld + ((x & (3u << (4 * u))) == 0u ? 1 : -8);
-                const int l1A = leftA - 1, u1A = up - 1;
-                const int vA = imax(imax(dA, l1A), u1A);
-                const int dB = leftA + ((x & (12u << (4 * u))) == 0u ? 1 : -8);
-                const int l1B = leftB - 1, u1B = vA - 1;
-                const int vB = imax(imax(dB, l1B), u1B);
-                ww = push_eq(push_eq(push_eq(ww, vA, l1A), vA, u1A), vA, dA);   // bit 2 left, bit 1 up, bit 0 diagonal
-                ww = push_eq(push_eq(push_eq(ww, vB, l1B), vB, u1B), vB, dB);
+                // max(d, left - 1, up - 1) = max(d + 1, left, up) - 1: the three candidates without their own decrements
+                const int eA = diagOld + ((x & (3u << (4 * u))) == 0u ? 2 : -7);
+                const int xA = imax(imax(eA, leftA), up);
+                const int vA = xA - 1;
+                const int eB = leftA + ((x & (12u << (4 * u))) == 0u ? 2 : -7);
+                const int xB = imax(imax(eB, leftB), vA);
+                const int vB = xB - 1;
+                ww = push_ne(push_ne(push_ne(ww, xA, leftA), xA, up), xA, eA);   // bit 2 left, bit 1 up, bit 0 diagonal
+                ww = push_ne(push_ne(push_ne(ww, xB, leftB), xB, vA), xB, eB);
                 H.set2(j, u, ((uint32_t)vA & 0xFFFFu) | ((uint32_t)vB << 16));
                 up = vB; diagOld = leftB;
             }
-            F.put(widx++, ww);
+            F.put(widx++, ww ^ 0x3FFFFFFFu);   // "differs" bits -> "equals" bits
             j += CPW;
         }
         rolled(last);
