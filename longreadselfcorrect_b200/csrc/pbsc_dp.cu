@@ -559,7 +559,7 @@ __device__ __forceinline__ int dp_row_origin(const DpRow& R, const DpJob& J)
 // sort key of a row: longest queries first, forward rows before reverse-complement rows; DPT_KEY_NONE = not for this pass
 __global__ void __launch_bounds__(256)
 dp_keys_kernel(uint64_t n_rows, const DpRow* __restrict__ rows, const DpJob* __restrict__ jobs, uint32_t* keys, uint32_t* order, int qmax,
-               unsigned int* n_thread_rows)
+               unsigned long long* n_eligible)
 {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
@@ -573,9 +573,9 @@ dp_keys_kernel(uint64_t n_rows, const DpRow* __restrict__ rows, const DpJob* __r
     }
     keys[i] = key;
     order[i] = (uint32_t)i;
-    // how many rows take this path (reported in pbsc_timing); one atomic per warp
+    // how many rows this pass could take; one atomic per warp
     const unsigned m = __ballot_sync(__activemask(), key != DPT_KEY_NONE);
-    if (key != DPT_KEY_NONE && (threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(n_thread_rows, (unsigned)__popc(m));
+    if (key != DPT_KEY_NONE && (threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(n_eligible, (unsigned long long)__popc(m));
 }
 
 template <class C>
@@ -622,9 +622,16 @@ template <class C>
 __global__ void __launch_bounds__(C::NT, 227 * 1024 / (C::SMEM + 1024))
 dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, DpRow* rows,
                        const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0, uint32_t* arenas,
-                       uint64_t arena_words, unsigned long long* counter, unsigned int* n_bad)
+                       uint64_t arena_words, unsigned long long* counter, unsigned int* n_bad, const unsigned long long* __restrict__ n_eligible,
+                       unsigned long long min_rows, unsigned int* n_thread_rows)
 {
     extern __shared__ uint32_t dpt_smem[];
+    // One alignment per thread pays when there are enough of them to fill the machine: an alignment of L query bases is a
+    // serial chain of ~L x 201 cells, a few milliseconds for L in the thousands.  A pass with only a few rows leaves them
+    // (`pass == 2`) to the warp-per-row kernel, which works inside one alignment.
+    const unsigned long long n_el = *n_eligible;
+    if (n_el < min_rows) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_thread_rows, (unsigned int)n_el);   // reported in pbsc_timing
     const int lane = threadIdx.x & 31;
     uint32_t* Hs = dpt_smem + threadIdx.x;
     uint32_t* Ss = dpt_smem + C::HWORDS * C::NT + threadIdx.x;
@@ -840,7 +847,7 @@ static cudaError_t arena(pbsc_index* idx, const char* name, size_t count, T** ou
 DpStats& last_dp_stats() { static thread_local DpStats s; return s; }
 
 // one pass of dp_align_thread_kernel<C>: queries of at most min(C::QMAX, longest query of the stage) bases
-struct DptPass { bool on = false; uint64_t qmax = 0, arena_words = 0; int blocks = 0; uint64_t flag_words() const { return on ? arena_words * (uint64_t)blocks : 0; } };
+struct DptPass { bool on = false; uint64_t qmax = 0, arena_words = 0, min_rows = 0; int blocks = 0; uint64_t flag_words() const { return on ? arena_words * (uint64_t)blocks : 0; } };
 template <class C>
 static cudaError_t dpt_pass_setup(pbsc_index* idx, uint64_t q_longest, uint64_t q_prev_max, int cap_per_sm, DptPass& g)
 {
@@ -863,12 +870,12 @@ static void dpt_pass_launch(const DptPass& g, cudaStream_t st, uint64_t nrows, D
                             uint64_t mem0, uint32_t* keys, uint32_t* keys2, uint32_t* order, uint32_t* order2, uint8_t* sort_tmp, size_t sort_bytes,
                             uint32_t* slabs, unsigned long long* counter, unsigned int* cnt)
 {
-    cudaMemsetAsync(counter, 0, 8, st);
-    dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, keys, order, (int)g.qmax, cnt + 2);
+    cudaMemsetAsync(counter, 0, 16, st);   // counter[0]: work queue, counter[1]: rows eligible for this pass
+    dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, keys, order, (int)g.qmax, counter + 1);
     cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys2, order, order2, (int)nrows, 0, DPT_KEY_BITS, st);
     const int tb = (int)std::min<uint64_t>((uint64_t)g.blocks, (nrows + C::NT - 1) / C::NT);
     dp_align_thread_kernel<C><<<tb, C::NT, C::SMEM, st>>>(nrows, keys2, order2, rows, jobs, tasks, mem, mem0, slabs, g.arena_words / (C::NT / 32), counter,
-                                                          cnt + 1);
+                                                          cnt + 1, counter + 1, g.min_rows, cnt + 2);
 }
 
 int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void* tasks_v, uint64_t n_items, const uint32_t* list, uint8_t* outpool,
@@ -884,7 +891,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     PBSC_CUDA(arena(idx, "dp.row_off", n_items + 1, &row_off));
     PBSC_CUDA(arena(idx, "dp.mem_off", n_items + 1, &mem_off));
     PBSC_CUDA(arena(idx, "dp.cnt", 4, &cnt));
-    PBSC_CUDA(arena(idx, "dp.qctr", 2, &qctr));
+    PBSC_CUDA(arena(idx, "dp.qctr", 4, &qctr));
     PBSC_CUDA(cudaMemsetAsync(cnt, 0, 16, st));
     cudaEvent_t ev[2];
     PBSC_CUDA(cudaEventCreate(&ev[0])); PBSC_CUDA(cudaEventCreate(&ev[1]));
@@ -978,6 +985,11 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         PBSC_CUDA(dpt_pass_setup<DptShort>(idx, q_longest, 0, cap, pass_s));
         if (longer) PBSC_CUDA(dpt_pass_setup<DptLong>(idx, q_longest, DptShort::QMAX, 0, pass_l));
         if (longer) PBSC_CUDA(dpt_pass_setup<DptHuge>(idx, q_longest, DptLong::QMAX, 0, pass_h));
+        // fewest rows worth a pass (PBSC_DPT_MIN_ROWS overrides all three; the tests run with 1 to force every pass)
+        // (config 2, first DP stage of a step: the few thousand rows of the 4000-base pass take 22 ms here and 35 ms in the
+        // warp-per-row kernel, which also serialises: a warp there fills 32 rows one after the other)
+        pass_s.min_rows = 512; pass_l.min_rows = 2048; pass_h.min_rows = 2048;
+        if (const char* e = getenv("PBSC_DPT_MIN_ROWS")) pass_s.min_rows = pass_l.min_rows = pass_h.min_rows = (uint64_t)std::max(0ll, atoll(e));
         PBSC_CUDA(arena(idx, "dp.tkeys", max_rows, &tkeys));
         PBSC_CUDA(arena(idx, "dp.tkeys2", max_rows, &tkeys2));
         PBSC_CUDA(arena(idx, "dp.torder", max_rows, &torder));
@@ -1037,7 +1049,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         dp_rows_kernel<<<(unsigned)((njc + 127) / 128), 128, 0, st>>>(j0, j1, jobs, tasks, b.codes.p, b.offsets.p, mem, h_mem[j0], rows, h_row[j0]);
         dp_retrieve_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(idx->dev, nrows, rows, jobs, mem, h_mem[j0]);
         prof.mark("rows+retrieve");
-        PBSC_CUDA(cudaMemsetAsync(qctr, 0, 16, st));
+        PBSC_CUDA(cudaMemsetAsync(qctr, 0, 32, st));
         if (pass_s.on)
         {
             dpt_pass_launch<DptShort>(pass_s, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,

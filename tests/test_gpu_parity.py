@@ -269,6 +269,14 @@ def test_repeat_rich_dataset_vs_oracle(api, oracle_bin, tmp_path, opts, kw, engi
 
 # ---- DP / multiple-alignment fallback (default options, correctByMSAlignment) ------------------------------------------
 
+def _select_dp_kernel(monkeypatch, dp_kernel):
+    if dp_kernel == "thread":
+        monkeypatch.setenv("PBSC_DP_THREAD", "1")
+        monkeypatch.setenv("PBSC_DPT_MIN_ROWS", "1")
+    elif dp_kernel == "warp":
+        monkeypatch.setenv("PBSC_DP_THREAD", "0")
+
+
 def _summary_counters(stats):
     m = stats[stats["merge"] == 1]
     return {k: int(m[k].sum()) for k in ("total_reads_len", "corrected_len", "total_seed_num", "total_walk_num", "fm_num", "dp_num",
@@ -277,12 +285,12 @@ def _summary_counters(stats):
 
 @pytest.mark.parametrize("name,kw", [("tiny", dict(coverage=30, genome=5)), ("tiny100", dict(coverage=100, genome=10))])
 @pytest.mark.parametrize("k0", [0, 13])
-@pytest.mark.parametrize("dp_kernel", ["thread", "warp"])
+@pytest.mark.parametrize("dp_kernel", ["thread", "warp", "auto"])
 def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, golden, name, kw, k0, dp_kernel, monkeypatch):
     """Default options: failed walks go through retrieveStr / extendMatch / MultipleAlignment on the GPU; fixtures written by
-    the reference binary (tests/golden/make_golden.py dp).  Both alignment kernels: one alignment per thread (default, with
-    the warp-per-row kernel taking what it leaves) and warp per row alone."""
-    monkeypatch.setenv("PBSC_DP_THREAD", "1" if dp_kernel == "thread" else "0")
+    the reference binary (tests/golden/make_golden.py dp).  Both alignment kernels: one alignment per thread (forced for every
+    pass, however few rows it has), warp per row alone, and the default mix (a pass with few rows is left to the warp kernel)."""
+    _select_dp_kernel(monkeypatch, dp_kernel)
     p = api.Params.make(no_dp=False, **kw)
     tiny_index.build_prefix_table(k0)
     out, poff, first, stats = tiny_index.correct_reads(p, [s for _, s in tiny_reads])
@@ -298,7 +306,9 @@ def test_dp_fallback_byte_identical_to_reference(api, tiny_index, tiny_reads, go
     assert got["seed_dis"] // got["total_walk_num"] == int(summ["DisBetweenSeeds"])
     tm = api.last_timing()
     assert tm["dp_jobs"] > 0
-    assert (tm["dp_thread_rows"] > 0) == (dp_kernel == "thread") and tm["dp_thread_rows"] <= tm["dp_rows"]
+    if dp_kernel != "auto":
+        assert (tm["dp_thread_rows"] > 0) == (dp_kernel == "thread")
+    assert tm["dp_thread_rows"] <= tm["dp_rows"]
     tiny_index.build_prefix_table(0)
 
 
@@ -315,7 +325,7 @@ def test_dp_fallback_repeat_rich_vs_oracle(api, oracle_bin, tmp_path, cov, opts,
     from conftest import run_oracle
     from longreadselfcorrect_b200 import bwt_build, synth
     monkeypatch.setenv("PBSC_DP_CHUNK_MB", "8")
-    monkeypatch.setenv("PBSC_DP_THREAD", "1" if dp_kernel == "thread" else "0")
+    _select_dp_kernel(monkeypatch, dp_kernel)
     g = synth.make_genome(15000, 23, repeat_families=1, tandem_arrays=3)
     codes, off = synth.simulate_reads(g, cov, 1200, 213, min_len=300)
     reads = synth.read_strings(codes, off)
