@@ -5,7 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <random>
+#include <sstream>
 #include <string>
 #include <vector>
 #include "../../longreadselfcorrect_b200/csrc/pbsc_dp_thread.cuh"
@@ -72,8 +74,74 @@ static std::vector<uint8_t> mutate(const std::vector<uint8_t>& s, double err, in
 }
 static std::string to_str(const std::vector<uint8_t>& s) { std::string o; for (uint8_t c : s) o.push_back("ACGT"[c]); return o; }
 
+// The reference's own answers: tests/golden/dp_units.txt holds "A s1 s2 start_1 start_2" records (and "M" pile-up records,
+// skipped here), dp_units.ref.txt what oracle/_ref/dp_dump — linked against the reference's Overlapper — printed for them:
+// "A score start0 end0 start1 end1 editDistance totalColumns cigar".  Everything but the score is compared.
+static std::string compact_ops(const std::string& ops)
+{
+    std::string out;
+    for (size_t i = 0; i < ops.size();)
+    {
+        size_t j = i;
+        while (j < ops.size() && ops[j] == ops[i]) j++;
+        out += std::to_string(j - i) + ops[i];
+        i = j;
+    }
+    return out;
+}
+static int check_vectors(const char* in_path, const char* ref_path)
+{
+    std::ifstream in(in_path), ref(ref_path);
+    if (!in || !ref) { printf("cannot open the vector files\n"); return 2; }
+    std::string tag;
+    long tested = 0, failed = 0, skipped = 0;
+    while (in >> tag)
+    {
+        std::string line;
+        if (tag == "M")
+        {
+            std::string q; int minCall, n;
+            in >> q >> minCall >> n;
+            for (int i = 0; i < n; i++) { std::string s; int a, b; in >> s >> a >> b; }
+            std::getline(ref, line);
+            continue;
+        }
+        std::string s1, s2; int a, b;
+        in >> s1 >> s2 >> a >> b;
+        std::getline(ref, line);
+        std::istringstream rs(line);
+        std::string rtag, cigar; int score, st0, en0, st1, en1, ed, cols;
+        rs >> rtag >> score >> st0 >> en0 >> st1 >> en1 >> ed >> cols >> cigar;
+        if (rtag != "A") { printf("answer file out of step\n"); return 2; }
+        const int qlen = (int)s1.size(), mlen = (int)s2.size();
+        const int origin = (b - a + 1) - (HALF + 1);
+        if (!eligible(qlen, mlen, origin, 4000)) { skipped++; continue; }
+        std::vector<uint8_t> q(qlen), r(mlen);
+        auto code = [](char c) { return (uint8_t)(c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3); };
+        for (int x = 0; x < qlen; x++) q[x] = code(s1[x]);
+        for (int x = 0; x < mlen; x++) r[x] = code(s2[x]);
+        HHost H; SHost S(r); FHost F((size_t)qlen * words_per_col(mlen));
+        auto qf = [&](int x) { return (int)q[x]; };
+        int bi = 0, bj = 0;
+        fill(qlen, mlen, origin, H, S, F, qf, bi, bj);
+        tested++;
+        if (bi <= 0) { if (cols > 0) { failed++; printf("vector %ld: no traceback start\n", tested); } continue; }
+        OHost O; int n = 0, e = 0, i0 = 0, j0 = 0;
+        traceback(qlen, mlen, origin, S, F, qf, bi, bj, O, n, e, i0, j0);
+        const std::string fwd(O.ops.rbegin(), O.ops.rend());
+        if (compact_ops(fwd) != cigar || n != cols || e != ed || i0 != st0 || j0 != st1 || bi - 1 != en0 || bj - 1 != en1)
+        {
+            failed++;
+            if (failed < 10) printf("vector %ld MISMATCH: %s\n  got %d %d %d %d %d %d %s\n", tested, line.c_str(), i0, bi - 1, j0, bj - 1, e, n, compact_ops(fwd).c_str());
+        }
+    }
+    printf("vectors tested %ld skipped %ld failed %ld\n", tested, skipped, failed);
+    return failed ? 1 : (tested < 300 ? 3 : 0);
+}
+
 int main(int argc, char** argv)
 {
+    if (argc > 3 && std::string(argv[1]) == "--vectors") return check_vectors(argv[2], argv[3]);
     const int cases = argc > 1 ? atoi(argv[1]) : 6000;
     long tested = 0, skipped = 0, failed = 0, badstart = 0;
     for (int it = 0; it < cases; it++)

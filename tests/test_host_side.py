@@ -73,6 +73,9 @@ def test_thread_per_alignment_dp_matches_oracle_extendmatch(tmp_path):
                     "-o", exe], check=True)
     r = subprocess.run([exe, "12000"], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0 and " failed 0" in r.stdout, r.stdout
+    # ... and against the reference's own Overlapper: the 360 extendMatch records answered by oracle/_ref/dp_dump
+    r = subprocess.run([exe, "--vectors", os.path.join(GOLDEN, "dp_units.txt"), os.path.join(GOLDEN, "dp_units.ref.txt")], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "tested 360" in r.stdout and " failed 0" in r.stdout, r.stdout
 
 
 def test_bwt_builder_equals_reference_index(oracle_bin, tmp_path):
