@@ -382,6 +382,8 @@ int pbsc_device_count(void)
     return n;
 }
 
+static void apply_l2_policy(pbsc_index* idx, int device);
+
 static int upload_strand(pbsc_index* idx, int which, const std::vector<FmBlock>& blocks, const std::vector<uint32_t>& dollars,
                          uint64_t n_symbols, uint64_t n_strings, const uint64_t total[5])
 {
@@ -431,8 +433,43 @@ int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt
     if (rc == PBSC_OK && cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__); }
     if (rc == PBSC_OK) cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (rc != PBSC_OK) { pbsc_index_destroy(idx); return rc; }
+    apply_l2_policy(idx, device);
     *out = idx;
     return PBSC_OK;
+}
+
+// EXPERIMENT, off unless PBSC_L2_PERSIST is set (not measured yet: prepared at the end of round 1 for round 2).
+// walk_levels_kernel is bound by DRAM random access (2.1 TB/s of 32-byte sectors at a 33 % L2 hit rate) and the two rank
+// tables are what its random reads hit (config 2: 2 x 119 MB against 126 MB of L2), while its per-lane scratch (~0.9 GB of
+// leaf records per pass) streams through the same L2.  PBSC_L2_PERSIST=<percent> sets aside the largest persisting L2
+// carve-out the device allows and puts an access-policy window on the launch stream over the span of the two block tables
+// (when the span fits the device's window limit; otherwise over the first table), hit ratio = percent / 100 (default: the
+// carve-out divided by the window), misses streaming.
+static void apply_l2_policy(pbsc_index* idx, int device)
+{
+    const char* e = getenv("PBSC_L2_PERSIST");
+    if (!e || !idx->stream || !idx->d_blocks[0] || !idx->d_blocks[1]) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    if (max_persist <= 0 || max_window <= 0) { fprintf(stderr, "[pbsc] PBSC_L2_PERSIST: the device reports no persisting L2\n"); return; }
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) { cudaGetLastError(); return; }
+    const uintptr_t a0 = (uintptr_t)idx->d_blocks[0], a1 = (uintptr_t)idx->d_blocks[1];
+    const size_t b0 = idx->n_blocks[0] * sizeof(FmBlock), b1 = idx->n_blocks[1] * sizeof(FmBlock);
+    uintptr_t lo = std::min(a0, a1), hi = std::max(a0 + b0, a1 + b1);
+    if (hi - lo > (uintptr_t)max_window) { lo = a0; hi = a0 + std::min(b0, (size_t)max_window); }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = (void*)lo;
+    attr.accessPolicyWindow.num_bytes = (size_t)(hi - lo);
+    double ratio = atof(e) > 1.0 ? atof(e) / 100.0 : (double)max_persist / (double)(hi - lo);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, std::max(0.0, ratio));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    const cudaError_t rc = cudaStreamSetAttribute(idx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (rc != cudaSuccess) cudaGetLastError();
+    fprintf(stderr, "[pbsc] PBSC_L2_PERSIST: carve-out %.1f MB, window %.1f MB (%s), hit ratio %.2f: %s\n", max_persist / 1048576.0, (hi - lo) / 1048576.0,
+            (hi - lo) >= b0 + b1 ? "both rank tables" : "first rank table", attr.accessPolicyWindow.hitRatio, rc == cudaSuccess ? "set" : cudaGetErrorString(rc));
 }
 
 static int read_bwt_file(const std::string& path, std::vector<uint8_t>& runs, uint64_t& n_strings, uint64_t& n_symbols)
@@ -539,6 +576,7 @@ int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t
     }
     if (cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__));
     cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    apply_l2_policy(idx, device);
     *out = idx;
     return PBSC_OK;
 }
