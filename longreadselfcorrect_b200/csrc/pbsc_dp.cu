@@ -25,6 +25,7 @@
 #include "pbsc_task.cuh"
 #include "pbsc_dp.cuh"
 #include "pbsc_dp_thread.cuh"
+#include "pbsc_dp_msa.cuh"
 
 namespace pbsc {
 
@@ -33,7 +34,6 @@ constexpr int DP_BW = 2 * DP_HALF + 1;    // cells per band column
 constexpr int DP_CPL = 7;                 // cells per lane: 32 x 7 = 224 >= 201
 constexpr int DP_NEG = -(1 << 28);
 constexpr int DP_WARPS = 8;               // warps per block of the alignment kernel
-constexpr int OP_M = 0, OP_I = 1, OP_D = 2;
 
 struct __align__(16) DpJob
 {
@@ -44,17 +44,6 @@ struct __align__(16) DpJob
     uint64_t row0;     // first row, numbered over the whole DP stage
     uint64_t mem;      // byte offset of the job's scratch, over the whole DP stage
 };
-
-struct __align__(16) DpRow
-{
-    uint32_t job, local;       // job index, row index inside the job
-    uint32_t len, seq_start;   // the retrieved read is buf[seq_start, seq_start + len)
-    uint32_t nops;             // alignment columns (ops are stored last column first)
-    int32_t start0, start1;    // match[0].start, match[1].start
-    uint32_t pass;             // 0 dropped, 1 enters the multiple alignment, 2 retrieved and waiting for alignment
-};
-
-struct __align__(8) GapCol { uint16_t cnt[5]; uint16_t pad; uint32_t next; };   // one inserted column: A,C,G,T,'-' counts
 
 __host__ __device__ inline uint32_t dp_max_len(uint32_t qlen)
 {
@@ -68,7 +57,6 @@ __host__ __device__ inline uint32_t dp_max_len(uint32_t qlen)
 }
 __host__ __device__ inline uint64_t dp_seq_bytes(uint32_t maxLen) { return align_up((size_t)maxLen, 16); }
 __host__ __device__ inline uint64_t dp_row_bytes(uint32_t qlen, uint32_t maxLen) { return dp_seq_bytes(maxLen) + align_up((size_t)qlen + maxLen, 16); }
-__host__ __device__ inline uint32_t dp_gap_cap(uint32_t qlen) { return 3 * qlen + 128; }
 __host__ __device__ inline uint64_t dp_msa_bytes(uint32_t qlen)
 {
     const uint64_t np = (uint64_t)qlen + 1;
@@ -156,12 +144,6 @@ __global__ void dp_offsets_kernel(uint64_t n_jobs, DpJob* jobs, const uint64_t* 
     if (j < n_jobs) { jobs[j].row0 = row_off[j]; jobs[j].mem = mem_off[j]; }
 }
 
-struct JobView
-{
-    uint8_t* q; uint8_t* rows;
-    uint16_t* baseCnt; uint16_t* startAt; uint32_t* head; uint32_t* tail; GapCol* pool;
-    uint64_t rowBytes, seqBytes;
-};
 __device__ __forceinline__ void job_view(uint8_t* mem, const DpJob& J, uint32_t rows, JobView& v)
 {
     uint8_t* p = mem;
@@ -692,12 +674,21 @@ dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const
 }
 
 // ---- stage 3: thread per job: multiple alignment on per-column counts, consensus ---------------------------------------
-// Column model.  MultipleAlignment::_addSequence places every incoming row against row 0 (the query); a new gap column is
-// only ever inserted immediately before a BASE column of row 0, i.e. appended to the run of gap columns in front of that
-// base, so the alignment is: for each query position p a list run(p) of inserted columns, then the base column p.  The
-// consensus only needs, per column, how many rows show A/C/G/T/'-' there.  A new column inserted before base column p gets a
-// '-' from every row that already spans it: rows covering base column p minus rows whose first column IS base column p
-// (MultipleAlignmentElement::insertGapBeforeColumn, multiple_alignment.cpp:112-134).
+// (the column model and the per-job code are in pbsc_dp_msa.cuh, shared with the host check tests/cpp/test_dp_msa.cpp)
+// what msa::consensus asks the task for, when it needs it (pbsc_dp_msa.cuh)
+struct MsaCtx
+{
+    WalkTask& tk; uint8_t* outpool;
+    __device__ __forceinline__ int min_call() const
+    {
+        // min_call_coverage = totalFreq > 50 ? totalFreq * 0.4 : 15 (PacBioSelfCorrectionProcess.cpp:236-240)
+        const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
+        return (int)(fsum > 50 ? (uint64_t)__dmul_rn((double)fsum, 0.4) : 15);
+    }
+    __device__ __forceinline__ uint8_t* out() const { return outpool + tk.out_off; }
+    __device__ __forceinline__ uint32_t cap() const { return tk.out_cap; }
+};
+
 // EXPERIMENT (PBSC_DP_SORT_JOBS, off by default): jobs of a chunk in order of decreasing work (alignment columns of the rows
 // that passed the filters), optionally dealt out across warps (warp w, lane l takes rank l * n_warps + w) so that every warp
 // holds one job of each weight class.  Measured on config 2: natural order 78 ms, dealt out 134 ms, plainly sorted 189 ms —
@@ -741,102 +732,13 @@ dp_msa_kernel(uint64_t j0, uint64_t j1, const uint32_t* __restrict__ order, int 
     WalkTask& tk = tasks[J.task];
     const uint32_t nr = job_rows_of(J);
     const DpRow* R = rows + (J.row0 - row_base);
-    uint32_t passing = 0;
-    for (uint32_t r = 0; r < nr; r++) passing += R[r].pass == 1;
-    if (passing < 3) { tk.dp_status = PBSC_DP_FEW_ROWS; return; }
     JobView v;
     job_view(mem + (J.mem - mem0), J, nr, v);
-    const uint32_t qlen = J.qlen;
-    const uint8_t* q = v.q;
-    for (uint32_t p = 0; p <= qlen; p++)
-    {
-        #pragma unroll
-        for (int c = 0; c < 5; c++) v.baseCnt[p * 5 + c] = 0;
-        v.startAt[p] = 0; v.head[p] = 0; v.tail[p] = 0;
-        if (p < qlen) v.baseCnt[p * 5 + q[p]] = 1;
-    }
-    v.startAt[0] = 1;   // row 0 starts at base column 0
-    const uint32_t gapCap = dp_gap_cap(qlen);
-    uint32_t nGap = 0;
-    bool bad = false;
-    for (uint32_t r = 0; r < nr && !bad; r++)
-    {
-        if (R[r].pass != 1) continue;
-        const uint8_t* buf = v.rows + (uint64_t)R[r].local * v.rowBytes;
-        const uint8_t* s2 = buf + R[r].seq_start;
-        const uint8_t* ops = buf + v.seqBytes;
-        uint32_t p = (uint32_t)R[r].start0, inc = (uint32_t)R[r].start1;
-        uint32_t cur = 0;   // 0: at base column p; otherwise gap column cur-1 of run(p)
-        bool firstOp = true;
-        int c = (int)R[r].nops - 1;
-        while (c >= 0)
-        {
-            const int op = ops[c];
-            if (cur)
-            {
-                GapCol& g = v.pool[cur - 1];
-                if (op == OP_I) { g.cnt[s2[inc]]++; inc++; c--; firstOp = false; }
-                else g.cnt[4]++;
-                cur = g.next;
-            }
-            else if (op == OP_I)
-            {
-                if (nGap >= gapCap) { bad = true; break; }
-                uint32_t cover = 0;
-                #pragma unroll
-                for (int s = 0; s < 5; s++) cover += v.baseCnt[p * 5 + s];
-                GapCol g;
-                g.cnt[0] = g.cnt[1] = g.cnt[2] = g.cnt[3] = 0; g.pad = 0; g.next = 0;
-                g.cnt[4] = (uint16_t)(cover - v.startAt[p]);
-                g.cnt[s2[inc]] = 1;
-                v.pool[nGap] = g;
-                nGap++;
-                if (v.tail[p]) v.pool[v.tail[p] - 1].next = nGap; else v.head[p] = nGap;
-                v.tail[p] = nGap;
-                inc++; c--; firstOp = false;
-            }
-            else
-            {
-                if (p >= qlen) { bad = true; break; }
-                v.baseCnt[p * 5 + (op == OP_M ? s2[inc] : 4)]++;
-                if (op == OP_M) inc++;
-                if (firstOp) v.startAt[p]++;
-                firstOp = false;
-                p++; c--;
-                cur = v.head[p];
-            }
-        }
-    }
-    if (bad) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_WALK_OVERFLOW; return; }
-    // calculateBaseConsensus(min_call_coverage, -1) (multiple_alignment.cpp:517-594)
-    const uint64_t fsum = (uint64_t)(int64_t)tk.freq_sum;
-    const int minCall = (int)(fsum > 50 ? (uint64_t)__dmul_rn((double)fsum, 0.4) : 15);
-    uint8_t* out = outpool + tk.out_off;
+    const MsaCtx ctx{tk, outpool};
     uint32_t n = 0;
-    const uint32_t cap = tk.out_cap;
-    auto call = [&](const uint16_t* cnt, int baseSym) -> int
-    {
-        int maxSym = -1, maxCount = -1;
-        #pragma unroll
-        for (int s = 0; s < 5; s++) if ((int)cnt[s] > maxCount) { maxSym = s; maxCount = cnt[s]; }   // order A,C,G,T,(N),'-'
-        const int baseCount = cnt[baseSym];
-        return (maxCount >= baseCount && baseCount < minCall) ? maxSym : baseSym;
-    };
-    bool over = false;
-    for (uint32_t p = 0; p < qlen && !over; p++)
-    {
-        if (p >= 1)
-            for (uint32_t g = v.head[p]; g; g = v.pool[g - 1].next)
-            {
-                const int s = call(v.pool[g - 1].cnt, 4);
-                if (s != 4) { if (n >= cap) { over = true; break; } out[n++] = (uint8_t)s; }
-            }
-        if (over) break;
-        const int s = call(v.baseCnt + p * 5, (int)q[p]);
-        if (s != 4) { if (n >= cap) { over = true; break; } out[n++] = (uint8_t)s; }
-    }
-    // out.erase(0, extendKmerSize) needs at least k bases
-    if (over || n < J.k) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_WALK_OVERFLOW; return; }
+    const int rc = msa::consensus(v, J.qlen, J.k, R, nr, ctx, n);
+    if (rc == 1) { tk.dp_status = PBSC_DP_FEW_ROWS; return; }
+    if (rc == 2) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_WALK_OVERFLOW; return; }
     tk.out_len = n;
     tk.dp_status = PBSC_DP_OK;
 }

@@ -78,6 +78,18 @@ def test_thread_per_alignment_dp_matches_oracle_extendmatch(tmp_path):
     assert r.returncode == 0 and "tested 360" in r.stdout and " failed 0" in r.stdout, r.stdout
 
 
+def test_multiple_alignment_column_model_matches_reference_vectors(tmp_path):
+    """msa::consensus (csrc/pbsc_dp_msa.cuh), the per-job code of dp_msa_kernel, compiled for the host: the 60 pile-ups answered
+    by the reference's own MultipleAlignment (oracle/_ref/dp_dump) and random pile-ups against the oracle's padded rows."""
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-Wno-sign-compare", "-Wno-unknown-pragmas",
+                    os.path.join(ROOT, "tests", "cpp", "test_dp_msa.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe, "--vectors", os.path.join(GOLDEN, "dp_units.txt"), os.path.join(GOLDEN, "dp_units.ref.txt")], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "tested 60" in r.stdout and " failed 0" in r.stdout, r.stdout
+    r = subprocess.run([exe, "1500"], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and " failed 0" in r.stdout, r.stdout
+
+
 def test_bwt_builder_equals_reference_index(oracle_bin, tmp_path):
     """The torch suffix sorter used for synthetic inputs yields the intervals of the reference's own (ropebwt2) index."""
     from longreadselfcorrect_b200 import bwt_build
