@@ -64,7 +64,9 @@ PBSC_MSA_HD int consensus(const JobView& v, const uint32_t qlen, const uint32_t 
     const uint8_t* q = v.q;
     for (uint32_t p = 0; p <= qlen; p++)
     {
+#if defined(__CUDA_ARCH__)
         #pragma unroll
+#endif
         for (int c = 0; c < 5; c++) v.baseCnt[p * 5 + c] = 0;
         v.startAt[p] = 0; v.head[p] = 0; v.tail[p] = 0;
         if (p < qlen) v.baseCnt[p * 5 + q[p]] = 1;
@@ -97,7 +99,9 @@ PBSC_MSA_HD int consensus(const JobView& v, const uint32_t qlen, const uint32_t 
             {
                 if (nGap >= gapCap) { bad = true; break; }
                 uint32_t cover = 0;
-                #pragma unroll
+        #if defined(__CUDA_ARCH__)
+        #pragma unroll
+#endif
                 for (int s = 0; s < 5; s++) cover += v.baseCnt[p * 5 + s];
                 GapCol g;
                 g.cnt[0] = g.cnt[1] = g.cnt[2] = g.cnt[3] = 0; g.pad = 0; g.next = 0;
@@ -130,7 +134,9 @@ PBSC_MSA_HD int consensus(const JobView& v, const uint32_t qlen, const uint32_t 
     auto call = [&](const uint16_t* cnt, int baseSym) -> int
     {
         int maxSym = -1, maxCount = -1;
+#if defined(__CUDA_ARCH__)
         #pragma unroll
+#endif
         for (int s = 0; s < 5; s++) if ((int)cnt[s] > maxCount) { maxSym = s; maxCount = cnt[s]; }   // order A,C,G,T,(N),'-'
         const int baseCount = cnt[baseSym];
         return (maxCount >= baseCount && baseCount < minCall) ? maxSym : baseSym;
