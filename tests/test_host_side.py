@@ -64,6 +64,15 @@ def test_sort_emulation_matches_libstdcxx(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("ok")
 
 
+def test_integer_ratio_rule_equals_the_reference_double_comparison(tmp_path):
+    """eval4 (csrc/pbsc_walk_thread.cuh) replaces `(double)kmerFreq/(double)maxfreq >= cutoff` by an integer cross-multiplication;
+    the two agree on 142 M (a, b) pairs including every cutoff boundary for b up to 2^31 - 1."""
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", os.path.join(ROOT, "tests", "cpp", "test_ratio_rule.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+
+
 def test_thread_per_alignment_dp_matches_oracle_extendmatch(tmp_path):
     """The fill / traceback templates that dp_align_thread_kernel instantiates (csrc/pbsc_dp_thread.cuh), compiled for the host
     over accessors that mimic the device storage, against the oracle's Overlapper::extendMatch: forward and reverse-complement
