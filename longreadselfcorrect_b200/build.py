@@ -47,6 +47,28 @@ def build_lib(force: bool = False, verbose: bool = False, extra: list[str] | Non
     return LIB
 
 
+def build_variant(name: str, extra: list[str]) -> str:
+    """An alternative build of the library for experiments (e.g. build_variant("fused", ["-DPBSC_FUSED_UPDATE"])): objects go
+    to csrc/_variant_<name>/, the library to libpbsc_<name>.so; select it with PBSC_LIB=<path> (api.py).  The default
+    library is not touched."""
+    odir = os.path.join(CSRC, f"_variant_{name}")
+    os.makedirs(odir, exist_ok=True)
+    lib = os.path.join(PKG, f"libpbsc_{name}.so")
+    procs, objs = [], []
+    for s in CU_SOURCES:
+        o = os.path.join(odir, s[:-3] + ".o")
+        objs.append(o)
+        cmd = [NVCC] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.run([NVCC, "-shared", "-o", lib] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++"], check=True)
+    return lib
+
+
 def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "pbcorrect_main.cpp")
     if not os.path.exists(src):
@@ -60,6 +82,9 @@ def build_cli(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":   # python -m longreadselfcorrect_b200.build --variant fused -DPBSC_FUSED_UPDATE
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
     build_cli(force="--force" in sys.argv)
     print(LIB)

@@ -64,6 +64,15 @@ struct Interval   // half-open
     __host__ __device__ __forceinline__ uint64_t size() const { return hi - lo; }
 };
 
+// The primitives below also compile for the host (tests/cpp/test_fm_occ.cpp checks them against naive counting).
+#if defined(__CUDA_ARCH__)
+#define PBSC_LDG(p) __ldg(p)
+#define PBSC_POPCLL(x) __popcll(x)
+#else
+#define PBSC_LDG(p) (*(p))
+#define PBSC_POPCLL(x) __builtin_popcountll(x)
+#endif
+
 #ifdef PBSC_COUNT_OCC
 __device__ unsigned long long g_occ_counter;
 #define PBSC_OCC_TICK(n) atomicAdd(&g_occ_counter, (unsigned long long)(n))
@@ -71,26 +80,26 @@ __device__ unsigned long long g_occ_counter;
 #define PBSC_OCC_TICK(n)
 #endif
 
-__device__ __forceinline__ uint32_t count_dollars(const FmTable& t, uint64_t from, uint64_t to)
+__host__ __device__ __forceinline__ uint32_t count_dollars(const FmTable& t, uint64_t from, uint64_t to)
 {
     // number of '$' positions in [from, to): two lower_bounds on the sorted list
     uint32_t lo = 0, hi = t.n_dollar;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint64_t)__ldg(t.dollar_pos + m) < from) lo = m + 1; else hi = m; }
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint64_t)PBSC_LDG(t.dollar_pos + m) < from) lo = m + 1; else hi = m; }
     uint32_t a = lo;
     hi = t.n_dollar;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint64_t)__ldg(t.dollar_pos + m) < to) lo = m + 1; else hi = m; }
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((uint64_t)PBSC_LDG(t.dollar_pos + m) < to) lo = m + 1; else hi = m; }
     return lo - a;
 }
 
 // occ(c, p): occurrences of base c in bwt[0, p)  ==  RLBWT::getOcc(c, p-1)  (RLBWT.h:121-140)
-__device__ __forceinline__ uint64_t occ(const FmTable& t, int c, uint64_t p)
+__host__ __device__ __forceinline__ uint64_t occ(const FmTable& t, int c, uint64_t p)
 {
     PBSC_OCC_TICK(1);
     const uint64_t blk = p >> 6;
     const uint32_t off = (uint32_t)p & 63u;
     const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
-    const uint4 cn = __ldg(bp);
-    const uint4 bs = __ldg(bp + 1);
+    const uint4 cn = PBSC_LDG(bp);
+    const uint4 bs = PBSC_LDG(bp + 1);
     uint32_t base = c == 0 ? cn.x : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
     const bool has_dollar = (cn.x >> 31) != 0;
     if (c == 0) base &= 0x7fffffffu;
@@ -103,24 +112,63 @@ __device__ __forceinline__ uint64_t occ(const FmTable& t, int c, uint64_t p)
     // keep the first `off` symbols
     if (off < 32) { m0 &= (1ull << (2 * off)) - 1ull; m1 = 0; }
     else { m1 &= (1ull << (2 * (off - 32))) - 1ull; }
-    uint64_t r = (uint64_t)base + __popcll(m0) + __popcll(m1);
-    if (c == 0 && has_dollar && off) r -= __popcll(__ldg(t.dollar_mask + blk) & ((1ull << off) - 1ull));
+    uint64_t r = (uint64_t)base + PBSC_POPCLL(m0) + PBSC_POPCLL(m1);
+    if (c == 0 && has_dollar && off) r -= PBSC_POPCLL(PBSC_LDG(t.dollar_mask + blk) & ((1ull << off) - 1ull));
     return r;
 }
 
+// occ(c, lo) and occ(c, hi) for lo <= hi: one sector load and one decode when both fall into the same 64-symbol block (the
+// usual case once an interval is down to ~coverage rows).  EXPERIMENT: used by update_interval only when the library is built
+// with -DPBSC_FUSED_UPDATE (not measured yet); checked against occ() on the host.
+__host__ __device__ __forceinline__ void occ_pair(const FmTable& t, int c, uint64_t lo, uint64_t hi, uint64_t& a, uint64_t& b)
+{
+    if ((lo >> 6) != (hi >> 6)) { a = occ(t, c, lo); b = occ(t, c, hi); return; }
+    PBSC_OCC_TICK(1);
+    const uint64_t blk = lo >> 6;
+    const uint32_t off_a = (uint32_t)lo & 63u, off_b = (uint32_t)hi & 63u;
+    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
+    const uint4 cn = PBSC_LDG(bp);
+    const uint4 bs = PBSC_LDG(bp + 1);
+    uint32_t base = c == 0 ? cn.x : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
+    const bool has_dollar = (cn.x >> 31) != 0;
+    if (c == 0) base &= 0x7fffffffu;
+    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
+    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
+    const uint64_t pat = 0x5555555555555555ull * (uint64_t)c;
+    const uint64_t x0 = w0 ^ pat, x1 = w1 ^ pat;
+    const uint64_t m0 = ~(x0 | (x0 >> 1)) & 0x5555555555555555ull;
+    const uint64_t m1 = ~(x1 | (x1 >> 1)) & 0x5555555555555555ull;
+    // symbols [0, off) of the block: all of word 0 and off - 32 of word 1 when off >= 32
+    const uint64_t ka0 = off_a < 32 ? (1ull << (2 * off_a)) - 1ull : ~0ull, ka1 = off_a < 32 ? 0ull : (1ull << (2 * (off_a - 32))) - 1ull;
+    const uint64_t kb0 = off_b < 32 ? (1ull << (2 * off_b)) - 1ull : ~0ull, kb1 = off_b < 32 ? 0ull : (1ull << (2 * (off_b - 32))) - 1ull;
+    a = (uint64_t)base + PBSC_POPCLL(m0 & ka0) + PBSC_POPCLL(m1 & ka1);
+    b = (uint64_t)base + PBSC_POPCLL(m0 & kb0) + PBSC_POPCLL(m1 & kb1);
+    if (c == 0 && has_dollar && off_b)
+    {
+        const uint64_t dm = PBSC_LDG(t.dollar_mask + blk);
+        if (off_a) a -= PBSC_POPCLL(dm & ((1ull << off_a) - 1ull));
+        b -= PBSC_POPCLL(dm & ((1ull << off_b) - 1ull));
+    }
+}
+
 // BWTAlgorithms::updateInterval (SuffixTools/BWTAlgorithms.h:66-72) on a half-open interval
-__device__ __forceinline__ Interval update_interval(const FmTable& t, Interval iv, int c)
+__host__ __device__ __forceinline__ Interval update_interval(const FmTable& t, Interval iv, int c)
 {
     Interval r;
+#ifdef PBSC_FUSED_UPDATE
+    uint64_t a, b;
+    occ_pair(t, c, iv.lo, iv.hi, a, b);
+#else
     const uint64_t a = occ(t, c, iv.lo);
     const uint64_t b = (iv.hi == iv.lo) ? a : occ(t, c, iv.hi);
+#endif
     r.lo = t.C[c] + a;
     r.hi = t.C[c] + b;
     return r;
 }
 
 // BWTAlgorithms::initInterval (BWTAlgorithms.h:136-140)
-__device__ __forceinline__ Interval init_interval(const FmTable& t, int c)
+__host__ __device__ __forceinline__ Interval init_interval(const FmTable& t, int c)
 {
     Interval r;
     r.lo = t.C[c];
@@ -129,10 +177,10 @@ __device__ __forceinline__ Interval init_interval(const FmTable& t, int c)
 }
 
 // read one prefix-table entry (one 32-byte sector) and return the strand the caller wants
-__device__ __forceinline__ void prefix_lookup(const FmIndexDev& idx, uint64_t key, Interval& fwd, Interval& rvc)
+__host__ __device__ __forceinline__ void prefix_lookup(const FmIndexDev& idx, uint64_t key, Interval& fwd, Interval& rvc)
 {
     const uint4* ep = reinterpret_cast<const uint4*>(idx.prefix + key);
-    const uint4 a = __ldg(ep), b = __ldg(ep + 1);
+    const uint4 a = PBSC_LDG(ep), b = PBSC_LDG(ep + 1);
     fwd.lo = (uint64_t)a.x | ((uint64_t)a.y << 32); fwd.hi = fwd.lo + b.x;
     rvc.lo = (uint64_t)a.z | ((uint64_t)a.w << 32); rvc.hi = rvc.lo + b.y;
 }

@@ -64,6 +64,19 @@ def test_sort_emulation_matches_libstdcxx(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("ok")
 
 
+@pytest.mark.parametrize("flags", [[], ["-DPBSC_FUSED_UPDATE"]])
+def test_rank_primitives_match_naive_counting(tmp_path, flags):
+    """occ / occ_pair / count_dollars / update_interval of csrc/fm_table.cuh — the code every kernel calls — compiled for the
+    host, against naive counting over random BWTs with '$' symbols (default build and the experimental fused update)."""
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", cuda_inc] + flags + [os.path.join(ROOT, "tests", "cpp", "test_fm_occ.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+
+
 def test_integer_ratio_rule_equals_the_reference_double_comparison(tmp_path):
     """eval4 (csrc/pbsc_walk_thread.cuh) replaces `(double)kmerFreq/(double)maxfreq >= cutoff` by an integer cross-multiplication;
     the two agree on 142 M (a, b) pairs including every cutoff boundary for b up to 2^31 - 1."""
