@@ -77,6 +77,20 @@ def test_rank_primitives_match_naive_counting(tmp_path, flags):
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
 
 
+@pytest.mark.parametrize("flags", [[], ["-DPBSC_FUSED_UPDATE"]])
+def test_backward_search_primitives_match_reference_findinterval(tmp_path, flags):
+    """init_interval / update_interval of csrc/fm_table.cuh compiled for the host, on the reference-built tiny.bwt / tiny.rbwt,
+    against the (lower, upper) pairs the reference's own BWTAlgorithms::findInterval printed for 2000 queries (fm_dump),
+    including its raw values at the early break."""
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", cuda_inc] + flags + [os.path.join(ROOT, "tests", "cpp", "test_fm_search.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe, GOLDEN], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok: 4000 intervals"), r.stdout
+
+
 def test_integer_ratio_rule_equals_the_reference_double_comparison(tmp_path):
     """eval4 (csrc/pbsc_walk_thread.cuh) replaces `(double)kmerFreq/(double)maxfreq >= cutoff` by an integer cross-multiplication;
     the two agree on 142 M (a, b) pairs including every cutoff boundary for b up to 2^31 - 1."""
