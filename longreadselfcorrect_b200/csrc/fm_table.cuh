@@ -176,6 +176,38 @@ __host__ __device__ __forceinline__ Interval init_interval(const FmTable& t, int
     return r;
 }
 
+// BWT symbol at idx and the LF step from it: returns the symbol (0..3) or -1 for '$'; idx becomes C[b] + occ(b, idx - 1)
+// (RLBWT::getChar + getPC + getOcc, LongReadOverlap.cpp:713-718) from one 32-byte sector
+__host__ __device__ __forceinline__ int lf_step(const FmTable& t, uint64_t& idx)
+{
+    const uint64_t blk = idx >> 6;
+    const uint32_t off = (uint32_t)idx & 63u;
+    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
+    const uint4 cn = PBSC_LDG(bp);
+    const uint4 bs = PBSC_LDG(bp + 1);
+    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
+    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
+    const int c = (int)(((off < 32 ? w0 : w1) >> (2 * (off & 31))) & 3);
+    const bool has_dollar = (cn.x >> 31) != 0;
+    uint64_t dmask = 0;
+    if (has_dollar)
+    {
+        dmask = PBSC_LDG(t.dollar_mask + blk);
+        if ((dmask >> off) & 1) return -1;
+    }
+    uint32_t base = c == 0 ? (cn.x & 0x7fffffffu) : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
+    const uint64_t pat = 0x5555555555555555ull * (uint64_t)c;
+    const uint64_t x0 = w0 ^ pat, x1 = w1 ^ pat;
+    uint64_t m0 = ~(x0 | (x0 >> 1)) & 0x5555555555555555ull;
+    uint64_t m1 = ~(x1 | (x1 >> 1)) & 0x5555555555555555ull;
+    if (off < 32) { m0 &= (1ull << (2 * off)) - 1ull; m1 = 0; }
+    else { m1 &= (1ull << (2 * (off - 32))) - 1ull; }
+    uint64_t r = (uint64_t)base + PBSC_POPCLL(m0) + PBSC_POPCLL(m1);
+    if (c == 0 && has_dollar && off) r -= PBSC_POPCLL(dmask & ((1ull << off) - 1ull));
+    idx = t.C[c] + r;
+    return c;
+}
+
 // read one prefix-table entry (one 32-byte sector) and return the strand the caller wants
 __host__ __device__ __forceinline__ void prefix_lookup(const FmIndexDev& idx, uint64_t key, Interval& fwd, Interval& rvc)
 {

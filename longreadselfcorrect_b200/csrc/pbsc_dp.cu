@@ -67,38 +67,6 @@ __host__ __device__ inline uint64_t dp_job_bytes(uint32_t qlen, uint32_t maxLen,
     return align_up(align_up((size_t)qlen, 16) + (uint64_t)rows * dp_row_bytes(qlen, maxLen) + dp_msa_bytes(qlen), 128);
 }
 
-// BWT symbol at idx and the LF step from it: returns the symbol (0..3) or -1 for '$'; idx becomes C[b] + occ(b, idx - 1)
-// (RLBWT::getChar + getPC + getOcc, LongReadOverlap.cpp:713-718) from one 32-byte sector
-__device__ __forceinline__ int lf_step(const FmTable& t, uint64_t& idx)
-{
-    const uint64_t blk = idx >> 6;
-    const uint32_t off = (uint32_t)idx & 63u;
-    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
-    const uint4 cn = __ldg(bp);
-    const uint4 bs = __ldg(bp + 1);
-    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
-    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
-    const int c = (int)(((off < 32 ? w0 : w1) >> (2 * (off & 31))) & 3);
-    const bool has_dollar = (cn.x >> 31) != 0;
-    uint64_t dmask = 0;
-    if (has_dollar)
-    {
-        dmask = __ldg(t.dollar_mask + blk);
-        if ((dmask >> off) & 1) return -1;
-    }
-    uint32_t base = c == 0 ? (cn.x & 0x7fffffffu) : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
-    const uint64_t pat = 0x5555555555555555ull * (uint64_t)c;
-    const uint64_t x0 = w0 ^ pat, x1 = w1 ^ pat;
-    uint64_t m0 = ~(x0 | (x0 >> 1)) & 0x5555555555555555ull;
-    uint64_t m1 = ~(x1 | (x1 >> 1)) & 0x5555555555555555ull;
-    if (off < 32) { m0 &= (1ull << (2 * off)) - 1ull; m1 = 0; }
-    else { m1 &= (1ull << (2 * (off - 32))) - 1ull; }
-    uint64_t r = (uint64_t)base + __popcll(m0) + __popcll(m1);
-    if (c == 0 && has_dollar && off) r -= __popcll(dmask & ((1ull << off) - 1ull));
-    idx = t.C[c] + r;
-    return c;
-}
-
 // ---- stage 0: which failed walks get the fallback, and how many rows each one retrieves --------------------------------
 __global__ void __launch_bounds__(128)
 dp_collect_kernel(const __grid_constant__ FmIndexDev idx, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks,

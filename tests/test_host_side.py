@@ -91,6 +91,18 @@ def test_backward_search_primitives_match_reference_findinterval(tmp_path, flags
     assert r.returncode == 0 and r.stdout.startswith("ok: 4000 intervals"), r.stdout
 
 
+def test_lf_step_spells_every_read_of_the_reference_index(tmp_path):
+    """lf_step of csrc/fm_table.cuh (BWT symbol + LF-mapping from one sector: the step of dp_retrieve_kernel) compiled for the
+    host: LF-walking from the '$' rows of the reference-built tiny.bwt / tiny.rbwt spells each of the 396 reads exactly once."""
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", cuda_inc, os.path.join(ROOT, "tests", "cpp", "test_fm_lf.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe, GOLDEN], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok: 396 reads"), r.stdout
+
+
 def test_integer_ratio_rule_equals_the_reference_double_comparison(tmp_path):
     """eval4 (csrc/pbsc_walk_thread.cuh) replaces `(double)kmerFreq/(double)maxfreq >= cutoff` by an integer cross-multiplication;
     the two agree on 142 M (a, b) pairs including every cutoff boundary for b up to 2^31 - 1."""
