@@ -117,6 +117,33 @@ __host__ __device__ __forceinline__ uint64_t occ(const FmTable& t, int c, uint64
     return r;
 }
 
+// occurrences of all four bases in bwt[0, p) from one 32-byte sector
+__host__ __device__ __forceinline__ void occ4(const FmTable& t, uint64_t p, uint64_t r[4])
+{
+    PBSC_OCC_TICK(1);
+    const uint64_t blk = p >> 6;
+    const uint32_t off = (uint32_t)p & 63u;
+    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
+    const uint4 cn = PBSC_LDG(bp);
+    const uint4 bs = PBSC_LDG(bp + 1);
+    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
+    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
+    const uint64_t M = 0x5555555555555555ull;
+    uint64_t k0, k1;   // position masks: one bit per symbol kept
+    if (off < 32) { k0 = ((1ull << (2 * off)) - 1ull) & M; k1 = 0; }
+    else { k0 = M; k1 = ((1ull << (2 * (off - 32))) - 1ull) & M; }
+    const uint64_t l0 = w0 & M, h0 = (w0 >> 1) & M, l1 = w1 & M, h1 = (w1 >> 1) & M;
+    const uint32_t nT = PBSC_POPCLL(h0 & l0 & k0) + PBSC_POPCLL(h1 & l1 & k1);
+    const uint32_t nG = PBSC_POPCLL(h0 & ~l0 & k0) + PBSC_POPCLL(h1 & ~l1 & k1);
+    const uint32_t nC = PBSC_POPCLL(~h0 & l0 & k0) + PBSC_POPCLL(~h1 & l1 & k1);
+    uint32_t nA = off - nT - nG - nC;
+    if ((cn.x >> 31) && off) nA -= PBSC_POPCLL(PBSC_LDG(t.dollar_mask + blk) & ((1ull << off) - 1ull));
+    r[0] = (uint64_t)(cn.x & 0x7fffffffu) + nA;
+    r[1] = (uint64_t)cn.y + nC;
+    r[2] = (uint64_t)cn.z + nG;
+    r[3] = (uint64_t)cn.w + nT;
+}
+
 // occ(c, lo) and occ(c, hi) for lo <= hi: one sector load and one decode when both fall into the same 64-symbol block (the
 // usual case once an interval is down to ~coverage rows).  EXPERIMENT: used by update_interval only when the library is built
 // with -DPBSC_FUSED_UPDATE (not measured yet); checked against occ() on the host.

@@ -72,33 +72,6 @@ __device__ inline void carve(uint8_t* base, uint32_t node_cap, Caps c, TScratch&
     w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.start4 = w.pos4 = nullptr;
 }
 
-// occurrences of all four bases in bwt[0, p) from one 32-byte sector
-__device__ __forceinline__ void occ4(const FmTable& t, uint64_t p, uint64_t r[4])
-{
-    PBSC_OCC_TICK(1);
-    const uint64_t blk = p >> 6;
-    const uint32_t off = (uint32_t)p & 63u;
-    const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
-    const uint4 cn = __ldg(bp);
-    const uint4 bs = __ldg(bp + 1);
-    const uint64_t w0 = (uint64_t)bs.x | ((uint64_t)bs.y << 32);
-    const uint64_t w1 = (uint64_t)bs.z | ((uint64_t)bs.w << 32);
-    const uint64_t M = 0x5555555555555555ull;
-    uint64_t k0, k1;   // position masks: one bit per symbol kept
-    if (off < 32) { k0 = ((1ull << (2 * off)) - 1ull) & M; k1 = 0; }
-    else { k0 = M; k1 = ((1ull << (2 * (off - 32))) - 1ull) & M; }
-    const uint64_t l0 = w0 & M, h0 = (w0 >> 1) & M, l1 = w1 & M, h1 = (w1 >> 1) & M;
-    const uint32_t nT = __popcll(h0 & l0 & k0) + __popcll(h1 & l1 & k1);
-    const uint32_t nG = __popcll(h0 & ~l0 & k0) + __popcll(h1 & ~l1 & k1);
-    const uint32_t nC = __popcll(~h0 & l0 & k0) + __popcll(~h1 & l1 & k1);
-    uint32_t nA = off - nT - nG - nC;
-    if ((cn.x >> 31) && off) nA -= __popcll(__ldg(t.dollar_mask + blk) & ((1ull << off) - 1ull));
-    r[0] = (uint64_t)(cn.x & 0x7fffffffu) + nA;
-    r[1] = (uint64_t)cn.y + nC;
-    r[2] = (uint64_t)cn.z + nG;
-    r[3] = (uint64_t)cn.w + nT;
-}
-
 static __device__ __noinline__ Interval update1(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
 // one copy of occ4 for the four probes of a leaf: the level loop is bound by instruction fetch (ncu: the GPC instruction cache
 // runs at 86 % of its request peak with 84 KB of SASS), so hot code is kept small rather than inlined

@@ -1,4 +1,4 @@
-// Host check of the rank primitives of longreadselfcorrect_b200/csrc/fm_table.cuh (occ, occ_pair, count_dollars,
+// Host check of the rank primitives of longreadselfcorrect_b200/csrc/fm_table.cuh (occ, occ4, occ_pair, count_dollars,
 // update_interval: the code every kernel calls, compiled here for the host) against naive counting over random BWTs with '$'
 // symbols, block boundaries at every offset and lengths that are and are not multiples of 64.
 //   occ(c, p) = occurrences of base c in bwt[0, p) = RLBWT::getOcc(c, p - 1) (SuffixTools/RLBWT.h:121-140)
@@ -51,6 +51,13 @@ int main()
                 checks++;
                 if (occ(t, c, p) != pre[c + 1][p]) { if (bad++ < 5) printf("occ(%d, %llu) = %llu, naive %llu (n = %llu)\n", c, (unsigned long long)p, (unsigned long long)occ(t, c, p), (unsigned long long)pre[c + 1][p], (unsigned long long)n); }
             }
+        for (uint64_t p = 0; p <= n; p++)
+        {
+            uint64_t r4[4];
+            occ4(t, p, r4);   // the walk kernel's probe: all four counts from one sector
+            checks++;
+            for (int c = 0; c < 4; c++) if (r4[c] != pre[c + 1][p]) { if (bad++ < 5) printf("occ4(%llu)[%d] wrong\n", (unsigned long long)p, c); }
+        }
         for (int q = 0; q < 4000; q++)
         {
             uint64_t lo = rng() % (n + 1), hi = (q % 3 == 0) ? lo + rng() % 70 : rng() % (n + 1);
