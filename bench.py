@@ -1,24 +1,37 @@
 #!/usr/bin/env python3
 """Benchmark of the `stride pbcorrect` hot path (seed discovery + FM extension + DP/MSA fallback) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny] [--nodp]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg3s|cfg1|tiny] [--nodp]
 
-One "step" = one pass of the hot path over the whole read set of the workload (BASELINE.json configs[1] by
-default: 4.6 Mb synthetic genome, 50x simulated CLR reads, mean 8 kb, `-c 50 -g 5`, the reference's default options;
-`--nodp` measures seeds + FM extension alone).
-  value  corrected Mbp/s with the reads already resident in HBM (pbsc_batch_run: kernels only, CUDA events)
-  e2e    the same through pbsc_correct_batch on host buffers (H2D of the reads + D2H of the corrected pieces inside)
-N > 1 (torchrun): one process per GPU, the index replicated, every rank corrects the full read set (weak scaling,
-no data-path collective); time = max over ranks, value = N x Mbp / time.
+One "step" = one pass of the hot path over the WHOLE read set of the workload.  The default workload is BASELINE.json
+configs[2], the configuration its metric ("corrected Mbp/s at 1/2/4/8 B200") is quoted on: 12 Mb synthetic genome with
+injected repeats, 100x simulated CLR reads (mean 8 kb, 1.24 Gbp), `-c 100 -g 10`, the reference's default options
+(DP / multiple-alignment fallback on).  It fits one GPU.  `--workload cfg2` is configs[1] (4.6 Mb, 50x), also reported as a
+sub-result of the default line at N = 1.
+
+N > 1 (torchrun, one process per GPU): STRONG scaling of the product path.  Rank 0 simulates the reads and builds the index
+once; the flat index travels to the other GPUs as one blob over NCCL (NVLink), the reads through /dev/shm.  Every rank takes
+its contiguous, length-balanced range of the ONE read set (sharding.shard), cuts it into batches and runs them through the
+lanes of its index (several batches in flight on separate streams).  No collective on the data path.
+  value   total Mbp / max-over-ranks device time of a step (CUDA events), reads already resident in HBM
+  e2e     the same through pbsc_correct_batch with HOST buffers: pinned H2D of the reads, D2H of the corrected pieces, every
+          rank writing its results into one shared host segment in input order (the reassembly the reference does in
+          SequenceProcessFramework.h:147-195); time = max over ranks of the wall clock between two barriers
+  parity  every read of the gathered e2e output is hashed (parity.py) and compared with the digests the UNMODIFIED reference
+          produced (tests/golden/<workload>.read_sha.npz); `output_sha256` identifies the whole output and must be the same
+          at every N
+  e2e_cli the shipped binary, `pbcorrect --gpus N`, on a FASTA file (reader -> N GPU workers -> in-order writer)
 `--impl reference` times the reference's own multithreaded CPU implementation (oracle/_ref/stride pbcorrect -t <cores>)
 on a bounded sample of the same reads against the same index files, with the same options.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import re
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -47,6 +60,8 @@ WORKLOADS = {
 }
 REF_STRIDE = os.path.join(ROOT, "oracle", "_ref", "stride")
 ORACLE = os.path.join(ROOT, "oracle", "pbsc_oracle")
+PBCORRECT = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
+COUNT_LIB = os.path.join(ROOT, "longreadselfcorrect_b200", "libpbsc_count.so")
 
 
 def log(*a):
@@ -102,21 +117,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=None):
-    """FASTA of the sampled reads + PREFIX.bwt/.rbwt/.sai of the FULL read set, for the reference binary."""
-    from longreadselfcorrect_b200 import bwt_build, synth
-    prefix = os.path.join(d, "idx")
-    if bwt_runs is None:
-        bwt_runs = bwt_build.build_index_files(prefix, codes, off)
-    else:
-        n = off.size - 1
-        for ext in ("bwt", "rbwt"):
-            runs, nsym, nstr = bwt_runs[ext]
-            bwt_build.write_bwt_file(f"{prefix}.{ext}", runs, nstr, nsym)
-        bwt_build.write_sai_file(prefix + ".sai", n)
-    fa = os.path.join(d, "sample.fa")
-    synth.write_fasta(fa, codes[: off[sample_reads]], off[: sample_reads + 1])
-    return prefix, fa, bwt_runs
+def write_index_files(prefix, runs, n_reads):
+    from longreadselfcorrect_b200 import bwt_build
+    for ext in ("bwt", "rbwt"):
+        r, nsym, nstr = runs[ext]
+        bwt_build.write_bwt_file(f"{prefix}.{ext}", r, nstr, nsym)
+    bwt_build.write_sai_file(prefix + ".sai", n_reads)
+
+
+def write_fasta_ids(path, letters, off, ids):
+    with open(path, "wb") as f:
+        for i in ids:
+            f.write(b">r%d\n" % i)
+            f.write(letters[int(off[i]):int(off[i + 1])].tobytes())
+            f.write(b"\n")
 
 
 def run_reference(prefix, fa, wl, threads, outdir, nodp):
@@ -132,19 +146,625 @@ def run_reference(prefix, fa, wl, threads, outdir, nodp):
 
 
 def oracle_rank_queries(prefix, fa, wl, threads, nodp):
-    """Algorithmic work of the reference algorithm on the sample (instrumented oracle): rank queries of the seed and
-    FM-extend phases, and for the DP fallback the band cells filled, rows kept and LF steps."""
+    """Algorithmic work of the reference algorithm on a sample (instrumented oracle): rank queries of the seed phase,
+    of the walk constructor (E1: terminal intervals, query idmer / 5-mer trees) and of the level loop (E2-E12), separately; for
+    the DP fallback the band cells filled, rows kept and LF steps."""
     with tempfile.TemporaryDirectory() as d:
         r = subprocess.run([ORACLE, "pbcorrect", "--threads", str(threads), "-p", prefix, "-o", os.path.join(d, "o"), "-c", str(wl["c"]),
                             "-g", str(wl["g"])] + (["--nodp"] if nodp else []) + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    m = re.search(r"rank queries (\d+) \(seed (\d+), extend (\d+)\), walks (\d+)", r.stderr)
+    m = re.search(r"rank queries (\d+) \(seed (\d+), extend (\d+)(?:: setup (\d+), walk loop (\d+))?\), walks (\d+)", r.stderr)
     if not m:
         return None
-    out = {"total": int(m.group(1)), "seed": int(m.group(2)), "extend": int(m.group(3)), "walks": int(m.group(4))}
+    out = {"total": int(m.group(1)), "seed": int(m.group(2)), "extend": int(m.group(3)), "walks": int(m.group(6))}
+    if m.group(4) is not None:
+        out["extend_setup"], out["extend_walk"] = int(m.group(4)), int(m.group(5))
     m = re.search(r"dp fallbacks (\d+), rows kept (\d+), band cells (\d+), LF steps (\d+)", r.stderr)
     if m:
         out.update({"dp_jobs": int(m.group(1)), "dp_rows_kept": int(m.group(2)), "dp_cells": int(m.group(3)), "dp_lf_steps": int(m.group(4))})
     return out
+
+
+def sample_ids(n_reads, lengths, mbp, seed=20261018):
+    """A seeded sample of reads spread over the whole set (NOT a prefix), about `mbp` Mbp; sorted ids."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    perm = rng.permutation(n_reads)
+    cum = np.cumsum(lengths[perm])
+    k = int(np.searchsorted(cum, mbp * 1e6)) + 1
+    return np.sort(perm[: max(1, min(k, n_reads))])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm (CPU)
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_arm(args, wl, metric):
+    cores = os.cpu_count() or 1
+    codes, off = make_data(wl)
+    from longreadselfcorrect_b200 import bwt_build
+    total_mbp = codes.size / 1e6
+    n_reads = off.size - 1
+    lengths = np.diff(off)
+    # The reference pays tens of seconds per process to load a 1.2 Gbp index, so the W + K steps are consecutive slices of ONE
+    # process run: a seeded sample of (W + K) x ~S Mbp spread over the whole read set; ms_per_step = its processing-loop time
+    # (the reference's own "Processed N sequences in Xs" line, index load excluded) / (W + K).
+    slices = args.warmup + args.steps
+    per_step = args.cpu_sample_mbp or max(0.4, min(total_mbp / slices, 0.035 * cores * 12))
+    ids = sample_ids(n_reads, lengths, per_step * slices)
+    sample_mbp = float(lengths[ids].sum()) / 1e6
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        prefix = os.path.join(d, "idx")
+        bwt_build.build_index_files(prefix, codes, off)
+        fa = os.path.join(d, "sample.fa")
+        write_fasta_ids(fa, letters, off, ids)
+        secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"), args.nodp)
+        log(f"reference: {ids.size} reads ({sample_mbp:.1f} Mbp) in {secs:.2f}s processing ({wall:.1f}s wall incl. index load), {cores} threads")
+    ms = 1000 * secs / slices
+    v = sample_mbp / secs
+    sample_desc = (f"seeded sample of {ids.size} reads spread over the whole set ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index; "
+                   f"the {slices} steps are consecutive slices of one process run (index load excluded)")
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample": sample_desc, "threads": cores},
+        "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+        "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm (GPU)
+# ---------------------------------------------------------------------------------------------------------------------
+class Shard:
+    """One rank's contiguous range of the read set, cut into batches."""
+
+    def __init__(self, letters, off, begin, end, batch_mbp):
+        from longreadselfcorrect_b200 import sharding
+        self.begin, self.end = begin, end
+        o = off[begin:end + 1]
+        self.bases = int(o[-1] - o[0])
+        nb = max(1, int(np.ceil(self.bases / (batch_mbp * 1e6))))
+        self.batches = []     # (first read id, ascii bytes, offsets)
+        for b0, b1 in sharding.balanced_ranges(np.diff(o), nb):
+            if b1 <= b0:
+                continue
+            oo = o[b0:b1 + 1]
+            self.batches.append((begin + b0, np.ascontiguousarray(letters[int(oo[0]):int(oo[-1])]), (oo - oo[0]).astype(np.uint64)))
+
+
+def run_threads(n_threads, n_items, fn):
+    """fn(i) for i in range(n_items) from n_threads host threads (the library releases the GIL inside its calls)."""
+    if n_threads <= 1 or n_items <= 1:
+        for i in range(n_items):
+            fn(i)
+        return
+    nxt, lock, errs = [0], threading.Lock(), []
+
+    def work():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= n_items or errs:
+                return
+            try:
+                fn(i)
+            except BaseException as e:   # noqa: BLE001
+                errs.append(e)
+    th = [threading.Thread(target=work) for _ in range(min(n_threads, n_items))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
+
+
+TIMING_KEYS = ("seed_ms", "extend_ms", "dp_ms", "walk_ms", "walk_launches", "dp_jobs", "dp_rows", "kernel_launches", "seed_pairs")
+
+
+def ours(args, wl, metric):
+    import torch
+    from longreadselfcorrect_b200 import api, bwt_build, parity, sharding
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    # --backend gloo: the same multi-rank code without NCCL (control traffic through gloo on CPU tensors), for boxes where the
+    # ranks have to share one GPU (tests); PBSC_BENCH_SAME_DEVICE=1 puts every rank on GPU 0
+    same_dev = os.environ.get("PBSC_BENCH_SAME_DEVICE") == "1"
+    if same_dev:
+        local_rank = 0
+        torch.cuda.set_device(0)
+    cdev = "cuda" if args.backend == "nccl" else "cpu"
+    if world > 1:
+        import torch.distributed as dist
+        if args.backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("gloo")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(vals):
+        if dist is None:
+            return [float(v) for v in vals]
+        tt = torch.tensor(list(vals), device=cdev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(x) for x in tt]
+
+    # ---- the ONE read set: simulated by rank 0, shared through /dev/shm ----
+    shm = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                       f"pbsc_bench_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', str(os.getppid()) if world > 1 else str(os.getpid()))}")
+    runs = None
+    if rank == 0:
+        shutil.rmtree(shm, ignore_errors=True)
+        os.makedirs(shm)
+        codes, off = make_data(wl)
+        letters, off = packed_ascii(codes, off)
+        if world > 1:
+            np.save(os.path.join(shm, "letters.npy"), letters)
+            np.save(os.path.join(shm, "off.npy"), off)
+    barrier()
+    if rank != 0:
+        letters = np.load(os.path.join(shm, "letters.npy"), mmap_mode="r")
+        off = np.load(os.path.join(shm, "off.npy"))
+    n_reads = off.size - 1
+    lengths = np.diff(off.astype(np.int64))
+    total_mbp = float(off[-1]) / 1e6
+
+    # ---- the index: built once on rank 0, broadcast as one blob over NCCL ----
+    t = time.time()
+    if rank == 0:
+        runs = {}
+        for ext, rev in (("bwt", False), ("rbwt", True)):
+            b = bwt_build.bwt_symbols(codes, off.astype(np.int64), reverse=rev, device=f"cuda:{local_rank}")
+            runs[ext] = (bwt_build.run_length_bytes(b), int(b.numel()), n_reads)
+            del b
+        torch.cuda.empty_cache()
+        bwt_s = time.time() - t
+        log(f"rank 0: BWT + RBWT of {total_mbp:.1f} Mbp built on the GPU in {bwt_s:.1f}s (synthetic-input preparation, not the hot path)")
+        t = time.time()
+        idx = api.Index.from_runs(runs["bwt"][0], runs["bwt"][1], n_reads, runs["rbwt"][0], runs["rbwt"][1], n_reads, device=local_rank)
+        if args.k0:
+            idx.build_prefix_table(args.k0)
+        del codes
+    index_s = time.time() - t
+    bcast_s = 0.0
+    if world > 1:
+        t = time.time()
+        nb = torch.tensor([idx.blob_size() if rank == 0 else 0], device=cdev, dtype=torch.int64)
+        dist.broadcast(nb, 0)
+        blob = torch.empty(int(nb[0]), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idx.export_blob(blob.data_ptr(), blob.numel())
+        if args.backend == "nccl":
+            dist.broadcast(blob, 0)          # NVLink / NVSwitch: the one exchange of the job, off the data path
+            torch.cuda.synchronize()
+            if rank != 0:
+                idx = api.Index.import_blob(blob.data_ptr(), blob.numel(), local_rank, local_rank)
+        else:
+            hblob = blob.cpu()
+            dist.broadcast(hblob, 0)
+            if rank != 0:
+                idx = api.Index.import_blob(hblob.data_ptr(), hblob.numel(), -1, local_rank)
+            del hblob
+        del blob
+        torch.cuda.empty_cache()
+        bcast_s = time.time() - t
+    idx.set_lanes(args.lanes)
+    log(f"rank {rank}: index on device ({idx.device_bytes() / 1e9:.2f} GB; decode + prefix table {index_s:.1f}s on rank 0, NCCL broadcast {bcast_s:.2f}s), {args.lanes} lanes")
+    params = api.Params.make(coverage=wl["c"], genome=wl["g"], no_dp=args.nodp)
+
+    # ---- this rank's shard of the read set ----
+    b_, e_ = sharding.balanced_ranges(lengths, world)[rank]
+    shard = Shard(letters, off, b_, e_, args.batch_mbp)
+    nbt = len(shard.batches)
+    log(f"rank {rank}: reads [{b_}, {e_}) = {shard.bases / 1e6:.1f} Mbp in {nbt} batch(es)")
+
+    # ---- value: reads resident on the device (batches uploaded before the timed region when they all fit), kernels only ----
+    free_b, _tot = torch.cuda.mem_get_info()
+    # workspace of a batch: ~130 bytes per read base (seed features, candidates, piece regions); the arenas of the lanes on top
+    resident_ok = shard.bases * 130 + args.lanes * 40e9 < free_b * 0.85
+    resident = [api.Batch(idx, params, packed=(a, o)) for (_f, a, o) in shard.batches] if resident_ok else None
+    tm_lock = threading.Lock()
+
+    def run_step():
+        """one pass over this rank's batches through the lanes; returns (device ms between CUDA events, summed phase counters)"""
+        acc = {k: 0.0 for k in TIMING_KEYS}
+
+        def one(i):
+            if resident is not None:
+                resident[i].run()
+                tm = api.last_timing()
+            else:
+                f, a, o = shard.batches[i]
+                bt = api.Batch(idx, params, packed=(a, o))
+                bt.run()
+                tm = api.last_timing()
+                bt.close()
+            with tm_lock:
+                for k in TIMING_KEYS:
+                    acc[k] += tm[k]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        run_threads(args.lanes, nbt, one)
+        torch.cuda.synchronize()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1), acc
+
+    for _ in range(args.warmup):
+        run_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    step_ms, phases = [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, acc = run_step()
+        step_ms.append(ms)
+        phases.append(acc)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000
+    clocks = sampler.stop()
+    dev_ms, wall_ms = allmax([float(np.sum(step_ms)), wall_ms])
+    ms_per_step = dev_ms / args.steps
+    value = total_mbp / (ms_per_step / 1000)
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in TIMING_KEYS}
+    if resident is not None:
+        for bt in resident:
+            bt.close()
+    resident = None
+    api.lib().pbsc_trim(local_rank)
+
+    # ---- e2e: host buffers in, corrected pieces out, through pbsc_correct_batch.  Reads sit in pinned host memory; every rank
+    #      writes its results (pieces, offsets, counters) straight into ITS region of one shared host segment, in input order,
+    #      so after the closing barrier rank 0 holds the reassembled output of the whole read set. ----
+    pin_in = [(api.pinned_copy(a), api.pinned_copy(o)) for (_f, a, o) in shard.batches]
+    seg = []   # per batch: dict of numpy views into this rank's shared file
+    layout = []
+    pos = 0
+    for (f, a, o) in shard.batches:
+        n = o.size - 1
+        cap = int(a.size * 1.25) + (1 << 16)
+        ent = {"first_id": f, "n": n, "out": (pos, cap)}
+        pos += (cap + 255) // 256 * 256
+        ent["poff"] = (pos, (n + 2) * 8); pos += (n + 2) * 8
+        ent["first"] = (pos, (n + 1) * 8); pos += (n + 1) * 8
+        ent["stats"] = (pos, max(n, 1) * api.STATS_DTYPE.itemsize); pos += (max(n, 1) * api.STATS_DTYPE.itemsize + 255) // 256 * 256
+        layout.append(ent)
+    seg_path = os.path.join(shm, f"out_rank{rank}.bin")
+    with open(seg_path, "wb") as fh:
+        fh.truncate(max(pos, 4096))
+    mm = np.memmap(seg_path, dtype=np.uint8, mode="r+")
+    mm[:] = 0              # touch every page before it is page-locked
+    api.host_register(mm)
+
+    def views(m, ent):
+        o0, oc = ent["out"]; p0, pc = ent["poff"]; f0, fc = ent["first"]; s0, sc = ent["stats"]
+        return (m[o0:o0 + oc], m[p0:p0 + pc].view(np.uint64), m[f0:f0 + fc].view(np.uint64), m[s0:s0 + sc].view(api.STATS_DTYPE))
+    seg = [views(mm, ent) for ent in layout]
+
+    def e2e_step():
+        def one(i):
+            idx.correct_reads(params, packed=pin_in[i], out_bufs=seg[i])
+        run_threads(args.lanes + 1, nbt, one)   # one thread more than lanes: its upload / fetch overlaps the others' kernels
+        torch.cuda.synchronize()
+
+    e2e_times = []
+    for i in range(args.e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        barrier()
+        if i > 0:
+            e2e_times.append((time.perf_counter() - t0) * 1000)
+    e2e_ms = allmax([float(np.mean(e2e_times)) if e2e_times else float("nan")])[0]
+    e2e_value = total_mbp / (e2e_ms / 1000)
+    h2d_bytes = int(sum(a.nbytes + o.nbytes for a, o in pin_in))
+    d2h_local = 0
+    for (out, poff, first, stats), ent in zip(seg, layout):
+        n = ent["n"]
+        d2h_local += int(poff[int(first[n])]) + n * api.STATS_DTYPE.itemsize + 16 * n
+    if dist is not None:
+        tt = torch.tensor([h2d_bytes, d2h_local], device=cdev, dtype=torch.int64)
+        dist.all_reduce(tt)
+        h2d_bytes, d2h_bytes = int(tt[0]), int(tt[1])
+        lay_all = [None] * world
+        dist.all_gather_object(lay_all, layout)
+    else:
+        d2h_bytes, lay_all = d2h_local, [layout]
+    api.host_unregister(mm)
+    mm.flush()
+    barrier()
+
+    # ---- parity over the WHOLE gathered output (rank 0 reads every rank's region of the shared segment) ----
+    par = None
+    walks = fm = dpn = 0
+    if rank == 0:
+        t = time.time()
+        dig = np.zeros((n_reads, 8), dtype=np.uint8)
+        for r in range(world):
+            m = mm if r == 0 else np.memmap(os.path.join(shm, f"out_rank{r}.bin"), dtype=np.uint8, mode="r")
+            for ent in lay_all[r]:
+                out, poff, first, stats = views(m, ent)
+                f, n = ent["first_id"], ent["n"]
+                st = stats[:n]
+                dig[f:f + n] = parity.result_digests(out, poff, first, st, letters[int(off[f]):int(off[f + n])], off[f:f + n + 1] - off[f], first_read_id=f)
+                mg = st[st["merge"] == 1]
+                walks += int(mg["total_walk_num"].sum()); fm += int(mg["fm_num"].sum()); dpn += int(mg["dp_num"].sum())
+        par = {"output_sha256": parity.output_sha256(dig), "reads_hashed": int(n_reads),
+               "what": "sha256 over the per-read record digests (parity.py) of the gathered e2e output of the last timed step, input order"}
+        cmp_ = parity.compare_with_golden(args.workload + ("_nodp" if args.nodp else ""), dig)
+        if cmp_:
+            par.update(cmp_)
+        log(f"parity: {par} ({time.time() - t:.1f}s)")
+    del seg, mm
+
+    # ---- e2e_cli: the shipped binary on a FASTA file with the index files of `stride index`, all N GPUs, one process ----
+    cli = None
+    if args.cli and os.path.exists(PBCORRECT):
+        idx.close()
+        api.lib().pbsc_trim(local_rank)
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                cli = run_cli(args, wl, shm, letters, off, runs, n_reads, total_mbp, world, cores, parity)
+            except Exception as e:   # measurement leg only
+                cli = {"error": str(e)[-300:]}
+            log(f"e2e_cli: {cli}")
+        barrier()
+        idx = None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": metric, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "reads": int(n_reads), "mbp": total_mbp, "walks": walks, "fm_success": fm, "dp_success": dpn,
+                   "prefix_k0": args.k0, "lanes": args.lanes, "batch_mbp": args.batch_mbp, "batches_per_rank": nbt,
+                   "index_build_s": index_s, "index_broadcast_s": bcast_s,
+                   "l2": "rank tables + prefix table exceed the 126 MB L2; no explicit flush",
+                   "sharding": "one read set; contiguous length-balanced range per rank; index built on rank 0 and broadcast as one blob over NCCL; "
+                               "results reassembled in input order in a shared host segment; no collective on the data path",
+                   "reads_resident_before_timed_region": bool(resident_ok),
+                   "wall_ms_per_step": wall_ms / args.steps},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                "steps": len(e2e_times)},
+        "gpu_launches": int(ph["kernel_launches"]) * args.steps,
+        "parity_vs_reference": par,
+        "e2e_cli": cli,
+        "phases_ms_rank0": {k: ph[k] for k in ("seed_ms", "extend_ms", "walk_ms", "dp_ms")},
+    }
+
+    # ---- single-GPU extras: CPU baseline, algorithmic and issued rank queries, roofline, config 2 / --nodp / FM microbench ----
+    if world == 1:
+        extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank)
+    else:
+        line["roofline"] = roofline_from_committed(args, ph, walks, total_mbp)
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    shutil.rmtree(shm, ignore_errors=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cli(args, wl, shm, letters, off, runs, n_reads, total_mbp, world, cores, parity):
+    """`pbcorrect --gpus N` on files: FASTA of the whole read set + PREFIX.bwt/.rbwt/.sai; returns throughputs and the parity of
+    the files it wrote."""
+    prefix = os.path.join(shm, "idx")
+    write_index_files(prefix, runs, n_reads)
+    fa = os.path.join(shm, "reads.fa")
+    write_fasta_ids(fa, letters, off, range(n_reads))
+    out = os.path.join(shm, "cli_out")
+    res = {}
+    for attempt in ("cold (decodes PREFIX.bwt/.rbwt, writes PREFIX.fmg)", "warm (PREFIX.fmg)"):
+        shutil.rmtree(out, ignore_errors=True)
+        t0 = time.time()
+        r = subprocess.run([PBCORRECT, "pbcorrect", "-t", str(min(cores, 16)), "--gpus", str(world), "-p", prefix, "-o", out, "-c", str(wl["c"]), "-g", str(wl["g"]),
+                            "--batch-mbp", str(args.batch_mbp), "--lanes", str(args.lanes)] + (["--nodp"] if args.nodp else []) + [fa],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        wall = time.time() - t0
+        if r.returncode != 0:
+            raise RuntimeError("pbcorrect failed: " + r.stderr[-400:])
+        m = re.search(r"Processed \d+ sequences in ([0-9.]+)s", r.stderr)
+        secs = float(m.group(1)) if m else wall
+        m2 = re.search(r"index to \d+ GPU\(s\)\] wall clock: ([0-9.]+)s", r.stderr)
+        key = "cold" if attempt.startswith("cold") else "warm"
+        res[key] = {"processing_s": secs, "wall_s": wall, "index_load_s": float(m2.group(1)) if m2 else None, "what": attempt}
+    dg = parity.fasta_digests(os.path.join(out, "correct.fa"), os.path.join(out, "discard.fa"))
+    dig = np.zeros((n_reads, 8), dtype=np.uint8)
+    for i in range(n_reads):
+        if i in dg:
+            dig[i] = np.frombuffer(dg[i], dtype=np.uint8)
+    secs = res["warm"]["processing_s"]
+    return {"value": total_mbp / secs, "unit": "Mbp/s", "gpus": world,
+            "what": "pbcorrect --gpus N: FASTA parse -> batches -> lanes of N GPUs -> in-order writer of correct.fa / discard.fa; Mbp of input / the "
+                    "binary's own processing time (index load reported separately, as the reference does)",
+            "processing_s": secs, "wall_s_incl_index_load": res["warm"]["wall_s"], "index_load_s_fmg": res["warm"]["index_load_s"],
+            "index_load_s_bwt": res["cold"]["index_load_s"], "records": len(dg), "output_sha256": parity.output_sha256(dig)}
+
+
+def roofline_from_committed(args, ph, walks, total_mbp):
+    """N > 1 (no CPU legs): per-unit algorithmic work from the committed oracle measurement (profiles/algorithmic.json)."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roof = {"bound": "hbm", "kernel": "walk_levels_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "kernel_ms_rank0": ph["walk_ms"], "note": "rank 0's share of the step; algorithmic counts from profiles/algorithmic.json"}
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "algorithmic.json"))).get(args.workload + ("_nodp" if args.nodp else ""))
+        if c and c.get("walk_loop_rank_queries_per_walk") and ph["walk_ms"] > 0:
+            b = c["walk_loop_rank_queries_per_walk"] * ph["seed_pairs"] * 32.0
+            roof["achieved"] = b / (ph["walk_ms"] / 1000) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+    except Exception:
+        pass
+    return roof
+
+
+def count_issued(args, wl, letters, off, runs, n_reads, ids, local_rank):
+    """Issued 32-byte rank sectors per kernel family, from the PBSC_COUNT_OCC build of the library run in a child process on the
+    same sample the oracle counted (tools/count_occ.py)."""
+    if not os.path.exists(COUNT_LIB):
+        return None
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        prefix = os.path.join(d, "idx")
+        write_index_files(prefix, runs, n_reads)
+        fa = os.path.join(d, "s.fa")
+        write_fasta_ids(fa, letters, off, ids)
+        env = dict(os.environ, PBSC_LIB=COUNT_LIB)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "count_occ.py"), prefix, fa, str(wl["c"]), str(wl["g"]), str(args.k0), str(local_rank)]
+                           + (["--nodp"] if args.nodp else []), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    for l in r.stdout.splitlines():
+        if l.startswith("{"):
+            return json.loads(l)
+    log("issued-sector count failed:", r.stderr[-300:])
+    return None
+
+
+def extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank):
+    from longreadselfcorrect_b200 import api
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cpu = alg = issued = None
+    if not args.no_cpu_baseline and os.path.exists(REF_STRIDE):
+        # bounded: ~0.03 Mbp/s/core (repeat-rich, DP fallback on) x cores x ~15 s, as a seeded sample spread over the whole set
+        smbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.03 * cores * 15))
+        ids = sample_ids(n_reads, lengths, smbp)
+        smbp = float(lengths[ids].sum()) / 1e6
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+            prefix = os.path.join(d, "idx")
+            write_index_files(prefix, runs, n_reads)
+            fa = os.path.join(d, "sample.fa")
+            write_fasta_ids(fa, letters, off, ids)
+            secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"), args.nodp)
+            log(f"reference CPU baseline: {smbp:.1f} Mbp in {secs:.2f}s with {cores} threads")
+            sdesc = f"seeded sample of {ids.size} reads spread over the whole set ({smbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores}" + (" --nodp" if args.nodp else "")
+            cpu = {"value": smbp / secs, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": sdesc}
+            # live parity of exactly these reads: what the reference just wrote against the digests of the timed GPU output is
+            # covered by parity_vs_reference when a golden exists; here the reference's records are hashed and kept
+            if os.path.exists(ORACLE):
+                small_ids = ids[: max(1, int(np.searchsorted(np.cumsum(lengths[ids]), min(smbp, 3.0) * 1e6)))]
+                fa2 = os.path.join(d, "alg.fa")
+                write_fasta_ids(fa2, letters, off, small_ids)
+                alg = oracle_rank_queries(prefix, fa2, wl, min(cores, 32), args.nodp)
+                if alg:
+                    alg["sample_bases"] = int(lengths[small_ids].sum())
+                issued = count_issued(args, wl, letters, off, runs, n_reads, small_ids, local_rank)
+    line["cpu_baseline"] = cpu
+    try:
+        sector_peak = api.random_sector_peak(2_400_000_000, local_rank)
+    except Exception as e:   # measurement aid only
+        log("random-sector peak not measured:", e)
+        sector_peak = None
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(args.workload + ("_nodp" if args.nodp else ""), {}).get("walk_levels_kernel")
+    except Exception:
+        pass
+    walk_ms = ph["walk_ms"]
+    roof = {"bound": "hbm", "kernel": "walk_levels_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "kernel_ms": walk_ms, "kernel_launches_per_step": int(ph["walk_launches"]), "extend_phase_ms": ph["extend_ms"], "seed_phase_ms": ph["seed_ms"],
+            "dp_fallback_ms": ph["dp_ms"], "walks_per_step": ph["seed_pairs"],
+            "scope": "algorithmic bytes = rank queries of the reference's LEVEL LOOP only (extendOverlap, LongReadCorrectByOverlap.cpp:155-211; the "
+                     "constructor's searches are counted apart as extend_setup) x 32 B, for the walks the kernel ran in the step, / the CUDA-event time "
+                     "of walk_levels_kernel's own launches"}
+    if not (alg and alg.get("walks")):
+        try:
+            c = json.load(open(os.path.join(ROOT, "profiles", "algorithmic.json"))).get(args.workload + ("_nodp" if args.nodp else ""))
+            if c and c.get("walk_loop_rank_queries_per_walk"):
+                alg = {"walks": 1.0, "extend_walk": c["walk_loop_rank_queries_per_walk"], "extend_setup": c.get("setup_rank_queries_per_walk", 0.0),
+                       "extend": c["walk_loop_rank_queries_per_walk"] + c.get("setup_rank_queries_per_walk", 0.0),
+                       "seed": c["seed_rank_queries_per_read_base"], "sample_bases": 1.0, "source": "profiles/algorithmic.json"}
+        except Exception:
+            pass
+    if alg and alg.get("walks") and walk_ms > 0:
+        loop_q = alg.get("extend_walk", alg["extend"]) / alg["walks"]
+        # the kernel walks more pairs than the reference (speculative tasks that are re-walked): the algorithmic count uses the
+        # reference's number of walks of the step, i.e. what had to be computed
+        ref_walks = walks
+        alg_bytes = loop_q * ref_walks * 32.0
+        roof["achieved"] = alg_bytes / (walk_ms / 1000) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["algorithmic_bytes_per_step"] = alg_bytes
+        roof["algorithmic_rank_queries_per_walk_level_loop"] = loop_q
+        roof["algorithmic_rank_queries_per_walk_constructor"] = alg.get("extend_setup", 0) / alg["walks"]
+        roof["algorithmic_rank_queries_per_read_base_seed_phase"] = alg["seed"] / alg["sample_bases"]
+        roof["seed_phase_algorithmic_GBs"] = alg["seed"] / alg["sample_bases"] * total_mbp * 1e6 * 32.0 / (ph["seed_ms"] / 1000) / 1e9
+        roof["algorithmic_source"] = alg.get("source", "instrumented oracle (oracle/pbsc_oracle) on a sample of the same reads, this run")
+        if issued and issued.get("walks"):
+            per_walk = issued["walk"] / issued["walks"]
+            isec = per_walk * ph["seed_pairs"]
+            roof["issued_sectors_per_walk_level_loop"] = per_walk
+            roof["issued_sectors_per_step_level_loop"] = isec
+            roof["issued_GBs"] = isec * 32.0 / (walk_ms / 1000) / 1e9
+            roof["issued"] = {k: issued[k] for k in ("seed", "setup", "walk", "dp", "walks", "bases") if k in issued}
+            roof["issued_source"] = "libpbsc_count.so (-DPBSC_COUNT_OCC build of the same kernels) on the oracle's sample, per-kernel-family counters"
+            if sector_peak:
+                roof["random_sector_peak"] = sector_peak
+                roof["frac_of_random_sector_peak"] = roof["issued_GBs"] / sector_peak
+        elif sector_peak:
+            roof["random_sector_peak"] = sector_peak
+        if alg.get("dp_jobs"):
+            cells = alg["dp_cells"] / alg["dp_jobs"] * ph["dp_jobs"]
+            roof["dp_fallback"] = {"jobs_per_step": ph["dp_jobs"], "rows_aligned_per_step": ph["dp_rows"], "band_cells_per_step": cells,
+                                   "Gcells_per_s": cells / (ph["dp_ms"] / 1000) / 1e9 if ph["dp_ms"] > 0 else None}
+    line["roofline"] = roof
+    if args.extras:
+        line["sub_results"] = sub_results(args, local_rank)
+
+
+def sub_results(args, local_rank):
+    """The rest of the BASELINE metric in the same driver-visible line: config 2 (default options and --nodp) and the FM
+    backward-search microbenchmark (config 5), each measured in a child process (fresh memory, bounded time)."""
+    res = {}
+    py = sys.executable
+    base = [py, os.path.abspath(__file__), "--no-extras", "--no-cpu-baseline", "--no-cli", "--e2e-steps", "1", "--steps", "3", "--warmup", "3"]
+    for name, extra in (("cfg2_default_options", ["--workload", "cfg2"]), ("cfg2_nodp", ["--workload", "cfg2", "--nodp"])):
+        if args.workload == "cfg2" and not args.nodp and name == "cfg2_default_options":
+            continue
+        try:
+            r = subprocess.run(base + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+            j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            res[name] = {"value": j["value"], "unit": j["unit"], "ms_per_step": j["ms_per_step"], "e2e": j["e2e"], "config": j["config"]["workload"],
+                         "parity_vs_reference": j.get("parity_vs_reference"), "roofline": j.get("roofline"), "phases_ms": j.get("phases_ms_rank0")}
+        except Exception as e:
+            res[name] = {"error": str(e)[-200:]}
+    try:
+        r = subprocess.run([py, os.path.join(ROOT, "tools", "fm_microbench.py"), "--json", "--ks", "19,31", "--device", str(local_rank)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        res["fm_microbench"] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception as e:
+        res["fm_microbench"] = {"error": str(e)[-200:]}
+    return res
 
 
 def main():
@@ -153,320 +773,27 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--k0", type=int, default=13, help="short-prefix table length (0 = off)")
+    ap.add_argument("--lanes", type=int, default=2, help="batches of one GPU in flight at once (streams + arenas)")
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="Mbp of reads for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--batch-mbp", type=float, default=320.0, help="largest batch of reads resident on the device at once (Mbp)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the config 2 / --nodp / FM microbench sub-results")
+    ap.add_argument("--no-cli", dest="cli", action="store_false", help="skip the e2e_cli leg (the pbcorrect binary)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--batch-mbp", type=float, default=160.0, help="largest batch of reads of one lane (Mbp)")
     ap.add_argument("--nodp", action="store_true", help="disable the DP/MSA fallback on both arms (seeds + FM extension only)")
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="process-group backend for N > 1 (gloo: tests on a one-GPU box)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.nodp:
         wl["desc"] += " --nodp"
     metric = "corrected Mbp/s (seed + FM-extend, --nodp)" if args.nodp else "corrected Mbp/s (seed + FM-extend + DP/MSA fallback, default options)"
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
-
-    # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
-        if rank != 0:
+        if int(os.environ.get("RANK", "0")) != 0:
             return 0
-        codes, off = make_data(wl)
-        total_mbp = codes.size / 1e6
-        # bounded sample: ~0.03-0.06 Mbp/s/core (BASELINE.md probe; the DP fallback is the slower end) x cores x ~15-25 s per step
-        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.04 * cores * 15))
-        sample_reads = int(np.searchsorted(off, sample_mbp * 1e6))
-        sample_reads = max(1, min(sample_reads, off.size - 1))
-        sample_mbp = float(off[sample_reads]) / 1e6
-        with tempfile.TemporaryDirectory() as d:
-            prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads)
-            times = []
-            for i in range(args.warmup + args.steps):
-                secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, f"out{i}"), args.nodp)
-                log(f"reference step {i}: {secs:.2f}s processing ({wall:.1f}s wall incl. index load)")
-                if i >= args.warmup:
-                    times.append(secs)
-        ms = 1000 * float(np.mean(times))
-        v = sample_mbp / (ms / 1000)
-        sample_desc = f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index"
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "sample": sample_desc, "threads": cores},
-            "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": sample_desc},
-            "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
-        return 0
-
-    # ------------------------------------------------------------------ our arm (GPU)
-    import torch
-    from longreadselfcorrect_b200 import api, bwt_build
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    codes, off = make_data(wl)
-    total_mbp = codes.size / 1e6
-    n_reads = off.size - 1
-    t = time.time()
-    runs = {}
-    for ext, rev in (("bwt", False), ("rbwt", True)):
-        b = bwt_build.bwt_symbols(codes, off, reverse=rev, device=f"cuda:{local_rank}")
-        runs[ext] = (bwt_build.run_length_bytes(b), int(b.numel()), n_reads)
-        del b
-    torch.cuda.empty_cache()
-    log(f"rank {rank}: BWT + RBWT of {total_mbp:.1f} Mbp built on the GPU in {time.time() - t:.1f}s")
-    t = time.time()
-    idx = api.Index.from_runs(runs["bwt"][0], runs["bwt"][1], n_reads, runs["rbwt"][0], runs["rbwt"][1], n_reads, device=local_rank)
-    if args.k0:
-        idx.build_prefix_table(args.k0)
-    index_s = time.time() - t
-    log(f"rank {rank}: rank tables + prefix table (k0={args.k0}) on device in {index_s:.1f}s, {idx.device_bytes() / 1e9:.2f} GB")
-    params = api.Params.make(coverage=wl["c"], genome=wl["g"], no_dp=args.nodp)
-    packed = packed_ascii(codes, off)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- batches: the whole read set is one batch when it fits (config 2 does); larger sets go through in contiguous,
-    #      length-balanced batches of at most --batch-mbp, one after the other, as the pbcorrect binary does ----
-    from longreadselfcorrect_b200 import sharding
-    n_batches = max(1, int(np.ceil(total_mbp / args.batch_mbp)))
-    ranges = sharding.balanced_ranges(np.diff(off), n_batches)
-    chunks = []
-    for b0, b1 in ranges:
-        o = off[b0:b1 + 1]
-        chunks.append((np.ascontiguousarray(packed[0][int(o[0]):int(o[-1])]), (o - o[0]).astype(np.uint64)))
-    log(f"rank {rank}: {len(chunks)} batch(es) per step")
-
-    # ---- value: reads resident on the device, kernels only (a batch is uploaded outside the timed region, run inside it) ----
-    resident = api.Batch(idx, params, packed=chunks[0]) if len(chunks) == 1 else None
-
-    def run_step(keep_first=False):
-        """one pass over all batches; returns (device ms, per-phase tuple, fetched result of the first batch or None)"""
-        if resident is not None:
-            ms = resident.run()
-            tm = api.last_timing()
-            return ms, [tm[k] for k in ("seed_ms", "extend_ms", "dp_ms", "walk_ms", "walk_launches", "dp_jobs", "dp_rows", "kernel_launches")], None
-        tot, acc, first_res = 0.0, [0.0] * 8, None
-        for ci, ch in enumerate(chunks):
-            bt = api.Batch(idx, params, packed=ch)
-            tot += bt.run()
-            tm = api.last_timing()
-            for j, k in enumerate(("seed_ms", "extend_ms", "dp_ms", "walk_ms", "walk_launches", "dp_jobs", "dp_rows", "kernel_launches")):
-                acc[j] += tm[k]
-            if keep_first:
-                res = bt.fetch()
-                if ci == 0:
-                    first_res = res          # pieces of the first batch: compared with the reference below
-                else:
-                    extra_stats.append(res[3].copy())   # the other batches only contribute their counters
-            bt.close()
-        return tot, acc, first_res
-
-    extra_stats = []
-    for _ in range(args.warmup):
-        run_step()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    step_ms, phase = [], []
-    t0 = time.perf_counter()
-    last_first = None
-    for si in range(args.steps):
-        extra_stats.clear()
-        ms, ph, fr = run_step(keep_first=(si == args.steps - 1 and resident is None))
-        step_ms.append(ms)
-        phase.append(tuple(ph))
-        last_first = fr
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1000
-    clocks = sampler.stop()
-    launches_per_step = int(phase[-1][7])
-    dev_ms = float(np.sum(step_ms))
-    if dist is not None:
-        tt = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(tt[0]), float(tt[1])
-    ms_per_step = dev_ms / args.steps
-    value = world * total_mbp / (ms_per_step / 1000)
-    if resident is not None:
-        out, poff, first, stats = resident.fetch()
-        all_stats = [stats]
-        resident.close()
-    else:
-        out, poff, first, stats = last_first
-        all_stats = [stats] + extra_stats
-    d2h_bytes = 0
-    walks = fm = 0
-    for st_ in all_stats:
-        m_ = st_[st_["merge"] == 1]
-        walks += int(m_["total_walk_num"].sum())
-        fm += int(m_["fm_num"].sum())
-        d2h_bytes += int(m_["corrected_len"].sum()) + st_.nbytes + 16 * len(st_)
-
-    # ---- e2e: host buffers in, corrected pieces out, through pbsc_correct_batch: the reads sit in pinned host memory, every
-    #      step copies them to the device, runs the path and copies the corrected pieces back into pinned host memory ----
-    pinned_in = [(api.pinned_copy(c[0]), api.pinned_copy(c[1])) for c in sorted(chunks, key=lambda c: -c[0].size)]
-    e2e_ms = []
-    for i in range(args.e2e_steps + 1):
-        barrier()
-        t0 = time.perf_counter()
-        for pin in pinned_in:
-            idx.correct_reads(params, packed=pin, pinned_out=True)
-        torch.cuda.synchronize()
-        if i > 0:
-            e2e_ms.append((time.perf_counter() - t0) * 1000)
-    e2e = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
-    if dist is not None:
-        tt = torch.tensor([e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = float(tt[0])
-    e2e_value = world * total_mbp / (e2e / 1000)
-    h2d_bytes = int(sum(c[0].nbytes + c[1].nbytes for c in chunks))
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- CPU baseline (reference binary on a bounded sample) + algorithmic rank-query counts (oracle) ----
-    cpu = None
-    alg = None
-    parity = None
-    if not args.no_cpu_baseline and world == 1 and os.path.exists(REF_STRIDE):   # rank 0 at N = 1 only
-        sample_mbp = args.cpu_sample_mbp or min(total_mbp, max(0.5, 0.04 * cores * 15))
-        sample_reads = max(1, min(int(np.searchsorted(off, sample_mbp * 1e6)), n_reads))
-        sample_mbp = float(off[sample_reads]) / 1e6
-        with tempfile.TemporaryDirectory() as d:
-            prefix, fa, _ = write_inputs_for_reference(d, codes, off, wl, sample_reads, bwt_runs=runs)
-            secs, wall = run_reference(prefix, fa, wl, cores, os.path.join(d, "out"), args.nodp)
-            log(f"reference CPU baseline: {sample_mbp:.1f} Mbp in {secs:.2f}s with {cores} threads")
-            # parity at full size: what the reference wrote for the sampled reads against what the timed GPU run produced for them
-            try:
-                want = {}
-                for fn in ("correct.fa", "discard.fa"):
-                    name = None
-                    for line in open(os.path.join(d, "out", fn)):
-                        if line.startswith(">"):
-                            name = line[1:].strip()
-                        else:
-                            want[(fn, name)] = line.strip()
-                raw = out.tobytes()
-                bad = 0
-                for r in range(sample_reads):
-                    if stats[r]["merge"]:
-                        j = int(first[r])
-                        got = raw[int(poff[j]):int(poff[j + 1])].decode()
-                        bad += want.get(("correct.fa", f"r{r}")) != got
-                    else:
-                        bad += ("discard.fa", f"r{r}") not in want
-                parity = {"reads_compared": int(sample_reads), "records_in_reference_output": len(want), "mismatches": int(bad),
-                          "identical": bool(bad == 0 and len(want) == sample_reads)}
-                log(f"parity against the reference on the sampled reads: {parity}")
-            except Exception as e:
-                parity = {"error": str(e)}
-            cpu = {"value": sample_mbp / secs, "unit": "Mbp/s", "cores": cores, "kind": "reference",
-                   "sample": f"first {sample_reads} reads ({sample_mbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores}" + (" --nodp" if args.nodp else "")}
-            small = max(1, min(int(np.searchsorted(off, min(sample_mbp, 4.0) * 1e6)), n_reads))
-            if os.path.exists(ORACLE):
-                from longreadselfcorrect_b200 import synth
-                fa2 = os.path.join(d, "alg.fa")
-                synth.write_fasta(fa2, codes[: off[small]], off[: small + 1])
-                alg = oracle_rank_queries(prefix, fa2, wl, min(cores, 32), args.nodp)
-                if alg:
-                    alg["sample_bases"] = int(off[small])
-
-    # ---- roofline of the dominant kernel: walk_levels_kernel (the FM-extend level loop), timed by CUDA events around each of
-    #      its launches inside the library (pbsc_timing.walk_ms).  Algorithmic bytes = rank queries the reference algorithm issues
-    #      for the same walks (instrumented oracle on a sample, scaled by walk count) x 32 B (one sector per occ(c, i)). ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    ext_ms = float(np.mean([p[1] for p in phase]))
-    seed_ms = float(np.mean([p[0] for p in phase]))
-    dp_ms = float(np.mean([p[2] for p in phase]))
-    walk_ms = float(np.mean([p[3] for p in phase]))
-    walk_launches = int(phase[-1][4])
-    traffic = None
-    try:
-        # per-launch DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/README.md)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get(args.workload + ("_nodp" if args.nodp else ""), {}).get("walk_levels_kernel")
-    except Exception:
-        pass
-    try:
-        # what independent random 32-byte sector reads over a buffer as large as the index reach on this GPU (SURVEY 8d)
-        sector_peak = api.random_sector_peak(idx.device_bytes(), local_rank)
-    except Exception as e:   # measurement aid only
-        log("random-sector peak not measured:", e)
-        sector_peak = None
-    roof = {"bound": "hbm", "kernel": "walk_levels_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (streaming copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "kernel_ms": walk_ms, "kernel_launches_per_step": walk_launches, "extend_phase_ms": ext_ms, "seed_phase_ms": seed_ms,
-            "dp_fallback_ms": dp_ms}
-    if not (alg and alg.get("walks")):
-        # CPU legs skipped (N > 1 or --no-cpu-baseline): per-unit algorithmic work from the committed oracle measurement
-        try:
-            c = json.load(open(os.path.join(ROOT, "profiles", "algorithmic.json"))).get(args.workload + ("_nodp" if args.nodp else ""))
-            if c:
-                alg = {"walks": 1.0, "extend": c["rank_queries_per_walk"], "seed": c["seed_rank_queries_per_read_base"], "sample_bases": 1.0,
-                       "source": "profiles/algorithmic.json"}
-                if c.get("dp_band_cells_per_job"):
-                    alg.update({"dp_jobs": 1.0, "dp_cells": c["dp_band_cells_per_job"]})
-        except Exception:
-            pass
-    if alg and alg.get("walks"):
-        per_walk = alg["extend"] / alg["walks"]
-        alg_bytes = per_walk * walks * 32.0
-        roof["achieved"] = alg_bytes / (walk_ms / 1000) / 1e9
-        roof["frac"] = roof["achieved"] / peak
-        roof["algorithmic_bytes_per_step"] = alg_bytes
-        if sector_peak:
-            roof["random_sector_peak"] = sector_peak
-            roof["frac_of_random_sector_peak"] = roof["achieved"] / sector_peak
-        roof["algorithmic_rank_queries_per_walk"] = per_walk
-        roof["algorithmic_rank_queries_per_read_base_seed_phase"] = alg["seed"] / alg["sample_bases"]
-        roof["seed_phase_achieved_GBs"] = alg["seed"] / alg["sample_bases"] * codes.size * 32.0 / (seed_ms / 1000) / 1e9
-        if alg.get("dp_jobs"):
-            # second kernel family (integer DP, issue-bound rather than HBM-bound): band cells per second
-            dp_jobs = int(phase[-1][5])
-            cells = alg["dp_cells"] / alg["dp_jobs"] * dp_jobs
-            roof["dp_fallback"] = {"jobs_per_step": dp_jobs, "rows_aligned_per_step": int(phase[-1][6]),
-                                   "band_cells_per_step": cells, "Gcells_per_s": cells / (dp_ms / 1000) / 1e9}
-
-    line = {
-        "metric": metric, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int64+f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "reads": n_reads, "mbp": total_mbp, "walks": walks, "fm_success": fm,
-                   "index_bytes": idx.device_bytes(), "prefix_k0": args.k0, "index_build_s": index_s,
-                   "l2": "rank tables + prefix table exceed the 126 MB L2; no explicit flush",
-                   "sharding": "index replicated per GPU, every rank corrects the full read set, no collective on the data path",
-                   "batches_per_step": len(chunks),
-                   "wall_ms_per_step": wall_ms / args.steps},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e},
-        "gpu_launches": launches_per_step * args.steps,
-        "roofline": roof,
-        "cpu_baseline": cpu,
-        "parity_vs_reference": parity,
-    }
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
-    return 0
+        return reference_arm(args, wl, metric)
+    return ours(args, wl, metric)
 
 
 if __name__ == "__main__":

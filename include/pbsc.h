@@ -103,6 +103,9 @@ int pbsc_device_count(void);
  * PCIe speed.  The reference has no counterpart (its reads live in std::string, SequenceWorkItem.h). */
 int pbsc_host_alloc(void** p, size_t bytes);
 void pbsc_host_free(void* p);
+/* page-lock memory the caller owns (cudaHostRegister), e.g. a shared mapping that several processes fill with results */
+int pbsc_host_register(void* p, size_t bytes);
+void pbsc_host_unregister(void* p);
 /* give the library's cache of per-batch device blocks on `device` back to the driver */
 void pbsc_trim(int device);
 /* measured peak (GB/s) of independent random 32-byte sector reads over `bytes` bytes of HBM: the roofline denominator for
@@ -130,6 +133,33 @@ int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t
 /* build the short-prefix interval table for all k0-mers (k0 in 1..15); 0 disables it */
 int pbsc_index_build_prefix_table(pbsc_index* idx, int k0);
 void pbsc_index_destroy(pbsc_index* idx);
+
+/* ---- the index as one relocatable blob (512-byte header + the tables exactly as they sit in HBM).  No counterpart in the
+ *      reference, which re-reads PREFIX.bwt/.rbwt and rebuilds its rank directory on every start
+ *      (SuffixTools/BWTReaderBinary.cpp:55-85, SuffixTools/RLBWT.cpp:109-248) once per process
+ *      (StriDe/PacBioSelfCorrection.cpp:155-172). ---- */
+/* PREFIX.fmg, the persisted flat index: written once, later runs skip the run-length decode and the prefix-table build */
+int pbsc_index_save(const pbsc_index* idx, const char* path);
+int pbsc_index_load_fmg(const char* path, int device, pbsc_index** out);
+/* `pbcorrect -p PREFIX`: PREFIX.fmg if present, well-formed and describing the same PREFIX.bwt/.rbwt (string, symbol and run
+ * counts of both headers) with a k0 prefix table; else the run-length files (+ prefix table), and PREFIX.fmg is written for
+ * the next run when write_fmg != 0.  *from_fmg (may be NULL) reports which way it went. */
+int pbsc_index_open(const char* prefix, int device, int require_sai, int k0, int write_fmg, int* from_fmg, pbsc_index** out);
+/* a copy of `src` on another GPU of the box: one peer copy per table over NVLink (cudaMemcpyPeerAsync), no host decode */
+int pbsc_index_clone(const pbsc_index* src, int device, pbsc_index** out);
+/* the same bytes through caller-owned memory, for callers that move the index themselves (one process per GPU + NCCL
+ * broadcast): export writes the blob to a device buffer on the index's GPU; import copies a blob that sits on GPU
+ * src_device (or in host memory when src_device < 0) into a new index on `device`. */
+int pbsc_index_blob_size(const pbsc_index* idx, uint64_t* bytes);
+int pbsc_index_export_blob(const pbsc_index* idx, void* d_dst, uint64_t cap);
+int pbsc_index_import_blob(const void* src, uint64_t bytes, int src_device, int device, pbsc_index** out);
+
+/* ---- lanes: how many batches of this index may RUN at the same time (1..4, default 1), each on its own stream with its own
+ *      scratch arena, so that the tail of one batch's rounds overlaps the dense kernels of another.  Together with the
+ *      per-batch copy streams of pbsc_batch_upload / pbsc_batch_fetch this replaces the worker threads of
+ *      Concurrency/SequenceProcessFramework.h:91-230: callers drive it from `lanes` (or more) host threads. ---- */
+int pbsc_index_set_lanes(pbsc_index* idx, int lanes);
+int pbsc_index_lanes(const pbsc_index* idx);
 uint64_t pbsc_index_num_symbols(const pbsc_index* idx, int which);
 uint64_t pbsc_index_num_strings(const pbsc_index* idx, int which);
 uint64_t pbsc_index_device_bytes(const pbsc_index* idx);
@@ -209,6 +239,10 @@ typedef struct pbsc_timing
     uint64_t dp_thread_rows; /* of dp_rows: aligned by the thread-per-alignment kernel (the rest by the warp-per-row kernel) */
 } pbsc_timing;
 int pbsc_last_timing(pbsc_timing* t);
+/* measurement build only (libpbsc_count.so, compiled with -DPBSC_COUNT_OCC): distinct 32-byte index sectors the kernels asked for
+ * since the last reset, per kernel family: out[0] seed phase, out[1] walk setup, out[2] level loop, out[3] DP fallback, out[4]
+ * other.  Returns 1 in the measurement build, 0 (and zeros) in the product build. */
+int pbsc_occ_counts(uint64_t* out, int reset);
 
 #ifdef __cplusplus
 }

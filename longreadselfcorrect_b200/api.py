@@ -71,7 +71,10 @@ EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc
             "pbsc_index_device_bytes", "pbsc_index_get_symbols", "pbsc_findinterval_batch", "pbsc_findinterval_device",
             "pbsc_seed_batch", "pbsc_extend_batch", "pbsc_correct_batch", "pbsc_last_timing",
             "pbsc_batch_upload", "pbsc_batch_run", "pbsc_batch_result_size", "pbsc_batch_fetch", "pbsc_batch_destroy",
-            "pbsc_host_alloc", "pbsc_host_free", "pbsc_trim", "pbsc_random_sector_bench"]
+            "pbsc_host_alloc", "pbsc_host_free", "pbsc_trim", "pbsc_random_sector_bench",
+            "pbsc_index_save", "pbsc_index_load_fmg", "pbsc_index_open", "pbsc_index_clone", "pbsc_index_blob_size",
+            "pbsc_index_export_blob", "pbsc_index_import_blob", "pbsc_index_set_lanes", "pbsc_index_lanes",
+            "pbsc_host_register", "pbsc_host_unregister", "pbsc_occ_counts"]
 
 _lib = None
 
@@ -153,6 +156,20 @@ def pinned_free(a: np.ndarray) -> None:
     _PINNED_OWNERS.pop(a.ctypes.data, None)
 
 
+def host_register(a: np.ndarray) -> None:
+    """Page-lock an existing numpy buffer (e.g. a np.memmap over /dev/shm)."""
+    L = lib()
+    L.pbsc_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    _check(L.pbsc_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)))
+
+
+def host_unregister(a: np.ndarray) -> None:
+    L = lib()
+    L.pbsc_host_unregister.argtypes = [C.c_void_p]
+    L.pbsc_host_unregister.restype = None
+    L.pbsc_host_unregister(C.c_void_p(a.ctypes.data))
+
+
 def _concat(strings):
     """list[str] -> (bytes array, uint64 offsets[n+1])"""
     enc = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
@@ -232,6 +249,55 @@ class Index:
                                                  C.c_int(device), C.byref(h)))
         return Index(h)
 
+    @staticmethod
+    def load_fmg(path: str, device: int = 0) -> "Index":
+        """PREFIX.fmg: the flat tables as persisted by save()."""
+        h = C.c_void_p()
+        _check(lib().pbsc_index_load_fmg(path.encode(), C.c_int(device), C.byref(h)))
+        return Index(h)
+
+    @staticmethod
+    def open(prefix: str, device: int = 0, require_sai: bool = True, k0: int = 13, write_fmg: bool = False):
+        """What `pbcorrect -p PREFIX` does: PREFIX.fmg when it matches PREFIX.bwt/.rbwt, else the run-length files.
+        Returns (Index, from_fmg)."""
+        h = C.c_void_p()
+        used = C.c_int(0)
+        _check(lib().pbsc_index_open(prefix.encode(), C.c_int(device), C.c_int(int(require_sai)), C.c_int(k0), C.c_int(int(write_fmg)),
+                                     C.byref(used), C.byref(h)))
+        return Index(h), bool(used.value)
+
+    @staticmethod
+    def import_blob(ptr: int, nbytes: int, src_device: int, device: int) -> "Index":
+        """New index on `device` from a blob at address `ptr` on GPU src_device (host memory when src_device < 0)."""
+        h = C.c_void_p()
+        _check(lib().pbsc_index_import_blob(C.c_void_p(ptr), C.c_uint64(nbytes), C.c_int(src_device), C.c_int(device), C.byref(h)))
+        return Index(h)
+
+    def save(self, path: str) -> None:
+        _check(lib().pbsc_index_save(self._h, path.encode()))
+
+    def clone(self, device: int) -> "Index":
+        """A copy on another GPU of the box (peer copies over NVLink)."""
+        h = C.c_void_p()
+        _check(lib().pbsc_index_clone(self._h, C.c_int(device), C.byref(h)))
+        return Index(h)
+
+    def blob_size(self) -> int:
+        n = C.c_uint64(0)
+        _check(lib().pbsc_index_blob_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def export_blob(self, ptr: int, cap: int) -> None:
+        """Write the blob to device memory at `ptr` (on this index's GPU)."""
+        _check(lib().pbsc_index_export_blob(self._h, C.c_void_p(ptr), C.c_uint64(cap)))
+
+    def set_lanes(self, lanes: int) -> None:
+        """How many batches of this index may run at once (each on its own stream and scratch arena)."""
+        _check(lib().pbsc_index_set_lanes(self._h, C.c_int(lanes)))
+
+    def lanes(self) -> int:
+        return int(lib().pbsc_index_lanes(self._h))
+
     def build_prefix_table(self, k0: int) -> None:
         _check(lib().pbsc_index_build_prefix_table(self._h, C.c_int(k0)))
 
@@ -306,9 +372,11 @@ class Index:
         return status[:n], merged
 
     # PacBioSelfCorrectionProcess::process over a batch; returns (pieces per read, stats structured array)
-    def correct_reads(self, params: Params, reads=None, packed=None, pinned_out: bool = False):
+    def correct_reads(self, params: Params, reads=None, packed=None, pinned_out: bool = False, out_bufs=None):
         """PacBioSelfCorrectionProcess::process over a batch on host buffers.  With pinned_out the result buffers are
-        page-locked blocks owned by this Index and reused by the next call (their contents are overwritten then)."""
+        page-locked blocks owned by this Index and reused by the next call (their contents are overwritten then).
+        out_bufs = (pieces uint8[cap], piece_offsets uint64[n+2], first_piece uint64[n+1], stats STATS_DTYPE[n]): caller-owned
+        result buffers (any host memory); raises PbscError(-5) when they are too small."""
         if packed is not None:
             buf, off = packed
             n = off.size - 1
@@ -316,6 +384,13 @@ class Index:
             buf, off = _concat(reads)
             n = len(reads)
         total = int(off[-1])
+        if out_bufs is not None:
+            out, poff, first, stats = out_bufs
+            need = C.c_uint64(0)
+            _check(lib().pbsc_correct_batch(self._h, C.byref(params.c), _ptr(buf, C.c_char), _ptr(off, C.c_uint64), C.c_uint64(n),
+                                            _ptr(out, C.c_char), C.c_uint64(out.size), _ptr(poff, C.c_uint64), C.c_uint64(poff.size),
+                                            _ptr(first, C.c_uint64), stats.ctypes.data_as(C.POINTER(CReadStats)), C.byref(need)))
+            return out, poff, first[: n + 1], stats[:n]
         cap = int(total * 1.3) + 4096 * 4
         while True:
             poff_cap = (total // 10 + 4 * n + 16) if params.c.split else (n + 2)
@@ -404,6 +479,15 @@ def random_sector_peak(nbytes: int, device: int = 0) -> float:
     g = C.c_float(0)
     _check(lib().pbsc_random_sector_bench(C.c_int(device), C.c_uint64(int(nbytes)), C.byref(g)))
     return float(g.value)
+
+
+def occ_counts(reset: bool = True):
+    """(is_measurement_build, {family: distinct 32-byte index sectors asked for}) -- zeros unless PBSC_LIB points at the
+    -DPBSC_COUNT_OCC build (libpbsc_count.so)."""
+    out = (C.c_uint64 * 5)()
+    rc = lib().pbsc_occ_counts(out, C.c_int(int(reset)))
+    _check(rc)
+    return bool(rc), dict(zip(("seed", "setup", "walk", "dp", "other"), (int(x) for x in out)))
 
 
 def last_timing() -> dict:

@@ -13,7 +13,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the reference's float/double pruning rules must not be contracted into FMAs
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O3,-ffp-contract=off", "-ccbin", "/usr/bin/g++"]
-CU_SOURCES = ["pbsc_index.cu", "pbsc_seed.cu", "pbsc_extend.cu", "pbsc_extend_thread.cu", "pbsc_dp.cu", "pbsc_pipeline.cu"]
+CU_SOURCES = ["pbsc_index.cu", "pbsc_seed.cu", "pbsc_extend.cu", "pbsc_extend_thread.cu", "pbsc_dp.cu", "pbsc_pipeline.cu", "pbsc_store.cu"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -47,13 +47,16 @@ def build_lib(force: bool = False, verbose: bool = False, extra: list[str] | Non
     return LIB
 
 
-def build_variant(name: str, extra: list[str]) -> str:
+def build_variant(name: str, extra: list[str], force: bool = False) -> str:
     """An alternative build of the library for experiments (e.g. build_variant("fused", ["-DPBSC_FUSED_UPDATE"])): objects go
     to csrc/_variant_<name>/, the library to libpbsc_<name>.so; select it with PBSC_LIB=<path> (api.py).  The default
     library is not touched."""
     odir = os.path.join(CSRC, f"_variant_{name}")
     os.makedirs(odir, exist_ok=True)
     lib = os.path.join(PKG, f"libpbsc_{name}.so")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [os.path.join(PKG, "..", "include", "pbsc.h")]
+    if not force and not _stale(lib, deps):
+        return lib
     procs, objs = [], []
     for s in CU_SOURCES:
         o = os.path.join(odir, s[:-3] + ".o")

@@ -73,9 +73,17 @@ struct Interval   // half-open
 #define PBSC_POPCLL(x) __builtin_popcountll(x)
 #endif
 
+// -DPBSC_COUNT_OCC: a measurement build (libpbsc_count.so) that counts the DISTINCT 32-byte sectors of the rank tables and
+// of the prefix table every lookup asks for ("issued sectors"): one per occ / occ4 / lf_step / prefix_lookup, one
+// (not two) for an updateInterval whose two bounds fall into the same block.  Host code reads and clears the counter at the
+// phase boundaries (occ_take below; every translation unit has its own copy of the symbol).
 #ifdef PBSC_COUNT_OCC
-__device__ unsigned long long g_occ_counter;
-#define PBSC_OCC_TICK(n) atomicAdd(&g_occ_counter, (unsigned long long)(n))
+static __device__ unsigned long long g_occ_counter;
+#if defined(__CUDA_ARCH__)
+#define PBSC_OCC_TICK(n) atomicAdd(&g_occ_counter, (unsigned long long)(long long)(n))
+#else
+#define PBSC_OCC_TICK(n)
+#endif
 #else
 #define PBSC_OCC_TICK(n)
 #endif
@@ -188,6 +196,7 @@ __host__ __device__ __forceinline__ Interval update_interval(const FmTable& t, I
 #else
     const uint64_t a = occ(t, c, iv.lo);
     const uint64_t b = (iv.hi == iv.lo) ? a : occ(t, c, iv.hi);
+    if (iv.hi != iv.lo && (iv.hi >> 6) == (iv.lo >> 6)) PBSC_OCC_TICK(-1);   // the second load hit the sector the first one fetched
 #endif
     r.lo = t.C[c] + a;
     r.hi = t.C[c] + b;
@@ -207,6 +216,7 @@ __host__ __device__ __forceinline__ Interval init_interval(const FmTable& t, int
 // (RLBWT::getChar + getPC + getOcc, LongReadOverlap.cpp:713-718) from one 32-byte sector
 __host__ __device__ __forceinline__ int lf_step(const FmTable& t, uint64_t& idx)
 {
+    PBSC_OCC_TICK(1);
     const uint64_t blk = idx >> 6;
     const uint32_t off = (uint32_t)idx & 63u;
     const uint4* bp = reinterpret_cast<const uint4*>(t.blocks + blk);
@@ -238,11 +248,30 @@ __host__ __device__ __forceinline__ int lf_step(const FmTable& t, uint64_t& idx)
 // read one prefix-table entry (one 32-byte sector) and return the strand the caller wants
 __host__ __device__ __forceinline__ void prefix_lookup(const FmIndexDev& idx, uint64_t key, Interval& fwd, Interval& rvc)
 {
+    PBSC_OCC_TICK(1);
     const uint4* ep = reinterpret_cast<const uint4*>(idx.prefix + key);
     const uint4 a = PBSC_LDG(ep), b = PBSC_LDG(ep + 1);
     fwd.lo = (uint64_t)a.x | ((uint64_t)a.y << 32); fwd.hi = fwd.lo + b.x;
     rvc.lo = (uint64_t)a.z | ((uint64_t)a.w << 32); rvc.hi = rvc.lo + b.y;
 }
+
+#ifdef PBSC_COUNT_OCC
+// sectors counted by this translation unit's kernels since the last call (synchronises the stream)
+static inline unsigned long long occ_take(cudaStream_t st)
+{
+    unsigned long long v = 0, z = 0;
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(&v, g_occ_counter, sizeof v);
+    cudaMemcpyToSymbol(g_occ_counter, &z, sizeof z);
+    return v;
+}
+#define PBSC_OCC_TAKE(slot, st) (pbsc::occ_counts()[slot] += pbsc::occ_take(st))
+#else
+#define PBSC_OCC_TAKE(slot, st)
+#endif
+// issued sectors per kernel family of the measurement build: [0] seed phase, [1] walk setup (setup_tasks_kernel),
+// [2] level loop (walk_levels_kernel), [3] DP fallback (collect + retrieve), [4] everything else
+unsigned long long* occ_counts();
 
 }  // namespace pbsc
 #endif

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,8 +44,11 @@ static const char* CORRECT_USAGE_MESSAGE =
     "      -o, --output=DIR                 Output results in the directory\n"
     "      -b, --barcode=FILE               Barcode of raw reads\n"
     "      --gpus=N                         Number of GPUs to use (default: all visible)\n"
-    "      --batch-mbp=N                    Read bases per GPU batch, in Mbp (default: 64)\n"
+    "      --batch-mbp=N                    Read bases per GPU batch, in Mbp (default: 160)\n"
     "      --prefix-k=N                     Length of the short-prefix interval table, 0 = off (default: 13)\n"
+    "      --lanes=N                        Batches in flight per GPU, 1..4 (default: 2)\n"
+    "      --write-fmg                      Leave PREFIX.fmg (the flat index as it sits in GPU memory) for later runs;\n"
+    "                                       a PREFIX.fmg that matches PREFIX.bwt/.rbwt is always used when present\n"
     "\nPacBio correction parameters:\n"
     "      -c, --PBcoverage=N               Coverage of PacBio reads (default: 90)\n"
     "      -e, --error-rate=N               The error rate of PacBio reads.(default:0.15)\n"
@@ -71,12 +75,13 @@ static int thread = 1;
 static std::string prefix, directory, barcode, readsFile;
 static pbsc_params params;
 static bool DebugSeed = false, OnlySeed = false;
-static int gpus = 0, prefix_k = 13;
-static double batch_mbp = 64;
+static int gpus = 0, prefix_k = 13, lanes = 2;
+static bool write_fmg = false;
+static double batch_mbp = 160;
 static int verbose = 0;
 }
 
-enum { OPT_HELP = 1, OPT_VERSION, OPT_SPLIT, OPT_DEBUGEXTEND, OPT_DEBUGSEED, OPT_ONLYSEED, OPT_NODP, OPT_GPUS, OPT_BATCH, OPT_PREFIXK };
+enum { OPT_HELP = 1, OPT_VERSION, OPT_SPLIT, OPT_DEBUGEXTEND, OPT_DEBUGSEED, OPT_ONLYSEED, OPT_NODP, OPT_GPUS, OPT_BATCH, OPT_PREFIXK, OPT_LANES, OPT_WRITEFMG };
 static const char* shortopts = "t:p:o:b:c:e:k:u:r:n:l:i:s:g:m:v";
 static const struct option longopts[] = {
     {"thread", required_argument, nullptr, 't'}, {"prefix", required_argument, nullptr, 'p'},
@@ -92,6 +97,7 @@ static const struct option longopts[] = {
     {"debugseed", no_argument, nullptr, OPT_DEBUGSEED}, {"onlyseed", no_argument, nullptr, OPT_ONLYSEED},
     {"nodp", no_argument, nullptr, OPT_NODP}, {"gpus", required_argument, nullptr, OPT_GPUS},
     {"batch-mbp", required_argument, nullptr, OPT_BATCH}, {"prefix-k", required_argument, nullptr, OPT_PREFIXK},
+    {"lanes", required_argument, nullptr, OPT_LANES}, {"write-fmg", no_argument, nullptr, OPT_WRITEFMG},
     {nullptr, 0, nullptr, 0}};
 
 // StriDe/PacBioSelfCorrection.cpp:262-434, same messages and exit codes
@@ -131,12 +137,15 @@ static void parseOptions(int argc, char** argv)
             case OPT_GPUS: arg >> opt::gpus; break;
             case OPT_BATCH: arg >> opt::batch_mbp; break;
             case OPT_PREFIXK: arg >> opt::prefix_k; break;
+            case OPT_LANES: arg >> opt::lanes; break;
+            case OPT_WRITEFMG: opt::write_fmg = true; break;
             default: die = true; break;
         }
     }
     if (argc - optind < 1) { std::cerr << SUBPROGRAM ": missing arguments\n"; die = true; }
     else if (argc - optind > 1) { std::cerr << SUBPROGRAM ": too many arguments\n"; die = true; }
     if (opt::thread <= 0) { std::cerr << SUBPROGRAM ": invalid number of threads: " << opt::thread << "\n"; die = true; }
+    if (opt::lanes < 1 || opt::lanes > 4) { std::cerr << SUBPROGRAM ": invalid number of lanes: " << opt::lanes << ", must be 1..4\n"; die = true; }
     if (opt::prefix.empty()) { std::cerr << SUBPROGRAM << ": no prefix\n"; die = true; }
     if (opt::directory.empty()) { std::cerr << SUBPROGRAM << ": no directory\n"; die = true; }
     else
@@ -172,37 +181,99 @@ static void parseOptions(int argc, char** argv)
 class LineReader
 {
   public:
-    explicit LineReader(const std::string& path) { f_ = gzopen(path.c_str(), "rb"); if (f_) gzbuffer(f_, 1 << 20); }
+    explicit LineReader(const std::string& path) : buf_(1 << 22) { f_ = gzopen(path.c_str(), "rb"); if (f_) gzbuffer(f_, 1 << 20); }
     ~LineReader() { if (f_) gzclose(f_); }
     bool ok() const { return f_ != nullptr; }
     bool good() const { return good_; }
     bool eof() const { return eof_; }
     int peek() { if (pos_ >= len_ && !fill()) return EOF; return (unsigned char)buf_[pos_]; }
-    // std::getline: the line is returned even when EOF ends it, but the stream is no longer good()
-    void getline(std::string& out)
+    // std::getline semantics: the line is delivered even when EOF ends it, but the stream is no longer good().  The line's
+    // bytes go to sink(ptr, n), possibly in several pieces (no intermediate string: sequence lines are copied once, from the
+    // read buffer into the batch's page-locked buffer).
+    template <class Sink>
+    void getline(Sink sink)
     {
-        out.clear();
         if (!good_) return;
-        bool any = false;
         for (;;)
         {
-            if (pos_ >= len_ && !fill()) { eof_ = true; good_ = false; (void)any; return; }
-            const char* nl = (const char*)memchr(buf_ + pos_, '\n', len_ - pos_);
-            if (nl) { out.append(buf_ + pos_, nl - (buf_ + pos_)); pos_ = (nl - buf_) + 1; return; }
-            out.append(buf_ + pos_, len_ - pos_);
-            any = true;
+            if (pos_ >= len_ && !fill()) { eof_ = true; good_ = false; return; }
+            const char* nl = (const char*)memchr(buf_.data() + pos_, '\n', len_ - pos_);
+            if (nl) { sink(buf_.data() + pos_, (size_t)(nl - (buf_.data() + pos_))); pos_ = (size_t)(nl - buf_.data()) + 1; return; }
+            sink(buf_.data() + pos_, len_ - pos_);
             pos_ = len_;
         }
     }
+    void getline(std::string& out) { out.clear(); getline([&](const char* p, size_t n) { out.append(p, n); }); }
   private:
-    bool fill() { if (!f_) return false; int n = gzread(f_, buf_, sizeof buf_); if (n <= 0) return false; len_ = n; pos_ = 0; return true; }
+    bool fill() { if (!f_) return false; int n = gzread(f_, buf_.data(), (unsigned)buf_.size()); if (n <= 0) return false; len_ = (size_t)n; pos_ = 0; return true; }
     gzFile f_ = nullptr;
-    char buf_[1 << 16];
-    int pos_ = 0, len_ = 0;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
     bool good_ = true, eof_ = false;
 };
 
-static bool readRecord(LineReader& in, std::string& id, std::string& seq)
+// ---- page-locked host buffers (pbsc_host_alloc), recycled: allocating them costs milliseconds per 100 MB ----
+struct PinBuf { char* p = nullptr; size_t cap = 0; };
+class PinPool
+{
+  public:
+    ~PinPool() { for (auto& b : free_) pbsc_host_free(b.p); }
+    PinBuf get(size_t need)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].cap >= need) { PinBuf b = free_[i]; free_[i] = free_.back(); free_.pop_back(); return b; }
+            if (!free_.empty()) { pbsc_host_free(free_.back().p); free_.pop_back(); }   // too small for this one: do not hoard it
+        }
+        PinBuf b;
+        b.cap = need + need / 4 + 4096;
+        void* p = nullptr;
+        if (pbsc_host_alloc(&p, b.cap) != PBSC_OK) { std::cerr << SUBPROGRAM ": " << pbsc_last_error() << "\n"; exit(EXIT_FAILURE); }
+        b.p = (char*)p;
+        return b;
+    }
+    void put(PinBuf b) { if (!b.p) return; std::lock_guard<std::mutex> lk(mu_); free_.push_back(b); }
+  private:
+    std::mutex mu_;
+    std::vector<PinBuf> free_;
+};
+static PinPool g_pins;
+
+struct Batch
+{
+    size_t seq = 0;
+    std::vector<std::string> ids;
+    PinBuf bases;                     // raw sequence bytes as read (upper-cased and validated by normalize())
+    size_t n_bases = 0;
+    std::vector<uint64_t> offsets{0};
+    // results
+    PinBuf pieces;
+    std::vector<uint64_t> piece_off, first;
+    std::vector<pbsc_read_stats> stats;
+    pbsc_timing timing{};
+    bool normalized = false, taken = false, done = false;
+    int rc = 0;
+    std::string err;
+    void append(const char* p, size_t n)
+    {
+        if (n_bases + n > bases.cap)
+        {
+            PinBuf nb = g_pins.get((n_bases + n) * 2);
+            if (n_bases) memcpy(nb.p, bases.p, n_bases);
+            g_pins.put(bases);
+            bases = nb;
+        }
+        memcpy(bases.p + n_bases, p, n);
+        n_bases += n;
+    }
+    void release() { g_pins.put(bases); g_pins.put(pieces); bases = PinBuf(); pieces = PinBuf(); }
+};
+
+// One record, exactly as SeqReader::get delivers it (Util/SeqReader.cpp:26-135): FASTA (multi-line) or FASTQ by the header's
+// first character; a FASTA sequence line that EOF ends without a newline is lost (:64-69); ids stop at the first blank or tab.
+// The sequence is appended to the batch as read; upper-casing and the ACGT check (:112-125) happen in normalize().
+static bool readRecord(LineReader& in, Batch& b)
 {
     std::string header;
     int rt = 0;
@@ -214,51 +285,51 @@ static bool readRecord(LineReader& in, std::string& id, std::string& seq)
         if (header[0] == '@') { rt = 2; break; }
     }
     if (rt == 0) return false;
+    const size_t start = b.n_bases;
     bool valid = false;
-    seq.clear();
-    std::string temp, qual;
     if (rt == 1)
     {
         while (in.good() && in.peek() != '>' && in.peek() != '@')
         {
-            in.getline(temp);
-            if (in.good() && temp.size() > 0) seq.append(temp);
+            const size_t before = b.n_bases;
+            in.getline([&](const char* p, size_t n) { b.append(p, n); });
+            if (!in.good()) b.n_bases = before;   // std::getline hit EOF: the reference drops this last, unterminated line
         }
-        valid = seq.size() > 0;
+        valid = b.n_bases > start;
     }
     else
     {
-        in.getline(seq); in.getline(temp); in.getline(qual);
-        if (seq.empty() || qual.empty()) std::cerr << "Warning, read " << header << " has no sequence or quality values\n";
+        std::string temp, qual;
+        in.getline([&](const char* p, size_t n) { b.append(p, n); });
+        in.getline(temp); in.getline(qual);
+        if (b.n_bases == start || qual.empty()) std::cerr << "Warning, read " << header << " has no sequence or quality values\n";
         valid = !in.eof();
     }
-    if (!valid) return false;
+    if (!valid) { b.n_bases = start; return false; }
     size_t endPos = std::min(header.find_first_of(' '), header.find_first_of('\t'));
-    id = endPos != std::string::npos ? header.substr(1, endPos - 1) : header.substr(1);
-    for (auto& c : seq) c = (char)toupper((unsigned char)c);
-    if (seq.find_first_not_of("ACGT") != std::string::npos)
-    {
-        std::cerr << "Error: read " << id << " contains non-ACGT characters.\n";
-        std::cerr << "Please run sga preprocess on the data first.\n";
-        exit(EXIT_FAILURE);
-    }
+    b.ids.push_back(endPos != std::string::npos ? header.substr(1, endPos - 1) : header.substr(1));
+    b.offsets.push_back(b.n_bases);
     return true;
 }
 
-struct Batch
+// upper-case in place and insist on ACGT (SeqReader.cpp:112-125): false + the offending read's id on anything else
+static bool normalize(Batch& b, std::string& bad_id)
 {
-    std::vector<std::string> ids;
-    std::string bases;
-    std::vector<uint64_t> offsets{0};
-    // results
-    std::vector<char> pieces;
-    std::vector<uint64_t> piece_off, first;
-    std::vector<pbsc_read_stats> stats;
-    pbsc_timing timing{};
-    bool done = false;
-    int rc = 0;
-    std::string err;
-};
+    static unsigned char lut[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        memset(lut, 0, sizeof lut);
+        for (const char* c = "ACGT"; *c; c++) { lut[(unsigned char)*c] = (unsigned char)*c; lut[(unsigned char)tolower(*c)] = (unsigned char)*c; }
+    });
+    unsigned char* s = (unsigned char*)b.bases.p;
+    unsigned char ok = 0xff;
+    for (size_t i = 0; i < b.n_bases; i++) { const unsigned char u = lut[s[i]]; ok &= (unsigned char)(u ? 0xff : 0); s[i] = u ? u : s[i]; }
+    if (ok) return true;
+    for (size_t r = 0; r + 1 < b.offsets.size(); r++)
+        for (uint64_t i = b.offsets[r]; i < b.offsets[r + 1]; i++)
+            if (!lut[s[i]]) { bad_id = b.ids[r]; return false; }
+    return false;
+}
 
 int main(int argc, char** argv)
 {
@@ -274,23 +345,31 @@ int main(int argc, char** argv)
     auto t_load = std::chrono::steady_clock::now();
     std::cerr << "Loading BWT: " << opt::prefix << ".bwt\n" << "Loading RBWT: " << opt::prefix << ".rbwt\n"
               << "Loading Sampled Suffix Array: " << opt::prefix << ".sai\n";
+    // The index is read and decoded ONCE (PREFIX.fmg, the persisted flat tables, when it matches PREFIX.bwt/.rbwt; else the
+    // run-length files), on GPU 0; the other GPUs receive it by peer copies over NVLink, all at the same time.
     std::vector<pbsc_index*> index(ngpu, nullptr);
+    int from_fmg = 0;
+    if (pbsc_index_open(opt::prefix.c_str(), 0, 1, opt::prefix_k, opt::write_fmg ? 1 : 0, &from_fmg, &index[0]) != PBSC_OK)
+    { std::cerr << pbsc_last_error() << "\n"; return EXIT_FAILURE; }
     {
         std::vector<std::thread> th;
         std::vector<int> rcs(ngpu, 0);
         std::vector<std::string> errs(ngpu);
-        for (int g = 0; g < ngpu; g++)
+        for (int g = 1; g < ngpu; g++)
             th.emplace_back([&, g]() {
-                rcs[g] = pbsc_index_load(opt::prefix.c_str(), g, 1, &index[g]);
-                if (rcs[g] == PBSC_OK && opt::prefix_k > 0) rcs[g] = pbsc_index_build_prefix_table(index[g], opt::prefix_k);
+                rcs[g] = pbsc_index_clone(index[0], g, &index[g]);
                 if (rcs[g] != PBSC_OK) errs[g] = pbsc_last_error();
             });
         for (auto& t : th) t.join();
         for (int g = 0; g < ngpu; g++)
+        {
             if (rcs[g] != PBSC_OK) { std::cerr << errs[g] << "\n"; return EXIT_FAILURE; }
+            if (pbsc_index_set_lanes(index[g], opt::lanes) != PBSC_OK) { std::cerr << pbsc_last_error() << "\n"; return EXIT_FAILURE; }
+        }
     }
     double load_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count();
-    std::cerr << "[timer - index to " << ngpu << " GPU(s)] wall clock: " << load_s << "s (" << pbsc_index_device_bytes(index[0]) / 1e9 << " GB per GPU)\n";
+    std::cerr << "[timer - index to " << ngpu << " GPU(s)] wall clock: " << load_s << "s (" << pbsc_index_device_bytes(index[0]) / 1e9 << " GB per GPU, from "
+              << (from_fmg ? "PREFIX.fmg" : "PREFIX.bwt/.rbwt") << (ngpu > 1 ? ", peer copies to the other GPUs" : "") << ")\n";
 
     const pbsc_params& P = opt::params;
     std::cerr << "\nCorrecting PacBio reads for " << opt::readsFile << " using--\n"
@@ -305,64 +384,108 @@ int main(int argc, char** argv)
 
     LineReader in(opt::readsFile);
     if (!in.ok()) { std::cerr << "Error: could not open " << opt::readsFile << " for read\n"; return EXIT_FAILURE; }
-    std::ofstream correct((opt::directory + "correct.fa").c_str()), discard((opt::directory + "discard.fa").c_str());
+    FILE* correct = fopen((opt::directory + "correct.fa").c_str(), "wb");
+    FILE* discard = fopen((opt::directory + "discard.fa").c_str(), "wb");
     if (!correct || !discard) { std::cerr << "Error: could not open output files in " << opt::directory << "\n"; return EXIT_FAILURE; }
+    std::vector<char> wbuf_c(8 << 20), wbuf_d(1 << 20);
+    setvbuf(correct, wbuf_c.data(), _IOFBF, wbuf_c.size());
+    setvbuf(discard, wbuf_d.data(), _IOFBF, wbuf_d.size());
 
     auto t0 = std::chrono::steady_clock::now();
-    // ---- pipeline: reader (this thread) -> one worker per GPU -> in-order writer (this thread) ----
+    // ---- pipeline (replaces Concurrency/SequenceProcessFramework.h:91-230):
+    //   reader (this thread: record boundaries, one copy of the sequence bytes into page-locked memory)
+    //   -> normalizers (-t threads: upper-case + ACGT check)
+    //   -> GPU workers (lanes + 1 host threads per GPU: pbsc_correct_batch = upload on a copy stream, kernels on a lane of the
+    //      index, fetch on the copy stream; one thread's copies overlap the other threads' kernels)
+    //   -> writer (one thread, batches in input order: the reference's `-t 1` record order)
+    // The reader stops while too many batches are in flight: memory is bounded by the GPU count, not by the file size. ----
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<std::unique_ptr<Batch>> batches;
-    size_t next_job = 0;
-    bool reading_done = false;
+    std::deque<std::unique_ptr<Batch>> inflight;   // batches [written, produced), in input order
+    size_t produced = 0, written = 0;
+    bool reading_done = false, failed = false;
+    std::string fail_msg;
+    auto fail = [&](const std::string& m) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_msg = m; } cv.notify_all(); };
+    auto at = [&](size_t seq) -> Batch* { return inflight[seq - written].get(); };   // call with mu held
+    const int n_workers = ngpu * (opt::lanes + 1);
+    const size_t max_inflight = (size_t)2 * n_workers + 2;
+
+    auto normalizer = [&]() {
+        for (;;)
+        {
+            Batch* b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] {
+                    if (failed) return true;
+                    for (size_t s = written; s < produced; s++) { Batch* x = at(s); if (!x->normalized && !x->taken) { b = x; return true; } }
+                    return reading_done;
+                });
+                if (failed || !b) return;
+                b->taken = true;
+            }
+            std::string bad;
+            const bool ok = normalize(*b, bad);
+            if (!ok) { fail("Error: read " + bad + " contains non-ACGT characters.\nPlease run sga preprocess on the data first."); return; }
+            { std::lock_guard<std::mutex> lk(mu); b->normalized = true; b->taken = false; }
+            cv.notify_all();
+        }
+    };
     auto worker = [&](int g) {
         for (;;)
         {
             Batch* b = nullptr;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return next_job < batches.size() || reading_done; });
-                if (next_job >= batches.size()) return;
-                b = batches[next_job++].get();
+                cv.wait(lk, [&] {
+                    if (failed) return true;
+                    bool pending = false;
+                    for (size_t s = written; s < produced; s++)
+                    {
+                        Batch* x = at(s);
+                        if (x->done) continue;
+                        if (x->normalized && !x->taken) { b = x; return true; }
+                        pending = true;
+                    }
+                    return reading_done && !pending;
+                });
+                if (failed || !b) return;
+                b->taken = true;
             }
             const uint64_t n = b->ids.size();
-            uint64_t cap = (uint64_t)(b->bases.size() * 1.3) + (1 << 16), need = 0;
+            uint64_t cap = (uint64_t)(b->n_bases * 1.3) + (1 << 16), need = 0;
             b->first.assign(n + 1, 0);
             b->stats.assign(n ? n : 1, pbsc_read_stats{});
             for (;;)
             {
-                b->pieces.resize(cap);
-                b->piece_off.assign((P.split ? b->bases.size() / 10 + 4 * n : n) + 16, 0);
-                b->rc = pbsc_correct_batch(index[g], &P, b->bases.data(), b->offsets.data(), n, b->pieces.data(), cap, b->piece_off.data(),
+                if (b->pieces.cap < cap) { g_pins.put(b->pieces); b->pieces = g_pins.get(cap); }
+                b->piece_off.assign((P.split ? b->n_bases / 10 + 4 * n : n) + 16, 0);
+                b->rc = pbsc_correct_batch(index[g], &P, b->bases.p, b->offsets.data(), n, b->pieces.p, b->pieces.cap, b->piece_off.data(),
                                            b->piece_off.size(), b->first.data(), b->stats.data(), &need);
-                if (b->rc == PBSC_ERR_LIMIT && need > cap) { cap = need + 64; continue; }
+                if (b->rc == PBSC_ERR_LIMIT && need > b->pieces.cap) { cap = need + 64; continue; }
                 break;
             }
-            if (b->rc != PBSC_OK) b->err = pbsc_last_error();
+            if (b->rc != PBSC_OK) { fail(pbsc_last_error()); return; }
             pbsc_last_timing(&b->timing);
             { std::lock_guard<std::mutex> lk(mu); b->done = true; }
             cv.notify_all();
         }
     };
-    std::vector<std::thread> workers;
-    for (int g = 0; g < ngpu; g++) workers.emplace_back(worker, g);
 
     int64_t totalReadsLen = 0, correctedLen = 0, totalSeedNum = 0, totalWalkNum = 0, highErrorNum = 0, exceedDepthNum = 0, exceedLeaveNum = 0, FMNum = 0,
             DPNum = 0, seedDis = 0;
     double seed_s = 0, fm_s = 0, dp_s = 0;
-    size_t written = 0, nreads = 0;
-    uint64_t inBases = 0;
-    auto flush = [&](bool all) -> bool {
+    auto writer = [&]() {
+        std::string line;
         for (;;)
         {
             Batch* b = nullptr;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                if (written >= batches.size()) return true;
-                b = batches[written].get();
-                if (!b->done) { if (!all) return true; cv.wait(lk, [&] { return b->done; }); }
+                cv.wait(lk, [&] { return failed || (written < produced && at(written)->done) || (reading_done && written == produced); });
+                if (failed || written == produced) return;
+                b = at(written);
             }
-            if (b->rc != PBSC_OK) { std::cerr << SUBPROGRAM ": " << b->err << "\n"; return false; }
             for (size_t r = 0; r < b->ids.size(); r++)
             {
                 const pbsc_read_stats& st = b->stats[r];
@@ -373,52 +496,69 @@ int main(int argc, char** argv)
                     exceedLeaveNum += st.exceed_leave_num; FMNum += st.fm_num; DPNum += st.dp_num; seedDis += st.seed_dis;
                     for (uint64_t j = b->first[r]; j < b->first[r + 1]; j++)
                     {
-                        correct << ">" << b->ids[r];
-                        if (P.split) correct << "_" << (j - b->first[r]);
-                        correct << "\n";
-                        correct.write(b->pieces.data() + b->piece_off[j], (std::streamsize)(b->piece_off[j + 1] - b->piece_off[j]));
-                        correct << "\n";
+                        line.assign(">"); line += b->ids[r];
+                        if (P.split) { line += "_"; line += std::to_string(j - b->first[r]); }
+                        line += "\n";
+                        fwrite(line.data(), 1, line.size(), correct);
+                        fwrite(b->pieces.p + b->piece_off[j], 1, (size_t)(b->piece_off[j + 1] - b->piece_off[j]), correct);
+                        fputc('\n', correct);
                     }
                 }
                 else
                 {
-                    discard << ">" << b->ids[r] << "\n";
-                    discard.write(b->bases.data() + b->offsets[r], (std::streamsize)(b->offsets[r + 1] - b->offsets[r]));
-                    discard << "\n";
+                    line.assign(">"); line += b->ids[r]; line += "\n";
+                    fwrite(line.data(), 1, line.size(), discard);
+                    fwrite(b->bases.p + b->offsets[r], 1, (size_t)(b->offsets[r + 1] - b->offsets[r]), discard);
+                    fputc('\n', discard);
                 }
             }
             seed_s += b->timing.seed_ms / 1e3; fm_s += (b->timing.extend_ms - b->timing.dp_ms) / 1e3; dp_s += b->timing.dp_ms / 1e3;
-            { std::lock_guard<std::mutex> lk(mu); batches[written].reset(new Batch()); batches[written]->done = true; }
-            written++;
+            b->release();
+            { std::lock_guard<std::mutex> lk(mu); inflight.pop_front(); written++; }
+            cv.notify_all();
         }
     };
 
+    std::vector<std::thread> threads;
+    for (int i = 0; i < std::max(1, opt::thread - 1); i++) threads.emplace_back(normalizer);
+    for (int w = 0; w < n_workers; w++) threads.emplace_back(worker, w % ngpu);
+    threads.emplace_back(writer);
+
     const uint64_t batch_bases = (uint64_t)(opt::batch_mbp * 1e6);
+    size_t nreads = 0;
+    uint64_t inBases = 0;
+    auto push = [&](std::unique_ptr<Batch>& cur) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || produced - written < max_inflight; });   // backpressure
+        if (failed) return;
+        cur->seq = produced++;
+        inflight.push_back(std::move(cur));
+        lk.unlock();
+        cv.notify_all();
+    };
     std::unique_ptr<Batch> cur(new Batch());
-    std::string id, seq;
-    bool ok = true;
-    while (ok && readRecord(in, id, seq))
+    cur->bases = g_pins.get(batch_bases + (1 << 20));
+    for (;;)
     {
-        cur->ids.push_back(id);
-        cur->bases += seq;
-        cur->offsets.push_back(cur->bases.size());
-        inBases += seq.size();
+        { std::lock_guard<std::mutex> lk(mu); if (failed) break; }
+        const size_t before = cur->n_bases;
+        if (!readRecord(in, *cur)) break;
+        inBases += cur->n_bases - before;
         nreads++;
-        if (cur->bases.size() >= batch_bases)
+        if (cur->n_bases >= batch_bases)
         {
-            { std::lock_guard<std::mutex> lk(mu); batches.push_back(std::move(cur)); }
-            cv.notify_all();
+            push(cur);
             cur.reset(new Batch());
-            ok = flush(false);
+            cur->bases = g_pins.get(batch_bases + (1 << 20));
         }
     }
-    if (!cur->ids.empty()) { std::lock_guard<std::mutex> lk(mu); batches.push_back(std::move(cur)); }
+    if (!cur->ids.empty()) push(cur); else if (cur) cur->release();
     { std::lock_guard<std::mutex> lk(mu); reading_done = true; }
     cv.notify_all();
-    if (ok) ok = flush(true);
-    for (auto& t : workers) t.join();
+    for (auto& t : threads) t.join();
+    fclose(correct); fclose(discard);
     for (auto* ix : index) pbsc_index_destroy(ix);
-    if (!ok) return EXIT_FAILURE;
+    if (failed) { std::cerr << fail_msg << "\n"; return EXIT_FAILURE; }
 
     double proc = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     fprintf(stderr, "Processed %zu sequences in %lfs (%lf sequences/s)\n", nreads, proc, (double)nreads / proc);

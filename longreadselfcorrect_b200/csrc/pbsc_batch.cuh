@@ -70,13 +70,14 @@ struct Workspace
     int blocks = 0;
     size_t scratch_stride = 0;
     float piece_factor = 1.5f;
+    uint32_t pool_nodes = 256;   // label-tree pool: nodes per task (successful light walks copy their tree there)
     bool thread_engine = true;
 };
 
-int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b);
+int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b, cudaStream_t st);
 int alloc_seed_workspace(const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w, cudaStream_t st);
 int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches);
-int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w);
+int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w, cudaStream_t st);
 // launches the chain kernel; returns PBSC_ERR_LIMIT when some read overflowed its scratch/piece capacity
 int run_extend_chain(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches);
 // thread-per-walk engine with speculative pair scheduling (pbsc_extend_thread.cu); same outputs in the same buffers

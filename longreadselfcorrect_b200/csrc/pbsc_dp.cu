@@ -23,6 +23,7 @@
 #include <vector>
 #include "pbsc_batch.cuh"
 #include "pbsc_task.cuh"
+#include <chrono>
 #include "pbsc_dp.cuh"
 #include "pbsc_dp_thread.cuh"
 #include "pbsc_dp_msa.cuh"
@@ -683,7 +684,8 @@ dp_job_keys_kernel(uint64_t j0, uint64_t j1, const DpJob* __restrict__ jobs, con
 
 __global__ void __launch_bounds__(64)
 dp_msa_kernel(uint64_t j0, uint64_t j1, const uint32_t* __restrict__ order, int deal, const DpJob* __restrict__ jobs, WalkTask* tasks,
-              const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem, uint64_t mem0, uint8_t* outpool, unsigned int* n_bad)
+              const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem, uint64_t mem0, uint8_t* outpool, unsigned int* n_bad,
+              uint32_t big_thr, uint32_t* big_list, unsigned int* n_big)
 {
     const uint64_t tx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint64_t njc = j1 - j0;
@@ -700,15 +702,60 @@ dp_msa_kernel(uint64_t j0, uint64_t j1, const uint32_t* __restrict__ order, int 
     WalkTask& tk = tasks[J.task];
     const uint32_t nr = job_rows_of(J);
     const DpRow* R = rows + (J.row0 - row_base);
+    if (big_list)
+    {
+        // a pile-up of more than big_thr alignment columns goes to the warp-per-job kernel: this launch would wait for it
+        uint32_t cost = 0, passing = 0;
+        for (uint32_t r = 0; r < nr; r++) { const DpRow x = R[r]; if (x.pass == 1) { passing++; cost += x.nops; } }
+        if (passing >= 3 && cost >= big_thr) { big_list[atomicAdd(n_big, 1u)] = (uint32_t)(jx - j0); return; }
+    }
     JobView v;
     job_view(mem + (J.mem - mem0), J, nr, v);
     const MsaCtx ctx{tk, outpool};
     uint32_t n = 0;
     const int rc = msa::consensus(v, J.qlen, J.k, R, nr, ctx, n);
     if (rc == 1) { tk.dp_status = PBSC_DP_FEW_ROWS; return; }
-    if (rc == 2) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_WALK_OVERFLOW; return; }
+    if (rc == 2) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_OVF_DP; return; }
     tk.out_len = n;
     tk.dp_status = PBSC_DP_OK;
+}
+
+// the large pile-ups dp_msa_kernel set aside: one warp per job, the alignment columns of every row cut into 32 segments
+// (msa::consensus_warp, pbsc_dp_msa.cuh); warps take jobs from a queue
+constexpr int MSA_WARPS = 4;
+__global__ void __launch_bounds__(MSA_WARPS * 32)
+dp_msa_warp_kernel(uint64_t j0, const uint32_t* __restrict__ big_list, const unsigned int* __restrict__ n_big, unsigned long long* counter,
+                   const DpJob* __restrict__ jobs, WalkTask* tasks, const DpRow* __restrict__ rows, uint64_t row_base, uint8_t* mem, uint64_t mem0,
+                   uint8_t* outpool, unsigned int* n_bad)
+{
+    __shared__ unsigned int gap_counter[MSA_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long n = *n_big;
+    for (;;)
+    {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n) break;
+        const uint64_t jx = j0 + big_list[it];
+        const DpJob J = jobs[jx];
+        WalkTask& tk = tasks[J.task];
+        const uint32_t nr = job_rows_of(J);
+        const DpRow* R = rows + (J.row0 - row_base);
+        JobView v;
+        job_view(mem + (J.mem - mem0), J, nr, v);
+        const MsaCtx ctx{tk, outpool};
+        uint32_t nout = 0;
+        const int rc = msa::consensus_warp(v, J.qlen, J.k, R, nr, ctx, nout, &gap_counter[warp]);
+        __syncwarp();
+        if (lane == 0)
+        {
+            if (rc == 1) tk.dp_status = PBSC_DP_FEW_ROWS;
+            else if (rc == 2) { atomicAdd(n_bad, 1u); tk.dp_status = PBSC_OVF_DP; }
+            else { tk.out_len = nout; tk.dp_status = PBSC_DP_OK; }
+        }
+        __syncwarp();
+    }
 }
 
 template <class T>
@@ -754,6 +801,16 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     WalkTask* tasks = (WalkTask*)tasks_v;
     cudaStream_t st = idx->stream;
     if (n_items == 0) return PBSC_OK;
+    // PBSC_ROUND_TRACE=1: host wall clock between the steps of this stage (diagnostics)
+    const bool htrace = getenv("PBSC_ROUND_TRACE") != nullptr;
+    auto h0 = std::chrono::steady_clock::now();
+    auto hmark = [&](const char* what) {
+        if (!htrace) return;
+        const auto now = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(now - h0).count();
+        if (ms > 2.0) fprintf(stderr, "[pbsc round trace]     dp host: %-22s %8.2f ms\n", what, ms);
+        h0 = now;
+    };
     DpJob* jobs; uint64_t *job_rows, *job_bytes, *row_off, *mem_off; unsigned int* cnt; unsigned long long* qctr;
     PBSC_CUDA(arena(idx, "dp.jobs", n_items, &jobs));
     PBSC_CUDA(arena(idx, "dp.job_rows", n_items + 1, &job_rows));
@@ -775,6 +832,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     if (launches) *launches += 1;
     const uint64_t nj = hcnt[0];
     DpStats& S = last_dp_stats();
+    hmark("collect + sync");
     if (nj == 0) return PBSC_OK;
     // offsets of every job's rows and scratch
     {
@@ -795,20 +853,23 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     PBSC_CUDA(cudaMemcpyAsync(h_mem.data(), mem_off, (nj + 1) * 8, cudaMemcpyDeviceToHost, st));
     PBSC_CUDA(cudaStreamSynchronize(st));
     if (launches) *launches += 3;
+    hmark("scans + sync");
     S.jobs += nj; S.rows += h_row[nj];
     // scratch budget of one chunk
     // Large chunks matter: the multiple-alignment kernel is one thread per job and a launch lasts as long as its longest job,
     // so few, full launches beat many small ones (repeat-rich 100x workload: DP stage 2.9 s with 6 GB chunks, 2.4 s with 20 GB).
     uint64_t budget = 20ull << 30;
     {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        // what is free now plus what the grow-only arena already holds for this purpose; cudaMemGetInfo costs 5-60 ms with tens
+        // of gigabytes allocated (PBSC_ROUND_TRACE), so it is asked only when this stage needs more than the arena has
+        const auto it = idx->arena.find("dp.mem");
+        const uint64_t have = it != idx->arena.end() ? (uint64_t)it->second.cap : 0;
+        if (h_mem[nj] > have)
         {
-            // what is free now plus what the grow-only arena already holds for this purpose
-            const auto it = idx->arena.find("dp.mem");
-            const uint64_t have = it != idx->arena.end() ? (uint64_t)it->second.cap : 0;
-            budget = std::min<uint64_t>(budget, std::max<uint64_t>(2ull << 30, (free_b + have) / 2));
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<uint64_t>(budget, std::max<uint64_t>(2ull << 30, (free_b + have) / 2));
         }
+        else budget = std::max<uint64_t>(have, 1);
     }
     if (const char* e = getenv("PBSC_DP_CHUNK_MB")) { if (atoll(e) > 0) budget = (uint64_t)atoll(e) << 20; }
     uint64_t max_job = 0;
@@ -816,7 +877,9 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     if (max_job > budget) budget = max_job;
     const uint64_t pool_bytes = std::min(budget, h_mem[nj]);
     uint8_t* mem;
+    hmark("budget");
     PBSC_CUDA(arena(idx, "dp.mem", pool_bytes, &mem));
+    hmark("arena dp.mem");
     // alignment kernel geometry: one flag slab per resident warp, sized for the longest query of this stage
     int per_sm = 0;
     PBSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_align_kernel, DP_WARPS * 32, 0));
@@ -837,6 +900,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         j0 = j1;
     }
     DpRow* rows;
+    hmark("flags arena + chunking");
     PBSC_CUDA(arena(idx, "dp.rows", max_rows, &rows));
     // thread-per-alignment kernel (stage 2t): sort keys, the sorted order, one flag arena per resident warp
     bool use_thread = true;
@@ -885,6 +949,14 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         cub::DeviceRadixSort::SortPairs(nullptr, jsort_bytes, jkeys, jkeys2, jord, jord2, (int)nj, 0, 16, st);
         PBSC_CUDA(arena(idx, "dp.jsorttmp", jsort_bytes, &jsort_tmp));
     }
+    // pile-ups of at least this many alignment columns are left to the warp-per-job kernel (PBSC_MSA_WARP_MIN: 0 = every job,
+    // -1 = none)
+    uint32_t msa_big_thr = 8192;
+    if (const char* e = getenv("PBSC_MSA_WARP_MIN")) msa_big_thr = atoll(e) < 0 ? 0xffffffffu : (uint32_t)atoll(e);
+    uint32_t* msa_big = nullptr;
+    unsigned long long* msa_q = nullptr;
+    PBSC_CUDA(arena(idx, "dp.msa_big", nj, &msa_big));
+    PBSC_CUDA(arena(idx, "dp.msa_q", 2, &msa_q));
     // PBSC_DP_PROFILE=1: per-kernel CUDA-event times of this stage on stderr (diagnostics, off by default)
     struct Prof
     {
@@ -910,6 +982,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     } prof;
     prof.st = st;
     if (const char* e = getenv("PBSC_DP_PROFILE")) prof.on = atoi(e) != 0;
+    hmark("pass setup + arenas");
     prof.mark("start");
     for (uint64_t j0 = 0; j0 < nj;)
     {
@@ -954,20 +1027,32 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
             jorder = jord2;
             if (launches) *launches += 3;
         }
+        PBSC_CUDA(cudaMemsetAsync(msa_q, 0, 16, st));
         dp_msa_kernel<<<(unsigned)((((njc + 31) / 32) * 32 + 63) / 64), 64, 0, st>>>(j0, j1, jorder, sort_jobs == 1, jobs, tasks, rows, h_row[j0], mem,
-                                                                                         h_mem[j0], outpool, cnt + 1);
+                                                                                         h_mem[j0], outpool, cnt + 1, msa_big_thr,
+                                                                                         msa_big_thr != 0xffffffffu ? msa_big : nullptr, (unsigned int*)(msa_q + 1));
         prof.mark("msa");
+        if (msa_big_thr != 0xffffffffu)
+        {
+            const int wb = (int)std::min<uint64_t>((uint64_t)idx->sm_count * 4, (njc + MSA_WARPS - 1) / MSA_WARPS);
+            dp_msa_warp_kernel<<<wb, MSA_WARPS * 32, 0, st>>>(j0, msa_big, (const unsigned int*)(msa_q + 1), msa_q, jobs, tasks, rows, h_row[j0], mem, h_mem[j0],
+                                                              outpool, cnt + 1);
+            prof.mark("msa_warp");
+            if (launches) *launches += 1;
+        }
         PBSC_CUDA(cudaGetLastError());
         if (launches) *launches += 4;
         S.chunks++;
         j0 = j1;
     }
     PBSC_CUDA(cudaEventRecord(ev[1], st));
+    hmark("chunk loop (launches)");
     prof.report();
     PBSC_CUDA(cudaMemcpyAsync(hcnt, cnt, 12, cudaMemcpyDeviceToHost, st));
     PBSC_CUDA(cudaStreamSynchronize(st));
     S.bad += hcnt[1];
     S.thread_rows += hcnt[2];
+    PBSC_OCC_TAKE(3, st);
     float ms = 0;
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
     S.ms += ms;

@@ -330,9 +330,8 @@ int launch_geometry(int device, int* blocks)
     return PBSC_OK;
 }
 
-int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w)
+int alloc_extend_workspace(pbsc_index* idx, const pbsc_params* p, const std::vector<uint64_t>& h_offsets, DeviceBatch& b, SeedBuffers& s, Workspace& w, cudaStream_t st)
 {
-    cudaStream_t st = idx->stream;
     const uint64_t n = b.n_reads;
     // per-read output regions sized from the read length alone, so nothing has to come back from the seed phase
     w.h_piece_region.assign(n + 1, 0);

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include "pbsc_batch.cuh"
 #include "pbsc_task.cuh"
 #include "pbsc_dp.cuh"
@@ -22,7 +23,6 @@
 namespace pbsc {
 
 constexpr int TW_BLOCK = 128;
-constexpr int HEAVY_WARPS = 4;
 struct ReadState
 {
     int32_t t, next, started, done, rstatus, firstType;
@@ -238,11 +238,16 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
                    unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
                    const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
                    unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy, uint32_t* nodepool,
-                   unsigned long long* pool_used, uint64_t pool_cap, tw::Caps caps, const unsigned int* n_items_dev, int last_pass)
+                   unsigned long long* pool_used, uint64_t pool_cap, tw::Caps caps, const unsigned int* n_items_dev, int last_pass, int owners)
 {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // lanes 0 .. owners-1 of every warp take walks (and own scratch); the others only work in the pooled stages
+    const bool owner = (int)(threadIdx.x & 31) < owners;
+    const size_t tid = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (size_t)owners + (threadIdx.x & 31);
+    __shared__ tw::LaneCtx ctx_all[TW_BLOCK];
+    tw::LaneCtx* ctx = ctx_all + (threadIdx.x & ~31u);    // this warp's 32 records
+    tw::LaneCtx& mine = ctx[threadIdx.x & 31];
     tw::TScratch lane;
-    tw::carve(scratch + tid * stride, P.node_cap, caps, lane);
+    tw::carve(scratch + (owner ? tid : 0) * stride, P.node_cap, caps, lane);
     if (n_items_dev) n_items = *n_items_dev;      // a later pass: its item count was produced on the device
     tw::State S;
     S.status = 0; S.n = 0;
@@ -253,7 +258,7 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
     // them (waiting until 8 lanes are idle) was measured and lost: 783 -> 832 ms on config 2, idle lanes cost more than the
     // divergent refill path.
     constexpr int REFILL_BATCH = 1;
-    bool active = false, ended = false, exhausted = false;
+    bool active = false, ended = false, exhausted = !owner;
     unsigned long long done = 0;
     for (;;)
     {
@@ -266,7 +271,7 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
                 int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
                 // the last pass carries everything the reference's loop can hold (-l leaves, 4 children each); only the
                 // label tree and the result list are bounded, and running out of those is reported, not hidden
-                if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_WALK_OVERFLOW;
+                if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_OVF_TREE;
                 tk->out_len = 0;
                 tk->status = st;
                 if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
@@ -294,17 +299,42 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
             }
         }
         if (__all_sync(FULL, !active)) break;   // only reached with nobody waiting either: every lane is exhausted
+        // ---- one level of extendOverlap's loop for every walking lane; the stages that touch the index or the per-walk
+        //      tables are pooled over the warp (pbsc_walk_thread.cuh) ----
+        const bool lv = active && tw::walk_continues(S);
+        if (lv) tw::publish(mine, S);
         {
-            // warp-wide stage: the leaves of all 32 walks that start this level by refining are pooled and dealt out evenly
-            const bool need = active && tw::walk_continues(S) && tw::needs_refine(S);
-            tw::refine_coop(idx, need ? S.n : 0u, S.s.oldL, (int)S.maxOverlap);
+            const bool need = lv && tw::needs_refine(S);
+            tw::refine_pool(idx, ctx, need ? S.n : 0u);
             if (need) S.curK = S.maxOverlap;
         }
-        if (active)
+        if (lv)
         {
-            if (tw::walk_continues(S)) tw::one_level(S);
-            if (!tw::walk_continues(S)) { active = false; ended = true; }
+            double minErr;
+            tw::filter_leaves(S, minErr);
+            mine.minErr = minErr; mine.n = S.n; mine.thr = S.phase == 2 ? S.minSA - 1 : S.minSA;
         }
+        tw::pool_run(lv ? S.n : 0u, [&](int owner, uint32_t i) { tw::probe_leaf(idx, ctx[owner], i); });
+        uint32_t m = 0, sel = 0;
+        bool go = false;
+        if (lv)
+        {
+            m = tw::adopt_children(S);
+            if (S.status == 0) go = tw::level_middle(S, mine, m, sel);
+            if (go) { mine.curLen = (uint32_t)S.curLen; mine.level = S.level; }
+        }
+        if (__any_sync(FULL, sel != 0))
+        {
+            tw::pool_run(sel, [&](int owner, uint32_t i) { tw::select_leaf(idx, ctx[owner], i); });
+            if (sel) tw::level_select(S, mine);
+            tw::pool_run(sel, [&](int owner, uint32_t i) { tw::reselect_leaf(idx, ctx[owner], i); });
+        }
+        tw::pool_run(go ? m : 0u, [&](int owner, uint32_t j) { tw::prune_leaf(P, ctx[owner], j); });
+        bool check_term = false;
+        if (go) { S.level++; check_term = S.curLen >= S.minLength; }
+        tw::pool_run(check_term ? m : 0u, [&](int owner, uint32_t j) { tw::term_leaf(ctx[owner], j); });
+        if (go) tw::finish_level(S, m, check_term);
+        if (active && !tw::walk_continues(S)) { active = false; ended = true; }
     }
     if (done) atomicAdd(walk_counter, done);
 }
@@ -317,23 +347,23 @@ walk_levels_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
                    unsigned long long* counter, uint64_t n_items, const uint32_t* __restrict__ list, WalkTask* tasks, uint8_t* recpool,
                    const uint64_t* __restrict__ rec_off, uint64_t pend_base, uint64_t pend_cap, uint8_t* outpool, uint64_t minSA,
                    unsigned long long* walk_counter, uint32_t* heavy_list, unsigned int* n_heavy, uint32_t* nodepool,
-                   unsigned long long* pool_used, uint64_t pool_cap, tw::Caps caps, const unsigned int* n_items_dev, int last_pass)
+                   unsigned long long* pool_used, uint64_t pool_cap, tw::Caps caps, const unsigned int* n_items_dev, int last_pass, int owners)
 {
     walk_levels_body(idx, P, scratch, stride, counter, n_items, list, tasks, recpool, rec_off, pend_base, pend_cap, outpool, minSA, walk_counter,
-                     heavy_list, n_heavy, nodepool, pool_used, pool_cap, caps, n_items_dev, last_pass);
+                     heavy_list, n_heavy, nodepool, pool_used, pool_cap, caps, n_items_dev, last_pass, owners);
 }
 typedef void (*WalkKernel)(FmIndexDev, ExtParamsDev, uint8_t*, size_t, unsigned long long*, uint64_t, const uint32_t*, WalkTask*, uint8_t*,
                            const uint64_t*, uint64_t, uint64_t, uint8_t*, uint64_t, unsigned long long*, uint32_t*, unsigned int*, uint32_t*,
-                           unsigned long long*, uint64_t, tw::Caps, const unsigned int*, int);
+                           unsigned long long*, uint64_t, tw::Caps, const unsigned int*, int, int);
 static WalkKernel walk_kernel_for(int minb)
 {
-    switch (minb) { case 3: return walk_levels_kernel<3>; case 4: return walk_levels_kernel<4>; case 5: return walk_levels_kernel<5>; default: return walk_levels_kernel<6>; }
+    switch (minb) { case 3: return walk_levels_kernel<3>; case 4: return walk_levels_kernel<4>; case 5: return walk_levels_kernel<5>; case 7: return walk_levels_kernel<7>; case 8: return walk_levels_kernel<8>; default: return walk_levels_kernel<6>; }
 }
 static int walk_min_blocks()
 {
     const char* e = getenv("PBSC_TW_MINB");
     const int v = e ? atoi(e) : 6;   // measured on config 2: 1002 ms at 3 blocks/SM, 867 ms at 6
-    return (v >= 3 && v <= 6) ? v : 6;
+    return (v >= 3 && v <= 8) ? v : 6;
 }
 
 // thread per task: write the merged sequence of every light walk that succeeded
@@ -354,65 +384,6 @@ materialize_kernel(uint64_t n_items, const uint32_t* __restrict__ list, WalkTask
     const int st = tw::materialize(v, min_overlap, nodepool, outpool + tk.out_off, tk.out_cap, &mlen);
     tk.out_len = st == 1 ? mlen : 0;
     tk.status = st;
-}
-
-// Heavy walks (wide frontiers) re-walked by the warp-cooperative engine: warp per task, lanes own leaves / probes.
-__global__ void __launch_bounds__(HEAVY_WARPS * 32, 2)
-walk_heavy_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant__ ExtParamsDev P, uint8_t* scratch, size_t stride,
-                  unsigned long long* counter, const unsigned int* n_heavy, const uint32_t* __restrict__ heavy_list, WalkTask* tasks,
-                  const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offsets, uint8_t* outpool, uint64_t minSA)
-{
-    __shared__ WarpShared shared[HEAVY_WARPS];
-    const int warp_in_block = threadIdx.x >> 5;
-    const int lane = lane_id();
-    WarpShared& sh = shared[warp_in_block];
-    WarpScratch ws;
-    carve_scratch(scratch + ((size_t)blockIdx.x * HEAVY_WARPS + warp_in_block) * stride, P, ws);
-    const unsigned long long n_items = *n_heavy;
-    for (;;)
-    {
-        unsigned long long it = 0;
-        if (lane == 0) it = atomicAdd(counter, 1ull);
-        it = __shfl_sync(FULL, it, 0);
-        if (it >= n_items) break;
-        WalkTask& tk = tasks[heavy_list[it]];
-        int interval; uint32_t trgLen, qlen;
-        task_shape(tk, interval, trgLen, qlen);
-        const uint8_t* read = codes + offsets[tk.read];
-        const uint8_t* pth = read + tk.src_end + 1;
-        const uint8_t* trgS = read + tk.trg_start;
-        const int k = tk.k;
-        int st;
-        uint32_t mlen = 0;
-        if (qlen > P.q_cap) st = PBSC_WALK_OVERFLOW;
-        else
-        {
-            for (uint32_t x = lane; x < qlen; x += 32)
-            {
-                uint8_t c;
-                if (!tk.rtou)
-                    c = x < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - x) : (x < (uint32_t)(k + interval) ? pth[x - k] : trgS[x - k - interval]);
-                else
-                {
-                    const uint32_t y = qlen - 1 - x;
-                    const uint8_t d = y < (uint32_t)k ? (uint8_t)tail_base(tk.src_hi, tk.src_lo, k - 1 - y)
-                                                      : (y < (uint32_t)(k + interval) ? pth[y - k] : trgS[y - k - interval]);
-                    c = 3 - d;
-                }
-                ws.q[x] = c;
-            }
-            __syncwarp();
-            st = walk_pair(idx, P, ws, sh, qlen, (uint32_t)k, interval, trgLen, minSA, &mlen);
-            __syncwarp();
-            if (st == 1)
-            {
-                if (mlen > tk.out_cap) st = PBSC_WALK_OVERFLOW;
-                else for (uint32_t x = lane; x < mlen; x += 32) outpool[tk.out_off + x] = ws.merged[x];
-            }
-        }
-        if (lane == 0) { tk.out_len = st == 1 ? mlen : 0; tk.status = st; }
-        __syncwarp();
-    }
 }
 
 struct StitchParams { int32_t start_kmer, next_target, split, no_dp; };
@@ -448,7 +419,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
         if (ns >= 2)
         {
             const pbsc_seed s0 = sv[0];
-            if ((uint64_t)s0.len > pieceCap || boundsCap < 2) S.rstatus = PBSC_WALK_OVERFLOW;
+            if ((uint64_t)s0.len > pieceCap || boundsCap < 2) S.rstatus = PBSC_OVF_PIECES;
             else
             {
                 for (int x = 0; x < s0.len; x++) piece[x] = read[s0.start + x];
@@ -515,7 +486,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                     }
                 }
                 const int stw = use->status;
-                if (stw == PBSC_WALK_OVERFLOW || stw == PBSC_WALK_UNSUPPORTED) { S.rstatus = stw; break; }
+                if (is_overflow(stw) || stw == PBSC_WALK_UNSUPPORTED) { S.rstatus = stw; break; }
                 if (S.next == 0)
                 {
                     S.firstType = stw;
@@ -529,14 +500,14 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                     if (!rtou)
                     {
                         outLen = mlen - k;
-                        if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_OVF_PIECES; break; }
                         for (uint64_t x = 0; x < outLen; x++) piece[S.plen + x] = merged[k + x];
                     }
                     else
                     {
                         const uint64_t tailLen = tg.len - k;
                         outLen = (mlen - k) + tailLen;
-                        if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_OVF_PIECES; break; }
                         for (uint64_t x = 0; x < mlen - k; x++) piece[S.plen + x] = 3 - merged[mlen - 1 - (k + x)];
                         for (uint64_t x = 0; x < tailLen; x++) piece[S.plen + (mlen - k) + x] = read[tg.start + k + x];
                     }
@@ -562,14 +533,14 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 else { S.rstatus = PBSC_WALK_NO_PATH; break; }
                 S.st.total_walk_num++;
                 // correctByMSAlignment (PacBioSelfCorrectionProcess.cpp:134-136, 208-245)
-                if (S.dpStatus0 == PBSC_WALK_OVERFLOW || S.dpStatus0 == PBSC_WALK_UNSUPPORTED) { S.rstatus = S.dpStatus0; break; }
+                if (is_overflow(S.dpStatus0) || S.dpStatus0 == PBSC_WALK_UNSUPPORTED) { S.rstatus = S.dpStatus0; break; }
                 if (S.dpStatus0 == PBSC_DP_OK)
                 {
                     int k; bool rtou;
                     pair_inputs(S.srcEndBest, S.srcRepeat, S.srcLen, tg, C.start_kmer, k, rtou);
                     const uint8_t* cons = outpool + S.dpOff0;
                     const uint64_t outLen = S.dpLen0 - (uint32_t)k;
-                    if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                    if (S.plen + outLen > pieceCap) { S.rstatus = PBSC_OVF_PIECES; break; }
                     for (uint64_t x = 0; x < outLen; x++) piece[S.plen + x] = cons[k + x];
                     S.plen += outLen;
                     S.srcLen += outLen;
@@ -581,7 +552,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 {
                     if (C.split)
                     {
-                        if (S.plen + tg.len > pieceCap || S.nPieces + 1 >= boundsCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        if (S.plen + tg.len > pieceCap || S.nPieces + 1 >= boundsCap) { S.rstatus = PBSC_OVF_PIECES; break; }
                         bounds[S.nPieces] = (uint32_t)S.plen;
                         S.nPieces++;
                         for (int x = 0; x < tg.len; x++) piece[S.plen + x] = read[tg.start + x];
@@ -592,7 +563,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                     {
                         const int tgEnd = tg.start + tg.len - 1;
                         const uint64_t n = (uint64_t)(tgEnd - S.srcEnd);
-                        if (S.plen + n > pieceCap) { S.rstatus = PBSC_WALK_OVERFLOW; break; }
+                        if (S.plen + n > pieceCap) { S.rstatus = PBSC_OVF_PIECES; break; }
                         for (uint64_t x = 0; x < n; x++) piece[S.plen + x] = read[S.srcEnd + 1 + x];
                         S.plen += n;
                         S.srcLen += n;
@@ -646,7 +617,7 @@ struct ThreadEngine
     tw::Caps light, heavy;
     size_t stride = 0, hstride = 0;
     int blocks = 0, hblocks = 0;
-    bool heavy_engine_warp = false;
+    int heavy_owners = 8;   // most lanes of a warp that own a walk in a full-capacity pass (PBSC_TW_HEAVY_OWNERS)
     bool no_dp = true;
     const pbsc_params* params = nullptr;
     WalkKernel kernel = nullptr;
@@ -654,6 +625,7 @@ struct ThreadEngine
     std::vector<cudaEvent_t> ev;
     ~ThreadEngine() { for (auto e : ev) cudaEventDestroy(e); }
     void mark(cudaStream_t st) { cudaEvent_t e; if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); ev.push_back(e); } }
+    std::vector<std::pair<const char*, uint64_t>> ev_what;   // PBSC_ROUND_TRACE: pass name and item count of every walk launch
     ArenaPtr<unsigned long long> pool_used;
     uint64_t pool_cap = 0;
     ArenaPtr<unsigned int> n_heavy;
@@ -678,84 +650,67 @@ static int launch_walk(pbsc_index* idx, const ExtParamsDev& P, ThreadEngine& E, 
     PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
     setup_tasks_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(idx->dev, P, n_items, list, tasks, b.codes.p, b.offsets.p, recpool, E.rec_off.p,
                                                                          E.pend_rec_base, pcap);
+    PBSC_OCC_TAKE(1, st);
     const uint64_t threads = (uint64_t)E.blocks * TW_BLOCK;
     int nb = E.blocks;
     if (n_items < threads) nb = (int)((n_items + TW_BLOCK - 1) / TW_BLOCK);
     if (nb < 1) nb = 1;
     PBSC_CUDA(cudaMemsetAsync(E.n_heavy.p, 0, 8, st));
     PBSC_CUDA(cudaMemsetAsync(E.pool_used.p, 0, 8, st));
-    // A small round (re-walks of mispredicted pairs) lasts as long as its longest walk, whatever the pass: one pass at full
-    // capacities instead of a light and a heavy one halves that.
-    bool dp_done = false;
-    const bool single_pass = !E.heavy_engine_warp && n_items * 2 <= (uint64_t)E.hblocks * TW_BLOCK;
+    // A pass of few, long walks (the full-capacity pass, the re-walk rounds) lasts as long as its longest walk, and a walk
+    // advances one level per round of the warp's pooled stages: the fewer walks share a warp, the fewer rounds a level takes.
+    // Such passes therefore give walks to only `owners` lanes of every warp (the other lanes only help), as few as the number
+    // of resident warps allows.  The light pass of a large round is bound by throughput and uses all 32.
+    const uint64_t warps_max = (uint64_t)E.blocks * (TW_BLOCK / 32);
+    auto geometry = [&](uint64_t walks, int& owners, int& blocks) {
+        owners = (int)std::min<uint64_t>((uint64_t)E.heavy_owners, std::max<uint64_t>(1, (walks + warps_max - 1) / warps_max));
+        blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)E.blocks, (walks + (uint64_t)owners * (TW_BLOCK / 32) - 1) / ((uint64_t)owners * (TW_BLOCK / 32))));
+    };
+    // A small round (re-walks of mispredicted pairs): one pass at full capacities instead of a light and a heavy one.
+    const bool single_pass = n_items <= warps_max * (uint64_t)E.heavy_owners / 2;
     if (single_pass)
     {
-        const int hb = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)E.hblocks, (n_items + TW_BLOCK - 1) / TW_BLOCK));
+        int owners, hb;
+        geometry(n_items, owners, hb);
+        E.ev_what.push_back({"single", n_items});
         E.mark(st);
         E.kernel<<<hb, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, n_items, list, tasks, recpool, E.rec_off.p,
                                           E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
-                                          E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, nullptr, 1);
+                                          E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, nullptr, 1, owners);
         E.mark(st);
     }
     else
     {
-    E.mark(st);
-    E.kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, recpool, E.rec_off.p,
-                                                E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
-                                                E.nodepool.p, E.pool_used.p, E.pool_cap, E.light, nullptr, 0);
-    E.mark(st);
-    PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
-    if (E.heavy_engine_warp)
-    {
-        // the walks that outgrew the light pass, on the warp engine (the kernel reads the count from the device)
-        walk_heavy_kernel<<<E.wblocks, HEAVY_WARPS * 32, 0, st>>>(idx->dev, E.Pw, E.wscratch.p, E.wstride, w.counters.p, E.n_heavy.p, E.heavy_list.p, tasks,
-                                                                 b.codes.p, b.offsets.p, E.outpool.p, minSA);
-    }
-    else
-    {
-        // The heavy pass is a few long, latency-bound walks; the DP fallback of the light pass's failures is issue-bound and
-        // touches disjoint tasks, so the two can overlap on a side stream (PBSC_OVERLAP=1).  Measured on config 2: no gain
-        // (1920 ms either way: both kernels slow down by what the other takes), so it is off by default.
-        const bool overlap = !E.no_dp && getenv("PBSC_OVERLAP") && atoi(getenv("PBSC_OVERLAP")) > 0;
-        if (overlap)
+        E.ev_what.push_back({"light", n_items});
+        E.mark(st);
+        E.kernel<<<nb, TW_BLOCK, 0, st>>>(idx->dev, P, E.scratch.p, E.stride, w.counters.p, n_items, list, tasks, recpool, E.rec_off.p,
+                                          E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p, E.n_heavy.p,
+                                          E.nodepool.p, E.pool_used.p, E.pool_cap, E.light, nullptr, 0, 32);
+        E.mark(st);
+        PBSC_CUDA(cudaMemsetAsync(w.counters.p, 0, 8, st));
+        // the walks that outgrew the light pass: how many there are decides the geometry (4-byte round trip)
+        unsigned int nh = 0;
+        PBSC_CUDA(cudaMemcpyAsync(&nh, E.n_heavy.p, 4, cudaMemcpyDeviceToHost, st));
+        PBSC_CUDA(cudaStreamSynchronize(st));
+        if (nh)
         {
-            if (!idx->stream2) PBSC_CUDA(cudaStreamCreateWithFlags(&idx->stream2, cudaStreamNonBlocking));
-            if (!idx->ev_a) PBSC_CUDA(cudaEventCreateWithFlags(&idx->ev_a, cudaEventDisableTiming));
-            if (!idx->ev_b) PBSC_CUDA(cudaEventCreateWithFlags(&idx->ev_b, cudaEventDisableTiming));
+            int owners, hb;
+            geometry(nh, owners, hb);
+            E.ev_what.push_back({"heavy", nh});
+            E.mark(st);
+            E.kernel<<<hb, TW_BLOCK, 0, st>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, nh, E.heavy_list.p, tasks, recpool, E.rec_off.p,
+                                              E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p + E.heavy_cap,
+                                              E.n_heavy.p + 1, E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, nullptr, 1, owners);
+            E.mark(st);
         }
-        cudaStream_t s2 = overlap ? idx->stream2 : st;
-        if (s2 != st) { PBSC_CUDA(cudaEventRecord(idx->ev_a, st)); PBSC_CUDA(cudaStreamWaitEvent(s2, idx->ev_a, 0)); }
-        E.mark(s2);
-        E.kernel<<<E.hblocks, TW_BLOCK, 0, s2>>>(idx->dev, E.Pw, E.hscratch.p, E.hstride, w.counters.p, 0, E.heavy_list.p, tasks, recpool, E.rec_off.p,
-                                                           E.pend_rec_base, pcap, E.outpool.p, minSA, w.counters.p + 1, E.heavy_list.p + E.heavy_cap,
-                                                           E.n_heavy.p + 1, E.nodepool.p, E.pool_used.p, E.pool_cap, E.heavy, E.n_heavy.p, 1);
-        E.mark(s2);
         PBSC_CUDA(cudaGetLastError());
-        if (s2 != st)
-        {
-            PBSC_CUDA(cudaEventRecord(idx->ev_b, s2));
-            // DP fallback of everything the light pass settled (tasks still in the heavy pass are skipped: their status is not final)
-            const int rc = run_dp_fallback(idx, E.params, b, tasks, n_items, list, E.outpool.p, w.q_cap, launches);
-            if (rc != PBSC_OK) { cudaStreamSynchronize(s2); return rc; }
-            PBSC_CUDA(cudaStreamWaitEvent(st, idx->ev_b, 0));
-            // ... and of the heavy pass's own failures
-            unsigned int nh = 0;
-            PBSC_CUDA(cudaMemcpyAsync(&nh, E.n_heavy.p, 4, cudaMemcpyDeviceToHost, st));
-            PBSC_CUDA(cudaStreamSynchronize(st));
-            if (nh)
-            {
-                const int rc2 = run_dp_fallback(idx, E.params, b, tasks, nh, E.heavy_list.p, E.outpool.p, w.q_cap, launches);
-                if (rc2 != PBSC_OK) return rc2;
-            }
-            dp_done = true;
-        }
     }
-    }
+    PBSC_OCC_TAKE(2, st);
     materialize_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, st>>>(n_items, list, tasks, recpool, E.rec_off.p, E.pend_rec_base, pcap,
                                                                          E.nodepool.p, E.outpool.p, P.min_overlap, P.seed_size);
     PBSC_CUDA(cudaGetLastError());
     if (launches) *launches += 4;
-    if (!E.no_dp && !dp_done)
+    if (!E.no_dp)
     {
         const int rc = run_dp_fallback(idx, E.params, b, tasks, n_items, list, E.outpool.p, w.q_cap, launches);
         if (rc != PBSC_OK) return rc;
@@ -785,6 +740,31 @@ static int scan_u64(DevBuf<uint8_t>& tmp, const uint64_t* in, uint64_t* out, uin
     return PBSC_OK;
 }
 
+// which idmers occur on which strand, for every possible idmer (4^-i entries): built once per index and -i value
+int ensure_idmer_table(pbsc_index* idx, int idmer_len)
+{
+    if (idx->dev.idmer_len == idmer_len && idx->dev.idmer_valid) return PBSC_OK;
+    PBSC_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    const uint64_t n_keys = 1ull << (2 * idmer_len);
+    if (idx->d_idmer_valid)
+    {
+        if (!idx->blob || (uint8_t*)idx->d_idmer_valid < (uint8_t*)idx->blob || (uint8_t*)idx->d_idmer_valid >= (uint8_t*)idx->blob + idx->blob_bytes) cudaFree(idx->d_idmer_valid);
+        idx->device_bytes -= 1ull << (2 * idx->dev.idmer_len);
+        idx->d_idmer_valid = nullptr;
+    }
+    idx->dev.idmer_valid = nullptr; idx->dev.idmer_len = 0;
+    PBSC_CUDA(cudaMalloc((void**)&idx->d_idmer_valid, n_keys));
+    idmer_valid_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx->dev, idmer_len, n_keys, idx->d_idmer_valid);
+    PBSC_CUDA(cudaGetLastError());
+    PBSC_CUDA(cudaStreamSynchronize(st));
+    idx->dev.idmer_valid = idx->d_idmer_valid;
+    idx->dev.idmer_len = idmer_len;
+    idx->device_bytes += n_keys;
+    PBSC_OCC_TAKE(4, st);
+    return PBSC_OK;
+}
+
 int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBuffers& s, Workspace& w, uint64_t* launches)
 {
     cudaStream_t st = idx->stream;
@@ -793,17 +773,23 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     ThreadEngine E;
     E.no_dp = p->no_dp != 0;
     E.params = p;
+    // PBSC_ROUND_TRACE=1: host wall clock of every stage of the round structure (each ends with a stream synchronisation)
+    const bool rtrace = getenv("PBSC_ROUND_TRACE") != nullptr;
+    auto rt0 = std::chrono::steady_clock::now();
+    auto trace = [&](const char* what, uint64_t items) {
+        if (!rtrace) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pbsc round trace] %-28s %10llu items %9.2f ms (DP so far %.1f ms)\n", what, (unsigned long long)items,
+                std::chrono::duration<double, std::milli>(now - rt0).count(), last_dp_stats().ms);
+        rt0 = now;
+    };
     if (idx->dev.idmer_len != p->idmer_len)
     {
-        const uint64_t n_keys = 1ull << (2 * p->idmer_len);
-        if (idx->d_idmer_valid) { cudaFree(idx->d_idmer_valid); idx->d_idmer_valid = nullptr; }
-        PBSC_CUDA(cudaMalloc((void**)&idx->d_idmer_valid, n_keys));
-        idx->dev.idmer_valid = nullptr;
-        idmer_valid_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx->dev, p->idmer_len, n_keys, idx->d_idmer_valid);
-        PBSC_CUDA(cudaGetLastError());
-        idx->dev.idmer_valid = idx->d_idmer_valid;
-        idx->dev.idmer_len = p->idmer_len;
-        idx->device_bytes += n_keys;
+        // lane_acquire() builds the table before any lane runs; this is the direct-call path of a single-lane index
+        if (idx->primary) { set_error("idmer table of the lane does not match -i %d", p->idmer_len); return PBSC_ERR_INTERNAL; }
+        const int rc = ensure_idmer_table(idx, p->idmer_len);
+        if (rc != PBSC_OK) return rc;
     }
     // ---- task index space: one slot per surviving seed ----
     PBSC_CUDA(E.task_base.get(idx, "tw.task_base", n + 1));
@@ -834,15 +820,11 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     {
         // "live leaves,children per level,history rings,results,label-tree nodes" of the light pass (experiments)
         unsigned a = 0, b2 = 0, c = 0, d = 0, n2 = 0;
-        if (sscanf(e, "%u,%u,%u,%u,%u", &a, &b2, &c, &d, &n2) == 5 && a >= 1 && b2 >= 4 * 1 && c >= a + 1 && c <= 255 && d >= 1 && n2 >= 64)
-        { light_caps = tw::Caps{a, b2, c, d}; t_node_cap = n2; }
+        if (sscanf(e, "%u,%u,%u,%u,%u", &a, &b2, &c, &d, &n2) == 5 && a >= 1 && a <= (unsigned)OLD_CAP && c >= a + 1 && c <= 255 && d >= 1 && n2 >= 64)
+        { (void)b2; light_caps = tw::Caps{a, 4 * a, c, d}; t_node_cap = n2; }   // children per level is always 4 x live leaves (slot = 4 i + base)
     }
     make_ext_params(p, P, w.q_cap, t_node_cap, pending_cap);
     make_ext_params(p, E.Pw, w.q_cap, std::max<uint32_t>(w.node_cap, 1u << 15), pending_cap);
-    {
-        const char* e = getenv("PBSC_HEAVY");
-        E.heavy_engine_warp = e && strcmp(e, "warp") == 0;
-    }
     const uint64_t minSA = p->pb_coverage > 60 ? (uint64_t)((p->pb_coverage / 60) * 3) : 3;
     E.kernel = walk_kernel_for(walk_min_blocks());
     int rc = thread_geometry(idx->device, &E.blocks);
@@ -852,25 +834,37 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     E.heavy = tw::Caps{(uint32_t)OLD_CAP, (uint32_t)NEW_CAP, (uint32_t)RING_SLOTS, (uint32_t)RES_CAP};
     E.stride = tw::thread_scratch_bytes(t_node_cap, E.light);
     PBSC_CUDA(E.scratch.get(idx, "tw.scratch", E.stride * (size_t)E.blocks * TW_BLOCK));
-    if (E.heavy_engine_warp)
-    {
-        E.wstride = warp_scratch_bytes(E.Pw.q_cap, E.Pw.node_cap, E.Pw.merged_cap);
-        E.wblocks = idx->sm_count * 2;
-        PBSC_CUDA(E.wscratch.get(idx, "tw.wscratch", E.wstride * (size_t)E.wblocks * HEAVY_WARPS));
-    }
-    else
     {
         E.hstride = tw::thread_scratch_bytes(E.Pw.node_cap, E.heavy);
-        E.hblocks = std::min(E.blocks, idx->sm_count * 3);   // latency-bound like the light pass, but 280 KB of scratch per lane
-        const char* e = getenv("PBSC_TW_HEAVY_BLOCKS_PER_SM");
-        if (e && atoi(e) > 0) E.hblocks = idx->sm_count * atoi(e);
-        PBSC_CUDA(E.hscratch.get(idx, "tw.hscratch", E.hstride * (size_t)E.hblocks * TW_BLOCK));
+        if (const char* e = getenv("PBSC_TW_HEAVY_OWNERS")) { if (atoi(e) >= 1 && atoi(e) <= 32) E.heavy_owners = atoi(e); }
+        // scratch of the full-capacity passes: hstride bytes (280 KB with the default label-tree size) per OWNER lane.  Never
+        // ask for more than the device has left (a grown node_cap multiplies hstride): fewer owners per warp first, then a
+        // clean PBSC_ERR_LIMIT instead of a CUDA out-of-memory error.  cudaMemGetInfo costs tens of milliseconds, so it is
+        // only asked when the arena has to grow.
+        {
+            const size_t have = idx->arena.count("tw.hscratch") ? idx->arena["tw.hscratch"].cap : 0;
+            auto need = [&]() { return E.hstride * (size_t)E.blocks * (TW_BLOCK / 32) * (size_t)E.heavy_owners; };
+            if (need() > have)
+            {
+                size_t free_b = 0, total_b = 0;
+                PBSC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                const size_t avail = (size_t)((double)(free_b + have) * 0.8);
+                while (need() > avail && E.heavy_owners > 1) E.heavy_owners /= 2;
+                if (need() > avail)
+                {
+                    set_error("walk scratch of %zu bytes per lane (label tree of %u nodes) does not fit the %zu MB left on the device", E.hstride, E.Pw.node_cap, free_b >> 20);
+                    return PBSC_ERR_LIMIT;
+                }
+            }
+        }
+        E.hblocks = E.blocks;
+        PBSC_CUDA(E.hscratch.get(idx, "tw.hscratch", E.hstride * (size_t)E.blocks * (TW_BLOCK / 32) * (size_t)E.heavy_owners));
     }
     PBSC_CUDA(E.spec.get(idx, "tw.spec", n_tasks)); PBSC_CUDA(E.pending.get(idx, "tw.pending", n)); PBSC_CUDA(E.caps.get(idx, "tw.caps", n_tasks + 1)); PBSC_CUDA(E.cap_off.get(idx, "tw.cap_off", n_tasks + 1));
     PBSC_CUDA(E.rec_caps.get(idx, "tw.rec_caps", n_tasks + 1)); PBSC_CUDA(E.rec_off.get(idx, "tw.rec_off", n_tasks + 1));
     E.heavy_cap = std::max<uint64_t>(n_tasks, n) + 1;
     PBSC_CUDA(E.heavy_list.get(idx, "tw.heavy_list", 2 * E.heavy_cap)); PBSC_CUDA(E.n_heavy.get(idx, "tw.n_heavy", 2));
-    E.pool_cap = std::max<uint64_t>(n_tasks, n) * (uint64_t)(w.node_cap >= (1u << 16) ? 2048 : 256) + 65536;
+    E.pool_cap = std::max<uint64_t>(n_tasks, n) * (uint64_t)w.pool_nodes + 65536;
     PBSC_CUDA(E.nodepool.get(idx, "tw.nodepool", E.pool_cap)); PBSC_CUDA(E.pool_used.get(idx, "tw.pool_used", 1));
     PBSC_CUDA(E.states.get(idx, "tw.states", n)); PBSC_CUDA(E.stalled.get(idx, "tw.stalled", n)); PBSC_CUDA(E.n_stalled.get(idx, "tw.n_stalled", 1));
     PBSC_CUDA(cudaMemsetAsync(E.states.p, 0, n * sizeof(ReadState), st));
@@ -912,12 +906,14 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         PBSC_CUDA(cudaMemsetAsync(E.alt.p, 0, n_tasks * sizeof(WalkTask), st));
     }
     else E.alt.p = nullptr;
+    trace("task setup (scans, pools)", n_tasks);
     // ---- round 1: all speculative walks ----
     if (n_tasks)
     {
         rc = launch_walk(idx, P, E, w, b, n_tasks, nullptr, E.spec.p, false, minSA, &nl);
         if (rc != PBSC_OK) return rc;
     }
+    trace("round 1 (speculative walks)", n_tasks);
     // ---- alternatives for the successors of pairs the DP fallback corrected (see make_alt_tasks_kernel) ----
     for (int ar = 0; use_alt && ar < alt_rounds; ar++)
     {
@@ -931,6 +927,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         if (na == 0) break;
         rc = launch_walk(idx, P, E, w, b, na, E.alt_list.p, E.alt.p, false, minSA, &nl, E.recpool.p + E.alt_rec_base);
         if (rc != PBSC_OK) return rc;
+        trace("alternative round", na);
     }
     StitchParams C;
     C.start_kmer = p->start_kmer; C.next_target = p->next_target; C.split = p->split; C.no_dp = p->no_dp;
@@ -950,7 +947,9 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         // the stalled reads' requests sit in pending[read]
         rc = launch_walk(idx, P, E, w, b, ns, E.stalled.p, E.pending.p, true, minSA, &nl);
         if (rc != PBSC_OK) return rc;
+        trace("stitch + re-walk round", ns);
     }
+    trace("last stitch", 0);
     if (launches) *launches += nl;
     {
         // every launch was followed by a stream synchronisation (the stitch loop reads its counter), so the events are complete
@@ -960,6 +959,8 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, E.ev[i], E.ev[i + 1]) == cudaSuccess) { T.walk_ms += ms; T.walk_launches++; }
+            if (getenv("PBSC_ROUND_TRACE") && i / 2 < E.ev_what.size())
+                fprintf(stderr, "[pbsc round trace] walk launch %zu: %s pass, %llu items, %.2f ms\n", i / 2, E.ev_what[i / 2].first, (unsigned long long)E.ev_what[i / 2].second, ms);
         }
     }
     return PBSC_OK;

@@ -107,6 +107,12 @@ void dev_cache_trim(int device)
     cudaSetDevice(cur);
 }
 
+unsigned long long* occ_counts()
+{
+    static unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    return c;
+}
+
 Timing& last_timing()
 {
     static thread_local Timing t;
@@ -481,6 +487,12 @@ static int read_bwt_file(const std::string& path, std::vector<uint8_t>& runs, ui
     if (!in || magic != 0xCACA) { set_error("BWT file is not properly formatted, aborting"); return PBSC_ERR_FORMAT; }   // BWTReaderBinary.cpp:61-65
     in.read((char*)&n_strings, 8); in.read((char*)&n_symbols, 8); in.read((char*)&n_runs, 8); in.read((char*)&flag, 4);
     if (!in) { set_error("truncated header in %s", path.c_str()); return PBSC_ERR_FORMAT; }
+    {
+        // the header is untrusted: a run holds 1..31 symbols, and the runs must fit the file
+        struct stat sb;
+        if (stat(path.c_str(), &sb) != 0 || (uint64_t)sb.st_size < 30 + n_runs || n_runs > n_symbols || n_symbols > 31 * n_runs)
+        { set_error("%s: header (%llu runs, %llu symbols) does not match the file size", path.c_str(), (unsigned long long)n_runs, (unsigned long long)n_symbols); return PBSC_ERR_FORMAT; }
+    }
     runs.resize(n_runs);
     in.read((char*)runs.data(), (std::streamsize)n_runs);
     if ((uint64_t)in.gcount() != n_runs) { set_error("truncated run data in %s", path.c_str()); return PBSC_ERR_FORMAT; }
@@ -502,7 +514,9 @@ int pbsc_index_load(const char* prefix, int device, int require_sai, pbsc_index*
         struct stat st;
         if (stat((p + ".sai").c_str(), &st) != 0) { set_error("cannot open %s.sai", prefix); return PBSC_ERR_IO; }
     }
-    return pbsc_index_create(r0.data(), r0.size(), n0, s0, r1.data(), r1.size(), n1, s1, device, out);
+    rc = pbsc_index_create(r0.data(), r0.size(), n0, s0, r1.data(), r1.size(), n1, s1, device, out);
+    if (rc == PBSC_OK) { (*out)->src_runs[0] = r0.size(); (*out)->src_runs[1] = r1.size(); }
+    return rc;
 }
 
 int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t seed, int device, pbsc_index** out)
@@ -585,7 +599,14 @@ int pbsc_index_build_prefix_table(pbsc_index* idx, int k0)
 {
     if (!idx || k0 < 0 || k0 > 15) { set_error("pbsc_index_build_prefix_table: k0 must be in 0..15"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
-    if (idx->d_prefix) { idx->device_bytes -= (sizeof(PrefixEntry) << (2 * idx->dev.k0)); cudaFree(idx->d_prefix); idx->d_prefix = nullptr; }
+    if (idx->primary) { set_error("pbsc_index_build_prefix_table: call it on the index, not on a lane"); return PBSC_ERR_ARG; }
+    {
+        // no batch may be running while the table is replaced
+        std::unique_lock<std::mutex> lk(idx->run_mu);
+        idx->lane_cv.wait(lk, [&] { return idx->lanes_active == 0; });
+    }
+    auto in_blob = [&](const void* p) { return idx->blob && (const uint8_t*)p >= (const uint8_t*)idx->blob && (const uint8_t*)p < (const uint8_t*)idx->blob + idx->blob_bytes; };
+    if (idx->d_prefix) { idx->device_bytes -= (sizeof(PrefixEntry) << (2 * idx->dev.k0)); if (!in_blob(idx->d_prefix)) cudaFree(idx->d_prefix); idx->d_prefix = nullptr; }
     idx->dev.prefix = nullptr;
     idx->dev.k0 = 0;
     if (k0 == 0) return PBSC_OK;
@@ -618,9 +639,26 @@ void pbsc_index_destroy(pbsc_index* idx)
 {
     if (!idx) return;
     cudaSetDevice(idx->device);
-    for (int w = 0; w < 2; w++) { if (idx->d_blocks[w]) cudaFree(idx->d_blocks[w]); if (idx->d_dollar[w]) cudaFree(idx->d_dollar[w]); if (idx->d_dmask[w]) cudaFree(idx->d_dmask[w]); }
-    if (idx->d_prefix) cudaFree(idx->d_prefix);
-    if (idx->d_idmer_valid) cudaFree(idx->d_idmer_valid);
+    for (pbsc_index* s : idx->shadows)
+    {
+        for (auto& kv : s->arena) if (kv.second.p) cudaFree(kv.second.p);
+        if (s->stream) cudaStreamDestroy(s->stream);
+        if (s->stream2) cudaStreamDestroy(s->stream2);
+        if (s->ev_a) cudaEventDestroy(s->ev_a);
+        if (s->ev_b) cudaEventDestroy(s->ev_b);
+        delete s;
+    }
+    idx->shadows.clear();
+    auto in_blob = [&](const void* p) { return idx->blob && (const uint8_t*)p >= (const uint8_t*)idx->blob && (const uint8_t*)p < (const uint8_t*)idx->blob + idx->blob_bytes; };
+    for (int w = 0; w < 2; w++)
+    {
+        if (idx->d_blocks[w] && !in_blob(idx->d_blocks[w])) cudaFree(idx->d_blocks[w]);
+        if (idx->d_dollar[w] && !in_blob(idx->d_dollar[w])) cudaFree(idx->d_dollar[w]);
+        if (idx->d_dmask[w] && !in_blob(idx->d_dmask[w])) cudaFree(idx->d_dmask[w]);
+    }
+    if (idx->d_prefix && !in_blob(idx->d_prefix)) cudaFree(idx->d_prefix);
+    if (idx->d_idmer_valid && !in_blob(idx->d_idmer_valid)) cudaFree(idx->d_idmer_valid);
+    if (idx->blob) cudaFree(idx->blob);
     for (auto& kv : idx->arena) if (kv.second.p) cudaFree(kv.second.p);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->stream2) cudaStreamDestroy(idx->stream2);
@@ -707,6 +745,14 @@ int pbsc_host_alloc(void** p, size_t bytes)
     return PBSC_OK;
 }
 void pbsc_host_free(void* p) { if (p) cudaFreeHost(p); }
+/* page-lock memory the caller already owns (e.g. a shared-memory mapping several processes write their results into) */
+int pbsc_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) { set_error("pbsc_host_register: null argument"); return PBSC_ERR_ARG; }
+    PBSC_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return PBSC_OK;
+}
+void pbsc_host_unregister(void* p) { if (p && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError(); }
 void pbsc_trim(int device) { dev_cache_trim(device); }
 
 uint64_t pbsc_index_num_symbols(const pbsc_index* idx, int which) { return idx && (which == 0 || which == 1) ? idx->n_symbols[which] : 0; }
@@ -859,6 +905,21 @@ int pbsc_threshold_table_text(const pbsc_params* p, char* buf, size_t cap)
     if (s.size() + 1 > cap) { set_error("pbsc_threshold_table_text: buffer too small"); return PBSC_ERR_LIMIT; }
     memcpy(buf, s.c_str(), s.size() + 1);
     return (int)s.size();
+}
+
+/* measurement build only (-DPBSC_COUNT_OCC, libpbsc_count.so): distinct 32-byte index sectors asked for since the last reset,
+ * per kernel family: out[0] seed phase, out[1] walk setup, out[2] level loop, out[3] DP fallback, out[4] other.
+ * Returns 1 in the measurement build, 0 (and zeros) in the product build. */
+int pbsc_occ_counts(uint64_t* out, int reset)
+{
+    if (!out) return PBSC_ERR_ARG;
+    unsigned long long* c = occ_counts();
+    for (int i = 0; i < 5; i++) { out[i] = c[i]; if (reset) c[i] = 0; }
+#ifdef PBSC_COUNT_OCC
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 int pbsc_last_timing(pbsc_timing* t)

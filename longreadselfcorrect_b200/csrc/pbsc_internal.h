@@ -7,10 +7,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <map>
+#include <mutex>
+#include <condition_variable>
 #include <string>
 #include <vector>
 #include "../../include/pbsc.h"
 #include "fm_table.cuh"
+#include "pbsc_status.h"
 
 struct pbsc_index
 {
@@ -30,6 +33,23 @@ struct pbsc_index
     // capacities a batch had to grow to (label-tree nodes per walk, piece bytes per read base): later batches start there
     uint32_t learned_node_cap = 0;
     float learned_piece_factor = 0;
+    uint32_t learned_pool_nodes = 0;
+    // one batch RUNS at a time per index (the arena below and `stream` are shared); uploads and fetches of other batches
+    // proceed on their own streams meanwhile (pbsc_pipeline.cu)
+    std::mutex run_mu;
+    // geometry of the source files (0 when the index was not loaded from .bwt/.rbwt): checked against PREFIX.fmg
+    uint64_t src_runs[2] = {0, 0};
+    void* blob = nullptr;        // single allocation that holds every table when the index came from a blob (import / .fmg / clone)
+    size_t blob_bytes = 0;
+    // Lanes: up to PBSC_MAX_LANES batches of one index run at the same time, each on its own stream with its own arena, so
+    // that the tail of one batch's rounds (a few long walks, the long alignment pile-ups) overlaps the dense kernels of
+    // another (replaces the worker threads of Concurrency/SequenceProcessFramework.h:91-230).  Lane 0 is the index itself;
+    // the others are shadow objects that borrow its tables (`primary` set, nothing owned but stream + arena).
+    pbsc_index* primary = nullptr;
+    std::vector<pbsc_index*> shadows;
+    std::vector<char> lane_busy;          // [0] = this object, [i] = shadows[i-1]
+    std::condition_variable lane_cv;      // guarded by run_mu
+    int lanes_active = 0;
     // named scratch buffers that survive across batches (grow-only), so that the hot path does not pay
     // cudaMalloc/cudaFree of gigabytes per batch; one batch runs at a time per index
     struct ArenaBuf { void* p = nullptr; size_t cap = 0; };
@@ -100,6 +120,14 @@ struct Timing
     uint64_t dp_thread_rows = 0;      // rows aligned by dp_align_thread_kernel
 };
 Timing& last_timing();
+
+#define PBSC_MAX_LANES 4
+// take a free lane of `primary` (blocks while all are busy); the returned object has the primary's tables and its own
+// stream and arena.  `idmer_len` is the -i of the batch about to run: the idmer validity table is (re)built first, with no
+// other lane running, when it differs from the table's.
+int lane_acquire(pbsc_index* primary, int idmer_len, pbsc_index** lane);
+void lane_release(pbsc_index* primary, pbsc_index* lane);
+int ensure_idmer_table(pbsc_index* idx, int idmer_len);   // pbsc_extend_thread.cu
 
 // 2-bit code of a base; -1 for anything else
 inline int base_code(char b) { switch (b) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; } }

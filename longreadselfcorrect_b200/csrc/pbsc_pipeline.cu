@@ -5,6 +5,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <chrono>
+#include <memory>
+#include <new>
 #include "pbsc_batch.cuh"
 #include "pbsc_dp.cuh"
 
@@ -12,7 +14,7 @@ using namespace pbsc;
 
 struct pbsc_batch
 {
-    pbsc_index* idx = nullptr;
+    pbsc_index* idx = nullptr;            // the index (lane 0); the lane that runs the batch is picked by pbsc_batch_run
     pbsc_params params;
     DeviceBatch b;
     SeedBuffers s;
@@ -25,85 +27,161 @@ struct pbsc_batch
     bool ran = false, fetched = false;
     float h2d_ms = 0, seed_ms = 0, extend_ms = 0, d2h_ms = 0;
     uint64_t launches = 0, walks = 0;
+    // copies of this batch run on its own stream: the upload of batch i+1 and the fetch of batch i-1 overlap the kernels of
+    // batch i, which run on a lane's stream (north_star (4); Concurrency/SequenceProcessFramework.h:91-230)
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_up = nullptr;
+    ~pbsc_batch() { if (ev_up) cudaEventDestroy(ev_up); if (cs) cudaStreamDestroy(cs); }
 };
 
-extern "C" {
-
-int pbsc_batch_upload(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets, uint64_t n_reads, pbsc_batch** out)
+namespace {
+// events that are destroyed on every return path
+struct Events
 {
-    if (!idx || !p || !reads || !offsets || !out) { set_error("pbsc_batch_upload: null argument"); return PBSC_ERR_ARG; }
-    *out = nullptr;
+    std::vector<cudaEvent_t> e;
+    cudaError_t create(int n) { e.assign(n, nullptr); for (auto& x : e) { cudaError_t rc = cudaEventCreate(&x); if (rc != cudaSuccess) return rc; } return cudaSuccess; }
+    ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+    cudaEvent_t operator[](int i) const { return e[i]; }
+};
+struct LaneGuard
+{
+    pbsc_index* primary; pbsc_index* lane;
+    ~LaneGuard() { if (lane) lane_release(primary, lane); }
+};
+// no C++ exception may cross the C ABI (std::bad_alloc from the host-side vectors, mostly)
+template <class F>
+int guarded(const char* who, F f)
+{
+    try { return f(); }
+    catch (const std::bad_alloc&) { set_error("%s: out of host memory", who); return PBSC_ERR_LIMIT; }
+    catch (const std::exception& e) { set_error("%s: %s", who, e.what()); return PBSC_ERR_INTERNAL; }
+    catch (...) { set_error("%s: unknown exception", who); return PBSC_ERR_INTERNAL; }
+}
+}  // namespace
+
+static int batch_upload_impl(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets, uint64_t n_reads, pbsc_batch** out)
+{
     if (!p->no_dp && !use_thread_engine())
     { set_error("the DP/MSA fallback (PacBioSelfCorrectionProcess.cpp:208-245) runs on the thread engine only; unset PBSC_ENGINE=warp or pass --nodp"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
-    pbsc_batch* bt = new pbsc_batch();
+    std::unique_ptr<pbsc_batch> bt(new pbsc_batch());
     bt->idx = idx;
     bt->params = *p;
     bt->h_offsets.assign(offsets, offsets + n_reads + 1);
-    if (idx->learned_node_cap) bt->w.node_cap = idx->learned_node_cap;
-    if (idx->learned_piece_factor > 0) bt->w.piece_factor = idx->learned_piece_factor;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, idx->stream);
-    int rc = upload_reads(idx, reads, offsets, n_reads, bt->b);
-    cudaEventRecord(e1, idx->stream);
-    if (rc == PBSC_OK) rc = alloc_seed_workspace(p, bt->h_offsets, bt->b, bt->s, bt->w, idx->stream);
-    if (rc == PBSC_OK) rc = alloc_extend_workspace(idx, p, bt->h_offsets, bt->b, bt->s, bt->w);
-    if (rc == PBSC_OK) { cudaEventSynchronize(e1); cudaEventElapsedTime(&bt->h2d_ms, e0, e1); }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (rc != PBSC_OK) { delete bt; return rc; }
-    *out = bt;
+    PBSC_CUDA(cudaStreamCreateWithFlags(&bt->cs, cudaStreamNonBlocking));
+    PBSC_CUDA(cudaEventCreateWithFlags(&bt->ev_up, cudaEventDisableTiming));
+    {
+        std::lock_guard<std::mutex> lk(idx->run_mu);
+        if (idx->learned_node_cap) bt->w.node_cap = idx->learned_node_cap;
+        if (idx->learned_piece_factor > 0) bt->w.piece_factor = idx->learned_piece_factor;
+        if (idx->learned_pool_nodes) bt->w.pool_nodes = idx->learned_pool_nodes;
+    }
+    Events ev;
+    PBSC_CUDA(ev.create(2));
+    cudaEventRecord(ev[0], bt->cs);
+    int rc = upload_reads(idx, reads, offsets, n_reads, bt->b, bt->cs);
+    cudaEventRecord(ev[1], bt->cs);
+    if (rc == PBSC_OK) rc = alloc_seed_workspace(p, bt->h_offsets, bt->b, bt->s, bt->w, bt->cs);
+    if (rc == PBSC_OK) rc = alloc_extend_workspace(idx, p, bt->h_offsets, bt->b, bt->s, bt->w, bt->cs);
+    if (rc == PBSC_OK) { cudaEventSynchronize(ev[1]); cudaEventElapsedTime(&bt->h2d_ms, ev[0], ev[1]); PBSC_CUDA(cudaEventRecord(bt->ev_up, bt->cs)); }
+    if (rc != PBSC_OK) return rc;
+    *out = bt.release();
     return PBSC_OK;
 }
 
-int pbsc_batch_run(pbsc_batch* bt, float* ms)
+static int batch_run_impl(pbsc_batch* bt, float* ms)
 {
-    if (!bt) { set_error("pbsc_batch_run: null"); return PBSC_ERR_ARG; }
-    pbsc_index* idx = bt->idx;
-    PBSC_CUDA(cudaSetDevice(idx->device));
+    pbsc_index* primary = bt->idx;
+    PBSC_CUDA(cudaSetDevice(primary->device));
+    LaneGuard g{primary, nullptr};
+    int rc = lane_acquire(primary, bt->params.idmer_len, &g.lane);
+    if (rc != PBSC_OK) return rc;
+    pbsc_index* idx = g.lane;
     cudaStream_t st = idx->stream;
-    cudaEvent_t e[3];
-    for (auto& x : e) PBSC_CUDA(cudaEventCreate(&x));
-    auto done = [&]() { for (auto& x : e) cudaEventDestroy(x); };
-    int rc = PBSC_OK;
+    Events e;
+    PBSC_CUDA(e.create(4));
+    PBSC_CUDA(cudaStreamWaitEvent(st, bt->ev_up, 0));
     bt->launches = 0; bt->walks = 0;
-    last_dp_stats() = DpStats();
+    // capacities other batches of this index had to grow to since this one was uploaded
+    bt->w.node_cap = std::max(bt->w.node_cap, idx->learned_node_cap);
+    bt->w.pool_nodes = std::max(bt->w.pool_nodes, idx->learned_pool_nodes);
+    if (idx->learned_piece_factor > bt->w.piece_factor)
+    {
+        bt->w.piece_factor = idx->learned_piece_factor;
+        rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
+        if (rc != PBSC_OK) return rc;
+    }
+    bool grew = false;
+    float extend_total = 0;
     for (int attempt = 0;; attempt++)
     {
-        cudaEventRecord(e[0], st);
-        rc = run_seed_phase(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);
-        cudaEventRecord(e[1], st);
-        if (rc == PBSC_OK) rc = bt->w.thread_engine ? run_extend_threads(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches)
-                                                    : run_extend_chain(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);
+        last_dp_stats() = DpStats();   // counters of the attempt that succeeds, not a sum over retries
+        bt->launches = 0;
+        if (attempt == 0)
+        {
+            cudaEventRecord(e[0], st);
+            rc = run_seed_phase(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);   // seeds do not depend on the capacities: once
+            cudaEventRecord(e[1], st);
+            if (rc != PBSC_OK) break;
+        }
         cudaEventRecord(e[2], st);
+        rc = bt->w.thread_engine ? run_extend_threads(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches)
+                                 : run_extend_chain(idx, &bt->params, bt->b, bt->s, bt->w, &bt->launches);
+        cudaEventRecord(e[3], st);
         if (rc != PBSC_OK) break;
         cudaError_t ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "hot-path kernels", __FILE__, __LINE__); break; }
+        { float t = 0; cudaEventElapsedTime(&t, e[2], e[3]); extend_total += t; }
         // any read that ran out of scratch or piece capacity? (4 bytes per read)
         const uint64_t n = bt->b.n_reads;
         std::vector<int32_t> status(n);
         if (n) PBSC_CUDA(cudaMemcpy(status.data(), bt->w.status.p, n * 4, cudaMemcpyDeviceToHost));
-        bool overflow = false;
+        uint64_t ovf_pieces = 0, ovf_tree = 0, ovf_pool = 0, ovf_dp = 0, ovf_other = 0;
         for (uint64_t r = 0; r < n && rc == PBSC_OK; r++)
         {
-            if (status[r] == -100) overflow = true;
-            else if (status[r] == -101) { set_error("read %llu: a seed pair is outside this build's limits (walk k-mer > 61 or target shorter than -s)", (unsigned long long)r); rc = PBSC_ERR_LIMIT; }
-            else if (status[r] == PBSC_WALK_NO_PATH) { set_error("Does it really happen?"); rc = PBSC_ERR_INTERNAL; }   // PacBioSelfCorrectionProcess.cpp:125-127
+            switch (status[r])
+            {
+                case PBSC_OVF_PIECES: ovf_pieces++; break;
+                case PBSC_OVF_TREE: ovf_tree++; break;
+                case PBSC_OVF_POOL: ovf_pool++; break;
+                case PBSC_OVF_DP: ovf_dp++; break;
+                case PBSC_WALK_OVERFLOW: ovf_other++; break;
+                case PBSC_WALK_UNSUPPORTED:
+                    set_error("read %llu: a seed pair is outside this build's limits (walk k-mer > 61 or target shorter than -s)", (unsigned long long)r); rc = PBSC_ERR_LIMIT; break;
+                case PBSC_WALK_NO_PATH: set_error("Does it really happen?"); rc = PBSC_ERR_INTERNAL; break;   // PacBioSelfCorrectionProcess.cpp:125-127
+                default: break;
+            }
         }
-        if (rc != PBSC_OK || !overflow) break;
-        if (attempt == 3) { set_error("walk scratch capacity exceeded after %d retries", attempt); rc = PBSC_ERR_LIMIT; break; }
-        // grow the capacities and run the batch again
-        bt->w.piece_factor *= 2.0f;
-        bt->w.node_cap *= 8;
-        idx->learned_node_cap = bt->w.node_cap;
-        idx->learned_piece_factor = bt->w.piece_factor;
-        rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w);
         if (rc != PBSC_OK) break;
+        if (ovf_dp)
+        {
+            // not a capacity: larger walk scratch cannot help
+            set_error("DP fallback: %llu read(s) need an alignment or consensus outside this build's limits (consensus longer than the walk's output slot, "
+                      "or more than 3 x query + 128 inserted columns)", (unsigned long long)ovf_dp);
+            rc = PBSC_ERR_LIMIT; break;
+        }
+        if (!(ovf_pieces || ovf_tree || ovf_pool || ovf_other)) break;
+        if (attempt == 3)
+        {
+            set_error("capacity exceeded after %d retries (piece regions %llu, label trees %llu, label-tree pool %llu, other %llu reads)", attempt,
+                      (unsigned long long)ovf_pieces, (unsigned long long)ovf_tree, (unsigned long long)ovf_pool, (unsigned long long)ovf_other);
+            rc = PBSC_ERR_LIMIT; break;
+        }
+        // grow only what ran out, then run the extend phase again (the seeds stay)
+        grew = true;
+        if (ovf_pieces || ovf_other) bt->w.piece_factor *= 2.0f;
+        if (ovf_tree || ovf_other) bt->w.node_cap *= 8;
+        if (ovf_pool) bt->w.pool_nodes *= 4;
+        if (ovf_pieces || ovf_other)
+        {
+            rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
+            if (rc != PBSC_OK) break;
+        }
     }
     if (rc == PBSC_OK)
     {
         cudaEventElapsedTime(&bt->seed_ms, e[0], e[1]);
-        cudaEventElapsedTime(&bt->extend_ms, e[1], e[2]);
+        bt->extend_ms = extend_total;
         unsigned long long hw = 0;
         cudaMemcpy(&hw, bt->w.counters.p + 1, 8, cudaMemcpyDeviceToHost);
         bt->walks = hw;
@@ -117,17 +195,40 @@ int pbsc_batch_run(pbsc_batch* bt, float* ms)
         const DpStats& D = last_dp_stats();
         T.dp_ms = D.ms; T.dp_jobs = D.jobs; T.dp_rows = D.rows; T.dp_thread_rows = D.thread_rows;
         if (D.bad) { set_error("DP fallback: %llu alignments or consensus buffers outside this build's limits", (unsigned long long)D.bad); rc = PBSC_ERR_LIMIT; }
+        if (grew && rc == PBSC_OK)
+        {
+            // later batches start from what this one needed -- recorded only now that it is known to work
+            std::lock_guard<std::mutex> lk(primary->run_mu);
+            primary->learned_node_cap = std::max(primary->learned_node_cap, bt->w.node_cap);
+            primary->learned_piece_factor = std::max(primary->learned_piece_factor, bt->w.piece_factor);
+            primary->learned_pool_nodes = std::max(primary->learned_pool_nodes, bt->w.pool_nodes);
+        }
     }
-    done();
     return rc;
 }
+
+extern "C" {
+
+int pbsc_batch_upload(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets, uint64_t n_reads, pbsc_batch** out)
+{
+    if (!idx || !p || !reads || !offsets || !out) { set_error("pbsc_batch_upload: null argument"); return PBSC_ERR_ARG; }
+    *out = nullptr;
+    return guarded("pbsc_batch_upload", [&] { return batch_upload_impl(idx, p, reads, offsets, n_reads, out); });
+}
+
+int pbsc_batch_run(pbsc_batch* bt, float* ms)
+{
+    if (!bt) { set_error("pbsc_batch_run: null"); return PBSC_ERR_ARG; }
+    return guarded("pbsc_batch_run", [&] { return batch_run_impl(bt, ms); });
+}
+
+}  // extern "C"
 
 // the small per-read results: counters and piece bounds
 static int fetch_device_results(pbsc_batch* bt)
 {
     if (bt->fetched) return PBSC_OK;
-    pbsc_index* idx = bt->idx;
-    cudaStream_t st = idx->stream;
+    cudaStream_t st = bt->cs;
     const uint64_t n = bt->b.n_reads;
     bt->h_bounds.resize(bt->w.h_bounds_region[n]);
     bt->h_stats.resize(n);
@@ -145,7 +246,7 @@ static int fetch_device_results(pbsc_batch* bt)
     return PBSC_OK;
 }
 
-int pbsc_batch_result_size(pbsc_batch* bt, uint64_t* piece_bytes, uint64_t* n_pieces)
+static int result_size_impl(pbsc_batch* bt, uint64_t* piece_bytes, uint64_t* n_pieces)
 {
     if (!bt || !bt->ran) { set_error("pbsc_batch_result_size: batch has not run"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(bt->idx->device));
@@ -170,18 +271,19 @@ __global__ void pack_pieces_kernel(uint64_t n_reads, const uint8_t* __restrict__
     for (uint64_t x = lane; x < e - a; x += 32) out[a + x] = "ACGT"[src[x] & 3];
 }
 
-int pbsc_batch_fetch(pbsc_batch* bt, char* pieces_out, uint64_t pieces_cap, uint64_t* piece_offsets, uint64_t piece_offsets_cap,
-                     uint64_t* first_piece, pbsc_read_stats* stats)
+static int fetch_impl(pbsc_batch* bt, char* pieces_out, uint64_t pieces_cap, uint64_t* piece_offsets, uint64_t piece_offsets_cap,
+                      uint64_t* first_piece, pbsc_read_stats* stats)
 {
     if (!bt || !bt->ran || !piece_offsets || !first_piece || !stats) { set_error("pbsc_batch_fetch: bad argument or batch has not run"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(bt->idx->device));
-    cudaStream_t st = bt->idx->stream;
-    cudaEvent_t e0, e1;
-    PBSC_CUDA(cudaEventCreate(&e0)); PBSC_CUDA(cudaEventCreate(&e1));
+    cudaStream_t st = bt->cs;
+    Events ev;
+    PBSC_CUDA(ev.create(2));
+    cudaEvent_t e0 = ev[0], e1 = ev[1];
     cudaEventRecord(e0, st);
     uint64_t nb = 0, np = 0;
     bt->fetched = false;
-    int rc = pbsc_batch_result_size(bt, &nb, &np);
+    int rc = result_size_impl(bt, &nb, &np);
     if (rc == PBSC_OK && (np + 1 > piece_offsets_cap || nb > pieces_cap || (!pieces_out && nb)))
     {
         set_error("pbsc_batch_fetch: output needs %llu bytes and %llu piece offsets", (unsigned long long)nb, (unsigned long long)(np + 1));
@@ -219,12 +321,24 @@ int pbsc_batch_fetch(pbsc_batch* bt, char* pieces_out, uint64_t pieces_cap, uint
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&bt->d2h_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     Timing& T = last_timing();
     T.d2h_ms = bt->d2h_ms;
     T.total_ms = bt->h2d_ms + bt->seed_ms + bt->extend_ms + bt->d2h_ms;
     T.kernel_launches = bt->launches + 1;
     return rc;
+}
+
+extern "C" {
+
+int pbsc_batch_result_size(pbsc_batch* bt, uint64_t* piece_bytes, uint64_t* n_pieces)
+{
+    return guarded("pbsc_batch_result_size", [&] { return result_size_impl(bt, piece_bytes, n_pieces); });
+}
+
+int pbsc_batch_fetch(pbsc_batch* bt, char* pieces_out, uint64_t pieces_cap, uint64_t* piece_offsets, uint64_t piece_offsets_cap,
+                     uint64_t* first_piece, pbsc_read_stats* stats)
+{
+    return guarded("pbsc_batch_fetch", [&] { return fetch_impl(bt, pieces_out, pieces_cap, piece_offsets, piece_offsets_cap, first_piece, stats); });
 }
 
 void pbsc_batch_destroy(pbsc_batch* bt)

@@ -441,7 +441,7 @@ seed_hitchhike_kernel(SeedParamsDev P, uint64_t n_reads, pbsc_seed* __restrict__
     outcast_count[r] = n - nsurv;
 }
 
-int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b)
+int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, uint64_t n_reads, DeviceBatch& b, cudaStream_t st)
 {
     const uint64_t n_bases = offsets[n_reads];
     for (uint64_t i = 0; i < n_reads; i++) if (offsets[i + 1] < offsets[i]) { set_error("read offsets must be non-decreasing"); return PBSC_ERR_ARG; }
@@ -451,17 +451,17 @@ int upload_reads(pbsc_index* idx, const char* reads, const uint64_t* offsets, ui
     PBSC_CUDA(ascii.alloc(n_bases));
     PBSC_CUDA(b.codes.alloc(n_bases + 64));
     PBSC_CUDA(b.offsets.alloc(n_reads + 1));
-    PBSC_CUDA(cudaMemcpyAsync(ascii.p, reads, n_bases, cudaMemcpyHostToDevice, idx->stream));
-    PBSC_CUDA(cudaMemcpyAsync(b.offsets.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, idx->stream));
-    PBSC_CUDA(cudaMemsetAsync(b.codes.p + n_bases, 0, 64, idx->stream));
+    PBSC_CUDA(cudaMemcpyAsync(ascii.p, reads, n_bases, cudaMemcpyHostToDevice, st));
+    PBSC_CUDA(cudaMemcpyAsync(b.offsets.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    PBSC_CUDA(cudaMemsetAsync(b.codes.p + n_bases, 0, 64, st));
     DevBuf<unsigned int> bad;
     PBSC_CUDA(bad.alloc(1));
-    PBSC_CUDA(cudaMemsetAsync(bad.p, 0, 4, idx->stream));
-    if (n_bases) ascii_to_codes_kernel<<<(unsigned)((n_bases / 16 + 256) / 256), 256, 0, idx->stream>>>(ascii.p, b.codes.p, n_bases, bad.p);
+    PBSC_CUDA(cudaMemsetAsync(bad.p, 0, 4, st));
+    if (n_bases) ascii_to_codes_kernel<<<(unsigned)((n_bases / 16 + 256) / 256), 256, 0, st>>>(ascii.p, b.codes.p, n_bases, bad.p);
     PBSC_CUDA(cudaGetLastError());
     unsigned int hbad = 0;
-    PBSC_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, idx->stream));
-    PBSC_CUDA(cudaStreamSynchronize(idx->stream));
+    PBSC_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, st));
+    PBSC_CUDA(cudaStreamSynchronize(st));
     if (hbad) { set_error("Error: read contains non-ACGT characters."); return PBSC_ERR_ARG; }   // SeqReader.cpp:118-125
     return PBSC_OK;
 }
@@ -534,6 +534,7 @@ int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBu
         nl += 3;
     }
     PBSC_CUDA(cudaGetLastError());
+    PBSC_OCC_TAKE(0, st);
     if (launches) *launches += nl;
     return PBSC_OK;
 }
@@ -551,7 +552,7 @@ extern "C" int pbsc_seed_batch(pbsc_index* idx, const pbsc_params* p, const char
     DeviceBatch b;
     SeedBuffers s;
     Workspace w;
-    int rc = upload_reads(idx, reads, offsets, n_reads, b);
+    int rc = upload_reads(idx, reads, offsets, n_reads, b, idx->stream);
     if (rc != PBSC_OK) return rc;
     std::vector<uint64_t> h_off(offsets, offsets + n_reads + 1);
     rc = alloc_seed_workspace(p, h_off, b, s, w, idx->stream);

@@ -16,6 +16,7 @@
 
 #include "fm_table.cuh"
 #include "stl_sort_emul.cuh"
+#include "pbsc_status.h"
 
 namespace pbsc {
 
@@ -26,9 +27,6 @@ constexpr int RING_LEN = 100;    // m_localSimilarlykmerSize
 constexpr int RES_CAP = 256;
 constexpr int TERM_CAP = 128;
 constexpr unsigned FULL = 0xffffffffu;
-
-#define PBSC_WALK_OVERFLOW (-100)   // scratch capacity exceeded: the host re-runs the read with larger scratch
-#define PBSC_WALK_UNSUPPORTED (-101)
 
 struct __align__(16) Leaf
 {
@@ -44,7 +42,7 @@ struct __align__(16) Leaf
     uint32_t node;                     // id in the label tree
     uint16_t ring;                     // slot of the 100-deep GlobalErrorRateRecord window
     uint8_t tailLetter, alive;
-    uint32_t pad[1];
+    uint32_t aux;                      // thread engine: accepted bases of a parent / terminal index + 1 of a child (pbsc_walk_thread.cuh)
 };
 static_assert(sizeof(Leaf) == 128, "Leaf must be 128 bytes");
 

@@ -25,16 +25,20 @@
 namespace pbsc {
 namespace tw {
 
-// A pass of the thread engine carries walks of at most `old_cap` live leaves and `new_cap` children per level.  A walk
+// A pass of the thread engine carries walks of at most `old_cap` live leaves and 4 * old_cap children per level.  A walk
 // that outgrows its pass (repeats, ExceedLeaves/ExceedDepth cases: a few percent of the walks, but each one costs 10-100x a
-// light walk and would stall the other 31 lanes of its warp) stops with PBSC_WALK_HEAVY and is re-walked from scratch in the
-// next pass, among walks of its own weight.
-struct Caps { uint32_t old_cap, new_cap, rings, res; };   // per-lane capacities of one pass of the thread engine
+// light walk) stops with PBSC_WALK_HEAVY and is re-walked from scratch in the next pass, among walks of its own weight.
+struct Caps { uint32_t old_cap, new_cap, rings, res; };   // per-lane capacities of one pass of the thread engine (new_cap = 4 * old_cap)
 #define PBSC_WALK_HEAVY (-102)
 
+// Leaves live in two banks of new_cap slots each.  The live leaves of a level are the slots named by a list (`oldList`, n
+// entries); the children of the i-th listed leaf go to slots 4 i + b of the other bank (b = appended base), so any lane can
+// create them without knowing what the other leaves do.  Nothing is ever moved: a level ends by writing the list of the
+// surviving children and swapping the roles of the banks.
 struct TScratch
 {
     Leaf* oldL; Leaf* newL;
+    uint8_t* oldList; uint8_t* newList;
     double* rings;
     uint32_t* nodes;
     WalkResult* res;
@@ -57,6 +61,7 @@ __host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap, Caps c
     b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     b += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
     b += align_up(c.rings, 16);
+    b += 2 * align_up(c.new_cap, 16);
     return align_up(b, 128);
 }
 
@@ -68,7 +73,9 @@ __device__ inline void carve(uint8_t* base, uint32_t node_cap, Caps c, TScratch&
     w.rings = (double*)p; p += sizeof(double) * (size_t)c.rings * RING_LEN;
     w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     w.res = (WalkResult*)p; p += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
-    w.ringStack = p;
+    w.ringStack = p; p += align_up(c.rings, 16);
+    w.oldList = p; p += align_up(c.new_cap, 16);
+    w.newList = p;
     w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.start4 = w.pos4 = nullptr;
 }
 
@@ -128,32 +135,42 @@ struct State
     int status;
 };
 
-__device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ringStack[S.nFree++] = (uint8_t)slot; }
-// released slots first, then slots never used by this walk (slot 0 is the root's)
-__device__ __forceinline__ int ring_take(State& S)
+// What the OTHER lanes of the warp need to know about a lane's walk to work on its leaves: every stage of a level that
+// touches the index or the per-walk tables is pooled over the warp (the leaves of all 32 walks are dealt out one per lane
+// per round), so a walk with 30 live leaves no longer holds 31 lanes for 30 rounds of dependent loads, and the longest
+// walk of a small round (re-walks, the full-capacity pass) advances 32 leaves at a time.  One record per lane in shared
+// memory, rewritten by its owner before every pooled stage.
+struct __align__(16) LaneCtx
 {
-    if (S.nFree) return (int)S.s.ringStack[--S.nFree];
-    return S.nFresh < S.cap.rings ? (int)S.nFresh++ : -1;
+    Leaf* oldL; Leaf* newL;
+    const uint8_t* oldList; const uint8_t* newList;
+    double* rings;
+    const uint16_t* start4; const uint16_t* pos4; const uint8_t* q;
+    const uint64_t* hash; const uint64_t* sF; const uint64_t* sR;
+    const Interval* termF; const Interval* termR;
+    double minErr;
+    uint64_t thr;
+    uint32_t curLen, maxIndel, n5, qlen, hashMask, n9F, n9R, nTerm, level, n, K, dup;
+    // SelectFreqsOfrange / refineSAInterval behind it (pooled): which leaves, the k-mer range, the per-size maxima
+    Leaf* selBank; const uint8_t* selList;
+    uint32_t selLB, selExtra, selK;
+    int selMx[3];
+};
+
+__device__ __forceinline__ void publish(LaneCtx& c, const State& S)
+{
+    c.oldL = S.s.oldL; c.newL = S.s.newL; c.oldList = S.s.oldList; c.newList = S.s.newList; c.rings = S.s.rings;
+    c.start4 = S.s.start4; c.pos4 = S.s.pos4; c.q = S.s.q; c.hash = S.s.hash; c.sF = S.s.sF; c.sR = S.s.sR; c.termF = S.s.termF; c.termR = S.s.termR;
+    c.curLen = (uint32_t)S.curLen; c.maxIndel = (uint32_t)S.maxIndel; c.n5 = S.n5; c.qlen = S.qlen; c.hashMask = S.hashMask; c.n9F = S.n9F; c.n9R = S.n9R;
+    c.nTerm = S.nTerm; c.level = S.level; c.n = S.n; c.K = S.maxOverlap; c.dup = S.dup ? 1u : 0u;
 }
 
-static __device__ __noinline__ void refine(State& S, Leaf* bank, uint32_t cnt, int K)
+// Deal `cnt` items of every lane out over the warp: f(owner lane, item index within the owner) runs once per item, 32 items
+// per round.  Must be called by all 32 lanes converged (cnt may be 0).
+template <class F>
+__device__ __forceinline__ void pool_run(uint32_t cnt, F f)
 {
-    #pragma unroll 1
-    for (uint32_t i = 0; i < cnt; i++)
-    {
-        const uint64_t hi = bank[i].rt_hi, lo = bank[i].rt_lo;
-        Interval f, r;
-        both_strands(*S.idx, [&](int j) { return tail_base(hi, lo, K - 1 - j); }, K, f, r);
-        bank[i].f_lo = f.lo; bank[i].f_hi = f.hi; bank[i].r_lo = r.lo; bank[i].r_hi = r.hi;
-    }
-}
-
-// refineSAInterval for a whole warp at once.  Every lane passes the leaves of its own walk (cnt may be 0); the warp pools
-// them and deals them out one per lane per round, so a walk with eight live leaves no longer holds the other 31 lanes for
-// eight rounds of dependent rank lookups (ncu, profiles/: the per-lane loop ran with 4.5 of 32 threads active and was 42 %
-// of the kernel's instructions).  Must be called by all 32 lanes converged.
-__device__ __forceinline__ void refine_coop(const FmIndexDev& idx, uint32_t cnt, Leaf* bank, int K)
-{
+    __syncwarp();
     const int lane = threadIdx.x & 31;
     uint32_t incl = cnt;
     #pragma unroll
@@ -164,7 +181,6 @@ __device__ __forceinline__ void refine_coop(const FmIndexDev& idx, uint32_t cnt,
     }
     const uint32_t excl = incl - cnt;
     const uint32_t T = __shfl_sync(FULL, incl, 31);
-    const unsigned long long bankBits = (unsigned long long)bank;
     #pragma unroll 1
     for (uint32_t base = 0; base < T; base += 32)
     {
@@ -180,22 +196,51 @@ __device__ __forceinline__ void refine_coop(const FmIndexDev& idx, uint32_t cnt,
             if (e <= x) lo = mid; else hi = mid - 1;
         }
         const uint32_t first = __shfl_sync(FULL, excl, lo);
-        Leaf* ob = (Leaf*)__shfl_sync(FULL, bankBits, lo);
-        const int oK = __shfl_sync(FULL, K, lo);
-        if (has)
-        {
-            Leaf* L = ob + (x - first);
-            const uint64_t rhi = L->rt_hi, rlo = L->rt_lo;
-            Interval f, r;
-            both_strands(idx, [&](int j) { return tail_base(rhi, rlo, oK - 1 - j); }, oK, f, r);
-            L->f_lo = f.lo; L->f_hi = f.hi; L->r_lo = r.lo; L->r_hi = r.hi;
-        }
+        if (has) f(lo, x - first);
     }
     __syncwarp();
 }
 
+__device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ringStack[S.nFree++] = (uint8_t)slot; }
+// released slots first, then slots never used by this walk (slot 0 is the root's)
+__device__ __forceinline__ int ring_take(State& S)
+{
+    if (S.nFree) return (int)S.s.ringStack[--S.nFree];
+    return S.nFresh < S.cap.rings ? (int)S.nFresh++ : -1;
+}
+
+// refineSAInterval (LongReadCorrectByOverlap.cpp:355-369) of the listed leaves of one walk, by its own lane (the rare path
+// behind SelectFreqsOfrange; the refinement that opens every level is pooled, refine_pool)
+static __device__ __noinline__ void refine(State& S, Leaf* bank, const uint8_t* list, uint32_t cnt, int K)
+{
+    #pragma unroll 1
+    for (uint32_t i = 0; i < cnt; i++)
+    {
+        Leaf& L = bank[list[i]];
+        const uint64_t hi = L.rt_hi, lo = L.rt_lo;
+        Interval f, r;
+        both_strands(*S.idx, [&](int j) { return tail_base(hi, lo, K - 1 - j); }, K, f, r);
+        L.f_lo = f.lo; L.f_hi = f.hi; L.r_lo = r.lo; L.r_hi = r.hi;
+    }
+}
+
+// refineSAInterval(maxOverlap) for a whole warp at once: every lane passes the number of leaves of its own walk that start
+// this level by cutting their k-mer back (0 if none)
+__device__ __forceinline__ void refine_pool(const FmIndexDev& idx, const LaneCtx* ctx, uint32_t cnt)
+{
+    pool_run(cnt, [&](int owner, uint32_t i) {
+        const LaneCtx& c = ctx[owner];
+        Leaf* L = c.oldL + c.oldList[i];
+        const uint64_t rhi = L->rt_hi, rlo = L->rt_lo;
+        const int K = (int)c.K;
+        Interval f, r;
+        both_strands(idx, [&](int j) { return tail_base(rhi, rlo, K - 1 - j); }, K, f, r);
+        L->f_lo = f.lo; L->f_hi = f.hi; L->r_lo = r.lo; L->r_hi = r.hi;
+    });
+}
+
 // SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331)
-static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint32_t cnt, uint64_t LB, uint64_t UB)
+static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, const uint8_t* list, uint32_t cnt, uint64_t LB, uint64_t UB)
 {
     const FmIndexDev& idx = *S.idx;
     const int extra = (int)(UB - LB);
@@ -203,7 +248,8 @@ static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint3
     #pragma unroll 1
     for (uint32_t i = 0; i < cnt; i++)
     {
-        const uint64_t hi = bank[i].rt_hi, lo = bank[i].rt_lo;
+        const Leaf& L = bank[list[i]];
+        const uint64_t hi = L.rt_hi, lo = L.rt_lo;
         // Fwdinterval = findInterval(BWT, startkmer): newest base first; Rvcinterval = findInterval(RBWT, complement(startkmer))
         Interval a, b;   // a on BWT, b on RBWT
         int d;
@@ -248,11 +294,11 @@ static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, uint3
 }
 
 // isInsufficientFreqs (LongReadCorrectByOverlap.cpp:334-352)
-__device__ __forceinline__ bool insufficient(const State& S, const Leaf* bank, uint32_t cnt)
+__device__ __forceinline__ bool insufficient(const State& S, const Leaf* bank, const uint8_t* list, uint32_t cnt)
 {
     uint32_t high = 0;
     #pragma unroll 1
-    for (uint32_t j = 0; j < cnt; j++) high += bank[j].kmerFreq > S.P->high_freq_thr;
+    for (uint32_t j = 0; j < cnt; j++) high += bank[list[j]].kmerFreq > S.P->high_freq_thr;
     if (high == 0) return true;
     if (high <= 2 && cnt >= 5) return true;
     if (high <= 1 && cnt >= 3) return true;
@@ -288,90 +334,139 @@ static __device__ __noinline__ uint32_t eval4(const int freq[4], uint64_t totalc
     return mask;
 }
 
-__device__ __forceinline__ uint32_t match5_mask(const State& S, uint32_t tail4);
-
-// attempToExtend + getFMIndexExtensions + updateLeaves (LongReadCorrectByOverlap.cpp:373-488, 667-784)
-static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
+// ismatchedbykmer (LongReadCorrectByOverlap.cpp:787-821) for the four probes of one leaf at once: bit b is set when the
+// query holds, starting within curLen +- maxIndel, the leaf's last four bases followed by base b
+__device__ __forceinline__ uint32_t match5_mask(const LaneCtx& c, uint32_t tail4)
 {
-    const FmIndexDev& idx = *S.idx;
+    const int64_t lo = max((int64_t)c.curLen - (int64_t)c.maxIndel, (int64_t)0);
+    const int64_t hi = min((int64_t)c.curLen + (int64_t)c.maxIndel, (int64_t)c.n5 - 1);
+    uint32_t mask = 0;
+    const uint32_t e1 = c.start4[tail4 + 1];
+    #pragma unroll 1
+    for (uint32_t e = c.start4[tail4]; e < e1; e++)
+    {
+        const int64_t p = c.pos4[e];
+        if (p >= lo && p <= hi) mask |= 1u << c.q[p + 4];
+    }
+    return mask;
+}
+
+// attempToExtend, first part (LongReadCorrectByOverlap.cpp:373-398), by the walk's own lane: drop the leaves whose local error
+// rate is far above the best one.  Only the list changes.
+static __device__ __noinline__ void filter_leaves(State& S, double& minErrOut)
+{
     Leaf* oldL = S.s.oldL;
-    Leaf* newL = S.s.newL;
+    uint8_t* list = S.s.oldList;
     double minErr = 1.0;
     #pragma unroll 1
-    for (uint32_t i = 0; i < S.n; i++) minErr = fmin(minErr, oldL[i].local_err);
-    // drop leaves whose local error rate is far above the best one
+    for (uint32_t i = 0; i < S.n; i++) minErr = fmin(minErr, oldL[list[i]].local_err);
+    uint32_t w = 0;
+    #pragma unroll 1
+    for (uint32_t i = 0; i < S.n; i++)
     {
-        uint32_t w = 0;
-        #pragma unroll 1
-        for (uint32_t i = 0; i < S.n; i++)
-        {
-            const double diff = __dsub_rn(oldL[i].local_err, minErr);
-            const bool drop = (diff > 0.05 && S.curLen > (uint64_t)(RING_LEN / 2)) || (diff > 0.1 && S.curLen > 15);
-            if (drop) { ring_release(S, oldL[i].ring); continue; }
-            if (w != i) leaf_copy(oldL + w, oldL + i);
-            w++;
-        }
-        S.n = w;
+        const Leaf& L = oldL[list[i]];
+        const double diff = __dsub_rn(L.local_err, minErr);
+        const bool drop = (diff > 0.05 && S.curLen > (uint64_t)(RING_LEN / 2)) || (diff > 0.1 && S.curLen > 15);
+        if (drop) { ring_release(S, L.ring); continue; }
+        if (w != i) list[w] = list[i];
+        w++;
     }
+    S.n = w;
+    minErrOut = minErr;
+}
+
+// getFMIndexExtensions + the leaf part of updateLeaves (LongReadCorrectByOverlap.cpp:468-488, 667-784) for ONE leaf, by
+// whichever lane the pool gave it to: the eight one-base probes from four sectors, the acceptance rule, and the accepted
+// children written to slots 4 i + b of the other bank.  The accepted bases are left in the parent's `aux` for its owner,
+// who numbers the children and gives them their history rings (adopt_children).
+__device__ __forceinline__ void probe_leaf(const FmIndexDev& idx, const LaneCtx& c, uint32_t i)
+{
+    Leaf* parent = c.oldL + c.oldList[i];
+    uint64_t fl[4], fh[4], rl[4], rh[4];
+    const uint64_t pf_lo = parent->f_lo, pf_hi = parent->f_hi, pr_lo = parent->r_lo, pr_hi = parent->r_hi;
+    const bool fV = pf_hi > pf_lo, rV = pr_hi > pr_lo;
+    if (fV) { occ4_ool(idx.t[PBSC_RBWT], pf_lo, fl); occ4_ool(idx.t[PBSC_RBWT], pf_hi, fh); }
+    if (rV) { occ4_ool(idx.t[PBSC_BWT], pr_lo, rl); occ4_ool(idx.t[PBSC_BWT], pr_hi, rh); }
+    int freq[4];
+    Interval pf[4], pr[4];
+    uint64_t total = 0;
+    int mx = 0;
+    uint32_t match5 = 0;
+    const uint64_t p_rt_hi = parent->rt_hi;
+    const uint32_t near5 = match5_mask(c, (uint32_t)(p_rt_hi >> 56));
+    #pragma unroll 1
+    for (int b = 0; b < 4; b++)
+    {
+        if (fV) { pf[b].lo = idx.t[PBSC_RBWT].C[b] + fl[b]; pf[b].hi = idx.t[PBSC_RBWT].C[b] + fh[b]; }
+        else { pf[b].lo = pf_lo; pf[b].hi = pf_hi; }
+        if (rV) { pr[b].lo = idx.t[PBSC_BWT].C[3 - b] + rl[3 - b]; pr[b].hi = idx.t[PBSC_BWT].C[3 - b] + rh[3 - b]; }
+        else { pr[b].lo = pr_lo; pr[b].hi = pr_hi; }
+        freq[b] = (int)((int64_t)pf[b].size() + (int64_t)pr[b].size());
+        total += (uint64_t)(int64_t)freq[b];
+        mx = max(mx, freq[b]);
+        if ((pf[b].valid() || pr[b].valid()) && ((near5 >> b) & 1)) match5 |= 1u << b;
+    }
+    const uint32_t p_tailCount = parent->tailCount;
+    uint32_t mask = eval4(freq, total, mx, match5, p_tailCount, c.thr);
+    if (!mask && parent->local_err == c.minErr && c.n > 1) mask = eval4(freq, total, mx, match5, p_tailCount, c.thr - 1);
+    parent->aux = mask;
+    if (!mask) return;
+    const uint32_t p_tailLetter = parent->tailLetter;
+    const uint64_t p_rt_lo = parent->rt_lo;
+    #pragma unroll 1
+    for (int b = 0; b < 4; b++)
+    {
+        if (!((mask >> b) & 1)) continue;
+        Leaf* ch = c.newL + 4 * i + b;
+        leaf_copy(ch, parent);
+        ch->f_lo = pf[b].lo; ch->f_hi = pf[b].hi; ch->r_lo = pr[b].lo; ch->r_hi = pr[b].hi;
+        ch->kmerFreq = freq[b];
+        uint64_t th = p_rt_hi, tl = p_rt_lo;
+        tail_push(th, tl, b);
+        ch->rt_hi = th; ch->rt_lo = tl;
+        if (p_tailLetter == (uint32_t)b) ch->tailCount = p_tailCount + 1; else { ch->tailLetter = (uint8_t)b; ch->tailCount = 1; }
+        ch->alive = 1;
+        ch->aux = 0;
+    }
+}
+
+// The sequential rest of updateLeaves (LongReadCorrectByOverlap.cpp:468-488; SAIOverlapNode3::createChild,
+// FMIndexWalk/SAINode.cpp:166-189), by the walk's own lane: children are numbered in the reference's order (leaves in list
+// order, bases A..T), the first child of a leaf inherits its history ring, the others get a copy.  Returns the number of
+// children and writes their slots to the child list.
+static __device__ __noinline__ uint32_t adopt_children(State& S)
+{
+    Leaf* oldL = S.s.oldL;
+    Leaf* newL = S.s.newL;
+    const uint8_t* list = S.s.oldList;
+    uint8_t* cl = S.s.newList;
     const uint32_t n = S.n;
+    uint32_t total = 0;
+    #pragma unroll 1
+    for (uint32_t i = 0; i < n; i++) total += __popc(oldL[list[i]].aux);
+    if (total == 0) return 0;
+    if (S.nNodes + total > S.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
     uint32_t m = 0;
     #pragma unroll 1
     for (uint32_t i = 0; i < n; i++)
     {
-        const Leaf* parent = oldL + i;
-        // the eight one-base probes from four sectors
-        uint64_t fl[4], fh[4], rl[4], rh[4];
-        const uint64_t pf_lo = parent->f_lo, pf_hi = parent->f_hi, pr_lo = parent->r_lo, pr_hi = parent->r_hi;
-        const bool fV = pf_hi > pf_lo, rV = pr_hi > pr_lo;
-        if (fV) { occ4_ool(idx.t[PBSC_RBWT], pf_lo, fl); occ4_ool(idx.t[PBSC_RBWT], pf_hi, fh); }
-        if (rV) { occ4_ool(idx.t[PBSC_BWT], pr_lo, rl); occ4_ool(idx.t[PBSC_BWT], pr_hi, rh); }
-        int freq[4];
-        Interval pf[4], pr[4];
-        uint64_t total = 0;
-        int mx = 0;
-        uint32_t match5 = 0;
-        const uint64_t p_rt_hi = parent->rt_hi;
-        const uint32_t near5 = match5_mask(S, (uint32_t)(p_rt_hi >> 56));
-        #pragma unroll 1
-        for (int b = 0; b < 4; b++)
-        {
-            if (fV) { pf[b].lo = idx.t[PBSC_RBWT].C[b] + fl[b]; pf[b].hi = idx.t[PBSC_RBWT].C[b] + fh[b]; }
-            else { pf[b].lo = pf_lo; pf[b].hi = pf_hi; }
-            if (rV) { pr[b].lo = idx.t[PBSC_BWT].C[3 - b] + rl[3 - b]; pr[b].hi = idx.t[PBSC_BWT].C[3 - b] + rh[3 - b]; }
-            else { pr[b].lo = pr_lo; pr[b].hi = pr_hi; }
-            freq[b] = (int)((int64_t)pf[b].size() + (int64_t)pr[b].size());
-            total += (uint64_t)(int64_t)freq[b];
-            mx = max(mx, freq[b]);
-            if ((pf[b].valid() || pr[b].valid()) && ((near5 >> b) & 1)) match5 |= 1u << b;
-        }
-        const uint32_t p_tailCount = parent->tailCount;
-        uint32_t mask = eval4(freq, total, mx, match5, p_tailCount, thr);
-        if (!mask && parent->local_err == minErr && n > 1) mask = eval4(freq, total, mx, match5, p_tailCount, thr - 1);
-        if (!mask) continue;
-        const uint32_t cnt = __popc(mask);
-        if (m + cnt > S.cap.new_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
-        if (S.nNodes + cnt > S.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
-        const uint32_t p_node = parent->node, p_ring = parent->ring, p_tailLetter = parent->tailLetter;
+        const Leaf& parent = oldL[list[i]];
+        const uint32_t mask = parent.aux;
+        const uint32_t p_ring = parent.ring;
+        if (!mask) { ring_release(S, p_ring); continue; }   // not extended: nobody inherits its ring
+        const uint32_t p_node = parent.node;
         uint32_t j = 0;
         #pragma unroll 1
         for (int b = 0; b < 4; b++)
         {
             if (!((mask >> b) & 1)) continue;
-            Leaf* c = newL + m;
-            leaf_copy(c, parent);
-            c->f_lo = pf[b].lo; c->f_hi = pf[b].hi; c->r_lo = pr[b].lo; c->r_hi = pr[b].hi;
-            c->kmerFreq = freq[b];
-            uint64_t th = p_rt_hi, tl = parent->rt_lo;
-            tail_push(th, tl, b);
-            c->rt_hi = th; c->rt_lo = tl;
-            if (p_tailLetter == (uint32_t)b) c->tailCount = p_tailCount + 1; else { c->tailLetter = (uint8_t)b; c->tailCount = 1; }
+            Leaf* c = newL + 4 * i + b;
             const uint32_t node = S.nNodes++;
             c->node = node;
             S.s.nodes[node] = (p_node << 2) | (uint32_t)b;
-            c->alive = 1;
             if (j > 0)
             {
-                // createChild copies both error-rate records (FMIndexWalk/SAINode.cpp:166-189)
+                // createChild copies both error-rate records
                 const int slot = ring_take(S);
                 if (slot < 0) { S.status = PBSC_WALK_HEAVY; return 0; }
                 const double* src = S.s.rings + (size_t)p_ring * RING_LEN;
@@ -381,7 +476,7 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
                 for (int x = 0; x < have; x++) dst[x] = src[x];
                 c->ring = (uint16_t)slot;
             }
-            m++;
+            cl[m++] = (uint8_t)(4 * i + b);
             j++;
         }
     }
@@ -389,16 +484,16 @@ static __device__ __noinline__ uint32_t attempt(State& S, uint64_t thr)
 }
 
 // first position of the query whose idmer has `key`, from the hash (no duplicate idmers in this query)
-__device__ __forceinline__ int hash_find(const State& S, uint32_t key)
+__device__ __forceinline__ int hash_find(const LaneCtx& c, uint32_t key)
 {
-    uint32_t h = (key * 2654435761u) & S.hashMask;
+    uint32_t h = (key * 2654435761u) & c.hashMask;
     #pragma unroll 1
     for (;;)
     {
-        const uint64_t e = S.s.hash[h];
+        const uint64_t e = c.hash[h];
         if (e == ~0ull) return -1;
         if ((uint32_t)(e >> 32) == key) return (int)(uint32_t)e;
-        h = (h + 1) & S.hashMask;
+        h = (h + 1) & c.hashMask;
     }
 }
 
@@ -406,128 +501,157 @@ __device__ __forceinline__ int hash_find(const State& S, uint32_t key)
 static __device__ __noinline__ double ddiv_ool(double a, double b) { return __ddiv_rn(a, b); }
 static __device__ __noinline__ uint64_t urem_ool(uint64_t a, uint64_t b) { return a % b; }
 
-// PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664)
-static __device__ __noinline__ void prune(State& S, uint32_t m)
+// PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664) for ONE new leaf, by
+// whichever lane the pool gave it to (c.curLen and c.level are the walk's values after curLen++ and before level++).  A leaf
+// whose local error rate is too high is only marked dead; its owner releases the ring (finish_level).
+__device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const LaneCtx& c, uint32_t j)
 {
-    const ExtParamsDev& P = *S.P;
     const uint64_t seedSize = (uint64_t)P.seed_size;
-    const uint64_t curLen = S.curLen;
+    const uint64_t curLen = c.curLen;
     const uint64_t currSeedIdx = curLen - seedSize;
-    const uint64_t indelOffset = seedSize + S.maxIndel;
+    const uint64_t indelOffset = seedSize + c.maxIndel;
     const uint64_t smallSeedIdx = currSeedIdx <= indelOffset ? 0 : currSeedIdx - indelOffset;
-    const uint64_t largeSeedIdx = (currSeedIdx + indelOffset) >= ((uint64_t)S.qlen - seedSize) ? ((uint64_t)S.qlen - seedSize) : currSeedIdx + indelOffset;
+    const uint64_t largeSeedIdx = (currSeedIdx + indelOffset) >= ((uint64_t)c.qlen - seedSize) ? ((uint64_t)c.qlen - seedSize) : currSeedIdx + indelOffset;
     const uint32_t keyMask = (1u << (2 * P.seed_size)) - 1u;
-    #pragma unroll 1
-    for (uint32_t j = 0; j < m; j++)
+    Leaf& L = c.newL[c.newList[j]];
+    bool found = false;
+    const uint64_t d = curLen - (uint64_t)L.lastOverlapLen;
+    if (d > seedSize || d <= 1)
     {
-        Leaf& L = S.s.newL[j];
-        bool found = false;
-        const uint64_t d = curLen - (uint64_t)L.lastOverlapLen;
-        if (d > seedSize || d <= 1)
+        const uint64_t preSeedIdx = L.lastSeedIdx;
+        const uint64_t seedIdxOffset = (uint64_t)L.lastOverlapLen < curLen - seedSize ? seedSize : curLen - (uint64_t)L.lastOverlapLen;
+        const uint64_t startSeedIdx = max(smallSeedIdx, (uint64_t)L.lastSeedIdx + seedIdxOffset);
+        const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
+        const uint32_t keyF = (uint32_t)(L.rt_hi >> (64 - 2 * P.seed_size));
+        if (!c.dup)
         {
-            const uint64_t preSeedIdx = L.lastSeedIdx;
-            const uint64_t seedIdxOffset = (uint64_t)L.lastOverlapLen < curLen - seedSize ? seedSize : curLen - (uint64_t)L.lastOverlapLen;
-            const uint64_t startSeedIdx = max(smallSeedIdx, (uint64_t)L.lastSeedIdx + seedIdxOffset);
-            const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
-            const uint32_t keyF = (uint32_t)(L.rt_hi >> (64 - 2 * P.seed_size));
-            if (!S.dup)
+            // every idmer of the query is unique: both result lists hold the same single position
+            if (fV || rV)
             {
-                // every idmer of the query is unique: both result lists hold the same single position
-                if (fV || rV)
+                const int p = hash_find(c, keyF);
+                if (p >= 0 && (uint64_t)p >= startSeedIdx && (uint64_t)p <= largeSeedIdx)
                 {
-                    const int p = hash_find(S, keyF);
-                    if (p >= 0 && (uint64_t)p >= startSeedIdx && (uint64_t)p <= largeSeedIdx)
-                    {
-                        if (abs(p - (int)currSeedIdx) < 10000) L.lastSeedIdx = (uint32_t)p;   // minIdxDiff starts at 10000 (:580)
-                        L.lastOverlapLen = (uint32_t)curLen;
-                        found = true;
-                    }
+                    if (abs(p - (int)currSeedIdx) < 10000) L.lastSeedIdx = (uint32_t)p;   // minIdxDiff starts at 10000 (:580)
+                    L.lastOverlapLen = (uint32_t)curLen;
+                    found = true;
                 }
             }
-            else
+        }
+        else
+        {
+            uint32_t nf = 0, nr = 0, gf = 0, gr = 0;
+            if (fV) gf = group_find(c.sF, c.n9F, keyF, nf);
+            if (rV) gr = group_find(c.sR, c.n9R, keyMask - keyF, nr);
+            int minIdxDiff = 10000;
+            const uint32_t lim = max(nf, nr);
+            #pragma unroll 1
+            for (uint32_t i = 0; i < lim; i++)
             {
-                uint32_t nf = 0, nr = 0, gf = 0, gr = 0;
-                if (fV) gf = group_find(S.s.sF, S.n9F, keyF, nf);
-                if (rV) gr = group_find(S.s.sR, S.n9R, keyMask - keyF, nr);
-                int minIdxDiff = 10000;
-                const uint32_t lim = max(nf, nr);
-                #pragma unroll 1
-                for (uint32_t i = 0; i < lim; i++)
+                uint64_t v = 0;
+                bool hit = false;
+                if (i < nf) { v = (uint32_t)c.sF[gf + i]; hit = v >= startSeedIdx && v <= largeSeedIdx; }
+                if (!hit && i < nr) { v = (uint32_t)c.sR[gr + i]; hit = v >= startSeedIdx && v <= largeSeedIdx; }
+                if (hit)
                 {
-                    uint64_t v = 0;
-                    bool hit = false;
-                    if (i < nf) { v = (uint32_t)S.s.sF[gf + i]; hit = v >= startSeedIdx && v <= largeSeedIdx; }
-                    if (!hit && i < nr) { v = (uint32_t)S.s.sR[gr + i]; hit = v >= startSeedIdx && v <= largeSeedIdx; }
-                    if (hit)
-                    {
-                        const int diff = abs((int)v - (int)currSeedIdx);
-                        if (diff < minIdxDiff) { L.lastSeedIdx = (uint32_t)v; minIdxDiff = diff; }
-                        L.lastOverlapLen = (uint32_t)curLen;
-                        found = true;
-                    }
+                    const int diff = abs((int)v - (int)currSeedIdx);
+                    if (diff < minIdxDiff) { L.lastSeedIdx = (uint32_t)v; minIdxDiff = diff; }
+                    L.lastOverlapLen = (uint32_t)curLen;
+                    found = true;
                 }
             }
-            if (found)
-            {
-                L.totalSeeds++;
-                if (currSeedIdx + (uint64_t)(int64_t)L.seedOff - preSeedIdx > seedSize) L.redeem = __dadd_rn(L.redeem, P.redeem_a);
-                L.seedOff = (int)L.lastSeedIdx - (int)currSeedIdx;
-            }
-            else
-            {
-                const uint64_t v = currSeedIdx + (uint64_t)(int64_t)L.seedOff - (uint64_t)L.lastSeedIdx;
-                if (urem_ool(v, seedSize) == 1) { /* numOfErrors++ : never read */ }
-                else if (v > seedSize - 1) L.redeem = __dadd_rn(L.redeem, P.redeem_b);
-            }
         }
-        else L.redeem = __dadd_rn(L.redeem, P.redeem_b);
-        // computeErrorRate
-        double matchedLen = __dsub_rn(__dadd_rn((double)L.totalSeeds, (double)seedSize), 1.0);
-        matchedLen = __dadd_rn(matchedLen, L.redeem);
-        const double totalLen = (double)curLen;
-        double err = ddiv_ool(__dsub_rn(totalLen, matchedLen), totalLen);
-        double* ring = S.s.rings + (size_t)L.ring * RING_LEN;
-        ring[S.level % RING_LEN] = err;
-        L.global_err = err;
-        if (S.level + 1 >= (uint32_t)RING_LEN)
+        if (found)
         {
-            const double old = ring[(S.level + 1) % RING_LEN];
-            err = ddiv_ool(__dsub_rn(__dmul_rn(err, totalLen), __dmul_rn(old, __dsub_rn(totalLen, (double)RING_LEN))), (double)RING_LEN);
+            L.totalSeeds++;
+            if (currSeedIdx + (uint64_t)(int64_t)L.seedOff - preSeedIdx > seedSize) L.redeem = __dadd_rn(L.redeem, P.redeem_a);
+            L.seedOff = (int)L.lastSeedIdx - (int)currSeedIdx;
         }
-        L.local_err = err;
-        if (err > P.walk_error_rate) { L.alive = 0; ring_release(S, L.ring); }
+        else
+        {
+            const uint64_t v = currSeedIdx + (uint64_t)(int64_t)L.seedOff - (uint64_t)L.lastSeedIdx;
+            if (urem_ool(v, seedSize) == 1) { /* numOfErrors++ : never read */ }
+            else if (v > seedSize - 1) L.redeem = __dadd_rn(L.redeem, P.redeem_b);
+        }
     }
+    else L.redeem = __dadd_rn(L.redeem, P.redeem_b);
+    // computeErrorRate
+    double matchedLen = __dsub_rn(__dadd_rn((double)L.totalSeeds, (double)seedSize), 1.0);
+    matchedLen = __dadd_rn(matchedLen, L.redeem);
+    const double totalLen = (double)curLen;
+    double err = ddiv_ool(__dsub_rn(totalLen, matchedLen), totalLen);
+    double* ring = c.rings + (size_t)L.ring * RING_LEN;
+    ring[c.level % RING_LEN] = err;
+    L.global_err = err;
+    if (c.level + 1 >= (uint32_t)RING_LEN)
+    {
+        const double old = ring[(c.level + 1) % RING_LEN];
+        err = ddiv_ool(__dsub_rn(__dmul_rn(err, totalLen), __dmul_rn(old, __dsub_rn(totalLen, (double)RING_LEN))), (double)RING_LEN);
+    }
+    L.local_err = err;
+    if (err > P.walk_error_rate) L.alive = 0;
 }
 
-// isTerminated (LongReadCorrectByOverlap.cpp:825-878)
-static __device__ __noinline__ void terminated(State& S, uint32_t m)
+// isTerminated, the search (LongReadCorrectByOverlap.cpp:825-860) for ONE new leaf: the last terminal interval that holds
+// the leaf's interval on either strand, at or after the one it matched before; left in `aux` as index + 1 (0 = none)
+__device__ __forceinline__ void term_leaf(const LaneCtx& c, uint32_t j)
 {
+    Leaf& L = c.newL[c.newList[j]];
+    if (!L.alive) { L.aux = 0; return; }
+    const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
+    const uint64_t f_lo = L.f_lo, f_hi = L.f_hi, r_lo = L.r_lo, r_hi = L.r_hi;
+    int ilast = -1;
+    #pragma unroll 1
+    for (int i = max(L.res_second, 0); i < (int)c.nTerm; i++)
+    {
+        const Interval tf = c.termF[i], tr = c.termR[i];
+        const bool ft = fV && tf.valid() && f_lo >= tf.lo && f_hi <= tf.hi;
+        const bool rt = rV && tr.valid() && r_lo >= tr.lo && r_hi <= tr.hi;
+        if (ft || rt) ilast = i;
+    }
+    L.aux = (uint32_t)(ilast + 1);
+}
+
+// End of a level, by the walk's own lane: isTerminated's bookkeeping (one result slot per leaf, overwritten while the leaf
+// keeps terminating, LongReadCorrectByOverlap.cpp:861-875), then the surviving children become the next level's leaves: the
+// banks swap roles (no copy; the walk kernel's DRAM traffic is mostly this scratch), the child list loses the dead entries.
+static __device__ __noinline__ void finish_level(State& S, uint32_t m, bool check_term)
+{
+    Leaf* newL = S.s.newL;
+    uint8_t* cl = S.s.newList;
+    if (check_term)
+    {
+        #pragma unroll 1
+        for (uint32_t j = 0; j < m; j++)
+        {
+            Leaf& L = newL[cl[j]];
+            if (!L.alive || L.aux == 0) continue;
+            const int ilast = (int)L.aux - 1;
+            int slot = L.res_first;
+            if (slot == -1)
+            {
+                if (S.nRes >= S.cap.res) { S.status = PBSC_WALK_HEAVY; return; }
+                slot = (int)++S.nRes;
+            }
+            WalkResult r; r.err = L.global_err; r.node = L.node; r.i = ilast; r.depth = (uint32_t)S.curLen; r.pad = 0;
+            S.s.res[slot - 1] = r;
+            L.res_first = slot; L.res_second = ilast;
+        }
+    }
+    uint32_t nn = 0;
     #pragma unroll 1
     for (uint32_t j = 0; j < m; j++)
     {
-        Leaf& L = S.s.newL[j];
-        if (!L.alive) continue;
-        const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
-        int ilast = -1;
-        #pragma unroll 1
-        for (int i = max(L.res_second, 0); i < (int)S.nTerm; i++)
-        {
-            const Interval tf = S.s.termF[i], tr = S.s.termR[i];
-            const bool ft = fV && tf.valid() && L.f_lo >= tf.lo && L.f_hi <= tf.hi;
-            const bool rt = rV && tr.valid() && L.r_lo >= tr.lo && L.r_hi <= tr.hi;
-            if (ft || rt) ilast = i;
-        }
-        if (ilast < 0) continue;
-        int slot = L.res_first;
-        if (slot == -1)
-        {
-            if (S.nRes >= S.cap.res) { S.status = PBSC_WALK_HEAVY; return; }
-            slot = (int)++S.nRes;
-        }
-        WalkResult r; r.err = L.global_err; r.node = L.node; r.i = ilast; r.depth = (uint32_t)S.curLen; r.pad = 0;
-        S.s.res[slot - 1] = r;
-        L.res_first = slot; L.res_second = ilast;
+        const uint8_t slot = cl[j];
+        const Leaf& L = newL[slot];
+        if (!L.alive) { ring_release(S, L.ring); continue; }
+        if (nn != j && nn < S.cap.old_cap) cl[nn] = slot;
+        nn++;
     }
+    { Leaf* t = S.s.oldL; S.s.oldL = S.s.newL; S.s.newL = t; }
+    { uint8_t* t = S.s.oldList; S.s.oldList = S.s.newList; S.s.newList = t; }
+    S.n = nn;
+    // more live leaves than this pass carries, and the reference's loop would go on: hand the walk over
+    if (nn > S.cap.old_cap && nn <= (uint32_t)S.P->max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -699,23 +823,6 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
     *v.hdr = H;
 }
 
-// ismatchedbykmer (LongReadCorrectByOverlap.cpp:787-821) for the four probes of one leaf at once: bit b is set when the
-// query holds, starting within curLen +- maxIndel, the leaf's last four bases followed by base b
-__device__ __forceinline__ uint32_t match5_mask(const State& S, uint32_t tail4)
-{
-    const int64_t lo = max((int64_t)S.curLen - (int64_t)S.maxIndel, (int64_t)0);
-    const int64_t hi = min((int64_t)S.curLen + (int64_t)S.maxIndel, (int64_t)S.n5 - 1);
-    uint32_t mask = 0;
-    const uint32_t e1 = S.s.start4[tail4 + 1];
-    #pragma unroll 1
-    for (uint32_t e = S.s.start4[tail4]; e < e1; e++)
-    {
-        const int64_t p = S.s.pos4[e];
-        if (p >= lo && p <= hi) mask |= 1u << S.s.q[p + 4];
-    }
-    return mask;
-}
-
 // start a walk from its setup record
 __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, const ExtParamsDev& P, const TScratch& lane_scratch, const SetupView& v,
                                            uint32_t node_cap, Caps cap, uint64_t minSA)
@@ -750,8 +857,9 @@ __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, cons
     #pragma unroll 1
     for (int j = (int)k - 1; j >= 0 && q[j] == R.tailLetter; j--) tc++;
     R.tailCount = tc;
-    R.node = 0; R.ring = 0; R.alive = 1; R.pad[0] = 0;
+    R.node = 0; R.ring = 0; R.alive = 1; R.aux = 0;
     S.s.oldL[0] = R;
+    S.s.oldList[0] = 0;
     S.s.nodes[0] = 0;
     S.s.rings[0] = 0.0;
     S.n = 1;
@@ -766,66 +874,124 @@ __device__ __forceinline__ bool walk_continues(const State& S)
     return S.status == 0 && S.n > 0 && S.n <= (uint32_t)S.P->max_leaves && S.curLen <= S.maxLength;
 }
 
-// One step of extendOverlap's loop (:161-197).  extendLeaves' fallbacks (reduce the k-mer, then lower the SA threshold,
-// :249-262) are rare per walk but long; run inline they would stall the other 31 lanes of the warp, so a walk that
-// needs them spends extra steps in phases 1 and 2 while its neighbours keep extending, and every lane runs the same
-// attempt / select / refine code in every step.
-//   phase 0: normal level            attempt(thr)
-//   phase 1: after the k-mer was reduced (select + refine on the old leaves happened at the end of the previous step)
-//   phase 2: last resort             attempt(thr - 1)
-static __device__ __noinline__ void one_level(State& S)
+// SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331) for ONE leaf, by whichever lane the pool gave it to: the
+// frequency of the leaf's last LB .. LB + extra bases, newest base first on BWT and complemented on RBWT; the walk-wide maxima
+// are collected in the owner's record (shared-memory atomics).
+__device__ __forceinline__ void select_leaf(const FmIndexDev& idx, LaneCtx& c, uint32_t i)
+{
+    const Leaf& L = c.selBank[c.selList[i]];
+    const uint64_t hi = L.rt_hi, lo = L.rt_lo;
+    const int LB = (int)c.selLB, extra = (int)c.selExtra;
+    Interval a, b;   // a on BWT, b on RBWT
+    int d;
+    if (idx.prefix != nullptr && LB >= idx.k0)
+    {
+        uint64_t key = 0;
+        #pragma unroll 1
+        for (int j = 0; j < idx.k0; j++) key |= (uint64_t)(3 - tail_base(hi, lo, j)) << (2 * j);
+        Interval f, r;
+        prefix_lookup(idx, key, f, r);
+        a = r; b = f;
+        d = idx.k0;
+    }
+    else
+    {
+        const int ch = tail_base(hi, lo, 0);
+        a = init_interval(idx.t[PBSC_BWT], ch);
+        b = init_interval(idx.t[PBSC_RBWT], 3 - ch);
+        d = 1;
+    }
+    #pragma unroll 1
+    for (; d < LB && (a.valid() || b.valid()); d++)
+    {
+        const int ch = tail_base(hi, lo, d);
+        if (a.valid()) a = update1(idx.t[PBSC_BWT], a, ch);
+        if (b.valid()) b = update1(idx.t[PBSC_RBWT], b, 3 - ch);
+    }
+    atomicMax(&c.selMx[0], (int)((int64_t)a.size() + (int64_t)b.size()));
+    #pragma unroll 1
+    for (int e = 1; e <= extra; e++)
+    {
+        const int ch = tail_base(hi, lo, LB - 1 + e);
+        if (a.valid()) a = update1(idx.t[PBSC_BWT], a, ch);
+        if (b.valid()) b = update1(idx.t[PBSC_RBWT], b, 3 - ch);
+        atomicMax(&c.selMx[e], (int)((int64_t)a.size() + (int64_t)b.size()));
+    }
+}
+
+// refineSAInterval(selK) of one leaf of the selected bank (the refinement that follows SelectFreqsOfrange)
+__device__ __forceinline__ void reselect_leaf(const FmIndexDev& idx, const LaneCtx& c, uint32_t i)
+{
+    Leaf& L = c.selBank[c.selList[i]];
+    const uint64_t hi = L.rt_hi, lo = L.rt_lo;
+    const int K = (int)c.selK;
+    Interval f, r;
+    both_strands(idx, [&](int j) { return tail_base(hi, lo, K - 1 - j); }, K, f, r);
+    L.f_lo = f.lo; L.f_hi = f.hi; L.r_lo = r.lo; L.r_hi = r.hi;
+}
+
+// One step of extendOverlap's loop (:161-197) is spread over stages that the level loop of walk_levels_kernel runs for all 32
+// lanes of a warp together (pooled = the leaves of all lanes dealt out over the warp; own = each lane for its walk):
+//   refine_pool      pooled   refineSAInterval(maxOverlap) that opens extendLeaves (:242-243)
+//   filter_leaves    own      attempToExtend's error-rate filter
+//   probe_leaf       pooled   getFMIndexExtensions + the children's leaf records
+//   adopt_children   own      node numbers, history rings
+//   level_middle     own      extendLeaves' bookkeeping and fallbacks (below)
+//   select_leaf      pooled   SelectFreqsOfrange's searches (only walks whose frequencies are insufficient)
+//   level_select     own      the reduced k-mer size
+//   reselect_leaf    pooled   refineSAInterval to it
+//   prune_leaf       pooled   PrunedBySeedSupport
+//   term_leaf        pooled   isTerminated's interval search
+//   finish_level     own      results, next level's leaf list
+// extendLeaves' fallbacks (reduce the k-mer, then lower the SA threshold, :249-262) are rare per walk but long; run inline
+// they would stall the other lanes of the warp, so a walk that needs them spends extra iterations in phases 1 and 2 while its
+// neighbours keep extending:
+//   phase 0: normal level            probes with thr
+//   phase 1: after the k-mer was reduced (select + refine on the old leaves happened at the end of the previous iteration)
+//   phase 2: last resort             probes with thr - 1
+// Returns true when the level produced children that go on to prune / terminal search / finish_level.
+// `sel` = how many leaves go through SelectFreqsOfrange + refineSAInterval before the level goes on (the owner's record says
+// which); level_select then turns the pooled maxima into the reduced k-mer size.
+static __device__ __noinline__ bool level_middle(State& S, LaneCtx& c, uint32_t m, uint32_t& sel)
 {
     const ExtParamsDev& P = *S.P;
-    // (the refineSAInterval(maxOverlap) that opens extendLeaves, :242-243, already ran warp-wide: needs_refine / refine_coop)
-    const uint32_t m = attempt(S, S.phase == 2 ? S.minSA - 1 : S.minSA);
-    if (S.status) return;
     Leaf* bank = nullptr;
+    const uint8_t* list = nullptr;
     uint32_t cnt = 0;
+    sel = 0;
     if (m > 0)
     {
-        // old leaves are gone: those that were not extended release their ring (children inherited the others)
-        #pragma unroll 1
-        for (uint32_t i = 0; i < S.n; i++)
-        {
-            bool inherited = false;
-            const uint16_t ring = S.s.oldL[i].ring;
-            #pragma unroll 1
-            for (uint32_t j = 0; j < m && !inherited; j++) inherited = S.s.newL[j].ring == ring;
-            if (!inherited) ring_release(S, ring);
-        }
         S.curLen++;
         S.curK++;
         S.phase = 0;
-        if (insufficient(S, S.s.newL, m)) { bank = S.s.newL; cnt = m; }
+        if (insufficient(S, S.s.newL, S.s.newList, m)) { bank = S.s.newL; list = S.s.newList; cnt = m; }
     }
-    else if (S.phase == 0) { bank = S.s.oldL; cnt = S.n; S.phase = 1; }   // level 1: reduce the k-mer size, then retry
-    else if (S.phase == 1) { S.phase = 2; return; }                        // level 2: retry with the lower threshold
-    else { S.n = 0; return; }                                              // newLeaves stays empty: the walk ends
+    else if (S.phase == 0) { bank = S.s.oldL; list = S.s.oldList; cnt = S.n; S.phase = 1; }   // level 1: reduce the k-mer size, then retry
+    else if (S.phase == 1) { S.phase = 2; return false; }                                       // level 2: retry with the lower threshold
+    else { S.n = 0; return false; }                                                             // newLeaves stays empty: the walk ends
     if (cnt)
     {
         const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
-        const uint64_t R = select_freqs(S, bank, cnt, LB, S.curK);
-        refine(S, bank, cnt, (int)R);
-        S.curK = R;
+        c.selBank = bank; c.selList = list; c.selLB = (uint32_t)LB; c.selExtra = (uint32_t)(S.curK - LB);
+        c.selMx[0] = c.selMx[1] = c.selMx[2] = 0;
+        sel = cnt;
     }
-    if (m == 0) return;
-    prune(S, m);
-    S.level++;
-    if (S.curLen >= S.minLength) { terminated(S, m); if (S.status) return; }
-    // the surviving children become the next level's leaves: the banks swap roles (no copy; the walk kernel's DRAM traffic is
-    // mostly this scratch, profiles/r1_walk_levels_cfg2_light_pass.txt), only the leaves behind a pruned one move forward
-    uint32_t nn = 0;
-    #pragma unroll 1
-    for (uint32_t j = 0; j < m; j++)
+    return m > 0;
+}
+
+// the decision of SelectFreqsOfrange (:318-330) from the maxima the pool collected
+__device__ __forceinline__ void level_select(State& S, LaneCtx& c)
+{
+    const uint64_t LB = c.selLB, UB = LB + c.selExtra;
+    uint64_t R = UB;
+    if (c.selMx[0] - S.P->freq_int[LB] < 5) R = LB;
+    else
     {
-        if (!S.s.newL[j].alive) continue;
-        if (nn != j && nn < S.cap.old_cap) leaf_copy(S.s.newL + nn, S.s.newL + j);
-        nn++;
+        #pragma unroll 1
+        for (uint32_t e = 1; e <= c.selExtra; e++) if (c.selMx[e] - S.P->freq_int[LB + e] < 5) { R = LB + e; break; }
     }
-    { Leaf* t = S.s.oldL; S.s.oldL = S.s.newL; S.s.newL = t; }
-    S.n = nn;
-    // more live leaves than this engine carries, and the reference's loop would go on: hand the walk over
-    if (nn > S.cap.old_cap && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
+    c.selK = (uint32_t)R;
+    S.curK = R;
 }
 
 #define PBSC_TASK_MATERIALIZE 2   // walk succeeded; the merged sequence is still to be written from the saved label tree
@@ -847,7 +1013,7 @@ static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t
         const WalkResult r = S.s.res[bi];
         const uint32_t nn = (S.nNodes + 3u) & ~3u;
         const uint64_t off = atomicAdd(pool_used, (unsigned long long)nn);
-        if (off + nn > pool_cap) return PBSC_WALK_OVERFLOW;
+        if (off + nn > pool_cap) return PBSC_OVF_POOL;
         const uint4* src = reinterpret_cast<const uint4*>(S.s.nodes);
         uint4* dst = reinterpret_cast<uint4*>(nodepool + off);
         #pragma unroll 4

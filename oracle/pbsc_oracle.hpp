@@ -1168,6 +1168,9 @@ struct ReadResult
     SeedVector seeds, outcastSeeds;
     bool outcastWritten = false, seedWritten = false;
     uint64_t occSeed = 0, occExtend = 0;   // rank queries issued by each phase (roofline numerator)
+    // occExtend split: the LongReadSelfCorrectByOverlap constructor (terminal intervals, query idmer and 5-mer interval trees, root
+    // intervals; LongReadCorrectByOverlap.cpp:17-152) and the level loop (extendOverlap, :155-211)
+    uint64_t occExtendSetup = 0, occExtendWalk = 0;
     uint64_t dpCells = 0, dpRows = 0, dpAttempts = 0, occDP = 0;   // banded-DP cells / rows kept / fallbacks tried / LF steps of the DP fallback
     std::vector<std::pair<int,int>> dpFailLog;                     // extend/<id>.dp rows
     std::vector<PairRecord> pairs;
@@ -1208,8 +1211,12 @@ struct Corrector
         rec.srcStart = source.seedStartPos; rec.trgStart = target.seedStartPos; rec.extendKmerSize = extendKmerSize;
         rec.dis = interval; rec.fromRtoU = isFromRtoU; rec.src = src; rec.path = path; rec.trg = trg;
         std::string mergedSeq;
+        const uint64_t occCtor0 = OccCounter::n();
         FMExtend tree(src, path, trg, interval, extendKmerSize, extendKmerSize + 2, P, min_SA_threshold);
+        const uint64_t occCtor1 = OccCounter::n();
         isFMExtensionSuccess = tree.extendOverlap(mergedSeq);
+        result.occExtendSetup += occCtor1 - occCtor0;
+        result.occExtendWalk += OccCounter::n() - occCtor1;
         rec.status = isFMExtensionSuccess;
         if (isFMExtensionSuccess < 0) { result.pairs.push_back(rec); return isFMExtensionSuccess; }
         rec.out = mergedSeq;

@@ -236,15 +236,16 @@ int main(int argc, char** argv)
                   << "ExceedLeaveNum: " << exceedLeaveNum << ", ratio: " << (float)(exceedLeaveNum * 100) / (DPNum + OutcastNum) << "%\n"
                   << "DisBetweenSeeds: " << seedDis / totalWalkNum << "\n";
     }
-    uint64_t occSeed = 0, occExtend = 0, walkAttempts = 0, dpCells = 0, dpRows = 0, dpAttempts = 0, occDP = 0;
+    uint64_t occSeed = 0, occExtend = 0, occSetup = 0, occWalk = 0, walkAttempts = 0, dpCells = 0, dpRows = 0, dpAttempts = 0, occDP = 0;
     for (const auto& r : results)
     {
-        occSeed += r.occSeed; occExtend += r.occExtend; walkAttempts += r.pairs.size();
+        occSeed += r.occSeed; occExtend += r.occExtend; occSetup += r.occExtendSetup; occWalk += r.occExtendWalk; walkAttempts += r.pairs.size();
         dpCells += r.dpCells; dpRows += r.dpRows; dpAttempts += r.dpAttempts; occDP += r.occDP;
     }
     fprintf(stderr, "[pbsc_oracle] dp fallbacks %llu, rows kept %llu, band cells %llu, LF steps %llu\n", (unsigned long long)dpAttempts,
             (unsigned long long)dpRows, (unsigned long long)dpCells, (unsigned long long)occDP);
-    fprintf(stderr, "[pbsc_oracle] %zu reads, %.3f s, threads %d, rank queries %llu (seed %llu, extend %llu), walks %llu\n", reads.size(), secs, threads,
-            (unsigned long long)occTotal, (unsigned long long)occSeed, (unsigned long long)occExtend, (unsigned long long)walkAttempts);
+    fprintf(stderr, "[pbsc_oracle] %zu reads, %.3f s, threads %d, rank queries %llu (seed %llu, extend %llu: setup %llu, walk loop %llu), walks %llu\n", reads.size(), secs,
+            threads, (unsigned long long)occTotal, (unsigned long long)occSeed, (unsigned long long)occExtend, (unsigned long long)occSetup, (unsigned long long)occWalk,
+            (unsigned long long)walkAttempts);
     return 0;
 }

@@ -270,6 +270,9 @@ def test_repeat_rich_dataset_vs_oracle(api, oracle_bin, tmp_path, opts, kw, engi
 # ---- DP / multiple-alignment fallback (default options, correctByMSAlignment) ------------------------------------------
 
 def _select_dp_kernel(monkeypatch, dp_kernel):
+    # the multiple alignment has two kernels as well: thread per pile-up (default for small ones) and warp per pile-up;
+    # "thread" runs forces every pile-up through the former, the others through the latter
+    monkeypatch.setenv("PBSC_MSA_WARP_MIN", "-1" if dp_kernel == "thread" else "0")
     if dp_kernel == "thread":
         monkeypatch.setenv("PBSC_DP_THREAD", "1")
         monkeypatch.setenv("PBSC_DPT_MIN_ROWS", "1")

@@ -1,0 +1,184 @@
+"""GPU tests of the persisted / relocatable flat index (PREFIX.fmg, clone, blob export/import) and of the lanes (several
+batches of one index in flight on separate streams): every variant must give the reference's bytes (tests/golden, written
+by the unmodified reference binary)."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import read_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from longreadselfcorrect_b200 import api as a
+    assert a.device_count() > 0, "no CUDA device: the hot path has no CPU fallback"
+    return a
+
+
+@pytest.fixture(scope="module")
+def tiny_reads(golden):
+    return read_fasta(os.path.join(golden, "tiny.reads.fa"))
+
+
+def _records(api, out, poff, first, stats, reads):
+    pieces = api.Index.pieces_as_strings(out, poff, first)
+    correct, discard = [], []
+    for (rid, seq), pc, st in zip(reads, pieces, stats):
+        if st["merge"]:
+            correct += [f">{rid}\n{s}\n" for s in pc]
+        else:
+            discard.append(f">{rid}\n{seq}\n")
+    return "".join(correct), "".join(discard)
+
+
+def _check_against_reference(api, idx, reads, golden):
+    p = api.Params.make(coverage=30, genome=5)
+    out, poff, first, stats = idx.correct_reads(p, [s for _, s in reads])
+    c, d = _records(api, out, poff, first, stats, reads)
+    assert c == open(os.path.join(golden, "tiny.dp.correct.fa")).read()
+    assert d == open(os.path.join(golden, "tiny.dp.discard.fa")).read()
+
+
+def _intervals(api, idx, golden):
+    qs = [l.strip() for l in open(os.path.join(golden, "tiny.fm_queries.txt")) if l.strip()][:400]
+    return [idx.find_interval(w, qs)[:2] for w in (api.PBSC_BWT, api.PBSC_RBWT)]
+
+
+def test_fmg_roundtrip_and_open(api, tiny_reads, golden, tmp_path):
+    """save -> load_fmg gives the same tables (symbols, intervals, corrected bytes); pbsc_index_open prefers a matching
+    PREFIX.fmg, rebuilds when the prefix-table length differs and rejects damaged files."""
+    import shutil
+    for ext in ("bwt", "rbwt", "sai"):
+        shutil.copy(os.path.join(golden, f"tiny.{ext}"), tmp_path / f"t.{ext}")
+    prefix = str(tmp_path / "t")
+    idx, used = api.Index.open(prefix, k0=11, write_fmg=True)
+    assert not used and os.path.exists(prefix + ".fmg")
+    want_iv = _intervals(api, idx, golden)
+    n = idx.num_symbols(api.PBSC_BWT)
+    want_sym = idx.symbols(api.PBSC_BWT, 0, n)
+    idx.close()
+    idx2, used = api.Index.open(prefix, k0=11, write_fmg=False)
+    assert used, "a matching PREFIX.fmg must be used"
+    assert idx2.symbols(api.PBSC_BWT, 0, n) == want_sym
+    for (lo, hi), (lo2, hi2) in zip(want_iv, _intervals(api, idx2, golden)):
+        assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
+    _check_against_reference(api, idx2, tiny_reads, golden)
+    # replacing the prefix table of a blob-backed index works and keeps results
+    idx2.build_prefix_table(9)
+    _check_against_reference(api, idx2, tiny_reads, golden)
+    idx2.close()
+    # another k0: the file does not match, the run-length files are used
+    idx3, used = api.Index.open(prefix, k0=10, write_fmg=False)
+    assert not used
+    idx3.close()
+    # damage: flip a header byte -> checksum fails -> falls back to the .bwt files; a direct load reports the format error
+    raw = bytearray(open(prefix + ".fmg", "rb").read())
+    raw[40] ^= 0xFF
+    open(prefix + ".fmg", "wb").write(raw)
+    with pytest.raises(api.PbscError):
+        api.Index.load_fmg(prefix + ".fmg")
+    idx4, used = api.Index.open(prefix, k0=11, write_fmg=False)
+    assert not used
+    idx4.close()
+    # truncated file
+    open(prefix + ".fmg", "wb").write(bytes(raw[: len(raw) // 2]))
+    with pytest.raises(api.PbscError):
+        api.Index.load_fmg(prefix + ".fmg")
+
+
+def test_truncated_bwt_is_a_format_error_not_a_crash(api, golden, tmp_path):
+    raw = open(os.path.join(golden, "tiny.bwt"), "rb").read()
+    for ext in ("rbwt", "sai"):
+        open(tmp_path / f"t.{ext}", "wb").write(open(os.path.join(golden, f"tiny.{ext}"), "rb").read())
+    open(tmp_path / "t.bwt", "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(api.PbscError) as e:
+        api.Index.load(str(tmp_path / "t"))
+    assert e.value.code == -3
+    # a header that promises an absurd number of runs must not be trusted with an allocation
+    bad = bytearray(raw)
+    bad[18:26] = (1 << 60).to_bytes(8, "little")
+    open(tmp_path / "t.bwt", "wb").write(bad)
+    with pytest.raises(api.PbscError) as e:
+        api.Index.load(str(tmp_path / "t"))
+    assert e.value.code == -3
+
+
+def test_clone_and_blob_import(api, tiny_reads, golden):
+    """pbsc_index_clone (peer copies; here onto the same GPU, and onto GPU 1 when the box has one) and export/import of
+    the blob through a caller-owned device buffer (what bench.py broadcasts with NCCL)."""
+    import torch
+    idx = api.Index.load(os.path.join(golden, "tiny"))
+    idx.build_prefix_table(10)
+    want_iv = _intervals(api, idx, golden)
+    targets = [0] + ([1] if api.device_count() > 1 else [])
+    for dev in targets:
+        c = idx.clone(dev)
+        for (lo, hi), (lo2, hi2) in zip(want_iv, _intervals(api, c, golden)):
+            assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
+        _check_against_reference(api, c, tiny_reads, golden)
+        c.close()
+    nb = idx.blob_size()
+    buf = torch.empty(nb, dtype=torch.uint8, device="cuda:0")
+    idx.export_blob(buf.data_ptr(), nb)
+    torch.cuda.synchronize()
+    imp = api.Index.import_blob(buf.data_ptr(), nb, 0, 0)
+    del buf
+    _check_against_reference(api, imp, tiny_reads, golden)
+    host = torch.empty(nb, dtype=torch.uint8)
+    tmp = torch.empty(nb, dtype=torch.uint8, device="cuda:0")
+    idx.export_blob(tmp.data_ptr(), nb)
+    host.copy_(tmp)
+    imp2 = api.Index.import_blob(host.data_ptr(), nb, -1, 0)
+    _check_against_reference(api, imp2, tiny_reads, golden)
+    imp.close(); imp2.close(); idx.close()
+
+
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_lanes_concurrent_batches_byte_identical(api, tiny_reads, golden, lanes):
+    """Batches of one index run at the same time on separate streams and arenas, driven by host threads (the stream pipeline
+    that replaces SequenceProcessFramework's worker threads); pieces concatenated in input order equal the reference's."""
+    idx = api.Index.load(os.path.join(golden, "tiny"))
+    idx.build_prefix_table(12)
+    idx.set_lanes(lanes)
+    assert idx.lanes() == lanes
+    p = api.Params.make(coverage=30, genome=5)
+    parts = 6
+    bounds = [len(tiny_reads) * i // parts for i in range(parts + 1)]
+    results = [None] * parts
+    errors = []
+
+    def work(i):
+        try:
+            sub = tiny_reads[bounds[i]:bounds[i + 1]]
+            b = api.Batch(idx, p, reads=[s for _, s in sub])
+            b.run()
+            results[i] = (sub, b.fetch())
+            b.close()
+        except Exception as e:   # surfaces in the main thread
+            errors.append(e)
+
+    for rep in range(2):
+        th = [threading.Thread(target=work, args=(i,)) for i in range(parts)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors
+        c, d = "", ""
+        for sub, (out, poff, first, stats) in results:
+            cc, dd = _records(api, out, poff, first, stats, sub)
+            c += cc
+            d += dd
+        assert c == open(os.path.join(golden, "tiny.dp.correct.fa")).read()
+        assert d == open(os.path.join(golden, "tiny.dp.discard.fa")).read()
+    # a different -i on a multi-lane index rebuilds the shared idmer table with no batch running
+    p7 = api.Params.make(coverage=30, genome=5, idmer_len=7)
+    out, poff, first, stats = idx.correct_reads(p7, [s for _, s in tiny_reads[:20]])
+    idx.set_lanes(1)
+    out1, poff1, first1, stats1 = idx.correct_reads(p7, [s for _, s in tiny_reads[:20]])
+    assert out[: int(poff[int(first[-1])])].tobytes() == out1[: int(poff1[int(first1[-1])])].tobytes()
+    idx.close()

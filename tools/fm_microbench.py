@@ -49,7 +49,16 @@ def main():
     ap.add_argument("--k0", type=int, default=13)
     ap.add_argument("--cpu-symbols", type=int, default=1 << 28)
     ap.add_argument("--cpu-queries", type=int, default=4_000_000)
+    ap.add_argument("--ks", default="17,19,21,23,25,27,29,31", help="k-mer lengths to run")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--json", action="store_true", help="one summary JSON object on the last line (what bench.py embeds as sub_results.fm_microbench); "
+                                                        "skips the CPU leg")
     args = ap.parse_args()
+    torch.cuda.set_device(args.device)
+    summary = {"metric": "FM k-mer backward-search queries/s", "bwt_symbols": args.symbols, "queries_per_k": args.queries, "strings": args.strings,
+               "what": "BASELINE.json configs[4]: uniform random k-mers against a synthetic i.i.d. BWT resident in HBM, CUDA events around "
+                       "findinterval_packed_kernel; algorithmic bytes = executed updateInterval steps x 2 rank queries x 32 B; issued sectors = "
+                       "with the prefix table one 32-byte entry replaces the first k0 - 1 steps", "results": []}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -57,11 +66,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t = time.time()
-    idx = api.Index.synthetic(args.symbols, args.strings, 5)
+    idx = api.Index.synthetic(args.symbols, args.strings, 5, device=args.device)
     print(f"[fm] synthetic BWT {args.symbols} symbols x 2 strands on device in {time.time() - t:.1f}s, {idx.device_bytes() / 1e9:.2f} GB", file=sys.stderr)
     g = torch.Generator(device="cuda")
     g.manual_seed(105)
-    for k in (17, 19, 21, 23, 25, 27, 29, 31):
+    for k in [int(x) for x in args.ks.split(",")]:
         kmers = torch.randint(0, 1 << 62, (args.queries,), generator=g, device="cuda", dtype=torch.int64) & ((1 << (2 * k)) - 1)
         ref = None
         for k0 in (0, args.k0):
@@ -75,13 +84,31 @@ def main():
                 # same intervals wherever the k-mer occurs; empty intervals stay empty
                 assert bool(torch.equal(lo[valid], ref[0][valid])) and bool(torch.equal(hi[valid], ref[1][valid])) and bool((lo[~valid] > hi[~valid]).all())
             alg_bytes = steps * 64.0
-            print(json.dumps({"metric": "FM k-mer backward-search queries/s", "k": k, "prefix_k0": k0, "queries": args.queries,
-                              "bwt_symbols": args.symbols, "ms": ms, "value": args.queries / (ms / 1e3), "unit": "queries/s",
-                              "update_steps": steps, "steps_per_query": steps / args.queries,
-                              "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                           "frac": alg_bytes / (ms / 1e3) / 1e9 / peak}}), flush=True)
+            # sectors the kernel asks for: every executed step reads the sector(s) of its two bounds; with the table the first
+            # k0 - 1 steps of every query are one 32-byte entry instead (executed steps beyond them are unchanged)
+            issued = float(2 * steps) if k0 == 0 else float(args.queries + 2 * int((st.to(torch.int64) - (k0 - 1)).clamp_(min=0).sum()))
+            rec = {"metric": "FM k-mer backward-search queries/s", "k": k, "prefix_k0": k0, "queries": args.queries,
+                   "bwt_symbols": args.symbols, "ms": ms, "value": args.queries / (ms / 1e3), "unit": "queries/s",
+                   "update_steps": steps, "steps_per_query": steps / args.queries,
+                   "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": alg_bytes / (ms / 1e3) / 1e9 / peak, "issued_sectors": issued, "issued_GBs": issued * 32.0 / (ms / 1e3) / 1e9}}
+            summary["results"].append({"k": k, "prefix_k0": k0, "Gq_per_s": rec["value"] / 1e9, "ms": ms, "steps_per_query": rec["steps_per_query"],
+                                       "algorithmic_GBs": rec["roofline"]["achieved"], "frac_of_streaming_peak": rec["roofline"]["frac"],
+                                       "issued_GBs": rec["roofline"]["issued_GBs"]})
+            if not args.json:
+                print(json.dumps(rec), flush=True)
         del kmers
     idx.close()
+    if args.json:
+        try:
+            sp = api.random_sector_peak(args.symbols // 2, args.device)
+            summary["random_sector_peak_GBs"] = sp
+            for r in summary["results"]:
+                r["issued_frac_of_random_sector_peak"] = r["issued_GBs"] / sp
+        except Exception:
+            pass
+        print(json.dumps(summary), flush=True)
+        return
     # ---- reference CPU baseline on a smaller synthetic BWT in the reference's own file format ----
     fm_dump = os.path.join(ROOT, "oracle", "_ref", "fm_dump")
     if os.path.exists(fm_dump) and args.cpu_symbols > 0:
