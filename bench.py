@@ -371,10 +371,9 @@ def ours(args, wl, metric):
     log(f"rank {rank}: reads [{b_}, {e_}) = {shard.bases / 1e6:.1f} Mbp in {nbt} batch(es)")
 
     # ---- value: reads resident on the device (batches uploaded before the timed region when they all fit), kernels only ----
-    free_b, _tot = torch.cuda.mem_get_info()
-    # workspace of a batch: ~130 bytes per read base (seed features, candidates, piece regions); the arenas of the lanes on top
-    resident_ok = shard.bases * 130 + args.lanes * 40e9 < free_b * 0.85
-    resident = [api.Batch(idx, params, packed=(a, o)) for (_f, a, o) in shard.batches] if resident_ok else None
+    # a batch that is not running holds only its reads (one byte per base) and, after a run, its results: all of them stay resident
+    resident_ok = True
+    resident = [api.Batch(idx, params, packed=(a, o)) for (_f, a, o) in shard.batches]
     tm_lock = threading.Lock()
 
     def run_step():
@@ -775,13 +774,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--k0", type=int, default=13, help="short-prefix table length (0 = off)")
-    ap.add_argument("--lanes", type=int, default=2, help="batches of one GPU in flight at once (streams + arenas)")
+    ap.add_argument("--lanes", type=int, default=1, help="batches of one GPU in flight at once (streams + arenas); 1 with batches as large as memory allows measured best")
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="Mbp of reads for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the config 2 / --nodp / FM microbench sub-results")
     ap.add_argument("--no-cli", dest="cli", action="store_false", help="skip the e2e_cli leg (the pbcorrect binary)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--batch-mbp", type=float, default=160.0, help="largest batch of reads of one lane (Mbp)")
+    ap.add_argument("--batch-mbp", type=float, default=256.0, help="largest batch of reads of one lane (Mbp)")
     ap.add_argument("--nodp", action="store_true", help="disable the DP/MSA fallback on both arms (seeds + FM extension only)")
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="process-group backend for N > 1 (gloo: tests on a one-GPU box)")
     args = ap.parse_args()

@@ -44,9 +44,9 @@ static const char* CORRECT_USAGE_MESSAGE =
     "      -o, --output=DIR                 Output results in the directory\n"
     "      -b, --barcode=FILE               Barcode of raw reads\n"
     "      --gpus=N                         Number of GPUs to use (default: all visible)\n"
-    "      --batch-mbp=N                    Read bases per GPU batch, in Mbp (default: 160)\n"
+    "      --batch-mbp=N                    Read bases per GPU batch, in Mbp (default: 256)\n"
     "      --prefix-k=N                     Length of the short-prefix interval table, 0 = off (default: 13)\n"
-    "      --lanes=N                        Batches in flight per GPU, 1..4 (default: 2)\n"
+    "      --lanes=N                        Batches in flight per GPU, 1..4 (default: 1)\n"
     "      --write-fmg                      Leave PREFIX.fmg (the flat index as it sits in GPU memory) for later runs;\n"
     "                                       a PREFIX.fmg that matches PREFIX.bwt/.rbwt is always used when present\n"
     "\nPacBio correction parameters:\n"
@@ -75,9 +75,9 @@ static int thread = 1;
 static std::string prefix, directory, barcode, readsFile;
 static pbsc_params params;
 static bool DebugSeed = false, OnlySeed = false;
-static int gpus = 0, prefix_k = 13, lanes = 2;
+static int gpus = 0, prefix_k = 13, lanes = 1;
 static bool write_fmg = false;
-static double batch_mbp = 160;
+static double batch_mbp = 256;
 static int verbose = 0;
 }
 

@@ -268,11 +268,12 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
         {
             if (ended)
             {
-                int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap);
+                uint32_t mlen = 0;
+                int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap, last_pass != 0, outpool + tk->out_off, tk->out_cap, &mlen);
                 // the last pass carries everything the reference's loop can hold (-l leaves, 4 children each); only the
                 // label tree and the result list are bounded, and running out of those is reported, not hidden
                 if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_OVF_TREE;
-                tk->out_len = 0;
+                tk->out_len = st == 1 ? mlen : 0;
                 tk->status = st;
                 if (st == PBSC_WALK_HEAVY) heavy_list[atomicAdd(n_heavy, 1u)] = (uint32_t)(tk - tasks);
                 ended = false;
@@ -617,7 +618,7 @@ struct ThreadEngine
     tw::Caps light, heavy;
     size_t stride = 0, hstride = 0;
     int blocks = 0, hblocks = 0;
-    int heavy_owners = 8;   // most lanes of a warp that own a walk in a full-capacity pass (PBSC_TW_HEAVY_OWNERS)
+    int heavy_owners = 16;  // most lanes of a warp that own a walk in a full-capacity pass (PBSC_TW_HEAVY_OWNERS)
     bool no_dp = true;
     const pbsc_params* params = nullptr;
     WalkKernel kernel = nullptr;
@@ -865,7 +866,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
     E.heavy_cap = std::max<uint64_t>(n_tasks, n) + 1;
     PBSC_CUDA(E.heavy_list.get(idx, "tw.heavy_list", 2 * E.heavy_cap)); PBSC_CUDA(E.n_heavy.get(idx, "tw.n_heavy", 2));
     E.pool_cap = std::max<uint64_t>(n_tasks, n) * (uint64_t)w.pool_nodes + 65536;
-    PBSC_CUDA(E.nodepool.get(idx, "tw.nodepool", E.pool_cap)); PBSC_CUDA(E.pool_used.get(idx, "tw.pool_used", 1));
+    PBSC_CUDA(E.pool_used.get(idx, "tw.pool_used", 1));
     PBSC_CUDA(E.states.get(idx, "tw.states", n)); PBSC_CUDA(E.stalled.get(idx, "tw.stalled", n)); PBSC_CUDA(E.n_stalled.get(idx, "tw.n_stalled", 1));
     PBSC_CUDA(cudaMemsetAsync(E.states.p, 0, n * sizeof(ReadState), st));
     PBSC_CUDA(cudaMemsetAsync(E.pending.p, 0, n * sizeof(WalkTask), st));
@@ -890,6 +891,10 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         rec_spec = tail[2] + tail[3];
         nl += 6;
     }
+    // label-tree pool of the light passes: a successful light walk parks one node per child it created, about 1.3 per base
+    // of its output on average; the output slots' total (just scanned) bounds that with room to spare
+    E.pool_cap = std::max<uint64_t>(E.pool_cap, 2 * pool_spec + 65536);
+    PBSC_CUDA(E.nodepool.get(idx, "tw.nodepool", E.pool_cap));
     // pools: [speculative tasks | their alternatives (same layout) | one pending request per read]
     int alt_rounds = 4;
     if (const char* e = getenv("PBSC_ALT_ROUNDS")) alt_rounds = std::max(0, atoi(e));

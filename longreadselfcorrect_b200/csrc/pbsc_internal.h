@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <condition_variable>
@@ -90,6 +92,7 @@ struct DevBuf
         n = count;
         return dev_cache_alloc((void**)&p, (count ? count : 1) * sizeof(T));
     }
+    void release() { if (p) dev_cache_free(p); p = nullptr; n = 0; }
 };
 
 // grow-only named device buffer owned by the index
@@ -98,12 +101,16 @@ inline cudaError_t arena_get(pbsc_index* idx, const char* name, size_t bytes, vo
     pbsc_index::ArenaBuf& a = idx->arena[name];
     if (a.cap < bytes || a.p == nullptr)
     {
+        const bool tr = getenv("PBSC_ROUND_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         if (a.p) cudaFree(a.p);
         a.p = nullptr; a.cap = 0;
         const size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&a.p, want);
         if (e != cudaSuccess) return e;
         a.cap = want;
+        if (tr) fprintf(stderr, "[pbsc round trace]     arena %-16s -> %8.1f MB in %7.2f ms\n", name, want / 1048576.0,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
     *out = a.p;
     return cudaSuccess;

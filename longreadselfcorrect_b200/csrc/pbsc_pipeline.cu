@@ -79,10 +79,11 @@ static int batch_upload_impl(pbsc_index* idx, const pbsc_params* p, const char* 
     Events ev;
     PBSC_CUDA(ev.create(2));
     cudaEventRecord(ev[0], bt->cs);
+    // only the reads travel now (one byte per base on the device): the ~130 bytes per base of seed and extend workspace are
+    // taken when the batch gets a lane and given back when its kernels are done, so a batch that waits for its turn, or for its
+    // results to be fetched, holds almost no device memory
     int rc = upload_reads(idx, reads, offsets, n_reads, bt->b, bt->cs);
     cudaEventRecord(ev[1], bt->cs);
-    if (rc == PBSC_OK) rc = alloc_seed_workspace(p, bt->h_offsets, bt->b, bt->s, bt->w, bt->cs);
-    if (rc == PBSC_OK) rc = alloc_extend_workspace(idx, p, bt->h_offsets, bt->b, bt->s, bt->w, bt->cs);
     if (rc == PBSC_OK) { cudaEventSynchronize(ev[1]); cudaEventElapsedTime(&bt->h2d_ms, ev[0], ev[1]); PBSC_CUDA(cudaEventRecord(bt->ev_up, bt->cs)); }
     if (rc != PBSC_OK) return rc;
     *out = bt.release();
@@ -105,12 +106,22 @@ static int batch_run_impl(pbsc_batch* bt, float* ms)
     // capacities other batches of this index had to grow to since this one was uploaded
     bt->w.node_cap = std::max(bt->w.node_cap, idx->learned_node_cap);
     bt->w.pool_nodes = std::max(bt->w.pool_nodes, idx->learned_pool_nodes);
-    if (idx->learned_piece_factor > bt->w.piece_factor)
+    bt->w.piece_factor = std::max(bt->w.piece_factor, idx->learned_piece_factor);
+    rc = alloc_seed_workspace(&bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
+    if (rc == PBSC_OK) rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
+    if (rc != PBSC_OK) return rc;
+    // what only the kernels need goes back to the block cache on every way out; the results (pieces, bounds, counters) stay
+    struct Scratch
     {
-        bt->w.piece_factor = idx->learned_piece_factor;
-        rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
-        if (rc != PBSC_OK) return rc;
-    }
+        pbsc_batch* bt;
+        ~Scratch()
+        {
+            Workspace& w = bt->w; SeedBuffers& s = bt->s;
+            w.feats.release(); w.cls.release(); w.attr.release(); w.ntriv.release(); w.prefix.release(); w.cand.release(); w.seed_tmp.release();
+            w.scratch.release(); w.order.release();
+            s.seeds.release(); s.region.release(); s.count.release(); s.outcast.release();
+        }
+    } scratch_guard{bt};
     bool grew = false;
     float extend_total = 0;
     for (int attempt = 0;; attempt++)

@@ -999,7 +999,8 @@ __device__ __forceinline__ void level_select(State& S, LaneCtx& c)
 // extendOverlap's return value and findTheBestPath (:199-236).  A successful walk does not chase its label chain here
 // (a serial pointer chase by one lane while 31 wait): it copies its label tree to the node pool and leaves the rest to
 // materialize_kernel.
-static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t* nodepool, unsigned long long* pool_used, uint64_t pool_cap)
+static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t* nodepool, unsigned long long* pool_used, uint64_t pool_cap, bool direct,
+                                               uint8_t* out, uint32_t outCap, uint32_t* outLen)
 {
     if (S.status) return S.status;
     const ExtParamsDev& P = *S.P;
@@ -1011,6 +1012,27 @@ static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t
         for (uint32_t i = 0; i < S.nRes; i++) { const double e = S.s.res[i].err; if (e < best) { best = e; bi = (int)i; } }
         if (bi < 0) return PBSC_WALK_NO_PATH;
         const WalkResult r = S.s.res[bi];
+        if (direct)
+        {
+            // a pass of few, long walks (most lanes of the warp only help): write the merged sequence here, from the lane's own
+            // label tree, instead of parking a tree of up to node_cap nodes in the shared pool
+            const uint8_t* q = S.s.q;
+            const uint8_t* trg = q + S.qlen - S.trgLen;
+            const uint32_t chain = r.depth - S.k;
+            const uint32_t tailFrom = (uint32_t)r.i + (uint32_t)P.min_overlap;
+            const uint32_t tailLen = S.trgLen > (uint32_t)P.min_overlap ? S.trgLen - tailFrom : 0;
+            const uint32_t len = r.depth + tailLen;
+            if (len > outCap) return PBSC_WALK_OVERFLOW;
+            #pragma unroll 1
+            for (uint32_t x = 0; x < S.k; x++) out[x] = q[x];
+            #pragma unroll 1
+            for (uint32_t x = 0; x < tailLen; x++) out[r.depth + x] = trg[tailFrom + x];
+            uint32_t node = r.node;
+            #pragma unroll 1
+            for (uint32_t x = 0; x < chain; x++) { const uint32_t w = S.s.nodes[node]; out[r.depth - 1 - x] = (uint8_t)(w & 3); node = w >> 2; }
+            *outLen = len;
+            return 1;
+        }
         const uint32_t nn = (S.nNodes + 3u) & ~3u;
         const uint64_t off = atomicAdd(pool_used, (unsigned long long)nn);
         if (off + nn > pool_cap) return PBSC_OVF_POOL;

@@ -74,11 +74,13 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3
 
-    for lanes in (1, args.lanes, 1, args.lanes):
+    for lanes in (1, args.lanes):
         one_pass(lanes)   # warm-up of the arenas of every lane
         ts = [one_pass(lanes) for _ in range(args.reps)]
         ms = min(ts)
-        print(f"{args.workload} parts={args.parts} lanes={lanes}: {ms:8.1f} ms per pass  {mbp / (ms / 1e3):7.1f} Mbp/s   ({', '.join(f'{t:.0f}' for t in ts)})", flush=True)
+        free_b, tot_b = torch.cuda.mem_get_info()
+        print(f"{args.workload} parts={args.parts} lanes={lanes}: {ms:8.1f} ms per pass  {mbp / (ms / 1e3):7.1f} Mbp/s   ({', '.join(f'{t:.0f}' for t in ts)})  "
+              f"device memory in use {(tot_b - free_b) / 1e9:.1f} GB", flush=True)
 
 
 if __name__ == "__main__":
