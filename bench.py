@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the `stride pbcorrect` hot path (seed discovery + FM extension + DP/MSA fallback) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg3s|cfg1|tiny] [--nodp]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg3s|cfg1|mini] [--nodp]
 
 One "step" = one pass of the hot path over the WHOLE read set of the workload.  The default workload is BASELINE.json
 configs[2], the configuration its metric ("corrected Mbp/s at 1/2/4/8 B200") is quoted on: 12 Mb synthetic genome with
@@ -55,7 +55,7 @@ WORKLOADS = {
     # the same recipe at 1/6 of the size: a repeat-rich parity and capacity check that fits a short GPU slot
     "cfg3s": dict(genome=2_000_000, gseed=3, cov=100, mean=8000, rseed=103, c=100, g=10, repeat_families=8, tandem_arrays=4,
                   desc="2 Mb synthetic genome with injected repeats, 100x simulated CLR reads (mean 8 kb, 13% error), -c 100 -g 10"),
-    "tiny": dict(genome=100_000, gseed=1, cov=30, mean=3000, rseed=101, c=30, g=5,
+    "mini": dict(genome=100_000, gseed=1, cov=30, mean=3000, rseed=101, c=30, g=5,
                  desc="100 kb synthetic genome, 30x simulated CLR reads (mean 3 kb), -c 30 -g 5"),
 }
 REF_STRIDE = os.path.join(ROOT, "oracle", "_ref", "stride")

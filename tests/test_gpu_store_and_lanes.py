@@ -182,3 +182,60 @@ def test_lanes_concurrent_batches_byte_identical(api, tiny_reads, golden, lanes)
     out1, poff1, first1, stats1 = idx.correct_reads(p7, [s for _, s in tiny_reads[:20]])
     assert out[: int(poff[int(first[-1])])].tobytes() == out1[: int(poff1[int(first1[-1])])].tobytes()
     idx.close()
+
+
+def _option_goldens(golden):
+    import json
+    return json.load(open(os.path.join(golden, "tiny.options.json")))
+
+
+@pytest.mark.parametrize("variant", ["adjust_k17_u2_r-2", "adjust_k21", "idmer7", "minkmer15", "error0.2", "leaves16", "mode2_nodp", "fastq"])
+def test_cli_options_byte_identical_to_reference(golden, tmp_path, variant):
+    """`pbcorrect` with the options the other fixtures leave at their defaults (-k/-u/-r, -i, -s, -e, -l, -m) and with FASTQ
+    input (lower-case bases, quality lines that start with '@' or '>'): the sha256 of correct.fa and discard.fa equal the
+    reference's (tests/golden/make_option_golden.py)."""
+    import hashlib
+    import subprocess
+    from conftest import ROOT
+    sys_path = os.path.join(ROOT, "tests", "golden")
+    g = _option_goldens(golden)[variant]
+    reads = os.path.join(golden, "tiny.reads.fa")
+    if g["input"] == "fastq":
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_option_golden", os.path.join(sys_path, "make_option_golden.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        reads = str(tmp_path / "tiny.reads.fq")
+        m.write_fastq(reads, read_fasta(os.path.join(golden, "tiny.reads.fa")))
+    exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
+    out = tmp_path / "out"
+    r = subprocess.run([exe, "pbcorrect", "-t", "3", "-p", os.path.join(golden, "tiny"), "-o", str(out), "--batch-mbp", "0.15", "--lanes", "2"] + g["options"] + [reads],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert hashlib.sha256(open(out / "correct.fa", "rb").read()).hexdigest() == g["correct_sha256"]
+    assert hashlib.sha256(open(out / "discard.fa", "rb").read()).hexdigest() == g["discard_sha256"]
+    summ = {l.split(":")[0]: l.split(":")[1].split(",")[0].strip() for l in r.stdout.splitlines() if ":" in l and not l.startswith("Time of")}
+    assert summ == g["summary"]
+
+
+def test_cli_fmg_and_multi_gpu_give_the_same_files(golden, tmp_path):
+    """The binary with --write-fmg (cold), then again from PREFIX.fmg (warm), then over every GPU of the box (index cloned by
+    peer copies, batches dealt to the GPUs, records written in input order): identical files, equal to the reference's."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from longreadselfcorrect_b200 import api as a
+    for ext in ("bwt", "rbwt", "sai"):
+        shutil.copy(os.path.join(golden, f"tiny.{ext}"), tmp_path / f"t.{ext}")
+    exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
+    want_c = open(os.path.join(golden, "tiny.dp.correct.fa"), "rb").read()
+    want_d = open(os.path.join(golden, "tiny.dp.discard.fa"), "rb").read()
+    runs = [("cold", ["--write-fmg", "--gpus", "1"], "PREFIX.bwt"), ("warm", ["--gpus", "1"], "PREFIX.fmg"), ("all", ["--gpus", str(a.device_count())], "PREFIX.fmg")]
+    for name, extra, source in runs:
+        out = tmp_path / f"out_{name}"
+        r = subprocess.run([exe, "-t", "2", "-p", str(tmp_path / "t"), "-o", str(out), "-c", "30", "-g", "5", "--batch-mbp", "0.1"] + extra + [os.path.join(golden, "tiny.reads.fa")],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr[-800:]
+        assert f"from {source}" in r.stderr, r.stderr[-800:]
+        assert open(out / "correct.fa", "rb").read() == want_c and open(out / "discard.fa", "rb").read() == want_d, name
+    assert os.path.exists(tmp_path / "t.fmg")

@@ -182,29 +182,49 @@ def test_balanced_ranges():
 
 
 _WORKER = r"""
-import os, sys
+import os, subprocess, sys
 sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np, torch, torch.distributed as dist
-from longreadselfcorrect_b200 import sharding
+from conftest import read_fasta
+from longreadselfcorrect_b200 import parity, sharding
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
-rng = np.random.default_rng(11)
-lens = rng.integers(10, 200, size=57)
-off = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
-buf = rng.integers(0, 4, size=int(off[-1])).astype(np.uint8)
+golden = os.path.join({root!r}, "tests", "golden")
+reads = read_fasta(os.path.join(golden, "tiny.reads.fa"))[:120]
+buf = np.frombuffer("".join(s for _, s in reads).encode(), dtype=np.uint8)
+off = np.concatenate(([0], np.cumsum([len(s) for _, s in reads]))).astype(np.uint64)
 sbuf, soff, (b, e) = sharding.shard(buf, off, rank, 2)
-# stand-in for the per-read hot path: any pure per-read function; here a checksum per read
-mine = [int(sbuf[int(soff[i]):int(soff[i + 1])].astype(np.int64).dot(np.arange(1, int(soff[i + 1] - soff[i]) + 1))) for i in range(e - b)]
+# the per-read hot path of this rank's shard: here the CPU oracle stands where a GPU rank calls pbsc_correct_batch
+d = {tmp!r} + "/rank%d" % rank
+os.makedirs(d)
+fa = d + "/shard.fa"
+with open(fa, "w") as f:
+    for (rid, _), i in zip(reads[b:e], range(e - b)):
+        f.write(">%s\n%s\n" % (rid, sbuf[int(soff[i]):int(soff[i + 1])].tobytes().decode()))
+subprocess.run([{oracle!r}, "pbcorrect", "--threads", "2", "-p", os.path.join(golden, "tiny"), "-o", d + "/o", "-c", "30", "-g", "5", fa], check=True,
+               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+mine = (b, e, open(d + "/o/correct.fa").read(), open(d + "/o/discard.fa").read())
 gathered = [None, None]
-dist.all_gather_object(gathered, (b, e, mine))
+dist.all_gather_object(gathered, mine)
 t = torch.tensor([float(rank + 1)])
 dist.all_reduce(t, op=dist.ReduceOp.MAX)          # the bench's max-over-ranks timing reduction
 if rank == 0:
-    out = []
-    for b_, e_, m in sorted(gathered):
-        out += m
-    ref = [int(buf[int(off[i]):int(off[i + 1])].astype(np.int64).dot(np.arange(1, int(lens[i]) + 1))) for i in range(57)]
-    assert out == ref and float(t) == 2.0
+    parts = sorted(gathered)
+    assert parts[0][0] == 0 and parts[0][1] == parts[1][0] and parts[1][1] == len(reads)      # contiguous ranges that tile the read set
+    correct = "".join(p[2] for p in parts); discard = "".join(p[3] for p in parts)
+    ids = set(r for r, _ in reads)
+    def first_records(path):
+        out, keep = [], False
+        for line in open(path):
+            if line.startswith(">"):
+                keep = line[1:].strip() in ids
+            if keep:
+                out.append(line)
+        return "".join(out)
+    assert correct == first_records(os.path.join(golden, "tiny.dp.correct.fa"))      # the reference's records, in input order
+    assert discard == first_records(os.path.join(golden, "tiny.dp.discard.fa"))
+    assert float(t) == 2.0
     print("ok")
 dist.destroy_process_group()
 """
@@ -217,8 +237,52 @@ def test_two_rank_sharding_gloo(tmp_path):
     port = s.getsockname()[1]
     s.close()
     script = tmp_path / "w.py"
-    script.write_text(_WORKER.format(root=ROOT, port=port))
+    from conftest import ORACLE, _ensure_oracle
+    _ensure_oracle()
+    script.write_text(_WORKER.format(root=ROOT, port=port, tmp=str(tmp_path), oracle=ORACLE))
     procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
-    outs = [p.communicate(timeout=120) for p in procs]
+    outs = [p.communicate(timeout=600) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "ok" in outs[0][0]
+
+
+def test_parity_digests_agree_between_results_files_and_goldens(tmp_path):
+    """parity.py: the digest of a read computed from a batch result (pieces + counters), from output files, and by the golden
+    generator are the same 8 bytes; the committed whole-output goldens load and describe every read of their workload."""
+    import importlib.util
+    import numpy as np
+    from longreadselfcorrect_b200 import api, parity
+    reads = [b"ACGTACGTAC", b"GGGTTTAAAC", b"TTTT"]
+    corrected = [b"ACGTTACGTAC", None, b"TTTTA"]           # read 1 is discarded
+    letters = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    off = np.concatenate(([0], np.cumsum([len(r) for r in reads]))).astype(np.uint64)
+    out = np.frombuffer(b"".join(c for c in corrected if c), dtype=np.uint8)
+    poff = np.array([0, 11, 16], dtype=np.uint64)
+    first = np.array([0, 1, 1, 2], dtype=np.uint64)
+    stats = np.zeros(3, dtype=api.STATS_DTYPE)
+    stats["merge"] = [1, 0, 1]
+    dig = parity.result_digests(out, poff, first, stats, letters, off, first_read_id=5)
+    with open(tmp_path / "correct.fa", "wb") as f:
+        f.write(b">r5\n" + corrected[0] + b"\n>r7\n" + corrected[2] + b"\n")
+    with open(tmp_path / "discard.fa", "wb") as f:
+        f.write(b">r6\n" + reads[1] + b"\n")
+    files = parity.fasta_digests(str(tmp_path / "correct.fa"), str(tmp_path / "discard.fa"))
+    spec = importlib.util.spec_from_file_location("mfg", os.path.join(ROOT, "tests", "golden", "make_full_golden.py"))
+    mfg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mfg)
+    for i, rid in enumerate((5, 6, 7)):
+        assert dig[i].tobytes() == files[rid]
+        seq = corrected[i] if corrected[i] else reads[i]
+        assert files[rid] == mfg.record_digest(b"r%d" % rid, seq, corrected[i] is not None)
+    assert dig[1, 7] == 0 and dig[0, 7] == 1
+    assert len(parity.output_sha256(dig)) == 64
+    for wl, n in (("cfg2", 28935), ("mini", 1015)):
+        ids, d, meta = parity.load_golden(wl)
+        assert ids.size == n == meta["reads_total"] and d.shape == (n, 8) and meta["sample"] == 1.0
+        assert "stride pbcorrect" in meta["command"]
+    # a perfect result compares clean, one flipped byte is found
+    ids, d, meta = parity.load_golden("mini")
+    assert parity.compare_with_golden("mini", d.copy())["identical"]
+    bad = d.copy(); bad[17, 3] ^= 1
+    r = parity.compare_with_golden("mini", bad)
+    assert not r["identical"] and r["mismatches"] == 1 and r["first_mismatch"] == 17

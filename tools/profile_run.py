@@ -11,7 +11,7 @@ import numpy as np  # noqa: E402
 import bench  # noqa: E402
 from longreadselfcorrect_b200 import api, bwt_build  # noqa: E402
 
-wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "tiny"]
+wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "mini"]
 k0 = int(sys.argv[2]) if len(sys.argv) > 2 else 13
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dp = len(sys.argv) > 4 and sys.argv[4] == "dp"
