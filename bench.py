@@ -272,14 +272,12 @@ def ours(args, wl, metric):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dist = None
     # --backend gloo: the same multi-rank code without NCCL (control traffic through gloo on CPU tensors), for boxes where the
     # ranks have to share one GPU (tests); PBSC_BENCH_SAME_DEVICE=1 puts every rank on GPU 0
-    same_dev = os.environ.get("PBSC_BENCH_SAME_DEVICE") == "1"
-    if same_dev:
+    if os.environ.get("PBSC_BENCH_SAME_DEVICE") == "1":
         local_rank = 0
-        torch.cuda.set_device(0)
+    torch.cuda.set_device(local_rank)
+    dist = None
     cdev = "cuda" if args.backend == "nccl" else "cpu"
     if world > 1:
         import torch.distributed as dist

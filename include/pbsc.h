@@ -71,6 +71,8 @@ typedef struct pbsc_params
     float hh_ratio;       /* 0.6f */
     float threshold[3][52]; /* KmerThreshold table[mode][k] (PacBio/KmerThreshold.cpp:43-79) */
     double freqs_of_kmer[101]; /* pow(1-e,i)*cov, i>=min_kmer (LongReadCorrectByOverlap.cpp:68-70) */
+    int32_t debug_seed;   /* --debugseed: batches keep what pbsc_batch_fetch_debug returns */
+    int32_t reserved;
 } pbsc_params;
 
 /* One seed of a read: SeedFeature (PacBio/SeedFeature.h:22-45) after
@@ -222,6 +224,17 @@ int pbsc_batch_result_size(pbsc_batch* b, uint64_t* piece_bytes, uint64_t* n_pie
 int pbsc_batch_fetch(pbsc_batch* b, char* pieces_out, uint64_t pieces_cap, uint64_t* piece_offsets,
                      uint64_t piece_offsets_cap, uint64_t* first_piece, pbsc_read_stats* stats);
 void pbsc_batch_destroy(pbsc_batch* b);
+
+/* ---- --debugseed (PacBio/LongReadProbe.cpp:109-114,172-173,221-226; PacBio/PacBioSelfCorrectionProcess.cpp:72-76,130-131,
+ *      139-140): what the reference's per-read dump files hold, for a batch that ran with params.debug_seed != 0.
+ *      seeds: the surviving seeds of read r at seed_offsets[r] .. +n_surviving[r], then its hitchhiked ones up to
+ *      seed_offsets[r+1] (seed/<id>.seed, seed/error/<id>.seed); ratio: the repeat ratio of every read position
+ *      (extend/<id>.log), n_bases floats; log: one record per seed pair whose FM walk failed, in walk order
+ *      (extend/<id>.ext: src_start, trg_start, code = walk outcome + 4; dp_failed != 0 also goes to extend/<id>.dp). ---- */
+typedef struct pbsc_walk_log { int32_t src_start, trg_start, code, dp_failed; } pbsc_walk_log;
+int pbsc_batch_debug_size(pbsc_batch* b, uint64_t* n_seeds, uint64_t* n_log);
+int pbsc_batch_fetch_debug(pbsc_batch* b, pbsc_seed* seeds, uint64_t seeds_cap, uint64_t* seed_offsets, uint32_t* n_surviving, float* ratio,
+                           uint64_t ratio_cap, pbsc_walk_log* log, uint64_t log_cap, uint64_t* log_offsets);
 
 /* timing/launch counters of the last pbsc_correct_batch / pbsc_batch_run on this thread (ms from CUDA events
  * on the launch stream) */

@@ -37,6 +37,7 @@ class CParams(C.Structure):
         ("offset", C.c_int32 * 3), ("pool", C.c_int32 * 8), ("n_pool", C.c_int32), ("scan_kmer", C.c_int32),
         ("kmer_up_bound", C.c_int32), ("radius", C.c_int32), ("hh_ratio", C.c_float),
         ("threshold", (C.c_float * 52) * 3), ("freqs_of_kmer", C.c_double * 101),
+        ("debug_seed", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -64,6 +65,8 @@ STATS_DTYPE = np.dtype([(n, "<i8") for n in ("total_reads_len", "corrected_len",
                                              "high_error_num", "exceed_depth_num", "exceed_leave_num", "fm_num",
                                              "dp_num", "seed_dis")] + [("merge", "<i4"), ("n_pieces", "<i4")])
 
+WALK_LOG_DTYPE = np.dtype([("src_start", "<i4"), ("trg_start", "<i4"), ("code", "<i4"), ("dp_failed", "<i4")])
+
 # every symbol include/pbsc.h declares
 EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc_params_derive",
             "pbsc_threshold_table_text", "pbsc_index_create", "pbsc_index_load", "pbsc_index_create_synthetic",
@@ -74,7 +77,8 @@ EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc
             "pbsc_host_alloc", "pbsc_host_free", "pbsc_trim", "pbsc_random_sector_bench",
             "pbsc_index_save", "pbsc_index_load_fmg", "pbsc_index_open", "pbsc_index_clone", "pbsc_index_blob_size",
             "pbsc_index_export_blob", "pbsc_index_import_blob", "pbsc_index_set_lanes", "pbsc_index_lanes",
-            "pbsc_host_register", "pbsc_host_unregister", "pbsc_occ_counts"]
+            "pbsc_host_register", "pbsc_host_unregister", "pbsc_occ_counts",
+            "pbsc_batch_debug_size", "pbsc_batch_fetch_debug"]
 
 _lib = None
 
@@ -191,12 +195,13 @@ class Params:
     def make(coverage: int = 90, error_rate: float = 0.15, genome: int = 10, kmer: int | None = None,
              unique_offset: int | None = None, repeat_offset: int | None = None, next_target: int = 1,
              max_leaves: int = 32, idmer_len: int = 9, min_kmer: int = 13, mode: int | None = None,
-             split: bool = False, no_dp: bool = False) -> "Params":
+             split: bool = False, no_dp: bool = False, debug_seed: bool = False) -> "Params":
         p = CParams()
         lib().pbsc_params_default(C.byref(p))
         p.pb_coverage, p.error_rate, p.genome = coverage, error_rate, genome
         p.next_target, p.max_leaves, p.idmer_len, p.min_kmer = next_target, max_leaves, idmer_len, min_kmer
         p.split, p.no_dp = int(split), int(no_dp)
+        p.debug_seed = int(debug_seed)
         if kmer is not None:
             p.start_kmer, p.adjust = kmer, 1
         if unique_offset is not None:
@@ -461,6 +466,23 @@ class Batch:
         _check(lib().pbsc_batch_fetch(self._h, _ptr(out, C.c_char), C.c_uint64(out.size), _ptr(poff, C.c_uint64), C.c_uint64(poff.size),
                                       _ptr(first, C.c_uint64), stats.ctypes.data_as(C.POINTER(CReadStats))))
         return out, poff, first, stats[: self.n]
+
+    def fetch_debug(self):
+        """--debugseed data of a batch that ran with Params.make(debug_seed=True): (seeds, seed_offsets, n_surviving, ratio, log,
+        log_offsets); see pbsc_batch_fetch_debug in pbsc.h."""
+        ns, nl = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().pbsc_batch_debug_size(self._h, C.byref(ns), C.byref(nl)))
+        seeds = np.zeros(max(int(ns.value), 1), dtype=SEED_DTYPE)
+        soff = np.zeros(self.n + 1, dtype=np.uint64)
+        nsurv = np.zeros(max(self.n, 1), dtype=np.uint32)
+        nb = int(self.off[-1])
+        ratio = np.zeros(max(nb, 1), dtype=np.float32)
+        log = np.zeros(max(int(nl.value), 1), dtype=WALK_LOG_DTYPE)
+        loff = np.zeros(self.n + 1, dtype=np.uint64)
+        _check(lib().pbsc_batch_fetch_debug(self._h, seeds.ctypes.data_as(C.POINTER(CSeed)), C.c_uint64(seeds.size), _ptr(soff, C.c_uint64),
+                                            _ptr(nsurv, C.c_uint32), _ptr(ratio, C.c_float), C.c_uint64(ratio.size), C.c_void_p(log.ctypes.data),
+                                            C.c_uint64(log.size), _ptr(loff, C.c_uint64)))
+        return seeds[: int(ns.value)], soff, nsurv[: self.n], ratio[:nb], log[: int(nl.value)], loff
 
     def close(self):
         if self._h:

@@ -6,6 +6,7 @@
 // (include/pbsc.h); there is no CPU fallback.  Records are written in input order, i.e. the reference's `-t 1` order
 // (with -t T > 1 the reference permutes records inside blocks of 500*T reads; contents are identical).
 #include <getopt.h>
+#include <sys/stat.h>
 #include <zlib.h>
 #include <atomic>
 #include <chrono>
@@ -169,10 +170,17 @@ static void parseOptions(int argc, char** argv)
     if (P.mode < 0 || P.mode > 2) { std::cerr << SUBPROGRAM ": invalid mode: " << P.mode << ", must be (0/1/2)\n"; die = true; }
     if (opt::OnlySeed && opt::barcode.empty()) { std::cerr << SUBPROGRAM ": no barcode\n"; die = true; }
     if (die) { std::cerr << "\n" << CORRECT_USAGE_MESSAGE; exit(EXIT_FAILURE); }
-    if (opt::OnlySeed || opt::DebugSeed)
+    if (opt::OnlySeed)
     {
-        std::cerr << SUBPROGRAM ": --debugseed/--onlyseed diagnostics are not part of this build (hot path only)\n";
+        std::cerr << SUBPROGRAM ": --onlyseed (seed validation against an alignment barcode, PacBio/BCode.cpp) is not part of this build\n";
         exit(EXIT_FAILURE);
+    }
+    if (opt::DebugSeed)
+    {
+        // StriDe/PacBioSelfCorrection.cpp:351-361
+        if (system(("mkdir -p " + opt::directory + "seed/error/").c_str()) != 0 || system(("mkdir -p " + opt::directory + "extend/").c_str()) != 0)
+        { std::cerr << SUBPROGRAM << ": something wrong making directory: " << opt::directory << "\n"; exit(EXIT_FAILURE); }
+        opt::params.debug_seed = 1;
     }
     opt::readsFile = argv[optind++];
 }
@@ -252,6 +260,9 @@ struct Batch
     std::vector<uint64_t> piece_off, first;
     std::vector<pbsc_read_stats> stats;
     pbsc_timing timing{};
+    // --debugseed
+    std::vector<pbsc_seed> dbg_seeds; std::vector<uint64_t> dbg_seed_off, dbg_log_off; std::vector<uint32_t> dbg_surv; std::vector<float> dbg_ratio;
+    std::vector<pbsc_walk_log> dbg_log;
     bool normalized = false, taken = false, done = false;
     int rc = 0;
     std::string err;
@@ -329,6 +340,53 @@ static bool normalize(Batch& b, std::string& bad_id)
         for (uint64_t i = b.offsets[r]; i < b.offsets[r + 1]; i++)
             if (!lut[s[i]]) { bad_id = b.ids[r]; return false; }
     return false;
+}
+
+// --debugseed: the reference's per-read dump files (same names, same text):
+//   seed/<id>.seed        the seeds that survive removeHitchhikingSeeds (operator<< of SeedVector, PacBio/SeedFeature.cpp:11-20)
+//   seed/error/<id>.seed  the hitchhiked ones; only when the read had at least two seeds (LongReadProbe.cpp:189,221-226)
+//   extend/<id>.log       position <tab> repeat ratio, one line per base (LongReadProbe.cpp:172-173; default ostream float format)
+//   extend/<id>.ext       source start <tab> target start <tab> walk outcome + 4 for every failed FM walk (PacBioSelfCorrectionProcess.cpp:130-131)
+//   extend/<id>.dp        source start <tab> target start where the DP fallback failed too (:139-140); both only for reads
+//                         with at least two seeds (:63,72-76)
+static void writeDebugFiles(const Batch& b)
+{
+    const char* s = b.bases.p;
+    std::string text;
+    char num[64];
+    for (size_t r = 0; r < b.ids.size(); r++)
+    {
+        const pbsc_seed* sv = b.dbg_seeds.data() + b.dbg_seed_off[r];
+        const uint32_t nsurv = b.dbg_surv[r], nall = (uint32_t)(b.dbg_seed_off[r + 1] - b.dbg_seed_off[r]);
+        auto seedText = [&](uint32_t from, uint32_t to) {
+            text.clear();
+            for (uint32_t i = from; i < to; i++)
+            {
+                text.append(s + b.offsets[r] + sv[i].start, (size_t)sv[i].len);
+                snprintf(num, sizeof num, "\t%d\t%d\t%s\n", sv[i].max_fixed_freq, sv[i].start, sv[i].is_repeat ? "Yes" : "No");
+                text += num;
+            }
+        };
+        auto put = [&](const std::string& path) { std::ofstream f(path.c_str()); f << text; };
+        seedText(0, nsurv);
+        put(opt::directory + "seed/" + b.ids[r] + ".seed");
+        if (nall >= 2) { seedText(nsurv, nall); put(opt::directory + "seed/error/" + b.ids[r] + ".seed"); }
+        {
+            std::ofstream f((opt::directory + "extend/" + b.ids[r] + ".log").c_str());
+            const uint64_t L = b.offsets[r + 1] - b.offsets[r];
+            for (uint64_t p = 0; p < L; p++) f << p << '\t' << b.dbg_ratio[b.offsets[r] + p] << '\n';
+        }
+        if (nsurv >= 2)
+        {
+            std::ofstream x((opt::directory + "extend/" + b.ids[r] + ".ext").c_str()), d((opt::directory + "extend/" + b.ids[r] + ".dp").c_str());
+            for (uint64_t i = b.dbg_log_off[r]; i < b.dbg_log_off[r + 1]; i++)
+            {
+                const pbsc_walk_log& e = b.dbg_log[i];
+                x << e.src_start << "\t" << e.trg_start << "\t" << e.code << "\n";
+                if (e.dp_failed) d << e.src_start << "\t" << e.trg_start << "\n";
+            }
+        }
+    }
 }
 
 int main(int argc, char** argv)
@@ -456,6 +514,32 @@ int main(int argc, char** argv)
             uint64_t cap = (uint64_t)(b->n_bases * 1.3) + (1 << 16), need = 0;
             b->first.assign(n + 1, 0);
             b->stats.assign(n ? n : 1, pbsc_read_stats{});
+            if (P.debug_seed)
+            {
+                // the staged interface, so that the batch is still there for pbsc_batch_fetch_debug
+                pbsc_batch* h = nullptr;
+                b->rc = pbsc_batch_upload(index[g], &P, b->bases.p, b->offsets.data(), n, &h);
+                if (b->rc == PBSC_OK) b->rc = pbsc_batch_run(h, nullptr);
+                uint64_t nb = 0, np = 0, ns = 0, nl = 0;
+                if (b->rc == PBSC_OK) b->rc = pbsc_batch_result_size(h, &nb, &np);
+                if (b->rc == PBSC_OK)
+                {
+                    b->pieces = g_pins.get(nb + 64);
+                    b->piece_off.assign(np + 16, 0);
+                    b->rc = pbsc_batch_fetch(h, b->pieces.p, b->pieces.cap, b->piece_off.data(), b->piece_off.size(), b->first.data(), b->stats.data());
+                }
+                if (b->rc == PBSC_OK) b->rc = pbsc_batch_debug_size(h, &ns, &nl);
+                if (b->rc == PBSC_OK)
+                {
+                    b->dbg_seeds.resize(ns + 1); b->dbg_log.resize(nl + 1); b->dbg_seed_off.assign(n + 1, 0); b->dbg_log_off.assign(n + 1, 0);
+                    b->dbg_surv.assign(n + 1, 0); b->dbg_ratio.resize(b->n_bases + 1);
+                    b->rc = pbsc_batch_fetch_debug(h, b->dbg_seeds.data(), b->dbg_seeds.size(), b->dbg_seed_off.data(), b->dbg_surv.data(), b->dbg_ratio.data(),
+                                                   b->dbg_ratio.size(), b->dbg_log.data(), b->dbg_log.size(), b->dbg_log_off.data());
+                }
+                if (b->rc != PBSC_OK) { fail(pbsc_last_error()); pbsc_batch_destroy(h); return; }
+                pbsc_batch_destroy(h);
+            }
+            else
             for (;;)
             {
                 if (b->pieces.cap < cap) { g_pins.put(b->pieces); b->pieces = g_pins.get(cap); }
@@ -512,6 +596,7 @@ int main(int argc, char** argv)
                     fputc('\n', discard);
                 }
             }
+            if (P.debug_seed) writeDebugFiles(*b);
             seed_s += b->timing.seed_ms / 1e3; fm_s += (b->timing.extend_ms - b->timing.dp_ms) / 1e3; dp_s += b->timing.dp_ms / 1e3;
             b->release();
             { std::lock_guard<std::mutex> lk(mu); inflight.pop_front(); written++; }
@@ -524,7 +609,14 @@ int main(int argc, char** argv)
     for (int w = 0; w < n_workers; w++) threads.emplace_back(worker, w % ngpu);
     threads.emplace_back(writer);
 
-    const uint64_t batch_bases = (uint64_t)(opt::batch_mbp * 1e6);
+    uint64_t batch_bases = (uint64_t)(opt::batch_mbp * 1e6);
+    {
+        // several GPUs: no batch larger than an even share of the input, so that every GPU gets work (a plain FASTA file is
+        // about one byte per base; a .gz or FASTQ input only makes the batches smaller than they had to be)
+        struct stat sb;
+        if (ngpu > 1 && stat(opt::readsFile.c_str(), &sb) == 0 && sb.st_size > 0)
+            batch_bases = std::min<uint64_t>(batch_bases, std::max<uint64_t>(16000000ull, ((uint64_t)sb.st_size + ngpu - 1) / ngpu));
+    }
     size_t nreads = 0;
     uint64_t inBases = 0;
     auto push = [&](std::unique_ptr<Batch>& cur) {

@@ -65,6 +65,10 @@ struct Workspace
     DevBuf<int32_t> status;
     DevBuf<unsigned long long> counters;   // [0] work queue, [1] walks attempted
     DevBuf<unsigned int> maxima;           // [0] largest seed gap, [1] largest target seed
+    // --debugseed only: repeat ratio per read position; failed walks per read (same per-read regions as the seeds) and their counts
+    DevBuf<float> dbg_ratio;
+    DevBuf<pbsc_walk_log> dbg_log;
+    DevBuf<uint32_t> dbg_log_n;
     std::vector<uint64_t> h_piece_region, h_bounds_region;
     uint32_t q_cap = 0, node_cap = 0, merged_cap = 0;
     int blocks = 0;

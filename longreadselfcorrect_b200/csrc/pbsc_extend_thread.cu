@@ -32,6 +32,8 @@ struct ReadState
     uint64_t plen;
     int32_t pending_trg;   // seed index the pending request targets
     int32_t srcFreq;       // source.maxFixedMerFreq
+    int32_t srcStart;      // source.seedStartPos: where the current piece began in the raw read
+    uint32_t nLog;         // --debugseed: failed walks logged so far
     // DP fallback result of the current target's first (next == 0) walk, kept while the look-ahead walks run
     int32_t dpStatus0;
     uint32_t dpLen0;
@@ -396,7 +398,8 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
               const uint64_t* __restrict__ task_base, WalkTask* spec, const WalkTask* alt, WalkTask* pending, const uint8_t* __restrict__ outpool,
               uint64_t pending_pool_off, uint32_t pending_cap, ReadState* states, uint8_t* __restrict__ pieces,
               const uint64_t* __restrict__ piece_region, uint32_t* __restrict__ piece_bounds, const uint64_t* __restrict__ bounds_region,
-              pbsc_read_stats* __restrict__ stats, int32_t* __restrict__ read_status, uint32_t* stalled_list, unsigned int* n_stalled)
+              pbsc_read_stats* __restrict__ stats, int32_t* __restrict__ read_status, uint32_t* stalled_list, unsigned int* n_stalled,
+              pbsc_walk_log* __restrict__ dbg_log, uint32_t* __restrict__ dbg_log_n)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -429,6 +432,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
             }
             S.srcLen = s0.len; S.srcEnd = s0.start + s0.len - 1; S.srcEndBest = s0.end_best_k; S.srcRepeat = s0.is_repeat;
             S.srcFreq = s0.max_fixed_freq;
+            S.srcStart = s0.start;
             S.nPieces = 1;
             S.t = 1; S.next = 0;
         }
@@ -535,6 +539,13 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                 S.st.total_walk_num++;
                 // correctByMSAlignment (PacBioSelfCorrectionProcess.cpp:134-136, 208-245)
                 if (is_overflow(S.dpStatus0) || S.dpStatus0 == PBSC_WALK_UNSUPPORTED) { S.rstatus = S.dpStatus0; break; }
+                if (dbg_log)
+                {
+                    // extend/<id>.ext and .dp (PacBioSelfCorrectionProcess.cpp:130-131, 139-140); one slot per seed of the read
+                    pbsc_walk_log e;
+                    e.src_start = S.srcStart; e.trg_start = tg.start; e.code = S.firstType + 4; e.dp_failed = S.dpStatus0 == PBSC_DP_OK ? 0 : 1;
+                    dbg_log[region[r] + S.nLog++] = e;
+                }
                 if (S.dpStatus0 == PBSC_DP_OK)
                 {
                     int k; bool rtou;
@@ -559,6 +570,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                         for (int x = 0; x < tg.len; x++) piece[S.plen + x] = read[tg.start + x];
                         S.plen += tg.len;
                         S.srcLen = tg.len;
+                        S.srcStart = tg.start;   // pieceVec.push_back(target): the next source is the target seed itself
                     }
                     else
                     {
@@ -591,6 +603,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
     if (S.nPieces && S.nPieces < boundsCap) bounds[S.nPieces] = (uint32_t)S.plen;
     stats[r] = S.st;
     read_status[r] = S.rstatus;
+    if (dbg_log_n) dbg_log_n[r] = S.nLog;
     states[r] = S;
 }
 
@@ -942,7 +955,7 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
         stitch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(C, n, b.codes.p, b.offsets.p, s.seeds.p, s.region.p, s.count.p, E.task_base.p, E.spec.p,
                                                                    E.alt.p, E.pending.p, E.outpool.p, pending_pool_off, pending_cap, E.states.p, w.pieces.p,
                                                                    w.piece_region.p, w.bounds.p, w.bounds_region.p, w.stats.p, w.status.p, E.stalled.p,
-                                                                   E.n_stalled.p);
+                                                                   E.n_stalled.p, w.dbg_log.p, w.dbg_log_n.p);
         nl++;
         unsigned int ns = 0;
         PBSC_CUDA(cudaMemcpyAsync(&ns, E.n_stalled.p, 4, cudaMemcpyDeviceToHost, st));

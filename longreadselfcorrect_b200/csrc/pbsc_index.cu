@@ -251,6 +251,78 @@ __global__ void unique_count_kernel(const uint32_t* sorted, uint32_t n, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
+// device decode of the on-disk run bytes (BWTReaderBinary.cpp:79-85, RLUnit.h:118-143): the host only reads the file
+// ------------------------------------------------------------------------------------------
+// per run: its length (and the length again if it is a run of '$'); malformed bytes are counted
+__global__ void run_lengths_kernel(const uint8_t* __restrict__ runs, uint64_t n_runs, uint64_t* __restrict__ len, uint64_t* __restrict__ dlen, unsigned int* bad)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint8_t u = runs[r];
+    const uint32_t sym = u >> 5, l = u & 0x1f;
+    if (sym > 4 || l == 0) atomicAdd(bad, 1u);
+    len[r] = l;
+    dlen[r] = sym == 0 ? l : 0;
+}
+
+// per run: its symbols into the 2-bit words of the blocks; '$' positions into the list and the per-block bit mask
+__global__ void run_scatter_kernel(const uint8_t* __restrict__ runs, uint64_t n_runs, const uint64_t* __restrict__ start, const uint64_t* __restrict__ dstart,
+                                   uint64_t n_symbols, FmBlock* blocks, uint32_t* __restrict__ dollar, unsigned long long* dmask, unsigned int* bad)
+{
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint8_t u = runs[r];
+    const uint32_t sym = u >> 5, l = u & 0x1f;
+    uint64_t pos = start[r];
+    if (pos + l > n_symbols) { atomicAdd(bad, 1u); return; }
+    if (sym == 0)
+    {
+        uint64_t d = dstart[r];
+        for (uint32_t i = 0; i < l; i++, pos++, d++) { dollar[d] = (uint32_t)pos; atomicOr(dmask + (pos >> 6), 1ull << (pos & 63u)); }
+        return;
+    }
+    if (sym == 1 || sym > 4) return;   // 'A' is code 0: nothing to set
+    const uint32_t code = sym - 1;
+    // at most three 32-bit words (16 symbols each) hold a run of up to 31 symbols
+    uint32_t left = l;
+    while (left)
+    {
+        const uint64_t b = pos >> 6;
+        const uint32_t j = (uint32_t)pos & 63u, w = j >> 4, o = j & 15u;
+        const uint32_t take = min(left, 16u - o);
+        const uint32_t pat = (take == 16 ? 0xffffffffu : ((1u << (2 * take)) - 1u)) & (0x55555555u * code);
+        atomicOr(&blocks[b].bases[w], pat << (2 * o));
+        pos += take; left -= take;
+    }
+}
+
+// per block: how many A, C, G, T it holds ('$' and the padding behind the last symbol are code 0 but not 'A')
+__global__ void block_counts_kernel(const FmBlock* __restrict__ blocks, const uint64_t* __restrict__ dmask, uint64_t n_blocks, uint64_t n_symbols,
+                                    uint32_t* cntA, uint32_t* cntC, uint32_t* cntG, uint32_t* cntT)
+{
+    const uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t startp = b << 6;
+    const uint32_t valid = startp >= n_symbols ? 0u : (uint32_t)((n_symbols - startp) < 64 ? (n_symbols - startp) : 64);
+    const FmBlock blk = blocks[b];
+    const uint64_t w0 = (uint64_t)blk.bases[0] | ((uint64_t)blk.bases[1] << 32), w1 = (uint64_t)blk.bases[2] | ((uint64_t)blk.bases[3] << 32);
+    const uint64_t M = 0x5555555555555555ull;
+    const uint64_t l0 = w0 & M, h0 = (w0 >> 1) & M, l1 = w1 & M, h1 = (w1 >> 1) & M;
+    const uint32_t nT = __popcll(h0 & l0) + __popcll(h1 & l1), nG = __popcll(h0 & ~l0) + __popcll(h1 & ~l1), nC = __popcll(~h0 & l0) + __popcll(~h1 & l1);
+    cntA[b] = valid - nT - nG - nC - (uint32_t)__popcll(dmask[b]);
+    cntC[b] = nC; cntG[b] = nG; cntT[b] = nT;
+}
+
+__global__ void block_headers_kernel(FmBlock* blocks, const uint64_t* __restrict__ dmask, const uint32_t* cumA, const uint32_t* cumC, const uint32_t* cumG,
+                                     const uint32_t* cumT, uint64_t n_blocks)
+{
+    const uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    blocks[b].cnt[0] = cumA[b] | (dmask[b] ? 0x80000000u : 0u);
+    blocks[b].cnt[1] = cumC[b]; blocks[b].cnt[2] = cumG[b]; blocks[b].cnt[3] = cumT[b];
+}
+
+// ------------------------------------------------------------------------------------------
 // short-prefix table: entry(w) for every k0-mer w, built level by level (one update per entry)
 // ------------------------------------------------------------------------------------------
 __global__ void prefix_level_kernel(FmIndexDev idx, const PrefixEntry* prev, PrefixEntry* cur, uint64_t n_cur, int level)
@@ -409,6 +481,67 @@ static int upload_strand(pbsc_index* idx, int which, const std::vector<FmBlock>&
     return PBSC_OK;
 }
 
+// One strand from its run bytes, decoded on the device: H2D of the bytes, lengths, two scans, one scatter, per-block counts,
+// four scans.  ~1 s for the 1.25 G symbols of config 3 (the host loop of decode_runs took 6 s per strand).
+static int upload_strand_device(pbsc_index* idx, int which, const uint8_t* runs, uint64_t n_runs, uint64_t n_symbols, uint64_t n_strings)
+{
+    if (n_symbols >= 0xffffffffull) { set_error("BWT has %llu symbols; this build supports < 2^32-1", (unsigned long long)n_symbols); return PBSC_ERR_LIMIT; }
+    if (n_runs == 0 || n_runs >= 0x7fffffffull) { set_error("BWT with %llu runs is outside this build's range", (unsigned long long)n_runs); return PBSC_ERR_LIMIT; }
+    const uint64_t nb = n_symbols / 64 + 1;
+    DevBuf<uint8_t> d_runs, tmp; DevBuf<uint64_t> len, dlen, start, dstart; DevBuf<unsigned int> bad; DevBuf<uint32_t> cnt[4], cum[4];
+    PBSC_CUDA(d_runs.alloc(n_runs)); PBSC_CUDA(len.alloc(n_runs + 1)); PBSC_CUDA(dlen.alloc(n_runs + 1)); PBSC_CUDA(start.alloc(n_runs + 1)); PBSC_CUDA(dstart.alloc(n_runs + 1));
+    PBSC_CUDA(bad.alloc(1));
+    PBSC_CUDA(cudaMemcpy(d_runs.p, runs, n_runs, cudaMemcpyHostToDevice));
+    PBSC_CUDA(cudaMemset(bad.p, 0, 4));
+    PBSC_CUDA(cudaMemset(len.p + n_runs, 0, 8)); PBSC_CUDA(cudaMemset(dlen.p + n_runs, 0, 8));
+    run_lengths_kernel<<<(unsigned)((n_runs + 255) / 256), 256>>>(d_runs.p, n_runs, len.p, dlen.p, bad.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, len.p, start.p, (int)(n_runs + 1));
+    PBSC_CUDA(tmp.alloc(tb));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.p, start.p, (int)(n_runs + 1));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, dlen.p, dstart.p, (int)(n_runs + 1));
+    uint64_t tot[2] = {0, 0};
+    PBSC_CUDA(cudaMemcpy(&tot[0], start.p + n_runs, 8, cudaMemcpyDeviceToHost));
+    PBSC_CUDA(cudaMemcpy(&tot[1], dstart.p + n_runs, 8, cudaMemcpyDeviceToHost));
+    unsigned int hbad = 0;
+    PBSC_CUDA(cudaMemcpy(&hbad, bad.p, 4, cudaMemcpyDeviceToHost));
+    if (hbad) { set_error("malformed run bytes (%u) in the BWT", hbad); return PBSC_ERR_FORMAT; }
+    if (tot[0] != n_symbols) { set_error("runs hold %llu symbols, header says %llu", (unsigned long long)tot[0], (unsigned long long)n_symbols); return PBSC_ERR_FORMAT; }
+    const uint64_t nd = tot[1];
+    PBSC_CUDA(cudaMalloc((void**)&idx->d_blocks[which], nb * sizeof(FmBlock)));
+    PBSC_CUDA(cudaMemset(idx->d_blocks[which], 0, nb * sizeof(FmBlock)));
+    PBSC_CUDA(cudaMalloc((void**)&idx->d_dollar[which], (nd + 1) * sizeof(uint32_t)));
+    PBSC_CUDA(cudaMalloc((void**)&idx->d_dmask[which], nb * sizeof(uint64_t)));
+    PBSC_CUDA(cudaMemset(idx->d_dmask[which], 0, nb * sizeof(uint64_t)));
+    run_scatter_kernel<<<(unsigned)((n_runs + 255) / 256), 256>>>(d_runs.p, n_runs, start.p, dstart.p, n_symbols, idx->d_blocks[which], idx->d_dollar[which],
+                                                                  (unsigned long long*)idx->d_dmask[which], bad.p);
+    d_runs.release(); len.release(); dlen.release(); start.release(); dstart.release();
+    for (int c = 0; c < 4; c++) { PBSC_CUDA(cnt[c].alloc(nb)); PBSC_CUDA(cum[c].alloc(nb)); }
+    block_counts_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(idx->d_blocks[which], idx->d_dmask[which], nb, n_symbols, cnt[0].p, cnt[1].p, cnt[2].p, cnt[3].p);
+    uint64_t total[5] = {nd, 0, 0, 0, 0};
+    for (int c = 0; c < 4; c++)
+    {
+        size_t tb2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt[c].p, cum[c].p, (int)nb);
+        if (tb2 > tmp.n) PBSC_CUDA(tmp.alloc(tb2));
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb2, cnt[c].p, cum[c].p, (int)nb);
+        uint32_t lastc = 0, lastv = 0;
+        PBSC_CUDA(cudaMemcpy(&lastc, cum[c].p + nb - 1, 4, cudaMemcpyDeviceToHost));
+        PBSC_CUDA(cudaMemcpy(&lastv, cnt[c].p + nb - 1, 4, cudaMemcpyDeviceToHost));
+        total[c + 1] = (uint64_t)lastc + lastv;
+    }
+    if (total[1] >= 0x80000000ull) { set_error("BWT has %llu 'A' symbols; this build supports < 2^31", (unsigned long long)total[1]); return PBSC_ERR_LIMIT; }
+    block_headers_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(idx->d_blocks[which], idx->d_dmask[which], cum[0].p, cum[1].p, cum[2].p, cum[3].p, nb);
+    PBSC_CUDA(cudaMemcpy(&hbad, bad.p, 4, cudaMemcpyDeviceToHost));
+    PBSC_CUDA(cudaDeviceSynchronize());
+    if (hbad) { set_error("runs hold more symbols than the header's %llu", (unsigned long long)n_symbols); return PBSC_ERR_FORMAT; }
+    if (total[0] + total[1] + total[2] + total[3] + total[4] != n_symbols) { set_error("decoded symbol counts do not add up to %llu", (unsigned long long)n_symbols); return PBSC_ERR_INTERNAL; }
+    idx->n_symbols[which] = n_symbols; idx->n_strings[which] = n_strings; idx->n_blocks[which] = nb;
+    idx->device_bytes += nb * (sizeof(FmBlock) + sizeof(uint64_t)) + (nd + 1) * sizeof(uint32_t);
+    fill_table(idx->dev.t[which], idx->d_blocks[which], idx->d_dollar[which], idx->d_dmask[which], n_symbols, total);
+    return PBSC_OK;
+}
+
 int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt_n_symbols, uint64_t bwt_n_strings,
                       const uint8_t* rbwt_runs, uint64_t rbwt_n_runs, uint64_t rbwt_n_symbols, uint64_t rbwt_n_strings,
                       int device, pbsc_index** out)
@@ -428,8 +561,11 @@ int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt
     int rc = PBSC_OK;
     const uint8_t* runs[2] = {bwt_runs, rbwt_runs};
     const uint64_t nr[2] = {bwt_n_runs, rbwt_n_runs}, ns[2] = {bwt_n_symbols, rbwt_n_symbols}, nstr[2] = {bwt_n_strings, rbwt_n_strings};
+    // PBSC_HOST_DECODE=1 keeps the sequential host decoder (the first implementation; the tests compare the two)
+    const bool host_decode = getenv("PBSC_HOST_DECODE") && atoi(getenv("PBSC_HOST_DECODE")) != 0;
     for (int w = 0; w < 2 && rc == PBSC_OK; w++)
     {
+        if (!host_decode) { rc = upload_strand_device(idx, w, runs[w], nr[w], ns[w], nstr[w]); continue; }
         std::vector<FmBlock> blocks;
         std::vector<uint32_t> dollars;
         uint64_t total[5];

@@ -110,6 +110,12 @@ static int batch_run_impl(pbsc_batch* bt, float* ms)
     rc = alloc_seed_workspace(&bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
     if (rc == PBSC_OK) rc = alloc_extend_workspace(idx, &bt->params, bt->h_offsets, bt->b, bt->s, bt->w, st);
     if (rc != PBSC_OK) return rc;
+    if (bt->params.debug_seed)
+    {
+        // --debugseed: the repeat ratio of every position and the failed walks of every read are kept for pbsc_batch_fetch_debug
+        PBSC_CUDA(bt->w.dbg_ratio.alloc(bt->b.n_bases)); PBSC_CUDA(bt->w.dbg_log.alloc(bt->s.total_slots)); PBSC_CUDA(bt->w.dbg_log_n.alloc(bt->b.n_reads));
+        PBSC_CUDA(cudaMemsetAsync(bt->w.dbg_log_n.p, 0, (bt->b.n_reads ? bt->b.n_reads : 1) * 4, st));
+    }
     // what only the kernels need goes back to the block cache on every way out; the results (pieces, bounds, counters) stay
     struct Scratch
     {
@@ -119,7 +125,7 @@ static int batch_run_impl(pbsc_batch* bt, float* ms)
             Workspace& w = bt->w; SeedBuffers& s = bt->s;
             w.feats.release(); w.cls.release(); w.attr.release(); w.ntriv.release(); w.prefix.release(); w.cand.release(); w.seed_tmp.release();
             w.scratch.release(); w.order.release();
-            s.seeds.release(); s.region.release(); s.count.release(); s.outcast.release();
+            if (!bt->params.debug_seed) { s.seeds.release(); s.region.release(); s.count.release(); s.outcast.release(); }
         }
     } scratch_guard{bt};
     bool grew = false;
@@ -350,6 +356,70 @@ int pbsc_batch_fetch(pbsc_batch* bt, char* pieces_out, uint64_t pieces_cap, uint
                      uint64_t* first_piece, pbsc_read_stats* stats)
 {
     return guarded("pbsc_batch_fetch", [&] { return fetch_impl(bt, pieces_out, pieces_cap, piece_offsets, piece_offsets_cap, first_piece, stats); });
+}
+
+int pbsc_batch_debug_size(pbsc_batch* bt, uint64_t* n_seeds, uint64_t* n_log)
+{
+    if (!bt || !bt->ran || !bt->params.debug_seed) { set_error("pbsc_batch_debug_size: the batch has not run with params.debug_seed set"); return PBSC_ERR_ARG; }
+    return guarded("pbsc_batch_debug_size", [&] {
+        PBSC_CUDA(cudaSetDevice(bt->idx->device));
+        const uint64_t n = bt->b.n_reads;
+        std::vector<uint32_t> a(n), b(n), c(n);
+        if (n)
+        {
+            PBSC_CUDA(cudaMemcpy(a.data(), bt->s.count.p, n * 4, cudaMemcpyDeviceToHost));
+            PBSC_CUDA(cudaMemcpy(b.data(), bt->s.outcast.p, n * 4, cudaMemcpyDeviceToHost));
+            PBSC_CUDA(cudaMemcpy(c.data(), bt->w.dbg_log_n.p, n * 4, cudaMemcpyDeviceToHost));
+        }
+        uint64_t ns = 0, nl = 0;
+        for (uint64_t r = 0; r < n; r++) { ns += (uint64_t)a[r] + b[r]; nl += c[r]; }
+        if (n_seeds) *n_seeds = ns;
+        if (n_log) *n_log = nl;
+        return PBSC_OK;
+    });
+}
+
+int pbsc_batch_fetch_debug(pbsc_batch* bt, pbsc_seed* seeds, uint64_t seeds_cap, uint64_t* seed_offsets, uint32_t* n_surviving, float* ratio,
+                           uint64_t ratio_cap, pbsc_walk_log* log, uint64_t log_cap, uint64_t* log_offsets)
+{
+    if (!bt || !bt->ran || !bt->params.debug_seed || !seed_offsets || !n_surviving || !log_offsets)
+    { set_error("pbsc_batch_fetch_debug: bad argument, or the batch has not run with params.debug_seed set"); return PBSC_ERR_ARG; }
+    return guarded("pbsc_batch_fetch_debug", [&] {
+        PBSC_CUDA(cudaSetDevice(bt->idx->device));
+        const uint64_t n = bt->b.n_reads;
+        std::vector<uint32_t> cnt(n), outc(n), nlog(n);
+        std::vector<uint64_t> region(n + 1, 0);
+        if (n)
+        {
+            PBSC_CUDA(cudaMemcpy(cnt.data(), bt->s.count.p, n * 4, cudaMemcpyDeviceToHost));
+            PBSC_CUDA(cudaMemcpy(outc.data(), bt->s.outcast.p, n * 4, cudaMemcpyDeviceToHost));
+            PBSC_CUDA(cudaMemcpy(nlog.data(), bt->w.dbg_log_n.p, n * 4, cudaMemcpyDeviceToHost));
+            PBSC_CUDA(cudaMemcpy(region.data(), bt->s.region.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
+        }
+        seed_offsets[0] = 0; log_offsets[0] = 0;
+        for (uint64_t r = 0; r < n; r++)
+        {
+            n_surviving[r] = cnt[r];
+            seed_offsets[r + 1] = seed_offsets[r] + cnt[r] + outc[r];
+            log_offsets[r + 1] = log_offsets[r] + nlog[r];
+        }
+        if (seed_offsets[n] > seeds_cap || log_offsets[n] > log_cap || bt->b.n_bases > ratio_cap || (!seeds && seed_offsets[n]) || (!log && log_offsets[n]) || (!ratio && bt->b.n_bases))
+        { set_error("pbsc_batch_fetch_debug: needs %llu seeds, %llu log records, %llu ratios", (unsigned long long)seed_offsets[n], (unsigned long long)log_offsets[n], (unsigned long long)bt->b.n_bases); return PBSC_ERR_LIMIT; }
+        std::vector<pbsc_seed> all(bt->s.total_slots);
+        std::vector<pbsc_walk_log> lg(bt->s.total_slots);
+        if (bt->s.total_slots)
+        {
+            PBSC_CUDA(cudaMemcpy(all.data(), bt->s.seeds.p, bt->s.total_slots * sizeof(pbsc_seed), cudaMemcpyDeviceToHost));
+            PBSC_CUDA(cudaMemcpy(lg.data(), bt->w.dbg_log.p, bt->s.total_slots * sizeof(pbsc_walk_log), cudaMemcpyDeviceToHost));
+        }
+        for (uint64_t r = 0; r < n; r++)
+        {
+            for (uint32_t i = 0; i < cnt[r] + outc[r]; i++) seeds[seed_offsets[r] + i] = all[region[r] + i];
+            for (uint32_t i = 0; i < nlog[r]; i++) log[log_offsets[r] + i] = lg[region[r] + i];
+        }
+        if (bt->b.n_bases) PBSC_CUDA(cudaMemcpy(ratio, bt->w.dbg_ratio.p, bt->b.n_bases * sizeof(float), cudaMemcpyDeviceToHost));
+        return PBSC_OK;
+    });
 }
 
 void pbsc_batch_destroy(pbsc_batch* bt)

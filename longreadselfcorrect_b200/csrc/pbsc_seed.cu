@@ -179,7 +179,7 @@ seed_prefix_kernel(const uint64_t* __restrict__ offsets, uint64_t n_reads, const
 // (2) thread per position: box counts of the +-150 window from the running counts, then the 2 % repeat-ratio rule
 __global__ void __launch_bounds__(256)
 seed_attr_kernel(SeedParamsDev P, const uint64_t* __restrict__ offsets, uint64_t n_reads, uint64_t n_bases, const uint4* __restrict__ pre,
-                 uint8_t* __restrict__ attr)
+                 uint8_t* __restrict__ attr, float* __restrict__ ratio_out)
 {
     const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (g >= n_bases) return;
@@ -198,6 +198,7 @@ seed_attr_kernel(SeedParamsDev P, const uint64_t* __restrict__ offsets, uint64_t
     const int boxN = (int)in.x - (int)outN, box2 = (int)in.y - (int)out2;
     const int size = (right - left + 1) - boxN;
     const float ratio = (float)((double)__fdiv_rn((float)box2, (float)size) + 0.0005);
+    if (ratio_out) ratio_out[g] = ratio;   // --debugseed: extend/<id>.log (LongReadProbe.cpp:172-173)
     uint8_t a = ((double)ratio >= 0.02) ? 2 : 1;
     if (P.manual) a = (uint8_t)P.mode;
     attr[g] = a;
@@ -524,7 +525,7 @@ int run_seed_phase(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, SeedBu
         const unsigned warp_blocks = (unsigned)((b.n_reads * 32 + 127) / 128);
         const unsigned base_blocks = (unsigned)((b.n_bases + 255) / 256);
         seed_prefix_kernel<<<warp_blocks, 128, 0, st>>>(b.offsets.p, b.n_reads, w.cls.p, (uint4*)w.prefix.p);
-        seed_attr_kernel<<<base_blocks, 256, 0, st>>>(P, b.offsets.p, b.n_reads, b.n_bases, (const uint4*)w.prefix.p, w.attr.p);
+        seed_attr_kernel<<<base_blocks, 256, 0, st>>>(P, b.offsets.p, b.n_reads, b.n_bases, (const uint4*)w.prefix.p, w.attr.p, w.dbg_ratio.p);
         seed_candidates_kernel<<<base_blocks, 256, 0, st>>>(idx->dev, P, b.codes.p, b.offsets.p, b.n_reads, b.n_bases, w.feats.p, w.attr.p,
                                                             (SeedCand*)w.cand.p, w.ntriv.p);
         seed_chain_kernel<<<warp_blocks, 128, 0, st>>>(P, b.offsets.p, b.n_reads, (const SeedCand*)w.cand.p, w.ntriv.p, w.seed_tmp.p, s.region.p, s.count.p);

@@ -60,5 +60,44 @@ def main():
     json.dump(out, open(os.path.join(HERE, "tiny.options.json"), "w"), indent=1)
 
 
+
+
+def debug_dump_digest(outdir, ids):
+    """sha256 per dump-file class of a --debugseed run: the files of all reads concatenated in read order, each preceded by
+    '#<id>\\n', or '#<id> missing\\n' when the reference did not create it."""
+    res = {}
+    for cls, pat in (("seed", "seed/%s.seed"), ("seed_error", "seed/error/%s.seed"), ("log", "extend/%s.log"), ("ext", "extend/%s.ext"), ("dp", "extend/%s.dp")):
+        h = hashlib.sha256()
+        n = 0
+        for rid in ids:
+            p = os.path.join(outdir, pat % rid)
+            if os.path.exists(p):
+                h.update(b"#" + rid.encode() + b"\n")
+                h.update(open(p, "rb").read())
+                n += 1
+            else:
+                h.update(b"#" + rid.encode() + b" missing\n")
+        res[cls] = {"sha256": h.hexdigest(), "files": n}
+    return res
+
+
+def debugseed_goldens():
+    """tests/golden/tiny.debugseed.json: the dump files of `stride pbcorrect --debugseed` with and without --nodp."""
+    reads = read_fasta(os.path.join(HERE, "tiny.reads.fa"))
+    ids = [r for r, _ in reads]
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, opts in (("nodp", ["-c", "30", "-g", "5", "--nodp"]), ("default", ["-c", "30", "-g", "5"])):
+            o = os.path.join(d, name)
+            subprocess.run([STRIDE, "pbcorrect", "-t", "1", "-p", os.path.join(HERE, "tiny"), "-o", o, "--debugseed"] + opts + [os.path.join(HERE, "tiny.reads.fa")],
+                           check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            out[name] = {"options": opts + ["--debugseed"], "dumps": debug_dump_digest(o + "/", ids)}
+            print(name, {k: (v["files"], v["sha256"][:12]) for k, v in out[name]["dumps"].items()}, flush=True)
+    json.dump(out, open(os.path.join(HERE, "tiny.debugseed.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "debugseed":
+        debugseed_goldens()
+    else:
+        main()

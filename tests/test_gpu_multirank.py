@@ -29,7 +29,7 @@ def _run_bench(world, extra=()):
     base = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "mini", "--gpus", str(world), "--steps", "1", "--warmup", "1", "--e2e-steps", "1",
             "--no-extras", "--no-cpu-baseline", "--batch-mbp", "1.0"] + list(extra)
     if world == 1:
-        r = subprocess.run(base, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        r = subprocess.run(base, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
         assert r.returncode == 0, r.stderr[-1500:]
         return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     port = _free_port()
@@ -42,7 +42,17 @@ def _run_bench(world, extra=()):
             env["PBSC_BENCH_SAME_DEVICE"] = "1"
             cmd += ["--backend", "gloo"]
         procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    outs = [p.communicate(timeout=900) for p in procs]
+    # a rank that dies leaves the others waiting in a collective: watch all of them, kill the rest as soon as one fails
+    import time
+    t0 = time.time()
+    while any(p.poll() is None for p in procs):
+        if any(p.poll() not in (None, 0) for p in procs) or time.time() - t0 > 420:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            break
+        time.sleep(0.5)
+    outs = [p.communicate() for p in procs]
     assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
     return json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][-1])
 

@@ -239,3 +239,62 @@ def test_cli_fmg_and_multi_gpu_give_the_same_files(golden, tmp_path):
         assert f"from {source}" in r.stderr, r.stderr[-800:]
         assert open(out / "correct.fa", "rb").read() == want_c and open(out / "discard.fa", "rb").read() == want_d, name
     assert os.path.exists(tmp_path / "t.fmg")
+
+
+def test_device_and_host_run_length_decoders_agree(api, golden, tmp_path, monkeypatch):
+    """The index is decoded from the reference's run bytes on the device (default) or by the sequential host loop
+    (PBSC_HOST_DECODE=1): same symbols, same '$' handling, same intervals; malformed run bytes are a format error."""
+    res = []
+    for host in ("0", "1"):
+        monkeypatch.setenv("PBSC_HOST_DECODE", host)
+        idx = api.Index.load(os.path.join(golden, "tiny"))
+        n = idx.num_symbols(api.PBSC_RBWT)
+        res.append((idx.symbols(api.PBSC_BWT, 0, idx.num_symbols(api.PBSC_BWT)), idx.symbols(api.PBSC_RBWT, 0, n), _intervals(api, idx, golden), idx.device_bytes()))
+        idx.close()
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1] and res[0][3] == res[1][3]
+    assert b"$" in res[0][0]
+    for (lo, hi), (lo2, hi2) in zip(res[0][2], res[1][2]):
+        assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
+    monkeypatch.setenv("PBSC_HOST_DECODE", "0")
+    raw = bytearray(open(os.path.join(golden, "tiny.bwt"), "rb").read())
+    for ext in ("rbwt", "sai"):
+        open(tmp_path / f"t.{ext}", "wb").write(open(os.path.join(golden, f"tiny.{ext}"), "rb").read())
+    for bad_byte in (0xE3, 0x40):     # symbol rank 7; run of length 0
+        b = bytearray(raw)
+        b[30 + 1000] = bad_byte
+        open(tmp_path / "t.bwt", "wb").write(b)
+        with pytest.raises(api.PbscError) as e:
+            api.Index.load(str(tmp_path / "t"))
+        assert e.value.code == -3
+
+
+@pytest.mark.parametrize("mode", ["nodp", "default"])
+def test_cli_debugseed_dumps_equal_the_reference(golden, tmp_path, mode):
+    """`pbcorrect --debugseed`: seed/<id>.seed, seed/error/<id>.seed, extend/<id>.log, .ext and .dp of every read, byte for byte
+    what the reference writes (sha256 per file class over all reads, tests/golden/tiny.debugseed.json); the committed
+    tiny.seeds.tsv / tiny.ext.tsv fixtures are the same dumps in clear text."""
+    import importlib.util
+    import json
+    import subprocess
+    from conftest import ROOT
+    g = json.load(open(os.path.join(golden, "tiny.debugseed.json")))[mode]
+    spec = importlib.util.spec_from_file_location("mog", os.path.join(ROOT, "tests", "golden", "make_option_golden.py"))
+    mog = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mog)
+    exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
+    out = tmp_path / "out"
+    r = subprocess.run([exe, "pbcorrect", "-t", "2", "-p", os.path.join(golden, "tiny"), "-o", str(out), "--batch-mbp", "0.2"] + g["options"]
+                       + [os.path.join(golden, "tiny.reads.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    ids = [rid for rid, _ in read_fasta(os.path.join(golden, "tiny.reads.fa"))]
+    got = mog.debug_dump_digest(str(out) + "/", ids)
+    for cls in ("seed", "seed_error", "ext", "dp", "log"):
+        assert got[cls] == g["dumps"][cls], cls
+    if mode == "nodp":
+        # clear-text fixtures of round 1
+        seeds = "".join(f"#{i}\n" + open(out / "seed" / f"{i}.seed").read() for i in ids)
+        assert seeds == open(os.path.join(golden, "tiny.seeds.tsv")).read()
+        ext = "".join(f"#{i}\n" + (open(out / "extend" / f"{i}.ext").read() if os.path.exists(out / "extend" / f"{i}.ext") else "") for i in ids)
+        assert ext == open(os.path.join(golden, "tiny.ext.tsv")).read()
+    name = "tiny" if mode == "nodp" else "tiny.dp"
+    assert open(out / "correct.fa").read() == open(os.path.join(golden, f"{name}.correct.fa")).read()
