@@ -554,7 +554,7 @@ def ours(args, wl, metric):
     if world == 1:
         extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank)
     else:
-        line["roofline"] = roofline_from_committed(args, ph, walks, total_mbp)
+        line["roofline"] = roofline_from_committed(args, ph, walks * shard.bases / max(1.0, total_mbp * 1e6), total_mbp)
         line["cpu_baseline"] = None
     print(json.dumps(line))
     shutil.rmtree(shm, ignore_errors=True)
@@ -613,7 +613,7 @@ def roofline_from_committed(args, ph, walks, total_mbp):
     try:
         c = json.load(open(os.path.join(ROOT, "profiles", "algorithmic.json"))).get(args.workload + ("_nodp" if args.nodp else ""))
         if c and c.get("walk_loop_rank_queries_per_walk") and ph["walk_ms"] > 0:
-            b = c["walk_loop_rank_queries_per_walk"] * ph["seed_pairs"] * 32.0
+            b = c["walk_loop_rank_queries_per_walk"] * walks * 32.0      # `walks`: the reference's walks of rank 0's share of the reads
             roof["achieved"] = b / (ph["walk_ms"] / 1000) / 1e9
             roof["frac"] = roof["achieved"] / peak
     except Exception:

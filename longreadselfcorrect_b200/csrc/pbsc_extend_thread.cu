@@ -32,7 +32,7 @@ struct ReadState
     uint64_t plen;
     int32_t pending_trg;   // seed index the pending request targets
     int32_t srcFreq;       // source.maxFixedMerFreq
-    int32_t srcStart;      // source.seedStartPos: where the current piece began in the raw read
+    int32_t srcStart;      // source.seedStartPos: SeedFeature::append takes it from the target (SeedFeature.h:22-33)
     uint32_t nLog;         // --debugseed: failed walks logged so far
     // DP fallback result of the current target's first (next == 0) walk, kept while the look-ahead walks run
     int32_t dpStatus0;
@@ -245,13 +245,12 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
     // lanes 0 .. owners-1 of every warp take walks (and own scratch); the others only work in the pooled stages
     const bool owner = (int)(threadIdx.x & 31) < owners;
     const size_t tid = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (size_t)owners + (threadIdx.x & 31);
-    __shared__ tw::LaneCtx ctx_all[TW_BLOCK];
-    tw::LaneCtx* ctx = ctx_all + (threadIdx.x & ~31u);    // this warp's 32 records
-    tw::LaneCtx& mine = ctx[threadIdx.x & 31];
-    tw::TScratch lane;
-    tw::carve(scratch + (owner ? tid : 0) * stride, P.node_cap, caps, lane);
+    __shared__ tw::Lane lanes_all[TW_BLOCK];
+    tw::Lane* ctx = lanes_all + (threadIdx.x & ~31u);    // this warp's 32 records
+    tw::Lane& S = ctx[threadIdx.x & 31];
+    const tw::Layout Y = tw::make_layout(P.node_cap, caps);
+    uint8_t* const my_scratch = scratch + (owner ? tid : 0) * stride;
     if (n_items_dev) n_items = *n_items_dev;      // a later pass: its item count was produced on the device
-    tw::State S;
     S.status = 0; S.n = 0;
     WalkTask* tk = nullptr;
     tw::SetupHdr* hdr = nullptr;
@@ -271,7 +270,7 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
             if (ended)
             {
                 uint32_t mlen = 0;
-                int st = tw::finish_walk(S, hdr, nodepool, pool_used, pool_cap, last_pass != 0, outpool + tk->out_off, tk->out_cap, &mlen);
+                int st = tw::finish_walk(S, Y, P, hdr, nodepool, pool_used, pool_cap, last_pass != 0, outpool + tk->out_off, tk->out_cap, &mlen);
                 // the last pass carries everything the reference's loop can hold (-l leaves, 4 children each); only the
                 // label tree and the result list are bounded, and running out of those is reported, not hidden
                 if (st == PBSC_WALK_HEAVY && last_pass) st = PBSC_OVF_TREE;
@@ -293,7 +292,7 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
                     task_shape(*tk, interval, trgLen, qlen);
                     tw::SetupView v;
                     tw::setup_view(task_record(ti, recpool, rec_off, pend_base, pend_cap), qlen, trgLen, P.min_overlap, P.seed_size, v);
-                    tw::begin_walk(S, idx, P, lane, v, P.node_cap, caps, minSA);
+                    tw::begin_walk(S, Y, P, my_scratch, v, minSA);
                     hdr = v.hdr;
                     active = true;
                     done++;
@@ -304,40 +303,38 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
         if (__all_sync(FULL, !active)) break;   // only reached with nobody waiting either: every lane is exhausted
         // ---- one level of extendOverlap's loop for every walking lane; the stages that touch the index or the per-walk
         //      tables are pooled over the warp (pbsc_walk_thread.cuh) ----
-        const bool lv = active && tw::walk_continues(S);
-        if (lv) tw::publish(mine, S);
+        const bool lv = active && tw::walk_continues(S, P);
         {
             const bool need = lv && tw::needs_refine(S);
-            tw::refine_pool(idx, ctx, need ? S.n : 0u);
+            tw::refine_pool(idx, Y, ctx, need ? S.n : 0u);
             if (need) S.curK = S.maxOverlap;
         }
         if (lv)
         {
-            double minErr;
-            tw::filter_leaves(S, minErr);
-            mine.minErr = minErr; mine.n = S.n; mine.thr = S.phase == 2 ? S.minSA - 1 : S.minSA;
+            tw::filter_leaves(S, Y);
+            S.thr = S.phase == 2 ? S.minSA - 1 : S.minSA;
         }
-        tw::pool_run(lv ? S.n : 0u, [&](int owner, uint32_t i) { tw::probe_leaf(idx, ctx[owner], i); });
+        tw::pool_run(lv ? S.n : 0u, [&](int owner_lane, uint32_t i) { tw::probe_leaf(idx, Y, ctx[owner_lane], i); });
         uint32_t m = 0, sel = 0;
         bool go = false;
         if (lv)
         {
-            m = tw::adopt_children(S);
-            if (S.status == 0) go = tw::level_middle(S, mine, m, sel);
-            if (go) { mine.curLen = (uint32_t)S.curLen; mine.level = S.level; }
+            m = tw::adopt_children(S, Y);
+            if (S.status == 0) go = tw::level_middle(S, Y, P, m, sel);
         }
         if (__any_sync(FULL, sel != 0))
         {
-            tw::pool_run(sel, [&](int owner, uint32_t i) { tw::select_leaf(idx, ctx[owner], i); });
-            if (sel) tw::level_select(S, mine);
-            tw::pool_run(sel, [&](int owner, uint32_t i) { tw::reselect_leaf(idx, ctx[owner], i); });
+            tw::pool_run(sel, [&](int owner_lane, uint32_t i) { tw::select_leaf(idx, Y, ctx[owner_lane], i); });
+            if (sel) tw::level_select(S, P);
+            tw::pool_run(sel, [&](int owner_lane, uint32_t i) { tw::reselect_leaf(idx, Y, ctx[owner_lane], i); });
         }
-        tw::pool_run(go ? m : 0u, [&](int owner, uint32_t j) { tw::prune_leaf(P, ctx[owner], j); });
+        // (prune_leaf reads the walk's curLen after curLen++ and its level before level++)
+        tw::pool_run(go ? m : 0u, [&](int owner_lane, uint32_t j) { tw::prune_leaf(P, Y, ctx[owner_lane], j); });
         bool check_term = false;
         if (go) { S.level++; check_term = S.curLen >= S.minLength; }
-        tw::pool_run(check_term ? m : 0u, [&](int owner, uint32_t j) { tw::term_leaf(ctx[owner], j); });
-        if (go) tw::finish_level(S, m, check_term);
-        if (active && !tw::walk_continues(S)) { active = false; ended = true; }
+        tw::pool_run(check_term ? m : 0u, [&](int owner_lane, uint32_t j) { tw::term_leaf(Y, ctx[owner_lane], j); });
+        if (go) tw::finish_level(S, Y, P, m, check_term);
+        if (active && !tw::walk_continues(S, P)) { active = false; ended = true; }
     }
     if (done) atomicAdd(walk_counter, done);
 }
@@ -522,7 +519,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                     S.st.fm_num++;
                     S.st.total_walk_num++;
                     S.srcLen += outLen;
-                    S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat; S.srcFreq = tg.max_fixed_freq;
+                    S.srcEnd = tg.start + tg.len - 1; S.srcStart = tg.start; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat; S.srcFreq = tg.max_fixed_freq;
                     S.t += S.next;
                     success = true;
                     break;
@@ -570,7 +567,6 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                         for (int x = 0; x < tg.len; x++) piece[S.plen + x] = read[tg.start + x];
                         S.plen += tg.len;
                         S.srcLen = tg.len;
-                        S.srcStart = tg.start;   // pieceVec.push_back(target): the next source is the target seed itself
                     }
                     else
                     {
@@ -583,7 +579,7 @@ stitch_kernel(StitchParams C, uint64_t n_reads, const uint8_t* __restrict__ code
                     }
                     S.st.corrected_len += tg.len;
                 }
-                S.srcEnd = tg.start + tg.len - 1; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat; S.srcFreq = tg.max_fixed_freq;
+                S.srcEnd = tg.start + tg.len - 1; S.srcStart = tg.start; S.srcEndBest = tg.end_best_k; S.srcRepeat = tg.is_repeat; S.srcFreq = tg.max_fixed_freq;
             }
             S.t++;
             S.next = 0;

@@ -31,24 +31,16 @@ namespace tw {
 struct Caps { uint32_t old_cap, new_cap, rings, res; };   // per-lane capacities of one pass of the thread engine (new_cap = 4 * old_cap)
 #define PBSC_WALK_HEAVY (-102)
 
-// Leaves live in two banks of new_cap slots each.  The live leaves of a level are the slots named by a list (`oldList`, n
-// entries); the children of the i-th listed leaf go to slots 4 i + b of the other bank (b = appended base), so any lane can
-// create them without knowing what the other leaves do.  Nothing is ever moved: a level ends by writing the list of the
-// surviving children and swapping the roles of the banks.
-struct TScratch
+// Leaves live in two banks of new_cap slots each.  The live leaves of a level are the slots named by a list (n entries); the
+// children of the i-th listed leaf go to slots 4 i + b of the other bank (b = appended base), so any lane can create them
+// without knowing what the other leaves do.  Nothing is ever moved: a level ends by writing the list of the surviving
+// children and flipping the roles of the banks.
+// Per-lane scratch (global memory), the same layout for every lane of a pass:
+struct Layout
 {
-    Leaf* oldL; Leaf* newL;
-    uint8_t* oldList; uint8_t* newList;
-    double* rings;
-    uint32_t* nodes;
-    WalkResult* res;
-    Interval* termF; Interval* termR;
-    uint8_t* q;
-    uint64_t* hash;
-    uint64_t* sF; uint64_t* sR;
-    uint16_t* start4;     // bucket starts of the query 4-mers (257 entries)
-    uint16_t* pos4;       // query positions grouped by 4-mer, ascending inside a bucket
-    uint8_t* ringStack;   // free ring slots
+    uint32_t bank1, rings, nodes, res, ringStack, list0, list1;   // byte offsets from the lane's base (bank 0 is at 0)
+    uint32_t node_cap;
+    Caps cap;
 };
 
 __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
@@ -56,7 +48,7 @@ __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; whil
 __host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap, Caps c)
 {
     size_t b = 0;
-    b += sizeof(Leaf) * (size_t)(2 * c.new_cap);   // two banks of the same size: the level loop swaps them instead of copying
+    b += sizeof(Leaf) * (size_t)(2 * c.new_cap);   // two banks of the same size: the level loop flips them instead of copying
     b += sizeof(double) * (size_t)c.rings * RING_LEN;
     b += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
     b += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
@@ -65,19 +57,51 @@ __host__ __device__ inline size_t thread_scratch_bytes(uint32_t node_cap, Caps c
     return align_up(b, 128);
 }
 
-__device__ inline void carve(uint8_t* base, uint32_t node_cap, Caps c, TScratch& w)
+__host__ __device__ inline Layout make_layout(uint32_t node_cap, Caps c)
 {
-    uint8_t* p = base;
-    w.oldL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.new_cap;
-    w.newL = (Leaf*)p; p += sizeof(Leaf) * (size_t)c.new_cap;
-    w.rings = (double*)p; p += sizeof(double) * (size_t)c.rings * RING_LEN;
-    w.nodes = (uint32_t*)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
-    w.res = (WalkResult*)p; p += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
-    w.ringStack = p; p += align_up(c.rings, 16);
-    w.oldList = p; p += align_up(c.new_cap, 16);
-    w.newList = p;
-    w.termF = w.termR = nullptr; w.q = nullptr; w.hash = w.sF = w.sR = nullptr; w.start4 = w.pos4 = nullptr;
+    Layout y;
+    size_t p = sizeof(Leaf) * (size_t)c.new_cap;
+    y.bank1 = (uint32_t)p; p += sizeof(Leaf) * (size_t)c.new_cap;
+    y.rings = (uint32_t)p; p += sizeof(double) * (size_t)c.rings * RING_LEN;
+    y.nodes = (uint32_t)p; p += align_up(sizeof(uint32_t) * (size_t)node_cap, 16);
+    y.res = (uint32_t)p; p += align_up(sizeof(WalkResult) * (size_t)c.res, 16);
+    y.ringStack = (uint32_t)p; p += align_up(c.rings, 16);
+    y.list0 = (uint32_t)p; p += align_up(c.new_cap, 16);
+    y.list1 = (uint32_t)p;
+    y.node_cap = node_cap; y.cap = c;
+    return y;
 }
+
+// Everything a walk carries from level to level besides its leaves: ONE record per lane in shared memory.  It used to be a
+// 576-byte struct on the thread's stack (local memory): with 768 walks per SM that is 440 KB against ~90 KB of L1, so nine in
+// ten accesses to it went to L2 and, L2 being thrashed by the leaf banks, often to DRAM (ncu, profiles/r2_walk_levels_cfg2_*:
+// 12.9 G of the kernel's 60 G L2 sector transactions were local memory, L1 hit rate 10 %).  In shared memory it is also what
+// the OTHER lanes of the warp read when the pooled stages give them one of this walk's leaves.
+struct __align__(16) Lane
+{
+    uint8_t* base;                                   // this lane's scratch (Layout)
+    const uint16_t* start4; const uint16_t* pos4; const uint8_t* q;   // the walk's setup record
+    const uint64_t* hash; const uint64_t* sF; const uint64_t* sR;
+    const Interval* termF; const Interval* termR;
+    double minErr;
+    uint32_t curLen, curK, maxLength, minLength, maxIndel, minSA, thr;
+    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, nFresh, phase, n;
+    // SelectFreqsOfrange / refineSAInterval behind it (pooled): the k-mer range, the per-size maxima, which bank
+    uint32_t selLB, selExtra, selK;
+    int selMx[3];
+    int status;
+    uint8_t dup, flip, selNew, pad;
+};
+static_assert(sizeof(Lane) == 208, "Lane: 208 bytes of shared memory per thread");
+
+__device__ __forceinline__ Leaf* old_bank(const Lane& s, const Layout& y) { return (Leaf*)(s.base + (s.flip ? y.bank1 : 0u)); }
+__device__ __forceinline__ Leaf* new_bank(const Lane& s, const Layout& y) { return (Leaf*)(s.base + (s.flip ? 0u : y.bank1)); }
+__device__ __forceinline__ uint8_t* old_list(const Lane& s, const Layout& y) { return s.base + (s.flip ? y.list1 : y.list0); }
+__device__ __forceinline__ uint8_t* new_list(const Lane& s, const Layout& y) { return s.base + (s.flip ? y.list0 : y.list1); }
+__device__ __forceinline__ double* rings_of(const Lane& s, const Layout& y) { return (double*)(s.base + y.rings); }
+__device__ __forceinline__ uint32_t* nodes_of(const Lane& s, const Layout& y) { return (uint32_t*)(s.base + y.nodes); }
+__device__ __forceinline__ WalkResult* res_of(const Lane& s, const Layout& y) { return (WalkResult*)(s.base + y.res); }
+__device__ __forceinline__ uint8_t* ring_stack(const Lane& s, const Layout& y) { return s.base + y.ringStack; }
 
 static __device__ __noinline__ Interval update1(const FmTable& t, Interval iv, int c) { return update_interval(t, iv, c); }
 // one copy of occ4 for the four probes of a leaf: the level loop is bound by instruction fetch (ncu: the GPC instruction cache
@@ -122,49 +146,6 @@ __device__ __forceinline__ void both_strands(const FmIndexDev& idx, Get get, int
     }
 }
 
-struct State
-{
-    const FmIndexDev* idx;
-    const ExtParamsDev* P;
-    TScratch s;
-    uint32_t n;
-    uint64_t curLen, curK, maxLength, minLength, maxIndel, minSA;
-    uint32_t qlen, k, maxOverlap, trgLen, nTerm, n9F, n9R, n5, nNodes, nRes, level, hashMask, nFree, nFresh, node_cap, phase;
-    Caps cap;
-    bool dup;
-    int status;
-};
-
-// What the OTHER lanes of the warp need to know about a lane's walk to work on its leaves: every stage of a level that
-// touches the index or the per-walk tables is pooled over the warp (the leaves of all 32 walks are dealt out one per lane
-// per round), so a walk with 30 live leaves no longer holds 31 lanes for 30 rounds of dependent loads, and the longest
-// walk of a small round (re-walks, the full-capacity pass) advances 32 leaves at a time.  One record per lane in shared
-// memory, rewritten by its owner before every pooled stage.
-struct __align__(16) LaneCtx
-{
-    Leaf* oldL; Leaf* newL;
-    const uint8_t* oldList; const uint8_t* newList;
-    double* rings;
-    const uint16_t* start4; const uint16_t* pos4; const uint8_t* q;
-    const uint64_t* hash; const uint64_t* sF; const uint64_t* sR;
-    const Interval* termF; const Interval* termR;
-    double minErr;
-    uint64_t thr;
-    uint32_t curLen, maxIndel, n5, qlen, hashMask, n9F, n9R, nTerm, level, n, K, dup;
-    // SelectFreqsOfrange / refineSAInterval behind it (pooled): which leaves, the k-mer range, the per-size maxima
-    Leaf* selBank; const uint8_t* selList;
-    uint32_t selLB, selExtra, selK;
-    int selMx[3];
-};
-
-__device__ __forceinline__ void publish(LaneCtx& c, const State& S)
-{
-    c.oldL = S.s.oldL; c.newL = S.s.newL; c.oldList = S.s.oldList; c.newList = S.s.newList; c.rings = S.s.rings;
-    c.start4 = S.s.start4; c.pos4 = S.s.pos4; c.q = S.s.q; c.hash = S.s.hash; c.sF = S.s.sF; c.sR = S.s.sR; c.termF = S.s.termF; c.termR = S.s.termR;
-    c.curLen = (uint32_t)S.curLen; c.maxIndel = (uint32_t)S.maxIndel; c.n5 = S.n5; c.qlen = S.qlen; c.hashMask = S.hashMask; c.n9F = S.n9F; c.n9R = S.n9R;
-    c.nTerm = S.nTerm; c.level = S.level; c.n = S.n; c.K = S.maxOverlap; c.dup = S.dup ? 1u : 0u;
-}
-
 // Deal `cnt` items of every lane out over the warp: f(owner lane, item index within the owner) runs once per item, 32 items
 // per round.  Must be called by all 32 lanes converged (cnt may be 0).
 template <class F>
@@ -201,104 +182,35 @@ __device__ __forceinline__ void pool_run(uint32_t cnt, F f)
     __syncwarp();
 }
 
-__device__ __forceinline__ void ring_release(State& S, uint32_t slot) { S.s.ringStack[S.nFree++] = (uint8_t)slot; }
+__device__ __forceinline__ void ring_release(Lane& S, const Layout& Y, uint32_t slot) { ring_stack(S, Y)[S.nFree++] = (uint8_t)slot; }
 // released slots first, then slots never used by this walk (slot 0 is the root's)
-__device__ __forceinline__ int ring_take(State& S)
+__device__ __forceinline__ int ring_take(Lane& S, const Layout& Y)
 {
-    if (S.nFree) return (int)S.s.ringStack[--S.nFree];
-    return S.nFresh < S.cap.rings ? (int)S.nFresh++ : -1;
-}
-
-// refineSAInterval (LongReadCorrectByOverlap.cpp:355-369) of the listed leaves of one walk, by its own lane (the rare path
-// behind SelectFreqsOfrange; the refinement that opens every level is pooled, refine_pool)
-static __device__ __noinline__ void refine(State& S, Leaf* bank, const uint8_t* list, uint32_t cnt, int K)
-{
-    #pragma unroll 1
-    for (uint32_t i = 0; i < cnt; i++)
-    {
-        Leaf& L = bank[list[i]];
-        const uint64_t hi = L.rt_hi, lo = L.rt_lo;
-        Interval f, r;
-        both_strands(*S.idx, [&](int j) { return tail_base(hi, lo, K - 1 - j); }, K, f, r);
-        L.f_lo = f.lo; L.f_hi = f.hi; L.r_lo = r.lo; L.r_hi = r.hi;
-    }
+    if (S.nFree) return (int)ring_stack(S, Y)[--S.nFree];
+    return S.nFresh < Y.cap.rings ? (int)S.nFresh++ : -1;
 }
 
 // refineSAInterval(maxOverlap) for a whole warp at once: every lane passes the number of leaves of its own walk that start
 // this level by cutting their k-mer back (0 if none)
-__device__ __forceinline__ void refine_pool(const FmIndexDev& idx, const LaneCtx* ctx, uint32_t cnt)
+__device__ __forceinline__ void refine_pool(const FmIndexDev& idx, const Layout& Y, const Lane* ctx, uint32_t cnt)
 {
     pool_run(cnt, [&](int owner, uint32_t i) {
-        const LaneCtx& c = ctx[owner];
-        Leaf* L = c.oldL + c.oldList[i];
+        const Lane& c = ctx[owner];
+        Leaf* L = old_bank(c, Y) + old_list(c, Y)[i];
         const uint64_t rhi = L->rt_hi, rlo = L->rt_lo;
-        const int K = (int)c.K;
+        const int K = (int)c.maxOverlap;
         Interval f, r;
         both_strands(idx, [&](int j) { return tail_base(rhi, rlo, K - 1 - j); }, K, f, r);
         L->f_lo = f.lo; L->f_hi = f.hi; L->r_lo = r.lo; L->r_hi = r.hi;
     });
 }
 
-// SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331)
-static __device__ __noinline__ uint64_t select_freqs(State& S, Leaf* bank, const uint8_t* list, uint32_t cnt, uint64_t LB, uint64_t UB)
-{
-    const FmIndexDev& idx = *S.idx;
-    const int extra = (int)(UB - LB);
-    int mx[3] = {0, 0, 0};
-    #pragma unroll 1
-    for (uint32_t i = 0; i < cnt; i++)
-    {
-        const Leaf& L = bank[list[i]];
-        const uint64_t hi = L.rt_hi, lo = L.rt_lo;
-        // Fwdinterval = findInterval(BWT, startkmer): newest base first; Rvcinterval = findInterval(RBWT, complement(startkmer))
-        Interval a, b;   // a on BWT, b on RBWT
-        int d;
-        if (idx.prefix != nullptr && (int)LB >= idx.k0)
-        {
-            uint64_t key = 0;
-            #pragma unroll 1
-            for (int j = 0; j < idx.k0; j++) key |= (uint64_t)(3 - tail_base(hi, lo, j)) << (2 * j);
-            Interval f, r;
-            prefix_lookup(idx, key, f, r);
-            a = r; b = f;
-            d = idx.k0;
-        }
-        else
-        {
-            const int c = tail_base(hi, lo, 0);
-            a = init_interval(idx.t[PBSC_BWT], c);
-            b = init_interval(idx.t[PBSC_RBWT], 3 - c);
-            d = 1;
-        }
-        #pragma unroll 1
-        for (; d < (int)LB && (a.valid() || b.valid()); d++)
-        {
-            const int c = tail_base(hi, lo, d);
-            if (a.valid()) a = update1(idx.t[PBSC_BWT], a, c);
-            if (b.valid()) b = update1(idx.t[PBSC_RBWT], b, 3 - c);
-        }
-        mx[0] = max(mx[0], (int)((int64_t)a.size() + (int64_t)b.size()));
-        #pragma unroll 1
-        for (int e = 1; e <= extra; e++)
-        {
-            const int c = tail_base(hi, lo, (int)LB - 1 + e);
-            if (a.valid()) a = update1(idx.t[PBSC_BWT], a, c);
-            if (b.valid()) b = update1(idx.t[PBSC_RBWT], b, 3 - c);
-            mx[e] = max(mx[e], (int)((int64_t)a.size() + (int64_t)b.size()));
-        }
-    }
-    if (mx[0] - S.P->freq_int[LB] < 5) return LB;
-    #pragma unroll 1
-    for (int e = 1; e <= extra; e++) if (mx[e] - S.P->freq_int[LB + e] < 5) return LB + e;
-    return UB;
-}
-
 // isInsufficientFreqs (LongReadCorrectByOverlap.cpp:334-352)
-__device__ __forceinline__ bool insufficient(const State& S, const Leaf* bank, const uint8_t* list, uint32_t cnt)
+__device__ __forceinline__ bool insufficient(const ExtParamsDev& P, const Leaf* bank, const uint8_t* list, uint32_t cnt)
 {
     uint32_t high = 0;
     #pragma unroll 1
-    for (uint32_t j = 0; j < cnt; j++) high += bank[list[j]].kmerFreq > S.P->high_freq_thr;
+    for (uint32_t j = 0; j < cnt; j++) high += bank[list[j]].kmerFreq > P.high_freq_thr;
     if (high == 0) return true;
     if (high <= 2 && cnt >= 5) return true;
     if (high <= 1 && cnt >= 3) return true;
@@ -336,7 +248,7 @@ static __device__ __noinline__ uint32_t eval4(const int freq[4], uint64_t totalc
 
 // ismatchedbykmer (LongReadCorrectByOverlap.cpp:787-821) for the four probes of one leaf at once: bit b is set when the
 // query holds, starting within curLen +- maxIndel, the leaf's last four bases followed by base b
-__device__ __forceinline__ uint32_t match5_mask(const LaneCtx& c, uint32_t tail4)
+__device__ __forceinline__ uint32_t match5_mask(const Lane& c, uint32_t tail4)
 {
     const int64_t lo = max((int64_t)c.curLen - (int64_t)c.maxIndel, (int64_t)0);
     const int64_t hi = min((int64_t)c.curLen + (int64_t)c.maxIndel, (int64_t)c.n5 - 1);
@@ -353,10 +265,10 @@ __device__ __forceinline__ uint32_t match5_mask(const LaneCtx& c, uint32_t tail4
 
 // attempToExtend, first part (LongReadCorrectByOverlap.cpp:373-398), by the walk's own lane: drop the leaves whose local error
 // rate is far above the best one.  Only the list changes.
-static __device__ __noinline__ void filter_leaves(State& S, double& minErrOut)
+static __device__ __noinline__ void filter_leaves(Lane& S, const Layout& Y)
 {
-    Leaf* oldL = S.s.oldL;
-    uint8_t* list = S.s.oldList;
+    Leaf* oldL = old_bank(S, Y);
+    uint8_t* list = old_list(S, Y);
     double minErr = 1.0;
     #pragma unroll 1
     for (uint32_t i = 0; i < S.n; i++) minErr = fmin(minErr, oldL[list[i]].local_err);
@@ -366,22 +278,22 @@ static __device__ __noinline__ void filter_leaves(State& S, double& minErrOut)
     {
         const Leaf& L = oldL[list[i]];
         const double diff = __dsub_rn(L.local_err, minErr);
-        const bool drop = (diff > 0.05 && S.curLen > (uint64_t)(RING_LEN / 2)) || (diff > 0.1 && S.curLen > 15);
-        if (drop) { ring_release(S, L.ring); continue; }
+        const bool drop = (diff > 0.05 && S.curLen > (uint32_t)(RING_LEN / 2)) || (diff > 0.1 && S.curLen > 15);
+        if (drop) { ring_release(S, Y, L.ring); continue; }
         if (w != i) list[w] = list[i];
         w++;
     }
     S.n = w;
-    minErrOut = minErr;
+    S.minErr = minErr;
 }
 
 // getFMIndexExtensions + the leaf part of updateLeaves (LongReadCorrectByOverlap.cpp:468-488, 667-784) for ONE leaf, by
 // whichever lane the pool gave it to: the eight one-base probes from four sectors, the acceptance rule, and the accepted
 // children written to slots 4 i + b of the other bank.  The accepted bases are left in the parent's `aux` for its owner,
 // who numbers the children and gives them their history rings (adopt_children).
-__device__ __forceinline__ void probe_leaf(const FmIndexDev& idx, const LaneCtx& c, uint32_t i)
+__device__ __forceinline__ void probe_leaf(const FmIndexDev& idx, const Layout& Y, const Lane& c, uint32_t i)
 {
-    Leaf* parent = c.oldL + c.oldList[i];
+    Leaf* parent = old_bank(c, Y) + old_list(c, Y)[i];
     uint64_t fl[4], fh[4], rl[4], rh[4];
     const uint64_t pf_lo = parent->f_lo, pf_hi = parent->f_hi, pr_lo = parent->r_lo, pr_hi = parent->r_hi;
     const bool fV = pf_hi > pf_lo, rV = pr_hi > pr_lo;
@@ -407,17 +319,18 @@ __device__ __forceinline__ void probe_leaf(const FmIndexDev& idx, const LaneCtx&
         if ((pf[b].valid() || pr[b].valid()) && ((near5 >> b) & 1)) match5 |= 1u << b;
     }
     const uint32_t p_tailCount = parent->tailCount;
-    uint32_t mask = eval4(freq, total, mx, match5, p_tailCount, c.thr);
-    if (!mask && parent->local_err == c.minErr && c.n > 1) mask = eval4(freq, total, mx, match5, p_tailCount, c.thr - 1);
+    uint32_t mask = eval4(freq, total, mx, match5, p_tailCount, (uint64_t)c.thr);
+    if (!mask && parent->local_err == c.minErr && c.n > 1) mask = eval4(freq, total, mx, match5, p_tailCount, (uint64_t)c.thr - 1);
     parent->aux = mask;
     if (!mask) return;
     const uint32_t p_tailLetter = parent->tailLetter;
     const uint64_t p_rt_lo = parent->rt_lo;
+    Leaf* newL = new_bank(c, Y);
     #pragma unroll 1
     for (int b = 0; b < 4; b++)
     {
         if (!((mask >> b) & 1)) continue;
-        Leaf* ch = c.newL + 4 * i + b;
+        Leaf* ch = newL + 4 * i + b;
         leaf_copy(ch, parent);
         ch->f_lo = pf[b].lo; ch->f_hi = pf[b].hi; ch->r_lo = pr[b].lo; ch->r_hi = pr[b].hi;
         ch->kmerFreq = freq[b];
@@ -434,18 +347,20 @@ __device__ __forceinline__ void probe_leaf(const FmIndexDev& idx, const LaneCtx&
 // FMIndexWalk/SAINode.cpp:166-189), by the walk's own lane: children are numbered in the reference's order (leaves in list
 // order, bases A..T), the first child of a leaf inherits its history ring, the others get a copy.  Returns the number of
 // children and writes their slots to the child list.
-static __device__ __noinline__ uint32_t adopt_children(State& S)
+static __device__ __noinline__ uint32_t adopt_children(Lane& S, const Layout& Y)
 {
-    Leaf* oldL = S.s.oldL;
-    Leaf* newL = S.s.newL;
-    const uint8_t* list = S.s.oldList;
-    uint8_t* cl = S.s.newList;
+    Leaf* oldL = old_bank(S, Y);
+    Leaf* newL = new_bank(S, Y);
+    const uint8_t* list = old_list(S, Y);
+    uint8_t* cl = new_list(S, Y);
+    uint32_t* nodes = nodes_of(S, Y);
+    double* rings = rings_of(S, Y);
     const uint32_t n = S.n;
     uint32_t total = 0;
     #pragma unroll 1
     for (uint32_t i = 0; i < n; i++) total += __popc(oldL[list[i]].aux);
     if (total == 0) return 0;
-    if (S.nNodes + total > S.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
+    if (S.nNodes + total > Y.node_cap) { S.status = PBSC_WALK_HEAVY; return 0; }
     uint32_t m = 0;
     #pragma unroll 1
     for (uint32_t i = 0; i < n; i++)
@@ -453,7 +368,7 @@ static __device__ __noinline__ uint32_t adopt_children(State& S)
         const Leaf& parent = oldL[list[i]];
         const uint32_t mask = parent.aux;
         const uint32_t p_ring = parent.ring;
-        if (!mask) { ring_release(S, p_ring); continue; }   // not extended: nobody inherits its ring
+        if (!mask) { ring_release(S, Y, p_ring); continue; }   // not extended: nobody inherits its ring
         const uint32_t p_node = parent.node;
         uint32_t j = 0;
         #pragma unroll 1
@@ -463,14 +378,14 @@ static __device__ __noinline__ uint32_t adopt_children(State& S)
             Leaf* c = newL + 4 * i + b;
             const uint32_t node = S.nNodes++;
             c->node = node;
-            S.s.nodes[node] = (p_node << 2) | (uint32_t)b;
+            nodes[node] = (p_node << 2) | (uint32_t)b;
             if (j > 0)
             {
                 // createChild copies both error-rate records
-                const int slot = ring_take(S);
+                const int slot = ring_take(S, Y);
                 if (slot < 0) { S.status = PBSC_WALK_HEAVY; return 0; }
-                const double* src = S.s.rings + (size_t)p_ring * RING_LEN;
-                double* dst = S.s.rings + (size_t)slot * RING_LEN;
+                const double* src = rings + (size_t)p_ring * RING_LEN;
+                double* dst = rings + (size_t)slot * RING_LEN;
                 const int have = min((int)S.level, RING_LEN);   // GlobalErrorRateRecord holds `level` entries so far
                 #pragma unroll 4
                 for (int x = 0; x < have; x++) dst[x] = src[x];
@@ -484,7 +399,7 @@ static __device__ __noinline__ uint32_t adopt_children(State& S)
 }
 
 // first position of the query whose idmer has `key`, from the hash (no duplicate idmers in this query)
-__device__ __forceinline__ int hash_find(const LaneCtx& c, uint32_t key)
+__device__ __forceinline__ int hash_find(const Lane& c, uint32_t key)
 {
     uint32_t h = (key * 2654435761u) & c.hashMask;
     #pragma unroll 1
@@ -504,7 +419,7 @@ static __device__ __noinline__ uint64_t urem_ool(uint64_t a, uint64_t b) { retur
 // PrunedBySeedSupport + isSupportedByNewSeed + computeErrorRate (LongReadCorrectByOverlap.cpp:491-664) for ONE new leaf, by
 // whichever lane the pool gave it to (c.curLen and c.level are the walk's values after curLen++ and before level++).  A leaf
 // whose local error rate is too high is only marked dead; its owner releases the ring (finish_level).
-__device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const LaneCtx& c, uint32_t j)
+__device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const Layout& Y, const Lane& c, uint32_t j)
 {
     const uint64_t seedSize = (uint64_t)P.seed_size;
     const uint64_t curLen = c.curLen;
@@ -513,7 +428,7 @@ __device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const LaneCtx&
     const uint64_t smallSeedIdx = currSeedIdx <= indelOffset ? 0 : currSeedIdx - indelOffset;
     const uint64_t largeSeedIdx = (currSeedIdx + indelOffset) >= ((uint64_t)c.qlen - seedSize) ? ((uint64_t)c.qlen - seedSize) : currSeedIdx + indelOffset;
     const uint32_t keyMask = (1u << (2 * P.seed_size)) - 1u;
-    Leaf& L = c.newL[c.newList[j]];
+    Leaf& L = new_bank(c, Y)[new_list(c, Y)[j]];
     bool found = false;
     const uint64_t d = curLen - (uint64_t)L.lastOverlapLen;
     if (d > seedSize || d <= 1)
@@ -579,7 +494,7 @@ __device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const LaneCtx&
     matchedLen = __dadd_rn(matchedLen, L.redeem);
     const double totalLen = (double)curLen;
     double err = ddiv_ool(__dsub_rn(totalLen, matchedLen), totalLen);
-    double* ring = c.rings + (size_t)L.ring * RING_LEN;
+    double* ring = rings_of(c, Y) + (size_t)L.ring * RING_LEN;
     ring[c.level % RING_LEN] = err;
     L.global_err = err;
     if (c.level + 1 >= (uint32_t)RING_LEN)
@@ -593,9 +508,9 @@ __device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const LaneCtx&
 
 // isTerminated, the search (LongReadCorrectByOverlap.cpp:825-860) for ONE new leaf: the last terminal interval that holds
 // the leaf's interval on either strand, at or after the one it matched before; left in `aux` as index + 1 (0 = none)
-__device__ __forceinline__ void term_leaf(const LaneCtx& c, uint32_t j)
+__device__ __forceinline__ void term_leaf(const Layout& Y, const Lane& c, uint32_t j)
 {
-    Leaf& L = c.newL[c.newList[j]];
+    Leaf& L = new_bank(c, Y)[new_list(c, Y)[j]];
     if (!L.alive) { L.aux = 0; return; }
     const bool fV = L.f_hi > L.f_lo, rV = L.r_hi > L.r_lo;
     const uint64_t f_lo = L.f_lo, f_hi = L.f_hi, r_lo = L.r_lo, r_hi = L.r_hi;
@@ -614,10 +529,11 @@ __device__ __forceinline__ void term_leaf(const LaneCtx& c, uint32_t j)
 // End of a level, by the walk's own lane: isTerminated's bookkeeping (one result slot per leaf, overwritten while the leaf
 // keeps terminating, LongReadCorrectByOverlap.cpp:861-875), then the surviving children become the next level's leaves: the
 // banks swap roles (no copy; the walk kernel's DRAM traffic is mostly this scratch), the child list loses the dead entries.
-static __device__ __noinline__ void finish_level(State& S, uint32_t m, bool check_term)
+static __device__ __noinline__ void finish_level(Lane& S, const Layout& Y, const ExtParamsDev& P, uint32_t m, bool check_term)
 {
-    Leaf* newL = S.s.newL;
-    uint8_t* cl = S.s.newList;
+    Leaf* newL = new_bank(S, Y);
+    uint8_t* cl = new_list(S, Y);
+    WalkResult* res = res_of(S, Y);
     if (check_term)
     {
         #pragma unroll 1
@@ -629,11 +545,11 @@ static __device__ __noinline__ void finish_level(State& S, uint32_t m, bool chec
             int slot = L.res_first;
             if (slot == -1)
             {
-                if (S.nRes >= S.cap.res) { S.status = PBSC_WALK_HEAVY; return; }
+                if (S.nRes >= Y.cap.res) { S.status = PBSC_WALK_HEAVY; return; }
                 slot = (int)++S.nRes;
             }
             WalkResult r; r.err = L.global_err; r.node = L.node; r.i = ilast; r.depth = (uint32_t)S.curLen; r.pad = 0;
-            S.s.res[slot - 1] = r;
+            res[slot - 1] = r;
             L.res_first = slot; L.res_second = ilast;
         }
     }
@@ -643,15 +559,14 @@ static __device__ __noinline__ void finish_level(State& S, uint32_t m, bool chec
     {
         const uint8_t slot = cl[j];
         const Leaf& L = newL[slot];
-        if (!L.alive) { ring_release(S, L.ring); continue; }
-        if (nn != j && nn < S.cap.old_cap) cl[nn] = slot;
+        if (!L.alive) { ring_release(S, Y, L.ring); continue; }
+        if (nn != j && nn < Y.cap.old_cap) cl[nn] = slot;
         nn++;
     }
-    { Leaf* t = S.s.oldL; S.s.oldL = S.s.newL; S.s.newL = t; }
-    { uint8_t* t = S.s.oldList; S.s.oldList = S.s.newList; S.s.newList = t; }
+    S.flip ^= 1;   // the banks and the lists change roles
     S.n = nn;
     // more live leaves than this pass carries, and the reference's loop would go on: hand the walk over
-    if (nn > S.cap.old_cap && nn <= (uint32_t)S.P->max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
+    if (nn > Y.cap.old_cap && nn <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength) S.status = PBSC_WALK_HEAVY;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -824,23 +739,22 @@ static __device__ __noinline__ void setup_task(const FmIndexDev& idx, const ExtP
 }
 
 // start a walk from its setup record
-__device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, const ExtParamsDev& P, const TScratch& lane_scratch, const SetupView& v,
-                                           uint32_t node_cap, Caps cap, uint64_t minSA)
+__device__ __forceinline__ void begin_walk(Lane& S, const Layout& Y, const ExtParamsDev& P, uint8_t* lane_scratch, const SetupView& v, uint64_t minSA)
 {
     const SetupHdr H = *v.hdr;
-    S.idx = &idx; S.P = &P; S.s = lane_scratch; S.node_cap = node_cap; S.cap = cap;
-    S.s.q = v.q; S.s.start4 = v.start4; S.s.pos4 = v.pos4; S.s.termF = v.termF; S.s.termR = v.termR; S.s.hash = v.hash; S.s.sF = v.sF; S.s.sR = v.sR;
+    S.base = lane_scratch;
+    S.q = v.q; S.start4 = v.start4; S.pos4 = v.pos4; S.termF = v.termF; S.termR = v.termR; S.hash = v.hash; S.sF = v.sF; S.sR = v.sR;
     S.status = H.status0;
-    S.qlen = H.qlen; S.k = H.k; S.maxOverlap = H.k + 2; S.trgLen = H.trgLen; S.minSA = minSA;
-    S.maxIndel = H.maxIndel; S.maxLength = H.maxLength; S.minLength = H.minLength;
+    S.qlen = H.qlen; S.k = H.k; S.maxOverlap = H.k + 2; S.trgLen = H.trgLen; S.minSA = (uint32_t)minSA; S.thr = (uint32_t)minSA;
+    S.maxIndel = (uint32_t)H.maxIndel; S.maxLength = (uint32_t)H.maxLength; S.minLength = (uint32_t)H.minLength;
     S.curLen = S.curK = H.k;
     S.nTerm = H.nTerm; S.n5 = H.n5; S.hashMask = H.hashMask; S.n9F = H.n9F; S.n9R = H.n9R; S.dup = H.dup != 0;
-    S.nNodes = 1; S.nRes = 0; S.level = 1; S.phase = 0;
+    S.nNodes = 1; S.nRes = 0; S.level = 1; S.phase = 0; S.flip = 0; S.selNew = 0; S.minErr = 0.0;
     S.n = 0;
     if (S.status) return;
     S.nFree = 0;
     S.nFresh = 1;
-    const uint8_t* q = S.s.q;
+    const uint8_t* q = S.q;
     const uint32_t k = H.k;
     const int s9 = P.seed_size;
     Leaf R;
@@ -858,28 +772,28 @@ __device__ __forceinline__ void begin_walk(State& S, const FmIndexDev& idx, cons
     for (int j = (int)k - 1; j >= 0 && q[j] == R.tailLetter; j--) tc++;
     R.tailCount = tc;
     R.node = 0; R.ring = 0; R.alive = 1; R.aux = 0;
-    S.s.oldL[0] = R;
-    S.s.oldList[0] = 0;
-    S.s.nodes[0] = 0;
-    S.s.rings[0] = 0.0;
+    old_bank(S, Y)[0] = R;
+    old_list(S, Y)[0] = 0;
+    nodes_of(S, Y)[0] = 0;
+    rings_of(S, Y)[0] = 0.0;
     S.n = 1;
 }
 
 // does extendLeaves start by cutting the k-mer back to maxOverlap (LongReadCorrectByOverlap.cpp:242-243)?
-__device__ __forceinline__ bool needs_refine(const State& S) { return S.phase == 0 && S.curK > S.maxOverlap; }
+__device__ __forceinline__ bool needs_refine(const Lane& S) { return S.phase == 0 && S.curK > S.maxOverlap; }
 
 // does extendOverlap's loop (LongReadCorrectByOverlap.cpp:161) run another level?
-__device__ __forceinline__ bool walk_continues(const State& S)
+__device__ __forceinline__ bool walk_continues(const Lane& S, const ExtParamsDev& P)
 {
-    return S.status == 0 && S.n > 0 && S.n <= (uint32_t)S.P->max_leaves && S.curLen <= S.maxLength;
+    return S.status == 0 && S.n > 0 && S.n <= (uint32_t)P.max_leaves && S.curLen <= S.maxLength;
 }
 
 // SelectFreqsOfrange (LongReadCorrectByOverlap.cpp:281-331) for ONE leaf, by whichever lane the pool gave it to: the
 // frequency of the leaf's last LB .. LB + extra bases, newest base first on BWT and complemented on RBWT; the walk-wide maxima
 // are collected in the owner's record (shared-memory atomics).
-__device__ __forceinline__ void select_leaf(const FmIndexDev& idx, LaneCtx& c, uint32_t i)
+__device__ __forceinline__ void select_leaf(const FmIndexDev& idx, const Layout& Y, Lane& c, uint32_t i)
 {
-    const Leaf& L = c.selBank[c.selList[i]];
+    const Leaf& L = (c.selNew ? new_bank(c, Y) : old_bank(c, Y))[(c.selNew ? new_list(c, Y) : old_list(c, Y))[i]];
     const uint64_t hi = L.rt_hi, lo = L.rt_lo;
     const int LB = (int)c.selLB, extra = (int)c.selExtra;
     Interval a, b;   // a on BWT, b on RBWT
@@ -920,9 +834,9 @@ __device__ __forceinline__ void select_leaf(const FmIndexDev& idx, LaneCtx& c, u
 }
 
 // refineSAInterval(selK) of one leaf of the selected bank (the refinement that follows SelectFreqsOfrange)
-__device__ __forceinline__ void reselect_leaf(const FmIndexDev& idx, const LaneCtx& c, uint32_t i)
+__device__ __forceinline__ void reselect_leaf(const FmIndexDev& idx, const Layout& Y, const Lane& c, uint32_t i)
 {
-    Leaf& L = c.selBank[c.selList[i]];
+    Leaf& L = (c.selNew ? new_bank(c, Y) : old_bank(c, Y))[(c.selNew ? new_list(c, Y) : old_list(c, Y))[i]];
     const uint64_t hi = L.rt_hi, lo = L.rt_lo;
     const int K = (int)c.selK;
     Interval f, r;
@@ -950,13 +864,10 @@ __device__ __forceinline__ void reselect_leaf(const FmIndexDev& idx, const LaneC
 //   phase 1: after the k-mer was reduced (select + refine on the old leaves happened at the end of the previous iteration)
 //   phase 2: last resort             probes with thr - 1
 // Returns true when the level produced children that go on to prune / terminal search / finish_level.
-// `sel` = how many leaves go through SelectFreqsOfrange + refineSAInterval before the level goes on (the owner's record says
-// which); level_select then turns the pooled maxima into the reduced k-mer size.
-static __device__ __noinline__ bool level_middle(State& S, LaneCtx& c, uint32_t m, uint32_t& sel)
+// `sel` = how many leaves go through SelectFreqsOfrange + refineSAInterval before the level goes on (selNew says which bank);
+// level_select then turns the pooled maxima into the reduced k-mer size.
+static __device__ __noinline__ bool level_middle(Lane& S, const Layout& Y, const ExtParamsDev& P, uint32_t m, uint32_t& sel)
 {
-    const ExtParamsDev& P = *S.P;
-    Leaf* bank = nullptr;
-    const uint8_t* list = nullptr;
     uint32_t cnt = 0;
     sel = 0;
     if (m > 0)
@@ -964,33 +875,33 @@ static __device__ __noinline__ bool level_middle(State& S, LaneCtx& c, uint32_t 
         S.curLen++;
         S.curK++;
         S.phase = 0;
-        if (insufficient(S, S.s.newL, S.s.newList, m)) { bank = S.s.newL; list = S.s.newList; cnt = m; }
+        if (insufficient(P, new_bank(S, Y), new_list(S, Y), m)) { S.selNew = 1; cnt = m; }
     }
-    else if (S.phase == 0) { bank = S.s.oldL; list = S.s.oldList; cnt = S.n; S.phase = 1; }   // level 1: reduce the k-mer size, then retry
-    else if (S.phase == 1) { S.phase = 2; return false; }                                       // level 2: retry with the lower threshold
-    else { S.n = 0; return false; }                                                             // newLeaves stays empty: the walk ends
+    else if (S.phase == 0) { S.selNew = 0; cnt = S.n; S.phase = 1; }   // level 1: reduce the k-mer size, then retry
+    else if (S.phase == 1) { S.phase = 2; return false; }               // level 2: retry with the lower threshold
+    else { S.n = 0; return false; }                                     // newLeaves stays empty: the walk ends
     if (cnt)
     {
-        const uint64_t LB = max(S.curK - 2, (uint64_t)P.min_overlap);
-        c.selBank = bank; c.selList = list; c.selLB = (uint32_t)LB; c.selExtra = (uint32_t)(S.curK - LB);
-        c.selMx[0] = c.selMx[1] = c.selMx[2] = 0;
+        const uint32_t LB = max(S.curK - 2, (uint32_t)P.min_overlap);
+        S.selLB = LB; S.selExtra = S.curK - LB;
+        S.selMx[0] = S.selMx[1] = S.selMx[2] = 0;
         sel = cnt;
     }
     return m > 0;
 }
 
 // the decision of SelectFreqsOfrange (:318-330) from the maxima the pool collected
-__device__ __forceinline__ void level_select(State& S, LaneCtx& c)
+__device__ __forceinline__ void level_select(Lane& S, const ExtParamsDev& P)
 {
-    const uint64_t LB = c.selLB, UB = LB + c.selExtra;
-    uint64_t R = UB;
-    if (c.selMx[0] - S.P->freq_int[LB] < 5) R = LB;
+    const uint32_t LB = S.selLB, UB = LB + S.selExtra;
+    uint32_t R = UB;
+    if (S.selMx[0] - P.freq_int[LB] < 5) R = LB;
     else
     {
         #pragma unroll 1
-        for (uint32_t e = 1; e <= c.selExtra; e++) if (c.selMx[e] - S.P->freq_int[LB + e] < 5) { R = LB + e; break; }
+        for (uint32_t e = 1; e <= S.selExtra; e++) if (S.selMx[e] - P.freq_int[LB + e] < 5) { R = LB + e; break; }
     }
-    c.selK = (uint32_t)R;
+    S.selK = R;
     S.curK = R;
 }
 
@@ -999,24 +910,25 @@ __device__ __forceinline__ void level_select(State& S, LaneCtx& c)
 // extendOverlap's return value and findTheBestPath (:199-236).  A successful walk does not chase its label chain here
 // (a serial pointer chase by one lane while 31 wait): it copies its label tree to the node pool and leaves the rest to
 // materialize_kernel.
-static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t* nodepool, unsigned long long* pool_used, uint64_t pool_cap, bool direct,
-                                               uint8_t* out, uint32_t outCap, uint32_t* outLen)
+static __device__ __noinline__ int finish_walk(Lane& S, const Layout& Y, const ExtParamsDev& P, SetupHdr* hdr, uint32_t* nodepool, unsigned long long* pool_used,
+                                               uint64_t pool_cap, bool direct, uint8_t* out, uint32_t outCap, uint32_t* outLen)
 {
     if (S.status) return S.status;
-    const ExtParamsDev& P = *S.P;
+    const WalkResult* res = res_of(S, Y);
+    const uint32_t* nodes = nodes_of(S, Y);
     if (S.nRes > 0)
     {
         double best = 1.0;
         int bi = -1;
         #pragma unroll 1
-        for (uint32_t i = 0; i < S.nRes; i++) { const double e = S.s.res[i].err; if (e < best) { best = e; bi = (int)i; } }
+        for (uint32_t i = 0; i < S.nRes; i++) { const double e = res[i].err; if (e < best) { best = e; bi = (int)i; } }
         if (bi < 0) return PBSC_WALK_NO_PATH;
-        const WalkResult r = S.s.res[bi];
+        const WalkResult r = res[bi];
         if (direct)
         {
             // a pass of few, long walks (most lanes of the warp only help): write the merged sequence here, from the lane's own
             // label tree, instead of parking a tree of up to node_cap nodes in the shared pool
-            const uint8_t* q = S.s.q;
+            const uint8_t* q = S.q;
             const uint8_t* trg = q + S.qlen - S.trgLen;
             const uint32_t chain = r.depth - S.k;
             const uint32_t tailFrom = (uint32_t)r.i + (uint32_t)P.min_overlap;
@@ -1029,14 +941,14 @@ static __device__ __noinline__ int finish_walk(State& S, SetupHdr* hdr, uint32_t
             for (uint32_t x = 0; x < tailLen; x++) out[r.depth + x] = trg[tailFrom + x];
             uint32_t node = r.node;
             #pragma unroll 1
-            for (uint32_t x = 0; x < chain; x++) { const uint32_t w = S.s.nodes[node]; out[r.depth - 1 - x] = (uint8_t)(w & 3); node = w >> 2; }
+            for (uint32_t x = 0; x < chain; x++) { const uint32_t w = nodes[node]; out[r.depth - 1 - x] = (uint8_t)(w & 3); node = w >> 2; }
             *outLen = len;
             return 1;
         }
         const uint32_t nn = (S.nNodes + 3u) & ~3u;
         const uint64_t off = atomicAdd(pool_used, (unsigned long long)nn);
         if (off + nn > pool_cap) return PBSC_OVF_POOL;
-        const uint4* src = reinterpret_cast<const uint4*>(S.s.nodes);
+        const uint4* src = reinterpret_cast<const uint4*>(nodes);
         uint4* dst = reinterpret_cast<uint4*>(nodepool + off);
         #pragma unroll 4
         for (uint32_t x = 0; x < nn / 4; x++) dst[x] = src[x];
