@@ -354,7 +354,6 @@ static __device__ __noinline__ uint32_t adopt_children(Lane& S, const Layout& Y)
     const uint8_t* list = old_list(S, Y);
     uint8_t* cl = new_list(S, Y);
     uint32_t* nodes = nodes_of(S, Y);
-    double* rings = rings_of(S, Y);
     const uint32_t n = S.n;
     uint32_t total = 0;
     #pragma unroll 1
@@ -382,14 +381,11 @@ static __device__ __noinline__ uint32_t adopt_children(Lane& S, const Layout& Y)
             if (j > 0)
             {
                 // createChild copies both error-rate records
+                // (the copy itself is left to whichever lane prunes this child: aux = parent's ring + 1)
                 const int slot = ring_take(S, Y);
                 if (slot < 0) { S.status = PBSC_WALK_HEAVY; return 0; }
-                const double* src = rings + (size_t)p_ring * RING_LEN;
-                double* dst = rings + (size_t)slot * RING_LEN;
-                const int have = min((int)S.level, RING_LEN);   // GlobalErrorRateRecord holds `level` entries so far
-                #pragma unroll 4
-                for (int x = 0; x < have; x++) dst[x] = src[x];
                 c->ring = (uint16_t)slot;
+                c->aux = p_ring + 1;
             }
             cl[m++] = (uint8_t)(4 * i + b);
             j++;
@@ -495,6 +491,17 @@ __device__ __forceinline__ void prune_leaf(const ExtParamsDev& P, const Layout& 
     const double totalLen = (double)curLen;
     double err = ddiv_ool(__dsub_rn(totalLen, matchedLen), totalLen);
     double* ring = rings_of(c, Y) + (size_t)L.ring * RING_LEN;
+    if (L.aux)
+    {
+        // second or later child of its parent: createChild's copy of both error-rate records (FMIndexWalk/SAINode.cpp:166-189).
+        // The first child shares the parent's ring and may already have written this level's entry into it; the same slot of
+        // the copy is overwritten just below, every other slot is older.
+        const double* src = rings_of(c, Y) + (size_t)(L.aux - 1) * RING_LEN;
+        const int have = min((int)c.level, RING_LEN);   // GlobalErrorRateRecord holds `level` entries so far
+        #pragma unroll 4
+        for (int x = 0; x < have; x++) ring[x] = src[x];
+        L.aux = 0;
+    }
     ring[c.level % RING_LEN] = err;
     L.global_err = err;
     if (c.level + 1 >= (uint32_t)RING_LEN)
