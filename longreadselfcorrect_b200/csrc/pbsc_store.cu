@@ -11,6 +11,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include "pbsc_internal.h"
 
@@ -421,14 +422,21 @@ int pbsc_index_open(const char* prefix, int device, int require_sai, int k0, int
         for (int w = 0; w < 2 && match; w++) match = H.n_strings[w] == ns[w] && H.n_symbols[w] == nsym[w] && H.src_runs[w] == nr[w];
         if (match)
         {
+            const auto t0 = std::chrono::steady_clock::now();
             const int rc = pbsc_index_load_fmg(fmg.c_str(), device, out);
+            if (getenv("PBSC_TRACE")) fprintf(stderr, "[pbsc] %s: %.2f GB in %.2f s\n", fmg.c_str(), H.total_bytes / 1e9, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
             if (rc == PBSC_OK) { if (from_fmg) *from_fmg = 1; return rc; }
         }
+        else if (getenv("PBSC_TRACE")) fprintf(stderr, "[pbsc] %s does not match the index files or k0 = %d: not used\n", fmg.c_str(), k0);
         // stale or damaged: fall through to the run-length files (and rewrite it below)
     }
+    const auto t1 = std::chrono::steady_clock::now();
     int rc = pbsc_index_load(prefix, device, 0, out);
     if (rc != PBSC_OK) return rc;
+    const auto t2 = std::chrono::steady_clock::now();
     if (k0 > 0) rc = pbsc_index_build_prefix_table(*out, k0);
+    if (getenv("PBSC_TRACE")) fprintf(stderr, "[pbsc] %s.bwt/.rbwt read + decoded in %.2f s, prefix table in %.2f s\n", prefix, std::chrono::duration<double>(t2 - t1).count(),
+                                      std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
     if (rc != PBSC_OK) { pbsc_index_destroy(*out); *out = nullptr; return rc; }
     if (write_fmg && pbsc_index_save(*out, fmg.c_str()) != PBSC_OK) fprintf(stderr, "[pbsc] warning: %s\n", pbsc_last_error());
     return PBSC_OK;
