@@ -21,6 +21,7 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 #include "pbsc_batch.cuh"
 #include "pbsc_task.cuh"
 #include <chrono>
@@ -484,18 +485,22 @@ dp_align_kernel(uint64_t n_rows, DpRow* rows, const DpJob* __restrict__ jobs, co
 // threads per block, three blocks per SM; longer ones up to 1024 bases with 64 threads per block (the 2-bit read in shared
 // memory is longer), four blocks per SM; up to 4000 bases (the 16-bit score limit) with one warp per block.  What is left
 // stays `pass == 2` for dp_align_kernel.
-template <int QMAX_, int NT_>
+template <int QMAX_, int NT_, bool GREAD_>
 struct DptCfg
 {
     static constexpr int QMAX = QMAX_;                                          // longest query
     static constexpr int NT = NT_;                                              // threads per block
+    static constexpr bool GREAD = GREAD_;                                       // the 2-bit read in global memory instead of shared
     static constexpr int HWORDS = dpt::HSLOTS / 2;                              // 16-bit scores, two per word
     static constexpr int SWORDS = (dpt::max_len_bound(QMAX_) + 15) / 16 + 1;    // 2-bit read + one word of slack for bits()
-    static constexpr int SMEM = (HWORDS + SWORDS) * NT_ * 4;
+    static constexpr int SMEM = (HWORDS + (GREAD_ ? 0 : SWORDS)) * NT_ * 4;
 };
-using DptShort = DptCfg<256, 128>;    // 75 776 B per block: three blocks (12 warps) per SM
-using DptLong = DptCfg<1024, 64>;     // 51 456 B per block: four blocks (8 warps) per SM
-using DptHuge = DptCfg<4000, 32>;     // 51 968 B per block: four blocks (4 warps) per SM; 8 * 4000 still fits 16 bits
+// The previous column (512 B per alignment) has to be in shared memory; the read does not: for the longer queries it is kept in
+// global memory, word n of the 32 lanes of a warp side by side (coalesced, L1/L2 resident), which takes the resident warps per
+// SM from 8 to 12 (queries up to 1024 bases) and from 4 to 13 (up to 4000).
+using DptShort = DptCfg<256, 128, false>;   // 75 776 B per block: three blocks (12 warps) per SM
+using DptLong = DptCfg<1024, 64, true>;     // 32 768 B per block: six blocks (12 warps) per SM (51 456 B and 8 warps with the read in shared memory)
+using DptHuge = DptCfg<4000, 32, true>;     // 16 384 B per block: 13 blocks (13 warps) per SM; 8 * 4000 still fits 16 bits
 constexpr uint32_t DPT_KEY_NONE = 0x3FFFu;
 constexpr int DPT_KEY_BITS = 14;
 
@@ -559,6 +564,16 @@ struct DptS   // the retrieved read at 2 bits per base, 16 bases per word, in th
         return __funnelshift_r(w[0], w[C::NT], 2 * (x & 15));   // shift < 32; bits 20.. are ignored by the caller
     }
 };
+struct DptSG   // the same read in global memory: word n of this lane at p[n * 32] (the 32 lanes of a warp side by side)
+{
+    const uint32_t* p;
+    __device__ __forceinline__ int base(int x) const { return (int)((p[(size_t)(x >> 4) * 32] >> (2 * (x & 15))) & 3u); }
+    __device__ __forceinline__ uint32_t bits(int x) const
+    {
+        const uint32_t* w = p + (size_t)(x >> 4) * 32;
+        return __funnelshift_r(w[0], w[32], 2 * (x & 15));
+    }
+};
 struct DptF   // flag words of this lane: word n of the lane at arena[n * 32 + lane] (a warp's stores coalesce)
 {
     uint32_t* p;
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(C::NT, 227 * 1024 / (C::SMEM + 1024))
 dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order, DpRow* rows,
                        const DpJob* __restrict__ jobs, const WalkTask* __restrict__ tasks, uint8_t* mem, uint64_t mem0, uint32_t* arenas,
                        uint64_t arena_words, unsigned long long* counter, unsigned int* n_bad, const unsigned long long* __restrict__ n_eligible,
-                       unsigned long long min_rows, unsigned int* n_thread_rows)
+                       unsigned long long min_rows, unsigned int* n_thread_rows, uint32_t* rarena)
 {
     extern __shared__ uint32_t dpt_smem[];
     // One alignment per thread pays when there are enough of them to fill the machine: an alignment of L query bases is a
@@ -585,8 +600,10 @@ dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_thread_rows, (unsigned int)n_el);   // reported in pbsc_timing
     const int lane = threadIdx.x & 31;
     uint32_t* Hs = dpt_smem + threadIdx.x;
-    uint32_t* Ss = dpt_smem + C::HWORDS * C::NT + threadIdx.x;
     const uint64_t warp = (uint64_t)blockIdx.x * (C::NT / 32) + (threadIdx.x >> 5);
+    // the read's words: this thread's column of shared memory, or this lane's column of the warp's slab in global memory
+    uint32_t* Ss = C::GREAD ? rarena + warp * (uint64_t)(C::SWORDS * 32) + lane : dpt_smem + C::HWORDS * C::NT + threadIdx.x;
+    constexpr int SSTRIDE = C::GREAD ? 32 : C::NT;
     DptF F{arenas + warp * arena_words + lane};
     for (;;)
     {
@@ -609,13 +626,13 @@ dp_align_thread_kernel(uint64_t n_rows, const uint32_t* __restrict__ keys, const
             uint32_t w = 0;
             const int m = min(16, g.mlen - x);
             for (int y = 0; y < m; y++) w |= (uint32_t)g.s2[x + y] << (2 * y);
-            Ss[(x >> 4) * C::NT] = w;
+            Ss[(x >> 4) * SSTRIDE] = w;
         }
-        Ss[((g.mlen + 15) >> 4) * C::NT] = 0u;
+        Ss[((g.mlen + 15) >> 4) * SSTRIDE] = 0u;
         #pragma unroll 8
         for (int x = 0; x < C::HWORDS; x++) Hs[x * C::NT] = 0u;
         DptH<C> H{Hs};
-        const DptS<C> S{Ss};
+        const typename std::conditional<C::GREAD, DptSG, DptS<C>>::type S{Ss};
         const DptQ q{g.q};
         int bi, bj;
         dpt::fill(g.qlen, g.mlen, g.origin, H, S, F, q, bi, bj);
@@ -764,7 +781,11 @@ static cudaError_t arena(pbsc_index* idx, const char* name, size_t count, T** ou
 DpStats& last_dp_stats() { static thread_local DpStats s; return s; }
 
 // one pass of dp_align_thread_kernel<C>: queries of at most min(C::QMAX, longest query of the stage) bases
-struct DptPass { bool on = false; uint64_t qmax = 0, arena_words = 0, min_rows = 0; int blocks = 0; uint64_t flag_words() const { return on ? arena_words * (uint64_t)blocks : 0; } };
+struct DptPass
+{
+    bool on = false; uint64_t qmax = 0, arena_words = 0, min_rows = 0, read_words = 0; int blocks = 0;
+    uint64_t flag_words() const { return on ? arena_words * (uint64_t)blocks : 0; }
+};
 template <class C>
 static cudaError_t dpt_pass_setup(pbsc_index* idx, uint64_t q_longest, uint64_t q_prev_max, int cap_per_sm, DptPass& g)
 {
@@ -780,19 +801,20 @@ static cudaError_t dpt_pass_setup(pbsc_index* idx, uint64_t q_longest, uint64_t 
     if (cap_per_sm > 0) per = std::min(per, cap_per_sm);
     g.blocks = idx->sm_count * std::max(per, 1);
     g.arena_words *= (uint64_t)(C::NT / 32);   // per block
+    g.read_words = C::GREAD ? (uint64_t)g.blocks * (C::NT / 32) * (uint64_t)(C::SWORDS * 32) : 0;
     return cudaSuccess;
 }
 template <class C>
 static void dpt_pass_launch(const DptPass& g, cudaStream_t st, uint64_t nrows, DpRow* rows, const DpJob* jobs, const WalkTask* tasks, uint8_t* mem,
                             uint64_t mem0, uint32_t* keys, uint32_t* keys2, uint32_t* order, uint32_t* order2, uint8_t* sort_tmp, size_t sort_bytes,
-                            uint32_t* slabs, unsigned long long* counter, unsigned int* cnt)
+                            uint32_t* slabs, unsigned long long* counter, unsigned int* cnt, uint32_t* rarena)
 {
     cudaMemsetAsync(counter, 0, 16, st);   // counter[0]: work queue, counter[1]: rows eligible for this pass
     dp_keys_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(nrows, rows, jobs, keys, order, (int)g.qmax, counter + 1);
     cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys2, order, order2, (int)nrows, 0, DPT_KEY_BITS, st);
     const int tb = (int)std::min<uint64_t>((uint64_t)g.blocks, (nrows + C::NT - 1) / C::NT);
     dp_align_thread_kernel<C><<<tb, C::NT, C::SMEM, st>>>(nrows, keys2, order2, rows, jobs, tasks, mem, mem0, slabs, g.arena_words / (C::NT / 32), counter,
-                                                          cnt + 1, counter + 1, g.min_rows, cnt + 2);
+                                                          cnt + 1, counter + 1, g.min_rows, cnt + 2, rarena);
 }
 
 int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void* tasks_v, uint64_t n_items, const uint32_t* list, uint8_t* outpool,
@@ -905,7 +927,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
     // thread-per-alignment kernel (stage 2t): sort keys, the sorted order, one flag arena per resident warp
     bool use_thread = true;
     if (const char* e = getenv("PBSC_DP_THREAD")) use_thread = atoi(e) != 0;
-    uint32_t *tkeys = nullptr, *tkeys2 = nullptr, *torder = nullptr, *torder2 = nullptr, *tslabs = nullptr;
+    uint32_t *tkeys = nullptr, *tkeys2 = nullptr, *torder = nullptr, *torder2 = nullptr, *tslabs = nullptr, *treads = nullptr;
     uint8_t* sort_tmp = nullptr;
     size_t sort_bytes = 0;
     // the longest query of this stage decides which passes run and how large their flag arenas are
@@ -931,6 +953,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, tkeys, tkeys2, torder, torder2, (int)max_rows, 0, DPT_KEY_BITS, st);
         PBSC_CUDA(arena(idx, "dp.sorttmp", sort_bytes, &sort_tmp));
         PBSC_CUDA(arena(idx, "dp.tflags", std::max(pass_s.flag_words(), std::max(pass_l.flag_words(), pass_h.flag_words())), &tslabs));
+        PBSC_CUDA(arena(idx, "dp.treads", std::max<uint64_t>(1, std::max(pass_l.on ? pass_l.read_words : 0, pass_h.on ? pass_h.read_words : 0)), &treads));
     }
     // job order of the multiple-alignment kernel
     // 0: natural order (default: neighbouring threads work on neighbouring scratch, which is what this memory-bound kernel
@@ -996,7 +1019,7 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         if (pass_s.on)
         {
             dpt_pass_launch<DptShort>(pass_s, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,
-                                      qctr + 1, cnt);
+                                      qctr + 1, cnt, treads);
             prof.mark("align_thread_256");
             if (launches) *launches += 4;   // keys, the sort's kernels counted as two, alignment
         }
@@ -1004,14 +1027,14 @@ int run_dp_fallback(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, void*
         {
             // the rows the first pass left: longer queries
             dpt_pass_launch<DptLong>(pass_l, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,
-                                     qctr + 1, cnt);
+                                     qctr + 1, cnt, treads);
             prof.mark("align_thread_1024");
             if (launches) *launches += 4;
         }
         if (pass_h.on)
         {
             dpt_pass_launch<DptHuge>(pass_h, st, nrows, rows, jobs, tasks, mem, h_mem[j0], tkeys, tkeys2, torder, torder2, sort_tmp, sort_bytes, tslabs,
-                                     qctr + 1, cnt);
+                                     qctr + 1, cnt, treads);
             prof.mark("align_thread_4000");
             if (launches) *launches += 4;
         }
