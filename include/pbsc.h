@@ -257,6 +257,23 @@ int pbsc_last_timing(pbsc_timing* t);
  * other.  Returns 1 in the measurement build, 0 (and zeros) in the product build. */
 int pbsc_occ_counts(uint64_t* out, int reset);
 
+/* ---- index construction: `stride index READS` (StriDe/index.cpp:86-214) --------------------------------------------------------------
+ * Replaces BWTCA::runRopebwt2 (SuffixTools/BWTCARopebwt.cpp:160-247, ropebwt2 with MR_SO_IO: one sentinel per read, ordered by read
+ * index), BWTWriterBinary (SuffixTools/BWTWriterBinary.cpp:28-94, run-length units of at most 31 symbols) and
+ * SampledSuffixArray::buildLexicoIndex / writeLexicoIndex (SuffixTools/SampledSuffixArray.cpp:158-190,248-258).  The suffixes are
+ * sorted on the GPU (pbsc_build.cu); PREFIX.bwt, PREFIX.rbwt, PREFIX.sai and PREFIX.rsai come out byte-identical to the reference's.
+ * `reads`: the bases of all reads, one ASCII letter each (ACGT, either case; anything else is PBSC_ERR_ARG: the reference's index
+ * holds $ACGT only), read r at [offsets[r], offsets[r + 1]).  Limits: fewer than 2^32-1 symbols (bases + reads). */
+#define PBSC_BUILD_NO_FORWARD 1   /* --no-forward: skip PREFIX.bwt / .sai */
+#define PBSC_BUILD_NO_REVERSE 2   /* --no-reverse: skip PREFIX.rbwt / .rsai */
+int pbsc_build_index_files(const char* reads, const uint64_t* offsets, uint64_t n_reads, const char* prefix, int device, int flags);
+/* One strand in memory: *runs = the RLUnit bytes of the .bwt (reverse = 0) or .rbwt (reverse = 1) body, *n_symbols = bases + reads,
+ * *lex_order (optional) = the read index of the r-th '$' of the BWT (the body of the .sai / .rsai).  Both arrays are malloc'd here;
+ * release them with pbsc_free.  pbsc_index_from_runs takes the bytes as they are. */
+int pbsc_build_bwt(const char* reads, const uint64_t* offsets, uint64_t n_reads, int reverse, int device, uint8_t** runs, uint64_t* n_runs,
+                   uint64_t* n_symbols, uint32_t** lex_order);
+void pbsc_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,7 +78,8 @@ EXPORTED = ["pbsc_last_error", "pbsc_device_count", "pbsc_params_default", "pbsc
             "pbsc_index_save", "pbsc_index_load_fmg", "pbsc_index_open", "pbsc_index_clone", "pbsc_index_blob_size",
             "pbsc_index_export_blob", "pbsc_index_import_blob", "pbsc_index_set_lanes", "pbsc_index_lanes",
             "pbsc_host_register", "pbsc_host_unregister", "pbsc_occ_counts",
-            "pbsc_batch_debug_size", "pbsc_batch_fetch_debug"]
+            "pbsc_batch_debug_size", "pbsc_batch_fetch_debug",
+            "pbsc_build_index_files", "pbsc_build_bwt", "pbsc_free"]
 
 _lib = None
 
@@ -172,6 +173,43 @@ def host_unregister(a: np.ndarray) -> None:
     L.pbsc_host_unregister.argtypes = [C.c_void_p]
     L.pbsc_host_unregister.restype = None
     L.pbsc_host_unregister(C.c_void_p(a.ctypes.data))
+
+
+def build_index_files(packed, prefix: str, device: int = 0, forward: bool = True, reverse: bool = True) -> None:
+    """`stride index` on the GPU (pbsc_build.cu): PREFIX.bwt/.sai and PREFIX.rbwt/.rsai, byte-identical to the reference's files.
+    packed = (ASCII bases of all reads as one uint8 array, uint64 offsets[n + 1])."""
+    bases, offsets = packed
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    flags = (0 if forward else 1) | (0 if reverse else 2)
+    L = lib()
+    L.pbsc_build_index_files.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int]
+    _check(L.pbsc_build_index_files(C.c_void_p(bases.ctypes.data), C.c_void_p(offsets.ctypes.data), C.c_uint64(offsets.size - 1),
+                                    prefix.encode(), C.c_int(device), C.c_int(flags)))
+
+
+def build_bwt(packed, reverse: bool = False, device: int = 0):
+    """One strand in memory: (RLUnit bytes, number of symbols, lexicographic read order); Index.from_runs takes the bytes."""
+    bases, offsets = packed
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = offsets.size - 1
+    L = lib()
+    L.pbsc_build_bwt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    L.pbsc_free.argtypes = [C.c_void_p]
+    L.pbsc_free.restype = None
+    runs, lex = C.c_void_p(), C.c_void_p()
+    n_runs, n_sym = C.c_uint64(), C.c_uint64()
+    _check(L.pbsc_build_bwt(C.c_void_p(bases.ctypes.data), C.c_void_p(offsets.ctypes.data), C.c_uint64(n), C.c_int(1 if reverse else 0),
+                            C.c_int(device), C.byref(runs), C.byref(n_runs), C.byref(n_sym), C.byref(lex)))
+    try:
+        r = np.ctypeslib.as_array(C.cast(runs, C.POINTER(C.c_uint8)), shape=(n_runs.value,)).copy() if n_runs.value else np.zeros(0, np.uint8)
+        lx = np.ctypeslib.as_array(C.cast(lex, C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+    finally:
+        L.pbsc_free(runs)
+        L.pbsc_free(lex)
+    return r, int(n_sym.value), lx
 
 
 def _concat(strings):

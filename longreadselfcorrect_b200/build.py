@@ -13,7 +13,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the reference's float/double pruning rules must not be contracted into FMAs
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-DPBSC_FUSED_UPDATE",
               "-Xcompiler", "-fPIC,-O3,-ffp-contract=off", "-ccbin", "/usr/bin/g++"]
-CU_SOURCES = ["pbsc_index.cu", "pbsc_seed.cu", "pbsc_extend.cu", "pbsc_extend_thread.cu", "pbsc_dp.cu", "pbsc_pipeline.cu", "pbsc_store.cu"]
+CU_SOURCES = ["pbsc_index.cu", "pbsc_seed.cu", "pbsc_extend.cu", "pbsc_extend_thread.cu", "pbsc_dp.cu", "pbsc_pipeline.cu", "pbsc_store.cu", "pbsc_build.cu"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:

@@ -389,8 +389,95 @@ static void writeDebugFiles(const Batch& b)
     }
 }
 
+// ---- `pbcorrect index [OPTION] ... READSFILE`: `stride index` (StriDe/index.cpp:34-52,86-214,262-352) with the suffix sorting on
+// the GPU (pbsc_build_index_files, pbsc_build.cu).  Same options, same default prefix (the reads file's name without directory
+// and extensions, in the current directory), same four files, byte for byte.  -t, -a, -d, -g and -c are accepted and ignored:
+// there is one algorithm here and it yields what ropebwt2 yields.
+static const char* INDEX_USAGE_MESSAGE =
+"Usage: pbcorrect index [OPTION] ... READSFILE\n"
+"Index the reads in READSFILE using a suffixarray/bwt\n"
+"\n"
+"  -v, --verbose                        display verbose output\n"
+"      --help                           display this help and exit\n"
+"  -a, --algorithm=STR                  accepted for compatibility (sais, ropebwt, ropebwt2): the GPU builder writes the same files\n"
+"  -t, --threads=NUM                    accepted for compatibility\n"
+"  -p, --prefix=PREFIX                  write index to file using PREFIX instead of prefix of READSFILE\n"
+"      --no-reverse                     suppress construction of the reverse BWT\n"
+"      --no-forward                     suppress construction of the forward BWT\n"
+"      --gpu=NUM                        CUDA device to build on (default: 0)\n\n";
+
+static int indexMain(int argc, char** argv)
+{
+    enum { IOPT_HELP = 1, IOPT_NO_REVERSE, IOPT_NO_FWD, IOPT_GPU };
+    static const struct option iopts[] = {
+        {"verbose", no_argument, nullptr, 'v'}, {"check", no_argument, nullptr, 'c'}, {"prefix", required_argument, nullptr, 'p'},
+        {"threads", required_argument, nullptr, 't'}, {"disk", required_argument, nullptr, 'd'}, {"gap-array", required_argument, nullptr, 'g'},
+        {"algorithm", required_argument, nullptr, 'a'}, {"no-reverse", no_argument, nullptr, IOPT_NO_REVERSE},
+        {"no-forward", no_argument, nullptr, IOPT_NO_FWD}, {"help", no_argument, nullptr, IOPT_HELP}, {"gpu", required_argument, nullptr, IOPT_GPU},
+        {nullptr, 0, nullptr, 0}};
+    const auto t0 = std::chrono::steady_clock::now();
+    const clock_t c0 = clock();
+    std::string prefix, reads;
+    int flags = 0, device = 0;
+    bool die = false;
+    optind = 1;
+    for (int c; (c = getopt_long(argc, argv, "p:a:m:t:d:g:cv", iopts, nullptr)) != -1;)
+    {
+        std::istringstream arg(optarg != nullptr ? optarg : "");
+        switch (c)
+        {
+            case 'p': arg >> prefix; break;
+            case 'a': case 't': case 'd': case 'g': case 'm': case 'c': case 'v': break;
+            case IOPT_NO_REVERSE: flags |= PBSC_BUILD_NO_REVERSE; break;
+            case IOPT_NO_FWD: flags |= PBSC_BUILD_NO_FORWARD; break;
+            case IOPT_GPU: arg >> device; break;
+            case IOPT_HELP: std::cout << INDEX_USAGE_MESSAGE; exit(EXIT_SUCCESS);
+            default: die = true; break;
+        }
+    }
+    if (argc - optind < 1) { std::cerr << "index: missing arguments\n"; die = true; }
+    else if (argc - optind > 1) { std::cerr << "index: too many arguments\n"; die = true; }
+    if (die) { std::cout << "\n" << INDEX_USAGE_MESSAGE; exit(EXIT_FAILURE); }
+    reads = argv[optind];
+    if (prefix.empty())
+    {
+        // getFilename (Util/Util.cpp:218-225)
+        std::string out = reads.substr(reads.find_last_of('/') == std::string::npos ? 0 : reads.find_last_of('/') + 1);
+        auto strip = [](const std::string& f) { const size_t dot = f.find_last_of('.'); return dot == std::string::npos ? f : f.substr(0, dot); };
+        if (out.size() >= 3 && out.compare(out.size() - 3, 3, ".gz") == 0) out = strip(out);
+        prefix = strip(out);
+    }
+    else
+    {
+        const size_t slash = prefix.find_last_of('/');
+        const std::string dir = (slash == std::string::npos ? std::string(".") : prefix.substr(0, slash)) + "/";
+        if (system(("mkdir -p " + dir).c_str()) != 0) { std::cerr << "index: something wrong making directory: " << dir << "\n"; return EXIT_FAILURE; }
+    }
+    if (pbsc_device_count() <= 0) { std::cerr << "index: no CUDA device available (this build has no CPU path)\n"; return EXIT_FAILURE; }
+    LineReader in(reads);
+    if (!in.ok()) { std::cerr << "Error: could not open " << reads << " for read\n"; return EXIT_FAILURE; }
+    Batch all;
+    while (readRecord(in, all)) {}
+    if (all.ids.empty()) { std::cerr << "index: input file is empty\n"; return EXIT_FAILURE; }
+    std::string bad;
+    if (!normalize(all, bad)) { std::cerr << "index: read " << bad << " holds letters other than ACGT\n"; return EXIT_FAILURE; }
+    std::cout << "Building index for " << reads << " on GPU " << device << "\n";
+    if (pbsc_build_index_files(all.bases.p, all.offsets.data(), all.ids.size(), prefix.c_str(), device, flags) != PBSC_OK)
+    { std::cerr << "index: " << pbsc_last_error() << "\n"; return EXIT_FAILURE; }
+    if (!(flags & PBSC_BUILD_NO_FORWARD)) std::cout << "\t done bwt construction, generating .sai file\n";
+    if (!(flags & PBSC_BUILD_NO_REVERSE)) std::cout << "\t done rbwt construction, generating .rsai file\n";
+    all.release();
+    char line[160];
+    snprintf(line, sizeof line, "[timer - Build FM index] wall clock: %.2fs CPU: %.2fs\n",
+             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), (double)(clock() - c0) / CLOCKS_PER_SEC);
+    std::cerr << line;
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    // `pbcorrect index ...` = `stride index ...`
+    if (argc > 1 && std::string(argv[1]) == "index") return indexMain(argc - 1, argv + 1);
     // accept both `pbcorrect [opts] READS` and `pbcorrect pbcorrect [opts] READS` (as `stride pbcorrect`)
     if (argc > 1 && std::string(argv[1]) == "pbcorrect") { argv++; argc--; }
     parseOptions(argc, argv);

@@ -232,6 +232,22 @@ setup_tasks_kernel(const __grid_constant__ FmIndexDev idx, const __grid_constant
     tw::setup_task(idx, P, v, qlen, (uint32_t)k, interval, trgLen, tk.out_cap);
 }
 
+// -DPBSC_STAGE_CLOCKS: a measurement build (tools/stage_clocks.py) that adds up, per warp, the clock64() time of every stage of the
+// level loop, the iterations, the walking lanes and the leaves dealt out by the pooled stages.  Not for timing runs.
+#ifdef PBSC_STAGE_CLOCKS
+#define PBSC_N_STAGE 24
+__device__ unsigned long long g_stage_clk[PBSC_N_STAGE];
+#define STAGE_BEGIN() long long stg_t = clock64(); unsigned long long stg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define STAGE_MARK(i) do { const long long stg_n = clock64(); stg_acc[i] += (unsigned long long)(stg_n - stg_t); stg_t = stg_n; } while (0)
+#define STAGE_COUNT(i, v) do { const unsigned stg_v = __reduce_add_sync(FULL, (unsigned)(v)); stg_acc[i] += stg_v; } while (0)
+#define STAGE_END() do { if ((threadIdx.x & 31) == 0) for (int stg_i = 0; stg_i < 12; stg_i++) atomicAdd(&g_stage_clk[stg_i], stg_acc[stg_i]); } while (0)
+#else
+#define STAGE_BEGIN()
+#define STAGE_MARK(i)
+#define STAGE_COUNT(i, v)
+#define STAGE_END()
+#endif
+
 // Level loop.  Every lane owns one walk at a time; all lanes of a warp run the same loop (one level of extendOverlap per
 // iteration), and a lane whose walk ended picks the next task at the top of the next iteration, so the warp stays converged
 // at the granularity of a level.
@@ -261,6 +277,7 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
     constexpr int REFILL_BATCH = 1;
     bool active = false, ended = false, exhausted = !owner;
     unsigned long long done = 0;
+    STAGE_BEGIN();
     for (;;)
     {
         const unsigned waiting = __ballot_sync(FULL, !active && !exhausted);
@@ -303,18 +320,25 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
         if (__all_sync(FULL, !active)) break;   // only reached with nobody waiting either: every lane is exhausted
         // ---- one level of extendOverlap's loop for every walking lane; the stages that touch the index or the per-walk
         //      tables are pooled over the warp (pbsc_walk_thread.cuh) ----
+        STAGE_MARK(0);                                    // filing results, next task, begin_walk
         const bool lv = active && tw::walk_continues(S, P);
         {
             const bool need = lv && tw::needs_refine(S);
+            STAGE_COUNT(9, 1u);                           // [9] lane-iterations (32 per warp iteration)
+            STAGE_COUNT(10, lv ? 1u : 0u);                // [10] walking lanes
+            STAGE_COUNT(11, lv ? S.n : 0u);               // [11] leaves probed
             tw::refine_pool(idx, Y, ctx, need ? S.n : 0u);
             if (need) S.curK = S.maxOverlap;
         }
+        STAGE_MARK(1);
         if (lv)
         {
             tw::filter_leaves(S, Y);
             S.thr = S.phase == 2 ? S.minSA - 1 : S.minSA;
         }
+        STAGE_MARK(2);
         tw::pool_run(lv ? S.n : 0u, [&](int owner_lane, uint32_t i) { tw::probe_leaf(idx, Y, ctx[owner_lane], i); });
+        STAGE_MARK(3);
         uint32_t m = 0, sel = 0;
         bool go = false;
         if (lv)
@@ -322,20 +346,26 @@ walk_levels_body(const FmIndexDev& idx, const ExtParamsDev& P, uint8_t* scratch,
             m = tw::adopt_children(S, Y);
             if (S.status == 0) go = tw::level_middle(S, Y, P, m, sel);
         }
+        STAGE_MARK(4);
         if (__any_sync(FULL, sel != 0))
         {
             tw::pool_run(sel, [&](int owner_lane, uint32_t i) { tw::select_leaf(idx, Y, ctx[owner_lane], i); });
             if (sel) tw::level_select(S, P);
             tw::pool_run(sel, [&](int owner_lane, uint32_t i) { tw::reselect_leaf(idx, Y, ctx[owner_lane], i); });
         }
+        STAGE_MARK(5);
         // (prune_leaf reads the walk's curLen after curLen++ and its level before level++)
         tw::pool_run(go ? m : 0u, [&](int owner_lane, uint32_t j) { tw::prune_leaf(P, Y, ctx[owner_lane], j); });
+        STAGE_MARK(6);
         bool check_term = false;
         if (go) { S.level++; check_term = S.curLen >= S.minLength; }
         tw::pool_run(check_term ? m : 0u, [&](int owner_lane, uint32_t j) { tw::term_leaf(Y, ctx[owner_lane], j); });
+        STAGE_MARK(7);
         if (go) tw::finish_level(S, Y, P, m, check_term);
         if (active && !tw::walk_continues(S, P)) { active = false; ended = true; }
+        STAGE_MARK(8);
     }
+    STAGE_END();
     if (done) atomicAdd(walk_counter, done);
 }
 
@@ -977,6 +1007,20 @@ int run_extend_threads(pbsc_index* idx, const pbsc_params* p, DeviceBatch& b, Se
                 fprintf(stderr, "[pbsc round trace] walk launch %zu: %s pass, %llu items, %.2f ms\n", i / 2, E.ev_what[i / 2].first, (unsigned long long)E.ev_what[i / 2].second, ms);
         }
     }
+#ifdef PBSC_STAGE_CLOCKS
+    {
+        unsigned long long h[PBSC_N_STAGE], z[PBSC_N_STAGE] = {0};
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_stage_clk, sizeof h);
+        cudaMemcpyToSymbol(g_stage_clk, z, sizeof z);
+        static const char* names[9] = {"refill", "refine", "filter", "probe", "adopt+middle", "select", "prune", "term", "finish"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 9; i++) tot += h[i];
+        fprintf(stderr, "[pbsc stage clocks] warp-cycles %llu; lane-iterations %llu, walking %.1f %%, leaves per walking lane %.2f\n", tot, h[9],
+                h[9] ? 100.0 * (double)h[10] / (double)h[9] : 0.0, h[10] ? (double)h[11] / (double)h[10] : 0.0);
+        for (int i = 0; i < 9; i++) fprintf(stderr, "[pbsc stage clocks]   %-14s %5.1f %%\n", names[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
+    }
+#endif
     return PBSC_OK;
 }
 

@@ -154,6 +154,18 @@ def test_bwt_builder_equals_reference_index(oracle_bin, tmp_path):
         assert got == open(os.path.join(GOLDEN, f"tiny.fm_{ext}.txt")).read()
 
 
+@pytest.mark.parametrize("name,fasta", [("tiny", "tiny.reads.fa"), ("index_edge", "index_edge.fa")])
+def test_index_builder_model_reproduces_reference_files(name, fasta, tmp_path):
+    """oracle/index_model.py (the GPU builder's algorithm, step by step, in numpy) writes the reference's four index files byte
+    for byte: tests/golden/<name>.{bwt,rbwt,sai,rsai} were written by `oracle/_ref/stride index`."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import index_model
+    codes, off = index_model.read_fasta_codes(os.path.join(GOLDEN, fasta))
+    index_model.build(str(tmp_path / "m"), codes, off)
+    for ext in ("bwt", "rbwt", "sai", "rsai"):
+        assert open(tmp_path / f"m.{ext}", "rb").read() == open(os.path.join(GOLDEN, f"{name}.{ext}"), "rb").read(), ext
+
+
 def test_cli_option_errors():
     exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
     if not os.path.exists(exe):

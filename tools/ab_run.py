@@ -8,7 +8,7 @@ the index is re-created from the same run-length BWTs (some knobs are read when 
 uploaded, `reps` passes are timed (CUDA events inside the library) and the median is printed with the phase times of
 `pbsc_last_timing`.  Example:
 
-    python tools/ab_run.py base l2_60:PBSC_L2_PERSIST=60 l2_100:PBSC_L2_PERSIST=100 nodpthread:PBSC_DP_THREAD=0
+    python tools/ab_run.py base l2_60:PBSC_L2_PERSIST=60 l2_100:PBSC_L2_PERSIST=100 nodpthread:PBSC_DP_THREAD=0 k15:K0=15
 """
 import argparse
 import os
@@ -56,12 +56,14 @@ def main():
     print(f"workload {args.workload}: {n} reads, {mbp:.1f} Mbp, reps {args.reps}, dp {'off' if args.nodp else 'on'}")
     print(f"{'variant':24s} {'ms':>9s} {'Mbp/s':>8s}  " + " ".join(f"{k:>14s}" for k in keys))
     for name, env in variants:
+        env = dict(env)
+        k0 = int(env.pop("K0", args.k0))   # `K0=15` in a variant: that variant's short-prefix table length
         saved = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
             idx = api.Index.from_runs(runs["bwt"][0], runs["bwt"][1], n, runs["rbwt"][0], runs["rbwt"][1], n)
-            if args.k0:
-                idx.build_prefix_table(args.k0)
+            if k0:
+                idx.build_prefix_table(k0)
             p = api.Params.make(coverage=wl["c"], genome=wl["g"], no_dp=args.nodp)
             batch = api.Batch(idx, p, packed=packed)
             batch.run()   # warm-up: grow-only arenas, learned capacities
