@@ -280,11 +280,29 @@ static cudaError_t select_positions(uint64_t N, Pred pred, uint32_t* out, uint64
 
 struct Result
 {
-    std::vector<uint8_t> runs;     // RLUnit bytes
+    uint8_t* runs = nullptr;       // RLUnit bytes (malloc: handed to the caller of pbsc_build_bwt as it is)
+    uint64_t n_runs = 0;
     std::vector<uint32_t> lex;     // read index of the r-th '$' of the BWT
     uint64_t n_symbols = 0;
     int rounds_max = 0;
     double ms_text = 0, ms_sort = 0, ms_bwt = 0;
+    ~Result() { free(runs); }
+    uint8_t* take_runs() { uint8_t* r = runs; runs = nullptr; return r; }
+};
+
+// one device allocation carved into the buffers of a phase (cudaMalloc / cudaFree of twenty buffers per strand cost more than the sort)
+struct Arena
+{
+    Buf mem; size_t used = 0;
+    template <class T> T* take(size_t count)
+    {
+        const size_t b = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (used + b > mem.bytes) return nullptr;
+        T* p = (T*)((char*)mem.p + used);
+        used += b;
+        return p;
+    }
+    void reset() { used = 0; }
 };
 
 #define BUILD_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return pbsc::cuda_fail(_e, #call, __FILE__, __LINE__); } while (0)
@@ -323,23 +341,26 @@ static int build_strand(const char* d_reads, const uint64_t* d_offsets, const ui
     uint64_t M = 0;
     for (int b = 0; b < N_BUCKETS; b++) M = std::max<uint64_t>(M, hist[b]);
     if (M >= 0x7fffffffull) { set_error("pbsc_build: a bucket of %llu suffixes is outside this build's range", (unsigned long long)M); return PBSC_ERR_LIMIT; }
-    // scratch of one bucket
-    Buf P, R, T, K, K2, I, I2, I3, RK, RK2, Pn, Rn, Kn, Tn, s1, s2, s3, s4, tmp;
-    BUILD_CUDA(P.alloc(M * 4)); BUILD_CUDA(R.alloc(M * 4)); BUILD_CUDA(T.alloc(M));
-    BUILD_CUDA(K.alloc(M * 8)); BUILD_CUDA(K2.alloc(M * 8));
-    BUILD_CUDA(I.alloc(M * 4)); BUILD_CUDA(I2.alloc(M * 4)); BUILD_CUDA(I3.alloc(M * 4));
-    BUILD_CUDA(RK.alloc(M * 4)); BUILD_CUDA(RK2.alloc(M * 4));
-    BUILD_CUDA(Pn.alloc(M * 4)); BUILD_CUDA(Rn.alloc(M * 4)); BUILD_CUDA(Kn.alloc(M * 8)); BUILD_CUDA(Tn.alloc(M));
-    BUILD_CUDA(s1.alloc(M * 4)); BUILD_CUDA(s2.alloc(M * 4)); BUILD_CUDA(s3.alloc(M * 4)); BUILD_CUDA(s4.alloc(M * 4));
+    // scratch: one arena, sized for the larger of the two phases (a bucket's rounds; the BWT and its run-length units)
+    size_t sort_tmp = 0;
     {
-        // temporary storage: the largest request of the calls below
         size_t a = 0, b2 = 0, c = 0, d = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, a, K.as<uint64_t>(), K2.as<uint64_t>(), I.as<uint32_t>(), I2.as<uint32_t>(), (int)M, 0, 63, st);
-        cub::DeviceRadixSort::SortPairs(nullptr, b2, RK.as<uint32_t>(), RK2.as<uint32_t>(), I2.as<uint32_t>(), I3.as<uint32_t>(), (int)M, 0, 32, st);
-        cub::DeviceScan::InclusiveScan(nullptr, c, s1.as<uint32_t>(), s2.as<uint32_t>(), cub::Max(), (int)M, st);
-        cub::DeviceScan::ExclusiveSum(nullptr, d, s1.as<uint32_t>(), s2.as<uint32_t>(), (int)M, st);
-        BUILD_CUDA(tmp.alloc(std::max(std::max(a, b2), std::max(c, d)) + 256));
+        cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)M, 0, 63, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, b2, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)M, 0, 32, st);
+        cub::DeviceScan::InclusiveScan(nullptr, c, (uint32_t*)nullptr, (uint32_t*)nullptr, cub::Max(), (int)M, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, d, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)M, st);
+        sort_tmp = std::max(std::max(a, b2), std::max(c, d)) + 256;
     }
+    Arena A;
+    Buf tmp;
+    BUILD_CUDA(tmp.alloc(sort_tmp));
+    BUILD_CUDA(A.mem.alloc(std::max<size_t>((size_t)M * 82 + 20 * 256, (size_t)N * 9 + (size_t)n * 8 + 8 * 256)));
+    uint32_t *P = A.take<uint32_t>(M), *R = A.take<uint32_t>(M), *I = A.take<uint32_t>(M), *I2 = A.take<uint32_t>(M), *I3 = A.take<uint32_t>(M),
+             *RK = A.take<uint32_t>(M), *RK2 = A.take<uint32_t>(M), *Pn = A.take<uint32_t>(M), *Rn = A.take<uint32_t>(M), *s1 = A.take<uint32_t>(M),
+             *s2 = A.take<uint32_t>(M), *s3 = A.take<uint32_t>(M), *s4 = A.take<uint32_t>(M);
+    uint64_t *K = A.take<uint64_t>(M), *K2 = A.take<uint64_t>(M), *Kn = A.take<uint64_t>(M);
+    uint8_t *T = A.take<uint8_t>(M), *Tn = A.take<uint8_t>(M);
+    if (!Tn) { set_error("pbsc_build: scratch arena too small"); return PBSC_ERR_INTERNAL; }
     uint64_t row0 = 0;
     for (int b = 0; b < N_BUCKETS; b++)
     {
@@ -347,42 +368,42 @@ static int build_strand(const char* d_reads, const uint64_t* d_offsets, const ui
         if (m == 0) continue;
         uint64_t got = 0;
         InBucket pred{text.as<uint8_t>(), 0, b};
-        BUILD_CUDA(select_positions(N, pred, P.as<uint32_t>(), M, &got, tmp, d_count, st));
+        BUILD_CUDA(select_positions(N, pred, P, M, &got, tmp, d_count, st));
         if (got != m) { set_error("pbsc_build: bucket %d holds %llu suffixes, expected %llu", b, (unsigned long long)got, (unsigned long long)m); return PBSC_ERR_INTERNAL; }
-        fill_kernel<<<grid_for(m), 256, 0, st>>>(R.as<uint32_t>(), T.as<uint8_t>(), m, (uint32_t)row0);
+        fill_kernel<<<grid_for(m), 256, 0, st>>>(R, T, m, (uint32_t)row0);
         row0 += m;
         uint32_t off = 0;
         int round = 0;
         while (m)
         {
-            keys_kernel<<<grid_for(m), 256, 0, st>>>(m, P.as<uint32_t>(), T.as<uint8_t>(), off, text.as<uint8_t>(), N, dollar.as<uint32_t>(), (uint32_t)n,
-                                                     K.as<uint64_t>(), I.as<uint32_t>());
+            keys_kernel<<<grid_for(m), 256, 0, st>>>(m, P, T, off, text.as<uint8_t>(), N, dollar.as<uint32_t>(), (uint32_t)n,
+                                                     K, I);
             size_t tb = tmp.bytes;
-            BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, K.as<uint64_t>(), K2.as<uint64_t>(), I.as<uint32_t>(), I2.as<uint32_t>(), (int)m, 0, 63, st));
-            const uint32_t* order = I2.as<uint32_t>();
+            BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, K, K2, I, I2, (int)m, 0, 63, st));
+            const uint32_t* order = I2;
             if (round > 0)
             {
-                gather_u32_kernel<<<grid_for(m), 256, 0, st>>>(m, R.as<uint32_t>(), I2.as<uint32_t>(), RK.as<uint32_t>());
+                gather_u32_kernel<<<grid_for(m), 256, 0, st>>>(m, R, I2, RK);
                 tb = tmp.bytes;
-                BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, RK.as<uint32_t>(), RK2.as<uint32_t>(), I2.as<uint32_t>(), I3.as<uint32_t>(), (int)m, 0, 32, st));
-                order = I3.as<uint32_t>();
+                BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, RK, RK2, I2, I3, (int)m, 0, 32, st));
+                order = I3;
             }
-            reorder_kernel<<<grid_for(m), 256, 0, st>>>(m, order, P.as<uint32_t>(), R.as<uint32_t>(), K.as<uint64_t>(), T.as<uint8_t>(), Pn.as<uint32_t>(),
-                                                        Rn.as<uint32_t>(), Kn.as<uint64_t>(), Tn.as<uint8_t>());
-            old_heads_kernel<<<grid_for(m), 256, 0, st>>>(m, Rn.as<uint32_t>(), s1.as<uint32_t>());
+            reorder_kernel<<<grid_for(m), 256, 0, st>>>(m, order, P, R, K, T, Pn,
+                                                        Rn, Kn, Tn);
+            old_heads_kernel<<<grid_for(m), 256, 0, st>>>(m, Rn, s1);
             tb = tmp.bytes;
-            BUILD_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, s1.as<uint32_t>(), s2.as<uint32_t>(), cub::Max(), (int)m, st));      // s2 = start of the old group
-            rows_kernel<<<grid_for(m), 256, 0, st>>>(m, Rn.as<uint32_t>(), Kn.as<uint64_t>(), s2.as<uint32_t>(), s3.as<uint32_t>(), s1.as<uint32_t>());   // s3 = row, s1 = new heads
+            BUILD_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, s1, s2, cub::Max(), (int)m, st));      // s2 = start of the old group
+            rows_kernel<<<grid_for(m), 256, 0, st>>>(m, Rn, Kn, s2, s3, s1);   // s3 = row, s1 = new heads
             tb = tmp.bytes;
-            BUILD_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, s1.as<uint32_t>(), s2.as<uint32_t>(), cub::Max(), (int)m, st));      // s2 = start of the new group
-            resolve_kernel<<<grid_for(m), 256, 0, st>>>(m, Pn.as<uint32_t>(), s2.as<uint32_t>(), s3.as<uint32_t>(), sa.as<uint32_t>(), s1.as<uint32_t>(), d_flags + 1);   // s1 = keep
+            BUILD_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, s1, s2, cub::Max(), (int)m, st));      // s2 = start of the new group
+            resolve_kernel<<<grid_for(m), 256, 0, st>>>(m, Pn, s2, s3, sa.as<uint32_t>(), s1, d_flags + 1);   // s1 = keep
             tb = tmp.bytes;
-            BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, s1.as<uint32_t>(), s4.as<uint32_t>(), (int)m, st));                    // s4 = slot in the next round
-            compact_kernel<<<grid_for(m), 256, 0, st>>>(m, s1.as<uint32_t>(), s4.as<uint32_t>(), Pn.as<uint32_t>(), s2.as<uint32_t>(), s3.as<uint32_t>(),
-                                                        Kn.as<uint64_t>(), Tn.as<uint8_t>(), P.as<uint32_t>(), R.as<uint32_t>(), T.as<uint8_t>(), d_flags + 1);
+            BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, s1, s4, (int)m, st));                    // s4 = slot in the next round
+            compact_kernel<<<grid_for(m), 256, 0, st>>>(m, s1, s4, Pn, s2, s3,
+                                                        Kn, Tn, P, R, T, d_flags + 1);
             uint32_t last[2] = {0, 0};
-            BUILD_CUDA(cudaMemcpyAsync(&last[0], s1.as<uint32_t>() + (m - 1), 4, cudaMemcpyDeviceToHost, st));
-            BUILD_CUDA(cudaMemcpyAsync(&last[1], s4.as<uint32_t>() + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+            BUILD_CUDA(cudaMemcpyAsync(&last[0], s1 + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+            BUILD_CUDA(cudaMemcpyAsync(&last[1], s4 + (m - 1), 4, cudaMemcpyDeviceToHost, st));
             BUILD_CUDA(cudaStreamSynchronize(st));
             const uint64_t left = (uint64_t)last[0] + last[1];
             if (trace) fprintf(stderr, "[pbsc build] %s bucket %2d round %d: %llu suffixes, %llu left\n", reverse ? "rbwt" : "bwt", b, round, (unsigned long long)m, (unsigned long long)left);
@@ -398,50 +419,57 @@ static int build_strand(const char* d_reads, const uint64_t* d_offsets, const ui
     if (flags[1]) { set_error("pbsc_build: %u suffixes tied after the comparison by read index", flags[1]); return PBSC_ERR_INTERNAL; }
     if (row0 != N) { set_error("pbsc_build: buckets hold %llu of %llu suffixes", (unsigned long long)row0, (unsigned long long)N); return PBSC_ERR_INTERNAL; }
     out.ms_sort = lap();
-    P.release(); R.release(); T.release(); K.release(); K2.release(); I.release(); I2.release(); I3.release(); RK.release(); RK2.release();
-    Pn.release(); Rn.release(); Kn.release(); Tn.release(); s1.release(); s2.release(); s3.release(); s4.release();
-    // ---- BWT and its run-length units ----
-    Buf bwt, starts, units, first, bytes, rows, lex;
-    BUILD_CUDA(bwt.alloc(N));
-    bwt_kernel<<<grid_for(N), 256, 0, st>>>(N, sa.as<uint32_t>(), text.as<uint8_t>(), bwt.as<uint8_t>());
-    BUILD_CUDA(starts.alloc(N * 4));
+    // ---- BWT, lexicographic read order (the read of the r-th '$' row), run-length units ----
+    double ms_part[6] = {0, 0, 0, 0, 0, 0};
+    A.reset();
+    uint8_t* bwt = A.take<uint8_t>(N);
+    uint32_t* rows = A.take<uint32_t>(n);
+    uint32_t* lex = A.take<uint32_t>(n);
+    bwt_kernel<<<grid_for(N), 256, 0, st>>>(N, sa.as<uint32_t>(), text.as<uint8_t>(), bwt);
+    uint64_t n_dollar = 0;
+    IsDollar isd{bwt, 0};
+    BUILD_CUDA(select_positions(N, isd, rows, n, &n_dollar, tmp, d_count, st));
+    if (n_dollar != n) { set_error("pbsc_build: %llu '$' in the BWT of %llu reads", (unsigned long long)n_dollar, (unsigned long long)n); return PBSC_ERR_INTERNAL; }
+    lex_kernel<<<grid_for(n), 256, 0, st>>>(n, rows, sa.as<uint32_t>(), dollar.as<uint32_t>(), lex);
+    out.lex.resize(n);
+    BUILD_CUDA(cudaMemcpyAsync(out.lex.data(), lex, n * 4, cudaMemcpyDeviceToHost, st));
+    if (trace) ms_part[0] = lap();
+    // the suffix array and the text are not needed any more: their memory holds the run starts and the unit bytes
+    uint32_t* starts = sa.as<uint32_t>();
+    uint8_t* bytes = text.as<uint8_t>();
     uint64_t n_runs = 0;
-    RunHead rh{bwt.as<uint8_t>(), 0};
-    BUILD_CUDA(select_positions(N, rh, starts.as<uint32_t>(), N, &n_runs, tmp, d_count, st));
-    BUILD_CUDA(units.alloc(n_runs * 4 + 4));
-    BUILD_CUDA(first.alloc(n_runs * 4 + 4));
-    run_units_kernel<<<grid_for(n_runs), 256, 0, st>>>(n_runs, starts.as<uint32_t>(), N, units.as<uint32_t>());
+    RunHead rh{bwt, 0};
+    BUILD_CUDA(select_positions(N, rh, starts, N, &n_runs, tmp, d_count, st));
+    if (n_runs >= 0x7fffffffull) { set_error("pbsc_build: %llu runs are outside this build's range", (unsigned long long)n_runs); return PBSC_ERR_LIMIT; }
+    if (trace) ms_part[1] = lap();
+    uint32_t* units = A.take<uint32_t>(n_runs + 1);
+    uint32_t* first = A.take<uint32_t>(n_runs + 1);
+    if (!first) { set_error("pbsc_build: scratch arena too small"); return PBSC_ERR_INTERNAL; }
+    run_units_kernel<<<grid_for(n_runs), 256, 0, st>>>(n_runs, starts, N, units);
     {
         size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, units.as<uint32_t>(), first.as<uint32_t>(), (int)n_runs, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, units, first, (int)n_runs, st);
         if (tmp.bytes < tb) BUILD_CUDA(tmp.alloc(tb));
         tb = tmp.bytes;
-        if (n_runs >= 0x7fffffffull) { set_error("pbsc_build: %llu runs are outside this build's range", (unsigned long long)n_runs); return PBSC_ERR_LIMIT; }
-        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, units.as<uint32_t>(), first.as<uint32_t>(), (int)n_runs, st));
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, units, first, (int)n_runs, st));
     }
     uint32_t lastu[2] = {0, 0};
-    BUILD_CUDA(cudaMemcpyAsync(&lastu[0], units.as<uint32_t>() + (n_runs - 1), 4, cudaMemcpyDeviceToHost, st));
-    BUILD_CUDA(cudaMemcpyAsync(&lastu[1], first.as<uint32_t>() + (n_runs - 1), 4, cudaMemcpyDeviceToHost, st));
+    BUILD_CUDA(cudaMemcpyAsync(&lastu[0], units + (n_runs - 1), 4, cudaMemcpyDeviceToHost, st));
+    BUILD_CUDA(cudaMemcpyAsync(&lastu[1], first + (n_runs - 1), 4, cudaMemcpyDeviceToHost, st));
     BUILD_CUDA(cudaStreamSynchronize(st));
     const uint64_t n_units = (uint64_t)lastu[0] + lastu[1];
-    BUILD_CUDA(bytes.alloc(n_units));
-    run_bytes_kernel<<<grid_for(n_runs), 256, 0, st>>>(n_runs, starts.as<uint32_t>(), first.as<uint32_t>(), N, bwt.as<uint8_t>(), bytes.as<uint8_t>());
-    out.runs.resize(n_units);
-    BUILD_CUDA(cudaMemcpyAsync(out.runs.data(), bytes.p, n_units, cudaMemcpyDeviceToHost, st));
-    // ---- lexicographic read order: the read of the r-th '$' row ----
-    starts.release(); units.release(); first.release();
-    BUILD_CUDA(rows.alloc(n * 4 + 4));
-    BUILD_CUDA(lex.alloc(n * 4 + 4));
-    uint64_t n_dollar = 0;
-    IsDollar isd{bwt.as<uint8_t>(), 0};
-    BUILD_CUDA(select_positions(N, isd, rows.as<uint32_t>(), n, &n_dollar, tmp, d_count, st));
-    if (n_dollar != n) { set_error("pbsc_build: %llu '$' in the BWT of %llu reads", (unsigned long long)n_dollar, (unsigned long long)n); return PBSC_ERR_INTERNAL; }
-    lex_kernel<<<grid_for(n), 256, 0, st>>>(n, rows.as<uint32_t>(), sa.as<uint32_t>(), dollar.as<uint32_t>(), lex.as<uint32_t>());
-    out.lex.resize(n);
-    BUILD_CUDA(cudaMemcpyAsync(out.lex.data(), lex.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n_units > N) { set_error("pbsc_build: %llu run-length units for %llu symbols", (unsigned long long)n_units, (unsigned long long)N); return PBSC_ERR_INTERNAL; }
+    run_bytes_kernel<<<grid_for(n_runs), 256, 0, st>>>(n_runs, starts, first, N, bwt, bytes);
+    if (trace) ms_part[2] = lap();
+    out.runs = (uint8_t*)malloc(n_units ? n_units : 1);
+    if (!out.runs) { set_error("pbsc_build: out of host memory"); return PBSC_ERR_LIMIT; }
+    out.n_runs = n_units;
+    BUILD_CUDA(cudaMemcpyAsync(out.runs, bytes, n_units, cudaMemcpyDeviceToHost, st));
     BUILD_CUDA(cudaStreamSynchronize(st));
     BUILD_CUDA(cudaGetLastError());
-    out.ms_bwt = lap();
+    if (trace) { ms_part[3] = lap(); fprintf(stderr, "[pbsc build]   bwt + read order %.1f ms, run starts %.1f ms, units %.1f ms, copy to host %.1f ms\n", ms_part[0], ms_part[1], ms_part[2], ms_part[3]); }
+    out.ms_bwt = ms_part[0] + ms_part[1] + ms_part[2] + ms_part[3];
+    if (!trace) out.ms_bwt = lap();
     if (trace) fprintf(stderr, "[pbsc build] %s: %llu symbols, %llu units; text %.0f ms, suffix sort %.0f ms (deepest bucket %d rounds), bwt + units %.0f ms\n",
                        reverse ? "rbwt" : "bwt", (unsigned long long)N, (unsigned long long)n_units, out.ms_text, out.ms_sort, out.rounds_max, out.ms_bwt);
     return PBSC_OK;
@@ -453,10 +481,10 @@ static int write_bwt_file(const std::string& path, const Result& r, uint64_t n_r
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) { set_error("pbsc_build: cannot write %s", path.c_str()); return PBSC_ERR_IO; }
     const uint16_t magic = 0xCACA;
-    const uint64_t ns = n_reads, nsym = r.n_symbols, nr = r.runs.size();
+    const uint64_t ns = n_reads, nsym = r.n_symbols, nr = r.n_runs;
     const uint32_t flag = 0;
     bool ok = fwrite(&magic, 2, 1, f) == 1 && fwrite(&ns, 8, 1, f) == 1 && fwrite(&nsym, 8, 1, f) == 1 && fwrite(&nr, 8, 1, f) == 1 && fwrite(&flag, 4, 1, f) == 1;
-    ok = ok && (r.runs.empty() || fwrite(r.runs.data(), 1, r.runs.size(), f) == r.runs.size());
+    ok = ok && (r.n_runs == 0 || fwrite(r.runs, 1, r.n_runs, f) == r.n_runs);
     ok = (fclose(f) == 0) && ok;
     if (!ok) { set_error("pbsc_build: short write to %s", path.c_str()); return PBSC_ERR_IO; }
     return PBSC_OK;
@@ -519,12 +547,11 @@ int pbsc_build_bwt(const char* reads, const uint64_t* offsets, uint64_t n_reads,
         build::Result r;
         rc = build::build_strand(up.reads.as<char>(), up.offsets.as<uint64_t>(), offsets, n_reads, reverse, r);
         if (rc != PBSC_OK) return rc;
-        uint8_t* o = (uint8_t*)malloc(r.runs.size() ? r.runs.size() : 1);
         uint32_t* l = lex_order ? (uint32_t*)malloc((r.lex.size() ? r.lex.size() : 1) * 4) : nullptr;
-        if (!o || (lex_order && !l)) { free(o); free(l); set_error("pbsc_build_bwt: out of host memory"); return PBSC_ERR_LIMIT; }
-        memcpy(o, r.runs.data(), r.runs.size());
+        if (lex_order && !l) { set_error("pbsc_build_bwt: out of host memory"); return PBSC_ERR_LIMIT; }
         if (l) memcpy(l, r.lex.data(), r.lex.size() * 4);
-        *runs = o; *n_runs = r.runs.size(); *n_symbols = r.n_symbols;
+        *n_runs = r.n_runs; *n_symbols = r.n_symbols;
+        *runs = r.take_runs();
         if (lex_order) *lex_order = l;
         return PBSC_OK;
     });
