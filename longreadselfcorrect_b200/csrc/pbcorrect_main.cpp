@@ -23,6 +23,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include "pbsc_bcode.h"
 #include "pbsc.h"
 
 #define SUBPROGRAM "PacBioSelfCorrection"
@@ -170,11 +171,6 @@ static void parseOptions(int argc, char** argv)
     if (P.mode < 0 || P.mode > 2) { std::cerr << SUBPROGRAM ": invalid mode: " << P.mode << ", must be (0/1/2)\n"; die = true; }
     if (opt::OnlySeed && opt::barcode.empty()) { std::cerr << SUBPROGRAM ": no barcode\n"; die = true; }
     if (die) { std::cerr << "\n" << CORRECT_USAGE_MESSAGE; exit(EXIT_FAILURE); }
-    if (opt::OnlySeed)
-    {
-        std::cerr << SUBPROGRAM ": --onlyseed (seed validation against an alignment barcode, PacBio/BCode.cpp) is not part of this build\n";
-        exit(EXIT_FAILURE);
-    }
     if (opt::DebugSeed)
     {
         // StriDe/PacBioSelfCorrection.cpp:351-361
@@ -376,7 +372,7 @@ static void writeDebugFiles(const Batch& b)
             const uint64_t L = b.offsets[r + 1] - b.offsets[r];
             for (uint64_t p = 0; p < L; p++) f << p << '\t' << b.dbg_ratio[b.offsets[r] + p] << '\n';
         }
-        if (nsurv >= 2)
+        if (nsurv >= 2 && !opt::OnlySeed)   // --onlyseed stops before the walks (PacBioSelfCorrectionProcess.cpp:58-62): no .ext / .dp
         {
             std::ofstream x((opt::directory + "extend/" + b.ids[r] + ".ext").c_str()), d((opt::directory + "extend/" + b.ids[r] + ".dp").c_str());
             for (uint64_t i = b.dbg_log_off[r]; i < b.dbg_log_off[r + 1]; i++)
@@ -474,8 +470,169 @@ static int indexMain(int argc, char** argv)
     return 0;
 }
 
+// ---- `pbcorrect kmercheck [OPTION] ... READSFILE`: `stride kmercheck` (StriDe/kmercheck.cpp:25-226, PacBio/KmerCheckProcess.cpp:12-63).
+// For every barcode block of every read and every k of the range, the frequency (both strands, KmerFeature.h:37-65) of each k-mer of
+// the block; the k-mers the barcode calls correct and the ones it calls wrong go to two histograms per k, summarised into
+// DIR/total.box and DIR/value.box (appended to, like the reference).  The frequencies are batched backward searches on the GPU
+// (pbsc_findinterval_batch); the barcode arithmetic and the histograms are host code (pbsc_bcode.h).
+static const char* KMERCHECK_USAGE_MESSAGE =
+"Usage: pbcorrect kmercheck [OPTION] ... READSFILE\n"
+"Get sequences kmer frequency\n"
+"  -t, --threads=NUM         Use NUM threads for the computation (default: 1)\n"
+"  -c, --coverage=NUM        Coverage of PacBio reads (default: 90)\n"
+"  -p, --prefix=PREFIX       Use PREFIX for the names of the index files\n"
+"  -o, --directory=PATH      Put results in the directory\n"
+"  -b, --barcode=FILE        Use the barcode to check kmer \n"
+"  -l, --lower=NUM           Kmer size lower bound (default: 15)\n"
+"  -u, --upper=NUM           Kmer size upper bound (default: 35)\n"
+"  -s, --step=NUM            Kmer size step (default: 1)\n"
+"  -v, --verbose             Display verbose output\n"
+"      --help                Display this help and exit\n"
+"      --version             Display version\n";
+
+static int kmercheckMain(int argc, char** argv)
+{
+    enum { KOPT_HELP = 1, KOPT_VERSION };
+    static const struct option kopts[] = {
+        {"threads", required_argument, nullptr, 't'}, {"coverage", required_argument, nullptr, 'c'}, {"prefix", required_argument, nullptr, 'p'},
+        {"directory", required_argument, nullptr, 'o'}, {"barcode", required_argument, nullptr, 'b'}, {"lower", required_argument, nullptr, 'l'},
+        {"upper", required_argument, nullptr, 'u'}, {"step", required_argument, nullptr, 's'}, {"verbose", no_argument, nullptr, 'v'},
+        {"help", no_argument, nullptr, KOPT_HELP}, {"version", no_argument, nullptr, KOPT_VERSION}, {nullptr, 0, nullptr, 0}};
+    int thread = 1, coverage = 90, lower = 15, upper = 35, step = 1;
+    std::string prefix, directory, barcode;
+    bool die = false;
+    optind = 1;
+    for (int c; (c = getopt_long(argc, argv, "t:c:p:o:b:l:u:s:v", kopts, nullptr)) != -1;)
+    {
+        std::istringstream arg(optarg != nullptr ? optarg : "");
+        switch (c)
+        {
+            case 't': arg >> thread; break;
+            case 'c': arg >> coverage; break;
+            case 'p': arg >> prefix; break;
+            case 'o': arg >> directory; break;
+            case 'b': arg >> barcode; break;
+            case 'l': arg >> lower; break;
+            case 'u': arg >> upper; break;
+            case 's': arg >> step; break;
+            case 'v': break;
+            case KOPT_HELP: std::cerr << KMERCHECK_USAGE_MESSAGE; exit(EXIT_SUCCESS);
+            case KOPT_VERSION: std::cerr << "kmercheck Version " PACKAGE_VERSION "\n\n"; exit(EXIT_SUCCESS);
+            default: die = true; break;
+        }
+    }
+    if (argc - optind < 1) { std::cerr << "kmercheck: missing arguments\n"; die = true; }
+    else if (argc - optind > 1) { std::cerr << "kmercheck: too many arguments\n"; die = true; }
+    if (thread <= 0) { std::cerr << "kmercheck: invalid number of threads: " << thread << "\n"; die = true; }
+    if (coverage <= 0) { std::cerr << "kmercheck: invalid coverage: " << coverage << "\n"; die = true; }
+    if (prefix.empty()) { std::cerr << "kmercheck: no prefix\n"; die = true; }
+    if (directory.empty()) { std::cerr << "kmercheck: no directory\n"; die = true; }
+    else
+    {
+        directory += "/";
+        if (system(("mkdir -p " + directory).c_str()) != 0) { std::cerr << "kmercheck: something wrong in directory: " << directory << "\n"; die = true; }
+    }
+    if (barcode.empty()) { std::cerr << "kmercheck: no barcode\n"; die = true; }
+    if (!(lower >= 9 && upper >= lower)) { std::cerr << "kmercheckinvalid range of kmer size:" << lower << " - " << upper << '\n'; die = true; }
+    if (step <= 0) { std::cerr << "kmercheckinvalid step size: " << step << '\n'; die = true; }
+    if (die) { std::cerr << "\n" << KMERCHECK_USAGE_MESSAGE; exit(EXIT_FAILURE); }
+    const std::string readsFile = argv[optind];
+    if (pbsc_device_count() <= 0) { std::cerr << "kmercheck: no CUDA device available (this build has no CPU path)\n"; return EXIT_FAILURE; }
+    std::cerr << "Loading BWT: " << prefix << ".bwt\n" << "Loading RBWT: " << prefix << ".rbwt\n";
+    pbsc_index* idx = nullptr;
+    int from_fmg = 0;
+    if (pbsc_index_open(prefix.c_str(), 0, 0, 13, 0, &from_fmg, &idx) != PBSC_OK) { std::cerr << pbsc_last_error() << "\n"; return EXIT_FAILURE; }
+    std::cerr << "Loading BARCODE: " << barcode << '\n';
+    pbsc::bcode::Table table;
+    std::string err;
+    if (!pbsc::bcode::load(barcode, table, err)) { std::cerr << "Error: " << err << "\n"; return EXIT_FAILURE; }
+    std::cerr << "Using kmer size : " << lower << " - " << upper << " (" << step << ")\n";
+    const auto t0 = std::chrono::steady_clock::now();
+    LineReader in(readsFile);
+    if (!in.ok()) { std::cerr << "Error: could not open " << readsFile << " for read\n"; return EXIT_FAILURE; }
+    std::map<int, pbsc::bcode::Histogram> crt, wrong;
+    // queries of one flush: both strands' strings of every k-mer, and where the answer goes
+    struct Query { uint32_t read; int32_t pos; int32_t k; uint32_t block; };
+    std::vector<Query> queries;
+    std::string fwd_s, rvc_s;                 // reverse(w) for the RBWT, reverse-complement(w) for the BWT, concatenated
+    std::vector<uint64_t> q_off(1, 0);
+    std::vector<std::string> seqs;            // reads of the current flush
+    std::vector<const std::vector<pbsc::bcode::Block>*> seq_blocks;
+    size_t nreads = 0;
+    int rc_all = 0;
+    auto flush = [&]() -> bool {
+        const uint64_t n = queries.size();
+        if (n)
+        {
+            std::vector<int64_t> lo(n), hi(n), lo2(n), hi2(n);
+            if (pbsc_findinterval_batch(idx, PBSC_RBWT, fwd_s.data(), q_off.data(), n, lo.data(), hi.data(), nullptr) != PBSC_OK ||
+                pbsc_findinterval_batch(idx, PBSC_BWT, rvc_s.data(), q_off.data(), n, lo2.data(), hi2.data(), nullptr) != PBSC_OK)
+            { std::cerr << "kmercheck: " << pbsc_last_error() << "\n"; return false; }
+            for (uint64_t i = 0; i < n; i++)
+            {
+                const Query& q = queries[i];
+                const int64_t freq = (hi[i] >= lo[i] ? hi[i] - lo[i] + 1 : 0) + (hi2[i] >= lo2[i] ? hi2[i] - lo2[i] + 1 : 0);
+                if (freq == 0) { std::cerr << "kmercheck: a k-mer of read " << q.read << " does not occur in the index (is " << prefix << " the index of these reads?)\n"; return false; }
+                if (freq == 1) continue;
+                bool ok;
+                try { ok = pbsc::bcode::validate(q.pos, q.k, (*seq_blocks[q.read])[q.block], seqs[q.read]); }
+                catch (const std::exception& e) { std::cerr << "kmercheck: " << e.what() << "\n"; return false; }
+                (ok ? crt : wrong)[q.k].add((int)freq);
+            }
+        }
+        queries.clear(); fwd_s.clear(); rvc_s.clear(); q_off.assign(1, 0); seqs.clear(); seq_blocks.clear();
+        return true;
+    };
+    for (;;)
+    {
+        Batch one;
+        one.bases = g_pins.get(1 << 16);
+        if (!readRecord(in, one)) { one.release(); break; }
+        std::string bad;
+        if (!normalize(one, bad)) { std::cerr << "kmercheck: read " << bad << " holds letters other than ACGT\n"; one.release(); rc_all = 1; break; }
+        nreads++;
+        pbsc::bcode::Table::const_iterator it = table.find(one.ids[0]);
+        if (it != table.end())
+        {
+            const uint32_t r = (uint32_t)seqs.size();
+            seqs.push_back(std::string(one.bases.p, one.n_bases));
+            seq_blocks.push_back(&it->second);
+            const std::string& seq = seqs.back();
+            for (uint32_t b = 0; b < it->second.size(); b++)
+                for (int k = lower; k <= upper; k += step)
+                    for (int pos = it->second[b].start; pos <= it->second[b].end - k; pos++)
+                    {
+                        if (pos < 0 || (size_t)(pos + k) > seq.size()) continue;   // KmerFeature::isFake: the reference asserts on these
+                        for (int j = k - 1; j >= 0; j--)
+                        {
+                            const char ch = seq[(size_t)(pos + j)];
+                            fwd_s += ch;
+                            rvc_s += ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : 'A';
+                        }
+                        q_off.push_back(fwd_s.size());
+                        queries.push_back(Query{r, pos, k, b});
+                    }
+        }
+        one.release();
+        if (fwd_s.size() > (64u << 20) && !flush()) { rc_all = 1; break; }
+    }
+    if (rc_all == 0 && !flush()) rc_all = 1;
+    pbsc_index_destroy(idx);
+    if (rc_all) return EXIT_FAILURE;
+    {
+        // KmerCheckPostProcess (KmerCheckProcess.cpp:42-53): both files are opened for appending
+        std::ofstream total_box((directory + "total.box").c_str(), std::ios_base::app), value_box((directory + "value.box").c_str(), std::ios_base::app);
+        for (int k = lower; k <= upper; k += step) pbsc::bcode::compare(total_box, value_box, coverage, k, crt[k], wrong[k]);
+    }
+    const double proc = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "Processed %zu sequences in %lfs (%lf sequences/s)\n", nreads, proc, (double)nreads / proc);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    // `pbcorrect kmercheck ...` = `stride kmercheck ...`
+    if (argc > 1 && std::string(argv[1]) == "kmercheck") return kmercheckMain(argc - 1, argv + 1);
     // `pbcorrect index ...` = `stride index ...`
     if (argc > 1 && std::string(argv[1]) == "index") return indexMain(argc - 1, argv + 1);
     // accept both `pbcorrect [opts] READS` and `pbcorrect pbcorrect [opts] READS` (as `stride pbcorrect`)
@@ -487,6 +644,15 @@ int main(int argc, char** argv)
     if (ndev <= 0) { std::cerr << SUBPROGRAM ": no CUDA device available (this build has no CPU path)\n"; return EXIT_FAILURE; }
     const int ngpu = opt::gpus > 0 ? std::min(opt::gpus, ndev) : ndev;
 
+    // StriDe/PacBioSelfCorrection.cpp:191 (BCode::load, PacBio/BCode.cpp:27-49)
+    pbsc::bcode::Table barcodes;
+    if (opt::OnlySeed)
+    {
+        std::cerr << "Loading BARCODE: " << opt::barcode << '\n';
+        std::string err;
+        if (!pbsc::bcode::load(opt::barcode, barcodes, err)) { std::cerr << "Error: " << err << "\n"; return EXIT_FAILURE; }
+        opt::params.no_dp = 1;   // nothing of the correction is reported in this mode: no reason to run the fallback
+    }
     auto t_load = std::chrono::steady_clock::now();
     std::cerr << "Loading BWT: " << opt::prefix << ".bwt\n" << "Loading RBWT: " << opt::prefix << ".rbwt\n"
               << "Loading Sampled Suffix Array: " << opt::prefix << ".sai\n";
@@ -529,12 +695,15 @@ int main(int argc, char** argv)
 
     LineReader in(opt::readsFile);
     if (!in.ok()) { std::cerr << "Error: could not open " << opt::readsFile << " for read\n"; return EXIT_FAILURE; }
-    FILE* correct = fopen((opt::directory + "correct.fa").c_str(), "wb");
-    FILE* discard = fopen((opt::directory + "discard.fa").c_str(), "wb");
-    if (!correct || !discard) { std::cerr << "Error: could not open output files in " << opt::directory << "\n"; return EXIT_FAILURE; }
+    // --onlyseed (PacBioSelfCorrectionProcess.cpp:265-287): DIR/total.seed instead of correct.fa / discard.fa
+    FILE* correct = opt::OnlySeed ? nullptr : fopen((opt::directory + "correct.fa").c_str(), "wb");
+    FILE* discard = opt::OnlySeed ? nullptr : fopen((opt::directory + "discard.fa").c_str(), "wb");
+    FILE* seed_status = opt::OnlySeed ? fopen((opt::directory + "total.seed").c_str(), "w") : nullptr;
+    if (opt::OnlySeed ? !seed_status : (!correct || !discard)) { std::cerr << "Error: could not open output files in " << opt::directory << "\n"; return EXIT_FAILURE; }
     std::vector<char> wbuf_c(8 << 20), wbuf_d(1 << 20);
-    setvbuf(correct, wbuf_c.data(), _IOFBF, wbuf_c.size());
-    setvbuf(discard, wbuf_d.data(), _IOFBF, wbuf_d.size());
+    if (correct) setvbuf(correct, wbuf_c.data(), _IOFBF, wbuf_c.size());
+    if (discard) setvbuf(discard, wbuf_d.data(), _IOFBF, wbuf_d.size());
+    size_t seed_total[3] = {0, 0, 0};
 
     auto t0 = std::chrono::steady_clock::now();
     // ---- pipeline (replaces Concurrency/SequenceProcessFramework.h:91-230):
@@ -657,7 +826,23 @@ int main(int argc, char** argv)
                 if (failed || written == produced) return;
                 b = at(written);
             }
-            for (size_t r = 0; r < b->ids.size(); r++)
+            for (size_t r = 0; r < b->ids.size() && opt::OnlySeed; r++)
+            {
+                // PacBioSelfCorrectionPostProcess::process, OnlySeed branch (:315-335): every surviving seed against the read's barcode blocks
+                size_t status[3] = {0, 0, 0};
+                const std::string seq(b->bases.p + b->offsets[r], (size_t)(b->offsets[r + 1] - b->offsets[r]));
+                pbsc::bcode::Table::const_iterator it = barcodes.find(b->ids[r]);
+                const pbsc_seed* sv = b->dbg_seeds.data() + b->dbg_seed_off[r];
+                try
+                {
+                    for (uint32_t i = 0; i < b->dbg_surv[r]; i++)
+                        status[pbsc::bcode::classify(it == barcodes.end() ? nullptr : &it->second, sv[i].start, sv[i].len, seq)]++;
+                }
+                catch (const std::exception& e) { fail(std::string(SUBPROGRAM ": read ") + b->ids[r] + ": " + e.what()); return; }
+                pbsc::bcode::summarize(seed_status, status, b->ids[r]);
+                for (int k = 0; k < 3; k++) seed_total[k] += status[k];
+            }
+            for (size_t r = 0; r < b->ids.size() && !opt::OnlySeed; r++)
             {
                 const pbsc_read_stats& st = b->stats[r];
                 if (st.merge)
@@ -735,7 +920,8 @@ int main(int argc, char** argv)
     { std::lock_guard<std::mutex> lk(mu); reading_done = true; }
     cv.notify_all();
     for (auto& t : threads) t.join();
-    fclose(correct); fclose(discard);
+    if (correct) fclose(correct);
+    if (discard) fclose(discard);
     for (auto* ix : index) pbsc_index_destroy(ix);
     if (failed) { std::cerr << fail_msg << "\n"; return EXIT_FAILURE; }
 
@@ -744,7 +930,12 @@ int main(int argc, char** argv)
     fprintf(stderr, "[timer - " PACKAGE_NAME "::" SUBPROGRAM "] wall clock: %.2fs, %.3f Mbp/s over %d GPU(s)\n", proc, inBases / 1e6 / proc, ngpu);
 
     // PacBioSelfCorrectionPostProcess::~PacBioSelfCorrectionPostProcess — PacBioSelfCorrectionProcess.cpp:281-311
-    if (totalWalkNum > 0 && totalReadsLen > 0)
+    if (opt::OnlySeed)
+    {
+        pbsc::bcode::summarize(stdout, seed_total, "TOTAL");
+        fclose(seed_status);
+    }
+    else if (totalWalkNum > 0 && totalReadsLen > 0)
     {
         int64_t OutcastNum = totalWalkNum - FMNum - DPNum;
         std::cout << "\n"

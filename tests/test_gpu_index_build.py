@@ -120,3 +120,36 @@ def test_cli_index_subcommand(tmp_path):
                        stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
     assert open(out / "correct.fa").read() == open(os.path.join(GOLDEN, "tiny.dp.correct.fa")).read()
+
+
+def test_cli_onlyseed(tmp_path):
+    """`pbcorrect --onlyseed -b BARCODE` (PacBioSelfCorrectionProcess.cpp:58-62,265-287,315-335; PacBio/BCode.cpp): seeds from the GPU,
+    validated on the host; DIR/total.seed and stdout equal the reference's, the seed dumps are written, nothing is corrected."""
+    out = tmp_path / "o"
+    r = subprocess.run([EXE, "-p", os.path.join(GOLDEN, "tiny"), "-o", str(out), "-c", "30", "-g", "5", "--onlyseed", "-b", os.path.join(GOLDEN, "tiny.barcode.txt"),
+                        os.path.join(GOLDEN, "tiny.reads.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Loading BARCODE" in r.stderr
+    assert r.stdout == open(os.path.join(GOLDEN, "tiny.onlyseed.stdout")).read()
+    assert open(out / "total.seed").read() == open(os.path.join(GOLDEN, "tiny.onlyseed.total.seed")).read()
+    assert sorted(os.listdir(out)) == ["extend", "seed", "threshold-table", "total.seed"]
+    assert len([f for f in os.listdir(out / "seed") if f.endswith(".seed")]) == 396
+    assert not [f for f in os.listdir(out / "extend") if not f.endswith(".log")]
+
+
+def test_cli_kmercheck(tmp_path):
+    """`pbcorrect kmercheck` = `stride kmercheck` (StriDe/kmercheck.cpp, PacBio/KmerCheckProcess.cpp): k-mer frequencies by batched
+    backward search on the GPU, barcode arithmetic and five-number summaries on the host; DIR/total.box and DIR/value.box equal the
+    reference's, and a second run appends like the reference does."""
+    out = tmp_path / "kc"
+    cmd = [EXE, "kmercheck", "-t", "2", "-c", "30", "-p", os.path.join(GOLDEN, "tiny"), "-o", str(out), "-b", os.path.join(GOLDEN, "tiny.barcode.txt"), "-l", "15", "-u", "23",
+           "-s", "4", os.path.join(GOLDEN, "tiny.reads.fa")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Using kmer size : 15 - 23 (4)" in r.stderr
+    want_t, want_v = (open(os.path.join(GOLDEN, f"tiny.kmercheck.{n}.box")).read() for n in ("total", "value"))
+    assert open(out / "total.box").read() == want_t and open(out / "value.box").read() == want_v
+    assert subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE).returncode == 0
+    assert open(out / "total.box").read() == want_t * 2
+    r = subprocess.run([EXE, "kmercheck", "-p", "x", "-o", str(tmp_path / "e"), "-l", "5", "reads.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "no barcode" in r.stderr and "invalid range of kmer size:5 - 35" in r.stderr

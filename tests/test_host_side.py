@@ -166,6 +166,19 @@ def test_index_builder_model_reproduces_reference_files(name, fasta, tmp_path):
         assert open(tmp_path / f"m.{ext}", "rb").read() == open(os.path.join(GOLDEN, f"{name}.{ext}"), "rb").read(), ext
 
 
+def test_onlyseed_barcode_check_matches_reference(tmp_path):
+    """csrc/pbsc_bcode.h (what `pbcorrect --onlyseed -b FILE` runs on the host) on the reference's own seeds of tiny.reads.fa and a
+    synthetic barcode file: DIR/total.seed and the TOTAL line equal what the unmodified reference wrote
+    (tests/golden/make_onlyseed_golden.py)."""
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "test_bcode.cpp"), "-o", exe, "-lz"], check=True)
+    r = subprocess.run([exe, os.path.join(GOLDEN, "tiny.reads.fa"), os.path.join(GOLDEN, "tiny.seeds.tsv"), os.path.join(GOLDEN, "tiny.barcode.txt"),
+                        str(tmp_path / "total.seed")], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0
+    assert r.stdout == open(os.path.join(GOLDEN, "tiny.onlyseed.stdout")).read()
+    assert open(tmp_path / "total.seed").read() == open(os.path.join(GOLDEN, "tiny.onlyseed.total.seed")).read()
+
+
 def test_cli_option_errors():
     exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
     if not os.path.exists(exe):
@@ -175,6 +188,8 @@ def test_cli_option_errors():
     assert "Usage: StriDe PacBioSelfCorrection" in r.stderr
     r = subprocess.run([exe, "-p", "x", "-o", "/tmp/pbsc_cli_test"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "missing arguments" in r.stderr
+    r = subprocess.run([exe, "-p", "x", "-o", "/tmp/pbsc_cli_test", "--onlyseed", "reads.fa"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "no barcode" in r.stderr
     # default options (DP fallback on) are accepted; without a GPU or an index the run fails loudly, never on a CPU path
     r = subprocess.run([exe, "-p", "x", "-o", "/tmp/pbsc_cli_test", "reads.fa"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and ("no CUDA device" in r.stderr or "x.bwt" in r.stderr) and "--nodp" not in r.stderr
