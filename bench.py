@@ -55,6 +55,9 @@ WORKLOADS = {
     # the same recipe at 1/6 of the size: a repeat-rich parity and capacity check that fits a short GPU slot
     "cfg3s": dict(genome=2_000_000, gseed=3, cov=100, mean=8000, rseed=103, c=100, g=10, repeat_families=8, tandem_arrays=4,
                   desc="2 Mb synthetic genome with injected repeats, 100x simulated CLR reads (mean 8 kb, 13% error), -c 100 -g 10"),
+    # BASELINE.json configs[3]: 100 Mb genome, 40x: 4.0 G symbols with the sentinels, just inside the 32-bit positions of the index
+    "cfg4": dict(genome=100_000_000, gseed=4, cov=40, mean=8000, rseed=104, c=40, g=100, sim="device",
+                 desc="100 Mb synthetic genome, 40x simulated CLR reads (mean 8 kb, 13% error), -c 40 -g 100"),
     "mini": dict(genome=100_000, gseed=1, cov=30, mean=3000, rseed=101, c=30, g=5,
                  desc="100 kb synthetic genome, 30x simulated CLR reads (mean 3 kb), -c 30 -g 5"),
 }
@@ -72,7 +75,10 @@ def make_data(wl):
     from longreadselfcorrect_b200 import synth
     t = time.time()
     g = synth.make_genome(wl["genome"], wl["gseed"], repeat_families=wl.get("repeat_families", 0), tandem_arrays=wl.get("tandem_arrays", 0))
-    codes, off = synth.simulate_reads(g, wl["cov"], wl["mean"], wl["rseed"])
+    if wl.get("sim") == "device":   # read sets numpy cannot simulate in one piece (config 4)
+        codes, off = synth.simulate_reads_device(g, wl["cov"], wl["mean"], wl["rseed"])
+    else:
+        codes, off = synth.simulate_reads(g, wl["cov"], wl["mean"], wl["rseed"])
     log(f"simulated {off.size - 1} reads, {codes.size / 1e6:.1f} Mbp in {time.time() - t:.1f}s")
     return codes, off
 
@@ -555,7 +561,7 @@ def ours(args, wl, metric):
 
     # ---- single-GPU extras: CPU baseline, algorithmic and issued rank queries, roofline, config 2 / --nodp / FM microbench ----
     if world == 1:
-        extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank)
+        extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank, dig)
     else:
         line["roofline"] = roofline_from_committed(args, ph, walks * shard.bases / max(1.0, total_mbp * 1e6), total_mbp)
         line["cpu_baseline"] = None
@@ -644,7 +650,7 @@ def count_issued(args, wl, letters, off, runs, n_reads, ids, local_rank):
     return None
 
 
-def extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank):
+def extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, lengths, ph, walks, cores, local_rank, dig=None):
     from longreadselfcorrect_b200 import api
     peaks = {}
     try:
@@ -667,9 +673,17 @@ def extras_single_gpu(args, wl, line, letters, off, runs, n_reads, total_mbp, le
             log(f"reference CPU baseline: {smbp:.1f} Mbp in {secs:.2f}s with {cores} threads")
             sdesc = f"seeded sample of {ids.size} reads spread over the whole set ({smbp:.1f} Mbp of {total_mbp:.1f}) against the full index, stride pbcorrect -t {cores}" + (" --nodp" if args.nodp else "")
             cpu = {"value": smbp / secs, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": sdesc}
+            # live parity on exactly these reads: the records the unmodified reference just wrote against the timed GPU output
+            if dig is not None and isinstance(line.get("parity_vs_reference"), dict):
+                from longreadselfcorrect_b200 import parity
+                ref = parity.fasta_digests(os.path.join(d, "out", "correct.fa"), os.path.join(d, "out", "discard.fa"))
+                same = sum(1 for i in ids if int(i) in ref and bytes(ref[int(i)]) == bytes(dig[int(i)].tobytes()))
+                line["parity_vs_reference"]["live_sample"] = {"reads": int(ids.size), "identical_to_reference": int(same),
+                                                              "what": "the CPU baseline's reads: records written by oracle/_ref/stride pbcorrect against the full index, compared with the timed GPU output"}
+                log(f"live parity: {same} of {ids.size} sampled reads identical to the reference")
             # live parity of exactly these reads: what the reference just wrote against the digests of the timed GPU output is
             # covered by parity_vs_reference when a golden exists; here the reference's records are hashed and kept
-            if os.path.exists(ORACLE):
+            if os.path.exists(ORACLE) and not args.no_oracle_count:
                 small_ids = ids[: max(1, int(np.searchsorted(np.cumsum(lengths[ids]), min(smbp, 3.0) * 1e6)))]
                 fa2 = os.path.join(d, "alg.fa")
                 write_fasta_ids(fa2, letters, off, small_ids)
@@ -785,6 +799,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=1, help="batches of one GPU in flight at once (streams + arenas); 1 with batches as large as memory allows measured best")
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.0, help="Mbp of reads for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-oracle-count", action="store_true", help="skip the instrumented-oracle and issued-sector counts of the roofline (profiles/algorithmic.json is used)")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the config 2 / --nodp / FM microbench sub-results")
     ap.add_argument("--no-cli", dest="cli", action="store_false", help="skip the e2e_cli leg (the pbcorrect binary)")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -219,20 +219,21 @@ struct IsDollar
     const uint8_t* bwt; uint64_t base;
     __device__ __forceinline__ bool operator()(uint32_t x) const { return bwt[base + x] == 0; }
 };
+// (n_runs runs of a chunk; `end` = N when the chunk holds the last run of the BWT, 0 when starts[n_runs] is the next chunk's first run)
 __global__ void __launch_bounds__(256)
-run_units_kernel(uint64_t n_runs, const uint32_t* __restrict__ starts, uint64_t N, uint32_t* units)
+run_units_kernel(uint64_t n_runs, const uint32_t* __restrict__ starts, uint64_t end, uint32_t* units)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
-    const uint64_t len = (r + 1 < n_runs ? (uint64_t)starts[r + 1] : N) - starts[r];
+    const uint64_t len = ((r + 1 < n_runs || end == 0) ? (uint64_t)starts[r + 1] : end) - starts[r];
     units[r] = (uint32_t)((len + 30) / 31);
 }
 __global__ void __launch_bounds__(256)
-run_bytes_kernel(uint64_t n_runs, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ first, uint64_t N, const uint8_t* __restrict__ bwt, uint8_t* out)
+run_bytes_kernel(uint64_t n_runs, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ first, uint64_t end, const uint8_t* __restrict__ bwt, uint8_t* out)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
-    uint64_t len = (r + 1 < n_runs ? (uint64_t)starts[r + 1] : N) - starts[r];
+    uint64_t len = ((r + 1 < n_runs || end == 0) ? (uint64_t)starts[r + 1] : end) - starts[r];
     const uint8_t sym = (uint8_t)(bwt[starts[r]] << 5);
     uint8_t* o = out + first[r];
     while (len > 31) { *o++ = (uint8_t)(sym | 31u); len -= 31; }
@@ -440,26 +441,34 @@ static int build_strand(const char* d_reads, const uint64_t* d_offsets, const ui
     uint64_t n_runs = 0;
     RunHead rh{bwt, 0};
     BUILD_CUDA(select_positions(N, rh, starts, N, &n_runs, tmp, d_count, st));
-    if (n_runs >= 0x7fffffffull) { set_error("pbsc_build: %llu runs are outside this build's range", (unsigned long long)n_runs); return PBSC_ERR_LIMIT; }
     if (trace) ms_part[1] = lap();
-    uint32_t* units = A.take<uint32_t>(n_runs + 1);
-    uint32_t* first = A.take<uint32_t>(n_runs + 1);
+    // unit counts, their prefix sums and the unit bytes, 2^28 runs at a time (a 4 G-symbol BWT has 2.6 G runs)
+    const char* chunk_env = getenv("PBSC_RUN_CHUNK");   // tests: small chunks
+    const uint64_t CHR = std::min<uint64_t>(n_runs, chunk_env && atoll(chunk_env) > 0 ? (uint64_t)atoll(chunk_env) : 1ull << 28);
+    uint32_t* units = A.take<uint32_t>(CHR + 1);
+    uint32_t* first = A.take<uint32_t>(CHR + 1);
     if (!first) { set_error("pbsc_build: scratch arena too small"); return PBSC_ERR_INTERNAL; }
-    run_units_kernel<<<grid_for(n_runs), 256, 0, st>>>(n_runs, starts, N, units);
     {
         size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, units, first, (int)n_runs, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, units, first, (int)CHR, st);
         if (tmp.bytes < tb) BUILD_CUDA(tmp.alloc(tb));
-        tb = tmp.bytes;
-        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, units, first, (int)n_runs, st));
     }
-    uint32_t lastu[2] = {0, 0};
-    BUILD_CUDA(cudaMemcpyAsync(&lastu[0], units + (n_runs - 1), 4, cudaMemcpyDeviceToHost, st));
-    BUILD_CUDA(cudaMemcpyAsync(&lastu[1], first + (n_runs - 1), 4, cudaMemcpyDeviceToHost, st));
-    BUILD_CUDA(cudaStreamSynchronize(st));
-    const uint64_t n_units = (uint64_t)lastu[0] + lastu[1];
-    if (n_units > N) { set_error("pbsc_build: %llu run-length units for %llu symbols", (unsigned long long)n_units, (unsigned long long)N); return PBSC_ERR_INTERNAL; }
-    run_bytes_kernel<<<grid_for(n_runs), 256, 0, st>>>(n_runs, starts, first, N, bwt, bytes);
+    uint64_t n_units = 0;
+    for (uint64_t r0 = 0; r0 < n_runs; r0 += CHR)
+    {
+        const uint64_t m = std::min<uint64_t>(CHR, n_runs - r0);
+        run_units_kernel<<<grid_for(m), 256, 0, st>>>(m, starts + r0, r0 + m < n_runs ? (uint64_t)0 : N, units);
+        size_t tb = tmp.bytes;
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, units, first, (int)m, st));
+        uint32_t lastu[2] = {0, 0};
+        BUILD_CUDA(cudaMemcpyAsync(&lastu[0], units + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+        BUILD_CUDA(cudaMemcpyAsync(&lastu[1], first + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+        BUILD_CUDA(cudaStreamSynchronize(st));
+        const uint64_t chunk_units = (uint64_t)lastu[0] + lastu[1];
+        if (n_units + chunk_units > N) { set_error("pbsc_build: more run-length units than symbols (%llu)", (unsigned long long)N); return PBSC_ERR_INTERNAL; }
+        run_bytes_kernel<<<grid_for(m), 256, 0, st>>>(m, starts + r0, first, r0 + m < n_runs ? (uint64_t)0 : N, bwt, bytes + n_units);
+        n_units += chunk_units;
+    }
     if (trace) ms_part[2] = lap();
     out.runs = (uint8_t*)malloc(n_units ? n_units : 1);
     if (!out.runs) { set_error("pbsc_build: out of host memory"); return PBSC_ERR_LIMIT; }

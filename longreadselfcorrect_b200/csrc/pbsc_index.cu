@@ -266,18 +266,21 @@ __global__ void run_lengths_kernel(const uint8_t* __restrict__ runs, uint64_t n_
 }
 
 // per run: its symbols into the 2-bit words of the blocks; '$' positions into the list and the per-block bit mask
+// (the runs come in chunks: `start` / `dstart` are relative to the chunk, sym0 / dollar0 = symbols and '$' before it)
 __global__ void run_scatter_kernel(const uint8_t* __restrict__ runs, uint64_t n_runs, const uint64_t* __restrict__ start, const uint64_t* __restrict__ dstart,
-                                   uint64_t n_symbols, FmBlock* blocks, uint32_t* __restrict__ dollar, unsigned long long* dmask, unsigned int* bad)
+                                   uint64_t sym0, uint64_t dollar0, uint64_t n_symbols, uint64_t n_dollar, FmBlock* blocks, uint32_t* __restrict__ dollar,
+                                   unsigned long long* dmask, unsigned int* bad)
 {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
     const uint8_t u = runs[r];
     const uint32_t sym = u >> 5, l = u & 0x1f;
-    uint64_t pos = start[r];
-    if (pos + l > n_symbols) { atomicAdd(bad, 1u); return; }
+    uint64_t pos = sym0 + start[r];
+    if (pos + l > n_symbols) { atomicAdd(bad + 2, 1u); return; }
     if (sym == 0)
     {
-        uint64_t d = dstart[r];
+        uint64_t d = dollar0 + dstart[r];
+        if (d + l > n_dollar) { atomicAdd(bad + 1, 1u); return; }
         for (uint32_t i = 0; i < l; i++, pos++, d++) { dollar[d] = (uint32_t)pos; atomicOr(dmask + (pos >> 6), 1ull << (pos & 63u)); }
         return;
     }
@@ -486,35 +489,49 @@ static int upload_strand(pbsc_index* idx, int which, const std::vector<FmBlock>&
 static int upload_strand_device(pbsc_index* idx, int which, const uint8_t* runs, uint64_t n_runs, uint64_t n_symbols, uint64_t n_strings)
 {
     if (n_symbols >= 0xffffffffull) { set_error("BWT has %llu symbols; this build supports < 2^32-1", (unsigned long long)n_symbols); return PBSC_ERR_LIMIT; }
-    if (n_runs == 0 || n_runs >= 0x7fffffffull) { set_error("BWT with %llu runs is outside this build's range", (unsigned long long)n_runs); return PBSC_ERR_LIMIT; }
+    if (n_runs == 0 || n_runs > n_symbols) { set_error("BWT with %llu runs is outside this build's range", (unsigned long long)n_runs); return PBSC_ERR_LIMIT; }
     const uint64_t nb = n_symbols / 64 + 1;
+    // The runs are decoded in chunks (33 bytes of scratch per run: a 4 G-symbol BWT has 2.6 G of them).  One '$' per read: the
+    // list of their positions has n_strings entries, and the decode checks that the runs hold exactly that many.
+    const char* chunk_env = getenv("PBSC_RUN_CHUNK");   // tests: small chunks
+    const uint64_t CH = std::min<uint64_t>(n_runs, chunk_env && atoll(chunk_env) > 0 ? (uint64_t)atoll(chunk_env) : 1ull << 28);
+    const uint64_t nd = n_strings;
     DevBuf<uint8_t> d_runs, tmp; DevBuf<uint64_t> len, dlen, start, dstart; DevBuf<unsigned int> bad; DevBuf<uint32_t> cnt[4], cum[4];
-    PBSC_CUDA(d_runs.alloc(n_runs)); PBSC_CUDA(len.alloc(n_runs + 1)); PBSC_CUDA(dlen.alloc(n_runs + 1)); PBSC_CUDA(start.alloc(n_runs + 1)); PBSC_CUDA(dstart.alloc(n_runs + 1));
-    PBSC_CUDA(bad.alloc(1));
-    PBSC_CUDA(cudaMemcpy(d_runs.p, runs, n_runs, cudaMemcpyHostToDevice));
-    PBSC_CUDA(cudaMemset(bad.p, 0, 4));
-    PBSC_CUDA(cudaMemset(len.p + n_runs, 0, 8)); PBSC_CUDA(cudaMemset(dlen.p + n_runs, 0, 8));
-    run_lengths_kernel<<<(unsigned)((n_runs + 255) / 256), 256>>>(d_runs.p, n_runs, len.p, dlen.p, bad.p);
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, len.p, start.p, (int)(n_runs + 1));
-    PBSC_CUDA(tmp.alloc(tb));
-    cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.p, start.p, (int)(n_runs + 1));
-    cub::DeviceScan::ExclusiveSum(tmp.p, tb, dlen.p, dstart.p, (int)(n_runs + 1));
-    uint64_t tot[2] = {0, 0};
-    PBSC_CUDA(cudaMemcpy(&tot[0], start.p + n_runs, 8, cudaMemcpyDeviceToHost));
-    PBSC_CUDA(cudaMemcpy(&tot[1], dstart.p + n_runs, 8, cudaMemcpyDeviceToHost));
-    unsigned int hbad = 0;
-    PBSC_CUDA(cudaMemcpy(&hbad, bad.p, 4, cudaMemcpyDeviceToHost));
-    if (hbad) { set_error("malformed run bytes (%u) in the BWT", hbad); return PBSC_ERR_FORMAT; }
-    if (tot[0] != n_symbols) { set_error("runs hold %llu symbols, header says %llu", (unsigned long long)tot[0], (unsigned long long)n_symbols); return PBSC_ERR_FORMAT; }
-    const uint64_t nd = tot[1];
+    PBSC_CUDA(d_runs.alloc(CH)); PBSC_CUDA(len.alloc(CH + 1)); PBSC_CUDA(dlen.alloc(CH + 1)); PBSC_CUDA(start.alloc(CH + 1)); PBSC_CUDA(dstart.alloc(CH + 1));
+    PBSC_CUDA(bad.alloc(4));   // [0] malformed bytes, [1] more '$' than strings, [2] more symbols than the header says
+    PBSC_CUDA(cudaMemset(bad.p, 0, 16));
     PBSC_CUDA(cudaMalloc((void**)&idx->d_blocks[which], nb * sizeof(FmBlock)));
     PBSC_CUDA(cudaMemset(idx->d_blocks[which], 0, nb * sizeof(FmBlock)));
     PBSC_CUDA(cudaMalloc((void**)&idx->d_dollar[which], (nd + 1) * sizeof(uint32_t)));
     PBSC_CUDA(cudaMalloc((void**)&idx->d_dmask[which], nb * sizeof(uint64_t)));
     PBSC_CUDA(cudaMemset(idx->d_dmask[which], 0, nb * sizeof(uint64_t)));
-    run_scatter_kernel<<<(unsigned)((n_runs + 255) / 256), 256>>>(d_runs.p, n_runs, start.p, dstart.p, n_symbols, idx->d_blocks[which], idx->d_dollar[which],
-                                                                  (unsigned long long*)idx->d_dmask[which], bad.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, len.p, start.p, (int)(CH + 1));
+    PBSC_CUDA(tmp.alloc(tb));
+    uint64_t tot[2] = {0, 0};
+    for (uint64_t r0 = 0; r0 < n_runs; r0 += CH)
+    {
+        const uint64_t m = std::min<uint64_t>(CH, n_runs - r0);
+        PBSC_CUDA(cudaMemcpy(d_runs.p, runs + r0, m, cudaMemcpyHostToDevice));
+        PBSC_CUDA(cudaMemset(len.p + m, 0, 8)); PBSC_CUDA(cudaMemset(dlen.p + m, 0, 8));
+        run_lengths_kernel<<<(unsigned)((m + 255) / 256), 256>>>(d_runs.p, m, len.p, dlen.p, bad.p);
+        size_t tb1 = tb;
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb1, len.p, start.p, (int)(m + 1));
+        tb1 = tb;
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb1, dlen.p, dstart.p, (int)(m + 1));
+        uint64_t part[2] = {0, 0};
+        PBSC_CUDA(cudaMemcpy(&part[0], start.p + m, 8, cudaMemcpyDeviceToHost));
+        PBSC_CUDA(cudaMemcpy(&part[1], dstart.p + m, 8, cudaMemcpyDeviceToHost));
+        run_scatter_kernel<<<(unsigned)((m + 255) / 256), 256>>>(d_runs.p, m, start.p, dstart.p, tot[0], tot[1], n_symbols, nd, idx->d_blocks[which],
+                                                               idx->d_dollar[which], (unsigned long long*)idx->d_dmask[which], bad.p);
+        tot[0] += part[0]; tot[1] += part[1];
+    }
+    unsigned int hbad2[4] = {0, 0, 0, 0};
+    PBSC_CUDA(cudaMemcpy(hbad2, bad.p, 16, cudaMemcpyDeviceToHost));
+    unsigned int hbad = hbad2[0];
+    if (hbad) { set_error("malformed run bytes (%u) in the BWT", hbad); return PBSC_ERR_FORMAT; }
+    if (tot[0] != n_symbols || hbad2[2]) { set_error("runs hold %llu symbols, header says %llu", (unsigned long long)tot[0], (unsigned long long)n_symbols); return PBSC_ERR_FORMAT; }
+    if (tot[1] != nd || hbad2[1]) { set_error("runs hold %llu '$', header says %llu strings", (unsigned long long)tot[1], (unsigned long long)nd); return PBSC_ERR_FORMAT; }
     d_runs.release(); len.release(); dlen.release(); start.release(); dstart.release();
     for (int c = 0; c < 4; c++) { PBSC_CUDA(cnt[c].alloc(nb)); PBSC_CUDA(cum[c].alloc(nb)); }
     block_counts_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(idx->d_blocks[which], idx->d_dmask[which], nb, n_symbols, cnt[0].p, cnt[1].p, cnt[2].p, cnt[3].p);

@@ -82,6 +82,82 @@ def simulate_reads(genome: np.ndarray, coverage: float, mean_len: int, seed: int
     return out, offsets
 
 
+def simulate_reads_device(genome: np.ndarray, coverage: float, mean_len: int, seed: int, device: str = "cuda:0",
+                          chunk_bases: int = 200_000_000, error: float = 0.13, sigma: float = 0.5, min_len: int = 500,
+                          ins: float = 0.55, dele: float = 0.30):
+    """The read model of simulate_reads with the per-base work on the GPU (torch), a few hundred Mbp of templates at a time: for
+    read sets numpy cannot hold in one piece (config 4: 4 Gbp, whose temporaries would take > 150 GB of host memory).  Read
+    lengths, positions and strands come from the same numpy generator; the per-base draws come from torch's generator, so a
+    seed does not give the reads simulate_reads gives."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(seed))
+    glen = genome.size
+    n_est = int(coverage * glen / mean_len * 1.3) + 16
+    mu = np.log(mean_len) - 0.5 * sigma * sigma
+    lens = np.maximum(rng.lognormal(mu, sigma, size=n_est).astype(np.int64), min_len)
+    lens = np.minimum(lens, glen)
+    cum = np.cumsum(lens)
+    n = int(np.searchsorted(cum, coverage * glen)) + 1
+    lens = lens[:n]
+    starts = (rng.random(n) * (glen - lens + 1)).astype(np.int64)
+    strand = rng.random(n) < 0.5
+    dev = torch.device(device)
+    g = torch.from_numpy(np.ascontiguousarray(genome)).to(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    p_del = error * dele
+    p_sub = error * (1.0 - ins - dele)
+    chunks, read_lens = [], []
+    toff_all = np.concatenate([[0], np.cumsum(lens)])
+    r0 = 0
+    while r0 < n:
+        r1 = int(np.searchsorted(toff_all, toff_all[r0] + chunk_bases, side="right")) - 1
+        r1 = min(n, max(r1, r0 + 1))
+        l = torch.from_numpy(lens[r0:r1]).to(dev)
+        st = torch.from_numpy(starts[r0:r1]).to(dev)
+        sd = torch.from_numpy(strand[r0:r1]).to(dev)
+        m = r1 - r0
+        toff = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        toff[1:] = torch.cumsum(l, 0)
+        total = int(toff[-1])
+        rid = torch.repeat_interleave(torch.arange(m, device=dev), l)
+        within = torch.arange(total, device=dev) - toff[rid]
+        rev = sd[rid]
+        gpos = torch.where(rev, st[rid] + l[rid] - 1 - within, st[rid] + within)
+        del within
+        base = g[gpos]
+        del gpos
+        base = torch.where(rev, 3 - base, base)
+        del rev, rid
+        u = torch.rand(total, device=dev, generator=gen)
+        is_del = u < p_del
+        is_sub = (u >= p_del) & (u < p_del + p_sub)
+        del u
+        sub = torch.randint(1, 4, (total,), device=dev, generator=gen, dtype=torch.uint8)
+        base = torch.where(is_sub, (base + sub) & 3, base)
+        del sub, is_sub
+        n_ins = (torch.rand(total, device=dev, generator=gen) < error * ins).to(torch.int64)
+        out_cnt = n_ins + (~is_del).to(torch.int64)
+        ooff = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+        ooff[1:] = torch.cumsum(out_cnt, 0)
+        del out_cnt
+        out = torch.empty(int(ooff[-1]), dtype=torch.uint8, device=dev)
+        ins_pos = ooff[:-1][n_ins > 0]
+        out[ins_pos] = torch.randint(0, 4, (int(ins_pos.numel()),), device=dev, generator=gen, dtype=torch.uint8)
+        keep = ~is_del
+        out[(ooff[:-1] + n_ins)[keep]] = base[keep]
+        ends = ooff[toff]
+        read_lens.append((ends[1:] - ends[:-1]).cpu().numpy())
+        chunks.append(out.cpu().numpy())
+        del out, ooff, n_ins, keep, is_del, base, ins_pos
+        r0 = r1
+    del g
+    torch.cuda.empty_cache()
+    codes = np.concatenate(chunks)
+    offsets = np.concatenate([[0], np.cumsum(np.concatenate(read_lens))]).astype(np.int64)
+    return codes, offsets
+
+
 def write_fasta(path: str, codes: np.ndarray, offsets: np.ndarray, prefix: str = "r") -> None:
     letters = _ACGT[codes]
     with open(path, "wb") as f:

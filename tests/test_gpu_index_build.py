@@ -41,6 +41,22 @@ def test_index_files_equal_the_reference(api, name, fasta, tmp_path):
     _same_files(str(tmp_path / "x"), name)
 
 
+def test_run_chunks(api, tmp_path, monkeypatch):
+    """Inputs of billions of runs are written (pbsc_build.cu) and decoded (pbsc_index.cu) 2^28 runs at a time; PBSC_RUN_CHUNK makes
+    the chunks small enough for the fixture to need hundreds of them: same files, same index, same corrected reads."""
+    monkeypatch.setenv("PBSC_RUN_CHUNK", "997")
+    recs = read_fasta(os.path.join(GOLDEN, "tiny.reads.fa"))
+    api.build_index_files(_packed([s for _, s in recs]), str(tmp_path / "c"))
+    _same_files(str(tmp_path / "c"), "tiny")
+    idx, _ = api.Index.open(str(tmp_path / "c"), k0=11)
+    p = api.Params.make(coverage=30, genome=5)
+    out, poff, first, stats = idx.correct_reads(p, [s for _, s in recs])
+    pieces = api.Index.pieces_as_strings(out, poff, first)
+    correct = "".join(f">{rid}\n{s}\n" for (rid, _), pc, st in zip(recs, pieces, stats) if st["merge"] for s in pc)
+    assert correct == open(os.path.join(GOLDEN, "tiny.dp.correct.fa")).read()
+    idx.close()
+
+
 def test_lower_case_and_strand_flags(api, tmp_path):
     seqs = [s.lower() for _, s in read_fasta(os.path.join(GOLDEN, "index_edge.fa"))]
     api.build_index_files(_packed(seqs), str(tmp_path / "f"), reverse=False)
