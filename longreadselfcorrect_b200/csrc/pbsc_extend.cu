@@ -415,6 +415,7 @@ extern "C" int pbsc_extend_batch(pbsc_index* idx, const pbsc_params* p, uint64_t
                                  const char* src, const uint64_t* src_off, const char* path, const uint64_t* path_off,
                                  const char* trg, const uint64_t* trg_off, const int32_t* dis, const int32_t* k,
                                  const int32_t* min_sa, int32_t* status, char* out, uint64_t out_cap, uint64_t* out_offsets)
+try
 {
     if (!idx || !p || !src || !src_off || !path || !path_off || !trg || !trg_off || !dis || !k || !min_sa || !status || !out_offsets)
     { set_error("pbsc_extend_batch: null argument"); return PBSC_ERR_ARG; }
@@ -479,3 +480,4 @@ extern "C" int pbsc_extend_batch(pbsc_index* idx, const pbsc_params* p, uint64_t
         for (uint32_t x = 0; x < hlen[i]; x++) out[out_offsets[i] + x] = "ACGT"[hout[region[i] + x] & 3];
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_extend_batch")

@@ -562,6 +562,7 @@ static int upload_strand_device(pbsc_index* idx, int which, const uint8_t* runs,
 int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt_n_symbols, uint64_t bwt_n_strings,
                       const uint8_t* rbwt_runs, uint64_t rbwt_n_runs, uint64_t rbwt_n_symbols, uint64_t rbwt_n_strings,
                       int device, pbsc_index** out)
+try
 {
     if (!bwt_runs || !rbwt_runs || !out) { set_error("pbsc_index_create: null argument"); return PBSC_ERR_ARG; }
     *out = nullptr;
@@ -596,6 +597,7 @@ int pbsc_index_create(const uint8_t* bwt_runs, uint64_t bwt_n_runs, uint64_t bwt
     *out = idx;
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_create")
 
 // EXPERIMENT, off unless PBSC_L2_PERSIST is set (not measured yet: prepared at the end of round 1 for round 2).
 // walk_levels_kernel is bound by DRAM random access (2.1 TB/s of 32-byte sectors at a 33 % L2 hit rate) and the two rank
@@ -653,6 +655,7 @@ static int read_bwt_file(const std::string& path, std::vector<uint8_t>& runs, ui
 }
 
 int pbsc_index_load(const char* prefix, int device, int require_sai, pbsc_index** out)
+try
 {
     if (!prefix || !out) { set_error("pbsc_index_load: null argument"); return PBSC_ERR_ARG; }
     std::string p(prefix);
@@ -671,8 +674,10 @@ int pbsc_index_load(const char* prefix, int device, int require_sai, pbsc_index*
     if (rc == PBSC_OK) { (*out)->src_runs[0] = r0.size(); (*out)->src_runs[1] = r1.size(); }
     return rc;
 }
+PBSC_CATCH_ALL("pbsc_index_load")
 
 int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t seed, int device, pbsc_index** out)
+try
 {
     if (!out || n_symbols == 0) { set_error("pbsc_index_create_synthetic: bad argument"); return PBSC_ERR_ARG; }
     if (n_symbols >= 0xffffffffull) { set_error("synthetic BWT of %llu symbols; this build supports < 2^32-1", (unsigned long long)n_symbols); return PBSC_ERR_LIMIT; }
@@ -747,8 +752,10 @@ int pbsc_index_create_synthetic(uint64_t n_symbols, uint64_t n_strings, uint64_t
     *out = idx;
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_create_synthetic")
 
 int pbsc_index_build_prefix_table(pbsc_index* idx, int k0)
+try
 {
     if (!idx || k0 < 0 || k0 > 15) { set_error("pbsc_index_build_prefix_table: k0 must be in 0..15"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
@@ -787,6 +794,7 @@ int pbsc_index_build_prefix_table(pbsc_index* idx, int k0)
     idx->device_bytes += n_final * sizeof(PrefixEntry);
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_build_prefix_table")
 
 void pbsc_index_destroy(pbsc_index* idx)
 {
@@ -913,6 +921,7 @@ uint64_t pbsc_index_num_strings(const pbsc_index* idx, int which) { return idx &
 uint64_t pbsc_index_device_bytes(const pbsc_index* idx) { return idx ? idx->device_bytes : 0; }
 
 int pbsc_index_get_symbols(const pbsc_index* idx, int which, uint64_t first, uint64_t count, char* out)
+try
 {
     if (!idx || !out || (which != 0 && which != 1) || first + count > idx->n_symbols[which]) { set_error("pbsc_index_get_symbols: bad argument"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
@@ -923,9 +932,11 @@ int pbsc_index_get_symbols(const pbsc_index* idx, int which, uint64_t first, uin
     PBSC_CUDA(cudaMemcpy(out, d.p, count, cudaMemcpyDeviceToHost));
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_get_symbols")
 
 int pbsc_findinterval_batch(pbsc_index* idx, int which, const char* kmers, const uint64_t* offsets, uint64_t n,
                             int64_t* lower, int64_t* upper, uint8_t* steps)
+try
 {
     if (!idx || !kmers || !offsets || !lower || !upper || (which != 0 && which != 1)) { set_error("pbsc_findinterval_batch: bad argument"); return PBSC_ERR_ARG; }
     if (n == 0) return PBSC_OK;
@@ -945,6 +956,7 @@ int pbsc_findinterval_batch(pbsc_index* idx, int which, const char* kmers, const
     PBSC_CUDA(cudaStreamSynchronize(idx->stream));
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_findinterval_batch")
 
 int pbsc_findinterval_device(pbsc_index* idx, int which, const uint64_t* d_kmers2bit, int k, uint64_t n,
                              int64_t* d_lower, int64_t* d_upper, uint8_t* d_steps, float* ms)
@@ -1049,6 +1061,7 @@ int pbsc_params_derive(pbsc_params* p)
 }
 
 int pbsc_threshold_table_text(const pbsc_params* p, char* buf, size_t cap)
+try
 {
     if (!p || !buf) { set_error("pbsc_threshold_table_text: null"); return PBSC_ERR_ARG; }
     std::ostringstream out;
@@ -1059,6 +1072,7 @@ int pbsc_threshold_table_text(const pbsc_params* p, char* buf, size_t cap)
     memcpy(buf, s.c_str(), s.size() + 1);
     return (int)s.size();
 }
+PBSC_CATCH_ALL("pbsc_threshold_table_text")
 
 /* measurement build only (-DPBSC_COUNT_OCC, libpbsc_count.so): distinct 32-byte index sectors asked for since the last reset,
  * per kernel family: out[0] seed phase, out[1] walk setup, out[2] level loop, out[3] DP fallback, out[4] other.

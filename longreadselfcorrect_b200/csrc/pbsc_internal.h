@@ -8,7 +8,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <chrono>
+#include <exception>
 #include <map>
+#include <new>
 #include <mutex>
 #include <condition_variable>
 #include <string>
@@ -62,6 +64,12 @@ namespace pbsc {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+// no C++ exception may cross the C ABI: entry points that allocate host memory are function-try-blocks closed by this
+#define PBSC_CATCH_ALL(who)                                                                                               \
+    catch (const std::bad_alloc&) { pbsc::set_error("%s: out of host memory", who); return PBSC_ERR_LIMIT; }              \
+    catch (const std::exception& e) { pbsc::set_error("%s: %s", who, e.what()); return PBSC_ERR_INTERNAL; }               \
+    catch (...) { pbsc::set_error("%s: unknown exception", who); return PBSC_ERR_INTERNAL; }
 
 #define PBSC_CUDA(call)                                                             \
     do {                                                                            \

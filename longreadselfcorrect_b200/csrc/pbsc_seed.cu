@@ -546,6 +546,7 @@ using namespace pbsc;
 
 extern "C" int pbsc_seed_batch(pbsc_index* idx, const pbsc_params* p, const char* reads, const uint64_t* offsets, uint64_t n_reads,
                                pbsc_seed* seeds_out, uint64_t seeds_cap, uint64_t* seed_offsets, uint64_t* seeds_needed, int keep_outcast)
+try
 {
     if (!idx || !p || !reads || !offsets || !seed_offsets) { set_error("pbsc_seed_batch: null argument"); return PBSC_ERR_ARG; }
     (void)keep_outcast;
@@ -578,3 +579,4 @@ extern "C" int pbsc_seed_batch(pbsc_index* idx, const pbsc_params* p, const char
         for (uint32_t i = 0; i < cnt[r]; i++) seeds_out[seed_offsets[r] + i] = all[region[r] + i];
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_seed_batch")

@@ -186,6 +186,7 @@ using namespace pbsc;
 extern "C" {
 
 int pbsc_index_set_lanes(pbsc_index* idx, int lanes)
+try
 {
     if (!idx || idx->primary || lanes < 1 || lanes > PBSC_MAX_LANES) { set_error("pbsc_index_set_lanes: lanes must be in 1..%d", PBSC_MAX_LANES); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
@@ -213,6 +214,7 @@ int pbsc_index_set_lanes(pbsc_index* idx, int lanes)
     idx->lane_busy.assign((size_t)lanes, 0);
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_set_lanes")
 
 int pbsc_index_lanes(const pbsc_index* idx) { return idx ? (int)idx->shadows.size() + 1 : 0; }
 
@@ -241,6 +243,7 @@ int pbsc_index_export_blob(const pbsc_index* idx, void* d_dst, uint64_t cap)
 }
 
 int pbsc_index_import_blob(const void* src, uint64_t bytes, int src_device, int device, pbsc_index** out)
+try
 {
     if (!src || !out || bytes < sizeof(FmgHeader)) { set_error("pbsc_index_import_blob: bad argument"); return PBSC_ERR_ARG; }
     *out = nullptr;
@@ -264,10 +267,12 @@ int pbsc_index_import_blob(const void* src, uint64_t bytes, int src_device, int 
     if (rc != PBSC_OK) cudaFree(blob);
     return rc;
 }
+PBSC_CATCH_ALL("pbsc_index_import_blob")
 
 // GPU `device` receives the tables of `src` (resident on another GPU of the box, or the same one) by peer copies: one
 // cudaMemcpyPeerAsync per table over NVLink, no host decode, no PCIe upload
 int pbsc_index_clone(const pbsc_index* src, int device, pbsc_index** out)
+try
 {
     if (!src || !out) { set_error("pbsc_index_clone: null argument"); return PBSC_ERR_ARG; }
     *out = nullptr;
@@ -300,9 +305,11 @@ int pbsc_index_clone(const pbsc_index* src, int device, pbsc_index** out)
     if (rc != PBSC_OK) cudaFree(blob);
     return rc;
 }
+PBSC_CATCH_ALL("pbsc_index_clone")
 
 // PREFIX.fmg: header + tables exactly as they sit in HBM
 int pbsc_index_save(const pbsc_index* idx, const char* path)
+try
 {
     if (!idx || !path) { set_error("pbsc_index_save: null argument"); return PBSC_ERR_ARG; }
     PBSC_CUDA(cudaSetDevice(idx->device));
@@ -339,8 +346,10 @@ int pbsc_index_save(const pbsc_index* idx, const char* path)
     if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); set_error("cannot write %s", path); return PBSC_ERR_IO; }
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_save")
 
 int pbsc_index_load_fmg(const char* path, int device, pbsc_index** out)
+try
 {
     if (!path || !out) { set_error("pbsc_index_load_fmg: null argument"); return PBSC_ERR_ARG; }
     *out = nullptr;
@@ -389,6 +398,7 @@ int pbsc_index_load_fmg(const char* path, int device, pbsc_index** out)
     if (rc != PBSC_OK) cudaFree(blob);
     return rc;
 }
+PBSC_CATCH_ALL("pbsc_index_load_fmg")
 
 static bool read_bwt_header(const std::string& path, uint64_t& n_strings, uint64_t& n_symbols, uint64_t& n_runs)
 {
@@ -403,6 +413,7 @@ static bool read_bwt_header(const std::string& path, uint64_t& n_strings, uint64
 // the run-length files, build the prefix table and, if write_fmg, leave PREFIX.fmg for the next run.
 // *from_fmg (optional) tells which way it went.
 int pbsc_index_open(const char* prefix, int device, int require_sai, int k0, int write_fmg, int* from_fmg, pbsc_index** out)
+try
 {
     if (!prefix || !out) { set_error("pbsc_index_open: null argument"); return PBSC_ERR_ARG; }
     *out = nullptr;
@@ -441,5 +452,6 @@ int pbsc_index_open(const char* prefix, int device, int require_sai, int k0, int
     if (write_fmg && pbsc_index_save(*out, fmg.c_str()) != PBSC_OK) fprintf(stderr, "[pbsc] warning: %s\n", pbsc_last_error());
     return PBSC_OK;
 }
+PBSC_CATCH_ALL("pbsc_index_open")
 
 }  // extern "C"

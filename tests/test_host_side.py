@@ -179,6 +179,53 @@ def test_onlyseed_barcode_check_matches_reference(tmp_path):
     assert open(tmp_path / "total.seed").read() == open(os.path.join(GOLDEN, "tiny.onlyseed.total.seed")).read()
 
 
+def test_kmercheck_summaries_match_reference(oracle_bin, tmp_path):
+    """`kmercheck` on the CPU: k-mer frequencies from the oracle's backward search (both strands of the reference-built tiny index),
+    barcode arithmetic and five-number summaries from csrc/pbsc_bcode.h; DIR/total.box and DIR/value.box equal what the unmodified
+    reference wrote (tests/golden/tiny.kmercheck.*, `stride kmercheck -c 30 -l 15 -u 23 -s 4`)."""
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "test_bcode.cpp"), "-o", exe, "-lz"], check=True)
+    reads = dict(read_fasta(os.path.join(GOLDEN, "tiny.reads.fa")))
+    comp = str.maketrans("ACGT", "TGCA")
+    recs, fwd_q, rvc_q = [], [], []
+    blocks_seen = {}
+    for line in open(os.path.join(GOLDEN, "tiny.barcode.txt")):
+        f = line.split()
+        if len(f) != 9:
+            continue
+        rid, a, b = f[0], int(f[1]), int(f[2])
+        bi = blocks_seen.get(rid, 0)
+        blocks_seen[rid] = bi + 1
+        seq = reads[rid]
+        for k in range(15, 24, 4):
+            for pos in range(a, b - k + 1):
+                w = seq[pos:pos + k]
+                recs.append((rid, bi, k, pos))
+                fwd_q.append(w[::-1])                      # findInterval(RBWT, reverse(w))
+                rvc_q.append(w[::-1].translate(comp))      # findInterval(BWT, reverse-complement(w))
+    def sizes(ext, qs):
+        qf = tmp_path / f"q.{ext}"
+        qf.write_text("\n".join(qs) + "\n")
+        out = subprocess.run([oracle_bin, "findinterval", os.path.join(GOLDEN, f"tiny.{ext}"), str(qf)], check=True, stdout=subprocess.PIPE, text=True).stdout
+        res = []
+        for l in out.splitlines():
+            t = l.split()
+            lo, hi = int(t[-2]), int(t[-1])
+            res.append(hi - lo + 1 if hi >= lo else 0)
+        return res
+    fs, rs = sizes("rbwt", fwd_q), sizes("bwt", rvc_q)
+    assert len(fs) == len(recs) == len(rs)
+    with open(tmp_path / "freqs.tsv", "w") as f:
+        for (rid, bi, k, pos), a, b in zip(recs, fs, rs):
+            assert a + b >= 1
+            f.write(f"{rid}\t{bi}\t{k}\t{pos}\t{a + b}\n")
+    r = subprocess.run([exe, "--kmercheck", os.path.join(GOLDEN, "tiny.reads.fa"), os.path.join(GOLDEN, "tiny.barcode.txt"), str(tmp_path / "freqs.tsv"), "30", "15", "23", "4",
+                        str(tmp_path / "total.box"), str(tmp_path / "value.box")])
+    assert r.returncode == 0
+    assert open(tmp_path / "total.box").read() == open(os.path.join(GOLDEN, "tiny.kmercheck.total.box")).read()
+    assert open(tmp_path / "value.box").read() == open(os.path.join(GOLDEN, "tiny.kmercheck.value.box")).read()
+
+
 def test_cli_option_errors():
     exe = os.path.join(ROOT, "longreadselfcorrect_b200", "pbcorrect")
     if not os.path.exists(exe):
