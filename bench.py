@@ -773,8 +773,8 @@ def sub_results(args, local_rank):
         except Exception as e:
             res[name] = {"error": str(e)[-200:]}
     try:
-        # index construction: both strands of config 2 by pbsc_build_bwt; the reference's `stride index` on a 2 Mbp sample
-        r = subprocess.run([py, os.path.join(ROOT, "tools", "index_bench.py"), "--json", "--workload", "cfg2", "--skip-torch", "--reference-mbp", "2"],
+        # index construction: both strands of config 2 by pbsc_build_bwt; the reference's `stride index` on a 1 Mbp sample
+        r = subprocess.run([py, os.path.join(ROOT, "tools", "index_bench.py"), "--json", "--workload", "cfg2", "--skip-torch", "--reference-mbp", "1"],
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
         res["index_build_cfg2"] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     except Exception as e:
@@ -802,7 +802,7 @@ def main():
     ap.add_argument("--no-oracle-count", action="store_true", help="skip the instrumented-oracle and issued-sector counts of the roofline (profiles/algorithmic.json is used)")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the config 2 / --nodp / FM microbench sub-results")
     ap.add_argument("--no-cli", dest="cli", action="store_false", help="skip the e2e_cli leg (the pbcorrect binary)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--batch-mbp", type=float, default=256.0, help="largest batch of reads of one lane (Mbp)")
     ap.add_argument("--nodp", action="store_true", help="disable the DP/MSA fallback on both arms (seeds + FM extension only)")
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="process-group backend for N > 1 (gloo: tests on a one-GPU box)")
