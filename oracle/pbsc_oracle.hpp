@@ -22,6 +22,7 @@
 #ifndef PBSC_ORACLE_HPP
 #define PBSC_ORACLE_HPP
 
+#include <atomic>
 #include <algorithm>
 #include <array>
 #include <cassert>
@@ -148,6 +149,15 @@ struct IndexSet { const FMIndex* pBWT = nullptr; const FMIndex* pRBWT = nullptr;
 
 // rank-query counter for the roofline numerator
 struct OccCounter { static uint64_t& n() { static thread_local uint64_t c = 0; return c; } };
+// PBSC_ORACLE_REFINE_STATS=1 (analysis aid): how many refineSAInterval re-searches there are, how many of them look
+// up a k-mer that occurs at least twice (both strands together), and how many steps they take; process-wide atomics
+struct RefineStats
+{
+    static bool on() { static const bool v = getenv("PBSC_ORACLE_REFINE_STATS") != nullptr; return v; }
+    static std::atomic<unsigned long long>& calls() { static std::atomic<unsigned long long> c{0}; return c; }
+    static std::atomic<unsigned long long>& twice() { static std::atomic<unsigned long long> c{0}; return c; }
+    static std::atomic<unsigned long long>& bases() { static std::atomic<unsigned long long> c{0}; return c; }
+};
 
 // BWTAlgorithms::updateInterval — SuffixTools/BWTAlgorithms.h:66-72
 inline void updateInterval(BWTInterval& iv, char b, const FMIndex* bwt, int* count = nullptr)
@@ -874,6 +884,13 @@ struct FMExtend
             std::string reducedKmer = leaf.getSuffix(newKmerSize);
             leaf.fwdInterval = findInterval(m_pRBWT, reverse(reducedKmer));
             leaf.rvcInterval = findInterval(m_pBWT, reverseComplement(reducedKmer));
+            if (RefineStats::on())
+            {
+                const int64_t f = leaf.fwdInterval.isValid() ? leaf.fwdInterval.upper - leaf.fwdInterval.lower + 1 : 0;
+                const int64_t r = leaf.rvcInterval.isValid() ? leaf.rvcInterval.upper - leaf.rvcInterval.lower + 1 : 0;
+                RefineStats::calls()++; RefineStats::bases() += newKmerSize;
+                if (f + r >= 2) RefineStats::twice()++;
+            }
         }
         m_currentKmerSize = newKmerSize;
     }

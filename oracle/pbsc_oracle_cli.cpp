@@ -244,6 +244,10 @@ int main(int argc, char** argv)
     }
     fprintf(stderr, "[pbsc_oracle] dp fallbacks %llu, rows kept %llu, band cells %llu, LF steps %llu\n", (unsigned long long)dpAttempts,
             (unsigned long long)dpRows, (unsigned long long)dpCells, (unsigned long long)occDP);
+    if (RefineStats::on())
+        fprintf(stderr, "[pbsc_oracle] refineSAInterval: %llu re-searches, mean %.2f bases, %llu (%.1f %%) of k-mers that occur at least twice\n",
+                (unsigned long long)RefineStats::calls(), RefineStats::calls() ? (double)RefineStats::bases() / (double)RefineStats::calls() : 0.0,
+                (unsigned long long)RefineStats::twice(), RefineStats::calls() ? 100.0 * (double)RefineStats::twice() / (double)RefineStats::calls() : 0.0);
     fprintf(stderr, "[pbsc_oracle] %zu reads, %.3f s, threads %d, rank queries %llu (seed %llu, extend %llu: setup %llu, walk loop %llu), walks %llu\n", reads.size(), secs,
             threads, (unsigned long long)occTotal, (unsigned long long)occSeed, (unsigned long long)occExtend, (unsigned long long)occSetup, (unsigned long long)occWalk,
             (unsigned long long)walkAttempts);
