@@ -1,12 +1,12 @@
-"""Synthetic-input helper: build the two BWTs `stride index` would produce (PREFIX.bwt = BWT of the
-reads, PREFIX.rbwt = BWT of the reversed reads; SuffixTools/BWTCARopebwt.cpp:160-247) for a simulated
-read set, fast enough for the 230 Mbp benchmark configuration.
+"""Test / measurement helper, NOT the product's index builder (that is csrc/pbsc_build.cu, `pbcorrect index`, `api.build_bwt`).
 
-This is data preparation for tests and bench.py, not the hot path: prefix-doubling suffix sorting with
-torch.sort on the GPU (or on the CPU for small inputs).  Each read gets its own sentinel, ordered by read
-index.  ropebwt2 orders equal suffixes differently, so the symbol sequences can differ inside blocks of
-identical suffixes, but every backward-search interval over ACGT patterns is identical (the tests check
-this against the reference's own index), and `stride pbcorrect` accepts the files.
+The two BWTs `stride index` produces (PREFIX.bwt = BWT of the reads, PREFIX.rbwt = BWT of the reversed reads;
+SuffixTools/BWTCARopebwt.cpp:160-247) by prefix-doubling suffix sorting with torch.sort, on the GPU or, for small inputs, on the
+CPU.  It is what the CPU tests use to make index files without a GPU, what the reference arm of bench.py uses to give the
+reference its index (none of the product's kernels on that arm), and an independent check of the product builder
+(`test_larger_input_equals_the_torch_builder`).  Each read gets its own sentinel, ordered by read index, which is the order
+ropebwt2 produces with MR_SO_IO: the .bwt / .rbwt bytes equal the reference's (checked on tests/golden/tiny.*).  `write_sai_file`
+writes a placeholder read order (identity); the real .sai / .rsai come from the product builder.
 """
 from __future__ import annotations
 
